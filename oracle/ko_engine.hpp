@@ -1,0 +1,194 @@
+// TEST INFRASTRUCTURE ONLY (see ko_base.hpp).  Restates the hot-path part of
+// minimizer_engine.f90: state singletons (:78-108), setters, calculate_seismograms /
+// scale_seismograms / calculate_misfits (:885-945), get_misfits (:1130-1172).
+//
+// Evaluation semantics: the reference never shrinks receiver%displacement strips
+// (seismogram.f90:102-106) nor probe spans (comparator.f90:245-249), so untapered and
+// amplitude-spectrum misfits depend on which sources were evaluated earlier.  A batched evaluator
+// cannot reproduce an evaluation order, so both the oracle and the CUDA path define FRESH-STATE
+// semantics: every candidate is evaluated as if it were the first one after set_ref_seismograms in
+// a new process.  `fresh=false` keeps the reference's history-dependent behaviour for study.
+#pragma once
+#include "ko_receiver.hpp"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace ko {
+
+struct Engine {
+    Psm psm;
+    float effective_dt = 1.f;          // minimizer_engine.f90:79
+    Tdsm tdsm;
+    std::vector<Receiver> receivers;
+    std::vector<std::vector<Probe>> ref_probes_initial;  // state right after set_ref_seismograms
+    Gfdb db;
+    int misfit_method = L2NORM;
+    float misfit = 0.f;
+    bool interpolate = false;
+    int xundersample = 1, zundersample = 1;
+    bool database_inited = false, receivers_inited = false, source_location_inited = false, source_inited = false,
+         ref_probes_inited = false;
+    bool fresh = true;
+    std::string errstr;
+    std::vector<Trace> scratch;  // per-thread bilinear scratch traces
+    std::vector<std::vector<IndexRecord>> index_records;  // filled when record_indices
+    bool record_indices = false;
+};
+
+// minimizer_engine.f90:165-286; coordinates in degrees as in the receivers file
+static inline bool set_receivers(Engine& e, int n, const double* lat_deg, const double* lon_deg, const float* depth,
+                                 const char* const* comps) {
+    if (!e.database_inited) { e.errstr = "no database set"; return false; }
+    e.receivers.assign(n, Receiver());
+    for (int i = 0; i < n; i++) {
+        GeoCoords o; o.lat = lat_deg[i]; o.lon = lon_deg[i];
+        if (!receiver_init(e.receivers[i], d2r_tgc(o), depth[i], comps[i], e.db.dt)) {
+            e.errstr = "initializing receiver failed";
+            e.receivers.clear(); e.receivers_inited = false; return false;
+        }
+    }
+    e.receivers_inited = true; e.ref_probes_inited = false;
+    return true;
+}
+// minimizer.f90:485-519 + minimizer_engine.f90:453-467: degrees are converted in default real
+static inline void set_source_location(Engine& e, float lat_deg, float lon_deg, double ref_time) {
+    e.psm.origin.lat = (double)d2r_r(lat_deg);
+    e.psm.origin.lon = (double)d2r_r(lon_deg);
+    e.psm.ref_time = ref_time;
+    e.source_location_inited = true;
+}
+// receiver.f90:746-801 with the file reading stripped: data starts at time `tbegin` rel. to ref time
+static inline bool set_ref_seismogram(Engine& e, int irec, int icomp, const float* data, int n, float tbegin) {
+    if (irec < 1 || irec > (int)e.receivers.size()) { e.errstr = "receiver index out of range"; return false; }
+    Receiver& r = e.receivers[irec - 1];
+    if (icomp < 1 || icomp > r.ncomponents) { e.errstr = "component index out of range"; return false; }
+    Strip strip;
+    seismogram_to_strip(data, n, tbegin, r.dt, strip);
+    probe_set_array(r.ref_probes[icomp - 1], strip);
+    return true;
+}
+static inline void finish_ref_seismograms(Engine& e) {
+    e.ref_probes_initial.clear();
+    for (auto& r : e.receivers) e.ref_probes_initial.push_back(r.ref_probes);
+    e.ref_probes_inited = true;
+}
+static inline void sync_initial_probe_settings(Engine& e) {
+    if (!e.ref_probes_inited) return;
+    for (size_t i = 0; i < e.receivers.size(); i++)
+        for (int c = 0; c < e.receivers[i].ncomponents; c++) {
+            Probe& p = e.ref_probes_initial[i][c];
+            p.taper = e.receivers[i].ref_probes[c].taper;
+            p.filter = e.receivers[i].ref_probes[c].filter;
+            dirtyfy_array_tapered(p);
+        }
+}
+// minimizer_engine.f90:668-698: ireceiver 1..n only
+static inline bool set_misfit_taper(Engine& e, int irec, const float* x, const float* y, int n) {
+    if (!e.receivers_inited) { e.errstr = "no receivers set"; return false; }
+    if (irec < 1 || irec > (int)e.receivers.size()) { e.errstr = "receiver index out of range"; return false; }
+    Plf t; plf_make(t, std::vector<float>(x, x + n), std::vector<float>(y, y + n));
+    receiver_set_taper(e.receivers[irec - 1], t);
+    sync_initial_probe_settings(e);
+    return true;
+}
+// minimizer_engine.f90:632-666: ireceiver 0 = all receivers
+static inline bool set_misfit_filter(Engine& e, int irec, const float* x, const float* y, int n) {
+    if (!e.receivers_inited) { e.errstr = "no receivers set"; return false; }
+    if (irec < 0 || irec > (int)e.receivers.size()) { e.errstr = "receiver index out of range"; return false; }
+    Plf f; plf_make(f, std::vector<float>(x, x + n), std::vector<float>(y, y + n));
+    if (irec == 0) { for (auto& r : e.receivers) receiver_set_filter(r, f); }
+    else receiver_set_filter(e.receivers[irec - 1], f);
+    sync_initial_probe_settings(e);
+    return true;
+}
+static inline void set_synthetics_factor(Engine& e, float f) { for (auto& r : e.receivers) receiver_set_synthetics_factor(r, f); }
+
+// minimizer_engine.f90:500-523 (change detection is a speed-up only; always re-evaluated here)
+static inline bool set_source_params(Engine& e, int sourcetype, const float* params, int nparams) {
+    if (!e.source_location_inited) { e.errstr = "no source location set"; return false; }
+    bool omc;
+    if (!psm_set(e.psm, sourcetype, params, nparams, omc)) { e.errstr = "unknown source type or wrong number of parameters"; return false; }
+    e.source_inited = true;
+    return true;
+}
+
+static inline void reset_to_fresh_state(Engine& e) {
+    for (size_t i = 0; i < e.receivers.size(); i++) {
+        Receiver& r = e.receivers[i];
+        for (int c = 0; c < r.ncomponents; c++) {
+            r.displacement[c] = Strip();
+            Probe np; probe_init(np, r.dt);
+            np.taper = r.syn_probes[c].taper; np.filter = r.syn_probes[c].filter; np.factor = r.syn_probes[c].factor;
+            r.syn_probes[c] = np;
+            if (e.ref_probes_inited) r.ref_probes[c] = e.ref_probes_initial[i][c];
+        }
+    }
+}
+
+// minimizer_engine.f90:876-907 discretize_source + calculate_seismograms
+static inline bool calculate_seismograms(Engine& e) {
+    if (!e.database_inited) { e.errstr = "no database set"; return false; }
+    if (!e.receivers_inited) { e.errstr = "no receivers set"; return false; }
+    if (!e.source_location_inited) { e.errstr = "no source location set"; return false; }
+    if (!e.source_inited) { e.errstr = "no source parameters set"; return false; }
+    if (e.fresh) reset_to_fresh_state(e);
+    bool ok;
+    psm_to_tdsm(e.psm, e.tdsm, e.effective_dt, ok);
+    if (!ok) return false;
+    int nthreads = 1;
+#ifdef _OPENMP
+    nthreads = omp_get_max_threads();
+#endif
+    if ((int)e.scratch.size() < nthreads) e.scratch.resize(nthreads);
+    int nr = (int)e.receivers.size();
+    if (e.record_indices) e.index_records.assign(nr, {});
+#pragma omp parallel for schedule(dynamic)
+    for (int ir = 0; ir < nr; ir++) {
+        int tid = 0;
+#ifdef _OPENMP
+        tid = omp_get_thread_num();
+#endif
+        if (e.receivers[ir].enabled)
+            make_seismogram(e.tdsm, e.receivers[ir], e.db, e.interpolate, e.xundersample, e.zundersample, e.scratch[tid],
+                            e.record_indices ? &e.index_records[ir] : nullptr);
+    }
+    return true;
+}
+// minimizer_engine.f90:909-921
+static inline void scale_seismograms(Engine& e) {
+    for (auto& r : e.receivers) receiver_scaled_seismograms_to_probes(r, e.psm.risetime, e.psm.moment);
+}
+// minimizer_engine.f90:924-945
+static inline bool calculate_misfits(Engine& e) {
+    if (!e.ref_probes_inited) { e.errstr = "no reference seismograms set"; return false; }
+    float misfit = 0.f, nf = 0.f;
+    for (auto& r : e.receivers) {
+        receiver_calculate_misfits(r, e.misfit_method);
+        float s = 0.f; for (float m : r.misfits) s = s + m * m;
+        misfit = misfit + s;
+        s = 0.f; for (float m : r.misfits_norm_factors) s = s + m * m;
+        nf = nf + s;
+    }
+    e.misfit = sqrtf(misfit) / sqrtf(nf);
+    return true;
+}
+// one full evaluation: set_source_params + get_misfits; out = (misfit, norm_factor) pairs of the
+// enabled receivers, receiver-major (minimizer_engine.f90:1130-1172).  Returns nmisfits or -1.
+static inline int evaluate(Engine& e, int sourcetype, const float* params, int nparams, float* out, int cap) {
+    if (!set_source_params(e, sourcetype, params, nparams)) return -1;
+    if (!calculate_seismograms(e)) return -1;
+    scale_seismograms(e);
+    if (!calculate_misfits(e)) return -1;
+    int n = 0;
+    for (auto& r : e.receivers) {
+        if (!r.enabled) continue;
+        for (int c = 0; c < r.ncomponents; c++) {
+            if (out && n < cap) { out[2 * n] = r.misfits[c]; out[2 * n + 1] = r.misfits_norm_factors[c]; }
+            n++;
+        }
+    }
+    return n;
+}
+
+}  // namespace ko

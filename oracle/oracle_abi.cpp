@@ -1,0 +1,177 @@
+// TEST INFRASTRUCTURE ONLY (see ko_base.hpp).  C ABI around the oracle so that tests/ (ctypes),
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs can drive it.
+// The entry points deliberately mirror include/kiwi_b200.h one to one.
+#include "ko_engine.hpp"
+#include <chrono>
+
+using namespace ko;
+
+extern "C" {
+
+void* oracle_create() { return new Engine(); }
+void oracle_destroy(void* h) { delete (Engine*)h; }
+const char* oracle_last_error(void* h) { return ((Engine*)h)->errstr.c_str(); }
+void oracle_set_fresh(void* h, int fresh) { ((Engine*)h)->fresh = fresh != 0; }
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+int oracle_max_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+// flat array form of a GFDB, see include/kiwi_b200.h kiwi_gfdb_view()
+int oracle_set_database(void* h, int nx, int nz, int ng, float dt, float dx, float dz, float firstx, float firstz,
+                        const int* span0, const int* len, const long long* offset, const float* data) {
+    Engine& e = *(Engine*)h;
+    gfdb_from_arrays(e.db, nx, nz, ng, dt, dx, dz, firstx, firstz, span0, len, offset, data);
+    e.database_inited = true;
+    return 0;
+}
+int oracle_set_local_interpolation(void* h, int bilinear) { ((Engine*)h)->interpolate = bilinear != 0; return 0; }
+int oracle_set_spacial_undersampling(void* h, int xu, int zu) {
+    Engine& e = *(Engine*)h;
+    if (xu < 1 || zu < 1) { e.errstr = "invalid undersampling value"; return 1; }
+    e.xundersample = xu; e.zundersample = zu; return 0;
+}
+int oracle_set_receivers(void* h, int n, const double* lat_deg, const double* lon_deg, const float* depth,
+                         const char* const* comps) {
+    return set_receivers(*(Engine*)h, n, lat_deg, lon_deg, depth, comps) ? 0 : 1;
+}
+int oracle_switch_receiver(void* h, int irec, int state) {
+    Engine& e = *(Engine*)h;
+    if (irec < 1 || irec > (int)e.receivers.size()) { e.errstr = "receiver index out of range"; return 1; }
+    receiver_set_enabled(e.receivers[irec - 1], state != 0); return 0;
+}
+int oracle_set_source_location(void* h, float lat_deg, float lon_deg, double ref_time) {
+    set_source_location(*(Engine*)h, lat_deg, lon_deg, ref_time); return 0;
+}
+int oracle_set_effective_dt(void* h, float dt) { ((Engine*)h)->effective_dt = dt; return 0; }
+int oracle_set_ref_seismogram(void* h, int irec, int icomp, float tbegin, int n, const float* data) {
+    Engine& e = *(Engine*)h;
+    if (!set_ref_seismogram(e, irec, icomp, data, n, tbegin)) return 1;
+    finish_ref_seismograms(e);
+    return 0;
+}
+int oracle_set_misfit_method(void* h, int id) { ((Engine*)h)->misfit_method = id; return 0; }
+int oracle_set_misfit_taper(void* h, int irec, int n, const float* x, const float* y) { return set_misfit_taper(*(Engine*)h, irec, x, y, n) ? 0 : 1; }
+int oracle_set_misfit_filter(void* h, int irec, int n, const float* x, const float* y) { return set_misfit_filter(*(Engine*)h, irec, x, y, n) ? 0 : 1; }
+int oracle_set_synthetics_factor(void* h, float f) { set_synthetics_factor(*(Engine*)h, f); return 0; }
+int oracle_set_floating_shiftrange(void* h, int irec, float lo, float hi) {  // minimizer_engine.f90:418-451
+    Engine& e = *(Engine*)h;
+    int r[2] = {f_nint(lo / e.db.dt), f_nint(hi / e.db.dt)};
+    if (irec == 0) { for (auto& rc : e.receivers) { rc.floating_shiftrange[0] = r[0]; rc.floating_shiftrange[1] = r[1]; } }
+    else if (irec < 1 || irec > (int)e.receivers.size()) { e.errstr = "receiver index out of range"; return 1; }
+    else { e.receivers[irec - 1].floating_shiftrange[0] = r[0]; e.receivers[irec - 1].floating_shiftrange[1] = r[1]; }
+    return 0;
+}
+int oracle_get_nmisfits(void* h) {
+    Engine& e = *(Engine*)h; int n = 0;
+    for (auto& r : e.receivers) if (r.enabled) n += r.ncomponents;
+    return n;
+}
+// batched in form, sequential in execution (this IS the reference's loop, seismosizer.py:703-716)
+int oracle_eval_sources(void* h, int sourcetype, int ns, int nparams, const float* params, float* misfits, int* status) {
+    Engine& e = *(Engine*)h;
+    int nm = oracle_get_nmisfits(h);
+    for (int s = 0; s < ns; s++) {
+        int n = evaluate(e, sourcetype, params + (size_t)s * nparams, nparams, misfits ? misfits + (size_t)s * nm * 2 : nullptr, nm);
+        if (status) status[s] = (n == nm) ? 0 : 1;
+        if (n < 0 && !status) return 1;
+    }
+    return 0;
+}
+float oracle_get_global_misfit(void* h) { return ((Engine*)h)->misfit; }
+int oracle_get_floating_shifts(void* h, int* shifts) {
+    Engine& e = *(Engine*)h; int n = 0;
+    for (auto& r : e.receivers) if (r.enabled) shifts[n++] = r.floating_shift;
+    return n;
+}
+// synthetic displacement of the last evaluated source (receiver%displacement, before scaling)
+// which: 0 = displacement strip, 1 = syn probe array over dataspan (scaled by moment)
+int oracle_get_seismogram(void* h, int irec, int icomp, int which, int* first_index, int* n, float* buf, int cap) {
+    Engine& e = *(Engine*)h;
+    if (irec < 1 || irec > (int)e.receivers.size()) return 1;
+    Receiver& r = e.receivers[irec - 1];
+    if (icomp < 1 || icomp > r.ncomponents) return 1;
+    if (which == 0) {
+        const Strip& s = r.displacement[icomp - 1];
+        *first_index = s.lo; *n = strip_length(s);
+        for (int i = 0; i < std::min(*n, cap); i++) buf[i] = s.d[i];
+    } else {
+        const Probe& p = r.syn_probes[icomp - 1];
+        *first_index = p.dataspan[0]; *n = slen(p.dataspan);
+        for (int i = 0; i < std::min(*n, cap); i++) buf[i] = p.array.at(p.dataspan[0] + i);
+    }
+    return 0;
+}
+int oracle_get_probe_spans(void* h, int irec, int icomp, int* out8) {
+    Engine& e = *(Engine*)h;
+    Receiver& r = e.receivers[irec - 1];
+    const Probe& a = r.ref_probes[icomp - 1]; const Probe& b = r.syn_probes[icomp - 1];
+    out8[0] = a.span[0]; out8[1] = a.span[1]; out8[2] = a.dataspan[0]; out8[3] = a.dataspan[1];
+    out8[4] = b.span[0]; out8[5] = b.span[1]; out8[6] = b.dataspan[0]; out8[7] = b.dataspan[1];
+    return 0;
+}
+// discretisation only: centroid table in the reference's AoS order (10 floats per centroid:
+// north east depth time mxx myy mzz mxy mxz myz).  Returns ncentroids (or -1); grid = nx,ny,nt.
+int oracle_discretize_source(void* h, int sourcetype, int nparams, const float* params, float* table, int cap, int* grid3) {
+    Engine& e = *(Engine*)h;
+    if (!set_source_params(e, sourcetype, params, nparams)) return -1;
+    bool ok; psm_to_tdsm(e.psm, e.tdsm, e.effective_dt, ok);
+    if (!ok) return -1;
+    int n = (int)e.tdsm.centroids.size();
+    for (int i = 0; i < std::min(n, cap); i++) {
+        const Centroid& c = e.tdsm.centroids[i];
+        float* t = table + (size_t)i * 10;
+        t[0] = c.north; t[1] = c.east; t[2] = c.depth; t[3] = c.time;
+        for (int k = 0; k < 6; k++) t[4 + k] = c.m[k];
+    }
+    if (grid3) for (size_t i = 0; i < 3; i++) grid3[i] = i < e.psm.grid_size.size() ? e.psm.grid_size[i] : 1;
+    return n;
+}
+// per-centroid integer arrays of the last evaluation for receiver irec (needs record on)
+void oracle_record_indices(void* h, int on) { ((Engine*)h)->record_indices = on != 0; }
+int oracle_get_indices(void* h, int irec, int* ix, int* iz, int* its, float* dix, float* diz, double* dist, double* azi, double* bazi, int cap) {
+    Engine& e = *(Engine*)h;
+    if (irec < 1 || irec > (int)e.index_records.size()) return -1;
+    auto& v = e.index_records[irec - 1];
+    int n = (int)v.size();
+    for (int i = 0; i < std::min(n, cap); i++) {
+        ix[i] = v[i].ix0; iz[i] = v[i].iz0; its[i] = v[i].its; dix[i] = v[i].dix; diz[i] = v[i].diz;
+        if (dist) dist[i] = v[i].dist; if (azi) azi[i] = v[i].azi; if (bazi) bazi[i] = v[i].bazi;
+    }
+    return n;
+}
+// per-receiver base geometry (seismogram.f90:99-100)
+int oracle_receiver_geometry(void* h, int irec, double* azi, double* bazi, double* dist) {
+    Engine& e = *(Engine*)h;
+    Receiver& r = e.receivers[irec - 1];
+    azibazi(e.psm.origin, r.origin, *azi, *bazi);
+    *dist = distance_accurate50m(e.psm.origin, r.origin);
+    return 0;
+}
+// stored span of one GF trace after trace_pack (for span parity of the slab packer)
+int oracle_trace_span(void* h, int ix, int iz, int ig, int* span2, int* nstrips) {
+    Engine& e = *(Engine*)h;
+    Trace* t = gfdb_get_trace(e.db, ix, iz, ig);
+    if (!t) return 1;
+    span2[0] = t->span[0]; span2[1] = t->span[1]; *nstrips = t->nstrips;
+    return 0;
+}
+// time `ns` evaluations; returns seconds of wall time
+double oracle_time_eval(void* h, int sourcetype, int ns, int nparams, const float* params) {
+    auto t0 = std::chrono::steady_clock::now();
+    oracle_eval_sources(h, sourcetype, ns, nparams, params, nullptr, nullptr);
+    auto t1 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+}  // extern "C"
