@@ -1,0 +1,195 @@
+/* kiwi_b200.h -- C ABI of the B200-native forward-modelling + misfit engine for Kiwi's
+ * source-inversion inner loop.
+ *
+ * The reference (emolch/kiwi, Fortran 90) has no plugin/FFI interface.  Its de-facto boundary is
+ * the module API of minimizer_engine.f90 (38 public subroutines `(args..., ok)` + global error
+ * string, minimizer_engine.f90:39-76, util.f90:106-116), driven by the text protocol of the
+ * `minimizer` program (minimizer.f90:1676-1813).  Every entry point below replaces one of those
+ * subroutines (cited as file:line of /root/reference) for the hot path
+ *     set_source_params -> discretise -> make_seismogram (all receivers) -> scale -> misfits.
+ * A Fortran host binds them with iso_c_binding (fortran/kiwi_b200_binding.f90).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; the message (same wording as the
+ *     reference's error() calls where one exists) is available from kiwi_last_error();
+ *   - plain pointers and sizes only; caller-provided output buffers with an explicit capacity;
+ *   - receiver / component / GF indices are 1-based as in the reference;
+ *   - one context = the module-level singletons of minimizer_engine.f90:78-108; calls on one
+ *     context must be serialised by the caller (the reference is single-threaded at this level);
+ *   - there is NO CPU fallback: any call that computes needs a CUDA device and fails loudly
+ *     without one.
+ */
+#ifndef KIWI_B200_H
+#define KIWI_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kiwi_ctx kiwi_ctx;
+typedef struct kiwi_gfdb kiwi_gfdb;
+
+/* source type ids (parameterized_source.f90 / source_all.f90:58-60) */
+#define KIWI_SOURCE_BILATERAL 1      /* source_bilat.f90, 14 parameters          */
+#define KIWI_SOURCE_CIRCULAR 2       /* not built (out of scope) */
+#define KIWI_SOURCE_POINT_LP 3       /* not built                                 */
+#define KIWI_SOURCE_EIKONAL 4        /* source_eikonal.f90, 15 parameters (next)  */
+#define KIWI_SOURCE_MT_EIKONAL 5     /* source_mt_eikonal.f90 (next)              */
+#define KIWI_SOURCE_MOMENT_TENSOR 6  /* source_moment_tensor.f90, 11 parameters   */
+
+/* misfit norm ids (comparator.f90:33-42) */
+#define KIWI_L2NORM 1
+#define KIWI_L1NORM 2
+#define KIWI_AMPSPEC_L2NORM 3
+#define KIWI_AMPSPEC_L1NORM 4
+#define KIWI_SCALAR_PRODUCT 5
+#define KIWI_PEAK 6
+#define KIWI_FLOATING_L2NORM 7
+#define KIWI_FLOATING_L1NORM 8
+
+/* per-candidate status of kiwi_eval_sources (the reference reports per-source failures through
+ * `ok=.false.` + g_errstr and the Python driver collects them as `failings`,
+ * python/tunguska/seismosizer.py:703-716) */
+#define KIWI_STATUS_OK 0
+#define KIWI_STATUS_BAD_PARAMS 1     /* discretisation failed                        */
+#define KIWI_STATUS_NONFINITE 2      /* NaN/Inf misfit (minimizer_engine.f90:1163-1166) */
+
+/* util.f90:106-116 error()/g_errstr.  Thread-local, valid until the next failing call. */
+const char* kiwi_last_error(void);
+/* library version string */
+const char* kiwi_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Green's function database, host side.  Replaces the storage half of gfdb.f90 (t_gfdb :93-146,
+ * gfdb_init :163-264, gfdb_save_trace) and gfdb_io_hdf.f90 (HDF5 is not available): a flat
+ * container with, for every (ix,iz,ig), one dense fp32 sample array that starts at sample index
+ * span0.  Packing follows trace_pack (sparse_trace.f90:443-555): leading zeros are dropped, of the
+ * trailing zeros exactly one is kept, inter-strip gaps are stored as explicit zeros.
+ * --------------------------------------------------------------------------------------------- */
+/* gfdb_build (gfdb_build.f90) / gfdb_init: create an empty database grid */
+kiwi_gfdb* kiwi_gfdb_create(int nx, int nz, int ng, float dt, float dx, float dz, float firstx, float firstz);
+void kiwi_gfdb_destroy(kiwi_gfdb* db);
+/* gfdb_build_ahfull.f90:193-216 gfdb_save_array: store samples data[0..n) of GF (ix,iz,ig), first
+ * sample at index span0 = nint(tbegin/dt) */
+int kiwi_gfdb_save_array(kiwi_gfdb* db, int ix, int iz, int ig, int span0, int n, const float* data);
+/* gfdb_build_ahfull.f90:70-191 addentry for EVERY grid node: analytical homogeneous full space
+ * (elseis.f90), material rho/alpha/beta, source time function stf[nstf] sampled at dt.
+ * nthreads <= 0: all host cores. */
+int kiwi_gfdb_build_ahfull(kiwi_gfdb* db, float rho, float alpha, float beta, const float* stf, int nstf,
+                           int nfflag, int ffflag, int nthreads);
+/* flat binary file "KGF1" (this repo's own format) */
+int kiwi_gfdb_write(const kiwi_gfdb* db, const char* path);
+kiwi_gfdb* kiwi_gfdb_read(const char* path);
+/* gfdb_info: grid metadata */
+int kiwi_gfdb_meta(const kiwi_gfdb* db, int* nx, int* nz, int* ng, float* dt, float* dx, float* dz, float* firstx,
+                   float* firstz, long long* ntraces, long long* nsamples);
+/* borrowed pointers to the flat arrays, index = ((ix-1)*nz + (iz-1))*ng + (ig-1); len==0: no trace */
+int kiwi_gfdb_view(kiwi_gfdb* db, const int** span0, const int** len, const long long** offset, const float** data);
+
+/* ---------------------------------------------------------------------------------------------
+ * Engine context = module state of minimizer_engine.f90:78-108, resident on one GPU
+ * --------------------------------------------------------------------------------------------- */
+kiwi_ctx* kiwi_create(int device);
+void kiwi_destroy(kiwi_ctx* ctx);
+
+/* set_database (minimizer_engine.f90:114-139): packs the database into 16-byte aligned slabs and
+ * uploads it to HBM once.  nipx/nipz (Gulunay interpolation) are not supported (out of scope). */
+int kiwi_set_database(kiwi_ctx* ctx, kiwi_gfdb* db);
+/* set_local_interpolation (minimizer_engine.f90:140-145): 0 nearest neighbour, 1 bilinear */
+int kiwi_set_local_interpolation(kiwi_ctx* ctx, int bilinear);
+/* set_spacial_undersampling (minimizer_engine.f90:147-163) */
+int kiwi_set_spacial_undersampling(kiwi_ctx* ctx, int xunder, int zunder);
+/* set_receivers (minimizer_engine.f90:165-286) with the file parsing stripped: coordinates in
+ * DEGREES as in the receivers file, components = string of distinct letters from "acrlduneswe"
+ * (receiver.f90:136-209) */
+int kiwi_set_receivers(kiwi_ctx* ctx, int n, const double* lat_deg, const double* lon_deg, const float* depth,
+                       const char* const* components);
+/* switch_receiver (minimizer_engine.f90:288-311) */
+int kiwi_switch_receiver(kiwi_ctx* ctx, int ireceiver, int state);
+/* set_source_location (minimizer.f90:485-519 + minimizer_engine.f90:453-467): degrees, seconds */
+int kiwi_set_source_location(kiwi_ctx* ctx, float lat_deg, float lon_deg, double ref_time);
+/* set_effective_dt (minimizer_engine.f90:610-618) */
+int kiwi_set_effective_dt(kiwi_ctx* ctx, float effective_dt);
+/* set_ref_seismograms (minimizer_engine.f90:313-352, receiver.f90:746-851) with the file reading
+ * stripped: n samples of component icomponent at receiver ireceiver, first sample at time tbegin
+ * [s] relative to the source reference time */
+int kiwi_set_ref_seismogram(kiwi_ctx* ctx, int ireceiver, int icomponent, float tbegin, int n, const float* data);
+/* set_misfit_method (minimizer_engine.f90:620-628) */
+int kiwi_set_misfit_method(kiwi_ctx* ctx, int norm_id);
+/* set_misfit_taper (minimizer_engine.f90:668-698): ireceiver in 1..n */
+int kiwi_set_misfit_taper(kiwi_ctx* ctx, int ireceiver, int n, const float* x, const float* y);
+/* set_misfit_filter (minimizer_engine.f90:632-666): ireceiver 0 = all receivers */
+int kiwi_set_misfit_filter(kiwi_ctx* ctx, int ireceiver, int n, const float* x, const float* y);
+/* set_synthetics_factor (minimizer_engine.f90:700-711) */
+int kiwi_set_synthetics_factor(kiwi_ctx* ctx, float factor);
+/* set_floating_shiftrange (minimizer_engine.f90:418-451): seconds; ireceiver 0 = all */
+int kiwi_set_floating_shiftrange(kiwi_ctx* ctx, int ireceiver, float shift_lo, float shift_hi);
+
+/* number of (misfit, norm-factor) pairs get_misfits returns: components of enabled receivers
+ * (minimizer_engine.f90:1141-1148) */
+int kiwi_get_nmisfits(kiwi_ctx* ctx);
+/* number of parameters of a source type (source_all.f90:97-121), 0 if unknown */
+int kiwi_get_n_source_params(int sourcetype);
+
+/* THE batched hot path.  For each of the ns candidates: set_source_params + get_misfits
+ * (minimizer_engine.f90:500-523, 876-945, 1130-1172), every candidate evaluated with fresh-state
+ * semantics.  params: [ns][nparams] host floats.  misfits: [ns][nmisfits][2] host
+ * floats, (misfit, norm factor) interleaved, receiver-major, enabled receivers only.
+ * status: [ns] (may be NULL).  This replaces the candidate loop of
+ * python/tunguska/seismosizer.py:682-722 (make_misfits_for_sources). */
+int kiwi_eval_sources(kiwi_ctx* ctx, int sourcetype, int ns, int nparams, const float* params, float* misfits,
+                      int* status);
+/* same, results left in DEVICE memory (d_misfits: [ns][nmisfits][2] floats on the context's GPU,
+ * e.g. an NCCL send buffer); returns after the work is enqueued and finished on the stream */
+int kiwi_eval_sources_device(kiwi_ctx* ctx, int sourcetype, int ns, int nparams, const float* params,
+                             float* d_misfits, int* status);
+/* global misfit per candidate, sqrt(sum m^2)/sqrt(sum n^2) (minimizer_engine.f90:939-942), from a
+ * host misfit block as returned by kiwi_eval_sources */
+int kiwi_global_misfits(int ns, int nmisfits, const float* misfits, float* global_misfits);
+
+/* ns = 1 convenience pair with the reference's names and change detection
+ * (minimizer_engine.f90:500-523: identical parameters are a no-op) */
+int kiwi_set_source_params(kiwi_ctx* ctx, int sourcetype, int nparams, const float* params);
+int kiwi_get_misfits(kiwi_ctx* ctx, float* misfits, int cap_pairs, int* nmisfits);   /* minimizer_engine.f90:1130-1172 */
+int kiwi_get_global_misfit(kiwi_ctx* ctx, float* misfit);                            /* minimizer_engine.f90:1083-1093 */
+int kiwi_get_floating_shifts(kiwi_ctx* ctx, int* shifts, int cap, int* n);           /* minimizer_engine.f90:1095-1128, in samples */
+/* In-memory replacement for output_seismograms (minimizer_engine.f90:947-1012; the reference only
+ * writes files): synthetic trace of the source set by kiwi_set_source_params.
+ * which: 0 = raw displacement (receiver%displacement), 1 = scaled (moment, rise time) as put into
+ * the syn probe.  first_index: sample index of buf[0] (sample i <-> time (i-1)*dt, receiver.f90:649) */
+int kiwi_get_seismogram(kiwi_ctx* ctx, int ireceiver, int icomponent, int which, int* first_index, int* n,
+                        float* buf, int cap);
+
+/* ---- inspection entry points used by the parity tests (bit-exact integer contract) ---------- */
+/* discretise one source on the device; table: [cap][10] floats north east depth time m(6) in the
+ * reference's centroid order (discrete_source.f90:27-30); grid3: nx,ny,nt.  Returns through
+ * *ncentroids. */
+int kiwi_discretize_source(kiwi_ctx* ctx, int sourcetype, int nparams, const float* params, float* table, int cap,
+                           int* ncentroids, int* grid3);
+/* per-centroid GF indices and sample shifts for receiver ireceiver of the source set by
+ * kiwi_set_source_params (gfdb_get_indices[_bilin] gfdb.f90:781-815; floor(time/dt)
+ * sparse_trace.f90:640).  near_boundary[i] != 0 flags centroids whose scaled grid coordinate lies
+ * within 4 fp32 ulps of an integer (device libm vs glibc may then legitimately differ). */
+int kiwi_get_indices(kiwi_ctx* ctx, int ireceiver, int* ix, int* iz, int* its, float* dix, float* diz,
+                     int* near_boundary, int cap, int* n);
+/* output spans [first,last] of the three internal strips (displacement_ar(1), displacement_ar(2),
+ * vertical) for receiver ireceiver (seismogram.f90:131-289) */
+int kiwi_get_spans(kiwi_ctx* ctx, int ireceiver, int* spans6);
+/* stored span of one GF trace in the HBM slab layout */
+int kiwi_trace_span(kiwi_ctx* ctx, int ix, int iz, int ig, int* span2);
+
+/* ---- measurement support -------------------------------------------------------------------- */
+/* algorithmic / logical GF bytes of the last kiwi_eval_sources batch:
+ * b_alg = distinct nodes per (candidate, receiver) x components used x trace length x 4 B
+ *         + one write of each synthetic + one read of each reference;
+ * b_log = every (group, corner, component) trace counted once per use. */
+int kiwi_last_batch_bytes(kiwi_ctx* ctx, double* b_alg, double* b_log);
+/* device time [ms] of the stages of the last kiwi_eval_sources call, measured with CUDA events on
+ * the engine's stream: [0] discretise, [1] geometry/index pre-pass, [2] synthesis, [3] misfit,
+ * [4] whole call incl. H2D/D2H; launches[0..3]: kernel launches per stage */
+int kiwi_last_timing(kiwi_ctx* ctx, float* ms5, int* launches4);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KIWI_B200_H */

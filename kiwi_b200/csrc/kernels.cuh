@@ -1,0 +1,29 @@
+// Launch wrappers of kernels.cu (host-callable) and the host->device parameter blocks.
+#pragma once
+#include "kiwi_dev.cuh"
+
+// per-candidate parameter block of the bilateral discretiser; the host evaluates everything that
+// needs libm (d2r, init_euler euler.f90:28-67) or is sequential and tiny (STF taps
+// source_bilat.f90:379-411, m_rot :426-428), the device lays out the sub-fault grid
+struct BilatCand {
+    float time, north, east, depth;
+    float length_a, length_b, width, rupvel;
+    float rot_rup[9];   // row-major rotmat_rup
+    float mhat[6];      // m_rot/np: (1,1) (2,2) (3,3) (1,2) (1,3) (2,3)
+    int nx, ny, nt;
+    int group_begin, tap_begin;
+};
+
+void launch_bilat_groups(const BilatCand* d_cands, int ncand, GroupSoA g, TapSoA taps, float dt, int ngroups_total, cudaStream_t st);
+void launch_group_tap_range(GroupSoA g, TapSoA taps, float dt, int gbegin, int gend, cudaStream_t st);
+void launch_expand_centroids(CandDev cand, GroupSoA g, TapSoA taps, int ngroups_total, float* d_table, int cap, cudaStream_t st);
+void launch_geometry(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, int interpolate,
+                     int xunder, int zunder, GeoRec* recs, size_t rec_stride, PairHdr* hdrs, int* tmax, cudaStream_t st);
+size_t synth_smem_bytes(int nwarps, int nq);
+cudaError_t launch_synth(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, TapSoA taps,
+                         int ngroups_total, int interpolate, int xunder, int zunder, const GeoRec* recs, size_t rec_stride,
+                         const PairHdr* hdrs, int nq_alloc, int nwarps, float* seis, size_t seis_stride, SeisHdr* shdrs,
+                         cudaStream_t st);
+void launch_misfit_td(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, const float* seis, size_t seis_stride,
+                      const SeisHdr* shdrs, const float* refdata, const float* taperdata, int method, float dt, float syn_factor,
+                      int nmisfits, float* out, int* status, cudaStream_t st);
