@@ -179,11 +179,12 @@ int kiwi_get_spans(kiwi_ctx* ctx, int ireceiver, int* spans6);
 int kiwi_trace_span(kiwi_ctx* ctx, int ix, int iz, int ig, int* span2);
 
 /* ---- measurement support -------------------------------------------------------------------- */
-/* algorithmic / logical GF bytes of the last kiwi_eval_sources batch:
- * b_alg = distinct nodes per (candidate, receiver) x components used x trace length x 4 B
+/* algorithmic / logical bytes per evaluation of the last kiwi_eval_sources batch (SURVEY.md
+ * section 8d), averaged over the first min(max_candidates, chunk) candidates of its last chunk:
+ * b_alg = distinct GF nodes per (candidate, receiver) x components used x stored window length x 4 B
  *         + one write of each synthetic + one read of each reference;
- * b_log = every (group, corner, component) trace counted once per use. */
-int kiwi_last_batch_bytes(kiwi_ctx* ctx, double* b_alg, double* b_log);
+ * b_log = every (centroid, corner, component) trace counted once per use (what the reference streams). */
+int kiwi_last_batch_bytes(kiwi_ctx* ctx, int max_candidates, double* b_alg, double* b_log, int* nsampled);
 /* device time [ms] of the stages of the last kiwi_eval_sources call, measured with CUDA events on
  * the engine's stream: [0] discretise, [1] geometry/index pre-pass, [2] synthesis, [3] misfit,
  * [4] whole call incl. H2D/D2H; launches[0..3]: kernel launches per stage */

@@ -1,0 +1,911 @@
+// Engine context and the C ABI of the hot path (include/kiwi_b200.h).
+//
+// This file is the B200-native counterpart of the module state and drivers of
+// minimizer_engine.f90 (state singletons :78-108, setters :114-711, calculate_seismograms /
+// scale_seismograms / calculate_misfits :885-945, get_misfits :1130-1172): it owns the HBM-resident
+// database, receivers, reference traces and tapers, prepares candidate sources on the host
+// (the few libm calls per candidate, host_math.cpp), and enqueues the kernels of kernels.cu on one
+// CUDA stream.  There is no CPU evaluation path: without a CUDA device kiwi_create() fails.
+// Citations are file:line of /root/reference.
+#include "kiwi_internal.hpp"
+#include "kernels.cuh"
+#include "host_math.hpp"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <climits>
+#include <unordered_set>
+
+#define CU_OK(call)                                                                                          \
+    do {                                                                                                     \
+        cudaError_t e__ = (call);                                                                            \
+        if (e__ != cudaSuccess) return kiwi_set_error("CUDA error: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes + bytes / 4 + 256);
+        if (e == cudaSuccess) cap = bytes + bytes / 4 + 256;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+// receiver.f90:56 component_names(-5:5) = w s u l c ? a r d n e
+int character_to_id(char ch) {
+    static const char names[11] = {'w', 's', 'u', 'l', 'c', '?', 'a', 'r', 'd', 'n', 'e'};
+    for (int i = -5; i <= 5; i++) if (i != 0 && ch == names[i + 5]) return i;
+    return 0;
+}
+
+struct HostReceiver {   // t_receiver, receiver.f90:58-99 (host mirror)
+    double lat = 0., lon = 0.;   // radians
+    float depth = 0.f;
+    bool enabled = true;
+    int ncomp = 0;
+    int comp[KIWI_MAX_COMP] = {0, 0, 0, 0, 0};
+    std::vector<float> ref[KIWI_MAX_COMP];
+    int ref_ds0[KIWI_MAX_COMP] = {0}, ref_ds1[KIWI_MAX_COMP] = {0};
+    bool has_ref[KIWI_MAX_COMP] = {false, false, false, false, false};
+    std::vector<float> taper_x, taper_y, filter_x, filter_y;
+    int fs0 = 0, fs1 = 0;
+};
+
+}  // namespace
+
+struct kiwi_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // database (set_database)
+    bool db_set = false;
+    GfdbDev db{};
+    DevBuf d_slabs, d_nodes, d_tspan;
+    std::vector<NodeInfo> h_nodes;
+    std::vector<int2> h_tspan;
+    int db_tmin = 0, db_tmax = 0;
+    // engine settings
+    bool interpolate = false;                 // minimizer_engine.f90:104
+    int xunder = 1, zunder = 1;               // :105
+    float effective_dt = 1.f;                 // :79
+    int misfit_method = KIWI_L2NORM;          // :100
+    float syn_factor = 1.f;
+    // receivers
+    bool receivers_set = false, receivers_dirty = true;
+    std::vector<HostReceiver> rcv;
+    DevBuf d_rcv, d_refdata, d_taper;
+    std::vector<ReceiverDev> h_rcvdev;
+    int nmisfits = 0;
+    // source location (minimizer_engine.f90:453-467)
+    bool loc_set = false;
+    double olat = 0., olon = 0., ref_time = 0.;
+    // workspace
+    DevBuf d_cands, d_bilat, d_gf, d_gi, d_tf, d_recs, d_hdrs, d_seis, d_shdrs, d_out, d_status, d_tmax, d_table;
+    PinBuf h_stage, h_out;
+    size_t work_budget = 0;
+    // description of the last chunk evaluated (inspection entry points, accounting)
+    struct Last {
+        bool valid = false;
+        int sourcetype = 0, n = 0, nrcv = 0;
+        size_t rec_stride = 0, seis_stride = 0;
+        int ngroups_total = 0;
+        std::vector<CandDev> cands;
+        GroupSoA g{};
+        TapSoA taps{};
+        std::vector<float> toff, wt;
+        bool seis_valid = false;
+    } last;
+    float ms[5] = {0, 0, 0, 0, 0};
+    int launches[4] = {0, 0, 0, 0};
+    // ns = 1 state (set_source_params / get_misfits pair)
+    bool src_set = false, src_dirty = true;
+    int src_type = 0;
+    std::vector<float> src_params, src_misfits;
+    int src_status = 0;
+};
+
+namespace {
+
+int require_db(kiwi_ctx* c) { return c->db_set ? 0 : kiwi_set_error("no database set"); }               // minimizer_engine.f90:1346
+int require_receivers(kiwi_ctx* c) { return c->receivers_set ? 0 : kiwi_set_error("no receivers set"); }  // :1362
+
+// ---- receivers -> device --------------------------------------------------------------------------
+int upload_receivers(kiwi_ctx* c) {
+    if (!c->receivers_dirty) return 0;
+    const int n = (int)c->rcv.size();
+    c->h_rcvdev.assign(n, ReceiverDev());
+    std::vector<float> refdata, taperdata;
+    int nm = 0;
+    const float dt = c->db.dt;
+    for (int i = 0; i < n; i++) {
+        const HostReceiver& h = c->rcv[i];
+        ReceiverDev& r = c->h_rcvdev[i];
+        memset(&r, 0, sizeof r);
+        if (c->loc_set) {   // seismogram.f90:99-100
+            kh::azibazi(c->olat, c->olon, h.lat, h.lon, &r.azi0, &r.bazi0);
+            r.dist0 = kh::distance_accurate50m(c->olat, c->olon, h.lat, h.lon);
+            kh::final_rotation(r.bazi0, &r.cl0, &r.sl0);
+        }
+        r.depth = h.depth;
+        r.enabled = h.enabled ? 1 : 0;
+        r.ncomp = h.ncomp;
+        r.misfit_base = nm;
+        if (h.enabled) nm += h.ncomp;
+        for (int k = 0; k < h.ncomp; k++) {
+            const int id = h.comp[k], aid = id < 0 ? -id : id;
+            const float sg = id < 0 ? -1.f : 1.f;
+            r.comp[k] = id;
+            if (aid == 1) { r.ja = k + 1; r.sa = sg; }
+            if (aid == 2) { r.jr = k + 1; r.sr = sg; }
+            if (aid == 3) { r.jd = k + 1; r.sd = sg; }
+            if (aid == 4) { r.jn = k + 1; r.sn = sg; }
+            if (aid == 5) { r.je = k + 1; r.se = sg; }
+            if (h.has_ref[k]) {
+                r.ref_ds0[k] = h.ref_ds0[k]; r.ref_ds1[k] = h.ref_ds1[k];
+                kh::initial_probe_span(h.ref_ds0[k], h.ref_ds1[k], &r.ref_sp0[k], &r.ref_sp1[k]);   // comparator.f90:222-271
+                r.ref_off[k] = (long long)refdata.size();
+                refdata.insert(refdata.end(), h.ref[k].begin(), h.ref[k].end());
+            } else {
+                r.ref_ds0[k] = 0; r.ref_ds1[k] = -1; r.ref_off[k] = 0;
+            }
+        }
+        if (!h.taper_x.empty()) {
+            std::vector<float> tab;
+            r.has_taper = 1;
+            kh::taper_table(h.taper_x, h.taper_y, dt, &r.tp0, &r.tp1, &tab);
+            kh::discrete_plf_span(h.taper_x, dt, &r.dps0, &r.dps1);
+            r.taper_off = (long long)taperdata.size();
+            taperdata.insert(taperdata.end(), tab.begin(), tab.end());
+        }
+        r.has_filter = h.filter_x.empty() ? 0 : 1;
+        r.fs0 = h.fs0; r.fs1 = h.fs1;
+    }
+    c->nmisfits = nm;
+    if (refdata.empty()) refdata.push_back(0.f);
+    if (taperdata.empty()) taperdata.push_back(0.f);
+    CU_OK(c->d_rcv.ensure(sizeof(ReceiverDev) * std::max(n, 1)));
+    CU_OK(c->d_refdata.ensure(sizeof(float) * refdata.size()));
+    CU_OK(c->d_taper.ensure(sizeof(float) * taperdata.size()));
+    CU_OK(cudaMemcpyAsync(c->d_rcv.p, c->h_rcvdev.data(), sizeof(ReceiverDev) * n, cudaMemcpyHostToDevice, c->stream));
+    CU_OK(cudaMemcpyAsync(c->d_refdata.p, refdata.data(), sizeof(float) * refdata.size(), cudaMemcpyHostToDevice, c->stream));
+    CU_OK(cudaMemcpyAsync(c->d_taper.p, taperdata.data(), sizeof(float) * taperdata.size(), cudaMemcpyHostToDevice, c->stream));
+    CU_OK(cudaStreamSynchronize(c->stream));
+    c->receivers_dirty = false;
+    return 0;
+}
+
+bool all_refs_set(const kiwi_ctx* c) {
+    for (const HostReceiver& h : c->rcv)
+        for (int k = 0; k < h.ncomp; k++) if (!h.has_ref[k]) return false;
+    return true;
+}
+
+int prep_candidate(int sourcetype, const float* p, float effective_dt, kh::SourcePrep* sp) {
+    if (sourcetype == KIWI_SOURCE_BILATERAL) return kh::prep_bilateral(p, effective_dt, sp) ? 0 : 1;
+    if (sourcetype == KIWI_SOURCE_MOMENT_TENSOR) return kh::prep_moment_tensor(p, effective_dt, sp) ? 0 : 1;
+    return 1;
+}
+
+// Evaluate candidates [0,n) of `params`; d_out: device [n][nmisfits][2]; h_status: host [n] or null.
+// want_misfits = false stops after synthesis (used by the seismogram getters).
+int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* params, float* d_out, int* h_status, bool want_misfits) {
+    if (require_db(c)) return 1;
+    if (require_receivers(c)) return 1;
+    if (!c->loc_set) return kiwi_set_error("no source location set");                   // minimizer_engine.f90:1378
+    if (nparams != kiwi_get_n_source_params(sourcetype) || nparams == 0) return kiwi_set_error("wrong number of source parameters or source type not available");
+    if (sourcetype != KIWI_SOURCE_BILATERAL && sourcetype != KIWI_SOURCE_MOMENT_TENSOR) return kiwi_set_error("source type not available in this build");
+    if (want_misfits && !all_refs_set(c)) return kiwi_set_error("no reference seismograms set");   // :1428
+    if (want_misfits) {
+        const int m = c->misfit_method;
+        if (!(m == KIWI_L2NORM || m == KIWI_L1NORM || m == KIWI_SCALAR_PRODUCT || m == KIWI_PEAK))
+            return kiwi_set_error("misfit method %d is not available in this build (time-domain norms only)", m);
+        for (const HostReceiver& h : c->rcv) if (h.enabled && !h.filter_x.empty())
+            return kiwi_set_error("misfit filters are not available in this build");
+    }
+    if (upload_receivers(c)) return 1;
+    const int nrcv = (int)c->rcv.size();
+    const int nm = c->nmisfits;
+    cudaStream_t st = c->stream;
+    for (int i = 0; i < 5; i++) c->ms[i] = 0.f;
+    for (int i = 0; i < 4; i++) c->launches[i] = 0;
+    if (n == 0) return 0;
+
+    // ---- host preparation of all candidates -------------------------------------------------------
+    std::vector<kh::SourcePrep> prep(n);
+    std::vector<int> bad(n, 0);
+    size_t max_groups = 1;
+    for (int i = 0; i < n; i++) {
+        bad[i] = prep_candidate(sourcetype, params + (size_t)i * nparams, c->effective_dt, &prep[i]);
+        if (bad[i]) { prep[i].ngroups = 0; prep[i].nt = 0; prep[i].toff.clear(); prep[i].wt.clear(); }
+        if (prep[i].nt > 32) { bad[i] = 1; prep[i].ngroups = 0; }   // SYN_MAXTAPS
+        max_groups = std::max(max_groups, (size_t)prep[i].ngroups);
+    }
+    // ---- chunking by workspace budget ---------------------------------------------------------------
+    if (c->work_budget == 0) {
+        size_t fr = 0, tot = 0;
+        CU_OK(cudaMemGetInfo(&fr, &tot));
+        c->work_budget = std::min<size_t>(fr / 2, (size_t)24 << 30);
+        for (DevBuf* b : {&c->d_recs, &c->d_seis}) c->work_budget += b->cap;   // already ours
+    }
+    const size_t per_cand_geo = (size_t)nrcv * max_groups * sizeof(GeoRec) + (size_t)nrcv * (sizeof(PairHdr) + KIWI_MAX_COMP * sizeof(SeisHdr));
+    int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, (c->work_budget / 2) / std::max<size_t>(per_cand_geo, 1)));
+
+    cudaEventRecord(c->ev[0], st);
+    for (int b0 = 0; b0 < n; b0 += chunk) {
+        const int nc = std::min(chunk, n - b0);
+        // ---- candidate / group / tap tables ---------------------------------------------------------
+        std::vector<CandDev> cands(nc);
+        int G = 0, Tp = 0;
+        size_t rec_stride = 1;
+        for (int i = 0; i < nc; i++) {
+            const kh::SourcePrep& sp = prep[b0 + i];
+            CandDev& cd = cands[i];
+            cd.group_begin = G; cd.ngroups = sp.ngroups; cd.tap_begin = Tp; cd.ntaps_total = sp.nt;
+            cd.moment = sp.moment; cd.risetime = sp.risetime; cd.nx = sp.nx; cd.ny = sp.ny; cd.nt = sp.nt;
+            cd.status = bad[b0 + i] ? KIWI_STATUS_BAD_PARAMS : KIWI_STATUS_OK;
+            G += sp.ngroups; Tp += sp.nt;
+            rec_stride = std::max(rec_stride, (size_t)sp.ngroups);
+        }
+        const int Galloc = std::max(G, 1), Talloc = std::max(Tp, 1);
+        CU_OK(c->d_cands.ensure(sizeof(CandDev) * nc));
+        CU_OK(c->d_gf.ensure(sizeof(float) * 10 * (size_t)Galloc));
+        CU_OK(c->d_gi.ensure(sizeof(int) * 4 * (size_t)Galloc));
+        CU_OK(c->d_tf.ensure(sizeof(float) * 2 * (size_t)Talloc));
+        GroupSoA g;
+        float* gf = c->d_gf.as<float>();
+        g.north = gf; g.east = gf + Galloc; g.depth = gf + 2 * (size_t)Galloc; g.tbase = gf + 3 * (size_t)Galloc; g.mhat = gf + 4 * (size_t)Galloc;
+        int* gi = c->d_gi.as<int>();
+        g.tap_begin = gi; g.tap_count = gi + Galloc; g.its_min = gi + 2 * (size_t)Galloc; g.its_max = gi + 3 * (size_t)Galloc;
+        TapSoA taps; taps.toff = c->d_tf.as<float>(); taps.wt = taps.toff + Talloc;
+        std::vector<float> toff(Talloc, 0.f), wt(Talloc, 0.f);
+        for (int i = 0; i < nc; i++) {
+            const kh::SourcePrep& sp = prep[b0 + i];
+            std::copy(sp.toff.begin(), sp.toff.end(), toff.begin() + cands[i].tap_begin);
+            std::copy(sp.wt.begin(), sp.wt.end(), wt.begin() + cands[i].tap_begin);
+        }
+        CU_OK(cudaMemcpyAsync(c->d_cands.p, cands.data(), sizeof(CandDev) * nc, cudaMemcpyHostToDevice, st));
+        CU_OK(cudaMemcpyAsync(taps.toff, toff.data(), sizeof(float) * Talloc, cudaMemcpyHostToDevice, st));
+        CU_OK(cudaMemcpyAsync(taps.wt, wt.data(), sizeof(float) * Talloc, cudaMemcpyHostToDevice, st));
+
+        cudaEventRecord(c->ev[1], st);
+        // ---- K1: sub-source groups ------------------------------------------------------------------
+        if (sourcetype == KIWI_SOURCE_BILATERAL) {
+            std::vector<BilatCand> bc(nc);
+            for (int i = 0; i < nc; i++) {
+                const kh::SourcePrep& sp = prep[b0 + i];
+                BilatCand& b = bc[i];
+                memset(&b, 0, sizeof b);
+                b.time = sp.p[0]; b.north = sp.p[1]; b.east = sp.p[2]; b.depth = sp.p[3];
+                b.length_a = sp.p[9]; b.length_b = sp.p[10]; b.width = sp.p[11]; b.rupvel = sp.p[12];
+                memcpy(b.rot_rup, sp.rot_rup, sizeof b.rot_rup);
+                memcpy(b.mhat, sp.mhat, sizeof b.mhat);
+                b.nx = sp.ngroups ? sp.nx : 0; b.ny = sp.ngroups ? sp.ny : 0; b.nt = sp.nt;
+                b.group_begin = cands[i].group_begin; b.tap_begin = cands[i].tap_begin;
+            }
+            CU_OK(c->d_bilat.ensure(sizeof(BilatCand) * nc));
+            CU_OK(cudaMemcpyAsync(c->d_bilat.p, bc.data(), sizeof(BilatCand) * nc, cudaMemcpyHostToDevice, st));
+            CU_OK(cudaStreamSynchronize(st));   // bc is a stack-lifetime staging vector
+            launch_bilat_groups(c->d_bilat.as<BilatCand>(), nc, g, taps, c->db.dt, Galloc, st);
+            c->launches[0] += 1;
+        } else {   // moment tensor: one group per candidate, filled on the host (source_moment_tensor.f90:256-263)
+            std::vector<float> hf((size_t)10 * Galloc, 0.f);
+            std::vector<int> hi((size_t)4 * Galloc, 0);
+            for (int i = 0; i < nc; i++) {
+                const kh::SourcePrep& sp = prep[b0 + i];
+                if (sp.ngroups == 0) continue;
+                const int gi0 = cands[i].group_begin;
+                hf[gi0] = sp.point[0]; hf[(size_t)Galloc + gi0] = sp.point[1]; hf[2 * (size_t)Galloc + gi0] = sp.point[2];
+                hf[3 * (size_t)Galloc + gi0] = sp.time;
+                for (int k = 0; k < 6; k++) hf[(4 + k) * (size_t)Galloc + gi0] = sp.mhat[k];
+                hi[gi0] = cands[i].tap_begin; hi[(size_t)Galloc + gi0] = sp.nt;
+            }
+            CU_OK(cudaMemcpyAsync(c->d_gf.p, hf.data(), sizeof(float) * hf.size(), cudaMemcpyHostToDevice, st));
+            CU_OK(cudaMemcpyAsync(c->d_gi.p, hi.data(), sizeof(int) * hi.size(), cudaMemcpyHostToDevice, st));
+            CU_OK(cudaStreamSynchronize(st));
+            launch_group_tap_range(g, taps, c->db.dt, 0, G, st);
+            c->launches[0] += 1;
+        }
+        cudaEventRecord(c->ev[2], st);
+        // ---- K2: geometry + indices + spans ---------------------------------------------------------
+        const size_t npairs = (size_t)nc * nrcv;
+        CU_OK(c->d_recs.ensure(sizeof(GeoRec) * npairs * rec_stride));
+        CU_OK(c->d_hdrs.ensure(sizeof(PairHdr) * npairs));
+        CU_OK(c->d_shdrs.ensure(sizeof(SeisHdr) * npairs * KIWI_MAX_COMP));
+        CU_OK(c->d_tmax.ensure(sizeof(int)));
+        CU_OK(cudaMemsetAsync(c->d_tmax.p, 0, sizeof(int), st));
+        launch_geometry(c->db, c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>(), nc, g, c->interpolate ? 1 : 0, c->xunder, c->zunder,
+                        c->d_recs.as<GeoRec>(), rec_stride, c->d_hdrs.as<PairHdr>(), c->d_tmax.as<int>(), st);
+        c->launches[1] += 1;
+        int tmax = 0;
+        CU_OK(cudaMemcpyAsync(&tmax, c->d_tmax.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        cudaEventRecord(c->ev[3], st);
+        CU_OK(cudaStreamSynchronize(st));
+        CU_OK(cudaGetLastError());
+        float ms01 = 0.f, ms12 = 0.f, ms23 = 0.f;
+        cudaEventElapsedTime(&ms12, c->ev[1], c->ev[2]);
+        cudaEventElapsedTime(&ms23, c->ev[2], c->ev[3]);
+        (void)ms01;
+        c->ms[0] += ms12; c->ms[1] += ms23;
+        // ---- K3 + K5: synthesis and misfit, in sub-chunks sized by the seismogram buffer ----------------
+        const int nq = (tmax + 6) / 4 + 1;
+        const size_t seis_stride = (size_t)4 * nq;
+        int nwarps = 8;
+        while (nwarps > 1 && synth_smem_bytes(nwarps, nq) > (size_t)110 * 1024) nwarps--;
+        if (synth_smem_bytes(nwarps, nq) > (size_t)220 * 1024)
+            return kiwi_set_error("synthetic window of %d samples does not fit the shared-memory accumulators", tmax);
+        const size_t per_cand_seis = (size_t)nrcv * KIWI_MAX_COMP * seis_stride * sizeof(float);
+        const int sub = (int)std::max<size_t>(1, std::min<size_t>((size_t)nc, (c->work_budget / 2) / std::max<size_t>(per_cand_seis, 1)));
+        CU_OK(c->d_seis.ensure(per_cand_seis * sub));
+        CU_OK(c->d_status.ensure(sizeof(int) * nc));
+        {
+            std::vector<int> stt(nc);
+            for (int i = 0; i < nc; i++) stt[i] = cands[i].status;
+            CU_OK(cudaMemcpyAsync(c->d_status.p, stt.data(), sizeof(int) * nc, cudaMemcpyHostToDevice, st));
+            CU_OK(cudaStreamSynchronize(st));
+        }
+        for (int s0 = 0; s0 < nc; s0 += sub) {
+            const int ns_ = std::min(sub, nc - s0);
+            const size_t poff = (size_t)s0 * nrcv;
+            cudaEventRecord(c->ev[3], st);
+            if (tmax > 0) {
+                cudaError_t e = launch_synth(c->db, c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>() + s0, ns_, g, taps, Galloc,
+                                             c->interpolate ? 1 : 0, c->xunder, c->zunder, c->d_recs.as<GeoRec>() + poff * rec_stride, rec_stride,
+                                             c->d_hdrs.as<PairHdr>() + poff, nq, nwarps, c->d_seis.as<float>(), seis_stride,
+                                             c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, st);
+                if (e != cudaSuccess) return kiwi_set_error("CUDA error launching synthesis: %s", cudaGetErrorString(e));
+                c->launches[2] += 1;
+            } else {
+                CU_OK(cudaMemsetAsync(c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, 0xff, sizeof(SeisHdr) * (size_t)ns_ * nrcv * KIWI_MAX_COMP, st));
+            }
+            cudaEventRecord(c->ev[4], st);
+            if (want_misfits && nm > 0) {
+                launch_misfit_td(c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>() + s0, ns_, c->d_seis.as<float>(), seis_stride,
+                                 c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, c->d_refdata.as<float>(), c->d_taper.as<float>(),
+                                 c->misfit_method, c->db.dt, c->syn_factor, nm, d_out + ((size_t)(b0 + s0) * nm) * 2, c->d_status.as<int>() + s0, st);
+                c->launches[3] += 1;
+            }
+            cudaEventRecord(c->ev[5], st);
+            CU_OK(cudaStreamSynchronize(st));
+            CU_OK(cudaGetLastError());
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, c->ev[3], c->ev[4]);
+            cudaEventElapsedTime(&b, c->ev[4], c->ev[5]);
+            c->ms[2] += a; c->ms[3] += b;
+        }
+        if (h_status) {
+            CU_OK(cudaMemcpy(h_status + b0, c->d_status.p, sizeof(int) * nc, cudaMemcpyDeviceToHost));
+        }
+        // remember this chunk for the inspection entry points
+        kiwi_ctx::Last& L = c->last;
+        L.valid = true; L.sourcetype = sourcetype; L.n = nc; L.nrcv = nrcv; L.rec_stride = rec_stride; L.seis_stride = seis_stride;
+        L.ngroups_total = Galloc; L.cands = cands; L.g = g; L.taps = taps; L.toff = toff; L.wt = wt;
+        L.seis_valid = (sub >= nc) && tmax > 0;
+    }
+    cudaEventRecord(c->ev[1], st);
+    CU_OK(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&c->ms[4], c->ev[0], c->ev[1]);
+    return 0;
+}
+
+int ensure_single(kiwi_ctx* c, bool want_misfits) {
+    if (!c->src_set) return kiwi_set_error("no source parameters set");   // minimizer_engine.f90:1394
+    if (!c->src_dirty && (!want_misfits || !c->src_misfits.empty()) && c->last.valid && c->last.n == 1) return 0;
+    if (upload_receivers(c)) return 1;
+    const int nm = c->nmisfits;
+    CU_OK(c->d_out.ensure(sizeof(float) * 2 * std::max(nm, 1)));
+    int status = 0;
+    c->src_misfits.clear();
+    if (eval_batch(c, c->src_type, 1, (int)c->src_params.size(), c->src_params.data(), c->d_out.as<float>(), &status, want_misfits)) return 1;
+    if (want_misfits) {
+        c->src_misfits.assign((size_t)2 * nm, 0.f);
+        if (nm > 0) CU_OK(cudaMemcpy(c->src_misfits.data(), c->d_out.p, sizeof(float) * 2 * nm, cudaMemcpyDeviceToHost));
+    }
+    c->src_status = status;
+    c->src_dirty = false;
+    if (status == KIWI_STATUS_BAD_PARAMS) return kiwi_set_error("discretisation of the source failed");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kiwi_get_n_source_params(int sourcetype) {   // source_all.f90:97-121
+    switch (sourcetype) {
+        case KIWI_SOURCE_BILATERAL: return 14;
+        case KIWI_SOURCE_MOMENT_TENSOR: return 11;
+        default: return 0;
+    }
+}
+
+kiwi_ctx* kiwi_create(int device) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { kiwi_set_error("kiwi_create: no CUDA device available (%s); this engine has no CPU path", cudaGetErrorString(e)); return nullptr; }
+    if (device < 0 || device >= ndev) { kiwi_set_error("kiwi_create: device %d out of range (0..%d)", device, ndev - 1); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { kiwi_set_error("kiwi_create: cudaSetDevice failed"); return nullptr; }
+    kiwi_ctx* c = new kiwi_ctx();
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; kiwi_set_error("kiwi_create: stream creation failed"); return nullptr; }
+    for (auto& ev : c->ev) cudaEventCreate(&ev);
+    return c;
+}
+
+void kiwi_destroy(kiwi_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (DevBuf* b : {&c->d_slabs, &c->d_nodes, &c->d_tspan, &c->d_rcv, &c->d_refdata, &c->d_taper, &c->d_cands, &c->d_bilat, &c->d_gf, &c->d_gi,
+                      &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table})
+        b->release();
+    c->h_stage.release(); c->h_out.release();
+    for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// set_database (minimizer_engine.f90:114-139): the whole database goes to HBM once, as one slab per
+// grid node (layout: kiwi_dev.cuh NodeInfo).
+int kiwi_set_database(kiwi_ctx* c, kiwi_gfdb* db) {
+    if (!c || !db) return kiwi_set_error("kiwi_set_database: null argument");
+    CU_OK(cudaSetDevice(c->device));
+    db->flatten();
+    const size_t nnodes = (size_t)db->nx * db->nz;
+    const int ng = db->ng;
+    c->h_nodes.assign(nnodes, NodeInfo());
+    c->h_tspan.assign(nnodes * ng, make_int2(0, -1));
+    unsigned long long total = 0;
+    int tmin = INT_MAX, tmax = INT_MIN;
+    for (size_t inode = 0; inode < nnodes; inode++) {
+        int lo = INT_MAX, hi = INT_MIN; bool all = true;
+        for (int k = 0; k < ng; k++) {
+            const size_t it = inode * ng + k;
+            if (db->len[it] <= 0) { all = false; continue; }
+            lo = std::min(lo, db->span0[it]); hi = std::max(hi, db->span0[it] + db->len[it] - 1);
+            c->h_tspan[it] = make_int2(db->span0[it], db->span0[it] + db->len[it] - 1);
+        }
+        NodeInfo& ni = c->h_nodes[inode];
+        if (!all) { ni.off = ~0ull; ni.w0 = 0; ni.wn = 0; continue; }   // node unusable: the centroid is skipped (seismogram.f90:172)
+        const int w0 = (int)(floor((double)lo / 4.0)) * 4;
+        const int wend = (int)(floor((double)hi / 4.0)) * 4 + 4;      // exclusive, multiple of 4
+        ni.off = total; ni.w0 = w0; ni.wn = wend - w0;
+        total += (unsigned long long)ni.wn * ng;
+        tmin = std::min(tmin, lo); tmax = std::max(tmax, hi);
+    }
+    c->db_tmin = tmin; c->db_tmax = tmax;
+    // fill the slabs through a bounded pinned staging buffer
+    CU_OK(c->d_slabs.ensure(sizeof(float) * std::max<unsigned long long>(total, 4)));
+    CU_OK(c->d_nodes.ensure(sizeof(NodeInfo) * nnodes));
+    CU_OK(c->d_tspan.ensure(sizeof(int2) * nnodes * ng));
+    const size_t stage_floats = (size_t)16 << 20;   // 64 MiB
+    CU_OK(c->h_stage.ensure(stage_floats * sizeof(float)));
+    float* stage = c->h_stage.as<float>();
+    size_t inode = 0;
+    while (inode < nnodes) {
+        // take as many whole nodes as fit the staging buffer
+        size_t first = inode; unsigned long long base = ~0ull; size_t used = 0;
+        for (; inode < nnodes; inode++) {
+            const NodeInfo& ni = c->h_nodes[inode];
+            if (ni.off == ~0ull) continue;
+            const size_t need = (size_t)ni.wn * ng;
+            if (need > stage_floats) return kiwi_set_error("kiwi_set_database: node slab larger than the staging buffer");
+            if (base == ~0ull) base = ni.off;
+            if (used + need > stage_floats) break;
+            float* dst = stage + (ni.off - base);
+            for (int k = 0; k < ng; k++) {
+                const size_t it = inode * ng + k;
+                const float* src = &db->data[(size_t)db->offset[it]];
+                const int s0 = db->span0[it], len = db->len[it];
+                float* row = dst + (size_t)k * ni.wn;
+                const int lead = s0 - ni.w0;
+                for (int j = 0; j < lead; j++) row[j] = 0.f;                        // zeros left of the trace span
+                memcpy(row + lead, src, sizeof(float) * len);
+                const float last = src[len - 1];
+                for (int j = lead + len; j < ni.wn; j++) row[j] = last;            // last sample repeats (sparse_trace.f90:29-50)
+            }
+            used += need;
+        }
+        (void)first;
+        if (used > 0) {
+            CU_OK(cudaMemcpyAsync(c->d_slabs.as<float>() + base, stage, sizeof(float) * used, cudaMemcpyHostToDevice, c->stream));
+            CU_OK(cudaStreamSynchronize(c->stream));
+        }
+    }
+    CU_OK(cudaMemcpy(c->d_nodes.p, c->h_nodes.data(), sizeof(NodeInfo) * nnodes, cudaMemcpyHostToDevice));
+    CU_OK(cudaMemcpy(c->d_tspan.p, c->h_tspan.data(), sizeof(int2) * nnodes * ng, cudaMemcpyHostToDevice));
+    GfdbDev& d = c->db;
+    d.dt = db->dt; d.dx = db->dx; d.dz = db->dz; d.firstx = db->firstx; d.firstz = db->firstz;
+    d.nx = db->nx; d.nz = db->nz; d.ng = db->ng;
+    d.slabs = c->d_slabs.as<float>(); d.nodes = c->d_nodes.as<NodeInfo>(); d.tspan = c->d_tspan.as<int2>(); d.lastval = nullptr;
+    c->db_set = true;
+    c->receivers_dirty = true; c->src_dirty = true; c->last.valid = false; c->work_budget = 0;
+    return 0;
+}
+
+int kiwi_set_local_interpolation(kiwi_ctx* c, int bilinear) {
+    if (!c) return kiwi_set_error("null context");
+    c->interpolate = bilinear != 0; c->src_dirty = true;
+    return 0;
+}
+int kiwi_set_spacial_undersampling(kiwi_ctx* c, int xunder, int zunder) {
+    if (!c) return kiwi_set_error("null context");
+    if (xunder < 1 || zunder < 1) return kiwi_set_error("invalid undersampling value");   // minimizer_engine.f90:155-158
+    c->xunder = xunder; c->zunder = zunder; c->src_dirty = true;
+    return 0;
+}
+
+int kiwi_set_receivers(kiwi_ctx* c, int n, const double* lat_deg, const double* lon_deg, const float* depth, const char* const* components) {
+    if (!c) return kiwi_set_error("null context");
+    if (require_db(c)) return 1;
+    std::vector<HostReceiver> v(n);
+    for (int i = 0; i < n; i++) {
+        HostReceiver& h = v[i];
+        h.lat = kh::d2r_d(lat_deg[i]); h.lon = kh::d2r_d(lon_deg[i]);   // minimizer_engine.f90:262 d2r(origin)
+        h.depth = depth ? depth[i] : 0.f;
+        const char* cs = components[i] ? components[i] : "";
+        const int nc = (int)strlen(cs);
+        if (nc > KIWI_MAX_COMP) return kiwi_set_error("initializing receiver failed: too many components at receiver %d", i + 1);
+        for (int k = 0; k < nc; k++) {   // receiver.f90:160-187
+            const int id = character_to_id(cs[k]);
+            if (id == 0) return kiwi_set_error("initializing receiver failed: unknown component '%c' at receiver %d", cs[k], i + 1);
+            for (int j = 0; j < k; j++) if (abs(h.comp[j]) == abs(id)) return kiwi_set_error("initializing receiver failed: conflicting components at receiver %d", i + 1);
+            h.comp[k] = id;
+        }
+        h.ncomp = nc;
+        h.enabled = nc > 0;   // receiver.f90:155-157
+    }
+    c->rcv.swap(v);
+    c->receivers_set = true; c->receivers_dirty = true; c->src_dirty = true; c->last.valid = false;
+    return 0;
+}
+
+int kiwi_switch_receiver(kiwi_ctx* c, int ireceiver, int state) {
+    if (!c) return kiwi_set_error("null context");
+    if (require_receivers(c)) return 1;
+    if (ireceiver < 1 || ireceiver > (int)c->rcv.size()) return kiwi_set_error("receiver index out of range");
+    c->rcv[ireceiver - 1].enabled = state != 0;
+    c->receivers_dirty = true; c->src_dirty = true;
+    return 0;
+}
+
+int kiwi_set_source_location(kiwi_ctx* c, float lat_deg, float lon_deg, double ref_time) {
+    if (!c) return kiwi_set_error("null context");
+    c->olat = (double)kh::d2r_r(lat_deg);   // minimizer.f90:512 d2r(lat) on default reals, widened at the call (:453-456)
+    c->olon = (double)kh::d2r_r(lon_deg);
+    c->ref_time = ref_time;
+    c->loc_set = true; c->receivers_dirty = true; c->src_dirty = true;
+    return 0;
+}
+
+int kiwi_set_effective_dt(kiwi_ctx* c, float effective_dt) {
+    if (!c) return kiwi_set_error("null context");
+    if (!(effective_dt > 0.f)) return kiwi_set_error("effective dt must be positive");
+    c->effective_dt = effective_dt; c->src_dirty = true;
+    return 0;
+}
+
+int kiwi_set_ref_seismogram(kiwi_ctx* c, int ireceiver, int icomponent, float tbegin, int n, const float* data) {
+    if (!c) return kiwi_set_error("null context");
+    if (require_receivers(c)) return 1;
+    if (ireceiver < 1 || ireceiver > (int)c->rcv.size()) return kiwi_set_error("receiver index out of range");
+    HostReceiver& h = c->rcv[ireceiver - 1];
+    if (icomponent < 1 || icomponent > h.ncomp) return kiwi_set_error("component index out of range");
+    if (n < 1) return kiwi_set_error("empty reference seismogram");
+    const int k = icomponent - 1;
+    const int ibeg = (int)lroundf(tbegin / c->db.dt);   // receiver.f90:843-848 seismogram_to_strip
+    h.ref[k].assign(data, data + n);
+    h.ref_ds0[k] = ibeg + 1; h.ref_ds1[k] = ibeg + n;
+    h.has_ref[k] = true;
+    c->receivers_dirty = true; c->src_dirty = true;
+    return 0;
+}
+
+int kiwi_set_misfit_method(kiwi_ctx* c, int norm_id) {
+    if (!c) return kiwi_set_error("null context");
+    if (norm_id < 1 || norm_id > 8) return kiwi_set_error("unknown norm method");
+    c->misfit_method = norm_id; c->src_dirty = true;
+    return 0;
+}
+
+int kiwi_set_misfit_taper(kiwi_ctx* c, int ireceiver, int n, const float* x, const float* y) {
+    if (!c) return kiwi_set_error("null context");
+    if (require_receivers(c)) return 1;
+    if (ireceiver < 1 || ireceiver > (int)c->rcv.size()) return kiwi_set_error("receiver index out of range");
+    if (n < 2) return kiwi_set_error("a taper needs at least two points");
+    HostReceiver& h = c->rcv[ireceiver - 1];
+    h.taper_x.assign(x, x + n); h.taper_y.assign(y, y + n);
+    c->receivers_dirty = true; c->src_dirty = true;
+    return 0;
+}
+
+int kiwi_set_misfit_filter(kiwi_ctx* c, int ireceiver, int n, const float* x, const float* y) {
+    if (!c) return kiwi_set_error("null context");
+    if (require_receivers(c)) return 1;
+    if (ireceiver < 0 || ireceiver > (int)c->rcv.size()) return kiwi_set_error("receiver index out of range");
+    if (n < 2) return kiwi_set_error("a filter needs at least two points");
+    for (int i = 0; i < (int)c->rcv.size(); i++) {
+        if (ireceiver != 0 && i != ireceiver - 1) continue;
+        c->rcv[i].filter_x.assign(x, x + n); c->rcv[i].filter_y.assign(y, y + n);
+    }
+    c->receivers_dirty = true; c->src_dirty = true;
+    return 0;
+}
+
+int kiwi_set_synthetics_factor(kiwi_ctx* c, float factor) {
+    if (!c) return kiwi_set_error("null context");
+    c->syn_factor = factor; c->src_dirty = true;
+    return 0;
+}
+
+int kiwi_set_floating_shiftrange(kiwi_ctx* c, int ireceiver, float lo, float hi) {
+    if (!c) return kiwi_set_error("null context");
+    if (require_receivers(c)) return 1;
+    if (ireceiver < 0 || ireceiver > (int)c->rcv.size()) return kiwi_set_error("receiver index out of range");
+    const int r0 = (int)lroundf(lo / c->db.dt), r1 = (int)lroundf(hi / c->db.dt);   // minimizer_engine.f90:436-437
+    for (int i = 0; i < (int)c->rcv.size(); i++) {
+        if (ireceiver != 0 && i != ireceiver - 1) continue;
+        c->rcv[i].fs0 = r0; c->rcv[i].fs1 = r1;
+    }
+    c->receivers_dirty = true; c->src_dirty = true;
+    return 0;
+}
+
+int kiwi_get_nmisfits(kiwi_ctx* c) {
+    if (!c) return 0;
+    int n = 0;
+    for (const HostReceiver& h : c->rcv) if (h.enabled) n += h.ncomp;
+    return n;
+}
+
+int kiwi_eval_sources_device(kiwi_ctx* c, int sourcetype, int ns, int nparams, const float* params, float* d_misfits, int* status) {
+    if (!c) return kiwi_set_error("null context");
+    CU_OK(cudaSetDevice(c->device));
+    if (ns < 0) return kiwi_set_error("negative number of sources");
+    c->src_dirty = true;
+    return eval_batch(c, sourcetype, ns, nparams, params, d_misfits, status, true);
+}
+
+int kiwi_eval_sources(kiwi_ctx* c, int sourcetype, int ns, int nparams, const float* params, float* misfits, int* status) {
+    if (!c) return kiwi_set_error("null context");
+    CU_OK(cudaSetDevice(c->device));
+    if (ns < 0) return kiwi_set_error("negative number of sources");
+    if (upload_receivers(c)) return 1;
+    const size_t nfl = (size_t)ns * std::max(c->nmisfits, 1) * 2;
+    CU_OK(c->d_out.ensure(sizeof(float) * std::max<size_t>(nfl, 2)));
+    c->src_dirty = true;
+    if (eval_batch(c, sourcetype, ns, nparams, params, c->d_out.as<float>(), status, true)) return 1;
+    if (ns > 0 && c->nmisfits > 0)
+        CU_OK(cudaMemcpy(misfits, c->d_out.p, sizeof(float) * (size_t)ns * c->nmisfits * 2, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int kiwi_global_misfits(int ns, int nmisfits, const float* misfits, float* global_misfits) {
+    // minimizer_engine.f90:937-942: fp32 sums in receiver order, sqrt(sum m^2)/sqrt(sum n^2)
+    for (int s = 0; s < ns; s++) {
+        float m = 0.f, nf = 0.f;
+        const float* p = misfits + (size_t)s * nmisfits * 2;
+        for (int i = 0; i < nmisfits; i++) { m = m + p[2 * i] * p[2 * i]; nf = nf + p[2 * i + 1] * p[2 * i + 1]; }
+        global_misfits[s] = sqrtf(m) / sqrtf(nf);
+    }
+    return 0;
+}
+
+int kiwi_set_source_params(kiwi_ctx* c, int sourcetype, int nparams, const float* params) {
+    if (!c) return kiwi_set_error("null context");
+    if (!c->loc_set) return kiwi_set_error("no source location set");
+    if (nparams != kiwi_get_n_source_params(sourcetype) || nparams == 0) return kiwi_set_error("wrong number of source parameters or source type not available");
+    // minimizer_engine.f90:511-513: identical parameters are a no-op
+    if (c->src_set && c->src_type == sourcetype && (int)c->src_params.size() == nparams &&
+        memcmp(c->src_params.data(), params, sizeof(float) * nparams) == 0) return 0;
+    c->src_type = sourcetype; c->src_params.assign(params, params + nparams);
+    c->src_set = true; c->src_dirty = true;
+    return 0;
+}
+
+int kiwi_get_misfits(kiwi_ctx* c, float* misfits, int cap_pairs, int* nmisfits) {
+    if (!c) return kiwi_set_error("null context");
+    CU_OK(cudaSetDevice(c->device));
+    if (ensure_single(c, true)) return 1;
+    const int nm = c->nmisfits;
+    if (nmisfits) *nmisfits = nm;
+    if (cap_pairs < nm) return kiwi_set_error("misfit buffer too small: need %d pairs", nm);
+    memcpy(misfits, c->src_misfits.data(), sizeof(float) * 2 * nm);
+    for (int i = 0; i < 2 * nm; i++)
+        if (!std::isfinite(misfits[i])) return kiwi_set_error("misfit is nan or very big at receiver component %d", i / 2 + 1);   // minimizer_engine.f90:1163-1166
+    return 0;
+}
+
+int kiwi_get_global_misfit(kiwi_ctx* c, float* misfit) {
+    if (!c) return kiwi_set_error("null context");
+    CU_OK(cudaSetDevice(c->device));
+    if (ensure_single(c, true)) return 1;
+    return kiwi_global_misfits(1, c->nmisfits, c->src_misfits.data(), misfit);
+}
+
+int kiwi_get_floating_shifts(kiwi_ctx* c, int* shifts, int cap, int* n) {
+    (void)c; (void)shifts; (void)cap; (void)n;
+    return kiwi_set_error("floating misfits are not available in this build");
+}
+
+int kiwi_get_seismogram(kiwi_ctx* c, int ireceiver, int icomponent, int which, int* first_index, int* n, float* buf, int cap) {
+    if (!c) return kiwi_set_error("null context");
+    CU_OK(cudaSetDevice(c->device));
+    if (ensure_single(c, false)) return 1;
+    if (ireceiver < 1 || ireceiver > (int)c->rcv.size()) return kiwi_set_error("receiver index out of range");
+    const HostReceiver& h = c->rcv[ireceiver - 1];
+    if (icomponent < 1 || icomponent > h.ncomp) return kiwi_set_error("component index out of range");
+    if (!c->last.seis_valid) return kiwi_set_error("no synthetic seismogram available");
+    const size_t item = (size_t)(ireceiver - 1) * KIWI_MAX_COMP + (icomponent - 1);
+    SeisHdr sh;
+    CU_OK(cudaMemcpy(&sh, c->d_shdrs.as<SeisHdr>() + item, sizeof sh, cudaMemcpyDeviceToHost));
+    if (sh.hi < sh.lo) { *first_index = 0; *n = 0; return 0; }
+    const int len = sh.hi - sh.lo + 1;
+    *first_index = sh.lo; *n = len;
+    const int m = std::min(len, cap);
+    if (m > 0) {
+        CU_OK(cudaMemcpy(buf, c->d_seis.as<float>() + item * c->last.seis_stride + (sh.lo - sh.base), sizeof(float) * m, cudaMemcpyDeviceToHost));
+        if (which == 1) {   // probe_set_array(..., factor_=moment) comparator.f90:265
+            const float moment = c->last.cands[0].moment;
+            for (int i = 0; i < m; i++) buf[i] = buf[i] * moment;
+        }
+    }
+    return 0;
+}
+
+int kiwi_discretize_source(kiwi_ctx* c, int sourcetype, int nparams, const float* params, float* table, int cap, int* ncentroids, int* grid3) {
+    if (!c) return kiwi_set_error("null context");
+    CU_OK(cudaSetDevice(c->device));
+    if (kiwi_set_source_params(c, sourcetype, nparams, params)) return 1;
+    if (ensure_single(c, false)) return 1;
+    const CandDev& cd = c->last.cands[0];
+    const int nc = cd.ngroups * cd.nt;
+    if (ncentroids) *ncentroids = nc;
+    if (grid3) { grid3[0] = cd.nx; grid3[1] = cd.ny; grid3[2] = cd.nt; }
+    const int m = std::min(nc, cap);
+    if (m > 0) {
+        CU_OK(c->d_table.ensure(sizeof(float) * 10 * (size_t)m));
+        launch_expand_centroids(cd, c->last.g, c->last.taps, c->last.ngroups_total, c->d_table.as<float>(), m, c->stream);
+        CU_OK(cudaMemcpyAsync(table, c->d_table.p, sizeof(float) * 10 * (size_t)m, cudaMemcpyDeviceToHost, c->stream));
+        CU_OK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+int kiwi_get_indices(kiwi_ctx* c, int ireceiver, int* ix, int* iz, int* its, float* dix, float* diz, int* near_boundary, int cap, int* n) {
+    if (!c) return kiwi_set_error("null context");
+    CU_OK(cudaSetDevice(c->device));
+    if (ensure_single(c, false)) return 1;
+    if (ireceiver < 1 || ireceiver > (int)c->rcv.size()) return kiwi_set_error("receiver index out of range");
+    const kiwi_ctx::Last& L = c->last;
+    const CandDev& cd = L.cands[0];
+    const int ng_ = cd.ngroups;
+    std::vector<GeoRec> recs(std::max(ng_, 1));
+    std::vector<float> tbase(std::max(ng_, 1));
+    if (ng_ > 0) {
+        CU_OK(cudaMemcpy(recs.data(), c->d_recs.as<GeoRec>() + (size_t)(ireceiver - 1) * L.rec_stride, sizeof(GeoRec) * ng_, cudaMemcpyDeviceToHost));
+        CU_OK(cudaMemcpy(tbase.data(), L.g.tbase + cd.group_begin, sizeof(float) * ng_, cudaMemcpyDeviceToHost));
+    }
+    int k = 0;
+    const float dt = c->db.dt;
+    for (int ig = 0; ig < ng_; ig++)
+        for (int it = 0; it < cd.nt; it++, k++) {
+            if (k >= cap) continue;
+            const float time = tbase[ig] + L.toff[cd.tap_begin + it];
+            ix[k] = recs[ig].ix1; iz[k] = recs[ig].iz1; dix[k] = recs[ig].dix; diz[k] = recs[ig].diz;
+            its[k] = (int)floorf(time / dt);   // sparse_trace.f90:640 on rshift = time/dt (seismogram.f90:139)
+            if (near_boundary) near_boundary[k] = (recs[ig].flags & GEO_NEAR) ? 1 : 0;
+        }
+    if (n) *n = k;
+    return 0;
+}
+
+int kiwi_get_spans(kiwi_ctx* c, int ireceiver, int* spans6) {
+    if (!c) return kiwi_set_error("null context");
+    CU_OK(cudaSetDevice(c->device));
+    if (ensure_single(c, false)) return 1;
+    if (ireceiver < 1 || ireceiver > (int)c->rcv.size()) return kiwi_set_error("receiver index out of range");
+    PairHdr h;
+    CU_OK(cudaMemcpy(&h, c->d_hdrs.as<PairHdr>() + (ireceiver - 1), sizeof h, cudaMemcpyDeviceToHost));
+    spans6[0] = h.s1lo; spans6[1] = h.s1hi; spans6[2] = h.s2lo; spans6[3] = h.s2hi; spans6[4] = h.s3lo; spans6[5] = h.s3hi;
+    return 0;
+}
+
+int kiwi_trace_span(kiwi_ctx* c, int ix, int iz, int ig, int* span2) {
+    if (!c) return kiwi_set_error("null context");
+    if (require_db(c)) return 1;
+    if (ix < 1 || ix > c->db.nx || iz < 1 || iz > c->db.nz || ig < 1 || ig > c->db.ng) return kiwi_set_error("gfdb: invalid request: out of bounds");
+    const int2 s = c->h_tspan[((size_t)(ix - 1) * c->db.nz + (iz - 1)) * c->db.ng + (ig - 1)];
+    if (s.y < s.x) return kiwi_set_error("no trace available for index");
+    span2[0] = s.x; span2[1] = s.y;
+    return 0;
+}
+
+int kiwi_last_batch_bytes(kiwi_ctx* c, int max_candidates, double* b_alg, double* b_log, int* nsampled) {
+    if (!c) return kiwi_set_error("null context");
+    CU_OK(cudaSetDevice(c->device));
+    const kiwi_ctx::Last& L = c->last;
+    if (!L.valid) return kiwi_set_error("no batch has been evaluated");
+    const int ns = std::max(1, std::min(max_candidates, L.n));
+    const int ng = c->db.ng;
+    double alg = 0., logi = 0.;
+    std::vector<GeoRec> recs(L.rec_stride);
+    std::vector<PairHdr> hdrs((size_t)ns * L.nrcv);
+    CU_OK(cudaMemcpy(hdrs.data(), c->d_hdrs.p, sizeof(PairHdr) * hdrs.size(), cudaMemcpyDeviceToHost));
+    std::unordered_set<int> seen;
+    for (int b = 0; b < ns; b++) {
+        const CandDev& cd = L.cands[b];
+        for (int ir = 0; ir < L.nrcv; ir++) {
+            const ReceiverDev& R = c->h_rcvdev[ir];
+            if (!R.enabled || cd.ngroups == 0) continue;
+            const bool need_h = (R.ja | R.jr | R.jn | R.je) != 0, need_v = R.jd != 0;
+            CU_OK(cudaMemcpy(recs.data(), c->d_recs.as<GeoRec>() + ((size_t)b * L.nrcv + ir) * L.rec_stride, sizeof(GeoRec) * cd.ngroups, cudaMemcpyDeviceToHost));
+            seen.clear();
+            for (int ig = 0; ig < cd.ngroups; ig++) {
+                const GeoRec& r = recs[ig];
+                if (r.flags & GEO_SKIP) continue;
+                const int nco = (r.flags & GEO_SINGLE) ? 1 : 4;
+                const int ix2 = r.ix1 + (c->interpolate ? c->xunder : 1), iz2 = r.iz1 + (c->interpolate ? c->zunder : 1);
+                const int cx[4] = {r.ix1, r.ix1, ix2, ix2}, cz[4] = {r.iz1, iz2, r.iz1, iz2};
+                for (int k = 0; k < nco; k++) {
+                    const int inode = (cx[k] - 1) * c->db.nz + (cz[k] - 1);
+                    double bytes = 0.;   // stored samples of the GF components this receiver uses
+                    for (int j = 0; j < ng; j++) {
+                        const bool horiz = (j < 5) || j == 8;
+                        if (horiz ? !need_h : !need_v) continue;
+                        const int2 sp = c->h_tspan[(size_t)inode * ng + j];
+                        bytes += 4.0 * (sp.y - sp.x + 1);
+                    }
+                    logi += bytes * cd.nt;          // the reference fetches per centroid (seismogram.f90:131-254)
+                    if (seen.insert(inode).second) alg += bytes;
+                }
+            }
+            const PairHdr& h = hdrs[(size_t)b * L.nrcv + ir];
+            const int s12lo = std::min(h.s1lo, h.s2lo), s12hi = std::max(h.s1hi, h.s2hi);
+            for (int k = 0; k < R.ncomp; k++) {
+                const int aid = abs(R.comp[k]);
+                int lo, hi;
+                if (aid == 1) { lo = h.s1lo; hi = h.s1hi; } else if (aid == 2) { lo = h.s2lo; hi = h.s2hi; }
+                else if (aid == 3) { lo = h.s3lo; hi = h.s3hi; } else { lo = s12lo; hi = s12hi; }
+                if (hi >= lo) { alg += 4.0 * (hi - lo + 1); logi += 4.0 * (hi - lo + 1); }
+                if (R.ref_ds1[k] >= R.ref_ds0[k]) { alg += 4.0 * (R.ref_ds1[k] - R.ref_ds0[k] + 1); logi += 4.0 * (R.ref_ds1[k] - R.ref_ds0[k] + 1); }
+            }
+        }
+    }
+    if (b_alg) *b_alg = alg / ns;
+    if (b_log) *b_log = logi / ns;
+    if (nsampled) *nsampled = ns;
+    return 0;
+}
+
+int kiwi_last_timing(kiwi_ctx* c, float* ms5, int* launches4) {
+    if (!c) return kiwi_set_error("null context");
+    if (ms5) for (int i = 0; i < 5; i++) ms5[i] = c->ms[i];
+    if (launches4) for (int i = 0; i < 4; i++) launches4[i] = c->launches[i];
+    return 0;
+}
+
+}  // extern "C"

@@ -70,7 +70,6 @@ struct GroupSoA {
     float* mhat;                // [6][ngroups_total] : mxx myy mzz mxy mxz myz
     int *tap_begin, *tap_count; // taps of this group
     int *its_min, *its_max;     // min/max of floor((tbase (+) toff)/dt) over the taps
-    int* time_first;            // 1: time = toff + tbase order (moment tensor), 0: tbase + toff (same value; kept for clarity)
 };
 struct TapSoA {
     float *toff, *wt;

@@ -1,0 +1,322 @@
+"""Host-side mirror of the reference's engine interface for the hot path.
+
+Method names, argument meaning and error behaviour follow the commands of the `minimizer` program
+(minimizer.f90:1729-1811) and the subroutines of minimizer_engine.f90 they call; a failing call
+raises KiwiError carrying the engine's error string (the reference answers "<cmd>: nok" +
+g_errstr, minimizer.f90:1676-1701).
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import lib, c_float_p, c_double_p, c_int_p, c_ll_p
+
+# source_all.f90:58-60 / parameterized_source.f90
+SOURCE_TYPES = {"bilateral": 1, "circular": 2, "point_lp": 3, "eikonal": 4, "mt_eikonal": 5, "moment_tensor": 6}
+# comparator.f90:33-42, names as accepted by set_misfit_method (minimizer.f90:842-873)
+NORMS = {"l2norm": 1, "l1norm": 2, "ampspec_l2norm": 3, "ampspec_l1norm": 4, "scalar_product": 5, "peak": 6,
+         "floating_l2norm": 7, "floating_l1norm": 8}
+# benchmark/kiwibench.py:51-72: the 20-sample ramp source time function of the kiwibench database
+KIWIBENCH_STF = np.array([0, 0, 0, 0, 0, 0, .1, .2, .3, .4, .5, .6, .7, .8, .9, 1, 1, 1, 1, 1], dtype=np.float32)
+
+
+class KiwiError(RuntimeError):
+    pass
+
+
+def _check(rc):
+    if rc != 0:
+        raise KiwiError(lib.kiwi_last_error().decode("utf-8", "replace"))
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _fp(a):
+    return a.ctypes.data_as(c_float_p)
+
+
+def n_source_params(sourcetype):
+    if isinstance(sourcetype, str):
+        sourcetype = SOURCE_TYPES[sourcetype]
+    return lib.kiwi_get_n_source_params(int(sourcetype))
+
+
+def global_misfits(misfits):
+    """sqrt(sum m^2)/sqrt(sum n^2) per candidate (minimizer_engine.f90:937-942)."""
+    m = _f32(misfits)
+    ns, nm = m.shape[0], m.shape[1]
+    out = np.empty(ns, dtype=np.float32)
+    _check(lib.kiwi_global_misfits(ns, nm, _fp(m), _fp(out)))
+    return out
+
+
+class Gfdb:
+    """Green's function database on the host (gfdb.f90 t_gfdb; tools gfdb_build, gfdb_build_ahfull)."""
+
+    def __init__(self, handle):
+        if not handle:
+            raise KiwiError(lib.kiwi_last_error().decode())
+        self._h = C.c_void_p(handle)
+
+    @classmethod
+    def create(cls, nx, nz, ng, dt, dx, dz, firstx, firstz):
+        """gfdb_build <db> nchunks nx nz ng dt dx dz firstx firstz (gfdb_build.f90)."""
+        return cls(lib.kiwi_gfdb_create(nx, nz, ng, dt, dx, dz, firstx, firstz))
+
+    @classmethod
+    def read(cls, path):
+        return cls(lib.kiwi_gfdb_read(str(path).encode()))
+
+    def write(self, path):
+        _check(lib.kiwi_gfdb_write(self._h, str(path).encode()))
+
+    def save_array(self, ix, iz, ig, span0, data):
+        d = _f32(data)
+        _check(lib.kiwi_gfdb_save_array(self._h, ix, iz, ig, span0, d.size, _fp(d)))
+
+    def build_ahfull(self, rho, alpha, beta, stf=KIWIBENCH_STF, nfflag=True, ffflag=True, nthreads=0):
+        """gfdb_build_ahfull for every grid node (gfdb_build_ahfull.f90:70-216)."""
+        s = _f32(stf)
+        _check(lib.kiwi_gfdb_build_ahfull(self._h, rho, alpha, beta, _fp(s), s.size, int(nfflag), int(ffflag), nthreads))
+        return self
+
+    def meta(self):
+        nx, nz, ng = C.c_int(), C.c_int(), C.c_int()
+        dt, dx, dz, fx, fz = C.c_float(), C.c_float(), C.c_float(), C.c_float(), C.c_float()
+        nt, ns = C.c_longlong(), C.c_longlong()
+        _check(lib.kiwi_gfdb_meta(self._h, nx, nz, ng, dt, dx, dz, fx, fz, nt, ns))
+        return dict(nx=nx.value, nz=nz.value, ng=ng.value, dt=dt.value, dx=dx.value, dz=dz.value, firstx=fx.value,
+                    firstz=fz.value, ntraces=nt.value, nsamples=ns.value)
+
+    def view(self):
+        """Borrowed flat arrays (span0, len, offset, data); index ((ix-1)*nz + (iz-1))*ng + (ig-1)."""
+        m = self.meta()
+        n = m["nx"] * m["nz"] * m["ng"]
+        ps0, pl, po, pd = c_int_p(), c_int_p(), c_ll_p(), c_float_p()
+        _check(lib.kiwi_gfdb_view(self._h, C.byref(ps0), C.byref(pl), C.byref(po), C.byref(pd)))
+        span0 = np.ctypeslib.as_array(ps0, shape=(n,))
+        length = np.ctypeslib.as_array(pl, shape=(n,))
+        offset = np.ctypeslib.as_array(po, shape=(n,))
+        data = np.ctypeslib.as_array(pd, shape=(max(int(m["nsamples"]), 1),))
+        return span0, length, offset, data
+
+    def close(self):
+        if self._h:
+            lib.kiwi_gfdb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One engine context = the module state of minimizer_engine.f90, resident on one B200."""
+
+    def __init__(self, device=0):
+        h = lib.kiwi_create(device)
+        if not h:
+            raise KiwiError(lib.kiwi_last_error().decode())
+        self._h = C.c_void_p(h)
+        self._db = None
+
+    def close(self):
+        if self._h:
+            lib.kiwi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- setters (one per reference command) --------------------------------------------------------
+    def set_database(self, db):
+        _check(lib.kiwi_set_database(self._h, db._h))
+        self._db = db
+
+    def set_local_interpolation(self, method):
+        if isinstance(method, str):
+            if method not in ("nearest_neighbor", "bilinear"):
+                raise KiwiError("unknown interpolation method: " + method)   # minimizer.f90:170-176
+            method = method == "bilinear"
+        _check(lib.kiwi_set_local_interpolation(self._h, int(bool(method))))
+
+    def set_spacial_undersampling(self, xunder, zunder):
+        _check(lib.kiwi_set_spacial_undersampling(self._h, xunder, zunder))
+
+    def set_receivers(self, lat_deg, lon_deg, depth=None, components=None):
+        lat = np.ascontiguousarray(lat_deg, dtype=np.float64)
+        lon = np.ascontiguousarray(lon_deg, dtype=np.float64)
+        n = lat.size
+        dep = _f32(np.zeros(n) if depth is None else depth)
+        if components is None:
+            components = ["ned"] * n
+        if isinstance(components, str):
+            components = [components] * n
+        arr = (C.c_char_p * n)(*[c.encode() for c in components])
+        _check(lib.kiwi_set_receivers(self._h, n, lat.ctypes.data_as(c_double_p), lon.ctypes.data_as(c_double_p), _fp(dep), arr))
+
+    def set_receivers_file(self, path, has_depth=False):
+        """set_receivers <file> [has_depth]: lat lon [depth] [components] per line (minimizer_engine.f90:165-286)."""
+        lat, lon, dep, comps = [], [], [], []
+        with open(path) as f:
+            for line in f:
+                line = line.split("#")[0].split()
+                if not line:
+                    continue
+                lat.append(float(line[0])); lon.append(float(line[1]))
+                k = 2
+                if has_depth:
+                    dep.append(float(line[2])); k = 3
+                else:
+                    dep.append(0.0)
+                comps.append(line[k] if len(line) > k else "ned")
+        self.set_receivers(lat, lon, dep, comps)
+        return len(lat)
+
+    def switch_receiver(self, ireceiver, state):
+        _check(lib.kiwi_switch_receiver(self._h, ireceiver, int(bool(state))))
+
+    def set_source_location(self, lat_deg, lon_deg, ref_time=0.0):
+        _check(lib.kiwi_set_source_location(self._h, lat_deg, lon_deg, ref_time))
+
+    def set_effective_dt(self, dt):
+        _check(lib.kiwi_set_effective_dt(self._h, dt))
+
+    def set_ref_seismogram(self, ireceiver, icomponent, tbegin, data):
+        d = _f32(data)
+        _check(lib.kiwi_set_ref_seismogram(self._h, ireceiver, icomponent, tbegin, d.size, _fp(d)))
+
+    def set_misfit_method(self, norm):
+        if isinstance(norm, str):
+            if norm not in NORMS:
+                raise KiwiError("unknown norm method: " + norm)
+            norm = NORMS[norm]
+        _check(lib.kiwi_set_misfit_method(self._h, norm))
+
+    def set_misfit_taper(self, ireceiver, x, y):
+        x, y = _f32(x), _f32(y)
+        _check(lib.kiwi_set_misfit_taper(self._h, ireceiver, x.size, _fp(x), _fp(y)))
+
+    def set_misfit_filter(self, x, y, ireceiver=0):
+        x, y = _f32(x), _f32(y)
+        _check(lib.kiwi_set_misfit_filter(self._h, ireceiver, x.size, _fp(x), _fp(y)))
+
+    def set_synthetics_factor(self, factor):
+        _check(lib.kiwi_set_synthetics_factor(self._h, factor))
+
+    def set_floating_shiftrange(self, lo, hi, ireceiver=0):
+        _check(lib.kiwi_set_floating_shiftrange(self._h, ireceiver, lo, hi))
+
+    # ---- evaluation -------------------------------------------------------------------------------
+    @property
+    def nmisfits(self):
+        return lib.kiwi_get_nmisfits(self._h)
+
+    def eval_sources(self, sourcetype, params):
+        """Batched set_source_params + get_misfits: returns (misfits[ns, nmisfits, 2], status[ns])."""
+        if isinstance(sourcetype, str):
+            sourcetype = SOURCE_TYPES[sourcetype]
+        p = _f32(params)
+        if p.ndim == 1:
+            p = p[None, :]
+        ns, nparams = p.shape
+        nm = self.nmisfits
+        out = np.empty((ns, nm, 2), dtype=np.float32)
+        status = np.zeros(ns, dtype=np.int32)
+        _check(lib.kiwi_eval_sources(self._h, sourcetype, ns, nparams, _fp(p), _fp(out), status.ctypes.data_as(c_int_p)))
+        return out, status
+
+    def eval_sources_device(self, sourcetype, params, d_misfits_ptr):
+        """Same, results left at the device address d_misfits_ptr ([ns][nmisfits][2] fp32)."""
+        if isinstance(sourcetype, str):
+            sourcetype = SOURCE_TYPES[sourcetype]
+        p = _f32(params)
+        if p.ndim == 1:
+            p = p[None, :]
+        ns, nparams = p.shape
+        status = np.zeros(ns, dtype=np.int32)
+        _check(lib.kiwi_eval_sources_device(self._h, sourcetype, ns, nparams, _fp(p), C.c_void_p(d_misfits_ptr), status.ctypes.data_as(c_int_p)))
+        return status
+
+    def set_source_params(self, sourcetype, params):
+        if isinstance(sourcetype, str):
+            sourcetype = SOURCE_TYPES[sourcetype]
+        p = _f32(params).ravel()
+        _check(lib.kiwi_set_source_params(self._h, sourcetype, p.size, _fp(p)))
+
+    def get_misfits(self):
+        """(misfit, norm factor) pairs of the enabled receivers, receiver-major (minimizer_engine.f90:1130-1172)."""
+        nm = self.nmisfits
+        out = np.empty((max(nm, 1), 2), dtype=np.float32)
+        n = C.c_int()
+        _check(lib.kiwi_get_misfits(self._h, _fp(out), nm, n))
+        return out[:n.value]
+
+    def get_global_misfit(self):
+        v = C.c_float()
+        _check(lib.kiwi_get_global_misfit(self._h, v))
+        return v.value
+
+    def get_floating_shifts(self):
+        nr = 4096
+        out = np.zeros(nr, dtype=np.int32)
+        n = C.c_int()
+        _check(lib.kiwi_get_floating_shifts(self._h, out.ctypes.data_as(c_int_p), nr, n))
+        return out[:n.value]
+
+    def get_seismogram(self, ireceiver, icomponent, which=0):
+        """In-memory replacement of output_seismograms: (first_index, samples)."""
+        first, n = C.c_int(), C.c_int()
+        cap = 1 << 16
+        buf = np.empty(cap, dtype=np.float32)
+        _check(lib.kiwi_get_seismogram(self._h, ireceiver, icomponent, which, first, n, _fp(buf), cap))
+        return first.value, buf[:min(n.value, cap)].copy()
+
+    # ---- inspection (bit-exact integer contract) --------------------------------------------------------
+    def discretize_source(self, sourcetype, params, cap=1 << 20):
+        if isinstance(sourcetype, str):
+            sourcetype = SOURCE_TYPES[sourcetype]
+        p = _f32(params).ravel()
+        table = np.empty((cap, 10), dtype=np.float32)
+        n = C.c_int()
+        grid = np.zeros(3, dtype=np.int32)
+        _check(lib.kiwi_discretize_source(self._h, sourcetype, p.size, _fp(p), _fp(table), cap, n, grid.ctypes.data_as(c_int_p)))
+        return table[:min(n.value, cap)].copy(), grid, n.value
+
+    def get_indices(self, ireceiver, cap=1 << 20):
+        ix = np.zeros(cap, np.int32); iz = np.zeros(cap, np.int32); its = np.zeros(cap, np.int32)
+        dix = np.zeros(cap, np.float32); diz = np.zeros(cap, np.float32); near = np.zeros(cap, np.int32)
+        n = C.c_int()
+        _check(lib.kiwi_get_indices(self._h, ireceiver, ix.ctypes.data_as(c_int_p), iz.ctypes.data_as(c_int_p), its.ctypes.data_as(c_int_p),
+                                    _fp(dix), _fp(diz), near.ctypes.data_as(c_int_p), cap, n))
+        k = min(n.value, cap)
+        return dict(ix=ix[:k], iz=iz[:k], its=its[:k], dix=dix[:k], diz=diz[:k], near=near[:k])
+
+    def get_spans(self, ireceiver):
+        s = np.zeros(6, np.int32)
+        _check(lib.kiwi_get_spans(self._h, ireceiver, s.ctypes.data_as(c_int_p)))
+        return s
+
+    def trace_span(self, ix, iz, ig):
+        s = np.zeros(2, np.int32)
+        _check(lib.kiwi_trace_span(self._h, ix, iz, ig, s.ctypes.data_as(c_int_p)))
+        return s
+
+    # ---- measurement ---------------------------------------------------------------------------------
+    def last_batch_bytes(self, max_candidates=4):
+        a, b, n = C.c_double(), C.c_double(), C.c_int()
+        _check(lib.kiwi_last_batch_bytes(self._h, max_candidates, a, b, n))
+        return a.value, b.value, n.value
+
+    def last_timing(self):
+        ms = np.zeros(5, np.float32); ln = np.zeros(4, np.int32)
+        _check(lib.kiwi_last_timing(self._h, _fp(ms), ln.ctypes.data_as(c_int_p)))
+        return dict(discretise_ms=float(ms[0]), geometry_ms=float(ms[1]), synthesis_ms=float(ms[2]), misfit_ms=float(ms[3]),
+                    total_ms=float(ms[4]), launches=[int(v) for v in ln])

@@ -1,0 +1,209 @@
+"""ctypes driver of the CPU parity oracle (oracle/_build/liboracle.so).  TEST INFRASTRUCTURE ONLY:
+imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+KAT_PATH = os.path.join(ROOT, "oracle", "_build", "kat")
+
+fp = C.POINTER(C.c_float)
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int)
+lp = C.POINTER(C.c_longlong)
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(LIB_PATH)
+        L.oracle_create.restype = C.c_void_p
+        L.oracle_last_error.restype = C.c_char_p
+        L.oracle_last_error.argtypes = [C.c_void_p]
+        L.oracle_get_global_misfit.restype = C.c_float
+        L.oracle_time_eval.restype = C.c_double
+        for name in ("oracle_destroy", "oracle_set_fresh", "oracle_set_database", "oracle_set_local_interpolation",
+                     "oracle_set_spacial_undersampling", "oracle_set_receivers", "oracle_switch_receiver",
+                     "oracle_set_source_location", "oracle_set_effective_dt", "oracle_set_ref_seismogram",
+                     "oracle_set_misfit_method", "oracle_set_misfit_taper", "oracle_set_misfit_filter",
+                     "oracle_set_synthetics_factor", "oracle_set_floating_shiftrange", "oracle_get_nmisfits",
+                     "oracle_eval_sources", "oracle_get_global_misfit", "oracle_get_floating_shifts", "oracle_get_seismogram",
+                     "oracle_get_probe_spans", "oracle_discretize_source", "oracle_record_indices", "oracle_get_indices",
+                     "oracle_receiver_geometry", "oracle_trace_span", "oracle_time_eval", "oracle_get_strip_spans"):
+            if hasattr(L, name):
+                getattr(L, name).argtypes = None
+        _lib = L
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+SOURCE_TYPES = {"bilateral": 1, "circular": 2, "point_lp": 3, "eikonal": 4, "mt_eikonal": 5, "moment_tensor": 6}
+NORMS = {"l2norm": 1, "l1norm": 2, "ampspec_l2norm": 3, "ampspec_l1norm": 4, "scalar_product": 5, "peak": 6,
+         "floating_l2norm": 7, "floating_l1norm": 8}
+
+
+class OracleError(RuntimeError):
+    pass
+
+
+class OracleEngine:
+    """Same surface as kiwi_b200.Engine, computed by the CPU restatement of the Fortran."""
+
+    def __init__(self, threads=None):
+        self.L = lib()
+        self.h = C.c_void_p(self.L.oracle_create())
+        if threads:
+            self.L.oracle_set_num_threads(C.c_int(threads))
+        self._keep = None
+
+    def close(self):
+        if self.h:
+            self.L.oracle_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise OracleError(self.L.oracle_last_error(self.h).decode())
+
+    def set_database(self, db):
+        m = db.meta()
+        span0, length, offset, data = db.view()
+        self._keep = db
+        self._check(self.L.oracle_set_database(self.h, C.c_int(m["nx"]), C.c_int(m["nz"]), C.c_int(m["ng"]), C.c_float(m["dt"]),
+                                               C.c_float(m["dx"]), C.c_float(m["dz"]), C.c_float(m["firstx"]), C.c_float(m["firstz"]),
+                                               span0.ctypes.data_as(ip), length.ctypes.data_as(ip), offset.ctypes.data_as(lp),
+                                               data.ctypes.data_as(fp)))
+
+    def set_local_interpolation(self, method):
+        if isinstance(method, str):
+            method = method == "bilinear"
+        self._check(self.L.oracle_set_local_interpolation(self.h, C.c_int(int(bool(method)))))
+
+    def set_spacial_undersampling(self, xu, zu):
+        self._check(self.L.oracle_set_spacial_undersampling(self.h, C.c_int(xu), C.c_int(zu)))
+
+    def set_receivers(self, lat_deg, lon_deg, depth=None, components=None):
+        lat = np.ascontiguousarray(lat_deg, dtype=np.float64)
+        lon = np.ascontiguousarray(lon_deg, dtype=np.float64)
+        n = lat.size
+        dep = _f32(np.zeros(n) if depth is None else depth)
+        if components is None:
+            components = ["ned"] * n
+        if isinstance(components, str):
+            components = [components] * n
+        arr = (C.c_char_p * n)(*[c.encode() for c in components])
+        self._check(self.L.oracle_set_receivers(self.h, C.c_int(n), lat.ctypes.data_as(dp), lon.ctypes.data_as(dp), dep.ctypes.data_as(fp), arr))
+
+    def switch_receiver(self, irec, state):
+        self._check(self.L.oracle_switch_receiver(self.h, C.c_int(irec), C.c_int(int(bool(state)))))
+
+    def set_source_location(self, lat, lon, ref_time=0.0):
+        self._check(self.L.oracle_set_source_location(self.h, C.c_float(lat), C.c_float(lon), C.c_double(ref_time)))
+
+    def set_effective_dt(self, dt):
+        self._check(self.L.oracle_set_effective_dt(self.h, C.c_float(dt)))
+
+    def set_ref_seismogram(self, irec, icomp, tbegin, data):
+        d = _f32(data)
+        self._check(self.L.oracle_set_ref_seismogram(self.h, C.c_int(irec), C.c_int(icomp), C.c_float(tbegin), C.c_int(d.size), d.ctypes.data_as(fp)))
+
+    def set_misfit_method(self, norm):
+        if isinstance(norm, str):
+            norm = NORMS[norm]
+        self._check(self.L.oracle_set_misfit_method(self.h, C.c_int(norm)))
+
+    def set_misfit_taper(self, irec, x, y):
+        x, y = _f32(x), _f32(y)
+        self._check(self.L.oracle_set_misfit_taper(self.h, C.c_int(irec), C.c_int(x.size), x.ctypes.data_as(fp), y.ctypes.data_as(fp)))
+
+    def set_misfit_filter(self, x, y, irec=0):
+        x, y = _f32(x), _f32(y)
+        self._check(self.L.oracle_set_misfit_filter(self.h, C.c_int(irec), C.c_int(x.size), x.ctypes.data_as(fp), y.ctypes.data_as(fp)))
+
+    def set_synthetics_factor(self, f):
+        self._check(self.L.oracle_set_synthetics_factor(self.h, C.c_float(f)))
+
+    def set_floating_shiftrange(self, lo, hi, irec=0):
+        self._check(self.L.oracle_set_floating_shiftrange(self.h, C.c_int(irec), C.c_float(lo), C.c_float(hi)))
+
+    @property
+    def nmisfits(self):
+        return self.L.oracle_get_nmisfits(self.h)
+
+    def eval_sources(self, sourcetype, params):
+        if isinstance(sourcetype, str):
+            sourcetype = SOURCE_TYPES[sourcetype]
+        p = _f32(params)
+        if p.ndim == 1:
+            p = p[None, :]
+        ns, npar = p.shape
+        nm = self.nmisfits
+        out = np.zeros((ns, nm, 2), dtype=np.float32)
+        status = np.zeros(ns, dtype=np.int32)
+        self._check(self.L.oracle_eval_sources(self.h, C.c_int(sourcetype), C.c_int(ns), C.c_int(npar), p.ctypes.data_as(fp),
+                                               out.ctypes.data_as(fp), status.ctypes.data_as(ip)))
+        return out, status
+
+    def time_eval(self, sourcetype, params):
+        if isinstance(sourcetype, str):
+            sourcetype = SOURCE_TYPES[sourcetype]
+        p = _f32(params)
+        if p.ndim == 1:
+            p = p[None, :]
+        return self.L.oracle_time_eval(self.h, C.c_int(sourcetype), C.c_int(p.shape[0]), C.c_int(p.shape[1]), p.ctypes.data_as(fp))
+
+    def get_global_misfit(self):
+        return float(self.L.oracle_get_global_misfit(self.h))
+
+    def get_floating_shifts(self):
+        out = np.zeros(4096, np.int32)
+        n = self.L.oracle_get_floating_shifts(self.h, out.ctypes.data_as(ip))
+        return out[:n]
+
+    def get_seismogram(self, irec, icomp, which=0):
+        first, n = C.c_int(), C.c_int()
+        cap = 1 << 16
+        buf = np.empty(cap, np.float32)
+        self._check(self.L.oracle_get_seismogram(self.h, C.c_int(irec), C.c_int(icomp), C.c_int(which), C.byref(first), C.byref(n), buf.ctypes.data_as(fp), C.c_int(cap)))
+        return first.value, buf[:n.value].copy()
+
+    def discretize_source(self, sourcetype, params, cap=1 << 20):
+        if isinstance(sourcetype, str):
+            sourcetype = SOURCE_TYPES[sourcetype]
+        p = _f32(params).ravel()
+        table = np.empty((cap, 10), np.float32)
+        grid = np.zeros(3, np.int32)
+        n = self.L.oracle_discretize_source(self.h, C.c_int(sourcetype), C.c_int(p.size), p.ctypes.data_as(fp), table.ctypes.data_as(fp), C.c_int(cap), grid.ctypes.data_as(ip))
+        if n < 0:
+            raise OracleError(self.L.oracle_last_error(self.h).decode())
+        return table[:n].copy(), grid, n
+
+    def record_indices(self, on=True):
+        self.L.oracle_record_indices(self.h, C.c_int(int(on)))
+
+    def get_indices(self, irec, cap=1 << 20):
+        ix = np.zeros(cap, np.int32); iz = np.zeros(cap, np.int32); its = np.zeros(cap, np.int32)
+        dix = np.zeros(cap, np.float32); diz = np.zeros(cap, np.float32)
+        dist = np.zeros(cap); azi = np.zeros(cap); bazi = np.zeros(cap)
+        n = self.L.oracle_get_indices(self.h, C.c_int(irec), ix.ctypes.data_as(ip), iz.ctypes.data_as(ip), its.ctypes.data_as(ip),
+                                      dix.ctypes.data_as(fp), diz.ctypes.data_as(fp), dist.ctypes.data_as(dp), azi.ctypes.data_as(dp),
+                                      bazi.ctypes.data_as(dp), C.c_int(cap))
+        return dict(ix=ix[:n], iz=iz[:n], its=its[:n], dix=dix[:n], diz=diz[:n], dist=dist[:n], azi=azi[:n], bazi=bazi[:n])
+
+    def trace_span(self, ix, iz, ig):
+        s = np.zeros(2, np.int32); ns = C.c_int()
+        self._check(self.L.oracle_trace_span(self.h, C.c_int(ix), C.c_int(iz), C.c_int(ig), s.ctypes.data_as(ip), C.byref(ns)))
+        return s, ns.value

@@ -1,0 +1,83 @@
+"""Host-side database container, KGF1 file and the analytical full-space builder (fixture generator)."""
+import numpy as np
+import pytest
+
+import scenario as sc
+from kiwi_b200 import Gfdb, KiwiError
+from oracle_lib import OracleEngine
+
+
+def test_save_array_packs_like_trace_pack():
+    # sparse_trace.f90:443-555: leading zeros dropped, exactly one trailing zero kept
+    db = Gfdb.create(2, 2, 10, 0.5, 100, 100, 100, 0)
+    db.save_array(1, 1, 1, 20, [0, 0, 0, 1, 2, 3, 0, 0, 0])
+    db.save_array(1, 1, 2, 5, [0, 0, 0, 0])
+    db.save_array(2, 2, 10, -3, [4, 5])
+    span0, length, offset, data = db.view()
+    assert (span0[0], length[0]) == (23, 4)
+    assert list(data[offset[0]:offset[0] + 4]) == [1, 2, 3, 0]
+    assert (span0[1], length[1]) == (5, 1) and data[offset[1]] == 0
+    i = ((2 - 1) * 2 + (2 - 1)) * 10 + 9
+    assert (span0[i], length[i]) == (-3, 2)
+    assert db.meta()["ntraces"] == 3
+    with pytest.raises(KiwiError, match="out of bounds"):
+        db.save_array(3, 1, 1, 0, [1.0])
+
+
+def test_spans_agree_with_oracle_trace_pack():
+    db = sc.small_db()
+    o = OracleEngine()
+    o.set_database(db)
+    span0, length, _, _ = db.view()
+    m = db.meta()
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        ix, iz, ig = int(rng.integers(1, m["nx"] + 1)), int(rng.integers(1, m["nz"] + 1)), int(rng.integers(1, 11))
+        i = ((ix - 1) * m["nz"] + (iz - 1)) * 10 + (ig - 1)
+        s, _n = o.trace_span(ix, iz, ig)
+        assert (s[0], s[1]) == (span0[i], span0[i] + length[i] - 1)
+
+
+def test_kgf1_round_trip(tmp_path):
+    db = sc.small_db_ng8()
+    path = tmp_path / "db.kgf1"
+    db.write(path)
+    db2 = Gfdb.read(path)
+    assert db.meta() == db2.meta()
+    for a, b in zip(db.view(), db2.view()):
+        assert np.array_equal(a, b)
+    with pytest.raises(KiwiError):
+        Gfdb.read(tmp_path / "missing.kgf1")
+
+
+def test_ahfull_arrival_times_and_far_field_amplitude():
+    """Physics check of the fixture generator (elseis.f90:133-209): P and S onsets at d/alpha, d/beta,
+    far-field P amplitude of the vertical-dip-slip-free component follows 1/(4 pi rho alpha^3 r)."""
+    rho, alpha, beta, dt = 2700.0, 6000.0, 3464.0, 0.1
+    db = Gfdb.create(40, 4, 10, dt, 500.0, 500.0, 500.0, 0.0).build_ahfull(rho, alpha, beta, nfflag=False)
+    span0, length, offset, data = db.view()
+    m = db.meta()
+    for ix in (10, 25, 40):
+        iz = 1
+        x = 500.0 * ix
+        i = ((ix - 1) * m["nz"] + (iz - 1)) * 10 + 0   # g1: radial, source a (mxx=myy-like term)
+        assert length[i] > 1
+        t0 = span0[i] * dt
+        # the stored trace starts where the far-field P pulse becomes non-zero: P travel time plus the
+        # 5 leading samples over which the kiwibench STF (and its central-difference derivative) is zero
+        assert abs(t0 - (x / alpha + 5 * dt)) <= 2 * dt
+        tr = data[offset[i]:offset[i] + length[i]]
+        # far-field P displacement for a ramp STF reaching 1: plateau of d(stf)/dt = 1/(10 dt) per sample
+        nP = int(round((x / beta - x / alpha) / dt))
+        peakP = np.abs(tr[:max(nP - 2, 3)]).max()
+        expect = 1.0 / (4 * np.pi * rho * alpha ** 3 * x) * (1.0 / (10 * dt))
+        assert 0.5 * expect < peakP < 2.0 * expect
+
+
+def test_near_field_static_offset_is_stored_as_last_sample():
+    db = sc.small_db()
+    span0, length, offset, data = db.view()
+    m = db.meta()
+    i = ((8 - 1) * m["nz"] + (6 - 1)) * 10 + 0
+    tr = data[offset[i]:offset[i] + length[i]]
+    assert tr[-1] != 0.0 and abs(tr[-1] - tr[-2]) < 1e-3 * abs(tr[-1])   # static displacement reached

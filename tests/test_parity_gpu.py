@@ -1,0 +1,180 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Bit-exact for discretisation, GF indices, sample shifts and spans; 1e-5 relative (north_star) for
+seismograms and misfits."""
+import numpy as np
+import pytest
+
+import scenario as sc
+from oracle_lib import OracleEngine
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5   # BASELINE.json north_star: "within 1e-5 relative for seismograms and misfits (fp32)"
+
+
+def misfit_tol(mo):
+    """Tolerance for a block [..., 2] of (misfit, norm factor) pairs: 1e-5 relative.  A misfit far
+    below its norm factor is a difference of nearly equal fp32 traces (e.g. the +7 % reference of
+    SURVEY.md 8d evaluated at the true source: m = 0.065 nf); the traces themselves only agree to
+    1e-5 of their size, so below m = 0.1 nf the bound is relative to 0.1 nf instead of m."""
+    return RTOL * np.maximum(np.abs(mo), 0.1 * np.abs(mo[..., 1:2]))
+
+COMPS6 = ["ned", "ar", "d", "neu", "cl", "wsd"]
+
+
+def engines(db, comps, n=6, **kw):
+    from kiwi_b200 import Engine
+    lat, lon, dep = sc.small_receivers(n)
+    g, o = Engine(0), OracleEngine()
+    for e in (g, o):
+        sc.setup(e, db, lat, lon, dep, comps, **kw)
+    return g, o
+
+
+def assert_seis_close(a, b, label):
+    (fa, da), (fb, dbb) = a, b
+    assert fa == fb and da.size == dbb.size, "%s: span differs: gpu [%d,+%d) oracle [%d,+%d)" % (label, fa, da.size, fb, dbb.size)
+    scale = np.abs(dbb).max()
+    assert scale > 0
+    err = np.abs(da - dbb).max() / scale
+    assert err <= RTOL, "%s: max deviation %.3g of peak" % (label, err)
+
+
+@pytest.mark.parametrize("params", [sc.BILAT_SMALL,
+                                    np.array([0, 0, 0, 2500, 1e18, 10, 45, -90, 0, 1500, 1500, 3000, 2500, 0.0], np.float32),
+                                    np.array([1, 100, 100, 2000, 1e18, 200, 89, 10, 90, 0, 0, 0, 3000, 1.0], np.float32)])
+def test_bilateral_discretisation_bit_exact(params):
+    g, o = engines(sc.small_db(), COMPS6)
+    tg, gg, ng = g.discretize_source("bilateral", params)
+    to, go, no = o.discretize_source("bilateral", params)
+    assert ng == no and list(gg) == list(go)
+    assert np.array_equal(tg.view(np.uint32), to.view(np.uint32))
+
+
+def test_moment_tensor_discretisation_bit_exact():
+    g, o = engines(sc.small_db(), COMPS6)
+    tg, gg, ng = g.discretize_source("moment_tensor", sc.MT_SMALL)
+    to, go, no = o.discretize_source("moment_tensor", sc.MT_SMALL)
+    assert ng == no == 4 and gg[2] == go[0]
+    assert np.array_equal(tg.view(np.uint32), to.view(np.uint32))
+
+
+@pytest.mark.parametrize("interp,under", [("bilinear", (1, 1)), ("nearest_neighbor", (1, 1)), ("bilinear", (2, 3))])
+def test_indices_shifts_spans_bit_exact(interp, under):
+    g, o = engines(sc.small_db(), COMPS6, interpolation=interp, under=under)
+    o.record_indices(True)
+    o.eval_sources("bilateral", sc.BILAT_SMALL)   # no references yet: status 1, seismograms are there
+    g.set_source_params("bilateral", sc.BILAT_SMALL)
+    nflag = 0
+    for ir in range(1, 7):
+        ig, io = g.get_indices(ir), o.get_indices(ir)
+        assert ig["ix"].size == io["ix"].size == 204
+        ok = ig["near"] == 0   # device libm vs glibc may differ only where the coordinate sits on a cell edge
+        nflag += int((~ok).sum())
+        for k in ("ix", "iz", "its"):
+            assert np.array_equal(ig[k][ok], io[k][ok]), k
+        assert np.array_equal(ig["its"], io["its"])
+        # dix/diz derive from real(dist): equal unless fp64 libm differs in the last bits (SURVEY.md 7 hard part 1)
+        assert np.allclose(ig["dix"][ok], io["dix"][ok], rtol=0, atol=2e-4)
+        assert np.allclose(ig["diz"][ok], io["diz"][ok], rtol=0, atol=0)
+        for ic in range(1, len(COMPS6[ir - 1]) + 1):
+            fg, dg = g.get_seismogram(ir, ic)
+            fo, do = o.get_seismogram(ir, ic)
+            assert (fg, dg.size) == (fo, do.size), "span of receiver %d component %d" % (ir, ic)
+    assert nflag < 10
+
+
+@pytest.mark.parametrize("stype,params", [("bilateral", sc.BILAT_SMALL), ("moment_tensor", sc.MT_SMALL)])
+@pytest.mark.parametrize("interp", ["bilinear", "nearest_neighbor"])
+def test_seismograms(stype, params, interp):
+    g, o = engines(sc.small_db(), COMPS6, interpolation=interp)
+    o.eval_sources(stype, params)
+    g.set_source_params(stype, params)
+    for ir in range(1, 7):
+        for ic in range(1, len(COMPS6[ir - 1]) + 1):
+            for which in (0, 1):
+                assert_seis_close(g.get_seismogram(ir, ic, which), o.get_seismogram(ir, ic, which), "rcv %d comp %d which %d" % (ir, ic, which))
+
+
+def test_seismograms_ng8():
+    g, o = engines(sc.small_db_ng8(), COMPS6)
+    o.eval_sources("bilateral", sc.BILAT_SMALL)
+    g.set_source_params("bilateral", sc.BILAT_SMALL)
+    for ir in range(1, 7):
+        for ic in range(1, len(COMPS6[ir - 1]) + 1):
+            assert_seis_close(g.get_seismogram(ir, ic), o.get_seismogram(ir, ic), "rcv %d comp %d" % (ir, ic))
+
+
+def _candidates():
+    p = np.tile(sc.BILAT_SMALL, (7, 1))
+    p[1, 5] += 15; p[2, 6] -= 20; p[3, 7] += 40; p[4, 3] += 500; p[5, 9] += 800; p[6, 4] *= 1.3
+    p[6, 13] = 0.2
+    return p
+
+
+@pytest.mark.parametrize("norm", ["l2norm", "l1norm", "scalar_product", "peak"])
+@pytest.mark.parametrize("taper", [False, True])
+def test_misfits_batched(norm, taper):
+    g, o = engines(sc.small_db(), COMPS6)
+    ncomps = [len(c) for c in COMPS6]
+    o.eval_sources("bilateral", sc.BILAT_SMALL)
+    sc.set_refs_from(o, [g, o], ncomps)
+    for e in (g, o):
+        e.set_misfit_method(norm)
+        if taper:
+            for ir in range(1, 7):
+                e.set_misfit_taper(ir, [1.0, 1.6, 4.0, 5.2], [0, 1, 1, 0])
+    p = _candidates()
+    mg, sg = g.eval_sources("bilateral", p)
+    mo, so = o.eval_sources("bilateral", p)
+    assert np.array_equal(sg, so) and not sg.any()
+    assert mg.shape == mo.shape == (7, 14, 2)
+    assert np.all(np.abs(mg - mo) <= misfit_tol(mo)), np.abs((mg - mo) / misfit_tol(mo)).max()
+    # ns = 1 pair with the reference's names gives the same numbers as the batch
+    g.set_source_params("bilateral", p[3])
+    assert np.array_equal(g.get_misfits(), mg[3])
+    from kiwi_b200 import global_misfits
+    gm = global_misfits(mg)
+    for i in (0, 3):
+        o.eval_sources("bilateral", p[i])
+        assert abs(gm[i] - o.get_global_misfit()) <= 1e-5 * max(abs(o.get_global_misfit()), 1e-3)
+
+
+def test_disabled_receivers_and_moment_tensor_batch():
+    g, o = engines(sc.small_db(), COMPS6)
+    ncomps = [len(c) for c in COMPS6]
+    o.eval_sources("moment_tensor", sc.MT_SMALL)
+    sc.set_refs_from(o, [g, o], ncomps)
+    for e in (g, o):
+        e.switch_receiver(2, False); e.switch_receiver(5, False)
+        e.set_misfit_method("l1norm")
+    assert g.nmisfits == o.nmisfits == 10
+    p = np.tile(sc.MT_SMALL, (5, 1))
+    p[1, 4:10] *= -0.5; p[2, 1] += 400; p[3, 3] -= 600; p[4, 10] = 0.25
+    mg, sg = g.eval_sources("moment_tensor", p)
+    mo, so = o.eval_sources("moment_tensor", p)
+    assert not sg.any() and not so.any()
+    assert np.all(np.abs(mg - mo) <= misfit_tol(mo))
+
+
+def test_error_behaviour():
+    from kiwi_b200 import Engine, KiwiError
+    e = Engine(0)
+    with pytest.raises(KiwiError, match="no database set"):
+        e.set_receivers([30.1], [70.1], [0], ["ned"])
+    e.set_database(sc.small_db())
+    with pytest.raises(KiwiError, match="no receivers set"):
+        e.eval_sources("bilateral", sc.BILAT_SMALL)
+    lat, lon, dep = sc.small_receivers(2)
+    with pytest.raises(KiwiError, match="initializing receiver failed"):
+        e.set_receivers(lat, lon, dep, ["ns", "d"])
+    e.set_receivers(lat, lon, dep, ["ned", "d"])
+    with pytest.raises(KiwiError, match="no source location set"):
+        e.eval_sources("bilateral", sc.BILAT_SMALL)
+    e.set_source_location(*sc.ORIGIN, 0.0)
+    with pytest.raises(KiwiError, match="no reference seismograms set"):
+        e.eval_sources("bilateral", sc.BILAT_SMALL)
+    with pytest.raises(KiwiError, match="no source parameters set"):
+        e.get_misfits()
+    with pytest.raises(KiwiError, match="wrong number"):
+        e.eval_sources("bilateral", sc.BILAT_SMALL[:5])
