@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Benchmark of the Kiwi source-inversion hot path on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|small] [--batch B]
+    python bench.py --impl reference ...      # the CPU restatement of the reference on the host cores
+
+A "step" is one batched evaluation (kiwi_eval_sources) of B candidate bilateral sources: source
+discretisation -> synthesis at all receivers -> scaling -> misfits.  Metric: source evaluations per
+second, whole job over all ranks.  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "source evals/sec (synth+misfit, all receivers)"
+UNIT = "evals/s"
+
+WORKLOADS = {
+    # Izmit bilateral rupture, ~1e4 sub-sources, 200 x 3 components,
+    # bench-L analytical full-space database (HBM resident, > L2), time-domain L2 misfit
+    "c3": dict(db="bench-L", nx=2000, nz=150, dx=100.0, dz=200.0, nrcv=200, effective_dt=0.35, dmin=45e3, dmax=150e3,
+               norm="l2norm", batch=32, cpu_sample=2),
+    # quick functional run (kiwibench-size pieces)
+    "small": dict(db="bench-L/8", nx=1000, nz=60, dx=100.0, dz=400.0, nrcv=24, effective_dt=0.5, dmin=45e3, dmax=55e3,
+                  norm="l2norm", batch=8, cpu_sample=2),
+}
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for nme, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_db(w, rank, world, barrier):
+    """rank 0 builds the analytical database once and shares it through a KGF1 file."""
+    from kiwi_b200 import Gfdb, synthetic
+    if world == 1:
+        return synthetic.bench_l_db(w["nx"], w["nz"], w["dx"], w["dz"])
+    path = "/tmp/kiwi_bench_%d_%d_%d.kgf1" % (w["nx"], w["nz"], os.getppid())
+    if rank == 0:
+        db = synthetic.bench_l_db(w["nx"], w["nz"], w["dx"], w["dz"])
+        db.write(path)
+    barrier()
+    if rank != 0:
+        db = Gfdb.read(path)
+    barrier()
+    if rank == 0:
+        try:
+            os.remove(path)
+        except OSError:
+            pass
+    return db
+
+
+def configure(eng, db, w, rlat, rlon, rdep):
+    from kiwi_b200 import synthetic  # noqa: F401
+    eng.set_database(db)
+    eng.set_local_interpolation("bilinear")
+    eng.set_receivers(rlat, rlon, rdep, ["ned"] * len(rlat))
+    eng.set_source_location(30.0, 70.0, 0.0)
+    eng.set_effective_dt(w["effective_dt"])
+    eng.set_misfit_method(w["norm"])
+
+
+def set_references(src, engines, nrcv, dt, scale=1.07):
+    """reference = synthetics of the base source with +7 % moment."""
+    for ir in range(1, nrcv + 1):
+        for ic in range(1, 4):
+            first, data = src.get_seismogram(ir, ic, 1)
+            REFS[(ir, ic)] = (first, data * np.float32(scale))
+            for e in engines:
+                e.set_ref_seismogram(ir, ic, (first - 1) * dt, REFS[(ir, ic)][1])
+
+
+REFS = {}
+
+
+def copy_references(src_unused, dst, nrcv, dt):
+    """give `dst` exactly the reference traces that set_references() handed out last"""
+    for (ir, ic), (first, data) in REFS.items():
+        dst.set_ref_seismogram(ir, ic, (first - 1) * dt, data)
+
+
+def run_reference_arm(args, w, rank):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.  The Fortran
+    cannot be built here (no Fortran compiler, HDF5, FFTW: SURVEY.md 8c), so this is the line-by-line
+    C++ restatement (oracle/), OpenMP over receivers exactly where the reference has its only
+    OpenMP loop (minimizer_engine.f90:893-903)."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import OracleEngine, lib as olib
+    from kiwi_b200 import synthetic
+    ncores = os.cpu_count() or 1
+    db = synthetic.bench_l_db(w["nx"], w["nz"], w["dx"], w["dz"])
+    rlat, rlon, rdep = synthetic.receivers(w["nrcv"], (30.0, 70.0), w["dmin"], w["dmax"])
+    o = OracleEngine(threads=ncores)
+    configure(o, db, w, rlat, rlon, rdep)
+    o.eval_sources("bilateral", synthetic.IZMIT)
+    set_references(o, [o], w["nrcv"], db.meta()["dt"])
+    sample = max(1, min(args.batch, w["cpu_sample"]))
+    cands = synthetic.bilateral_sweep(max(args.batch, 32))[:sample]
+    for _ in range(min(args.warmup, 1)):
+        o.time_eval("bilateral", cands[:1])
+    t = 0.0
+    for _ in range(args.steps):
+        t += o.time_eval("bilateral", cands)
+    value = sample * args.steps / t
+    threads = olib().oracle_max_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(w, args, sample),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "%d candidate(s) per step of the same workload; restated CPU path (oracle/), not the Fortran binary" % sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(w, args, batch):
+    return {"workload": "C3/C5 bilateral (Izmit, minimizer.f90:1632) ~1e4 sub-sources x %d receivers x ned, %s GFDB %dx%dx10, %s, "
+                        "bilinear, candidates swept in strike/dip/rake/depth/length" % (w["nrcv"], w["db"], w["nx"], w["nz"], w["norm"]),
+            "name": args.workload, "candidates_per_step": batch, "receivers": w["nrcv"], "effective_dt": w["effective_dt"],
+            "cache": "database %s exceeds L2; every candidate streams its own node set (no L2 flush needed)" % w["db"]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="kiwi_b200", choices=["kiwi_b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="candidates per step and per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.batch <= 0:
+        args.batch = w["batch"]
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+
+    if args.impl == "reference":
+        run_reference_arm(args, w, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    import kiwi_b200
+    from kiwi_b200 import synthetic
+    db = make_db(w, rank, world, barrier)
+    dt = db.meta()["dt"]
+    rlat, rlon, rdep = synthetic.receivers(w["nrcv"], (30.0, 70.0), w["dmin"], w["dmax"])
+    eng = kiwi_b200.Engine(local)
+    configure(eng, db, w, rlat, rlon, rdep)
+    eng.set_source_params("bilateral", synthetic.IZMIT)
+    set_references(eng, [eng], w["nrcv"], dt)
+    nm = eng.nmisfits
+    B = args.batch
+    # candidates are block-partitioned over the ranks; weak scaling: B per GPU
+    allc = synthetic.bilateral_sweep(max(B * world, 32))
+    mine = np.ascontiguousarray(allc[rank * B:(rank + 1) * B])
+    d_out = torch.empty((B, nm, 2), dtype=torch.float32, device="cuda")
+    gathered = torch.empty((world * B, nm, 2), dtype=torch.float32, device="cuda") if world > 1 else None
+
+    def step_device():
+        st = eng.eval_sources_device("bilateral", mine, d_out.data_ptr())
+        t = eng.last_timing()
+        if world > 1:   # only the small misfit block crosses NVLink
+            dist.all_gather_into_tensor(gathered, d_out)
+        return st, t
+
+    for _ in range(max(args.warmup, 3)):
+        st, _t = step_device()
+    assert not st.any(), "candidate evaluation failed: %s" % st
+    b_alg, b_log, nsamp, nskip = eng.last_batch_bytes(4)
+    assert nskip == 0, "%d centroids fell outside the database" % nskip
+
+    # ---- timed region 1: device-resident results (value) -----------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms = synth_ms = 0.0
+    launches = nsynth = 0
+    stage = np.zeros(4)
+    for _ in range(args.steps):
+        st, t = step_device()
+        dev_ms += t["total_ms"]; synth_ms += t["synthesis_ms"]; launches += sum(t["launches"]); nsynth += t["launches"][2]
+        stage += [t["discretise_ms"], t["geometry_ms"], t["synthesis_ms"], t["misfit_ms"]]
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    tt = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_ms_max, wall_ms_max = [float(v) for v in tt.cpu()]
+    # whole-job throughput, K steps timed with CUDA events on the engine's stream around each call
+    # (device work + per-step table uploads), max over ranks
+    value = world * B * args.steps / (dev_ms_max * 1e-3)
+
+    # ---- timed region 2: end to end through the C ABI with host buffers (e2e) ----------------------------
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        mis, st = eng.eval_sources("bilateral", mine)
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    te = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(te.cpu()[0])
+    h2d = int(mine.nbytes + B * (36 + 100) + 7 * 8 * B)     # params + CandDev/BilatCand tables + STF taps
+    d2h = int(mis.nbytes + st.nbytes + 4)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_kind = peaks()
+    evals_per_launch = B * args.steps / max(nsynth, 1)
+    ms_per_launch = synth_ms / max(nsynth, 1)
+    achieved = b_alg * evals_per_launch / (ms_per_launch * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.workload)
+        except Exception:
+            traffic = None
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(w, args, B),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_synth", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_kind": peak_kind, "traffic": traffic, "algorithmic_bytes_per_eval": b_alg, "logical_bytes_per_eval": b_log,
+                         "evals_per_launch": evals_per_launch, "ms_per_launch": ms_per_launch},
+            "stage_ms_per_step": {k: float(v) / args.steps for k, v in zip(["discretise", "geometry", "synthesis", "misfit"], stage)},
+            "wall_ms_per_step": wall_ms_max / args.steps}
+
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(w, db, rlat, rlon, rdep, dt, mine, mis)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(w, db, rlat, rlon, rdep, dt, cands, gpu_misfits):
+    """The oracle (restated CPU path) timed on the host cores on a bounded sample of the same
+    workload, and used as the checker of the batch just measured."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import OracleEngine, lib as olib
+    from kiwi_b200 import synthetic
+    ncores = os.cpu_count() or 1
+    o = OracleEngine(threads=ncores)
+    configure(o, db, w, rlat, rlon, rdep)
+    copy_references(None, o, w["nrcv"], dt)
+    n = max(1, min(w["cpu_sample"], cands.shape[0]))
+    t0 = time.perf_counter()
+    mo, so = o.eval_sources("bilateral", cands[:n])
+    t = time.perf_counter() - t0
+    # the same sample with the strip arithmetic of the restatement carried in double (oracle -DKO_WIDE):
+    # separates the GPU's deviation from the fp32 reference path's own accumulation noise
+    ow = OracleEngine(threads=ncores, wide=True)
+    configure(ow, db, w, rlat, rlon, rdep)
+    copy_references(None, ow, w["nrcv"], dt)
+    mw, _ = ow.eval_sources("bilateral", cands[:n])
+
+    def dev(a, b):
+        return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 0.1 * np.abs(b[..., 1:2]))))
+    d32, dw, d32w = dev(gpu_misfits[:n], mo), dev(gpu_misfits[:n], mw), dev(mo, mw)
+    return {"value": n / t, "unit": UNIT, "cores": int(olib().oracle_max_threads()), "kind": "port",
+            "sample": "first %d candidate(s) of the step, %.1f s; restated CPU path (oracle/), OpenMP over receivers" % (n, t),
+            "parity": {"gpu_vs_fp32_path": d32, "gpu_vs_double_accumulation": dw, "fp32_path_vs_double_accumulation": d32w, "tol": 1e-5,
+                       "ok": bool(dw <= 1e-5 and d32 <= max(1e-5, 2.0 * d32w)),
+                       "note": "relative misfit deviation; at ~1e4 sub-sources the fp32 reference path's own sequential "
+                               "accumulation noise exceeds 1e-5, so the bar is 1e-5 against the double-accumulated "
+                               "restatement and 2x the reference path's own noise against the fp32 restatement"}}
+
+
+if __name__ == "__main__":
+    main()

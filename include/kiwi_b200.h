@@ -183,8 +183,11 @@ int kiwi_trace_span(kiwi_ctx* ctx, int ix, int iz, int ig, int* span2);
  * section 8d), averaged over the first min(max_candidates, chunk) candidates of its last chunk:
  * b_alg = distinct GF nodes per (candidate, receiver) x components used x stored window length x 4 B
  *         + one write of each synthetic + one read of each reference;
- * b_log = every (centroid, corner, component) trace counted once per use (what the reference streams). */
-int kiwi_last_batch_bytes(kiwi_ctx* ctx, int max_candidates, double* b_alg, double* b_log, int* nsampled);
+ * b_log = every (centroid, corner, component) trace counted once per use (what the reference streams).
+ * nskipped: centroids of the sampled candidates dropped because a GF node was outside the database
+ * (seismogram.f90:172). */
+int kiwi_last_batch_bytes(kiwi_ctx* ctx, int max_candidates, double* b_alg, double* b_log, int* nsampled,
+                          long long* nskipped);
 /* device time [ms] of the stages of the last kiwi_eval_sources call, measured with CUDA events on
  * the engine's stream: [0] discretise, [1] geometry/index pre-pass, [2] synthesis, [3] misfit,
  * [4] whole call incl. H2D/D2H; launches[0..3]: kernel launches per stage */

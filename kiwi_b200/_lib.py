@@ -55,7 +55,7 @@ SIGNATURES = {
     "kiwi_get_indices": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_int_p, c_int_p, c_float_p, c_float_p, c_int_p, C.c_int, c_int_p]),
     "kiwi_get_spans": (C.c_int, [C.c_void_p, C.c_int, c_int_p]),
     "kiwi_trace_span": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_int_p]),
-    "kiwi_last_batch_bytes": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, c_int_p]),
+    "kiwi_last_batch_bytes": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, c_int_p, c_ll_p]),
     "kiwi_last_timing": (C.c_int, [C.c_void_p, c_float_p, c_int_p]),
 }
 

@@ -620,14 +620,14 @@ int kiwi_set_ref_seismogram(kiwi_ctx* c, int ireceiver, int icomponent, float tb
     h.ref[k].assign(data, data + n);
     h.ref_ds0[k] = ibeg + 1; h.ref_ds1[k] = ibeg + n;
     h.has_ref[k] = true;
-    c->receivers_dirty = true; c->src_dirty = true;
+    c->receivers_dirty = true; c->src_misfits.clear();
     return 0;
 }
 
 int kiwi_set_misfit_method(kiwi_ctx* c, int norm_id) {
     if (!c) return kiwi_set_error("null context");
     if (norm_id < 1 || norm_id > 8) return kiwi_set_error("unknown norm method");
-    c->misfit_method = norm_id; c->src_dirty = true;
+    c->misfit_method = norm_id; c->src_misfits.clear();
     return 0;
 }
 
@@ -638,7 +638,7 @@ int kiwi_set_misfit_taper(kiwi_ctx* c, int ireceiver, int n, const float* x, con
     if (n < 2) return kiwi_set_error("a taper needs at least two points");
     HostReceiver& h = c->rcv[ireceiver - 1];
     h.taper_x.assign(x, x + n); h.taper_y.assign(y, y + n);
-    c->receivers_dirty = true; c->src_dirty = true;
+    c->receivers_dirty = true; c->src_misfits.clear();
     return 0;
 }
 
@@ -651,13 +651,13 @@ int kiwi_set_misfit_filter(kiwi_ctx* c, int ireceiver, int n, const float* x, co
         if (ireceiver != 0 && i != ireceiver - 1) continue;
         c->rcv[i].filter_x.assign(x, x + n); c->rcv[i].filter_y.assign(y, y + n);
     }
-    c->receivers_dirty = true; c->src_dirty = true;
+    c->receivers_dirty = true; c->src_misfits.clear();
     return 0;
 }
 
 int kiwi_set_synthetics_factor(kiwi_ctx* c, float factor) {
     if (!c) return kiwi_set_error("null context");
-    c->syn_factor = factor; c->src_dirty = true;
+    c->syn_factor = factor; c->src_misfits.clear();
     return 0;
 }
 
@@ -670,7 +670,7 @@ int kiwi_set_floating_shiftrange(kiwi_ctx* c, int ireceiver, float lo, float hi)
         if (ireceiver != 0 && i != ireceiver - 1) continue;
         c->rcv[i].fs0 = r0; c->rcv[i].fs1 = r1;
     }
-    c->receivers_dirty = true; c->src_dirty = true;
+    c->receivers_dirty = true; c->src_misfits.clear();
     return 0;
 }
 
@@ -844,7 +844,7 @@ int kiwi_trace_span(kiwi_ctx* c, int ix, int iz, int ig, int* span2) {
     return 0;
 }
 
-int kiwi_last_batch_bytes(kiwi_ctx* c, int max_candidates, double* b_alg, double* b_log, int* nsampled) {
+int kiwi_last_batch_bytes(kiwi_ctx* c, int max_candidates, double* b_alg, double* b_log, int* nsampled, long long* nskipped) {
     if (!c) return kiwi_set_error("null context");
     CU_OK(cudaSetDevice(c->device));
     const kiwi_ctx::Last& L = c->last;
@@ -852,6 +852,7 @@ int kiwi_last_batch_bytes(kiwi_ctx* c, int max_candidates, double* b_alg, double
     const int ns = std::max(1, std::min(max_candidates, L.n));
     const int ng = c->db.ng;
     double alg = 0., logi = 0.;
+    long long skipped = 0;
     std::vector<GeoRec> recs(L.rec_stride);
     std::vector<PairHdr> hdrs((size_t)ns * L.nrcv);
     CU_OK(cudaMemcpy(hdrs.data(), c->d_hdrs.p, sizeof(PairHdr) * hdrs.size(), cudaMemcpyDeviceToHost));
@@ -866,7 +867,7 @@ int kiwi_last_batch_bytes(kiwi_ctx* c, int max_candidates, double* b_alg, double
             seen.clear();
             for (int ig = 0; ig < cd.ngroups; ig++) {
                 const GeoRec& r = recs[ig];
-                if (r.flags & GEO_SKIP) continue;
+                if (r.flags & GEO_SKIP) { skipped += cd.nt; continue; }
                 const int nco = (r.flags & GEO_SINGLE) ? 1 : 4;
                 const int ix2 = r.ix1 + (c->interpolate ? c->xunder : 1), iz2 = r.iz1 + (c->interpolate ? c->zunder : 1);
                 const int cx[4] = {r.ix1, r.ix1, ix2, ix2}, cz[4] = {r.iz1, iz2, r.iz1, iz2};
@@ -898,6 +899,7 @@ int kiwi_last_batch_bytes(kiwi_ctx* c, int max_candidates, double* b_alg, double
     if (b_alg) *b_alg = alg / ns;
     if (b_log) *b_log = logi / ns;
     if (nsampled) *nsampled = ns;
+    if (nskipped) *nskipped = skipped;
     return 0;
 }
 

@@ -311,9 +311,10 @@ class Engine:
 
     # ---- measurement ---------------------------------------------------------------------------------
     def last_batch_bytes(self, max_candidates=4):
-        a, b, n = C.c_double(), C.c_double(), C.c_int()
-        _check(lib.kiwi_last_batch_bytes(self._h, max_candidates, a, b, n))
-        return a.value, b.value, n.value
+        """(B_alg, B_log) bytes per evaluation, candidates sampled, centroids skipped."""
+        a, b, n, k = C.c_double(), C.c_double(), C.c_int(), C.c_longlong()
+        _check(lib.kiwi_last_batch_bytes(self._h, max_candidates, a, b, n, k))
+        return a.value, b.value, n.value, k.value
 
     def last_timing(self):
         ms = np.zeros(5, np.float32); ln = np.zeros(4, np.int32)

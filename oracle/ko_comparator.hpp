@@ -36,13 +36,13 @@ static inline void fft_c(std::vector<cfloat>& a, int sign) {
         }
     }
 }
-static inline void fft_r2c(const float* in, int n, std::vector<cfloat>& out) {
+static inline void fft_r2c(const sreal* in, int n, std::vector<cfloat>& out) {
     std::vector<cfloat> a(n);
-    for (int i = 0; i < n; i++) a[i] = cfloat(in[i], 0.f);
+    for (int i = 0; i < n; i++) a[i] = cfloat((float)in[i], 0.f);
     if (n > 1) fft_c(a, -1);
     out.assign(a.begin(), a.begin() + n / 2 + 1);
 }
-static inline void fft_c2r(const std::vector<cfloat>& in, int n, float* out) {
+static inline void fft_c2r(const std::vector<cfloat>& in, int n, sreal* out) {
     std::vector<cfloat> a(n);
     for (int k = 0; k <= n / 2; k++) a[k] = in[k];
     for (int k = n / 2 + 1; k < n; k++) a[k] = std::conj(in[n - k]);
@@ -228,47 +228,55 @@ static inline void update_array_filtered(Probe& p) { update_spectrum_filtered(p)
 
 // norm functions, :627-697: element arithmetic in fp32, sum in fp64, result fp32
 struct Norm2 { virtual float f(const float* a, const float* b, int n, float dt, float fa, float fb) const = 0; virtual ~Norm2() {} };
-static inline float scalar_product_2(const float* a, const float* b, int n, float dt, float fa, float fb) {
+template <class T>
+static inline float scalar_product_2(const T* a, const T* b, int n, float dt, float fa, float fb) {
     (void)dt; double s = 0.;
     if (fa == 1.f && fb == 1.f) for (int i = 0; i < n; i++) s += (double)(a[i] * b[i]);
     else for (int i = 0; i < n; i++) s += (double)(a[i] * fa * b[i] * fb);
     return (float)s;
 }
-static inline float l1norm_func(const float* a, const float* b, int n, float dt, float fa, float fb) {
+template <class T>
+static inline float l1norm_func(const T* a, const T* b, int n, float dt, float fa, float fb) {
     double s = 0.;
-    if (fa == 1.f && fb == 1.f) for (int i = 0; i < n; i++) s += (double)fabsf(a[i] - b[i]);
-    else for (int i = 0; i < n; i++) s += (double)fabsf(fa * a[i] - fb * b[i]);
+    if (fa == 1.f && fb == 1.f) for (int i = 0; i < n; i++) s += (double)std::abs(a[i] - b[i]);
+    else for (int i = 0; i < n; i++) s += (double)std::abs(fa * a[i] - fb * b[i]);
     return (float)((double)dt * s);
 }
-static inline float l2norm_func(const float* a, const float* b, int n, float dt, float fa, float fb) {
+template <class T>
+static inline float l2norm_func(const T* a, const T* b, int n, float dt, float fa, float fb) {
     double s = 0.;
     if (fa == 1.f && fb == 1.f) for (int i = 0; i < n; i++) { double d = (double)(a[i] - b[i]); s += d * d; }
     else for (int i = 0; i < n; i++) { double d = (double)(fa * a[i] - fb * b[i]); s += d * d; }
     return (float)sqrt((double)dt * s);
 }
-static inline float maxabs_func(const float* a, const float* b, int n, float dt, float fa, float fb) {
+template <class T>
+static inline float maxabs_func(const T* a, const T* b, int n, float dt, float fa, float fb) {
     (void)dt; double m = -std::numeric_limits<double>::max();
     for (int i = 0; i < n; i++) { double x = (double)(fa * a[i]), y = (double)(fb * b[i]); m = std::max(m, sqrt(x * x + y * y)); }
     return (float)m;
 }
-static inline float scalar_product_1(const float* a, int n, float dt, float fa) {
+template <class T>
+static inline float scalar_product_1(const T* a, int n, float dt, float fa) {
     (void)dt; double s = 0.; for (int i = 0; i < n; i++) s += (double)(a[i] * a[i]);
     return fa * fa * (float)s;
 }
-static inline float l1norm_func_1(const float* a, int n, float dt, float fa) {
-    double s = 0.; for (int i = 0; i < n; i++) s += (double)fabsf(a[i]);
+template <class T>
+static inline float l1norm_func_1(const T* a, int n, float dt, float fa) {
+    double s = 0.; for (int i = 0; i < n; i++) s += (double)std::abs(a[i]);
     return fa * (float)((double)dt * s);
 }
-static inline float l2norm_func_1(const float* a, int n, float dt, float fa) {
+template <class T>
+static inline float l2norm_func_1(const T* a, int n, float dt, float fa) {
     double s = 0.; for (int i = 0; i < n; i++) { double d = (double)a[i]; s += d * d; }
     return fa * (float)sqrt((double)dt * s);
 }
-static inline float maxabs_func_1(const float* a, int n, float dt, float fa) {
-    (void)dt; float m = -std::numeric_limits<float>::max(); for (int i = 0; i < n; i++) m = std::max(m, fabsf(a[i]));
+template <class T>
+static inline float maxabs_func_1(const T* a, int n, float dt, float fa) {
+    (void)dt; float m = -std::numeric_limits<float>::max(); for (int i = 0; i < n; i++) m = std::max(m, (float)std::abs(a[i]));
     return fa * m;
 }
-typedef float (*normfn2)(const float*, const float*, int, float, float, float);
-typedef float (*normfn1)(const float*, int, float, float);
+typedef float (*normfn2)(const sreal*, const sreal*, int, float, float, float);
+typedef float (*normfn1)(const sreal*, int, float, float);
 
 static long g_warn_empty_region = 0;
 
@@ -310,7 +318,9 @@ static inline float probe_norm_timedomain(Probe& a, normfn1 fn) {
     return fn(&a.array.d[span[0] - a.array.lo], n, a.dt, a.factor);
 }
 // :861-886
-static inline float probes_norm_frequencydomain(Probe& a, Probe& b, normfn2 fn) {
+typedef float (*normfn2f)(const float*, const float*, int, float, float, float);
+typedef float (*normfn1f)(const float*, int, float, float);
+static inline float probes_norm_frequencydomain(Probe& a, Probe& b, normfn2f fn) {
     probes_adjust_spans(a, b);
     if (a.filter.defined && b.filter.defined) {
         update_spectrum_filtered(a); update_spectrum_filtered(b);
@@ -320,7 +330,7 @@ static inline float probes_norm_frequencydomain(Probe& a, Probe& b, normfn2 fn) 
     return fn(a.amp_spectrum.data(), b.amp_spectrum.data(), (int)a.amp_spectrum.size(), a.df, a.factor, b.factor);
 }
 // :888-909
-static inline float probe_norm_frequencydomain(Probe& a, normfn1 fn) {
+static inline float probe_norm_frequencydomain(Probe& a, normfn1f fn) {
     if (a.filter.defined) { update_spectrum_filtered(a); return fn(a.amp_spectrum_filtered.data(), (int)a.amp_spectrum_filtered.size(), a.df, a.factor); }
     update_spectrum(a);
     return fn(a.amp_spectrum.data(), (int)a.amp_spectrum.size(), a.df, a.factor);
@@ -328,24 +338,24 @@ static inline float probe_norm_frequencydomain(Probe& a, normfn1 fn) {
 // :911-953
 static inline float probes_norm(Probe& a, Probe& b, int method = L2NORM) {
     switch (method) {
-        case L2NORM: return probes_norm_timedomain(a, b, l2norm_func);
-        case L1NORM: return probes_norm_timedomain(a, b, l1norm_func);
-        case SCALAR_PRODUCT: return probes_norm_timedomain(a, b, scalar_product_2);
-        case AMPSPEC_L2NORM: return probes_norm_frequencydomain(a, b, l2norm_func);
-        case AMPSPEC_L1NORM: return probes_norm_frequencydomain(a, b, l1norm_func);
-        case PEAK: return probes_norm_timedomain(a, b, maxabs_func);
+        case L2NORM: return probes_norm_timedomain(a, b, l2norm_func<sreal>);
+        case L1NORM: return probes_norm_timedomain(a, b, l1norm_func<sreal>);
+        case SCALAR_PRODUCT: return probes_norm_timedomain(a, b, scalar_product_2<sreal>);
+        case AMPSPEC_L2NORM: return probes_norm_frequencydomain(a, b, l2norm_func<float>);
+        case AMPSPEC_L1NORM: return probes_norm_frequencydomain(a, b, l1norm_func<float>);
+        case PEAK: return probes_norm_timedomain(a, b, maxabs_func<sreal>);
     }
     fprintf(stderr, "probes_norm(): unknown norm method\n"); abort();
 }
 // :955-996
 static inline float probe_norm(Probe& a, int method = L2NORM) {
     switch (method) {
-        case L2NORM: return probe_norm_timedomain(a, l2norm_func_1);
-        case L1NORM: return probe_norm_timedomain(a, l1norm_func_1);
-        case SCALAR_PRODUCT: return probe_norm_timedomain(a, scalar_product_1);
-        case AMPSPEC_L2NORM: return probe_norm_frequencydomain(a, l2norm_func_1);
-        case AMPSPEC_L1NORM: return probe_norm_frequencydomain(a, l1norm_func_1);
-        case PEAK: return probe_norm_timedomain(a, maxabs_func_1);
+        case L2NORM: return probe_norm_timedomain(a, l2norm_func_1<sreal>);
+        case L1NORM: return probe_norm_timedomain(a, l1norm_func_1<sreal>);
+        case SCALAR_PRODUCT: return probe_norm_timedomain(a, scalar_product_1<sreal>);
+        case AMPSPEC_L2NORM: return probe_norm_frequencydomain(a, l2norm_func_1<float>);
+        case AMPSPEC_L1NORM: return probe_norm_frequencydomain(a, l1norm_func_1<float>);
+        case PEAK: return probe_norm_timedomain(a, maxabs_func_1<sreal>);
     }
     fprintf(stderr, "probe_norm(): unknown norm method\n"); abort();
 }
@@ -355,7 +365,7 @@ static inline void probes_windowed_cross_corr(Probe& a, Probe& b, const int shif
     for (int i = 0; i < slen(shiftrange); i++) {
         probe_shift(b, ishift);
         ishift = 1;
-        cross_corr[i] = probes_norm_timedomain(a, b, scalar_product_2);
+        cross_corr[i] = probes_norm_timedomain(a, b, scalar_product_2<sreal>);
     }
     probe_shift(b, -shiftrange[1]);
 }

@@ -63,7 +63,7 @@ static inline Trace* gfdb_get_trace_bilin(Gfdb& db, const int ix[2], const int i
         tp->span[0] = span[0]; tp->span[1] = span[1];
     }
     std::fill(tp->strips[0].d.begin(), tp->strips[0].d.end(), 0.f);
-    float* arr = tp->strips[0].d.data();
+    sreal* arr = tp->strips[0].d.data();
     trace_multiply_add_nogrow(*t00, arr, span[0], span[1], (1.f - dix) * (1.f - diz));
     trace_multiply_add_nogrow(*t01, arr, span[0], span[1], (1.f - dix) * diz);
     trace_multiply_add_nogrow(*t10, arr, span[0], span[1], dix * (1.f - diz));

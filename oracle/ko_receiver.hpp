@@ -261,8 +261,8 @@ static inline void make_seismogram(const Tdsm& source, Receiver& receiver, Gfdb&
             float sl = (float)sin(bazi_orig + (double)pi);
             strip_extend_to_same_span({&ar[0], &ar[1]});
             for (int i = 0; i < ar[0].size(); i++) {  // seismogram.f90:303-314 rotate
-                float a = ar[0].d[i], b = ar[1].d[i];
-                float aa = cl * a - sl * b;
+                sreal a = ar[0].d[i], b = ar[1].d[i];
+                sreal aa = cl * a - sl * b;
                 b = cl * b + sl * a;
                 ar[0].d[i] = aa; ar[1].d[i] = b;
             }

@@ -6,15 +6,25 @@ namespace ko {
 
 static const int maxgap = 5;  // sparse_trace.f90:24
 
+// Sample type of strips.  The reference has `real` (fp32) everywhere and that is what the oracle
+// uses.  -DKO_WIDE builds a second library whose strip arithmetic (trace sums, probes, norms) runs
+// in double on the same fp32 inputs, indices and weights: it measures how far the fp32 reference
+// path itself is from the exactly accumulated result (accuracy evidence only, never a parity bar).
+#ifdef KO_WIDE
+typedef double sreal;
+#else
+typedef float sreal;
+#endif
+
 // util.f90:339-357 `resize`: no preservation, no initialisation, length 0 deallocates
 struct Strip {  // sparse_trace.f90:28-32
     int lo = 0;
-    std::vector<float> d;
+    std::vector<sreal> d;
     bool alloc = false;
     int hi() const { return lo + (int)d.size() - 1; }
     int size() const { return (int)d.size(); }
-    float& at(int i) { return d[i - lo]; }
-    float at(int i) const { return d[i - lo]; }
+    sreal& at(int i) { return d[i - lo]; }
+    sreal at(int i) const { return d[i - lo]; }
 };
 static inline void resize(Strip& s, int offset, int length) {
     if (!s.alloc) {
@@ -35,7 +45,8 @@ struct Trace {  // sparse_trace.f90:34-50
     bool alloc = false;  // allocated(trace%strips)
 };
 
-static inline void strip_init(int s0, int s1, const float* data, int ndata, Strip& strip) {  // :72-88
+template <class T>
+static inline void strip_init(int s0, int s1, const T* data, int ndata, Strip& strip) {  // :72-88
     int length = s1 - s0 + 1;
     if (ndata != length) { fprintf(stderr, "strip_init(): length of data does not match span\n"); abort(); }
     resize(strip, s0, length);
@@ -55,7 +66,7 @@ static inline bool trace_is_empty(const Trace& t) { return !t.alloc; }  // :915-
 
 // :316-345
 static inline void strip_extend(Strip& s, int n0, int n1) {
-    std::vector<float> temp; int r0 = 0, r1 = -1; bool had = false;
+    std::vector<sreal> temp; int r0 = 0, r1 = -1; bool had = false;
     if (s.alloc) { r0 = s.lo; r1 = s.hi(); temp = s.d; had = true; }
     resize(s, n0, n1 - n0 + 1);
     if (had) {
@@ -77,13 +88,14 @@ static inline void strip_dataspan(const Strip& s, int out[2]) {
     if (strip_length(s) == 0) { out[0] = 0; out[1] = -1; return; }
     int s0 = s.lo, s1 = s.hi();
     out[0] = s0; out[1] = s1;
-    float firstvalue = 0.f;
+    sreal firstvalue = 0.f;
     for (int i = s0; i <= s1; i++) { out[0] = i; if (s.at(i) != firstvalue) break; }
-    float lastvalue = s.at(s1);
+    sreal lastvalue = s.at(s1);
     for (int i = s1; i >= s0; i--) { if (s.at(i) != lastvalue) break; out[1] = i; }
 }
 // :404-418
-static inline void trace_create_simple(Trace& t, const float* data, int s0, int s1) {
+template <class T>
+static inline void trace_create_simple(Trace& t, const T* data, int s0, int s1) {
     trace_destroy(t);
     t.strips.resize(1); t.alloc = true; t.nstrips = 1;
     resize(t.strips[0], s0, s1 - s0 + 1);
@@ -213,16 +225,16 @@ static inline void trace_multiply_add(const Trace& trace, Strip& strip, float fa
             }
         }
         if (is == trace.nstrips && r1 + 1 <= strip.hi()) {
-            float lastval = ts.at(ts.hi());
+            sreal lastval = ts.at(ts.hi());
             if (lastval != 0.f) for (int x = r1 + 1; x <= strip.hi(); x++) strip.at(x) = strip.at(x) + factor * lastval;
         }
     }
 }
 
 // :710-792 fixed window variant; array covers [a0, a1]
-static inline void trace_multiply_add_nogrow(const Trace& trace, float* array, int a0, int a1, float factor = 1.f,
+static inline void trace_multiply_add_nogrow(const Trace& trace, sreal* array, int a0, int a1, float factor = 1.f,
                                              ShiftKind kind = SHIFT_NONE, int itraceshift_ = 0, float rtraceshift_ = 0.f) {
-    auto A = [&](int x) -> float& { return array[x - a0]; };
+    auto A = [&](int x) -> sreal& { return array[x - a0]; };
     int itraceshift = 0;
     float weight_right = 0.f, weight_left = 0.f;
     bool rpresent = (kind == SHIFT_REAL);
@@ -254,7 +266,7 @@ static inline void trace_multiply_add_nogrow(const Trace& trace, float* array, i
             }
         }
         if (is == trace.nstrips && r1 + 1 <= a1) {
-            float lastval = ts.at(ts.hi());
+            sreal lastval = ts.at(ts.hi());
             if (lastval != 0.f) for (int x = r1 + 1; x <= a1; x++) A(x) = A(x) + factor * lastval;
         }
     }

@@ -7,6 +7,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+WIDE_LIB_PATH = os.path.join(ROOT, "oracle", "_build", "liboracle_wide.so")   # strip arithmetic in double
 KAT_PATH = os.path.join(ROOT, "oracle", "_build", "kat")
 
 fp = C.POINTER(C.c_float)
@@ -14,13 +15,12 @@ dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int)
 lp = C.POINTER(C.c_longlong)
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        L = C.CDLL(LIB_PATH)
+def lib(wide=False):
+    if wide not in _libs:
+        L = C.CDLL(WIDE_LIB_PATH if wide else LIB_PATH)
         L.oracle_create.restype = C.c_void_p
         L.oracle_last_error.restype = C.c_char_p
         L.oracle_last_error.argtypes = [C.c_void_p]
@@ -36,8 +36,8 @@ def lib():
                      "oracle_receiver_geometry", "oracle_trace_span", "oracle_time_eval", "oracle_get_strip_spans"):
             if hasattr(L, name):
                 getattr(L, name).argtypes = None
-        _lib = L
-    return _lib
+        _libs[wide] = L
+    return _libs[wide]
 
 
 def _f32(a):
@@ -56,8 +56,8 @@ class OracleError(RuntimeError):
 class OracleEngine:
     """Same surface as kiwi_b200.Engine, computed by the CPU restatement of the Fortran."""
 
-    def __init__(self, threads=None):
-        self.L = lib()
+    def __init__(self, threads=None, wide=False):
+        self.L = lib(wide)
         self.h = C.c_void_p(self.L.oracle_create())
         if threads:
             self.L.oracle_set_num_threads(C.c_int(threads))
