@@ -104,7 +104,9 @@ struct kiwi_ctx {
     bool loc_set = false;
     double olat = 0., olon = 0., ref_time = 0.;
     // workspace
-    DevBuf d_cands, d_bilat, d_gf, d_gi, d_tf, d_recs, d_hdrs, d_seis, d_shdrs, d_out, d_status, d_tmax, d_table;
+    DevBuf d_cands, d_bilat, d_gf, d_gi, d_tf, d_recs, d_hdrs, d_seis, d_shdrs, d_out, d_status, d_tmax, d_table, d_tw, d_fshift;
+    int tw_n = 0;                            // twiddle table exp(-2 pi i k / tw_n), k < tw_n/2
+    std::vector<int> last_fshift;            // floating shifts of the last ns = 1 evaluation
     PinBuf h_stage, h_out;
     size_t work_budget = 0;
     // description of the last chunk evaluated (inspection entry points, accounting)
@@ -183,6 +185,11 @@ int upload_receivers(kiwi_ctx* c) {
         }
         r.has_filter = h.filter_x.empty() ? 0 : 1;
         r.fs0 = h.fs0; r.fs1 = h.fs1;
+        if (h.taper_x.size() > KIWI_MAX_PLF || h.filter_x.size() > KIWI_MAX_PLF)
+            return kiwi_set_error("tapers and filters are limited to %d points", KIWI_MAX_PLF);
+        r.ntp = (int)h.taper_x.size(); r.nfp = (int)h.filter_x.size();
+        for (int k = 0; k < r.ntp; k++) { r.tpx[k] = h.taper_x[k]; r.tpy[k] = h.taper_y[k]; }
+        for (int k = 0; k < r.nfp; k++) { r.fpx[k] = h.filter_x[k]; r.fpy[k] = h.filter_y[k]; }
     }
     c->nmisfits = nm;
     if (refdata.empty()) refdata.push_back(0.f);
@@ -219,12 +226,11 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
     if (nparams != kiwi_get_n_source_params(sourcetype) || nparams == 0) return kiwi_set_error("wrong number of source parameters or source type not available");
     if (sourcetype != KIWI_SOURCE_BILATERAL && sourcetype != KIWI_SOURCE_MOMENT_TENSOR) return kiwi_set_error("source type not available in this build");
     if (want_misfits && !all_refs_set(c)) return kiwi_set_error("no reference seismograms set");   // :1428
+    bool general = false;   // anything beyond plain time-domain norms goes through k_misfit_general
     if (want_misfits) {
         const int m = c->misfit_method;
-        if (!(m == KIWI_L2NORM || m == KIWI_L1NORM || m == KIWI_SCALAR_PRODUCT || m == KIWI_PEAK))
-            return kiwi_set_error("misfit method %d is not available in this build (time-domain norms only)", m);
-        for (const HostReceiver& h : c->rcv) if (h.enabled && !h.filter_x.empty())
-            return kiwi_set_error("misfit filters are not available in this build");
+        general = (m == KIWI_AMPSPEC_L2NORM || m == KIWI_AMPSPEC_L1NORM || m == KIWI_FLOATING_L2NORM || m == KIWI_FLOATING_L1NORM);
+        for (const HostReceiver& h : c->rcv) if (h.enabled && !h.filter_x.empty()) general = true;
     }
     if (upload_receivers(c)) return 1;
     const int nrcv = (int)c->rcv.size();
@@ -335,13 +341,16 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         CU_OK(c->d_recs.ensure(sizeof(GeoRec) * npairs * rec_stride));
         CU_OK(c->d_hdrs.ensure(sizeof(PairHdr) * npairs));
         CU_OK(c->d_shdrs.ensure(sizeof(SeisHdr) * npairs * KIWI_MAX_COMP));
-        CU_OK(c->d_tmax.ensure(sizeof(int)));
-        CU_OK(cudaMemsetAsync(c->d_tmax.p, 0, sizeof(int), st));
-        launch_geometry(c->db, c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>(), nc, g, c->interpolate ? 1 : 0, c->xunder, c->zunder,
+        CU_OK(c->d_tmax.ensure(sizeof(int) * 4));
+        {
+            static const int init3[4] = {0, INT_MAX, INT_MIN, 0};   // max window length, min first sample, max last sample
+            CU_OK(cudaMemcpyAsync(c->d_tmax.p, init3, sizeof init3, cudaMemcpyHostToDevice, st));
+        }
+        launch_geometry(c->db, c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>(), nc, g, Galloc, c->interpolate ? 1 : 0, c->xunder, c->zunder,
                         c->d_recs.as<GeoRec>(), rec_stride, c->d_hdrs.as<PairHdr>(), c->d_tmax.as<int>(), st);
         c->launches[1] += 1;
-        int tmax = 0;
-        CU_OK(cudaMemcpyAsync(&tmax, c->d_tmax.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        int tm3[4] = {0, 0, 0, 0};
+        CU_OK(cudaMemcpyAsync(tm3, c->d_tmax.p, sizeof tm3, cudaMemcpyDeviceToHost, st));
         cudaEventRecord(c->ev[3], st);
         CU_OK(cudaStreamSynchronize(st));
         CU_OK(cudaGetLastError());
@@ -351,6 +360,7 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         (void)ms01;
         c->ms[0] += ms12; c->ms[1] += ms23;
         // ---- K3 + K5: synthesis and misfit, in sub-chunks sized by the seismogram buffer ----------------
+        const int tmax = tm3[0];
         const int nq = (tmax + 6) / 4 + 1;
         const size_t seis_stride = (size_t)4 * nq;
         int nwarps = 8;
@@ -382,10 +392,53 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
                 CU_OK(cudaMemsetAsync(c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, 0xff, sizeof(SeisHdr) * (size_t)ns_ * nrcv * KIWI_MAX_COMP, st));
             }
             cudaEventRecord(c->ev[4], st);
-            if (want_misfits && nm > 0) {
+            if (want_misfits && nm > 0 && !general) {
                 launch_misfit_td(c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>() + s0, ns_, c->d_seis.as<float>(), seis_stride,
                                  c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, c->d_refdata.as<float>(), c->d_taper.as<float>(),
                                  c->misfit_method, c->db.dt, c->syn_factor, nm, d_out + ((size_t)(b0 + s0) * nm) * 2, c->d_status.as<int>() + s0, st);
+                c->launches[3] += 1;
+            } else if (want_misfits && nm > 0) {
+                // bound of the padded probe span (comparator.f90:1092-1109) over this chunk: union of all synthetic
+                // and (shifted) reference spans, at least twice the longest data span, next power of two
+                int lo = tm3[1], hi = tm3[2], rlen = 1, nshift = 1;
+                const bool floating = c->misfit_method >= KIWI_FLOATING_L2NORM;
+                bool need_fft = (c->misfit_method == KIWI_AMPSPEC_L2NORM || c->misfit_method == KIWI_AMPSPEC_L1NORM);
+                for (const ReceiverDev& r : c->h_rcvdev) {
+                    if (!r.enabled) continue;
+                    if (r.has_filter) need_fft = true;
+                    if (floating) nshift = std::max(nshift, r.fs1 - r.fs0 + 1);
+                    for (int k = 0; k < r.ncomp; k++) {
+                        lo = std::min(lo, std::min(r.ref_sp0[k], r.ref_ds0[k] + (floating ? r.fs0 : 0)));
+                        hi = std::max(hi, std::max(r.ref_sp1[k], r.ref_ds1[k] + (floating ? r.fs1 : 0)));
+                        rlen = std::max(rlen, r.ref_ds1[k] - r.ref_ds0[k] + 1);
+                    }
+                }
+                int n_alloc = 2;
+                if (need_fft) {
+                    const long long want = std::max<long long>((long long)hi - lo + 1, 2LL * std::max(tmax, rlen));
+                    while (n_alloc < want) n_alloc <<= 1;
+                    n_alloc <<= 1;   // head room for re-centred unions
+                    if (n_alloc > 16384) n_alloc = 16384;   // 128 KiB of shared memory; longer spans are flagged per candidate
+                    if (c->tw_n == 0) {   // twiddles rounded from double, as an fp32 FFT library tabulates them
+                        const int N = 32768;
+                        std::vector<float> twh((size_t)N);
+                        for (int k = 0; k < N / 2; k++) {
+                            const double a = -2.0 * M_PI * (double)k / (double)N;
+                            twh[2 * (size_t)k] = (float)cos(a); twh[2 * (size_t)k + 1] = (float)sin(a);
+                        }
+                        CU_OK(c->d_tw.ensure(sizeof(float) * N));
+                        CU_OK(cudaMemcpy(c->d_tw.p, twh.data(), sizeof(float) * N, cudaMemcpyHostToDevice));
+                        c->tw_n = N;
+                    }
+                }
+                if (misfit_general_smem_bytes(n_alloc, nshift) > (size_t)200 * 1024) return kiwi_set_error("floating shift range too large");
+                CU_OK(c->d_fshift.ensure(sizeof(int) * (size_t)nc * nrcv));
+                cudaError_t e = launch_misfit_general(c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>() + s0, ns_, c->d_seis.as<float>(), seis_stride,
+                                                      c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, c->d_refdata.as<float>(), c->d_taper.as<float>(),
+                                                      (const float2*)c->d_tw.p, c->tw_n > 0 ? c->tw_n : 2, c->misfit_method, c->db.dt, c->syn_factor, nm,
+                                                      d_out + ((size_t)(b0 + s0) * nm) * 2, c->d_status.as<int>() + s0, c->d_fshift.as<int>() + poff, n_alloc,
+                                                      nshift, st);
+                if (e != cudaSuccess) return kiwi_set_error("CUDA error launching the misfit kernel: %s", cudaGetErrorString(e));
                 c->launches[3] += 1;
             }
             cudaEventRecord(c->ev[5], st);
@@ -424,6 +477,11 @@ int ensure_single(kiwi_ctx* c, bool want_misfits) {
         c->src_misfits.assign((size_t)2 * nm, 0.f);
         if (nm > 0) CU_OK(cudaMemcpy(c->src_misfits.data(), c->d_out.p, sizeof(float) * 2 * nm, cudaMemcpyDeviceToHost));
     }
+    c->last_fshift.clear();
+    if (want_misfits && c->misfit_method >= KIWI_FLOATING_L2NORM && c->d_fshift.p) {
+        c->last_fshift.assign(c->rcv.size(), 0);
+        CU_OK(cudaMemcpy(c->last_fshift.data(), c->d_fshift.p, sizeof(int) * c->rcv.size(), cudaMemcpyDeviceToHost));
+    }
     c->src_status = status;
     c->src_dirty = false;
     if (status == KIWI_STATUS_BAD_PARAMS) return kiwi_set_error("discretisation of the source failed");
@@ -460,7 +518,7 @@ void kiwi_destroy(kiwi_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->d_slabs, &c->d_nodes, &c->d_tspan, &c->d_rcv, &c->d_refdata, &c->d_taper, &c->d_cands, &c->d_bilat, &c->d_gf, &c->d_gi,
-                      &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table})
+                      &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift})
         b->release();
     c->h_stage.release(); c->h_out.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -491,7 +549,7 @@ int kiwi_set_database(kiwi_ctx* c, kiwi_gfdb* db) {
         NodeInfo& ni = c->h_nodes[inode];
         if (!all) { ni.off = ~0ull; ni.w0 = 0; ni.wn = 0; continue; }   // node unusable: the centroid is skipped (seismogram.f90:172)
         const int w0 = (int)(floor((double)lo / 4.0)) * 4;
-        const int wend = (int)(floor((double)hi / 4.0)) * 4 + 4;      // exclusive, multiple of 4
+        const int wend = (int)(floor((double)hi / 4.0)) * 4 + 8;      // exclusive, multiple of 4; last quad = continuation only
         ni.off = total; ni.w0 = w0; ni.wn = wend - w0;
         total += (unsigned long long)ni.wn * ng;
         tmin = std::min(tmin, lo); tmax = std::max(tmax, hi);
@@ -746,9 +804,19 @@ int kiwi_get_global_misfit(kiwi_ctx* c, float* misfit) {
     return kiwi_global_misfits(1, c->nmisfits, c->src_misfits.data(), misfit);
 }
 
-int kiwi_get_floating_shifts(kiwi_ctx* c, int* shifts, int cap, int* n) {
-    (void)c; (void)shifts; (void)cap; (void)n;
-    return kiwi_set_error("floating misfits are not available in this build");
+int kiwi_get_floating_shifts(kiwi_ctx* c, int* shifts, int cap, int* n) {   // minimizer_engine.f90:1095-1128
+    if (!c) return kiwi_set_error("null context");
+    CU_OK(cudaSetDevice(c->device));
+    if (c->misfit_method < KIWI_FLOATING_L2NORM) return kiwi_set_error("floating shifts need a floating misfit method");
+    if (ensure_single(c, true)) return 1;
+    int k = 0;
+    for (size_t i = 0; i < c->rcv.size(); i++) {
+        if (!c->rcv[i].enabled) continue;
+        if (k < cap) shifts[k] = i < c->last_fshift.size() ? c->last_fshift[i] : 0;
+        k++;
+    }
+    if (n) *n = k;
+    return 0;
 }
 
 int kiwi_get_seismogram(kiwi_ctx* c, int ireceiver, int icomponent, int which, int* first_index, int* n, float* buf, int cap) {

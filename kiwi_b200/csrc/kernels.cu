@@ -155,8 +155,8 @@ __device__ __forceinline__ void set_span(const GfdbDev& db, const int inode[4], 
 }
 
 __global__ void __launch_bounds__(256) k_geometry(GfdbDev db, const ReceiverDev* __restrict__ rcv, int nrcv,
-                                                   const CandDev* __restrict__ cands, GroupSoA g, int interpolate, int xunder,
-                                                   int zunder, GeoRec* __restrict__ recs, size_t rec_stride,
+                                                   const CandDev* __restrict__ cands, GroupSoA g, int ngroups_total, int interpolate,
+                                                   int xunder, int zunder, GeoRec* __restrict__ recs, size_t rec_stride,
                                                    PairHdr* __restrict__ hdrs, int* __restrict__ tmax) {
     const int pair = blockIdx.x;
     const int b = pair / nrcv, ir = pair % nrcv;
@@ -181,7 +181,23 @@ __global__ void __launch_bounds__(256) k_geometry(GfdbDev db, const ReceiverDev*
             double azi, bazi, dist;
             approx_differential_azidist(dnorth, deast, R.azi0, R.bazi0, R.dist0, azi, bazi, dist);
             GeoRec rec;
-            rec.azi = (float)azi;
+            {   // make_weights seismogram.f90:316-336 on the group's moment-tensor shape; the scalar tap
+                // weight wt multiplies the result later (the reference applies it to m first)
+                float m[6];
+#pragma unroll
+                for (int k = 0; k < 6; k++) m[k] = g.mhat[(size_t)k * ngroups_total + gi];
+                const float azf = (float)azi;
+                float sa, ca, s2a, c2a;
+                sincosf(azf, &sa, &ca);
+                sincosf(2.f * azf, &s2a, &c2a);
+                rec.f[0] = m[0] * (ca * ca) + m[1] * (sa * sa) + m[3] * s2a;
+                rec.f[1] = m[4] * ca + m[5] * sa;
+                rec.f[2] = m[2];
+                rec.f[3] = 0.5f * (m[1] - m[0]) * s2a + m[3] * c2a;
+                rec.f[4] = m[5] * ca - m[4] * sa;
+                rec.f[5] = m[0] * (sa * sa) + m[1] * (ca * ca) - m[3] * s2a;
+                rec.pad[0] = rec.pad[1] = rec.pad[2] = 0;
+            }
             const float x = (float)dist;
             const float z = S_(depth, R.depth);
             int ix1, iz1, ix2, iz2; float dix, diz; int flags = 0;
@@ -293,7 +309,7 @@ __global__ void __launch_bounds__(256) k_geometry(GfdbDev db, const ReceiverDev*
         int lo = min(min(h.s1lo, h.s2lo), h.s3lo), hi = max(max(h.s1hi, h.s2hi), h.s3hi);
         if (hi < lo) { h.out0 = 0; h.T = 0; } else { h.out0 = lo; h.T = hi - lo + 1; }
         hdrs[pair] = h;
-        if (h.T > 0) atomicMax(tmax, h.T);
+        if (h.T > 0) { atomicMax(tmax, h.T); atomicMin(tmax + 1, lo); atomicMax(tmax + 2, hi); }
     }
 }
 
@@ -315,7 +331,6 @@ __device__ __forceinline__ NodeInfo ld_node(const NodeInfo* p) {
     NodeInfo n; n.off = ((unsigned long long)u.y << 32) | u.x; n.w0 = (int)u.z; n.wn = (int)u.w;
     return n;
 }
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ void fma4(float4& a, float s, const float4& v) {
     a.x = fmaf(s, v.x, a.x); a.y = fmaf(s, v.y, a.y); a.z = fmaf(s, v.z, a.z); a.w = fmaf(s, v.w, a.w);
@@ -334,7 +349,7 @@ __device__ __forceinline__ float4 shfl4(const float4& v, int src) {
 }
 
 // out quad += wl * A(y - its) + wr * A(y - its - 1) for the four samples of one output quad;
-// P = A(4q-4..4q-1), C = A(4q..4q+3), s = its mod 4 (warp-uniform)
+// P = A(4q-4..4q-1), C = A(4q..4q+3), S = its mod 4 (warp-uniform)
 template <int S>
 __device__ __forceinline__ void tap_quad(float4& o, const float4& P, const float4& C, float wl, float wr) {
     // E[i] = A(4q-4+i), i=0..7;  o[j] += wl*E[4-S+j] + wr*E[3-S+j]
@@ -344,18 +359,178 @@ __device__ __forceinline__ void tap_quad(float4& o, const float4& P, const float
     o.z = fmaf(wl, E[6 - S], o.z); o.z = fmaf(wr, E[5 - S], o.z);
     o.w = fmaf(wl, E[7 - S], o.w); o.w = fmaf(wr, E[6 - S], o.w);
 }
-__device__ __forceinline__ void tap_apply(float4* acc, int qrel, int nq, int s, const float4& P, const float4& C, float wl, float wr) {
-    if (qrel < 0 || qrel >= nq) return;
-    float4 o = acc[qrel];
-    switch (s) {
-        case 0: tap_quad<0>(o, P, C, wl, wr); break;
-        case 1: tap_quad<1>(o, P, C, wl, wr); break;
-        case 2: tap_quad<2>(o, P, C, wl, wr); break;
-        default: tap_quad<3>(o, P, C, wl, wr); break;
+// one tap applied to the strips the receiver needs; the sub-quad shift is resolved once per tap
+template <int S, bool H, bool V>
+__device__ __forceinline__ void tap_strips(float4* a1, float4* a2, float4* a3, const float4& P1, const float4& A1, const float4& P2,
+                                           const float4& A2, const float4& P3, const float4& A3, float wl, float wr) {
+    if (H) {
+        float4 o = *a1; tap_quad<S>(o, P1, A1, wl, wr); *a1 = o;
+        o = *a2; tap_quad<S>(o, P2, A2, wl, wr); *a2 = o;
     }
-    acc[qrel] = o;
+    if (V) { float4 o = *a3; tap_quad<S>(o, P3, A3, wl, wr); *a3 = o; }
 }
 
+// One warp, one group.  H/V: the receiver has horizontal / vertical components.
+template <bool H, bool V>
+__device__ __forceinline__ void synth_group(const GfdbDev& db, const GeoRec& rec, const GroupSoA& g, const TapSoA& taps, int gi, int xstep,
+                                            int zstep, bool ng10, float sd, float4* __restrict__ acc, float* __restrict__ step, int nq,
+                                            int baseq, int lane) {
+    const float dt = db.dt;
+    // ---- corners (gfdb.f90:943-948 weights in the reference's association) -------------------------
+    const bool single = rec.flags & GEO_SINGLE;
+    const float dix = rec.dix, diz = rec.diz;
+    const float wc0 = single ? 1.f : (1.f - dix) * (1.f - diz), wc1 = single ? 0.f : (1.f - dix) * diz,
+                wc2 = single ? 0.f : dix * (1.f - diz), wc3 = single ? 0.f : dix * diz;
+    const int inode0 = (rec.ix1 - 1) * db.nz + (rec.iz1 - 1);
+    const NodeInfo n0 = ld_node(&db.nodes[inode0]);
+    const NodeInfo n1 = single ? n0 : ld_node(&db.nodes[inode0 + zstep]);
+    const NodeInfo n2 = single ? n0 : ld_node(&db.nodes[inode0 + xstep * db.nz]);
+    const NodeInfo n3 = single ? n0 : ld_node(&db.nodes[inode0 + xstep * db.nz + zstep]);
+    const float4* b0 = reinterpret_cast<const float4*>(db.slabs + n0.off);
+    const float4* b1 = reinterpret_cast<const float4*>(db.slabs + n1.off);
+    const float4* b2 = reinterpret_cast<const float4*>(db.slabs + n2.off);
+    const float4* b3 = reinterpret_cast<const float4*>(db.slabs + n3.off);
+    const int w0q0 = n0.w0 >> 2, w0q1 = n1.w0 >> 2, w0q2 = n2.w0 >> 2, w0q3 = n3.w0 >> 2;     // first quad of each window
+    const int nq0 = n0.wn >> 2, nq1 = n1.wn >> 2, nq2 = n2.wn >> 2, nq3 = n3.wn >> 2;          // quads per row
+    const int q_first = min(min(w0q0, w0q1), min(w0q2, w0q3));
+    // last quad of the longest window: continuation only, for every corner
+    const int q_last = max(max(w0q0 + nq0, w0q1 + nq1), max(w0q2 + nq2, w0q3 + nq3)) - 1;
+    // ---- taps: lane k prepares tap k (sparse_trace.f90:639-646) ---------------------------------------
+    const int tb = g.tap_begin[gi], tn = min(g.tap_count[gi], SYN_MAXTAPS);
+    int my_its = 0; float my_wl = 0.f, my_wr = 0.f;
+    if (lane < tn) {
+        const float time = A_(g.tbase[gi], taps.toff[tb + lane]);
+        const float rshift = D_(time, dt);
+        my_its = (int)floorf(rshift);
+        const float wr0 = S_(rshift, (float)my_its);
+        const float wl0 = S_(1.f, wr0);
+        const float wt = taps.wt[tb + lane];
+        my_wr = M_(wr0, wt); my_wl = M_(wl0, wt);
+    }
+    const float f1 = rec.f[0], f2 = rec.f[1], f3 = rec.f[2], f4 = rec.f[3], f5 = rec.f[4], f6 = rec.f[5];
+    const float cl = rec.cl, sl = rec.sl;
+    const float v1 = f1 * sd, v2 = f2 * sd, v3 = f3 * sd, v6 = f6 * sd;
+
+    float4 carry1 = f4zero(), carry2 = f4zero(), carry3 = f4zero();   // quad left of the chunk (zeros left of the windows)
+    for (int q0 = q_first; q0 <= q_last; q0 += 32) {
+        const int q = q0 + lane;
+        const bool active = q <= q_last;
+        float4 A1 = f4zero(), A2 = f4zero(), A3 = f4zero();
+        if (active) {
+            // per corner: row pointer of component 1 at this lane's quad (clamped into the window: the
+            // last quad is the continuation; left of the window the weight is zero)
+            const int o0 = q - w0q0, o1 = q - w0q1, o2 = q - w0q2, o3 = q - w0q3;
+            const float4* p0 = b0 + min(max(o0, 0), nq0 - 1);
+            const float4* p1 = b1 + min(max(o1, 0), nq1 - 1);
+            const float4* p2 = b2 + min(max(o2, 0), nq2 - 1);
+            const float4* p3 = b3 + min(max(o3, 0), nq3 - 1);
+            const float c0 = o0 < 0 ? 0.f : wc0, c1 = o1 < 0 ? 0.f : wc1, c2 = o2 < 0 ? 0.f : wc2, c3 = o3 < 0 ? 0.f : wc3;
+            // software pipeline over the GF components: the four corner quads of component i+2 are in
+            // flight while component i is combined (keeps ~12 128-bit loads per lane outstanding)
+#define KIWI_LOAD(buf, ig) { buf[0] = __ldg(p0 + (ig) * nq0); buf[1] = __ldg(p1 + (ig) * nq1); buf[2] = __ldg(p2 + (ig) * nq2); buf[3] = __ldg(p3 + (ig) * nq3); }
+#define KIWI_COMB(buf, dst, wgt) { float4 r = f4zero(); fma4(r, c0, buf[0]); fma4(r, c1, buf[1]); fma4(r, c2, buf[2]); fma4(r, c3, buf[3]); fma4(dst, wgt, r); }
+            float4 ta[4], tb[4], tc[4];
+            if (H && V) {
+                float4 Rr = f4zero(), Tt = f4zero();
+                KIWI_LOAD(ta, 0) KIWI_LOAD(tb, 1) KIWI_LOAD(tc, 2)
+                KIWI_COMB(ta, Rr, f1) KIWI_LOAD(ta, 3)
+                KIWI_COMB(tb, Rr, f2) KIWI_LOAD(tb, 4)
+                KIWI_COMB(tc, Rr, f3) KIWI_LOAD(tc, 5)
+                KIWI_COMB(ta, Tt, f4) KIWI_LOAD(ta, 6)
+                KIWI_COMB(tb, Tt, f5) KIWI_LOAD(tb, 7)
+                KIWI_COMB(tc, A3, v1)
+                if (ng10) {
+                    KIWI_LOAD(tc, 8)
+                    KIWI_COMB(ta, A3, v2) KIWI_LOAD(ta, 9)
+                    KIWI_COMB(tb, A3, v3)
+                    KIWI_COMB(tc, Rr, f6)
+                    KIWI_COMB(ta, A3, v6)
+                } else {
+                    KIWI_COMB(ta, A3, v2)
+                    KIWI_COMB(tb, A3, v3)
+                }
+                // seismogram.f90:200-203: ar1 += cl*temp1 - sl*temp2; ar2 += cl*temp2 + sl*temp1
+                fma4(A1, cl, Rr); fma4(A1, -sl, Tt);
+                fma4(A2, cl, Tt); fma4(A2, sl, Rr);
+            } else if (H) {
+                float4 Rr = f4zero(), Tt = f4zero();
+                KIWI_LOAD(ta, 0) KIWI_LOAD(tb, 1) KIWI_LOAD(tc, 2)
+                KIWI_COMB(ta, Rr, f1) KIWI_LOAD(ta, 3)
+                KIWI_COMB(tb, Rr, f2) KIWI_LOAD(tb, 4)
+                KIWI_COMB(tc, Rr, f3)
+                if (ng10) { KIWI_LOAD(tc, 8) }
+                KIWI_COMB(ta, Tt, f4)
+                KIWI_COMB(tb, Tt, f5)
+                if (ng10) { KIWI_COMB(tc, Rr, f6) }
+                fma4(A1, cl, Rr); fma4(A1, -sl, Tt);
+                fma4(A2, cl, Tt); fma4(A2, sl, Rr);
+            } else {
+                KIWI_LOAD(ta, 5) KIWI_LOAD(tb, 6) KIWI_LOAD(tc, 7)
+                KIWI_COMB(ta, A3, v1)
+                if (ng10) { KIWI_LOAD(ta, 9) }
+                KIWI_COMB(tb, A3, v2)
+                KIWI_COMB(tc, A3, v3)
+                if (ng10) { KIWI_COMB(ta, A3, v6) }
+            }
+#undef KIWI_LOAD
+#undef KIWI_COMB
+        }
+        // previous quad: lane-1; lane 0 takes the carry of the previous chunk
+        float4 P1, P2, P3;
+        if (H) { P1 = shfl_up4(A1, 1); P2 = shfl_up4(A2, 1); if (lane == 0) { P1 = carry1; P2 = carry2; } }
+        if (V) { P3 = shfl_up4(A3, 1); if (lane == 0) P3 = carry3; }
+        const bool more = q0 + 32 <= q_last;
+        if (more) {
+            if (H) { carry1 = shfl4(A1, 31); carry2 = shfl4(A2, 31); }
+            if (V) carry3 = shfl4(A3, 31);
+        }
+        for (int k = 0; k < tn; k++) {
+            const int its = __shfl_sync(0xffffffffu, my_its, k);
+            const float wl = __shfl_sync(0xffffffffu, my_wl, k), wr = __shfl_sync(0xffffffffu, my_wr, k);
+            const int qrel = q + (its >> 2) - baseq;
+            if (active && qrel >= 0 && qrel < nq) {
+                float4* a1 = acc + qrel; float4* a2 = a1 + nq; float4* a3 = a2 + nq;
+                switch (its & 3) {
+                    case 0: tap_strips<0, H, V>(a1, a2, a3, P1, A1, P2, A2, P3, A3, wl, wr); break;
+                    case 1: tap_strips<1, H, V>(a1, a2, a3, P1, A1, P2, A2, P3, A3, wl, wr); break;
+                    case 2: tap_strips<2, H, V>(a1, a2, a3, P1, A1, P2, A2, P3, A3, wl, wr); break;
+                    default: tap_strips<3, H, V>(a1, a2, a3, P1, A1, P2, A2, P3, A3, wl, wr); break;
+                }
+            }
+            __syncwarp();
+        }
+        if (!more) {
+            // ---- end-value repetition (sparse_trace.f90:696-703): every sample right of the last
+            // processed quad gets (wl+wr)*A_end; recorded as a step at quad q_last+1+shift, prefix-summed
+            // at the end.  Lane c owns strip c: fixed order over the taps, no two lanes share a word.
+            const int src = q_last - q0;
+            const float e1 = H ? __shfl_sync(0xffffffffu, A1.w, src) : 0.f;
+            const float e2 = H ? __shfl_sync(0xffffffffu, A2.w, src) : 0.f;
+            const float e3 = V ? __shfl_sync(0xffffffffu, A3.w, src) : 0.f;
+            const float ae = lane == 0 ? e1 : (lane == 1 ? e2 : e3);
+            const bool mine = lane < 3 && (lane < 2 ? H : V);
+            for (int k = 0; k < tn; k++) {
+                const int its = __shfl_sync(0xffffffffu, my_its, k);
+                const float w = __shfl_sync(0xffffffffu, my_wl, k) + __shfl_sync(0xffffffffu, my_wr, k);
+                const int qs = q_last + 1 + (its >> 2) - baseq;
+                if (mine && qs >= 0 && qs < nq) step[lane * nq + qs] += w * ae;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// =================================================================================================
+// K3: synthesis.  One CTA per (candidate, receiver); every warp owns a private set of three
+// accumulator strips (displacement_ar(1), displacement_ar(2), vertical) in shared memory and works
+// through its share of the groups.  Per group and 128-sample chunk a lane owns one aligned sample
+// quad: 4 corners x ng rows are fetched with coalesced 128-bit loads from the HBM slabs, combined
+// bilinearly (gfdb.f90:943-948), weighted with the moment-tensor/azimuth factors (make_weights
+// seismogram.f90:316-336, precomputed by k_geometry), rotated by the centroid's back-azimuth
+// difference (:196-203), and then added nt times with the sample shift and linear sub-sample
+// interpolation of trace_multiply_add (sparse_trace.f90:639-705).  The "last sample repeats for
+// ever" rule (:696-703) becomes a step per (group, tap) that is prefix-summed once at the end.
+// =================================================================================================
 __global__ void __launch_bounds__(256, 2) k_synth(GfdbDev db, const ReceiverDev* __restrict__ rcv, int nrcv,
                                                    const CandDev* __restrict__ cands, GroupSoA g, TapSoA taps, int ngroups_total,
                                                    int interpolate, int xunder, int zunder, const GeoRec* __restrict__ recs,
@@ -389,144 +564,21 @@ __global__ void __launch_bounds__(256, 2) k_synth(GfdbDev db, const ReceiverDev*
     const bool need_v = R.jd != 0;
     const bool ng10 = db.ng == 10;
     const GeoRec* myrecs = recs + (size_t)pair * rec_stride;
-    const float dt = db.dt;
+    const int xstep = interpolate ? xunder : 1, zstep = interpolate ? zunder : 1;
+    (void)ngroups_total;
 
     for (int ip = warp; ip < cand.ngroups; ip += nwarps) {
-        const GeoRec rec = myrecs[ip];
+        GeoRec rec;
+        {   // 64-byte record, four 128-bit loads
+            const uint4* rp = reinterpret_cast<const uint4*>(myrecs + ip);
+            uint4* dp = reinterpret_cast<uint4*>(&rec);
+            dp[0] = __ldg(rp); dp[1] = __ldg(rp + 1); dp[2] = __ldg(rp + 2); dp[3] = __ldg(rp + 3);
+        }
         if (rec.flags & GEO_SKIP) continue;
         const int gi = cand.group_begin + ip;
-        // ---- moment tensor / azimuth weights, make_weights seismogram.f90:316-336 -------------
-        float m[6];
-#pragma unroll
-        for (int k = 0; k < 6; k++) m[k] = g.mhat[(size_t)k * ngroups_total + gi];
-        float sa, ca, s2a, c2a;
-        sincosf(rec.azi, &sa, &ca);
-        sincosf(2.f * rec.azi, &s2a, &c2a);
-        const float f1 = m[0] * ca * ca + m[1] * sa * sa + m[3] * s2a;
-        const float f2 = m[4] * ca + m[5] * sa;
-        const float f3 = m[2];
-        const float f4 = 0.5f * (m[1] - m[0]) * s2a + m[3] * c2a;
-        const float f5 = m[5] * ca - m[4] * sa;
-        const float f6 = m[0] * sa * sa + m[1] * ca * ca - m[3] * s2a;
-        const float cl = rec.cl, sl = rec.sl, sd = R.sd;
-        // ---- corners ------------------------------------------------------------------------------
-        const bool single = rec.flags & GEO_SINGLE;
-        const int ncorner = single ? 1 : 4;
-        const int ix2 = rec.ix1 + (interpolate ? xunder : 1), iz2 = rec.iz1 + (interpolate ? zunder : 1);
-        const float dix = rec.dix, diz = rec.diz;
-        // gfdb.f90:943-948 weights, in the reference's association
-        float wc[4] = {(1.f - dix) * (1.f - diz), (1.f - dix) * diz, dix * (1.f - diz), dix * diz};
-        if (single) wc[0] = 1.f;
-        const float* rowbase[4]; int w0[4], wn[4];
-        int U0 = INT_MAX, U1 = INT_MIN;
-        {
-            const int cx[4] = {rec.ix1, rec.ix1, ix2, ix2}, cz[4] = {rec.iz1, iz2, rec.iz1, iz2};
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                if (c < ncorner) {
-                    const NodeInfo ni = ld_node(&db.nodes[(cx[c] - 1) * db.nz + (cz[c] - 1)]);
-                    rowbase[c] = db.slabs + ni.off; w0[c] = ni.w0; wn[c] = ni.wn;
-                    U0 = min(U0, ni.w0); U1 = max(U1, ni.w0 + ni.wn);
-                } else { rowbase[c] = db.slabs; w0[c] = 0; wn[c] = 4; wc[c] = 0.f; }
-            }
-        }
-        // ---- taps: lane k prepares tap k (sparse_trace.f90:639-646) ---------------------------------
-        const int tb = g.tap_begin[gi], tn = min(g.tap_count[gi], SYN_MAXTAPS);
-        int my_its = 0; float my_wl = 0.f, my_wr = 0.f;
-        if (lane < tn) {
-            const float time = A_(g.tbase[gi], taps.toff[tb + lane]);
-            const float rshift = D_(time, dt);
-            my_its = (int)floorf(rshift);
-            const float wr0 = S_(rshift, (float)my_its);
-            const float wl0 = S_(1.f, wr0);
-            const float wt = taps.wt[tb + lane];
-            my_wr = M_(wr0, wt); my_wl = M_(wl0, wt);
-        }
-        // ---- sample loop ----------------------------------------------------------------------------
-        float4 carry1 = f4zero(), carry2 = f4zero(), carry3 = f4zero();   // quad left of the chunk (zeros left of U0)
-        const int q_first = U0 >> 2, q_last = U1 >> 2;                    // q_last = first constant quad
-        float4 aend1 = f4zero(), aend2 = f4zero(), aend3 = f4zero();
-        for (int q0 = q_first; q0 <= q_last; q0 += 32) {
-            const int q = q0 + lane;
-            const bool active = q <= q_last;
-            float4 A1 = f4zero(), A2 = f4zero(), A3 = f4zero();
-            if (active) {
-                const int x = q << 2;
-                int off[4]; float wcl[4];
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const int o = x - w0[c];
-                    wcl[c] = (o < 0) ? 0.f : wc[c];
-                    off[c] = min(max(o, 0), wn[c] - 4);
-                    off[c] |= (o >= wn[c]) ? 0x40000000 : 0;   // flag: right of the window -> splat last sample
-                }
-                auto fetch = [&](int igm1) -> float4 {   // bilinear combination of one GF component
-                    float4 r = f4zero();
-#pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        if (c < ncorner) {
-                            float4 v = ldg4(rowbase[c] + (size_t)igm1 * wn[c] + (off[c] & 0x3fffffff));
-                            if (off[c] & 0x40000000) { v.x = v.w; v.y = v.w; v.z = v.w; }
-                            fma4(r, wcl[c], v);
-                        }
-                    }
-                    return r;
-                };
-                if (need_h) {
-                    float4 Rr = f4zero(), Tt = f4zero();
-                    float4 v;
-                    v = fetch(0); fma4(Rr, f1, v);
-                    v = fetch(1); fma4(Rr, f2, v);
-                    v = fetch(2); fma4(Rr, f3, v);
-                    if (ng10) { v = fetch(8); fma4(Rr, f6, v); }
-                    v = fetch(3); fma4(Tt, f4, v);
-                    v = fetch(4); fma4(Tt, f5, v);
-                    // seismogram.f90:200-203: ar1 += cl*temp1 - sl*temp2; ar2 += cl*temp2 + sl*temp1
-                    fma4(A1, cl, Rr); fma4(A1, -sl, Tt);
-                    fma4(A2, cl, Tt); fma4(A2, sl, Rr);
-                }
-                if (need_v) {
-                    float4 v;
-                    v = fetch(5); fma4(A3, f1 * sd, v);
-                    v = fetch(6); fma4(A3, f2 * sd, v);
-                    v = fetch(7); fma4(A3, f3 * sd, v);
-                    if (ng10) { v = fetch(9); fma4(A3, f6 * sd, v); }
-                }
-            }
-            // previous quad: lane-1, lane 0 takes the carry of the previous chunk
-            float4 P1 = shfl_up4(A1, 1), P2 = shfl_up4(A2, 1), P3 = shfl_up4(A3, 1);
-            if (lane == 0) { P1 = carry1; P2 = carry2; P3 = carry3; }
-            carry1 = shfl4(A1, 31); carry2 = shfl4(A2, 31); carry3 = shfl4(A3, 31);
-            // the constant tail value lives in the quad q_last
-            {
-                const int src = q_last - q0;
-                if (src >= 0 && src < 32) { aend1 = shfl4(A1, src); aend2 = shfl4(A2, src); aend3 = shfl4(A3, src); }
-            }
-            for (int k = 0; k < tn; k++) {
-                const int its = __shfl_sync(0xffffffffu, my_its, k);
-                const float wl = __shfl_sync(0xffffffffu, my_wl, k), wr = __shfl_sync(0xffffffffu, my_wr, k);
-                if (active) {
-                    const int mq = its >> 2, s = its & 3;
-                    const int qrel = q + mq - baseq;
-                    if (need_h) { tap_apply(acc, qrel, nq, s, P1, A1, wl, wr); tap_apply(acc + nq, qrel, nq, s, P2, A2, wl, wr); }
-                    if (need_v) tap_apply(acc + 2 * nq, qrel, nq, s, P3, A3, wl, wr);
-                }
-            }
-            __syncwarp();
-        }
-        // ---- end-value repetition (sparse_trace.f90:696-703): step at the first quad after the
-        // last processed one, height (wl+wr)*A_end, one lane per tap -------------------------------------
-        {   // lane c owns strip c: no two lanes touch the same word, order over taps is fixed
-            const float ae = lane == 0 ? aend1.w : (lane == 1 ? aend2.w : aend3.w);
-            const bool mine = lane < 3 && (lane < 2 ? need_h : need_v);
-            for (int k = 0; k < tn; k++) {
-                const int its = __shfl_sync(0xffffffffu, my_its, k);
-                const float w = __shfl_sync(0xffffffffu, my_wl, k) + __shfl_sync(0xffffffffu, my_wr, k);
-                const int qs = q_last + 1 + (its >> 2) - baseq;
-                if (mine && qs >= 0 && qs < nq) step[lane * nq + qs] += w * ae;
-            }
-        }
-        __syncwarp();
+        if (need_h && need_v) synth_group<true, true>(db, rec, g, taps, gi, xstep, zstep, ng10, R.sd, acc, step, nq, baseq, lane);
+        else if (need_h) synth_group<true, false>(db, rec, g, taps, gi, xstep, zstep, ng10, R.sd, acc, step, nq, baseq, lane);
+        else if (need_v) synth_group<false, true>(db, rec, g, taps, gi, xstep, zstep, ng10, R.sd, acc, step, nq, baseq, lane);
     }
     __syncthreads();
     // ---- reduce the warps' strips (fixed order: deterministic) -------------------------------------
@@ -707,6 +759,266 @@ __global__ void __launch_bounds__(128) k_misfit_td(const ReceiverDev* __restrict
     }
 }
 
+// =================================================================================================
+// K6/K7: general misfit kernel -- everything k_misfit_td does not cover: amplitude-spectrum norms
+// (comparator.f90:861-909), norms of band-pass filtered traces (make_spectrum_filtered /
+// make_array_filtered :1217-1263) and floating-shift norms (receiver.f90:439-510).  One CTA per
+// (candidate, receiver); reference and synthetic of a component are transformed together as
+// z = ref + i*syn with one complex FFT in shared memory (decimation in frequency forward, natural ->
+// bit-reversed; decimation in time inverse, bit-reversed -> natural), so the real-filter product and
+// the inverse transform act on both traces at once.
+// =================================================================================================
+__device__ __forceinline__ float ip_cos_dev(float x0, float y0, float x1, float y1, float xi) {   // piecewise_linear_function.f90:308-316
+    if (y1 != y0) return y0 + (y1 - y0) * (0.5f - 0.5f * cosf((xi - x0) / (x1 - x0) * 3.14159265358979f));
+    return y0;
+}
+// multiplier that plf_taper_array_{r,c} (piecewise_linear_function.f90:195-282) applies to element j
+// of an array sampled at dx: 0 for j <= floor(x1/dx) and j >= floor(xn/dx)+1, the interpolated
+// flank value in between (ip_cos) or the 0/1 mask of ip_zero_one (:318-327)
+__device__ float plf_factor(const float* px, const float* py, int np, float dx, int j, bool zero_one) {
+    if (j <= (int)floorf(px[0] / dx)) return 0.f;
+    if (j >= (int)floorf(px[np - 1] / dx) + 1) return 0.f;
+    for (int i = 0; i < np - 1; i++) {
+        const int ibeg = (int)floorf(px[i] / dx) + 1, iend = (int)floorf(px[i + 1] / dx);
+        if (j >= ibeg && j <= iend) {
+            if (zero_one) return (py[i] == 0.f && py[i + 1] == 0.f) ? 0.f : 1.f;
+            return ip_cos_dev(px[i], py[i], px[i + 1], py[i + 1], (float)j * dx);
+        }
+    }
+    return 1.f;
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// forward transform exp(-i...), natural order in, bit-reversed order out
+__device__ void fft_dif_forward(float2* z, int n, const float2* __restrict__ tw, int tw_n) {
+    for (int half = n >> 1; half >= 1; half >>= 1) {
+        const int tstride = tw_n / (2 * half);
+        for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+            const int j = t & (half - 1);
+            const int i0 = ((t - j) << 1) + j, i1 = i0 + half;
+            const float2 a = z[i0], b = z[i1];
+            z[i0] = make_float2(a.x + b.x, a.y + b.y);
+            z[i1] = cmul(make_float2(a.x - b.x, a.y - b.y), __ldg(&tw[j * tstride]));
+        }
+        __syncthreads();
+    }
+}
+// inverse transform exp(+i...), bit-reversed order in, natural order out, unnormalised
+__device__ void fft_dit_inverse(float2* z, int n, const float2* __restrict__ tw, int tw_n) {
+    for (int half = 1; half < n; half <<= 1) {
+        const int tstride = tw_n / (2 * half);
+        for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+            const int j = t & (half - 1);
+            const int i0 = ((t - j) << 1) + j, i1 = i0 + half;
+            float2 w = __ldg(&tw[j * tstride]); w.y = -w.y;
+            const float2 a = z[i0], b = cmul(z[i1], w);
+            z[i0] = make_float2(a.x + b.x, a.y + b.y);
+            z[i1] = make_float2(a.x - b.x, a.y - b.y);
+        }
+        __syncthreads();
+    }
+}
+
+// block-wide reductions of two doubles at once (sum or max); result valid in all threads
+__device__ void block_reduce2(double& a, double& b, bool is_max, double* scratch /* [2*32] */) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int o = 16; o; o >>= 1) {
+        const double ta = __shfl_xor_sync(0xffffffffu, a, o), tb = __shfl_xor_sync(0xffffffffu, b, o);
+        if (is_max) { a = fmax(a, ta); b = fmax(b, tb); } else { a += ta; b += tb; }
+    }
+    __syncthreads();
+    if (lane == 0) { scratch[wid] = a; scratch[32 + wid] = b; }
+    __syncthreads();
+    a = scratch[0]; b = scratch[32];
+    for (int w = 1; w < nw; w++) {
+        if (is_max) { a = fmax(a, scratch[w]); b = fmax(b, scratch[32 + w]); } else { a += scratch[w]; b += scratch[32 + w]; }
+    }
+    __syncthreads();
+}
+
+// accumulate one element of the two-trace norm and of the reference-only norm (comparator.f90:627-697)
+__device__ __forceinline__ void norm_accum2(int bm, float a, float b, float fa, float fb, bool unit, double& acc) {
+    if (bm == 1) { const double d = (double)(unit ? a - b : fa * a - fb * b); acc += d * d; }
+    else if (bm == 2) acc += (double)fabsf(unit ? a - b : fa * a - fb * b);
+    else if (bm == 5) acc += (double)(unit ? a * b : a * fa * b * fb);
+    else { const double xx = (double)(fa * a), yy = (double)(fb * b); acc = fmax(acc, sqrt(xx * xx + yy * yy)); }
+}
+__device__ __forceinline__ void norm_accum1(int bm, float a, double& acc) {
+    if (bm == 1) { const double d = (double)a; acc += d * d; }
+    else if (bm == 2) acc += (double)fabsf(a);
+    else if (bm == 5) acc += (double)(a * a);
+    else acc = fmax(acc, (double)fabsf(a));
+}
+__device__ __forceinline__ void norm_finish(int bm, double acc, double accn, float dx, float fa, float& mis, float& nf) {
+    if (bm == 1) { mis = (float)sqrt((double)dx * acc); nf = fa * (float)sqrt((double)dx * accn); }
+    else if (bm == 2) { mis = (float)((double)dx * acc); nf = fa * (float)((double)dx * accn); }
+    else if (bm == 5) { mis = (float)acc; nf = fa * fa * (float)accn; }
+    else { mis = (float)acc; nf = fa * (float)accn; }
+}
+
+__global__ void __launch_bounds__(256) k_misfit_general(const ReceiverDev* __restrict__ rcv, int nrcv, const CandDev* __restrict__ cands,
+                                                         const float* __restrict__ seis, size_t seis_stride,
+                                                         const SeisHdr* __restrict__ shdrs, const float* __restrict__ refdata,
+                                                         const float* __restrict__ taperdata, const float2* __restrict__ tw, int tw_n,
+                                                         int method, float dt, float syn_factor, int nmisfits, float* __restrict__ out,
+                                                         int* __restrict__ status, int* __restrict__ fshift, int n_alloc, int nshift_alloc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* z = reinterpret_cast<float2*>(smem_raw);
+    float* sm_m = reinterpret_cast<float*>(z + n_alloc);
+    float* sm_n = sm_m + (size_t)nshift_alloc * KIWI_MAX_COMP;
+    __shared__ double scratch[64];
+    const int pair = blockIdx.x;
+    const int b = pair / nrcv, ir = pair % nrcv;
+    const ReceiverDev& R = rcv[ir];
+    if (!R.enabled || R.ncomp == 0) return;
+    const CandDev cand = cands[b];
+    float* o = out + ((size_t)b * nmisfits + R.misfit_base) * 2;
+    const bool floating = method >= 7;
+    const int bm = method == 7 ? 1 : (method == 8 ? 2 : (method == 3 ? 1 : (method == 4 ? 2 : method)));   // norm applied
+    const bool freq = method == 3 || method == 4;
+    const int nshift = floating ? (R.fs1 - R.fs0 + 1) : 1;
+    bool fail = cand.status != 0 || nshift < 1 || nshift > nshift_alloc;
+    for (int ic = 0; ic < R.ncomp && !fail; ic++) if (shdrs[(size_t)pair * KIWI_MAX_COMP + ic].hi < shdrs[(size_t)pair * KIWI_MAX_COMP + ic].lo) fail = true;
+    if (fail) {
+        if (threadIdx.x < R.ncomp) { o[2 * threadIdx.x] = nanf(""); o[2 * threadIdx.x + 1] = nanf(""); }
+        if (threadIdx.x == 0) { if (cand.status == 0) atomicMax(&status[b], 1); if (fshift) fshift[pair] = 0; }
+        return;
+    }
+    const float* tp = taperdata + R.taper_off;
+    const float fa = 1.f, fb = syn_factor;
+    const bool unit = (fa == 1.f && fb == 1.f);
+    const float moment = cand.moment;
+    const bool tapered = R.has_taper != 0, filtered = R.has_filter != 0;
+
+    for (int ic = 0; ic < R.ncomp; ic++) {
+        const SeisHdr sh = shdrs[(size_t)pair * KIWI_MAX_COMP + ic];
+        const float* srow = seis + ((size_t)pair * KIWI_MAX_COMP + ic) * seis_stride;
+        const float* rdat = refdata + R.ref_off[ic];
+        const int sds0 = sh.lo, sds1 = sh.hi;
+        int rds0 = R.ref_ds0[ic], rds1 = R.ref_ds1[ic];
+        int rsp0 = R.ref_sp0[ic], rsp1 = R.ref_sp1[ic];
+        int ssp0, ssp1;
+        allowed_span(sds0, sds1, ceil_len2(sds1 - sds0 + 1), ssp0, ssp1);   // probe_set_array(syn) on a fresh probe
+        const int rlen = rds1 - rds0 + 1;
+        int shift_total = 0;
+        for (int i = 0; i < nshift; i++) {
+            if (floating) {   // probe_shift (comparator.f90:273-288): the span only grows (:245-249)
+                const int ishift = (i == 0) ? R.fs0 : 1;
+                shift_total += ishift;
+                rds0 += ishift; rds1 += ishift;
+                allowed_span(min(rds0, rsp0), max(rds1, rsp1), ceil_len2(rlen), rsp0, rsp1);
+            }
+            {   // probes_adjust_spans (comparator.f90:464-486)
+                const int u0 = min(rds0, sds0), u1 = max(rds1, sds1);
+                const int minlength = max(ceil_len2(rlen), ceil_len2(sds1 - sds0 + 1));
+                int n0, n1;
+                allowed_span(u0, u1, minlength, n0, n1);
+                const bool same = (rsp0 == ssp0 && rsp1 == ssp1) && ((rsp1 - rsp0) == (n1 - n0)) && (rsp0 <= sds0 && sds1 <= rsp1) &&
+                                  (ssp0 <= rds0 && rds1 <= ssp1);
+                if (!same) { rsp0 = ssp0 = n0; rsp1 = ssp1 = n1; }
+            }
+            const int F0 = rsp0, F1 = rsp1, n = F1 - F0 + 1;
+            // element x of the probe arrays with the continuation rule (comparator.f90:264-267) and the taper
+            auto refval = [&](int x) -> float {
+                if (x < rds0) return 0.f;
+                float v = rdat[min(x, rds1) - rds0];
+                if (tapered) v = (x >= R.tp0 && x <= R.tp1) ? v * tp[x - R.tp0] : 0.f;
+                return v;
+            };
+            auto synval = [&](int x) -> float {
+                if (x < sds0) return 0.f;
+                float v = srow[min(x, sds1) - sh.base] * moment;
+                if (tapered) v = (x >= R.tp0 && x <= R.tp1) ? v * tp[x - R.tp0] : 0.f;
+                return v;
+            };
+            // summation spans of the time-domain norms (comparator.f90:784-801, 838-846)
+            int p0, p1, q0, q1;
+            if (tapered) { p0 = max(R.dps0, F0); p1 = min(R.dps1, F1); q0 = p0; q1 = p1; }
+            else { p0 = min(rds0, sds0); p1 = max(rds1, sds1); q0 = rds0; q1 = rds1; }
+            double acc = (bm == 6) ? -DBL_MAX : 0., accn = (bm == 6) ? -DBL_MAX : 0.;
+            float dx = dt;
+            bool bad = false;
+            if (!freq && !filtered) {
+                for (int x = p0 + threadIdx.x; x <= p1; x += blockDim.x) norm_accum2(bm, refval(x), synval(x), fa, fb, unit, acc);
+                for (int x = q0 + threadIdx.x; x <= q1; x += blockDim.x) norm_accum1(bm, refval(x), accn);
+            } else if (n > n_alloc || n < 2 || (n & (n - 1)) != 0) {
+                bad = true;
+            } else {
+                for (int j = threadIdx.x; j < n; j += blockDim.x) z[j] = make_float2(refval(F0 + j), synval(F0 + j));
+                __syncthreads();
+                fft_dif_forward(z, n, tw, tw_n);
+                int log2n = 0; while ((1 << log2n) < n) log2n++;
+                const float df = 1.f / ((float)n * dt);   // comparator.f90:1213
+                if (freq) {
+                    dx = df;
+                    for (int k = threadIdx.x; k <= (n >> 1); k += blockDim.x) {
+                        const int pk = (int)(__brev((unsigned)k) >> (32 - log2n));
+                        const int pm = (int)(__brev((unsigned)((n - k) & (n - 1))) >> (32 - log2n));
+                        const float2 zk = z[pk], zm = z[pm];
+                        // Ref_k = (Z_k + conj Z_{n-k})/2, Syn_k = (Z_k - conj Z_{n-k})/(2i)
+                        const float rr = 0.5f * (zk.x + zm.x), ri = 0.5f * (zk.y - zm.y);
+                        const float sr = 0.5f * (zk.y + zm.y), si = -0.5f * (zk.x - zm.x);
+                        float A = sqrtf(rr * rr + ri * ri), B = sqrtf(sr * sr + si * si);
+                        if (filtered) { const float hfac = plf_factor(R.fpx, R.fpy, R.nfp, df, k, false); A *= hfac; B *= hfac; }
+                        norm_accum2(bm, A, B, fa, fb, unit, acc);
+                        norm_accum1(bm, A, accn);
+                    }
+                } else {
+                    // spectrum_filtered = spectrum * filter(k df) (comparator.f90:1217-1231), applied to bins k and n-k alike
+                    for (int pz = threadIdx.x; pz < n; pz += blockDim.x) {
+                        const int k = (int)(__brev((unsigned)pz) >> (32 - log2n));
+                        const int kk = k <= (n >> 1) ? k : n - k;
+                        const float hfac = plf_factor(R.fpx, R.fpy, R.nfp, df, kk, false);
+                        z[pz].x *= hfac; z[pz].y *= hfac;
+                    }
+                    __syncthreads();
+                    fft_dit_inverse(z, n, tw, tw_n);
+                    const float fn = (float)n;
+                    for (int j = threadIdx.x; j < n; j += blockDim.x) {   // comparator.f90:1250-1261
+                        float2 v = z[j]; v.x = v.x / fn; v.y = v.y / fn;
+                        if (tapered) { const float m01 = plf_factor(R.tpx, R.tpy, R.ntp, dt, F0 + j, true); v.x *= m01; v.y *= m01; }
+                        z[j] = v;
+                    }
+                    __syncthreads();
+                    for (int x = p0 + threadIdx.x; x <= p1; x += blockDim.x) { const float2 v = z[x - F0]; norm_accum2(bm, v.x, v.y, fa, fb, unit, acc); }
+                    for (int x = q0 + threadIdx.x; x <= q1; x += blockDim.x) norm_accum1(bm, z[x - F0].x, accn);
+                }
+            }
+            block_reduce2(acc, accn, bm == 6, scratch);
+            if (threadIdx.x == 0) {
+                float mis, nf;
+                norm_finish(bm, acc, accn, dx, fa, mis, nf);
+                if (!freq && p1 < p0) mis = 0.f;          // "applying timedomain norm to empty region" (comparator.f90:803-807)
+                if (!freq && q1 < q0) nf = (bm == 6) ? fa * -FLT_MAX : 0.f;
+                if (bad) { mis = nanf(""); nf = nanf(""); atomicMax(&status[b], 3); }
+                sm_m[i * KIWI_MAX_COMP + ic] = mis; sm_n[i * KIWI_MAX_COMP + ic] = nf;
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) {
+        int iloc = 0;
+        if (floating) {   // minloc(sum(misfits[**2],1),1): first minimum (receiver.f90:486-494)
+            float best = 0.f;
+            for (int i = 0; i < nshift; i++) {
+                float s = 0.f;
+                for (int ic = 0; ic < R.ncomp; ic++) { const float m = sm_m[i * KIWI_MAX_COMP + ic]; s = s + (bm == 2 ? m : m * m); }
+                if (i == 0 || s < best) { best = s; iloc = i; }
+            }
+            if (fshift) fshift[pair] = R.fs0 + iloc;
+        } else if (fshift) fshift[pair] = 0;
+        for (int ic = 0; ic < R.ncomp; ic++) {
+            const float mis = sm_m[iloc * KIWI_MAX_COMP + ic];
+            float nf;
+            if (floating) { float s = 0.f; for (int i = 0; i < nshift; i++) s = s + sm_n[i * KIWI_MAX_COMP + ic]; nf = s / (float)nshift; }
+            else nf = sm_n[ic];
+            o[2 * ic] = mis; o[2 * ic + 1] = nf;
+            if (!isfinite(mis) || !isfinite(nf)) atomicMax(&status[b], 2);
+        }
+    }
+}
+
 // ---- host-callable launch wrappers ---------------------------------------------------------------
 void launch_bilat_groups(const BilatCand* d_cands, int ncand, GroupSoA g, TapSoA taps, float dt, int ngroups_total, cudaStream_t st) {
     if (ncand > 0) k_bilat_groups<<<ncand, 128, 0, st>>>(d_cands, g, taps, dt, ngroups_total);
@@ -718,9 +1030,9 @@ void launch_group_tap_range(GroupSoA g, TapSoA taps, float dt, int gbegin, int g
 void launch_expand_centroids(CandDev cand, GroupSoA g, TapSoA taps, int ngroups_total, float* d_table, int cap, cudaStream_t st) {
     k_expand_centroids<<<(cand.ngroups + 127) / 128, 128, 0, st>>>(cand, g, taps, ngroups_total, d_table, cap);
 }
-void launch_geometry(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, int interpolate,
-                     int xunder, int zunder, GeoRec* recs, size_t rec_stride, PairHdr* hdrs, int* tmax, cudaStream_t st) {
-    k_geometry<<<ncand * nrcv, 256, 0, st>>>(db, rcv, nrcv, cands, g, interpolate, xunder, zunder, recs, rec_stride, hdrs, tmax);
+void launch_geometry(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, int ngroups_total,
+                     int interpolate, int xunder, int zunder, GeoRec* recs, size_t rec_stride, PairHdr* hdrs, int* tmax, cudaStream_t st) {
+    k_geometry<<<ncand * nrcv, 256, 0, st>>>(db, rcv, nrcv, cands, g, ngroups_total, interpolate, xunder, zunder, recs, rec_stride, hdrs, tmax);
 }
 size_t synth_smem_bytes(int nwarps, int nq) { return (size_t)nwarps * 3 * nq * (sizeof(float4) + sizeof(float)); }
 cudaError_t launch_synth(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, TapSoA taps,
@@ -742,4 +1054,20 @@ void launch_misfit_td(const ReceiverDev* rcv, int nrcv, const CandDev* cands, in
     if (blocks > 0)
         k_misfit_td<<<blocks, 128, 0, st>>>(rcv, nrcv, cands, ncand, seis, seis_stride, shdrs, refdata, taperdata, method, dt, syn_factor,
                                             nmisfits, out, status);
+}
+
+size_t misfit_general_smem_bytes(int n_alloc, int nshift_alloc) {
+    return (size_t)n_alloc * sizeof(float2) + (size_t)2 * nshift_alloc * KIWI_MAX_COMP * sizeof(float);
+}
+cudaError_t launch_misfit_general(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, const float* seis, size_t seis_stride,
+                                  const SeisHdr* shdrs, const float* refdata, const float* taperdata, const float2* tw, int tw_n, int method,
+                                  float dt, float syn_factor, int nmisfits, float* out, int* status, int* fshift, int n_alloc,
+                                  int nshift_alloc, cudaStream_t st) {
+    const size_t smem = misfit_general_smem_bytes(n_alloc, nshift_alloc);
+    cudaError_t e = cudaFuncSetAttribute(k_misfit_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (ncand * nrcv > 0)
+        k_misfit_general<<<ncand * nrcv, 256, smem, st>>>(rcv, nrcv, cands, seis, seis_stride, shdrs, refdata, taperdata, tw, tw_n, method, dt,
+                                                         syn_factor, nmisfits, out, status, fshift, n_alloc, nshift_alloc);
+    return cudaGetLastError();
 }

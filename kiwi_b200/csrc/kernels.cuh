@@ -17,8 +17,8 @@ struct BilatCand {
 void launch_bilat_groups(const BilatCand* d_cands, int ncand, GroupSoA g, TapSoA taps, float dt, int ngroups_total, cudaStream_t st);
 void launch_group_tap_range(GroupSoA g, TapSoA taps, float dt, int gbegin, int gend, cudaStream_t st);
 void launch_expand_centroids(CandDev cand, GroupSoA g, TapSoA taps, int ngroups_total, float* d_table, int cap, cudaStream_t st);
-void launch_geometry(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, int interpolate,
-                     int xunder, int zunder, GeoRec* recs, size_t rec_stride, PairHdr* hdrs, int* tmax, cudaStream_t st);
+void launch_geometry(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, int ngroups_total,
+                     int interpolate, int xunder, int zunder, GeoRec* recs, size_t rec_stride, PairHdr* hdrs, int* tmax, cudaStream_t st);
 size_t synth_smem_bytes(int nwarps, int nq);
 cudaError_t launch_synth(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, TapSoA taps,
                          int ngroups_total, int interpolate, int xunder, int zunder, const GeoRec* recs, size_t rec_stride,
@@ -27,3 +27,8 @@ cudaError_t launch_synth(GfdbDev db, const ReceiverDev* rcv, int nrcv, const Can
 void launch_misfit_td(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, const float* seis, size_t seis_stride,
                       const SeisHdr* shdrs, const float* refdata, const float* taperdata, int method, float dt, float syn_factor,
                       int nmisfits, float* out, int* status, cudaStream_t st);
+size_t misfit_general_smem_bytes(int n_alloc, int nshift_alloc);
+cudaError_t launch_misfit_general(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, const float* seis, size_t seis_stride,
+                                  const SeisHdr* shdrs, const float* refdata, const float* taperdata, const float2* tw, int tw_n, int method,
+                                  float dt, float syn_factor, int nmisfits, float* out, int* status, int* fshift, int n_alloc,
+                                  int nshift_alloc, cudaStream_t st);

@@ -6,6 +6,7 @@
 
 #define KIWI_MAX_COMP 5          // receiver.f90:35-48: at most a/c r/l d/u n/s e/w
 #define KIWI_NG_MAX 10
+#define KIWI_MAX_PLF 8           // points of a taper / filter piecewise linear function kept on the device
 
 // ---- Green's function database in HBM -----------------------------------------------------------
 // One slab per grid node (ix,iz): ng rows of `wn` fp32 samples, all rows on the node's common
@@ -48,8 +49,12 @@ struct ReceiverDev {
     int dps0, dps1;              // discrete_plf_span (comparator.f90:1145-1157)
     long long taper_off;         // offset into d_taper
     int has_filter;
-    long long filter_id;
     int fs0, fs1;                // floating shift range in samples
+    // the piecewise linear functions themselves (piecewise_linear_function.f90:27-35): the filter is
+    // evaluated at k*df on the device because df depends on the padded span of each candidate
+    int ntp, nfp;
+    float tpx[KIWI_MAX_PLF], tpy[KIWI_MAX_PLF];
+    float fpx[KIWI_MAX_PLF], fpy[KIWI_MAX_PLF];
 };
 
 // ---- discretised sources (device SoA; discrete_source.f90:27-45 made column-wise) -----------------
@@ -76,12 +81,13 @@ struct TapSoA {
 };
 
 // ---- per (candidate, receiver, group) geometry record written by the pre-pass ---------------------
-struct GeoRec {
+struct __align__(16) GeoRec {
     int ix1, iz1;       // gfdb_get_indices[_bilin] gfdb.f90:781-815
     float dix, diz;
-    float azi;          // real(azi) fed to make_weights, seismogram.f90:144
+    float f[6];         // make_weights(real(azi), mhat) seismogram.f90:316-336 (tap weight applied later)
     float cl, sl;       // real(cos/sin(bazi - bazi0)), seismogram.f90:163-164
     int flags;
+    int pad[3];
 };
 #define GEO_SKIP 1      // a needed node is outside the database: centroid skipped (seismogram.f90:172)
 #define GEO_ROT 2       // lambda /= 0: per-centroid rotation branch (seismogram.f90:160)

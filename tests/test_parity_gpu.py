@@ -202,3 +202,77 @@ def test_medium_source_against_fp32_and_double_accumulating_oracle():
     d32, dw, d32w = dev(mg, mo), dev(mg, mw), dev(mo, mw)
     assert dw <= RTOL, (d32, dw, d32w)
     assert d32 <= max(RTOL, 2.0 * d32w), (d32, dw, d32w)
+
+
+FILTER = ([0.2, 0.5, 2.0, 3.0], [0, 1, 1, 0])      # band-pass, Hz (shape of python/tunguska/filtering.py:14-19)
+TAPER = ([1.0, 1.6, 4.0, 5.2], [0, 1, 1, 0])
+
+
+def _spectral_setup(norm, taper, filt, comps=COMPS6):
+    g, o = engines(sc.small_db(), comps)
+    ncomps = [len(c) for c in comps]
+    o.eval_sources("bilateral", sc.BILAT_SMALL)
+    sc.set_refs_from(o, [g, o], ncomps)
+    for e in (g, o):
+        e.set_misfit_method(norm)
+        if taper:
+            for ir in range(1, len(comps) + 1):
+                e.set_misfit_taper(ir, *TAPER)
+        if filt:
+            e.set_misfit_filter(*FILTER)
+    return g, o
+
+
+@pytest.mark.parametrize("norm", ["ampspec_l2norm", "ampspec_l1norm"])
+@pytest.mark.parametrize("taper,filt", [(False, False), (True, False), (True, True), (False, True)])
+def test_amplitude_spectrum_misfits(norm, taper, filt):
+    """comparator.f90:861-909 through the shared-memory FFT kernel"""
+    g, o = _spectral_setup(norm, taper, filt)
+    p = _candidates()
+    mg, sg = g.eval_sources("bilateral", p)
+    mo, so = o.eval_sources("bilateral", p)
+    assert not sg.any() and not so.any()
+    assert np.all(np.abs(mg - mo) <= misfit_tol(mo)), np.abs((mg - mo) / misfit_tol(mo)).max()
+
+
+@pytest.mark.parametrize("norm", ["l2norm", "l1norm", "scalar_product", "peak"])
+@pytest.mark.parametrize("taper", [False, True])
+def test_filtered_time_domain_misfits(norm, taper):
+    """make_spectrum_filtered / make_array_filtered (comparator.f90:1217-1263): r2c -> filter -> c2r -> norm"""
+    g, o = _spectral_setup(norm, taper, True)
+    p = _candidates()
+    mg, sg = g.eval_sources("bilateral", p)
+    mo, so = o.eval_sources("bilateral", p)
+    assert not sg.any() and not so.any()
+    tol = misfit_tol(mo)
+    assert np.all(np.abs(mg - mo) <= tol), np.abs((mg - mo) / tol).max()
+
+
+@pytest.mark.parametrize("norm", ["floating_l2norm", "floating_l1norm"])
+@pytest.mark.parametrize("taper,filt", [(False, False), (True, False), (True, True)])
+def test_floating_misfits(norm, taper, filt):
+    """receiver_calculate_floating_misfits (receiver.f90:439-510): best integer shift over all components"""
+    g, o = engines(sc.small_db(), COMPS6)
+    ncomps = [len(c) for c in COMPS6]
+    o.eval_sources("bilateral", sc.BILAT_SMALL)
+    sc.set_refs_from(o, [g, o], ncomps, shift=3)          # references late by 3 samples
+    for e in (g, o):
+        e.set_misfit_method(norm)
+        e.set_floating_shiftrange(-0.6, 0.5)
+        e.set_floating_shiftrange(-0.2, 0.9, 2)      # receiver 2: a range that excludes the true shift
+        if taper:
+            for ir in range(1, 7):
+                e.set_misfit_taper(ir, *TAPER)
+        if filt:
+            e.set_misfit_filter(*FILTER)
+    p = _candidates()
+    mg, sg = g.eval_sources("bilateral", p)
+    mo, so = o.eval_sources("bilateral", p)
+    assert not sg.any() and not so.any()
+    assert np.all(np.abs(mg - mo) <= misfit_tol(mo)), np.abs((mg - mo) / misfit_tol(mo)).max()
+    # the shift itself is an integer result: exact
+    o.eval_sources("bilateral", p[0])
+    g.set_source_params("bilateral", p[0])
+    g.get_misfits()
+    assert list(g.get_floating_shifts()) == list(o.get_floating_shifts())
+    assert list(g.get_floating_shifts())[0] == -3
