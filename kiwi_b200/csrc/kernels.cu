@@ -20,6 +20,11 @@ __device__ __forceinline__ float S_(float a, float b) { return __fsub_rn(a, b); 
 __device__ __forceinline__ float M_(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float D_(float a, float b) { return __fdiv_rn(a, b); }
 
+__device__ __forceinline__ NodeInfo ld_node(const NodeInfo* p) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    NodeInfo n; n.off = ((unsigned long long)u.y << 32) | u.x; n.w0 = (int)u.z; n.wn = (int)u.w;
+    return n;
+}
 __device__ __forceinline__ int floordiv4(int x) { return x >> 2; }            // arithmetic shift = floor
 __device__ __forceinline__ int floor4(int x) { return x & ~3; }
 
@@ -230,14 +235,21 @@ __global__ void __launch_bounds__(256) k_geometry(GfdbDev db, const ReceiverDev*
             int inode[4]; int ncorner = single ? 1 : 4;
             const int cx[4] = {ix1, ix1, ix2, ix2}, cz[4] = {iz1, iz2, iz1, iz2};
             bool ok = true;
-            for (int c = 0; c < ncorner; c++) {
-                if (cx[c] < 1 || cx[c] > db.nx || cz[c] < 1 || cz[c] > db.nz) { ok = false; inode[c] = 0; continue; }
+            for (int c = 0; c < 4; c++) {
+                if (c >= ncorner) { rec.node[c] = rec.node[0]; continue; }
+                if (cx[c] < 1 || cx[c] > db.nx || cz[c] < 1 || cz[c] > db.nz) { ok = false; inode[c] = 0; rec.node[c].off = ~0ull; rec.node[c].w0 = 0; rec.node[c].wn = 4; continue; }
                 inode[c] = (cx[c] - 1) * db.nz + (cz[c] - 1);
-                if (__ldg(&db.nodes[inode[c]].off) == ~0ull) ok = false;
+                rec.node[c] = ld_node(&db.nodes[inode[c]]);
+                if (rec.node[c].off == ~0ull) ok = false;
             }
             if (!ok) flags |= GEO_SKIP;
             rec.ix1 = ix1; rec.iz1 = iz1; rec.dix = dix; rec.diz = diz; rec.flags = flags;
-            myrecs[ip] = rec;
+            {   // 128-byte record, eight 128-bit stores
+                const uint4* sp = reinterpret_cast<const uint4*>(&rec);
+                uint4* dp = reinterpret_cast<uint4*>(myrecs + ip);
+#pragma unroll
+                for (int k = 0; k < 8; k++) dp[k] = sp[k];
+            }
             if (ok && (need_h || need_v)) {
                 const int smin = g.its_min[gi], smax = g.its_max[gi];
                 int lo, hi;
@@ -326,11 +338,6 @@ __global__ void __launch_bounds__(256) k_geometry(GfdbDev db, const ReceiverDev*
 // =================================================================================================
 #define SYN_MAXTAPS 32
 
-__device__ __forceinline__ NodeInfo ld_node(const NodeInfo* p) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
-    NodeInfo n; n.off = ((unsigned long long)u.y << 32) | u.x; n.w0 = (int)u.z; n.wn = (int)u.w;
-    return n;
-}
 __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ void fma4(float4& a, float s, const float4& v) {
     a.x = fmaf(s, v.x, a.x); a.y = fmaf(s, v.y, a.y); a.z = fmaf(s, v.z, a.z); a.w = fmaf(s, v.w, a.w);
@@ -370,10 +377,20 @@ __device__ __forceinline__ void tap_strips(float4* a1, float4* a2, float4* a3, c
     if (V) { float4 o = *a3; tap_quad<S>(o, P3, A3, wl, wr); *a3 = o; }
 }
 
+// asynchronous copy of one 128-byte group record into shared memory (lanes 0..7, 16 bytes each)
+__device__ __forceinline__ void rec_prefetch(const GeoRec* __restrict__ recs, int ip, int ngroups, GeoRec* dst_slot, int lane) {
+    if (ip < ngroups && lane < 8) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(reinterpret_cast<uint4*>(dst_slot) + lane);
+        const uint4* src = reinterpret_cast<const uint4*>(recs + ip) + lane;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 // One warp, one group.  H/V: the receiver has horizontal / vertical components.
 template <bool H, bool V>
-__device__ __forceinline__ void synth_group(const GfdbDev& db, const GeoRec& rec, const GroupSoA& g, const TapSoA& taps, int gi, int xstep,
-                                            int zstep, bool ng10, float sd, float4* __restrict__ acc, float* __restrict__ step, int nq,
+__device__ __forceinline__ void synth_group(const GfdbDev& db, const GeoRec& rec, const GroupSoA& g, const TapSoA& taps, int gi,
+                                            bool ng10, float sd, float4* __restrict__ acc, float* __restrict__ step, int nq,
                                             int baseq, int lane) {
     const float dt = db.dt;
     // ---- corners (gfdb.f90:943-948 weights in the reference's association) -------------------------
@@ -381,11 +398,7 @@ __device__ __forceinline__ void synth_group(const GfdbDev& db, const GeoRec& rec
     const float dix = rec.dix, diz = rec.diz;
     const float wc0 = single ? 1.f : (1.f - dix) * (1.f - diz), wc1 = single ? 0.f : (1.f - dix) * diz,
                 wc2 = single ? 0.f : dix * (1.f - diz), wc3 = single ? 0.f : dix * diz;
-    const int inode0 = (rec.ix1 - 1) * db.nz + (rec.iz1 - 1);
-    const NodeInfo n0 = ld_node(&db.nodes[inode0]);
-    const NodeInfo n1 = single ? n0 : ld_node(&db.nodes[inode0 + zstep]);
-    const NodeInfo n2 = single ? n0 : ld_node(&db.nodes[inode0 + xstep * db.nz]);
-    const NodeInfo n3 = single ? n0 : ld_node(&db.nodes[inode0 + xstep * db.nz + zstep]);
+    const NodeInfo n0 = rec.node[0], n1 = rec.node[1], n2 = rec.node[2], n3 = rec.node[3];
     const float4* b0 = reinterpret_cast<const float4*>(db.slabs + n0.off);
     const float4* b1 = reinterpret_cast<const float4*>(db.slabs + n1.off);
     const float4* b2 = reinterpret_cast<const float4*>(db.slabs + n2.off);
@@ -427,21 +440,25 @@ __device__ __forceinline__ void synth_group(const GfdbDev& db, const GeoRec& rec
             const float c0 = o0 < 0 ? 0.f : wc0, c1 = o1 < 0 ? 0.f : wc1, c2 = o2 < 0 ? 0.f : wc2, c3 = o3 < 0 ? 0.f : wc3;
             // software pipeline over the GF components: the four corner quads of component i+2 are in
             // flight while component i is combined (keeps ~12 128-bit loads per lane outstanding)
-#define KIWI_LOAD(buf, ig) { buf[0] = __ldg(p0 + (ig) * nq0); buf[1] = __ldg(p1 + (ig) * nq1); buf[2] = __ldg(p2 + (ig) * nq2); buf[3] = __ldg(p3 + (ig) * nq3); }
+            // running row pointers: KIWI_LOAD fetches the current component's four corner quads and
+            // steps to the next component's rows
+#define KIWI_LOAD(buf) { buf[0] = __ldg(r0); buf[1] = __ldg(r1); buf[2] = __ldg(r2); buf[3] = __ldg(r3); r0 += nq0; r1 += nq1; r2 += nq2; r3 += nq3; }
+#define KIWI_SKIP(n) { r0 += (n) * nq0; r1 += (n) * nq1; r2 += (n) * nq2; r3 += (n) * nq3; }
 #define KIWI_COMB(buf, dst, wgt) { float4 r = f4zero(); fma4(r, c0, buf[0]); fma4(r, c1, buf[1]); fma4(r, c2, buf[2]); fma4(r, c3, buf[3]); fma4(dst, wgt, r); }
+            const float4 *r0 = p0, *r1 = p1, *r2 = p2, *r3 = p3;
             float4 ta[4], tb[4], tc[4];
             if (H && V) {
                 float4 Rr = f4zero(), Tt = f4zero();
-                KIWI_LOAD(ta, 0) KIWI_LOAD(tb, 1) KIWI_LOAD(tc, 2)
-                KIWI_COMB(ta, Rr, f1) KIWI_LOAD(ta, 3)
-                KIWI_COMB(tb, Rr, f2) KIWI_LOAD(tb, 4)
-                KIWI_COMB(tc, Rr, f3) KIWI_LOAD(tc, 5)
-                KIWI_COMB(ta, Tt, f4) KIWI_LOAD(ta, 6)
-                KIWI_COMB(tb, Tt, f5) KIWI_LOAD(tb, 7)
+                KIWI_LOAD(ta) KIWI_LOAD(tb) KIWI_LOAD(tc)                 // g1 g2 g3
+                KIWI_COMB(ta, Rr, f1) KIWI_LOAD(ta)                       // g4
+                KIWI_COMB(tb, Rr, f2) KIWI_LOAD(tb)                       // g5
+                KIWI_COMB(tc, Rr, f3) KIWI_LOAD(tc)                       // g6
+                KIWI_COMB(ta, Tt, f4) KIWI_LOAD(ta)                       // g7
+                KIWI_COMB(tb, Tt, f5) KIWI_LOAD(tb)                       // g8
                 KIWI_COMB(tc, A3, v1)
                 if (ng10) {
-                    KIWI_LOAD(tc, 8)
-                    KIWI_COMB(ta, A3, v2) KIWI_LOAD(ta, 9)
+                    KIWI_LOAD(tc)                                         // g9
+                    KIWI_COMB(ta, A3, v2) KIWI_LOAD(ta)                   // g10
                     KIWI_COMB(tb, A3, v3)
                     KIWI_COMB(tc, Rr, f6)
                     KIWI_COMB(ta, A3, v6)
@@ -454,25 +471,27 @@ __device__ __forceinline__ void synth_group(const GfdbDev& db, const GeoRec& rec
                 fma4(A2, cl, Tt); fma4(A2, sl, Rr);
             } else if (H) {
                 float4 Rr = f4zero(), Tt = f4zero();
-                KIWI_LOAD(ta, 0) KIWI_LOAD(tb, 1) KIWI_LOAD(tc, 2)
-                KIWI_COMB(ta, Rr, f1) KIWI_LOAD(ta, 3)
-                KIWI_COMB(tb, Rr, f2) KIWI_LOAD(tb, 4)
+                KIWI_LOAD(ta) KIWI_LOAD(tb) KIWI_LOAD(tc)                 // g1 g2 g3
+                KIWI_COMB(ta, Rr, f1) KIWI_LOAD(ta)                       // g4
+                KIWI_COMB(tb, Rr, f2) KIWI_LOAD(tb)                       // g5
                 KIWI_COMB(tc, Rr, f3)
-                if (ng10) { KIWI_LOAD(tc, 8) }
+                if (ng10) { KIWI_SKIP(3) KIWI_LOAD(tc) }                  // g9
                 KIWI_COMB(ta, Tt, f4)
                 KIWI_COMB(tb, Tt, f5)
                 if (ng10) { KIWI_COMB(tc, Rr, f6) }
                 fma4(A1, cl, Rr); fma4(A1, -sl, Tt);
                 fma4(A2, cl, Tt); fma4(A2, sl, Rr);
             } else {
-                KIWI_LOAD(ta, 5) KIWI_LOAD(tb, 6) KIWI_LOAD(tc, 7)
+                KIWI_SKIP(5)
+                KIWI_LOAD(ta) KIWI_LOAD(tb) KIWI_LOAD(tc)                 // g6 g7 g8
                 KIWI_COMB(ta, A3, v1)
-                if (ng10) { KIWI_LOAD(ta, 9) }
+                if (ng10) { KIWI_SKIP(1) KIWI_LOAD(ta) }                  // g10
                 KIWI_COMB(tb, A3, v2)
                 KIWI_COMB(tc, A3, v3)
                 if (ng10) { KIWI_COMB(ta, A3, v6) }
             }
 #undef KIWI_LOAD
+#undef KIWI_SKIP
 #undef KIWI_COMB
         }
         // previous quad: lane-1; lane 0 takes the carry of the previous chunk
@@ -564,22 +583,25 @@ __global__ void __launch_bounds__(256, 2) k_synth(GfdbDev db, const ReceiverDev*
     const bool need_v = R.jd != 0;
     const bool ng10 = db.ng == 10;
     const GeoRec* myrecs = recs + (size_t)pair * rec_stride;
-    const int xstep = interpolate ? xunder : 1, zstep = interpolate ? zunder : 1;
-    (void)ngroups_total;
+    (void)ngroups_total; (void)interpolate; (void)xunder; (void)zunder;
 
-    for (int ip = warp; ip < cand.ngroups; ip += nwarps) {
-        GeoRec rec;
-        {   // 64-byte record, four 128-bit loads
-            const uint4* rp = reinterpret_cast<const uint4*>(myrecs + ip);
-            uint4* dp = reinterpret_cast<uint4*>(&rec);
-            dp[0] = __ldg(rp); dp[1] = __ldg(rp + 1); dp[2] = __ldg(rp + 2); dp[3] = __ldg(rp + 3);
-        }
+    // the 128-byte group records are prefetched one group ahead into a per-warp shared-memory slot with
+    // cp.async, so that the data loads of a group can start as soon as the previous group is done
+    GeoRec* slot = reinterpret_cast<GeoRec*>(step_all + (size_t)nwarps * 3 * nq) + 2 * warp;
+    rec_prefetch(myrecs, warp, cand.ngroups, slot, lane);
+    int buf = 0;
+    for (int ip = warp; ip < cand.ngroups; ip += nwarps, buf ^= 1) {
+        rec_prefetch(myrecs, ip + nwarps, cand.ngroups, slot + (buf ^ 1), lane);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        const GeoRec& rec = slot[buf];   // read field by field from shared memory (stays valid: the next prefetch fills the other slot)
         if (rec.flags & GEO_SKIP) continue;
         const int gi = cand.group_begin + ip;
-        if (need_h && need_v) synth_group<true, true>(db, rec, g, taps, gi, xstep, zstep, ng10, R.sd, acc, step, nq, baseq, lane);
-        else if (need_h) synth_group<true, false>(db, rec, g, taps, gi, xstep, zstep, ng10, R.sd, acc, step, nq, baseq, lane);
-        else if (need_v) synth_group<false, true>(db, rec, g, taps, gi, xstep, zstep, ng10, R.sd, acc, step, nq, baseq, lane);
+        if (need_h && need_v) synth_group<true, true>(db, rec, g, taps, gi, ng10, R.sd, acc, step, nq, baseq, lane);
+        else if (need_h) synth_group<true, false>(db, rec, g, taps, gi, ng10, R.sd, acc, step, nq, baseq, lane);
+        else if (need_v) synth_group<false, true>(db, rec, g, taps, gi, ng10, R.sd, acc, step, nq, baseq, lane);
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     // ---- reduce the warps' strips (fixed order: deterministic) -------------------------------------
     for (int i = threadIdx.x; i < 3 * nq; i += blockDim.x) {
@@ -1034,7 +1056,7 @@ void launch_geometry(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev
                      int interpolate, int xunder, int zunder, GeoRec* recs, size_t rec_stride, PairHdr* hdrs, int* tmax, cudaStream_t st) {
     k_geometry<<<ncand * nrcv, 256, 0, st>>>(db, rcv, nrcv, cands, g, ngroups_total, interpolate, xunder, zunder, recs, rec_stride, hdrs, tmax);
 }
-size_t synth_smem_bytes(int nwarps, int nq) { return (size_t)nwarps * 3 * nq * (sizeof(float4) + sizeof(float)); }
+size_t synth_smem_bytes(int nwarps, int nq) { return (size_t)nwarps * 3 * nq * (sizeof(float4) + sizeof(float)) + (size_t)nwarps * 2 * sizeof(GeoRec); }
 cudaError_t launch_synth(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, TapSoA taps,
                          int ngroups_total, int interpolate, int xunder, int zunder, const GeoRec* recs, size_t rec_stride,
                          const PairHdr* hdrs, int nq_alloc, int nwarps, float* seis, size_t seis_stride, SeisHdr* shdrs,

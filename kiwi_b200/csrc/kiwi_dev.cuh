@@ -81,13 +81,14 @@ struct TapSoA {
 };
 
 // ---- per (candidate, receiver, group) geometry record written by the pre-pass ---------------------
-struct __align__(16) GeoRec {
+struct __align__(16) GeoRec {   // 128 bytes: everything k_synth needs to start streaming a group
     int ix1, iz1;       // gfdb_get_indices[_bilin] gfdb.f90:781-815
     float dix, diz;
     float f[6];         // make_weights(real(azi), mhat) seismogram.f90:316-336 (tap weight applied later)
     float cl, sl;       // real(cos/sin(bazi - bazi0)), seismogram.f90:163-164
     int flags;
     int pad[3];
+    NodeInfo node[4];   // slabs of the corners (ix1,iz1) (ix1,iz2) (ix2,iz1) (ix2,iz2); all = corner 0 if GEO_SINGLE
 };
 #define GEO_SKIP 1      // a needed node is outside the database: centroid skipped (seismogram.f90:172)
 #define GEO_ROT 2       // lambda /= 0: per-centroid rotation branch (seismogram.f90:160)
