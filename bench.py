@@ -29,6 +29,10 @@ WORKLOADS = {
     # bench-L analytical full-space database (HBM resident, > L2), time-domain L2 misfit
     "c3": dict(db="bench-L", nx=2000, nz=150, dx=100.0, dz=200.0, nrcv=200, effective_dt=0.35, dmin=45e3, dmax=150e3,
                norm="l2norm", batch=32, cpu_sample=2),
+    # point moment-tensor grid search, (north, east, depth) lattice x unit
+    # tensors on a Fibonacci sphere, rise time 1 s, effective_dt 0.5 -> 3 centroids per candidate
+    "c2": dict(db="bench-L", nx=2000, nz=150, dx=100.0, dz=200.0, nrcv=100, effective_dt=0.5, dmin=45e3, dmax=150e3,
+               norm="l2norm", batch=100000, cpu_sample=2000, source="moment_tensor"),
     # quick functional run (kiwibench-size pieces)
     "small": dict(db="bench-L/8", nx=1000, nz=60, dx=100.0, dz=400.0, nrcv=24, effective_dt=0.5, dmin=45e3, dmax=55e3,
                   norm="l2norm", batch=8, cpu_sample=2),
@@ -159,15 +163,16 @@ def run_reference_arm(args, w, rank):
     rlat, rlon, rdep = synthetic.receivers(w["nrcv"], (30.0, 70.0), w["dmin"], w["dmax"])
     o = OracleEngine(threads=ncores)
     configure(o, db, w, rlat, rlon, rdep)
-    o.eval_sources("bilateral", synthetic.IZMIT)
+    stype, allc, base = candidates(w, max(args.batch, 32))
+    o.eval_sources(stype, base)
     set_references(o, [o], w["nrcv"], db.meta()["dt"])
     sample = max(1, min(args.batch, w["cpu_sample"]))
-    cands = synthetic.bilateral_sweep(max(args.batch, 32))[:sample]
+    cands = allc[:sample]
     for _ in range(min(args.warmup, 1)):
-        o.time_eval("bilateral", cands[:1])
+        o.time_eval(stype, cands[:1])
     t = 0.0
     for _ in range(args.steps):
-        t += o.time_eval("bilateral", cands)
+        t += o.time_eval(stype, cands)
     value = sample * args.steps / t
     threads = olib().oracle_max_threads()
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -179,7 +184,23 @@ def run_reference_arm(args, w, rank):
     print(json.dumps(line), flush=True)
 
 
+def candidates(w, n):
+    """candidate list of the workload and the base source the references come from"""
+    from kiwi_b200 import synthetic
+    if w.get("source") == "moment_tensor":
+        side = max(1, int(round((n / 100.0) ** (1.0 / 3.0))))
+        p = synthetic.moment_tensor_sweep(side, 100)
+        reps = -(-n // p.shape[0])
+        return "moment_tensor", np.tile(p, (reps, 1))[:n], p[p.shape[0] // 2 + 7]
+    return "bilateral", synthetic.bilateral_sweep(n), synthetic.IZMIT
+
+
 def workload_config(w, args, batch):
+    if w.get("source") == "moment_tensor":
+        return {"workload": "C2 point moment-tensor grid search: (north, east, depth) lattice x 100 unit tensors, 3 centroids each, x %d receivers "
+                            "x ned, %s GFDB %dx%dx10, %s, bilinear" % (w["nrcv"], w["db"], w["nx"], w["nz"], w["norm"]),
+                "name": args.workload, "candidates_per_step": batch, "receivers": w["nrcv"], "effective_dt": w["effective_dt"],
+                "cache": "database %s exceeds L2 (no L2 flush needed)" % w["db"]}
     return {"workload": "C3/C5 bilateral (Izmit, minimizer.f90:1632) ~1e4 sub-sources x %d receivers x ned, %s GFDB %dx%dx10, %s, "
                         "bilinear, candidates swept in strike/dip/rake/depth/length" % (w["nrcv"], w["db"], w["nx"], w["nz"], w["norm"]),
             "name": args.workload, "candidates_per_step": batch, "receivers": w["nrcv"], "effective_dt": w["effective_dt"],
@@ -225,18 +246,18 @@ def main():
     rlat, rlon, rdep = synthetic.receivers(w["nrcv"], (30.0, 70.0), w["dmin"], w["dmax"])
     eng = kiwi_b200.Engine(local)
     configure(eng, db, w, rlat, rlon, rdep)
-    eng.set_source_params("bilateral", synthetic.IZMIT)
-    set_references(eng, [eng], w["nrcv"], dt)
-    nm = eng.nmisfits
     B = args.batch
     # candidates are block-partitioned over the ranks; weak scaling: B per GPU
-    allc = synthetic.bilateral_sweep(max(B * world, 32))
+    stype, allc, base = candidates(w, max(B * world, 32))
+    eng.set_source_params(stype, base)
+    set_references(eng, [eng], w["nrcv"], dt)
+    nm = eng.nmisfits
     mine = np.ascontiguousarray(allc[rank * B:(rank + 1) * B])
     d_out = torch.empty((B, nm, 2), dtype=torch.float32, device="cuda")
     gathered = torch.empty((world * B, nm, 2), dtype=torch.float32, device="cuda") if world > 1 else None
 
     def step_device():
-        st = eng.eval_sources_device("bilateral", mine, d_out.data_ptr())
+        st = eng.eval_sources_device(stype, mine, d_out.data_ptr())
         t = eng.last_timing()
         if world > 1:   # only the small misfit block crosses NVLink
             dist.all_gather_into_tensor(gathered, d_out)
@@ -276,7 +297,7 @@ def main():
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        mis, st = eng.eval_sources("bilateral", mine)
+        mis, st = eng.eval_sources(stype, mine)
     barrier()
     e2e_wall = time.perf_counter() - t0
     te = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
@@ -314,13 +335,13 @@ def main():
             "wall_ms_per_step": wall_ms_max / args.steps}
 
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(w, db, rlat, rlon, rdep, dt, mine, mis)
+        line["cpu_baseline"] = cpu_baseline(w, db, rlat, rlon, rdep, dt, stype, mine, mis)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(w, db, rlat, rlon, rdep, dt, cands, gpu_misfits):
+def cpu_baseline(w, db, rlat, rlon, rdep, dt, stype, cands, gpu_misfits):
     """The oracle (restated CPU path) timed on the host cores on a bounded sample of the same
     workload, and used as the checker of the batch just measured."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -332,14 +353,14 @@ def cpu_baseline(w, db, rlat, rlon, rdep, dt, cands, gpu_misfits):
     copy_references(None, o, w["nrcv"], dt)
     n = max(1, min(w["cpu_sample"], cands.shape[0]))
     t0 = time.perf_counter()
-    mo, so = o.eval_sources("bilateral", cands[:n])
+    mo, so = o.eval_sources(stype, cands[:n])
     t = time.perf_counter() - t0
     # the same sample with the strip arithmetic of the restatement carried in double (oracle -DKO_WIDE):
     # separates the GPU's deviation from the fp32 reference path's own accumulation noise
     ow = OracleEngine(threads=ncores, wide=True)
     configure(ow, db, w, rlat, rlon, rdep)
     copy_references(None, ow, w["nrcv"], dt)
-    mw, _ = ow.eval_sources("bilateral", cands[:n])
+    mw, _ = ow.eval_sources(stype, cands[:n])
 
     def dev(a, b):
         return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 0.1 * np.abs(b[..., 1:2]))))

@@ -1,0 +1,61 @@
+"""Multi-rank host logic on CPU: world_size 2, gloo backend.  The per-rank evaluator is the CPU
+oracle (allowed in tests); the thing under test is the partition / pad / all_gather / reassembly of
+kiwi_b200.sharding, which is what the GPU ranks run over NCCL."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_block_partition():
+    from kiwi_b200.sharding import block_partition
+    assert block_partition(10, 4) == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert block_partition(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    assert block_partition(0, 2) == [(0, 0), (0, 0)]
+    for n in (1, 7, 64, 1000):
+        for w in (1, 2, 4, 8):
+            p = block_partition(n, w)
+            assert p[0][0] == 0 and p[-1][1] == n and all(a[1] == b[0] for a, b in zip(p, p[1:]))
+            sizes = [e - b for b, e in p]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    import scenario as sc
+    from oracle_lib import OracleEngine
+    from kiwi_b200.sharding import eval_sources_sharded
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    comps = ["ned", "d", "ar"]
+    lat, lon, dep = sc.small_receivers(3)
+    o = OracleEngine(threads=1)
+    sc.setup(o, sc.small_db(), lat, lon, dep, comps)
+    o.eval_sources("bilateral", sc.BILAT_SMALL)
+    sc.set_refs_from(o, [o], [3, 1, 2])
+    p = np.tile(sc.BILAT_SMALL, (5, 1)); p[:, 5] += np.arange(5) * 7.0      # 5 candidates over 2 ranks: blocks of 3 and 2
+    mis, st = eval_sources_sharded(o, "bilateral", p)
+    ref, rst = o.eval_sources("bilateral", p)
+    q.put((rank, bool(np.array_equal(mis, ref)), bool(np.array_equal(st, rst)), mis.shape))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_evaluation_two_ranks_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, same_m, same_s, shape in res:
+        assert same_m and same_s and shape == (5, 6, 2), (rank, same_m, same_s, shape)
