@@ -125,6 +125,13 @@ int kiwi_set_synthetics_factor(kiwi_ctx* ctx, float factor);
 /* set_floating_shiftrange (minimizer_engine.f90:418-451): seconds; ireceiver 0 = all */
 int kiwi_set_floating_shiftrange(kiwi_ctx* ctx, int ireceiver, float shift_lo, float shift_hi);
 
+/* Point moment-tensor grid searches (candidates of kiwi_eval_sources that share time, position and rise
+ * time and differ only in the tensor; the grids of python/tunguska/gridsearch.py:114-139 over a
+ * moment_tensor source): by default such batches are evaluated by synthesising six unit-tensor basis
+ * seismograms per location and contracting all tensors against them on the tensor cores (tcgen05).
+ * enabled = 0 forces the direct per-candidate path (same results within rounding). */
+int kiwi_set_mt_grid(kiwi_ctx* ctx, int enabled);
+
 /* number of (misfit, norm-factor) pairs get_misfits returns: components of enabled receivers
  * (minimizer_engine.f90:1141-1148) */
 int kiwi_get_nmisfits(kiwi_ctx* ctx);

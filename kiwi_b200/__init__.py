@@ -3,9 +3,16 @@
 Host-side mirror of the reference's command surface (minimizer.f90 / minimizer_engine.f90) on top
 of the C ABI in include/kiwi_b200.h.  All computation happens in the hand-written sm_100a kernels
 of libkiwi_b200.so; this package only marshals arguments.
-"""
-from .engine import (Engine, Gfdb, KiwiError, SOURCE_TYPES, NORMS, KIWIBENCH_STF, n_source_params,
-                     global_misfits)
 
+The names below resolve lazily so that `python -m kiwi_b200.build` can run before the shared
+library exists; anything else fails loudly if the library is missing (kiwi_b200/_lib.py).
+"""
 __all__ = ["Engine", "Gfdb", "KiwiError", "SOURCE_TYPES", "NORMS", "KIWIBENCH_STF", "n_source_params",
            "global_misfits"]
+
+
+def __getattr__(name):
+    if name in __all__:
+        from . import engine
+        return getattr(engine, name)
+    raise AttributeError("module 'kiwi_b200' has no attribute %r" % name)

@@ -15,6 +15,8 @@
 #include <cstring>
 #include <climits>
 #include <unordered_set>
+#include <unordered_map>
+#include <functional>
 
 #define CU_OK(call)                                                                                          \
     do {                                                                                                     \
@@ -109,6 +111,8 @@ struct kiwi_ctx {
     std::vector<int> last_fshift;            // floating shifts of the last ns = 1 evaluation
     PinBuf h_stage, h_out;
     size_t work_budget = 0;
+    bool mt_grid_enabled = true;             // point moment-tensor grid searches go through the tcgen05 contraction
+    DevBuf d_mtlocs, d_mts, d_candof;
     // description of the last chunk evaluated (inspection entry points, accounting)
     struct Last {
         bool valid = false;
@@ -217,9 +221,19 @@ int prep_candidate(int sourcetype, const float* p, float effective_dt, kh::Sourc
     return 1;
 }
 
+// called after the synthesis of every sub-chunk when the caller consumes the synthetics itself
+// (point moment-tensor grid search): candidates [cand0, cand0+ncand) of the batch, their rows in `seis`
+struct SynthHook {
+    int align = 1;   // sub-chunks hold a multiple of `align` candidates
+    std::function<int(int cand0, int ncand, const float* seis, size_t seis_stride, const SeisHdr* shdrs)> fn;
+};
+
+int eval_mt_grid(kiwi_ctx* c, int n, const float* params, float* d_out, int* h_status, bool* used);
+
 // Evaluate candidates [0,n) of `params`; d_out: device [n][nmisfits][2]; h_status: host [n] or null.
 // want_misfits = false stops after synthesis (used by the seismogram getters).
-int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* params, float* d_out, int* h_status, bool want_misfits) {
+int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* params, float* d_out, int* h_status, bool want_misfits,
+               const SynthHook* hook = nullptr) {
     if (require_db(c)) return 1;
     if (require_receivers(c)) return 1;
     if (!c->loc_set) return kiwi_set_error("no source location set");                   // minimizer_engine.f90:1378
@@ -233,6 +247,12 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         for (const HostReceiver& h : c->rcv) if (h.enabled && !h.filter_x.empty()) general = true;
     }
     if (upload_receivers(c)) return 1;
+    if (!hook && want_misfits && !general && sourcetype == KIWI_SOURCE_MOMENT_TENSOR &&
+        (c->misfit_method == KIWI_L2NORM || c->misfit_method == KIWI_L1NORM) && c->mt_grid_enabled) {
+        bool used = false;
+        const int rc = eval_mt_grid(c, n, params, d_out, h_status, &used);
+        if (rc || used) return rc;
+    }
     const int nrcv = (int)c->rcv.size();
     const int nm = c->nmisfits;
     cudaStream_t st = c->stream;
@@ -259,6 +279,8 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
     }
     const size_t per_cand_geo = (size_t)nrcv * max_groups * sizeof(GeoRec) + (size_t)nrcv * (sizeof(PairHdr) + KIWI_MAX_COMP * sizeof(SeisHdr));
     int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, (c->work_budget / 2) / std::max<size_t>(per_cand_geo, 1)));
+    const int align = hook ? std::max(1, hook->align) : 1;
+    if (chunk < n) chunk = std::max(align, chunk / align * align);
 
     cudaEventRecord(c->ev[0], st);
     for (int b0 = 0; b0 < n; b0 += chunk) {
@@ -368,7 +390,8 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         if (synth_smem_bytes(nwarps, nq) > (size_t)220 * 1024)
             return kiwi_set_error("synthetic window of %d samples does not fit the shared-memory accumulators", tmax);
         const size_t per_cand_seis = (size_t)nrcv * KIWI_MAX_COMP * seis_stride * sizeof(float);
-        const int sub = (int)std::max<size_t>(1, std::min<size_t>((size_t)nc, (c->work_budget / 2) / std::max<size_t>(per_cand_seis, 1)));
+        int sub = (int)std::max<size_t>(1, std::min<size_t>((size_t)nc, (c->work_budget / 2) / std::max<size_t>(per_cand_seis, 1)));
+        if (sub < nc) sub = std::max(align, sub / align * align);
         CU_OK(c->d_seis.ensure(per_cand_seis * sub));
         CU_OK(c->d_status.ensure(sizeof(int) * nc));
         {
@@ -392,6 +415,10 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
                 CU_OK(cudaMemsetAsync(c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, 0xff, sizeof(SeisHdr) * (size_t)ns_ * nrcv * KIWI_MAX_COMP, st));
             }
             cudaEventRecord(c->ev[4], st);
+            if (hook && hook->fn) {
+                if (hook->fn(b0 + s0, ns_, c->d_seis.as<float>(), seis_stride, c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP)) return 1;
+                c->launches[3] += 1;
+            }
             if (want_misfits && nm > 0 && !general) {
                 launch_misfit_td(c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>() + s0, ns_, c->d_seis.as<float>(), seis_stride,
                                  c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, c->d_refdata.as<float>(), c->d_taper.as<float>(),
@@ -464,6 +491,77 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
     return 0;
 }
 
+typedef MtLoc MtLocHost;
+
+// Point moment-tensor grid search (python/tunguska/gridsearch.py:159-197 over source.py:119-164 grids of a
+// moment_tensor source): candidates that share (time, north, east, depth, rise-time) differ only in the six
+// tensor components, in which the synthetics are linear.  Per distinct location the six unit-tensor basis
+// seismograms are synthesised by the normal path; all candidates of the location are then contracted against
+// them on the tensor cores with the misfit as epilogue (k_mt_contract).  *used = false: not worth it / not a grid.
+int eval_mt_grid(kiwi_ctx* c, int n, const float* params, float* d_out, int* h_status, bool* used) {
+    *used = false;
+    if (n < 64) return 0;
+    struct Key { unsigned v[5]; bool operator==(const Key& o) const { return memcmp(v, o.v, sizeof v) == 0; } };
+    struct KeyHash { size_t operator()(const Key& k) const { size_t h = 1469598103934665603ull; for (unsigned x : k.v) { h ^= x; h *= 1099511628211ull; } return h; } };
+    std::unordered_map<Key, int, KeyHash> ids;
+    std::vector<int> loc_of(n);
+    std::vector<int> first_of;
+    for (int i = 0; i < n; i++) {
+        const float* p = params + (size_t)i * 11;
+        Key k;
+        memcpy(&k.v[0], &p[0], 4); memcpy(&k.v[1], &p[1], 4); memcpy(&k.v[2], &p[2], 4); memcpy(&k.v[3], &p[3], 4); memcpy(&k.v[4], &p[10], 4);
+        auto it = ids.find(k);
+        if (it == ids.end()) { it = ids.emplace(k, (int)first_of.size()).first; first_of.push_back(i); }
+        loc_of[i] = it->second;
+    }
+    const int nloc = (int)first_of.size();
+    if ((long long)nloc * 8 > n) return 0;   // fewer than 8 tensors per location on average: the direct path is as good
+    // candidates sorted by location
+    std::vector<MtLocHost> locs(nloc, MtLocHost{0, 0});
+    for (int i = 0; i < n; i++) locs[loc_of[i]].mt_count++;
+    for (int l = 1; l < nloc; l++) locs[l].mt_begin = locs[l - 1].mt_begin + locs[l - 1].mt_count;
+    std::vector<int> fill(nloc, 0), cand_of(n);
+    std::vector<float> mts((size_t)n * 6);
+    for (int i = 0; i < n; i++) {
+        const int l = loc_of[i], at = locs[l].mt_begin + fill[l]++;
+        cand_of[at] = i;
+        memcpy(&mts[(size_t)at * 6], params + (size_t)i * 11 + 4, sizeof(float) * 6);
+    }
+    // six unit tensors per location
+    std::vector<float> basis((size_t)nloc * 6 * 11, 0.f);
+    for (int l = 0; l < nloc; l++)
+        for (int k = 0; k < 6; k++) {
+            float* b = &basis[((size_t)l * 6 + k) * 11];
+            const float* p = params + (size_t)first_of[l] * 11;
+            b[0] = p[0]; b[1] = p[1]; b[2] = p[2]; b[3] = p[3]; b[10] = p[10];
+            b[4 + k] = 1.f;
+        }
+    CU_OK(c->d_mtlocs.ensure(sizeof(MtLocHost) * nloc));
+    CU_OK(c->d_mts.ensure(sizeof(float) * 6 * (size_t)n));
+    CU_OK(c->d_candof.ensure(sizeof(int) * (size_t)n));
+    CU_OK(cudaMemcpyAsync(c->d_mtlocs.p, locs.data(), sizeof(MtLocHost) * nloc, cudaMemcpyHostToDevice, c->stream));
+    CU_OK(cudaMemcpyAsync(c->d_mts.p, mts.data(), sizeof(float) * 6 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CU_OK(cudaMemcpyAsync(c->d_candof.p, cand_of.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CU_OK(cudaStreamSynchronize(c->stream));
+    const int nrcv = (int)c->rcv.size();
+    SynthHook hook;
+    hook.align = 6;
+    hook.fn = [&](int cand0, int ncand, const float* seis, size_t seis_stride, const SeisHdr* shdrs) -> int {
+        const int l0 = cand0 / 6, nl = ncand / 6;
+        launch_mt_contract(c->d_rcv.as<ReceiverDev>(), nrcv, reinterpret_cast<const MtLoc*>(c->d_mtlocs.p) + l0, nl, c->d_mts.as<float>(),
+                           c->d_candof.as<int>(), seis, seis_stride, shdrs, c->d_refdata.as<float>(), c->d_taper.as<float>(), c->misfit_method,
+                           c->db.dt, c->syn_factor, c->nmisfits, d_out, c->stream);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return kiwi_set_error("CUDA error launching the moment-tensor contraction: %s", cudaGetErrorString(e));
+        return 0;
+    };
+    std::vector<int> bstatus((size_t)nloc * 6, 0);
+    if (eval_batch(c, KIWI_SOURCE_MOMENT_TENSOR, nloc * 6, 11, basis.data(), nullptr, bstatus.data(), false, &hook)) return 1;
+    if (h_status) for (int i = 0; i < n; i++) h_status[i] = bstatus[(size_t)loc_of[i] * 6];
+    *used = true;
+    return 0;
+}
+
 int ensure_single(kiwi_ctx* c, bool want_misfits) {
     if (!c->src_set) return kiwi_set_error("no source parameters set");   // minimizer_engine.f90:1394
     if (!c->src_dirty && (!want_misfits || !c->src_misfits.empty()) && c->last.valid && c->last.n == 1) return 0;
@@ -518,7 +616,7 @@ void kiwi_destroy(kiwi_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->d_slabs, &c->d_nodes, &c->d_tspan, &c->d_rcv, &c->d_refdata, &c->d_taper, &c->d_cands, &c->d_bilat, &c->d_gf, &c->d_gi,
-                      &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift})
+                      &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift, &c->d_mtlocs, &c->d_mts, &c->d_candof})
         b->release();
     c->h_stage.release(); c->h_out.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -710,6 +808,12 @@ int kiwi_set_misfit_filter(kiwi_ctx* c, int ireceiver, int n, const float* x, co
         c->rcv[i].filter_x.assign(x, x + n); c->rcv[i].filter_y.assign(y, y + n);
     }
     c->receivers_dirty = true; c->src_misfits.clear();
+    return 0;
+}
+
+int kiwi_set_mt_grid(kiwi_ctx* c, int enabled) {
+    if (!c) return kiwi_set_error("null context");
+    c->mt_grid_enabled = enabled != 0;
     return 0;
 }
 

@@ -1041,6 +1041,238 @@ __global__ void __launch_bounds__(256) k_misfit_general(const ReceiverDev* __res
     }
 }
 
+// =================================================================================================
+// K8: point moment-tensor grid search (config C2).  For a point source the synthetic is linear in the
+// six moment-tensor components (make_weights seismogram.f90:316-336 is linear in m, everything after
+// it too), so for every grid location the six unit-tensor "basis" seismograms B_i are synthesised
+// once by k_synth and every candidate tensor m_j of that location costs only
+//     syn_j(t) = sum_i m_j,i B_i(t)           -- a dense [nmt x 6] . [6 x T] contraction
+// followed by the misfit reduction over t.  The contraction runs on the 5th-generation tensor cores:
+// tcgen05.mma kind::tf32, A (tensors) and B (basis samples) in shared memory in the canonical K-major
+// no-swizzle layout, fp32 accumulator tile 128 x 128 in tensor memory.  TF32 keeps 10 mantissa bits, so
+// both operands are split hi + lo and K is laid out as [hi | hi | lo] x [hi | lo | hi] (3xTF32,
+// K = 18 padded to 24): the dropped lo*lo term is 2^-22 relative.  Each of the 128 threads then owns one
+// candidate (one TMEM lane) and streams its row of the accumulator through the misfit norm
+// (comparator.f90:627-697, 770-859).  One CTA per (location, receiver).
+// =================================================================================================
+#define MTC_M 128          // candidates (TMEM lanes) per tile
+#define MTC_N 128          // samples (TMEM columns) per chunk
+#define MTC_K 24           // 3 x 6 split components, padded to 3 MMA k-steps of 8
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// shared-memory matrix descriptor, K-major, SWIZZLE_NONE: 8x16-byte core matrices; SBO = distance
+// between core matrices along M/N, LBO = distance between the two core matrices along K (16-byte units)
+__device__ __forceinline__ unsigned long long umma_desc(unsigned saddr, unsigned lbo_bytes, unsigned sbo_bytes) {
+    unsigned long long d = 0;
+    d |= (unsigned long long)((saddr >> 4) & 0x3fff);
+    d |= (unsigned long long)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (unsigned long long)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= 1ull << 46;                                      // descriptor version (Blackwell)
+    return d;                                             // base offset 0, layout type 0 = no swizzle
+}
+// byte offset of element (row, k) of an [rows x MTC_K] K-major operand tile stored as
+// [k-core (4 elements)][row-core (8 rows)][8 rows][4 elements]
+__device__ __forceinline__ unsigned operand_off(int row, int k, int rows) {
+    return (unsigned)(((k >> 2) * (rows >> 3) + (row >> 3)) * 128 + (row & 7) * 16 + (k & 3) * 4);
+}
+
+__global__ void __launch_bounds__(128) k_mt_contract(const ReceiverDev* __restrict__ rcv, int nrcv, const MtLoc* __restrict__ locs,
+                                                      const float* __restrict__ mts /* [n][6] sorted by location */,
+                                                      const int* __restrict__ cand_of /* [n] original candidate index */,
+                                                      const float* __restrict__ seis, size_t seis_stride,
+                                                      const SeisHdr* __restrict__ shdrs, const float* __restrict__ refdata,
+                                                      const float* __restrict__ taperdata, int method, float dt, float syn_factor,
+                                                      int nmisfits, float* __restrict__ out) {
+    __shared__ __align__(128) float sA[MTC_M * MTC_K];       // 12 KiB
+    __shared__ __align__(128) float sB[MTC_N * MTC_K];       // 12 KiB
+    __shared__ float s_ref[MTC_N], s_tap[MTC_N];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ unsigned s_tmem;
+    __shared__ double s_red[2][4];
+
+    const int loc = blockIdx.x / nrcv, ir = blockIdx.x % nrcv;
+    const ReceiverDev& R = rcv[ir];
+    if (!R.enabled || R.ncomp == 0) return;
+    const MtLoc L = locs[loc];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool l1 = method == 2;
+
+    // ---- one-time setup: mbarrier, tensor memory (128 columns = one 128 x 128 fp32 accumulator) ----
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(MTC_N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem = s_tmem;
+    unsigned phase = 0;
+    // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
+    const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(MTC_N >> 3) << 17) | ((unsigned)(MTC_M >> 4) << 24);
+    const float fa = 1.f, fb = syn_factor;
+    const float* tp = taperdata + R.taper_off;
+    const bool tapered = R.has_taper != 0;
+
+    for (int m0 = 0; m0 < L.mt_count; m0 += MTC_M) {
+        // ---- A tile: this thread's candidate tensor, split hi/lo, zero rows beyond the list ----------
+        const int j = m0 + tid;
+        const bool have = j < L.mt_count;
+        {
+            float m[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) m[k] = have ? __ldg(&mts[(size_t)(L.mt_begin + j) * 6 + k]) : 0.f;
+            char* a = reinterpret_cast<char*>(sA);
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                const float hi = tf32_hi(m[k]), lo = tf32_hi(m[k] - hi);
+                *reinterpret_cast<float*>(a + operand_off(tid, k, MTC_M)) = hi;
+                *reinterpret_cast<float*>(a + operand_off(tid, 6 + k, MTC_M)) = hi;
+                *reinterpret_cast<float*>(a + operand_off(tid, 12 + k, MTC_M)) = lo;
+                *reinterpret_cast<float*>(a + operand_off(tid, 18 + k, MTC_M)) = 0.f;
+            }
+        }
+        for (int ic = 0; ic < R.ncomp; ic++) {
+            const size_t item0 = ((size_t)(loc * 6) * nrcv + ir) * KIWI_MAX_COMP + ic;     // basis tensor 0 of this location
+            const size_t item_stride = (size_t)nrcv * KIWI_MAX_COMP;                        // next basis tensor
+            const SeisHdr sh = shdrs[item0];
+            float* o = have ? out + ((size_t)cand_of[L.mt_begin + j] * nmisfits + R.misfit_base + ic) * 2 : nullptr;
+            if (sh.hi < sh.lo) { if (o) { o[0] = nanf(""); o[1] = nanf(""); } continue; }
+            const int sds0 = sh.lo, sds1 = sh.hi;
+            const int rds0 = R.ref_ds0[ic], rds1 = R.ref_ds1[ic];
+            const float* rdat = refdata + R.ref_off[ic];
+            int F0, F1;
+            probe_spans(rds0, rds1, R.ref_sp0[ic], R.ref_sp1[ic], sds0, sds1, F0, F1);
+            int p0, p1, q0, q1;
+            if (tapered) { p0 = max(R.dps0, F0); p1 = min(R.dps1, F1); q0 = p0; q1 = p1; }
+            else { p0 = min(rds0, sds0); p1 = max(rds1, sds1); q0 = rds0; q1 = rds1; }
+            auto refval = [&](int x) -> float {
+                if (x < rds0) return 0.f;
+                float v = rdat[min(x, rds1) - rds0];
+                if (tapered) v = (x >= R.tp0 && x <= R.tp1) ? v * tp[x - R.tp0] : 0.f;
+                return v;
+            };
+            auto tapval = [&](int x) -> float { return tapered ? ((x >= R.tp0 && x <= R.tp1) ? tp[x - R.tp0] : 0.f) : 1.f; };
+            double acc = 0.;
+            // (i) left of the synthetic's data span the synthetic is zero: reference only
+            for (int x = p0; x <= min(p1, sds0 - 1); x++) { const float a = refval(x); acc += l1 ? (double)fabsf(fa * a) : (double)(fa * a) * (double)(fa * a); }
+            // (ii) columns x in [xs, xe] come out of the tensor-core contraction, 128 at a time; xe = sds1 is
+            // always included when the span reaches past it, its value is the continuation (comparator.f90:264-267)
+            const int xs = max(p0, sds0), xe = min(p1, sds1) < xs ? -1 : ((p1 > sds1) ? sds1 : min(p1, sds1));
+            float e_last = 0.f;
+            for (int c0 = xs; xe >= xs && c0 <= xe; c0 += MTC_N) {
+                // ---- B chunk: six basis rows, split hi/lo -------------------------------------------------
+                {
+                    const int x = c0 + tid;
+                    const bool in = x <= xe;
+                    char* bsm = reinterpret_cast<char*>(sB);
+#pragma unroll
+                    for (int k = 0; k < 6; k++) {
+                        const float v = in ? __ldg(seis + (item0 + (size_t)k * item_stride) * seis_stride + (x - sh.base)) : 0.f;
+                        const float hi = tf32_hi(v), lo = tf32_hi(v - hi);
+                        *reinterpret_cast<float*>(bsm + operand_off(tid, k, MTC_N)) = hi;
+                        *reinterpret_cast<float*>(bsm + operand_off(tid, 6 + k, MTC_N)) = lo;
+                        *reinterpret_cast<float*>(bsm + operand_off(tid, 12 + k, MTC_N)) = hi;
+                        *reinterpret_cast<float*>(bsm + operand_off(tid, 18 + k, MTC_N)) = 0.f;
+                    }
+                    s_ref[tid] = in ? refval(x) : 0.f;
+                    s_tap[tid] = in ? tapval(x) : 0.f;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> async proxy (tensor core)
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncthreads();
+                if (tid == 0) {
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const unsigned a0 = smem_u32(sA), b0 = smem_u32(sB);
+#pragma unroll
+                    for (int ks = 0; ks < MTC_K / 8; ks++) {
+                        // k-step ks covers k-cores 2ks, 2ks+1; a k-core block is (rows/8)*128 bytes
+                        const unsigned long long da = umma_desc(a0 + ks * 2 * (MTC_M / 8) * 128, (MTC_M / 8) * 128, 128);
+                        const unsigned long long dbb = umma_desc(b0 + ks * 2 * (MTC_N / 8) * 128, (MTC_N / 8) * 128, 128);
+                        const unsigned accum = ks > 0 ? 1u : 0u;
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem),
+                            "l"(da), "l"(dbb), "r"(idesc), "r"(accum)
+                            : "memory");
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_bar)) : "memory");
+                }
+                // ---- wait for the accumulator, then every thread folds its row into the norm -----------------
+                {
+                    unsigned done = 0, spins = 0;
+                    while (!done) {
+                        if (++spins > (1u << 26)) { asm volatile("trap;"); }   // never spin for ever on a lost completion
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                            : "=r"(done)
+                            : "r"(smem_u32(&s_bar)), "r"(phase)
+                            : "memory");
+                    }
+                    phase ^= 1;
+                }
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int ncol = min(MTC_N, xe - c0 + 1);
+                for (int cc = 0; cc < ncol; cc += 32) {
+                    unsigned v[32];
+                    const unsigned taddr = tmem + ((unsigned)(warp * 32) << 16) + (unsigned)cc;
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                        : "r"(taddr)
+                        : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int u = 0; u < 32; u++) {
+                        if (cc + u < ncol) {
+                            const float d = __uint_as_float(v[u]);
+                            const float b = d * s_tap[cc + u];       // moment = 1 for a moment-tensor source (source_moment_tensor.f90:199)
+                            const float a = s_ref[cc + u];
+                            const float r = fa * a - fb * b;
+                            acc += l1 ? (double)fabsf(r) : (double)r * (double)r;
+                            if (c0 + cc + u == sds1) e_last = d;
+                        }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncthreads();      // accumulator and operand tiles are free again
+            }
+            // (iii) right of the data span the synthetic repeats its last sample
+            for (int x = max(max(p0, sds0), sds1 + 1); x <= p1; x++) {
+                const float r = fa * refval(x) - fb * (e_last * tapval(x));
+                acc += l1 ? (double)fabsf(r) : (double)r * (double)r;
+            }
+            // reference-only norm (the same for all candidates): block reduction
+            double accn = 0.;
+            for (int x = q0 + tid; x <= q1; x += MTC_M) { const float a = refval(x); accn += l1 ? (double)fabsf(a) : (double)a * (double)a; }
+            for (int ofs = 16; ofs; ofs >>= 1) accn += __shfl_xor_sync(0xffffffffu, accn, ofs);
+            if (lane == 0) s_red[ic & 1][warp] = accn;
+            __syncthreads();
+            accn = s_red[ic & 1][0] + s_red[ic & 1][1] + s_red[ic & 1][2] + s_red[ic & 1][3];
+            if (o) {
+                float mis, nf;
+                if (l1) { mis = (float)((double)dt * acc); nf = fa * (float)((double)dt * accn); }
+                else { mis = (float)sqrt((double)dt * acc); nf = fa * (float)sqrt((double)dt * accn); }
+                if (p1 < p0) mis = 0.f;
+                o[0] = mis; o[1] = nf;
+            }
+        }
+        __syncthreads();   // before the next A tile overwrites sA
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(MTC_N) : "memory");
+}
+
 // ---- host-callable launch wrappers ---------------------------------------------------------------
 void launch_bilat_groups(const BilatCand* d_cands, int ncand, GroupSoA g, TapSoA taps, float dt, int ngroups_total, cudaStream_t st) {
     if (ncand > 0) k_bilat_groups<<<ncand, 128, 0, st>>>(d_cands, g, taps, dt, ngroups_total);
@@ -1092,4 +1324,12 @@ cudaError_t launch_misfit_general(const ReceiverDev* rcv, int nrcv, const CandDe
         k_misfit_general<<<ncand * nrcv, 256, smem, st>>>(rcv, nrcv, cands, seis, seis_stride, shdrs, refdata, taperdata, tw, tw_n, method, dt,
                                                          syn_factor, nmisfits, out, status, fshift, n_alloc, nshift_alloc);
     return cudaGetLastError();
+}
+
+void launch_mt_contract(const ReceiverDev* rcv, int nrcv, const MtLoc* locs, int nloc, const float* mts, const int* cand_of, const float* seis,
+                        size_t seis_stride, const SeisHdr* shdrs, const float* refdata, const float* taperdata, int method, float dt,
+                        float syn_factor, int nmisfits, float* out, cudaStream_t st) {
+    if (nloc * nrcv > 0)
+        k_mt_contract<<<nloc * nrcv, 128, 0, st>>>(rcv, nrcv, locs, mts, cand_of, seis, seis_stride, shdrs, refdata, taperdata, method, dt,
+                                                  syn_factor, nmisfits, out);
 }

@@ -95,6 +95,11 @@ struct __align__(16) GeoRec {   // 128 bytes: everything k_synth needs to start 
 #define GEO_NEAR 4      // scaled coordinate within 4 ulps of an integer
 #define GEO_SINGLE 8    // dix == 0 and diz == 0: node trace used directly (gfdb.f90:893-896)
 
+// one grid location of a point moment-tensor grid search: its candidates in the location-sorted tensor list
+struct MtLoc {
+    int mt_begin, mt_count;
+};
+
 // per (candidate, receiver) header
 struct PairHdr {
     int s1lo, s1hi;     // span of displacement_ar(1)

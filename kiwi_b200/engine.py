@@ -211,6 +211,10 @@ class Engine:
     def set_synthetics_factor(self, factor):
         _check(lib.kiwi_set_synthetics_factor(self._h, factor))
 
+    def set_mt_grid(self, enabled):
+        """tensor-core path for point moment-tensor grid searches on (default) / off"""
+        _check(lib.kiwi_set_mt_grid(self._h, int(bool(enabled))))
+
     def set_floating_shiftrange(self, lo, hi, ireceiver=0):
         _check(lib.kiwi_set_floating_shiftrange(self._h, ireceiver, lo, hi))
 

@@ -280,3 +280,42 @@ def test_floating_misfits(norm, taper, filt):
     g.get_misfits()
     assert list(g.get_floating_shifts()) == list(o.get_floating_shifts())
     assert list(g.get_floating_shifts())[0] == -3
+
+
+def _mt_grid(nloc=3, nmt=45):
+    from kiwi_b200 import synthetic
+    mts = synthetic.fibonacci_moment_tensors(nmt) * 1e18
+    rng = np.random.default_rng(3)
+    mts = mts * rng.uniform(0.3, 2.0, (nmt, 1)).astype(np.float32)
+    p = np.zeros((nloc, nmt, 11), np.float32)
+    for l in range(nloc):
+        p[l, :, 0] = 0.1 * l; p[l, :, 1] = 150 + 300 * l; p[l, :, 2] = -250 + 200 * l; p[l, :, 3] = 2800 - 400 * l
+        p[l, :, 4:10] = mts; p[l, :, 10] = 0.7
+    p = p.reshape(-1, 11)
+    return p[rng.permutation(p.shape[0])]      # locations interleaved: the engine has to find the grid itself
+
+
+@pytest.mark.parametrize("norm", ["l2norm", "l1norm"])
+@pytest.mark.parametrize("taper", [False, True])
+def test_moment_tensor_grid_search_tensor_core_path(norm, taper):
+    """config C2: candidates sharing a location are contracted against six unit-tensor basis synthetics
+    with tcgen05 (3xTF32); held against the oracle and against the engine's own direct path"""
+    g, o = engines(sc.small_db(), COMPS6)
+    ncomps = [len(c) for c in COMPS6]
+    o.eval_sources("moment_tensor", sc.MT_SMALL)
+    sc.set_refs_from(o, [g, o], ncomps)
+    for e in (g, o):
+        e.set_misfit_method(norm)
+        if taper:
+            for ir in range(1, 7):
+                e.set_misfit_taper(ir, *TAPER)
+    p = _mt_grid()
+    mg, sg = g.eval_sources("moment_tensor", p)
+    assert g.last_timing()["launches"][3] >= 1
+    mo, so = o.eval_sources("moment_tensor", p)
+    assert not sg.any() and not so.any()
+    assert np.all(np.abs(mg - mo) <= misfit_tol(mo)), np.abs((mg - mo) / misfit_tol(mo)).max()
+    g.set_mt_grid(False)
+    md, sd = g.eval_sources("moment_tensor", p)
+    assert np.all(np.abs(mg - md) <= misfit_tol(mo)), np.abs((mg - md) / misfit_tol(mo)).max()
+    assert not np.array_equal(mg, md)      # really two different code paths
