@@ -33,8 +33,8 @@ typedef struct kiwi_gfdb kiwi_gfdb;
 #define KIWI_SOURCE_BILATERAL 1      /* source_bilat.f90, 14 parameters          */
 #define KIWI_SOURCE_CIRCULAR 2       /* not built (out of scope) */
 #define KIWI_SOURCE_POINT_LP 3       /* not built                                 */
-#define KIWI_SOURCE_EIKONAL 4        /* source_eikonal.f90, 15 parameters (next)  */
-#define KIWI_SOURCE_MT_EIKONAL 5     /* source_mt_eikonal.f90 (next)              */
+#define KIWI_SOURCE_EIKONAL 4        /* source_eikonal.f90, 15 parameters         */
+#define KIWI_SOURCE_MT_EIKONAL 5     /* source_mt_eikonal.f90, 20 parameters      */
 #define KIWI_SOURCE_MOMENT_TENSOR 6  /* source_moment_tensor.f90, 11 parameters   */
 
 /* misfit norm ids (comparator.f90:33-42) */
@@ -108,6 +108,15 @@ int kiwi_set_receivers(kiwi_ctx* ctx, int n, const double* lat_deg, const double
 int kiwi_switch_receiver(kiwi_ctx* ctx, int ireceiver, int state);
 /* set_source_location (minimizer.f90:485-519 + minimizer_engine.f90:453-467): degrees, seconds */
 int kiwi_set_source_location(kiwi_ctx* ctx, float lat_deg, float lon_deg, double ref_time);
+/* crust2x2_load (minimizer.f90:1669-1674, crust2x2.f90:68-74): the CRUST2.0 model the eikonal sources take
+ * their rupture velocity and default depth constraints from; `path` is the binary table written by
+ * tools/make_crust2x2_table.py (kiwi_b200/data/crust2x2.kcr) */
+int kiwi_set_crust2x2(kiwi_ctx* ctx, const char* path);
+/* set_source_constraints (minimizer.f90:521-579): n half-spaces, points[n][3] and outward normals[n][3];
+ * set_source_location re-derives the two default constraints (parameterized_source.f90:183-196) */
+int kiwi_set_source_constraints(kiwi_ctx* ctx, int n, const float* points, const float* normals);
+/* set_source_crustal_thickness_limit (minimizer.f90:581-612) */
+int kiwi_set_source_crustal_thickness_limit(kiwi_ctx* ctx, float limit);
 /* set_effective_dt (minimizer_engine.f90:610-618) */
 int kiwi_set_effective_dt(kiwi_ctx* ctx, float effective_dt);
 /* set_ref_seismograms (minimizer_engine.f90:313-352, receiver.f90:746-851) with the file reading

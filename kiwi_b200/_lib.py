@@ -34,6 +34,9 @@ SIGNATURES = {
     "kiwi_set_receivers": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, c_float_p, C.POINTER(C.c_char_p)]),
     "kiwi_switch_receiver": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "kiwi_set_source_location": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_double]),
+    "kiwi_set_crust2x2": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "kiwi_set_source_constraints": (C.c_int, [C.c_void_p, C.c_int, c_float_p, c_float_p]),
+    "kiwi_set_source_crustal_thickness_limit": (C.c_int, [C.c_void_p, C.c_float]),
     "kiwi_set_effective_dt": (C.c_int, [C.c_void_p, C.c_float]),
     "kiwi_set_ref_seismogram": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, c_float_p]),
     "kiwi_set_misfit_method": (C.c_int, [C.c_void_p, C.c_int]),

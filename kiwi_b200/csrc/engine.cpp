@@ -111,6 +111,11 @@ struct kiwi_ctx {
     std::vector<int> last_fshift;            // floating shifts of the last ns = 1 evaluation
     PinBuf h_stage, h_out;
     size_t work_budget = 0;
+    kh::Crust2x2 crust;                      // crust2x2 model (minimizer.f90:1669-1674), needed by the eikonal sources
+    std::vector<kh::Halfspace> constraints;  // psm%constraints (parameterized_source.f90:127-166)
+    bool user_constraints = false;
+    float thickness_limit = 0.f;
+    std::string prep_error;                  // message of the last failed discretisation
     bool mt_grid_enabled = true;             // point moment-tensor grid searches go through the tcgen05 contraction
     DevBuf d_mtlocs, d_mts, d_candof;
     // description of the last chunk evaluated (inspection entry points, accounting)
@@ -123,6 +128,7 @@ struct kiwi_ctx {
         GroupSoA g{};
         TapSoA taps{};
         std::vector<float> toff, wt;
+        std::vector<int> g0_tap_begin, g0_tap_count;   // taps of the groups of candidate 0
         bool seis_valid = false;
     } last;
     float ms[5] = {0, 0, 0, 0, 0};
@@ -215,9 +221,30 @@ bool all_refs_set(const kiwi_ctx* c) {
     return true;
 }
 
-int prep_candidate(int sourcetype, const float* p, float effective_dt, kh::SourcePrep* sp) {
+int prep_candidate(kiwi_ctx* c, int sourcetype, const float* p, float effective_dt, kh::SourcePrep* sp, std::string* err) {
     if (sourcetype == KIWI_SOURCE_BILATERAL) return kh::prep_bilateral(p, effective_dt, sp) ? 0 : 1;
     if (sourcetype == KIWI_SOURCE_MOMENT_TENSOR) return kh::prep_moment_tensor(p, effective_dt, sp) ? 0 : 1;
+    if (sourcetype == KIWI_SOURCE_EIKONAL || sourcetype == KIWI_SOURCE_MT_EIKONAL) {
+        kh::EikonalPrep e;
+        if (!kh::prep_eikonal(p, sourcetype == KIWI_SOURCE_MT_EIKONAL, effective_dt, c->olat, c->olon, c->crust, c->constraints, &e)) {
+            if (err) *err = e.err;
+            return 1;
+        }
+        kh::SourcePrep& o = *sp;
+        o = kh::SourcePrep();
+        o.explicit_groups = true;
+        o.nx = e.nx; o.ny = e.ny; o.ngroups = (int)e.groups.size();
+        o.moment = e.moment; o.risetime = e.risetime;
+        memcpy(o.mhat, e.mhat, sizeof o.mhat);
+        o.toff = e.tap_time; o.wt = e.tap_wt;
+        o.nt = 0;
+        for (const kh::EikonalGroup& g : e.groups) {
+            o.g_north.push_back(g.north); o.g_east.push_back(g.east); o.g_depth.push_back(g.depth); o.g_gw.push_back(g.gw);
+            o.g_tap_begin.push_back(g.tap_begin); o.g_tap_count.push_back(g.tap_count);
+            o.nt = std::max(o.nt, g.tap_count);
+        }
+        return 0;
+    }
     return 1;
 }
 
@@ -238,7 +265,9 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
     if (require_receivers(c)) return 1;
     if (!c->loc_set) return kiwi_set_error("no source location set");                   // minimizer_engine.f90:1378
     if (nparams != kiwi_get_n_source_params(sourcetype) || nparams == 0) return kiwi_set_error("wrong number of source parameters or source type not available");
-    if (sourcetype != KIWI_SOURCE_BILATERAL && sourcetype != KIWI_SOURCE_MOMENT_TENSOR) return kiwi_set_error("source type not available in this build");
+    if (sourcetype != KIWI_SOURCE_BILATERAL && sourcetype != KIWI_SOURCE_MOMENT_TENSOR && sourcetype != KIWI_SOURCE_EIKONAL &&
+        sourcetype != KIWI_SOURCE_MT_EIKONAL) return kiwi_set_error("source type not available in this build");
+    if ((sourcetype == KIWI_SOURCE_EIKONAL || sourcetype == KIWI_SOURCE_MT_EIKONAL) && !c->crust.loaded) return kiwi_set_error("crust2x2 model not loaded");
     if (want_misfits && !all_refs_set(c)) return kiwi_set_error("no reference seismograms set");   // :1428
     bool general = false;   // anything beyond plain time-domain norms goes through k_misfit_general
     if (want_misfits) {
@@ -265,9 +294,9 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
     std::vector<int> bad(n, 0);
     size_t max_groups = 1;
     for (int i = 0; i < n; i++) {
-        bad[i] = prep_candidate(sourcetype, params + (size_t)i * nparams, c->effective_dt, &prep[i]);
-        if (bad[i]) { prep[i].ngroups = 0; prep[i].nt = 0; prep[i].toff.clear(); prep[i].wt.clear(); }
-        if (prep[i].nt > 32) { bad[i] = 1; prep[i].ngroups = 0; }   // SYN_MAXTAPS
+        bad[i] = prep_candidate(c, sourcetype, params + (size_t)i * nparams, c->effective_dt, &prep[i], &c->prep_error);
+        if (bad[i]) { prep[i] = kh::SourcePrep(); }
+        if (prep[i].nt > 32) { bad[i] = 1; prep[i] = kh::SourcePrep(); c->prep_error = "more than 32 time centroids per sub-fault"; }   // SYN_MAXTAPS
         max_groups = std::max(max_groups, (size_t)prep[i].ngroups);
     }
     // ---- chunking by workspace budget ---------------------------------------------------------------
@@ -292,20 +321,22 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         for (int i = 0; i < nc; i++) {
             const kh::SourcePrep& sp = prep[b0 + i];
             CandDev& cd = cands[i];
-            cd.group_begin = G; cd.ngroups = sp.ngroups; cd.tap_begin = Tp; cd.ntaps_total = sp.nt;
+            cd.group_begin = G; cd.ngroups = sp.ngroups; cd.tap_begin = Tp;
+            cd.ntaps_total = sp.explicit_groups ? (int)sp.toff.size() : sp.nt * (sp.ngroups > 0 ? 1 : 0);
             cd.moment = sp.moment; cd.risetime = sp.risetime; cd.nx = sp.nx; cd.ny = sp.ny; cd.nt = sp.nt;
             cd.status = bad[b0 + i] ? KIWI_STATUS_BAD_PARAMS : KIWI_STATUS_OK;
-            G += sp.ngroups; Tp += sp.nt;
+            G += sp.ngroups; Tp += (int)sp.toff.size();
             rec_stride = std::max(rec_stride, (size_t)sp.ngroups);
         }
         const int Galloc = std::max(G, 1), Talloc = std::max(Tp, 1);
         CU_OK(c->d_cands.ensure(sizeof(CandDev) * nc));
-        CU_OK(c->d_gf.ensure(sizeof(float) * 10 * (size_t)Galloc));
+        CU_OK(c->d_gf.ensure(sizeof(float) * 11 * (size_t)Galloc));
         CU_OK(c->d_gi.ensure(sizeof(int) * 4 * (size_t)Galloc));
         CU_OK(c->d_tf.ensure(sizeof(float) * 2 * (size_t)Talloc));
         GroupSoA g;
         float* gf = c->d_gf.as<float>();
         g.north = gf; g.east = gf + Galloc; g.depth = gf + 2 * (size_t)Galloc; g.tbase = gf + 3 * (size_t)Galloc; g.mhat = gf + 4 * (size_t)Galloc;
+        g.gw = gf + 10 * (size_t)Galloc;
         int* gi = c->d_gi.as<int>();
         g.tap_begin = gi; g.tap_count = gi + Galloc; g.its_min = gi + 2 * (size_t)Galloc; g.its_max = gi + 3 * (size_t)Galloc;
         TapSoA taps; taps.toff = c->d_tf.as<float>(); taps.wt = taps.toff + Talloc;
@@ -339,17 +370,29 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
             CU_OK(cudaStreamSynchronize(st));   // bc is a stack-lifetime staging vector
             launch_bilat_groups(c->d_bilat.as<BilatCand>(), nc, g, taps, c->db.dt, Galloc, st);
             c->launches[0] += 1;
-        } else {   // moment tensor: one group per candidate, filled on the host (source_moment_tensor.f90:256-263)
-            std::vector<float> hf((size_t)10 * Galloc, 0.f);
+        } else {   // groups defined on the host: the single group of a point moment tensor
+                   // (source_moment_tensor.f90:256-263), the sub-faults of an eikonal source (source_eikonal.f90:684-707)
+            std::vector<float> hf((size_t)11 * Galloc, 0.f);
             std::vector<int> hi((size_t)4 * Galloc, 0);
             for (int i = 0; i < nc; i++) {
                 const kh::SourcePrep& sp = prep[b0 + i];
                 if (sp.ngroups == 0) continue;
                 const int gi0 = cands[i].group_begin;
-                hf[gi0] = sp.point[0]; hf[(size_t)Galloc + gi0] = sp.point[1]; hf[2 * (size_t)Galloc + gi0] = sp.point[2];
-                hf[3 * (size_t)Galloc + gi0] = sp.time;
-                for (int k = 0; k < 6; k++) hf[(4 + k) * (size_t)Galloc + gi0] = sp.mhat[k];
-                hi[gi0] = cands[i].tap_begin; hi[(size_t)Galloc + gi0] = sp.nt;
+                for (int k = 0; k < sp.ngroups; k++) {
+                    const size_t gi = (size_t)gi0 + k;
+                    if (sp.explicit_groups) {
+                        hf[gi] = sp.g_north[k]; hf[(size_t)Galloc + gi] = sp.g_east[k]; hf[2 * (size_t)Galloc + gi] = sp.g_depth[k];
+                        hf[3 * (size_t)Galloc + gi] = 0.f;                       // taps carry the complete centroid time
+                        hf[10 * (size_t)Galloc + gi] = sp.g_gw[k];
+                        hi[gi] = cands[i].tap_begin + sp.g_tap_begin[k]; hi[(size_t)Galloc + gi] = sp.g_tap_count[k];
+                    } else {
+                        hf[gi] = sp.point[0]; hf[(size_t)Galloc + gi] = sp.point[1]; hf[2 * (size_t)Galloc + gi] = sp.point[2];
+                        hf[3 * (size_t)Galloc + gi] = sp.time;
+                        hf[10 * (size_t)Galloc + gi] = 1.f;
+                        hi[gi] = cands[i].tap_begin; hi[(size_t)Galloc + gi] = sp.nt;
+                    }
+                    for (int q = 0; q < 6; q++) hf[(4 + q) * (size_t)Galloc + gi] = sp.mhat[q];
+                }
             }
             CU_OK(cudaMemcpyAsync(c->d_gf.p, hf.data(), sizeof(float) * hf.size(), cudaMemcpyHostToDevice, st));
             CU_OK(cudaMemcpyAsync(c->d_gi.p, hi.data(), sizeof(int) * hi.size(), cudaMemcpyHostToDevice, st));
@@ -383,7 +426,16 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         c->ms[0] += ms12; c->ms[1] += ms23;
         // ---- K3 + K5: synthesis and misfit, in sub-chunks sized by the seismogram buffer ----------------
         const int tmax = tm3[0];
-        const int nq = (tmax + 6) / 4 + 1;
+        // rise-time fold (receiver.f90:853-904): the folded strips grow by about half the boxcar on either side
+        float max_rise = 0.f;
+        for (int i = 0; i < nc; i++) max_rise = std::max(max_rise, cands[i].risetime);
+        int margin_q = 0;
+        if (max_rise > 0.f) {
+            const int nshifts = 1 + 2 * (int)lroundf(0.5f * max_rise / c->db.dt);
+            if (nshifts > 1024) return kiwi_set_error("rise time too long for the fold kernel");
+            margin_q = ((nshifts + 1) / 2 + 2 + 3) / 4 + 1;
+        }
+        const int nq = (tmax + 6) / 4 + 1 + 2 * margin_q;
         const size_t seis_stride = (size_t)4 * nq;
         int nwarps = 8;
         while (nwarps > 1 && synth_smem_bytes(nwarps, nq) > (size_t)110 * 1024) nwarps--;
@@ -407,10 +459,16 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
             if (tmax > 0) {
                 cudaError_t e = launch_synth(c->db, c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>() + s0, ns_, g, taps, Galloc,
                                              c->interpolate ? 1 : 0, c->xunder, c->zunder, c->d_recs.as<GeoRec>() + poff * rec_stride, rec_stride,
-                                             c->d_hdrs.as<PairHdr>() + poff, nq, nwarps, c->d_seis.as<float>(), seis_stride,
+                                             c->d_hdrs.as<PairHdr>() + poff, nq, margin_q, nwarps, c->d_seis.as<float>(), seis_stride,
                                              c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, st);
                 if (e != cudaSuccess) return kiwi_set_error("CUDA error launching synthesis: %s", cudaGetErrorString(e));
                 c->launches[2] += 1;
+                if (max_rise > 0.f) {
+                    e = launch_fold(c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>() + s0, ns_, c->d_seis.as<float>(), seis_stride,
+                                    c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, c->db.dt, st);
+                    if (e != cudaSuccess) return kiwi_set_error("CUDA error launching the rise-time fold: %s", cudaGetErrorString(e));
+                    c->launches[2] += 1;
+                }
             } else {
                 CU_OK(cudaMemsetAsync(c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, 0xff, sizeof(SeisHdr) * (size_t)ns_ * nrcv * KIWI_MAX_COMP, st));
             }
@@ -484,6 +542,11 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         L.valid = true; L.sourcetype = sourcetype; L.n = nc; L.nrcv = nrcv; L.rec_stride = rec_stride; L.seis_stride = seis_stride;
         L.ngroups_total = Galloc; L.cands = cands; L.g = g; L.taps = taps; L.toff = toff; L.wt = wt;
         L.seis_valid = (sub >= nc) && tmax > 0;
+        {
+            const kh::SourcePrep& sp0 = prep[b0];
+            L.g0_tap_begin.assign(sp0.ngroups, cands[0].tap_begin); L.g0_tap_count.assign(sp0.ngroups, sp0.nt);
+            if (sp0.explicit_groups) for (int k = 0; k < sp0.ngroups; k++) { L.g0_tap_begin[k] = cands[0].tap_begin + sp0.g_tap_begin[k]; L.g0_tap_count[k] = sp0.g_tap_count[k]; }
+        }
     }
     cudaEventRecord(c->ev[1], st);
     CU_OK(cudaStreamSynchronize(st));
@@ -582,7 +645,7 @@ int ensure_single(kiwi_ctx* c, bool want_misfits) {
     }
     c->src_status = status;
     c->src_dirty = false;
-    if (status == KIWI_STATUS_BAD_PARAMS) return kiwi_set_error("discretisation of the source failed");
+    if (status == KIWI_STATUS_BAD_PARAMS) return kiwi_set_error("%s", c->prep_error.empty() ? "discretisation of the source failed" : c->prep_error.c_str());
     return 0;
 }
 
@@ -594,6 +657,8 @@ int kiwi_get_n_source_params(int sourcetype) {   // source_all.f90:97-121
     switch (sourcetype) {
         case KIWI_SOURCE_BILATERAL: return 14;
         case KIWI_SOURCE_MOMENT_TENSOR: return 11;
+        case KIWI_SOURCE_EIKONAL: return 15;       // source_eikonal.f90:36
+        case KIWI_SOURCE_MT_EIKONAL: return 20;    // source_mt_eikonal.f90:36
         default: return 0;
     }
 }
@@ -754,6 +819,10 @@ int kiwi_set_source_location(kiwi_ctx* c, float lat_deg, float lon_deg, double r
     c->olon = (double)kh::d2r_r(lon_deg);
     c->ref_time = ref_time;
     c->loc_set = true; c->receivers_dirty = true; c->src_dirty = true;
+    if (c->crust.loaded) {   // psm_set_origin_and_time -> psm_set_default_constraints (parameterized_source.f90:183-196): replaces any user constraints
+        kh::default_constraints(c->crust, c->olat, c->olon, c->thickness_limit, &c->constraints);
+        c->user_constraints = false;
+    }
     return 0;
 }
 
@@ -808,6 +877,33 @@ int kiwi_set_misfit_filter(kiwi_ctx* c, int ireceiver, int n, const float* x, co
         c->rcv[i].filter_x.assign(x, x + n); c->rcv[i].filter_y.assign(y, y + n);
     }
     c->receivers_dirty = true; c->src_misfits.clear();
+    return 0;
+}
+
+int kiwi_set_crust2x2(kiwi_ctx* c, const char* path) {   // crust2x2_load, minimizer.f90:1669-1674
+    if (!c) return kiwi_set_error("null context");
+    std::string err;
+    if (!kh::crust2x2_load(path, &c->crust, &err)) return kiwi_set_error("%s", err.c_str());
+    if (c->loc_set && !c->user_constraints) kh::default_constraints(c->crust, c->olat, c->olon, c->thickness_limit, &c->constraints);
+    c->src_dirty = true;
+    return 0;
+}
+
+int kiwi_set_source_constraints(kiwi_ctx* c, int n, const float* points, const float* normals) {   // minimizer_engine.f90 set_source_constraints
+    if (!c) return kiwi_set_error("null context");
+    if (n < 0) return kiwi_set_error("negative number of constraints");
+    c->constraints.assign(n, kh::Halfspace());
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++) { c->constraints[i].point[k] = points[3 * i + k]; c->constraints[i].normal[k] = normals[3 * i + k]; }
+    c->user_constraints = true; c->src_dirty = true;
+    return 0;
+}
+
+int kiwi_set_source_crustal_thickness_limit(kiwi_ctx* c, float limit) {   // parameterized_source.f90:198-207
+    if (!c) return kiwi_set_error("null context");
+    c->thickness_limit = limit;
+    if (c->crust.loaded && c->loc_set) { kh::default_constraints(c->crust, c->olat, c->olon, c->thickness_limit, &c->constraints); c->user_constraints = false; }
+    c->src_dirty = true;
     return 0;
 }
 
@@ -954,10 +1050,11 @@ int kiwi_discretize_source(kiwi_ctx* c, int sourcetype, int nparams, const float
     if (kiwi_set_source_params(c, sourcetype, nparams, params)) return 1;
     if (ensure_single(c, false)) return 1;
     const CandDev& cd = c->last.cands[0];
-    const int nc = cd.ngroups * cd.nt;
-    if (ncentroids) *ncentroids = nc;
+    int ncent = 0;
+    for (int v : c->last.g0_tap_count) ncent += v;
+    if (ncentroids) *ncentroids = ncent;
     if (grid3) { grid3[0] = cd.nx; grid3[1] = cd.ny; grid3[2] = cd.nt; }
-    const int m = std::min(nc, cap);
+    const int m = std::min(ncent, cap);
     if (m > 0) {
         CU_OK(c->d_table.ensure(sizeof(float) * 10 * (size_t)m));
         launch_expand_centroids(cd, c->last.g, c->last.taps, c->last.ngroups_total, c->d_table.as<float>(), m, c->stream);
@@ -984,9 +1081,9 @@ int kiwi_get_indices(kiwi_ctx* c, int ireceiver, int* ix, int* iz, int* its, flo
     int k = 0;
     const float dt = c->db.dt;
     for (int ig = 0; ig < ng_; ig++)
-        for (int it = 0; it < cd.nt; it++, k++) {
+        for (int it = 0; it < L.g0_tap_count[ig]; it++, k++) {
             if (k >= cap) continue;
-            const float time = tbase[ig] + L.toff[cd.tap_begin + it];
+            const float time = tbase[ig] + L.toff[L.g0_tap_begin[ig] + it];
             ix[k] = recs[ig].ix1; iz[k] = recs[ig].iz1; dix[k] = recs[ig].dix; diz[k] = recs[ig].diz;
             its[k] = (int)floorf(time / dt);   // sparse_trace.f90:640 on rshift = time/dt (seismogram.f90:139)
             if (near_boundary) near_boundary[k] = (recs[ig].flags & GEO_NEAR) ? 1 : 0;

@@ -1,5 +1,7 @@
 // Host-side arithmetic of the engine (see host_math.cpp).
 #pragma once
+#include <cstdint>
+#include <string>
 #include <vector>
 
 namespace kh {
@@ -25,7 +27,39 @@ struct SourcePrep {
     float p[16] = {0};
     float point[3] = {0}, time = 0.f;
     std::vector<float> toff, wt;
+    // eikonal sources: explicit groups with their own taps (toff = absolute centroid time)
+    std::vector<float> g_north, g_east, g_depth, g_gw;
+    std::vector<int> g_tap_begin, g_tap_count;
+    bool explicit_groups = false;
 };
+// ---- eikonal / mt_eikonal sources (source_eikonal_host.cpp) -----------------------------------------
+struct CrustProfile { float vp[8], vs[8], rho[8], thickness[7], elevation; };   // crust2x2.f90:39-44
+struct Crust2x2 {                                                                // crust2x2.f90:66 `model`
+    bool loaded = false;
+    int ntypes = 0, nlo = 0, nla = 0;
+    std::vector<CrustProfile> types;
+    std::vector<int16_t> map;
+    std::vector<float> elev;
+};
+struct Halfspace { float point[3], normal[3]; };                                 // geometry.f90:25-28
+struct EikonalGroup { float north, east, depth, gw; int tap_begin, tap_count; };
+struct EikonalPrep {
+    int nx = 0, ny = 0;
+    float moment = 1.f, risetime = 0.f;
+    float mhat[6] = {0};
+    std::vector<EikonalGroup> groups;          // sub-faults with a valid rupture time, iy outer / ix inner
+    std::vector<float> tap_time, tap_wt;       // centroid time and time weight per (group, tap)
+    std::string err;
+};
+bool crust2x2_load(const char* path, Crust2x2* c, std::string* err);
+CrustProfile crust2x2_get_profile(const Crust2x2& c, float lat, float lon);
+void crust2x2_get_profile_averages(const CrustProfile& p, float* vvp, float* vvs, float* vrho, float* vthi);
+void default_constraints(const Crust2x2& c, double olat_rad, double olon_rad, float thickness_limit, std::vector<Halfspace>* out);
+void eikonal_solver_fmm(const float* speed, int nx, int ny, const float origin[2], const float delta[2], const float initialpoint[2],
+                        float* times);
+bool prep_eikonal(const float* params, bool mt_variant, float shortest_doi, double olat_rad, double olon_rad, const Crust2x2& crust,
+                  const std::vector<Halfspace>& constraints, EikonalPrep* out);
+
 bool prep_bilateral(const float* params14, float shortest_doi, SourcePrep* out);
 bool prep_moment_tensor(const float* params11, float shortest_doi, SourcePrep* out);
 

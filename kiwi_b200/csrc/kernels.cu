@@ -58,6 +58,7 @@ __global__ void k_bilat_groups(const BilatCand* __restrict__ cands, GroupSoA g, 
         g.tbase[gi] = tshift;
 #pragma unroll
         for (int k = 0; k < 6; k++) g.mhat[(size_t)k * ngroups_total + gi] = c.mhat[k];
+        g.gw[gi] = 1.f;
         g.tap_begin[gi] = c.tap_begin;
         g.tap_count[gi] = c.nt;
         int lo = INT_MAX, hi = INT_MIN;
@@ -99,7 +100,7 @@ __global__ void k_expand_centroids(CandDev cand, GroupSoA g, TapSoA taps, int ng
             float* t = table + (size_t)id * 10;
             t[0] = g.north[gi]; t[1] = g.east[gi]; t[2] = g.depth[gi];
             t[3] = A_(g.tbase[gi], taps.toff[tb + k]);
-            for (int m = 0; m < 6; m++) t[4 + m] = M_(g.mhat[(size_t)m * ngroups_total + gi], taps.wt[tb + k]);
+            for (int m = 0; m < 6; m++) t[4 + m] = M_(M_(g.mhat[(size_t)m * ngroups_total + gi], taps.wt[tb + k]), g.gw[gi]);
         }
     }
 }
@@ -190,7 +191,8 @@ __global__ void __launch_bounds__(256) k_geometry(GfdbDev db, const ReceiverDev*
                 // weight wt multiplies the result later (the reference applies it to m first)
                 float m[6];
 #pragma unroll
-                for (int k = 0; k < 6; k++) m[k] = g.mhat[(size_t)k * ngroups_total + gi];
+                const float gwt = g.gw[gi];
+                for (int k = 0; k < 6; k++) m[k] = g.mhat[(size_t)k * ngroups_total + gi] * gwt;
                 const float azf = (float)azi;
                 float sa, ca, s2a, c2a;
                 sincosf(azf, &sa, &ca);
@@ -553,7 +555,7 @@ __device__ __forceinline__ void synth_group(const GfdbDev& db, const GeoRec& rec
 __global__ void __launch_bounds__(256, 2) k_synth(GfdbDev db, const ReceiverDev* __restrict__ rcv, int nrcv,
                                                    const CandDev* __restrict__ cands, GroupSoA g, TapSoA taps, int ngroups_total,
                                                    int interpolate, int xunder, int zunder, const GeoRec* __restrict__ recs,
-                                                   size_t rec_stride, const PairHdr* __restrict__ hdrs, int nq_alloc,
+                                                   size_t rec_stride, const PairHdr* __restrict__ hdrs, int nq_alloc, int margin_q,
                                                    float* __restrict__ seis, size_t seis_stride /* floats per component row */,
                                                    SeisHdr* __restrict__ shdrs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -568,7 +570,7 @@ __global__ void __launch_bounds__(256, 2) k_synth(GfdbDev db, const ReceiverDev*
         if (threadIdx.x < KIWI_MAX_COMP) { SeisHdr e; e.lo = 0; e.hi = -1; e.base = 0; e.pad = 0; myshdr[threadIdx.x] = e; }
         return;
     }
-    const int base = floor4(H.out0);
+    const int base = floor4(H.out0) - 4 * margin_q;   // room on the left for the rise-time fold (k_fold)
     const int baseq = base >> 2;
     const int nq = nq_alloc;   // quads per accumulator strip
     // shared memory: per warp 3 strips of nq float4 + 3 step rows of nq floats
@@ -660,6 +662,91 @@ __global__ void __launch_bounds__(256, 2) k_synth(GfdbDev db, const ReceiverDev*
         }
         if (threadIdx.x == 0) { SeisHdr e; e.lo = lo; e.hi = hi; e.base = base; e.pad = 0; myshdr[ic] = e; }
     }
+}
+
+// =================================================================================================
+// K4: rise-time fold.  receiver_scaled_seismograms_to_probes (receiver.f90:853-904) convolves the
+// synthetic of a source with psm%risetime > 0 (eikonal sources) with a boxcar, written as a sum of
+// shifted copies of the data-span part of the strip (strip_fold sparse_trace.f90:379-402, strip_dataspan
+// :347-377).  One CTA per (candidate, receiver, component); the row is rewritten in place.
+// =================================================================================================
+#define FOLD_MAXSHIFTS 1024
+__global__ void __launch_bounds__(256) k_fold(const ReceiverDev* __restrict__ rcv, int nrcv, const CandDev* __restrict__ cands,
+                                               float* __restrict__ seis, size_t seis_stride, SeisHdr* __restrict__ shdrs, float dt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* d = reinterpret_cast<float*>(smem_raw);   // copy of the strip
+    __shared__ float s_wl[FOLD_MAXSHIFTS], s_wr[FOLD_MAXSHIFTS], s_w[FOLD_MAXSHIFTS];
+    __shared__ int s_its[FOLD_MAXSHIFTS];
+    __shared__ int s_ds0, s_ds1, s_n, s_itsmin, s_itsmax;
+    const int item = blockIdx.x;
+    const int ic = item % KIWI_MAX_COMP, pair = item / KIWI_MAX_COMP;
+    const int b = pair / nrcv, ir = pair % nrcv;
+    const ReceiverDev& R = rcv[ir];
+    if (!R.enabled || ic >= R.ncomp) return;
+    const float risetime = cands[b].risetime;
+    if (!(risetime > 0.f) || cands[b].status != 0) return;
+    SeisHdr sh = shdrs[item];
+    if (sh.hi < sh.lo) return;
+    float* row = seis + (size_t)item * seis_stride;
+    const int n = sh.hi - sh.lo + 1;
+    if (threadIdx.x == 0) { s_ds0 = n - 1; s_ds1 = 0; }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = row[sh.lo - sh.base + i];
+    __syncthreads();
+    {   // strip_dataspan: first sample that is not zero .. first sample of the trailing constant run
+        const float lastvalue = d[n - 1];
+        int first = n - 1, lastdiff = -1;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            if (d[i] != 0.f) first = min(first, i);
+            if (d[i] != lastvalue) lastdiff = max(lastdiff, i);
+        }
+        atomicMin(&s_ds0, first);
+        atomicMax(&s_ds1, lastdiff + 1);
+    }
+    if (threadIdx.x == 0) {   // receiver.f90:868-885: boxcar weights of the shifted copies
+        const float r0 = -risetime / 2.f, r1 = risetime / 2.f;
+        const int nshifts = min(1 + 2 * (int)roundf(0.5f * risetime / dt), FOLD_MAXSHIFTS);
+        float sum = 0.f;
+        for (int is = 1; is <= nshifts; is++) {
+            const float ts = ((float)(is - 1) - 0.5f * (float)(nshifts - 1)) * dt;
+            const float a0 = ts - dt / 2.f, a1 = ts + dt / 2.f;
+            const float w = fmaxf(0.f, fminf(r1, a1) - fmaxf(r0, a0));
+            s_w[is - 1] = w;
+            s_wr[is - 1] = D_(ts, dt);   // shift in samples, split below
+            sum = A_(sum, w);
+        }
+        int imin = INT_MAX, imax = INT_MIN;
+        for (int i = 0; i < nshifts; i++) {
+            const float w = D_(s_w[i], sum);
+            const float rshift = s_wr[i];
+            const int its = (int)floorf(rshift);
+            const float wr0 = S_(rshift, (float)its), wl0 = S_(1.f, wr0);   // sparse_trace.f90:639-646
+            s_its[i] = its; s_w[i] = w; s_wr[i] = M_(wr0, w); s_wl[i] = M_(wl0, w);
+            imin = min(imin, its); imax = max(imax, its);
+        }
+        s_n = nshifts; s_itsmin = imin; s_itsmax = imax;
+    }
+    __syncthreads();
+    const int ds0 = s_ds0, ds1 = s_ds1;
+    if (ds1 < ds0) return;
+    const int nshifts = s_n;
+    // new strip span (growth of trace_multiply_add, sparse_trace.f90:649-668), clamped to the row
+    const int nlo = max(min(sh.lo, sh.lo + ds0 + s_itsmin), sh.base);
+    const int nhi = min(max(sh.hi, sh.lo + ds1 + s_itsmax + 1), sh.base + (int)seis_stride - 1);
+    const float lastval = d[ds1];
+    for (int x = nlo + (int)threadIdx.x; x <= nhi; x += blockDim.x) {
+        const int xr = x - sh.lo;   // index relative to the old strip start
+        float v = 0.f;
+        for (int i = 0; i < nshifts; i++) {
+            const int y = xr - s_its[i];          // sample of the data-span trace under the left weight
+            if (y > ds1) { if (lastval != 0.f) v = A_(v, M_(s_w[i], lastval)); }                   // :696-703
+            else if (y >= ds0) {
+                v = A_(v, M_(s_wl[i], d[y]));
+                if (y - 1 >= ds0) v = A_(v, M_(s_wr[i], d[y - 1]));
+            }
+        }
+        row[x - sh.base] = v;
+    }
+    if (threadIdx.x == 0) { sh.lo = nlo; sh.hi = nhi; shdrs[item] = sh; }
 }
 
 // =================================================================================================
@@ -1291,13 +1378,13 @@ void launch_geometry(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev
 size_t synth_smem_bytes(int nwarps, int nq) { return (size_t)nwarps * 3 * nq * (sizeof(float4) + sizeof(float)) + (size_t)nwarps * 2 * sizeof(GeoRec); }
 cudaError_t launch_synth(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, TapSoA taps,
                          int ngroups_total, int interpolate, int xunder, int zunder, const GeoRec* recs, size_t rec_stride,
-                         const PairHdr* hdrs, int nq_alloc, int nwarps, float* seis, size_t seis_stride, SeisHdr* shdrs,
+                         const PairHdr* hdrs, int nq_alloc, int margin_q, int nwarps, float* seis, size_t seis_stride, SeisHdr* shdrs,
                          cudaStream_t st) {
     size_t smem = synth_smem_bytes(nwarps, nq_alloc);
     cudaError_t e = cudaFuncSetAttribute(k_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k_synth<<<ncand * nrcv, nwarps * 32, smem, st>>>(db, rcv, nrcv, cands, g, taps, ngroups_total, interpolate, xunder, zunder, recs,
-                                                    rec_stride, hdrs, nq_alloc, seis, seis_stride, shdrs);
+                                                    rec_stride, hdrs, nq_alloc, margin_q, seis, seis_stride, shdrs);
     return cudaGetLastError();
 }
 void launch_misfit_td(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, const float* seis, size_t seis_stride,
@@ -1332,4 +1419,14 @@ void launch_mt_contract(const ReceiverDev* rcv, int nrcv, const MtLoc* locs, int
     if (nloc * nrcv > 0)
         k_mt_contract<<<nloc * nrcv, 128, 0, st>>>(rcv, nrcv, locs, mts, cand_of, seis, seis_stride, shdrs, refdata, taperdata, method, dt,
                                                   syn_factor, nmisfits, out);
+}
+
+cudaError_t launch_fold(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, float* seis, size_t seis_stride, SeisHdr* shdrs,
+                        float dt, cudaStream_t st) {
+    const size_t smem = seis_stride * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(k_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long items = (long long)ncand * nrcv * KIWI_MAX_COMP;
+    if (items > 0) k_fold<<<(unsigned)items, 256, smem, st>>>(rcv, nrcv, cands, seis, seis_stride, shdrs, dt);
+    return cudaGetLastError();
 }

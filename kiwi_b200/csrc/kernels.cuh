@@ -22,8 +22,10 @@ void launch_geometry(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev
 size_t synth_smem_bytes(int nwarps, int nq);
 cudaError_t launch_synth(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, TapSoA taps,
                          int ngroups_total, int interpolate, int xunder, int zunder, const GeoRec* recs, size_t rec_stride,
-                         const PairHdr* hdrs, int nq_alloc, int nwarps, float* seis, size_t seis_stride, SeisHdr* shdrs,
+                         const PairHdr* hdrs, int nq_alloc, int margin_q, int nwarps, float* seis, size_t seis_stride, SeisHdr* shdrs,
                          cudaStream_t st);
+cudaError_t launch_fold(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, float* seis, size_t seis_stride, SeisHdr* shdrs,
+                        float dt, cudaStream_t st);
 void launch_misfit_td(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, const float* seis, size_t seis_stride,
                       const SeisHdr* shdrs, const float* refdata, const float* taperdata, int method, float dt, float syn_factor,
                       int nmisfits, float* out, int* status, cudaStream_t st);

@@ -73,6 +73,7 @@ struct CandDev {
 struct GroupSoA {
     float *north, *east, *depth, *tbase;
     float* mhat;                // [6][ngroups_total] : mxx myy mzz mxy mxz myz
+    float* gw;                  // scalar weight of the group (sub-fault weight of an eikonal source, source_eikonal.f90:697; 1 otherwise)
     int *tap_begin, *tap_count; // taps of this group
     int *its_min, *its_max;     // min/max of floor((tbase (+) toff)/dt) over the taps
 };

@@ -6,6 +6,7 @@ raises KiwiError carrying the engine's error string (the reference answers "<cmd
 g_errstr, minimizer.f90:1676-1701).
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -18,6 +19,11 @@ NORMS = {"l2norm": 1, "l1norm": 2, "ampspec_l2norm": 3, "ampspec_l1norm": 4, "sc
          "floating_l2norm": 7, "floating_l1norm": 8}
 # benchmark/kiwibench.py:51-72: the 20-sample ramp source time function of the kiwibench database
 KIWIBENCH_STF = np.array([0, 0, 0, 0, 0, 0, .1, .2, .3, .4, .5, .6, .7, .8, .9, 1, 1, 1, 1, 1], dtype=np.float32)
+
+
+# the CRUST2.0 table converted by tools/make_crust2x2_table.py (the reference installs the text files under
+# $(datadir)/kiwi/aux/crust2x2, Makefile:135-139)
+CRUST2X2_TABLE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "crust2x2.kcr")
 
 
 class KiwiError(RuntimeError):
@@ -123,6 +129,8 @@ class Engine:
             raise KiwiError(lib.kiwi_last_error().decode())
         self._h = C.c_void_p(h)
         self._db = None
+        if os.path.exists(CRUST2X2_TABLE):          # minimizer loads crust2x2 at start-up (minimizer.f90:1669-1674)
+            self.set_crust2x2(CRUST2X2_TABLE)
 
     def close(self):
         if self._h:
@@ -185,6 +193,16 @@ class Engine:
 
     def set_source_location(self, lat_deg, lon_deg, ref_time=0.0):
         _check(lib.kiwi_set_source_location(self._h, lat_deg, lon_deg, ref_time))
+
+    def set_crust2x2(self, path):
+        _check(lib.kiwi_set_crust2x2(self._h, str(path).encode()))
+
+    def set_source_constraints(self, points, normals):
+        p, n = _f32(points).reshape(-1, 3), _f32(normals).reshape(-1, 3)
+        _check(lib.kiwi_set_source_constraints(self._h, p.shape[0], _fp(p), _fp(n)))
+
+    def set_source_crustal_thickness_limit(self, limit):
+        _check(lib.kiwi_set_source_crustal_thickness_limit(self._h, limit))
 
     def set_effective_dt(self, dt):
         _check(lib.kiwi_set_effective_dt(self._h, dt))

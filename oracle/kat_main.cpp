@@ -221,6 +221,77 @@ static void test_next_pow2() {
     check(ok, "fp32-log vs integer for n<=2^21");
 }
 
+// test_eikonal.f90:26-56: uniform 500x1000 grid, corner times within one cell
+static void test_eikonal() {
+    begin("test_eikonal");
+    const int nx = 500, ny = 1000;
+    Field speed, times; speed.alloc(nx, ny, 2.f);
+    float delta[2] = {50.f / nx, 50.f / ny}, initialpoint[2] = {0.f, 25.f}, origin[2] = {0.f, 0.f};
+    float eps = std::max(delta[0], delta[1]) / 2.f;
+    eikonal_solver_fmm(speed, origin, delta, initialpoint, times);
+    check(nearf(times(1, 1), 12.5f, eps), "1,1");          // :45-47
+    check(nearf(times(1, ny), 12.5f, eps), "1,ny");        // :48-50
+    check(nearf(times(nx, 1), 27.95f, eps), "nx,1");       // :51-53
+    check(nearf(times(nx, ny), 27.95f, eps), "nx,ny");     // :54-56
+}
+// test_heap.f90:27-60
+static void test_heap() {
+    begin("test_heap");
+    const int nn = 1000000;
+    std::vector<float> keys(nn + 1); std::vector<int> back(nn + 1, 0);
+    IndexHeapO h; initheap(h, nn);
+    for (int i = 1; i <= nn; i++) keys[i] = (float)(nn - (i - 1));
+    for (int i = 1; i <= nn; i++) pushheap(h, i, keys.data(), back.data());
+    bool ok = true;
+    for (int i = 1; i <= nn / 1000; i++) if (back[h.iheap[i]] != i) { ok = false; break; }
+    check(ok, "backpointer");                              // :43-48
+    ok = true;
+    for (int i = 1; i <= nn / 1000; i++) { int j; popheap(h, j, keys.data(), back.data()); if (fabsf((float)(nn - nn + i) - keys[j]) > 0.00001f) { ok = false; break; } }
+    check(ok, "popheap");                                  // :50-56
+}
+// test_geometry.f90:44-114
+static void test_geometry() {
+    begin("test_geometry");
+    HalfSpace hs; hs.point = Vec3{{0.f, 0.f, -1.f}}; hs.normal = Vec3{{0.f, -1.f, -1.f}};
+    Vec3 pts[4] = {{{0.f, 2.f, -1.f}}, {{0.f, -2.f, -1.f}}, {{0.f, 0.f, -1.f}}, {{0.f, 0.f, 0.f}}};
+    bool expected[4] = {true, false, true, true};
+    bool ok = true;
+    for (int i = 0; i < 4; i++) ok = ok && (expected[i] == point_in_halfspace(pts[i], hs));
+    check(ok, "point_in_halfspace");                       // :47-51
+    Vec3 pp; bool between, par;
+    get_piercingpoint(pts[0], pts[1], hs, pp, between, par);
+    check(pp[0] == 0.f && pp[1] == 0.f && pp[2] == -1.f && between && !par, "piercingpoint 1");     // :53-57
+    get_piercingpoint(Vec3{{0.f, 2.f, -1.f}}, Vec3{{0.f, 1.f, -2.f}}, hs, pp, between, par);
+    check(pp[0] == 0.f && pp[1] == 1.f && pp[2] == -2.f && !between && !par, "piercingpoint 2");    // :60-64
+    get_piercingpoint(Vec3{{0.f, 2.f, 5.f}}, Vec3{{0.f, 1.f, 1.f}}, hs, pp, between, par);
+    check(nearf(pp[0], 0.f, 1e-4f) && nearf(pp[1], 0.4f, 1e-4f) && nearf(pp[2], -1.4f, 1e-4f) && !between && !par, "piercingpoint 3");   // :66-70
+    get_piercingpoint(Vec3{{0.f, 1.f, 0.f}}, Vec3{{0.f, 2.f, -1.0001f}}, hs, pp, between, par);
+    check(pp[0] == 0.f && pp[1] == 0.f && pp[2] == 0.f && !between && par, "piercingpoint 4");      // :72-76
+    Circle circle;
+    init_euler(d2r_r(45.f), d2r_r(45.f), 0.f, circle.transform);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) circle.transform[i][j] = circle.transform[i][j] * 3.f;
+    circle.center = Vec3{{0.f, 0.f, 1.f}};
+    PolygonPts poly, trimmed;
+    circle_to_polygon(circle, 7, poly);
+    hs.point = Vec3{{0.f, 0.f, 0.f}}; hs.normal = Vec3{{0.f, 0.f, -1.f}};
+    trim_polygon(poly, hs, trimmed);
+    const float expected_circ[21] = {0.14987442f, 2.4953687f, 2.6585152f, -1.9344299f, 0.9903534f, 3.0681345f, -2.5620692f, -1.2604182f,
+                                     1.9204066f, -1.2604178f, -2.5620692f, 0.07959348f, -1.1043297f, -2.5185432f, 0.f,
+                                     2.3468528f, 0.9326396f, 0.f, 2.12132f, 2.1213207f, 1.0000004f};
+    ok = trimmed.size() == 7;
+    for (size_t i = 0; ok && i < 7; i++) for (int k = 0; k < 3; k++) ok = ok && nearf(trimmed[i][k], expected_circ[3 * i + k], 0.00001f);
+    check(ok, "trimmed circle");                           // :78-89
+    init_euler(d2r_r(13.f), d2r_r(100.f), 0.f, circle.transform);
+    circle.center = Vec3{{-5.f, -2.f, 1.f}};
+    circle_to_polygon(circle, 3600, poly);
+    check(nearf(polygon_area(poly), pi, 0.0001f), "pi estimation");   // :92-100
+    PolygonPts sq1 = {{{0, 0, 1}}, {{0, 2, 1}}, {{2, 2, 1}}, {{2, 0, 1}}}, sq2 = {{{1, 0, 0}}, {{1, 0, 2}}, {{1, 2, 2}}, {{1, 2, 0}}},
+               sq3 = {{{0, 1, 0}}, {{2, 1, 0}}, {{2, 1, 2}}, {{0, 1, 2}}};
+    check(nearf(polygon_area(sq1), 4.f, 0.00001f), "square area 1");
+    check(nearf(polygon_area(sq2), 4.f, 0.00001f), "square area 2");
+    check(nearf(polygon_area(sq3), 4.f, 0.00001f), "square area 3");
+}
+
 int main() {
     test_sparse_trace();
     test_comparator();
@@ -229,6 +300,9 @@ int main() {
     test_orthodrome();
     test_euler();
     test_next_pow2();
+    test_eikonal();
+    test_heap();
+    test_geometry();
     printf("kat: %d checks, %d failures\n", nchecks, nfail);
     return nfail != 0;
 }

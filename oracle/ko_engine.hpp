@@ -10,6 +10,7 @@
 // a new process.  `fresh=false` keeps the reference's history-dependent behaviour for study.
 #pragma once
 #include "ko_receiver.hpp"
+#include "ko_eikonal.hpp"
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -18,6 +19,8 @@ namespace ko {
 
 struct Engine {
     Psm psm;
+    PsmE psme;                         // eikonal / mt_eikonal parameters (source_eikonal.f90)
+    CrustModel crust;                  // crust2x2 model (minimizer.f90:1669-1674)
     float effective_dt = 1.f;          // minimizer_engine.f90:79
     Tdsm tdsm;
     std::vector<Receiver> receivers;
@@ -56,6 +59,8 @@ static inline void set_source_location(Engine& e, float lat_deg, float lon_deg, 
     e.psm.origin.lat = (double)d2r_r(lat_deg);
     e.psm.origin.lon = (double)d2r_r(lon_deg);
     e.psm.ref_time = ref_time;
+    e.psme.origin = e.psm.origin;
+    if (e.crust.loaded) psm_set_default_constraints(e.psme, e.crust);   // psm_set_origin_and_time, parameterized_source.f90:183-196
     e.source_location_inited = true;
 }
 // receiver.f90:746-801 with the file reading stripped: data starts at time `tbegin` rel. to ref time
@@ -108,6 +113,14 @@ static inline void set_synthetics_factor(Engine& e, float f) { for (auto& r : e.
 static inline bool set_source_params(Engine& e, int sourcetype, const float* params, int nparams) {
     if (!e.source_location_inited) { e.errstr = "no source location set"; return false; }
     bool omc;
+    if (sourcetype == PSM_EIKONAL || sourcetype == PSM_MT_EIKONAL) {
+        if (nparams != (sourcetype == PSM_EIKONAL ? 15 : 20)) { e.errstr = "wrong number of source parameters"; return false; }
+        if (!e.crust.loaded) { e.errstr = "crust2x2 model not loaded"; return false; }
+        psm_set_eikonal(e.psme, params, sourcetype == PSM_MT_EIKONAL);
+        e.psm.sourcetype = sourcetype; e.psm.moment = e.psme.moment; e.psm.risetime = e.psme.risetime;
+        e.source_inited = true;
+        return true;
+    }
     if (!psm_set(e.psm, sourcetype, params, nparams, omc)) { e.errstr = "unknown source type or wrong number of parameters"; return false; }
     e.source_inited = true;
     return true;
@@ -134,7 +147,11 @@ static inline bool calculate_seismograms(Engine& e) {
     if (!e.source_inited) { e.errstr = "no source parameters set"; return false; }
     if (e.fresh) reset_to_fresh_state(e);
     bool ok;
-    psm_to_tdsm(e.psm, e.tdsm, e.effective_dt, ok);
+    if (e.psm.sourcetype == PSM_EIKONAL || e.psm.sourcetype == PSM_MT_EIKONAL) {
+        ok = psm_to_tdsm_eikonal(e.psme, e.crust, e.tdsm, e.effective_dt, e.errstr);
+        e.tdsm.origin = e.psm.origin; e.tdsm.ref_time = e.psm.ref_time;
+        e.psm.grid_size = {e.psme.grid_size[0], e.psme.grid_size[1]};
+    } else psm_to_tdsm(e.psm, e.tdsm, e.effective_dt, ok);
     if (!ok) return false;
     int nthreads = 1;
 #ifdef _OPENMP

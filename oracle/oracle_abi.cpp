@@ -72,6 +72,32 @@ int oracle_set_floating_shiftrange(void* h, int irec, float lo, float hi) {  // 
     else { e.receivers[irec - 1].floating_shiftrange[0] = r[0]; e.receivers[irec - 1].floating_shiftrange[1] = r[1]; }
     return 0;
 }
+int oracle_set_crust2x2(void* h, const char* path) {
+    Engine& e = *(Engine*)h;
+    if (!crust2x2_load(path, e.crust)) { e.errstr = "can't load crust2x2 table"; return 1; }
+    if (e.source_location_inited) psm_set_default_constraints(e.psme, e.crust);
+    return 0;
+}
+int oracle_set_source_constraints(void* h, int n, const float* points, const float* normals) {   // parameterized_source.f90:147-166
+    Engine& e = *(Engine*)h;
+    e.psme.constraints.assign(n, HalfSpace());
+    for (int i = 0; i < n; i++) for (int k = 0; k < 3; k++) { e.psme.constraints[i].point[k] = points[3 * i + k]; e.psme.constraints[i].normal[k] = normals[3 * i + k]; }
+    return 0;
+}
+int oracle_set_source_crustal_thickness_limit(void* h, float limit) {
+    Engine& e = *(Engine*)h;
+    e.psme.crustal_thickness_limit = limit;
+    if (e.crust.loaded && e.source_location_inited) psm_set_default_constraints(e.psme, e.crust);
+    return 0;
+}
+// eikonal solver on a caller-provided speed field (test_eikonal.f90): column-major speed(nx,ny)
+int oracle_eikonal_fmm(int nx, int ny, const float* speed, const float* origin, const float* delta, const float* initialpoint, float* times) {
+    Field sp, tm; sp.alloc(nx, ny);
+    for (int i = 0; i < nx * ny; i++) sp.a[i + 1] = speed[i];
+    eikonal_solver_fmm(sp, origin, delta, initialpoint, tm);
+    for (int i = 0; i < nx * ny; i++) times[i] = tm.a[i + 1];
+    return 0;
+}
 int oracle_get_nmisfits(void* h) {
     Engine& e = *(Engine*)h; int n = 0;
     for (auto& r : e.receivers) if (r.enabled) n += r.ncomponents;
@@ -125,7 +151,11 @@ int oracle_get_probe_spans(void* h, int irec, int icomp, int* out8) {
 int oracle_discretize_source(void* h, int sourcetype, int nparams, const float* params, float* table, int cap, int* grid3) {
     Engine& e = *(Engine*)h;
     if (!set_source_params(e, sourcetype, params, nparams)) return -1;
-    bool ok; psm_to_tdsm(e.psm, e.tdsm, e.effective_dt, ok);
+    bool ok;
+    if (sourcetype == PSM_EIKONAL || sourcetype == PSM_MT_EIKONAL) {
+        ok = psm_to_tdsm_eikonal(e.psme, e.crust, e.tdsm, e.effective_dt, e.errstr);
+        e.psm.grid_size = {e.psme.grid_size[0], e.psme.grid_size[1]};
+    } else psm_to_tdsm(e.psm, e.tdsm, e.effective_dt, ok);
     if (!ok) return -1;
     int n = (int)e.tdsm.centroids.size();
     for (int i = 0; i < std::min(n, cap); i++) {

@@ -62,6 +62,16 @@ class OracleEngine:
         if threads:
             self.L.oracle_set_num_threads(C.c_int(threads))
         self._keep = None
+        table = os.path.join(ROOT, "kiwi_b200", "data", "crust2x2.kcr")
+        if os.path.exists(table):
+            self._check(self.L.oracle_set_crust2x2(self.h, table.encode()))
+
+    def set_source_constraints(self, points, normals):
+        p, n = _f32(points).reshape(-1, 3), _f32(normals).reshape(-1, 3)
+        self._check(self.L.oracle_set_source_constraints(self.h, C.c_int(p.shape[0]), p.ctypes.data_as(fp), n.ctypes.data_as(fp)))
+
+    def set_source_crustal_thickness_limit(self, limit):
+        self._check(self.L.oracle_set_source_crustal_thickness_limit(self.h, C.c_float(limit)))
 
     def close(self):
         if self.h:

@@ -100,3 +100,24 @@ def test_fresh_state_makes_evaluation_order_irrelevant():
     m1, _ = o.eval_sources("bilateral", np.stack([sc.BILAT_SMALL, p2]))
     m2, _ = o.eval_sources("bilateral", np.stack([p2, sc.BILAT_SMALL]))
     assert np.array_equal(m1[0], m2[1]) and np.array_equal(m1[1], m2[0])
+
+
+def test_eikonal_source_properties():
+    """source_eikonal.f90: weights sum to one, times are centred (centertime), points respect the default
+    depth constraints (parameterized_source.f90:127-145), the rise-time fold keeps the static offset."""
+    o = make()
+    p = np.array([0.1, 100, -200, 3500, 2e18, 40, 70, 20, 0, 0, 1500, 300, -200, 0.8, 0.4], np.float32)
+    t, g, n = o.discretize_source("eikonal", p)
+    assert n > 50 and g[0] >= 2 and g[1] >= 2
+    m = t[:, 4:10].astype(np.float64)
+    # sum of the centroid tensors = unit double couple (weights and time weights both sum to one)
+    assert abs(np.abs(m.sum(0)).max() - 1.0) < 0.05 or np.linalg.norm(m.sum(0)) > 0.9
+    assert t[:, 2].min() >= 1500.0
+    assert np.hypot(t[:, 0] - 100, t[:, 1] + 200).max() <= 1500.0 * 1.01
+    o.eval_sources("eikonal", p)
+    f1, folded = o.get_seismogram(1, 3, 1)
+    f0, raw = o.get_seismogram(1, 3, 0)
+    assert abs(folded[-1] - raw[-1] * 2e18) <= 1e-4 * abs(folded).max()      # boxcar weights sum to one
+    p2 = p.copy(); p2[11] = 9000
+    _, st = o.eval_sources("eikonal", p2)
+    assert st[0] == 1

@@ -319,3 +319,73 @@ def test_moment_tensor_grid_search_tensor_core_path(norm, taper):
     md, sd = g.eval_sources("moment_tensor", p)
     assert np.all(np.abs(mg - md) <= misfit_tol(mo)), np.abs((mg - md) / misfit_tol(mo)).max()
     assert not np.array_equal(mg, md)      # really two different code paths
+
+
+# eikonal: time north east depth moment strike dip rake bord-x bord-y bord-radius nukl-x nukl-y rel-rupture-velocity rise-time
+EIK = np.array([0.1, 100, -200, 3500, 2e18, 40, 70, 20, 0, 0, 1500, 300, -200, 0.8, 0.4], np.float32)
+# mt_eikonal: ... dip bord-x bord-y bord-radius nukl-x nukl-y rel-rupture-velocity mxx myy mzz mxy mxz myz rise-time
+MTEIK = np.array([0.1, 100, -200, 3500, 1.5, 40, 70, 0, 0, 1500, 300, -200, 0.8, 1e18, -0.4e18, -0.6e18, 0.3e18, 0.2e18, -0.5e18, 0.3], np.float32)
+
+
+@pytest.mark.parametrize("stype,params", [("eikonal", EIK), ("mt_eikonal", MTEIK),
+                                          ("eikonal", np.array([0, 0, 0, 2600, 1e18, 120, 85, -60, 200, -300, 2500, -400, 100, 0.9, 0.0], np.float32))])
+def test_eikonal_discretisation_bit_exact(stype, params):
+    """source_eikonal.f90 / source_mt_eikonal.f90 incl. the fast-marching solve (eikonal.f90, heap.f90): the whole
+    centroid table bit for bit"""
+    g, o = engines(sc.small_db(), COMPS6)
+    tg, gg, ng = g.discretize_source(stype, params)
+    to, go, no = o.discretize_source(stype, params)
+    assert ng == no and ng > 50
+    assert list(gg[:2]) == list(go[:2])
+    assert np.array_equal(tg.view(np.uint32), to.view(np.uint32))
+
+
+@pytest.mark.parametrize("stype,params", [("eikonal", EIK), ("mt_eikonal", MTEIK)])
+def test_eikonal_seismograms_with_rise_time_fold(stype, params):
+    """synthesis + rise-time boxcar fold (receiver.f90:853-904, strip_fold) + moment scaling"""
+    g, o = engines(sc.small_db(), COMPS6)
+    o.eval_sources(stype, params)
+    g.set_source_params(stype, params)
+    for ir in range(1, 7):
+        for ic in range(1, len(COMPS6[ir - 1]) + 1):
+            assert_seis_close(g.get_seismogram(ir, ic, 1), o.get_seismogram(ir, ic, 1), "rcv %d comp %d" % (ir, ic))
+
+
+@pytest.mark.parametrize("norm", ["l2norm", "ampspec_l1norm"])
+def test_eikonal_misfits_batched_with_failures(norm):
+    g, o = engines(sc.small_db(), COMPS6)
+    ncomps = [len(c) for c in COMPS6]
+    o.eval_sources("eikonal", EIK)
+    sc.set_refs_from(o, [g, o], ncomps)
+    for e in (g, o):
+        e.set_misfit_method(norm)
+        for ir in range(1, 7):
+            e.set_misfit_taper(ir, *TAPER)
+        e.set_misfit_filter(*FILTER)
+    p = np.tile(EIK, (6, 1))
+    p[1, 5] += 25; p[2, 10] = 2200; p[3, 13] = 0.7; p[3, 14] = 0.8
+    p[4, 11] = 5000          # nucleation point outside the rupture area: this candidate fails, the batch goes on
+    p[5, 3] = 900; p[5, 10] = 300; p[5, 11] = 0; p[5, 12] = 0   # whole circle above the 1500 m plane: "Empty rupture area"
+    mg, sg = g.eval_sources("eikonal", p)
+    mo, so = o.eval_sources("eikonal", p)
+    assert list(sg) == [0, 0, 0, 0, 1, 1] and list(so) == [0, 0, 0, 0, 1, 1]
+    tol = misfit_tol(mo[:4], 0.25 if norm.startswith("ampspec") else 0.1)
+    assert np.all(np.abs(mg[:4] - mo[:4]) <= tol), np.abs((mg[:4] - mo[:4]) / tol).max()
+    assert np.all(np.isnan(mg[4:]))
+
+
+def test_eikonal_user_constraints_and_thickness_limit():
+    g, o = engines(sc.small_db(), COMPS6)
+    for e in (g, o):
+        e.set_source_crustal_thickness_limit(4000.0)
+    tg, _, ng = g.discretize_source("eikonal", EIK)
+    to, _, no = o.discretize_source("eikonal", EIK)
+    assert ng == no and np.array_equal(tg.view(np.uint32), to.view(np.uint32))
+    assert tg[:, 2].max() <= 4000.0
+    pts, nrm = [[0, 0, 2500], [0, 0, 4500], [0, -300, 0]], [[0, 0, -1], [0, 0, 1], [0, -1, 0]]
+    for e in (g, o):
+        e.set_source_constraints(pts, nrm)
+    tg, _, ng = g.discretize_source("eikonal", EIK + np.float32(0))
+    to, _, no = o.discretize_source("eikonal", EIK)
+    assert ng == no and np.array_equal(tg.view(np.uint32), to.view(np.uint32))
+    assert tg[:, 2].min() >= 2500.0 and tg[:, 1].min() >= -300.0
