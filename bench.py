@@ -64,7 +64,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -73,9 +73,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -86,7 +86,13 @@ class ClockSampler:
         self.thread.join(timeout=2)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        # samples that arrived inside the timed region; a short region is padded with the samples of the
+        # warm-up steps right before it (same kernels, same load) so that there are at least three
+        inside = [r for (t, r) in self.rows if t0 is None or (t0 <= t <= (t1 or t) + 0.15)]
+        before = [r for (t, r) in self.rows if t0 is not None and t < t0]
+        padded = len(inside) < 3
+        rows = (before[-(3 - len(inside)):] if padded else []) + inside
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except (ValueError, IndexError):
@@ -95,7 +101,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nme)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": len(inside), "padded_with_warmup_samples": bool(padded)}
 
 
 def make_db(w, rank, world, barrier):
@@ -226,6 +232,8 @@ def main():
         run_reference_arm(args, w, rank)
         return
 
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)          # anything a library prints on fd 1 (e.g. the NCCL version banner) goes to stderr
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -263,6 +271,9 @@ def main():
             dist.all_gather_into_tensor(gathered, d_out)
         return st, t
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         st, _t = step_device()
     assert not st.any(), "candidate evaluation failed: %s" % st
@@ -275,11 +286,9 @@ def main():
         b_alg, b_log = b_alg * scale, b_log * scale
 
     # ---- timed region 1: device-resident results (value) -----------------------------------------------
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     barrier()
     t0 = time.perf_counter()
+    t0_wall = time.time()
     dev_ms = synth_ms = 0.0
     launches = nsynth = 0
     stage = np.zeros(4)
@@ -289,7 +298,7 @@ def main():
         stage += [t["discretise_ms"], t["geometry_ms"], t["synthesis_ms"], t["misfit_ms"]]
     barrier()
     wall = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
+    t1_wall = time.time()
     tt = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -309,6 +318,7 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(te.cpu()[0])
+    clocks = sampler.stop(t0_wall, t1_wall) if rank == 0 else None
     h2d = int(mine.nbytes + B * (36 + 100) + 7 * 8 * B)     # params + CandDev/BilatCand tables + STF taps
     d2h = int(mis.nbytes + st.nbytes + 4)
 
@@ -359,7 +369,8 @@ def main():
 
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(w, db, rlat, rlon, rdep, dt, stype, mine, mis)
-    print(json.dumps(line), flush=True)
+    real_stdout.write(json.dumps(line) + "\n")
+    real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 

@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libkiwi_b200.so")
+MINIMIZER = os.path.join(HERE, "kiwi_minimizer")
 CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 NVCC = os.path.join(CUDA_HOME, "bin", "nvcc")
 CXX = os.environ.get("CXX", "g++")
@@ -59,6 +60,14 @@ def build(force=False, verbose=False):
                 sys.stderr.write(r.stderr)
     if force or _newer(LIB, objs):
         cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-Xcompiler", "-pthread"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("link failed: " + " ".join(cmd))
+    # the `minimizer`-compatible command front-end (text protocol of minimizer.f90:1676-1813)
+    main_src = os.path.join(CSRC, "minimizer_main.cpp")
+    if force or _newer(MINIMIZER, [main_src, LIB] + headers):
+        cmd = [CXX, "-O2", "-std=c++17", main_src, "-o", MINIMIZER, "-L" + HERE, "-lkiwi_b200", "-Wl,-rpath,$ORIGIN", "-pthread"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

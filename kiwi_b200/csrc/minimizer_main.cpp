@@ -1,0 +1,310 @@
+// kiwi_minimizer -- command front-end speaking the text protocol of the reference's `minimizer`
+// program (minimizer.f90:1676-1813) on top of the C ABI of libkiwi_b200.
+//
+// One command per stdin line, `#` comments and repeated blanks stripped (reduce_whitespace,
+// minimizer.f90:1815-1846); the reply is "<cmd>: ok", "<cmd>: ok >" + answer line, "<cmd>: nok" or
+// "<cmd>: nok >" + error line, flushed per command (:1682-1699), so the Python drivers of the
+// reference (python/tunguska/seismosizer.py:306-338) can talk to it unchanged.  Only the commands on
+// the hot path are implemented; the others answer "nok > unknown command".
+// Additions: `set_database` takes a KGF1 file (HDF5 is not available here), and
+// `eval_sources <type> <file>` evaluates a whole table of candidates in one call.
+#include "../../include/kiwi_b200.h"
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+namespace {
+
+std::string reduce_whitespace(const std::string& in) {   // minimizer.f90:1815-1846
+    std::string out;
+    bool ws = true;
+    for (char ch : in) {
+        if (ch != ' ' && ch != '\t') {
+            if (ch == '#') break;
+            out.push_back(ch); ws = false;
+        } else if (!ws) { out.push_back(' '); ws = true; }
+    }
+    while (!out.empty() && out.back() == ' ') out.pop_back();
+    return out;
+}
+std::vector<std::string> words(const std::string& s) {
+    std::vector<std::string> w; std::istringstream is(s); std::string t;
+    while (is >> t) w.push_back(t);
+    return w;
+}
+bool to_floats(const std::vector<std::string>& w, size_t from, std::vector<float>* out) {
+    out->clear();
+    for (size_t i = from; i < w.size(); i++) {
+        char* end = nullptr;
+        const float v = strtof(w[i].c_str(), &end);
+        if (end == w[i].c_str() || *end != 0) return false;
+        out->push_back(v);
+    }
+    return true;
+}
+int source_id(const std::string& n) {   // source_all.f90:92-97
+    if (n == "bilateral") return KIWI_SOURCE_BILATERAL;
+    if (n == "circular") return KIWI_SOURCE_CIRCULAR;
+    if (n == "point_lp") return KIWI_SOURCE_POINT_LP;
+    if (n == "eikonal") return KIWI_SOURCE_EIKONAL;
+    if (n == "mt_eikonal") return KIWI_SOURCE_MT_EIKONAL;
+    if (n == "moment_tensor") return KIWI_SOURCE_MOMENT_TENSOR;
+    return 0;
+}
+int norm_id(const std::string& n) {   // comparator.f90:33-42, comparator_get_norm_id
+    static const char* names[] = {"l2norm", "l1norm", "ampspec_l2norm", "ampspec_l1norm", "scalar_product", "peak", "floating_l2norm", "floating_l1norm"};
+    for (int i = 0; i < 8; i++) if (n == names[i]) return i + 1;
+    return 0;
+}
+std::string fmt_floats(const float* v, size_t n) {   // list-directed output: blank separated reals
+    std::string s; char buf[40];
+    for (size_t i = 0; i < n; i++) { snprintf(buf, sizeof buf, "%s%.9g", i ? " " : " ", v[i]); s += buf; }
+    return s;
+}
+// `table` seismogram file: two columns time value (seismogram_io.f90:123-136, 231-245)
+bool read_table(const std::string& fn, float* tbegin, float* dt, std::vector<float>* data) {
+    std::ifstream f(fn);
+    if (!f) return false;
+    std::vector<double> t; data->clear();
+    double a, b;
+    while (f >> a >> b) { t.push_back(a); data->push_back((float)b); }
+    if (t.empty()) return false;
+    *tbegin = (float)t[0];
+    *dt = t.size() > 1 ? (float)((t.back() - t[0]) / (double)(t.size() - 1)) : 0.f;
+    return true;
+}
+
+struct State {
+    kiwi_ctx* ctx = nullptr;
+    kiwi_gfdb* db = nullptr;
+    std::vector<std::string> comps;   // component strings of the receivers
+    float dt = 0.f;
+    double ref_time = 0.;
+};
+
+// returns ok; answer / err filled
+bool do_command(State& S, const std::string& cmd, const std::vector<std::string>& w, std::string* answer, std::string* err) {
+    auto fail = [&](const std::string& m) { *err = m; return false; };
+    auto cfail = [&]() { *err = kiwi_last_error(); return false; };
+    static const char* known[] = {"set_database", "set_local_interpolation", "set_spacial_undersampling", "set_receivers", "switch_receiver",
+                                  "set_source_location", "set_source_constraints", "set_source_crustal_thickness_limit", "set_source_params",
+                                  "set_effective_dt", "set_ref_seismograms", "set_misfit_method", "set_misfit_taper", "set_misfit_filter",
+                                  "set_synthetics_factor", "set_floating_shiftrange", "get_misfits", "get_global_misfit", "get_floating_shifts",
+                                  "output_seismograms", "eval_sources"};
+    bool is_known = false;
+    for (const char* k : known) if (cmd == k) is_known = true;
+    if (!is_known) return fail("unknown command: " + cmd);   // minimizer.f90:1809-1811
+    if (!S.ctx) {
+        S.ctx = kiwi_create(0);
+        if (!S.ctx) return cfail();
+        const char* table = getenv("KIWI_CRUST2X2");
+        if (table && *table) kiwi_set_crust2x2(S.ctx, table);   // crust2x2_load at start-up, minimizer.f90:1669-1674
+    }
+    std::vector<float> v;
+    if (cmd == "set_database") {
+        if (w.size() < 2) return fail("usage: set_database dbpath [ nipx nipz ]");
+        if (w.size() >= 4 && (atoi(w[2].c_str()) != 1 || atoi(w[3].c_str()) != 1)) return fail("set_database: trace interpolation (nipx, nipz > 1) is not available");
+        kiwi_gfdb* db = kiwi_gfdb_read(w[1].c_str());
+        if (!db) return cfail();
+        if (kiwi_set_database(S.ctx, db)) { kiwi_gfdb_destroy(db); return cfail(); }
+        if (S.db) kiwi_gfdb_destroy(S.db);
+        S.db = db;
+        kiwi_gfdb_meta(db, nullptr, nullptr, nullptr, &S.dt, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        return true;
+    }
+    if (cmd == "set_local_interpolation") {
+        if (w.size() != 2 || (w[1] != "nearest_neighbor" && w[1] != "bilinear")) return fail("unknown interpolation method: " + (w.size() > 1 ? w[1] : std::string()));
+        return kiwi_set_local_interpolation(S.ctx, w[1] == "bilinear") ? cfail() : true;
+    }
+    if (cmd == "set_spacial_undersampling") {
+        if (w.size() != 3) return fail("usage: set_spacial_undersampling xunder zunder");
+        return kiwi_set_spacial_undersampling(S.ctx, atoi(w[1].c_str()), atoi(w[2].c_str())) ? cfail() : true;
+    }
+    if (cmd == "set_receivers") {   // minimizer_engine.f90:165-286
+        if (w.size() < 2) return fail("usage: set_receivers filename [ has_depth ]");
+        const bool has_depth = w.size() > 2 && w[2] == "has_depth";
+        std::ifstream f(w[1]);
+        if (!f) return fail("can't open file: " + w[1]);
+        std::vector<double> lat, lon; std::vector<float> dep; std::vector<std::string> comps;
+        std::string line;
+        while (std::getline(f, line)) {
+            std::vector<std::string> t = words(reduce_whitespace(line));
+            if (t.empty()) continue;
+            const size_t need = has_depth ? 3 : 2;
+            if (t.size() < need) return fail("failed to parse receivers file: " + w[1]);
+            lat.push_back(atof(t[0].c_str())); lon.push_back(atof(t[1].c_str()));
+            dep.push_back(has_depth ? (float)atof(t[2].c_str()) : 0.f);
+            comps.push_back(t.size() > need ? t[need] : "ned");
+        }
+        std::vector<const char*> cp;
+        for (auto& s : comps) cp.push_back(s.c_str());
+        if (kiwi_set_receivers(S.ctx, (int)lat.size(), lat.data(), lon.data(), dep.data(), cp.data())) return cfail();
+        S.comps = comps;
+        return true;
+    }
+    if (cmd == "switch_receiver") {
+        if (w.size() != 3 || (w[2] != "on" && w[2] != "off")) return fail("usage: switch_receiver ireceiver ( on | off )");
+        return kiwi_switch_receiver(S.ctx, atoi(w[1].c_str()), w[2] == "on") ? cfail() : true;
+    }
+    if (cmd == "set_source_location") {
+        if (w.size() != 4) return fail("usage: set_source_location latitude longitude reference-time");
+        S.ref_time = atof(w[3].c_str());
+        return kiwi_set_source_location(S.ctx, (float)atof(w[1].c_str()), (float)atof(w[2].c_str()), S.ref_time) ? cfail() : true;
+    }
+    if (cmd == "set_source_constraints") {
+        if (!to_floats(w, 1, &v) || v.size() % 6 != 0) return fail("usage: set_source_constraints px1 py1 pz1 nx1 ny1 nz1 ...");
+        std::vector<float> p, n;
+        for (size_t i = 0; i < v.size(); i += 6) { p.insert(p.end(), &v[i], &v[i] + 3); n.insert(n.end(), &v[i + 3], &v[i + 3] + 3); }
+        return kiwi_set_source_constraints(S.ctx, (int)(v.size() / 6), p.data(), n.data()) ? cfail() : true;
+    }
+    if (cmd == "set_source_crustal_thickness_limit") {
+        if (!to_floats(w, 1, &v) || v.size() != 1) return fail("usage: set_source_crustal_thickness_limit thickness-limit");
+        return kiwi_set_source_crustal_thickness_limit(S.ctx, v[0]) ? cfail() : true;
+    }
+    if (cmd == "set_source_params") {   // minimizer.f90:636-692
+        if (w.size() < 2) return fail("usage: set_source_params source-type source-params ...");
+        const int st = source_id(w[1]);
+        if (!st) return fail("unknown source type name: " + w[1]);
+        const int np = kiwi_get_n_source_params(st);
+        if (!to_floats(w, 2, &v)) return fail("failed to parse source params");
+        if ((int)v.size() != np) return fail("source of type '" + w[1] + "' requires " + std::to_string(np) + " parameters.");
+        return kiwi_set_source_params(S.ctx, st, np, v.data()) ? cfail() : true;
+    }
+    if (cmd == "set_effective_dt") {
+        if (!to_floats(w, 1, &v) || v.size() != 1) return fail("usage: set_effective_dt effective_dt");
+        return kiwi_set_effective_dt(S.ctx, v[0]) ? cfail() : true;
+    }
+    if (cmd == "set_ref_seismograms") {   // minimizer_engine.f90:313-352, receiver.f90:746-801
+        if (w.size() != 3) return fail("usage: set_ref_seismograms filenamebase fileformat");
+        if (w[2] != "table") return fail("file format not available: " + w[2]);
+        static const char names[11] = {'w', 's', 'u', 'l', 'c', '?', 'a', 'r', 'd', 'n', 'e'};
+        (void)names;
+        for (size_t ir = 0; ir < S.comps.size(); ir++)
+            for (size_t ic = 0; ic < S.comps[ir].size(); ic++) {
+                const std::string fn = w[1] + "-" + std::to_string(ir + 1) + "-" + S.comps[ir][ic] + "." + w[2];
+                float tb, dtf; std::vector<float> data;
+                if (!read_table(fn, &tb, &dtf, &data)) return fail("can't open file: " + fn);
+                if (data.size() > 1 && S.dt > 0.f && fabs(dtf - S.dt) > 1e-4f * S.dt) return fail("sampling rate of seismogram does not match gfdb: " + fn);   // receiver.f90:776-781
+                if (kiwi_set_ref_seismogram(S.ctx, (int)ir + 1, (int)ic + 1, (float)((double)tb - S.ref_time), (int)data.size(), data.data())) return cfail();
+            }
+        return true;
+    }
+    if (cmd == "set_misfit_method") {
+        if (w.size() != 2 || !norm_id(w[1])) return fail("unknown norm method: " + (w.size() > 1 ? w[1] : std::string()));
+        return kiwi_set_misfit_method(S.ctx, norm_id(w[1])) ? cfail() : true;
+    }
+    if (cmd == "set_misfit_taper") {
+        if (!to_floats(w, 1, &v) || v.size() < 5 || v.size() % 2 != 1) return fail("failed to parse values");
+        std::vector<float> x, y;
+        for (size_t i = 1; i + 1 < v.size(); i += 2) { x.push_back(v[i]); y.push_back(v[i + 1]); }
+        return kiwi_set_misfit_taper(S.ctx, (int)v[0], (int)x.size(), x.data(), y.data()) ? cfail() : true;
+    }
+    if (cmd == "set_misfit_filter") {
+        if (!to_floats(w, 1, &v) || v.size() < 4 || v.size() % 2 != 0) return fail("failed to parse coordinates");
+        std::vector<float> x, y;
+        for (size_t i = 0; i + 1 < v.size(); i += 2) { x.push_back(v[i]); y.push_back(v[i + 1]); }
+        return kiwi_set_misfit_filter(S.ctx, 0, (int)x.size(), x.data(), y.data()) ? cfail() : true;
+    }
+    if (cmd == "set_synthetics_factor") {
+        if (!to_floats(w, 1, &v) || v.size() != 1) return fail("usage: set_synthetics_factor factor");
+        return kiwi_set_synthetics_factor(S.ctx, v[0]) ? cfail() : true;
+    }
+    if (cmd == "set_floating_shiftrange") {
+        if (!to_floats(w, 1, &v) || v.size() != 3) return fail("usage: set_floating_shiftrange ireceiver min-shift max-shift");
+        return kiwi_set_floating_shiftrange(S.ctx, (int)v[0], v[1], v[2]) ? cfail() : true;
+    }
+    if (cmd == "get_misfits") {
+        const int nm = kiwi_get_nmisfits(S.ctx);
+        std::vector<float> m((size_t)2 * (nm > 0 ? nm : 1));
+        int n = 0;
+        if (kiwi_get_misfits(S.ctx, m.data(), nm, &n)) return cfail();
+        *answer = fmt_floats(m.data(), (size_t)2 * n);
+        return true;
+    }
+    if (cmd == "get_global_misfit") {
+        float g;
+        if (kiwi_get_global_misfit(S.ctx, &g)) return cfail();
+        *answer = fmt_floats(&g, 1);
+        return true;
+    }
+    if (cmd == "get_floating_shifts") {   // minimizer_engine.f90:1095-1128: seconds
+        std::vector<int> s(S.comps.size() + 1); int n = 0;
+        if (kiwi_get_floating_shifts(S.ctx, s.data(), (int)s.size(), &n)) return cfail();
+        std::vector<float> f(n);
+        for (int i = 0; i < n; i++) f[i] = (float)s[i] * S.dt;
+        *answer = fmt_floats(f.data(), f.size());
+        return true;
+    }
+    if (cmd == "output_seismograms") {   // minimizer_engine.f90:947-1012, `table` format, synthetics plain only
+        if (w.size() < 3) return fail("usage: output_seismograms filenamebase fileformat (synthetics|references) (plain|tapered|filtered)");
+        if (w[2] != "table") return fail("file format not available: " + w[2]);
+        if ((w.size() > 3 && w[3] != "synthetics") || (w.size() > 4 && w[4] != "plain")) return fail("only plain synthetics can be written by this front-end");
+        std::vector<float> buf(1 << 20);
+        for (size_t ir = 0; ir < S.comps.size(); ir++)
+            for (size_t ic = 0; ic < S.comps[ir].size(); ic++) {
+                int first = 0, n = 0;
+                if (kiwi_get_seismogram(S.ctx, (int)ir + 1, (int)ic + 1, 1, &first, &n, buf.data(), (int)buf.size())) return cfail();
+                const std::string fn = w[1] + "-" + std::to_string(ir + 1) + "-" + S.comps[ir][ic] + "." + w[2];
+                FILE* f = fopen(fn.c_str(), "w");
+                if (!f) return fail("can't open file: " + fn);
+                for (int i = 0; i < n; i++) fprintf(f, "%.9g %.9g\n", S.ref_time + (double)(first - 1 + i) * (double)S.dt, buf[i]);   // receiver.f90:649
+                fclose(f);
+            }
+        return true;
+    }
+    if (cmd == "eval_sources") {   // batched evaluation: one candidate per line of the file, answer = global misfits
+        if (w.size() != 3) return fail("usage: eval_sources source-type filename");
+        const int st = source_id(w[1]);
+        if (!st) return fail("unknown source type name: " + w[1]);
+        const int np = kiwi_get_n_source_params(st);
+        std::ifstream f(w[2]);
+        if (!f) return fail("can't open file: " + w[2]);
+        std::vector<float> params; std::string line;
+        while (std::getline(f, line)) {
+            std::vector<std::string> t = words(reduce_whitespace(line));
+            if (t.empty()) continue;
+            std::vector<float> p;
+            if (!to_floats(t, 0, &p) || (int)p.size() != np) return fail("failed to parse source params");
+            params.insert(params.end(), p.begin(), p.end());
+        }
+        const int ns = (int)(params.size() / (size_t)np), nm = kiwi_get_nmisfits(S.ctx);
+        std::vector<float> mis((size_t)ns * nm * 2 + 2), g(ns + 1);
+        std::vector<int> status(ns + 1);
+        if (kiwi_eval_sources(S.ctx, st, ns, np, params.data(), mis.data(), status.data())) return cfail();
+        kiwi_global_misfits(ns, nm, mis.data(), g.data());
+        *answer = fmt_floats(g.data(), ns);
+        return true;
+    }
+    return fail("unknown command: " + cmd);
+}
+
+}  // namespace
+
+int main() {
+    State S;
+    std::string line;
+    while (std::getline(std::cin, line)) {
+        const std::string args = reduce_whitespace(line);
+        if (args.empty()) continue;
+        const std::vector<std::string> w = words(args);
+        std::string answer, err;
+        const bool ok = do_command(S, w[0], w, &answer, &err);
+        if (ok) {
+            if (answer.empty()) printf("%s: ok\n", w[0].c_str());
+            else printf("%s: ok >\n%s\n", w[0].c_str(), answer.c_str());
+        } else {
+            if (err.empty()) printf("%s: nok\n", w[0].c_str());
+            else printf("%s: nok >\n%s\n", w[0].c_str(), err.c_str());
+        }
+        fflush(stdout);
+    }
+    if (S.ctx) kiwi_destroy(S.ctx);
+    if (S.db) kiwi_gfdb_destroy(S.db);
+    return 0;
+}

@@ -1,0 +1,91 @@
+"""The `minimizer`-compatible command front-end (kiwi_b200/kiwi_minimizer): reply format of
+minimizer.f90:1676-1701 and, on a GPU, a whole session held against the Python binding."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import scenario as sc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "kiwi_b200", "kiwi_minimizer")
+
+
+def talk(lines, env=None):
+    r = subprocess.run([BIN], input="\n".join(lines) + "\n", capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr
+    return r.stdout.splitlines()
+
+
+def test_reply_format_and_line_cleaning():
+    out = talk(["", "   # only a comment", "bogus_command 1 2   # trailing comment", "   frobnicate"])
+    # blank and comment-only lines produce no reply (minimizer.f90:1721-1725); unknown commands answer nok + message
+    assert out == ["bogus_command: nok >", "unknown command: bogus_command", "frobnicate: nok >", "unknown command: frobnicate"]
+
+
+def test_no_cpu_path_behind_the_protocol():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    out = talk(["set_effective_dt 0.5"])
+    assert out[0] == "set_effective_dt: nok >" and "no CUDA device" in out[1]
+
+
+@pytest.mark.gpu
+def test_session_matches_python_binding(tmp_path):
+    from kiwi_b200 import Engine
+    db = sc.small_db()
+    dbfile = tmp_path / "db.kgf1"
+    db.write(dbfile)
+    lat, lon, dep = sc.small_receivers(4)
+    comps = ["ned", "d", "ar", "neu"]
+    rfile = tmp_path / "receivers.table"
+    with open(rfile, "w") as f:
+        f.write("# lat lon depth components\n")
+        for a, b, c, d in zip(lat, lon, dep, comps):
+            f.write("%.10f %.10f %g %s\n" % (a, b, c, d))
+    p = " ".join("%.9g" % v for v in sc.BILAT_SMALL)
+    p2 = sc.BILAT_SMALL.copy(); p2[5] += 20
+    base = str(tmp_path / "ref")
+    cands = tmp_path / "cands.txt"
+    np.savetxt(cands, np.stack([sc.BILAT_SMALL, p2]), fmt="%.9g")
+    env = dict(os.environ, KIWI_CRUST2X2=os.path.join(ROOT, "kiwi_b200", "data", "crust2x2.kcr"))
+    out = talk(["set_database %s" % dbfile, "set_local_interpolation bilinear", "set_receivers %s has_depth" % rfile,
+                "set_source_location %g %g 0" % sc.ORIGIN, "set_effective_dt 0.2", "set_source_params bilateral " + p,
+                "get_misfits",                                   # no references yet
+                "output_seismograms %s table synthetics plain" % base, "set_ref_seismograms %s table" % base,
+                "set_misfit_method l1norm", "set_misfit_taper 1 1.0 0 1.6 1 4.0 1 5.2 0",
+                "set_source_params bilateral " + " ".join("%.9g" % v for v in p2), "get_misfits", "get_global_misfit",
+                "eval_sources bilateral %s" % cands, "switch_receiver 2 off", "get_misfits", "set_misfit_method nonsense"], env=env)
+    it = iter(out)
+    for _ in range(6):
+        assert next(it).endswith(": ok")
+    assert next(it) == "get_misfits: nok >" and next(it) == "no reference seismograms set"
+    for _ in range(5):
+        assert next(it).endswith(": ok")
+    assert next(it) == "get_misfits: ok >"
+    mis = np.array(next(it).split(), np.float32).reshape(-1, 2)
+    assert next(it) == "get_global_misfit: ok >"
+    gm = float(next(it))
+    assert next(it) == "eval_sources: ok >"
+    gms = np.array(next(it).split(), np.float32)
+    assert next(it) == "switch_receiver: ok"
+    assert next(it) == "get_misfits: ok >"
+    mis_off = np.array(next(it).split(), np.float32).reshape(-1, 2)
+    assert next(it) == "set_misfit_method: nok >" and next(it) == "unknown norm method: nonsense"
+    # the same through the Python binding: references = the table files the front-end wrote (text round trip)
+    e = Engine(0)
+    sc.setup(e, db, lat, lon, dep, comps)
+    for ir, c in enumerate(comps, 1):
+        for ic, ch in enumerate(c, 1):
+            t = np.loadtxt("%s-%d-%s.table" % (base, ir, ch))
+            e.set_ref_seismogram(ir, ic, np.float32(t[0, 0]), t[:, 1].astype(np.float32))
+    e.set_misfit_method("l1norm"); e.set_misfit_taper(1, [1.0, 1.6, 4.0, 5.2], [0, 1, 1, 0])
+    e.set_source_params("bilateral", p2)
+    want = e.get_misfits()
+    assert mis.shape == want.shape == (9, 2)
+    assert np.allclose(mis, want, rtol=1e-6, atol=0)
+    assert abs(gm - e.get_global_misfit()) <= 1e-6 * gm
+    assert abs(gms[1] - gm) <= 1e-6 * gm and gms[0] < 1e-3 * gm       # candidate 0 is the reference itself
+    assert mis_off.shape == (8, 2)

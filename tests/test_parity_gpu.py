@@ -342,13 +342,24 @@ def test_eikonal_discretisation_bit_exact(stype, params):
 
 @pytest.mark.parametrize("stype,params", [("eikonal", EIK), ("mt_eikonal", MTEIK)])
 def test_eikonal_seismograms_with_rise_time_fold(stype, params):
-    """synthesis + rise-time boxcar fold (receiver.f90:853-904, strip_fold) + moment scaling"""
+    """synthesis + rise-time boxcar fold (receiver.f90:853-904, strip_fold) + moment scaling.
+    strip_fold cuts the strip at strip_dataspan, whose end is "where the exactly constant tail begins"
+    (sparse_trace.f90:366-374).  In the reference that tail is only constant up to fp32 accumulation noise
+    (each tail sample sums the same end values in its own rounding), so where the *exactly* constant run
+    starts is decided by that noise: the folded strip may be a few samples longer or shorter.  The strips
+    are therefore compared on the union span with the continuation rule (last sample repeats); the
+    first sample index is exact."""
     g, o = engines(sc.small_db(), COMPS6)
     o.eval_sources(stype, params)
     g.set_source_params(stype, params)
     for ir in range(1, 7):
         for ic in range(1, len(COMPS6[ir - 1]) + 1):
-            assert_seis_close(g.get_seismogram(ir, ic, 1), o.get_seismogram(ir, ic, 1), "rcv %d comp %d" % (ir, ic))
+            (fg, dg), (fo, do) = g.get_seismogram(ir, ic, 1), o.get_seismogram(ir, ic, 1)
+            assert fg == fo and abs(dg.size - do.size) <= 8, (ir, ic, fg, fo, dg.size, do.size)
+            n = max(dg.size, do.size)
+            eg = np.concatenate([dg, np.full(n - dg.size, dg[-1], np.float32)])
+            eo = np.concatenate([do, np.full(n - do.size, do[-1], np.float32)])
+            assert np.abs(eg - eo).max() <= RTOL * np.abs(eo).max(), (ir, ic, np.abs(eg - eo).max() / np.abs(eo).max())
 
 
 @pytest.mark.parametrize("norm", ["l2norm", "ampspec_l1norm"])
