@@ -379,173 +379,230 @@ __device__ __forceinline__ void tap_strips(float4* a1, float4* a2, float4* a3, c
     if (V) { float4 o = *a3; tap_quad<S>(o, P3, A3, wl, wr); *a3 = o; }
 }
 
-// asynchronous copy of one 128-byte group record into shared memory (lanes 0..7, 16 bytes each)
-__device__ __forceinline__ void rec_prefetch(const GeoRec* __restrict__ recs, int ip, int ngroups, GeoRec* dst_slot, int lane) {
-    if (ip < ngroups && lane < 8) {
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(reinterpret_cast<uint4*>(dst_slot) + lane);
-        const uint4* src = reinterpret_cast<const uint4*>(recs + ip) + lane;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+// ---- asynchronous staging (cp.async): group records and GF quads travel HBM -> shared memory without
+// passing through registers, so a warp keeps SYN_STAGES x 4 128-bit loads in flight also while it is
+// busy with the tap phase of the previous chunk -------------------------------------------------------------
+#define SYN_STAGES 3      // ring depth per warp: items (one GF component x four corners) in flight
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// copy of one 128-byte group record (lanes 0..7, 16 bytes each); not committed here
+__device__ __forceinline__ void rec_copy_async(const GeoRec* __restrict__ recs, int ip, int ngroups, GeoRec* dst_slot, int lane) {
+    if (ip < ngroups && lane < 8) cp_async16(reinterpret_cast<uint4*>(dst_slot) + lane, reinterpret_cast<const uint4*>(recs + ip) + lane);
 }
 
-// One warp, one group.  H/V: the receiver has horizontal / vertical components.
-template <bool H, bool V>
-__device__ __forceinline__ void synth_group(const GfdbDev& db, const GeoRec& rec, const GroupSoA& g, const TapSoA& taps, int gi,
-                                            bool ng10, float sd, float4* __restrict__ acc, float* __restrict__ step, int nq,
-                                            int baseq, int lane) {
-    const float dt = db.dt;
-    // ---- corners (gfdb.f90:943-948 weights in the reference's association) -------------------------
-    const bool single = rec.flags & GEO_SINGLE;
-    const float dix = rec.dix, diz = rec.diz;
-    const float wc0 = single ? 1.f : (1.f - dix) * (1.f - diz), wc1 = single ? 0.f : (1.f - dix) * diz,
-                wc2 = single ? 0.f : dix * (1.f - diz), wc3 = single ? 0.f : dix * diz;
-    const NodeInfo n0 = rec.node[0], n1 = rec.node[1], n2 = rec.node[2], n3 = rec.node[3];
-    const float4* b0 = reinterpret_cast<const float4*>(db.slabs + n0.off);
-    const float4* b1 = reinterpret_cast<const float4*>(db.slabs + n1.off);
-    const float4* b2 = reinterpret_cast<const float4*>(db.slabs + n2.off);
-    const float4* b3 = reinterpret_cast<const float4*>(db.slabs + n3.off);
-    const int w0q0 = n0.w0 >> 2, w0q1 = n1.w0 >> 2, w0q2 = n2.w0 >> 2, w0q3 = n3.w0 >> 2;     // first quad of each window
-    const int nq0 = n0.wn >> 2, nq1 = n1.wn >> 2, nq2 = n2.wn >> 2, nq3 = n3.wn >> 2;          // quads per row
-    const int q_first = min(min(w0q0, w0q1), min(w0q2, w0q3));
-    // last quad of the longest window: continuation only, for every corner
-    const int q_last = max(max(w0q0 + nq0, w0q1 + nq1), max(w0q2 + nq2, w0q3 + nq3)) - 1;
-    // ---- taps: lane k prepares tap k (sparse_trace.f90:639-646) ---------------------------------------
-    const int tb = g.tap_begin[gi], tn = min(g.tap_count[gi], SYN_MAXTAPS);
-    int my_its = 0; float my_wl = 0.f, my_wr = 0.f;
-    if (lane < tn) {
-        const float time = A_(g.tbase[gi], taps.toff[tb + lane]);
-        const float rshift = D_(time, dt);
-        my_its = (int)floorf(rshift);
-        const float wr0 = S_(rshift, (float)my_its);
-        const float wl0 = S_(1.f, wr0);
-        const float wt = taps.wt[tb + lane];
-        my_wr = M_(wr0, wt); my_wl = M_(wl0, wt);
-    }
-    const float f1 = rec.f[0], f2 = rec.f[1], f3 = rec.f[2], f4 = rec.f[3], f5 = rec.f[4], f6 = rec.f[5];
-    const float cl = rec.cl, sl = rec.sl;
-    const float v1 = f1 * sd, v2 = f2 * sd, v3 = f3 * sd, v6 = f6 * sd;
+// GF components a receiver with horizontal (H) / vertical (V) components needs, in the reference's order of
+// accumulation (seismogram.f90:167-250): g1 g2 g3 (g9) -> radial, g4 g5 -> transverse, g6 g7 g8 (g10) -> vertical
+template <bool H, bool V, bool NG10>
+struct CompSeq {
+    static constexpr int N = (H && V) ? (NG10 ? 10 : 8) : (H ? (NG10 ? 6 : 5) : (NG10 ? 4 : 3));
+    __host__ __device__ static constexpr int comp(int j) { return (H && V) ? j : (H ? (j < 5 ? j : 8) : (j < 3 ? 5 + j : 9)); }
+};
 
-    float4 carry1 = f4zero(), carry2 = f4zero(), carry3 = f4zero();   // quad left of the chunk (zeros left of the windows)
-    for (int q0 = q_first; q0 <= q_last; q0 += 32) {
-        const int q = q0 + lane;
-        const bool active = q <= q_last;
-        float4 A1 = f4zero(), A2 = f4zero(), A3 = f4zero();
-        if (active) {
-            // per corner: row pointer of component 1 at this lane's quad (clamped into the window: the
-            // last quad is the continuation; left of the window the weight is zero)
-            const int o0 = q - w0q0, o1 = q - w0q1, o2 = q - w0q2, o3 = q - w0q3;
-            const float4* p0 = b0 + min(max(o0, 0), nq0 - 1);
-            const float4* p1 = b1 + min(max(o1, 0), nq1 - 1);
-            const float4* p2 = b2 + min(max(o2, 0), nq2 - 1);
-            const float4* p3 = b3 + min(max(o3, 0), nq3 - 1);
-            const float c0 = o0 < 0 ? 0.f : wc0, c1 = o1 < 0 ? 0.f : wc1, c2 = o2 < 0 ? 0.f : wc2, c3 = o3 < 0 ? 0.f : wc3;
-            // software pipeline over the GF components: the four corner quads of component i+2 are in
-            // flight while component i is combined (keeps ~12 128-bit loads per lane outstanding)
-            // running row pointers: KIWI_LOAD fetches the current component's four corner quads and
-            // steps to the next component's rows
-#define KIWI_LOAD(buf) { buf[0] = __ldg(r0); buf[1] = __ldg(r1); buf[2] = __ldg(r2); buf[3] = __ldg(r3); r0 += nq0; r1 += nq1; r2 += nq2; r3 += nq3; }
-#define KIWI_SKIP(n) { r0 += (n) * nq0; r1 += (n) * nq1; r2 += (n) * nq2; r3 += (n) * nq3; }
-#define KIWI_COMB(buf, dst, wgt) { float4 r = f4zero(); fma4(r, c0, buf[0]); fma4(r, c1, buf[1]); fma4(r, c2, buf[2]); fma4(r, c3, buf[3]); fma4(dst, wgt, r); }
-            const float4 *r0 = p0, *r1 = p1, *r2 = p2, *r3 = p3;
-            float4 ta[4], tb[4], tc[4];
-            if (H && V) {
-                float4 Rr = f4zero(), Tt = f4zero();
-                KIWI_LOAD(ta) KIWI_LOAD(tb) KIWI_LOAD(tc)                 // g1 g2 g3
-                KIWI_COMB(ta, Rr, f1) KIWI_LOAD(ta)                       // g4
-                KIWI_COMB(tb, Rr, f2) KIWI_LOAD(tb)                       // g5
-                KIWI_COMB(tc, Rr, f3) KIWI_LOAD(tc)                       // g6
-                KIWI_COMB(ta, Tt, f4) KIWI_LOAD(ta)                       // g7
-                KIWI_COMB(tb, Tt, f5) KIWI_LOAD(tb)                       // g8
-                KIWI_COMB(tc, A3, v1)
-                if (ng10) {
-                    KIWI_LOAD(tc)                                         // g9
-                    KIWI_COMB(ta, A3, v2) KIWI_LOAD(ta)                   // g10
-                    KIWI_COMB(tb, A3, v3)
-                    KIWI_COMB(tc, Rr, f6)
-                    KIWI_COMB(ta, A3, v6)
-                } else {
-                    KIWI_COMB(ta, A3, v2)
-                    KIWI_COMB(tb, A3, v3)
-                }
-                // seismogram.f90:200-203: ar1 += cl*temp1 - sl*temp2; ar2 += cl*temp2 + sl*temp1
-                fma4(A1, cl, Rr); fma4(A1, -sl, Tt);
-                fma4(A2, cl, Tt); fma4(A2, sl, Rr);
-            } else if (H) {
-                float4 Rr = f4zero(), Tt = f4zero();
-                KIWI_LOAD(ta) KIWI_LOAD(tb) KIWI_LOAD(tc)                 // g1 g2 g3
-                KIWI_COMB(ta, Rr, f1) KIWI_LOAD(ta)                       // g4
-                KIWI_COMB(tb, Rr, f2) KIWI_LOAD(tb)                       // g5
-                KIWI_COMB(tc, Rr, f3)
-                if (ng10) { KIWI_SKIP(3) KIWI_LOAD(tc) }                  // g9
-                KIWI_COMB(ta, Tt, f4)
-                KIWI_COMB(tb, Tt, f5)
-                if (ng10) { KIWI_COMB(tc, Rr, f6) }
-                fma4(A1, cl, Rr); fma4(A1, -sl, Tt);
-                fma4(A2, cl, Tt); fma4(A2, sl, Rr);
-            } else {
-                KIWI_SKIP(5)
-                KIWI_LOAD(ta) KIWI_LOAD(tb) KIWI_LOAD(tc)                 // g6 g7 g8
-                KIWI_COMB(ta, A3, v1)
-                if (ng10) { KIWI_SKIP(1) KIWI_LOAD(ta) }                  // g10
-                KIWI_COMB(tb, A3, v2)
-                KIWI_COMB(tc, A3, v3)
-                if (ng10) { KIWI_COMB(ta, A3, v6) }
+// where a lane reads one chunk from: row pointers of GF component 1 at the lane's quad for the four
+// corners (clamped into each window: the last quad is the continuation), row strides in quads
+struct ChunkSrc {
+    const float4 *r0, *r1, *r2, *r3;
+    int s0, s1, s2, s3;
+    bool active;
+};
+__device__ __forceinline__ ChunkSrc chunk_src(const float* slabs, const NodeInfo& n0, const NodeInfo& n1, const NodeInfo& n2, const NodeInfo& n3,
+                                              int q, int q_last) {
+    ChunkSrc c;
+    c.s0 = n0.wn >> 2; c.s1 = n1.wn >> 2; c.s2 = n2.wn >> 2; c.s3 = n3.wn >> 2;
+    c.r0 = reinterpret_cast<const float4*>(slabs + n0.off) + min(max(q - (n0.w0 >> 2), 0), c.s0 - 1);
+    c.r1 = reinterpret_cast<const float4*>(slabs + n1.off) + min(max(q - (n1.w0 >> 2), 0), c.s1 - 1);
+    c.r2 = reinterpret_cast<const float4*>(slabs + n2.off) + min(max(q - (n2.w0 >> 2), 0), c.s2 - 1);
+    c.r3 = reinterpret_cast<const float4*>(slabs + n3.off) + min(max(q - (n3.w0 >> 2), 0), c.s3 - 1);
+    c.active = q <= q_last;
+    return c;
+}
+__device__ __forceinline__ void window_quads(const NodeInfo& n0, const NodeInfo& n1, const NodeInfo& n2, const NodeInfo& n3, int& q_first,
+                                             int& q_last) {
+    q_first = min(min(n0.w0, n1.w0), min(n2.w0, n3.w0)) >> 2;
+    // last quad of the longest window: continuation only, for every corner
+    q_last = (max(max(n0.w0 + n0.wn, n1.w0 + n1.wn), max(n2.w0 + n2.wn, n3.w0 + n3.wn)) >> 2) - 1;
+}
+// one item = GF component `comp` of the chunk -> ring slot `stage` (4 corners x 32 lanes x 16 bytes)
+__device__ __forceinline__ void issue_item(const ChunkSrc& c, int comp, float4* ring, int stage, int lane) {
+    if (c.active) {
+        float4* dst = ring + (stage * 4) * 32 + lane;
+        cp_async16(dst, c.r0 + comp * c.s0);
+        cp_async16(dst + 32, c.r1 + comp * c.s1);
+        cp_async16(dst + 64, c.r2 + comp * c.s2);
+        cp_async16(dst + 96, c.r3 + comp * c.s3);
+    }
+}
+
+// One warp works through its share of the groups of one (candidate, receiver) pair.
+template <bool H, bool V, bool NG10>
+__device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __restrict__ myrecs, int ngroups, int group_begin,
+                                           const GroupSoA& g, const TapSoA& taps, float sd, float4* __restrict__ acc,
+                                           float* __restrict__ step, int nq, int baseq, GeoRec* slot /* [3] */, float4* ring, int warp,
+                                           int nwarps, int lane) {
+    typedef CompSeq<H, V, NG10> Seq;
+    constexpr int N = Seq::N, S = SYN_STAGES;
+    static_assert(N >= S, "ring deeper than the component list");
+    const float dt = db.dt;
+    // records of the first two groups synchronously; from then on two groups ahead
+    rec_copy_async(myrecs, warp, ngroups, slot, lane);
+    rec_copy_async(myrecs, warp + nwarps, ngroups, slot + 1, lane);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    int stage = 0;          // ring slot of the next item to consume
+    bool primed = false;    // the first S items of the chunk about to be processed are already in flight
+    int sl = 0;             // slot of the current group's record
+    for (int ip = warp; ip < ngroups; ip += nwarps, sl = (sl + 1) % 3) {
+        // record of the group after next; rides in the next commit group
+        rec_copy_async(myrecs, ip + 2 * nwarps, ngroups, slot + (sl + 2) % 3, lane);
+        const GeoRec& rec = slot[sl];
+        if (rec.flags & GEO_SKIP) {   // (never primed: the look-ahead does not cross skipped groups)
+            cp_async_commit(); cp_async_wait<0>(); __syncwarp();   // rare path: make sure the records fetched ahead have landed
+            continue;
+        }
+        const int gi = group_begin + ip;
+        // ---- corners (gfdb.f90:943-948 weights in the reference's association) -------------------------
+        const bool single = rec.flags & GEO_SINGLE;
+        const float dix = rec.dix, diz = rec.diz;
+        const float wc0 = single ? 1.f : (1.f - dix) * (1.f - diz), wc1 = single ? 0.f : (1.f - dix) * diz,
+                    wc2 = single ? 0.f : dix * (1.f - diz), wc3 = single ? 0.f : dix * diz;
+        const NodeInfo n0 = rec.node[0], n1 = rec.node[1], n2 = rec.node[2], n3 = rec.node[3];
+        int q_first, q_last;
+        window_quads(n0, n1, n2, n3, q_first, q_last);
+        // next group of this warp (for the look-ahead at the end of this group's last chunk)
+        const GeoRec& nrec = slot[(sl + 1) % 3];
+        const bool next_ok = (ip + nwarps < ngroups) && !(nrec.flags & GEO_SKIP);
+        // ---- taps: lane k prepares tap k (sparse_trace.f90:639-646) ---------------------------------------
+        const int tb = g.tap_begin[gi], tn = min(g.tap_count[gi], SYN_MAXTAPS);
+        int my_its = 0; float my_wl = 0.f, my_wr = 0.f;
+        if (lane < tn) {
+            const float time = A_(g.tbase[gi], taps.toff[tb + lane]);
+            const float rshift = D_(time, dt);
+            my_its = (int)floorf(rshift);
+            const float wr0 = S_(rshift, (float)my_its);
+            const float wl0 = S_(1.f, wr0);
+            const float wt = taps.wt[tb + lane];
+            my_wr = M_(wr0, wt); my_wl = M_(wl0, wt);
+        }
+        const float f1 = rec.f[0], f2 = rec.f[1], f3 = rec.f[2], f4 = rec.f[3], f5 = rec.f[4], f6 = rec.f[5];
+        const float cl = rec.cl, sl_ = rec.sl;
+
+        float4 carry1 = f4zero(), carry2 = f4zero(), carry3 = f4zero();   // quad left of the chunk (zeros left of the windows)
+        for (int q0 = q_first; q0 <= q_last; q0 += 32) {
+            const int q = q0 + lane;
+            const ChunkSrc cur = chunk_src(db.slabs, n0, n1, n2, n3, q, q_last);
+            const bool active = cur.active;
+            if (!primed) {   // pipeline (re)start: first S items of this chunk
+#pragma unroll
+                for (int j = 0; j < S; j++) { issue_item(cur, Seq::comp(j), ring, (stage + j) % S, lane); cp_async_commit(); }
             }
-#undef KIWI_LOAD
-#undef KIWI_SKIP
-#undef KIWI_COMB
-        }
-        // previous quad: lane-1; lane 0 takes the carry of the previous chunk
-        float4 P1, P2, P3;
-        if (H) { P1 = shfl_up4(A1, 1); P2 = shfl_up4(A2, 1); if (lane == 0) { P1 = carry1; P2 = carry2; } }
-        if (V) { P3 = shfl_up4(A3, 1); if (lane == 0) P3 = carry3; }
-        const bool more = q0 + 32 <= q_last;
-        if (more) {
-            if (H) { carry1 = shfl4(A1, 31); carry2 = shfl4(A2, 31); }
-            if (V) carry3 = shfl4(A3, 31);
-        }
-        for (int k = 0; k < tn; k++) {
-            const int its = __shfl_sync(0xffffffffu, my_its, k);
-            const float wl = __shfl_sync(0xffffffffu, my_wl, k), wr = __shfl_sync(0xffffffffu, my_wr, k);
-            const int qrel = q + (its >> 2) - baseq;
-            if (active && qrel >= 0 && qrel < nq) {
-                float4* a1 = acc + qrel; float4* a2 = a1 + nq; float4* a3 = a2 + nq;
-                switch (its & 3) {
-                    case 0: tap_strips<0, H, V>(a1, a2, a3, P1, A1, P2, A2, P3, A3, wl, wr); break;
-                    case 1: tap_strips<1, H, V>(a1, a2, a3, P1, A1, P2, A2, P3, A3, wl, wr); break;
-                    case 2: tap_strips<2, H, V>(a1, a2, a3, P1, A1, P2, A2, P3, A3, wl, wr); break;
-                    default: tap_strips<3, H, V>(a1, a2, a3, P1, A1, P2, A2, P3, A3, wl, wr); break;
+            const bool more = q0 + 32 <= q_last;
+            const bool have_next = more || next_ok;
+            ChunkSrc nxt = cur;
+            // left of a corner's window the trace is zero
+            const float c0 = q < (n0.w0 >> 2) ? 0.f : wc0, c1 = q < (n1.w0 >> 2) ? 0.f : wc1, c2 = q < (n2.w0 >> 2) ? 0.f : wc2,
+                        c3 = q < (n3.w0 >> 2) ? 0.f : wc3;
+            float4 A1 = f4zero(), A2 = f4zero(), A3 = f4zero(), Rr = f4zero(), Tt = f4zero();
+#pragma unroll
+            for (int j = 0; j < N; j++) {
+                cp_async_wait<S - 1>();    // item j has landed (this lane's own copies; no other lane reads them)
+                if (active) {
+                    const float4* src = ring + (stage * 4) * 32 + lane;
+                    const float4 t0 = src[0], t1 = src[32], t2 = src[64], t3 = src[96];
+                    float4 r = f4zero();
+                    fma4(r, c0, t0); fma4(r, c1, t1); fma4(r, c2, t2); fma4(r, c3, t3);
+                    const int k = Seq::comp(j);   // constant after unrolling
+                    if (k == 0) fma4(Rr, f1, r);
+                    else if (k == 1) fma4(Rr, f2, r);
+                    else if (k == 2) fma4(Rr, f3, r);
+                    else if (k == 3) fma4(Tt, f4, r);
+                    else if (k == 4) fma4(Tt, f5, r);
+                    else if (k == 5) fma4(A3, f1 * sd, r);
+                    else if (k == 6) fma4(A3, f2 * sd, r);
+                    else if (k == 7) fma4(A3, f3 * sd, r);
+                    else if (k == 8) fma4(Rr, f6, r);
+                    else fma4(A3, f6 * sd, r);
                 }
+                // refill the slot just consumed: a later item of this chunk, or the first items of the next chunk
+                if (j + S < N) issue_item(cur, Seq::comp(j + S), ring, stage, lane);
+                else if (have_next) {
+                    const int jj = j + S - N;     // constant after unrolling
+                    if (jj == 0) {
+                        if (more) nxt = chunk_src(db.slabs, n0, n1, n2, n3, q + 32, q_last);
+                        else {
+                            const NodeInfo m0 = nrec.node[0], m1 = nrec.node[1], m2 = nrec.node[2], m3 = nrec.node[3];
+                            int qf, ql;
+                            window_quads(m0, m1, m2, m3, qf, ql);
+                            nxt = chunk_src(db.slabs, m0, m1, m2, m3, qf + lane, ql);
+                        }
+                    }
+                    issue_item(nxt, Seq::comp(jj), ring, stage, lane);
+                }
+                cp_async_commit();
+                stage = (stage + 1) % S;
             }
-            __syncwarp();
-        }
-        if (!more) {
-            // ---- end-value repetition (sparse_trace.f90:696-703): every sample right of the last
-            // processed quad gets (wl+wr)*A_end; recorded as a step at quad q_last+1+shift, prefix-summed
-            // at the end.  Lane c owns strip c: fixed order over the taps, no two lanes share a word.
-            const int src = q_last - q0;
-            const float e1 = H ? __shfl_sync(0xffffffffu, A1.w, src) : 0.f;
-            const float e2 = H ? __shfl_sync(0xffffffffu, A2.w, src) : 0.f;
-            const float e3 = V ? __shfl_sync(0xffffffffu, A3.w, src) : 0.f;
-            const float ae = lane == 0 ? e1 : (lane == 1 ? e2 : e3);
-            const bool mine = lane < 3 && (lane < 2 ? H : V);
+            primed = have_next;
+            if (H) {   // seismogram.f90:200-203: ar1 += cl*temp1 - sl*temp2; ar2 += cl*temp2 + sl*temp1
+                fma4(A1, cl, Rr); fma4(A1, -sl_, Tt);
+                fma4(A2, cl, Tt); fma4(A2, sl_, Rr);
+            }
+            // previous quad: lane-1; lane 0 takes the carry of the previous chunk
+            float4 P1, P2, P3;
+            if (H) { P1 = shfl_up4(A1, 1); P2 = shfl_up4(A2, 1); if (lane == 0) { P1 = carry1; P2 = carry2; } }
+            if (V) { P3 = shfl_up4(A3, 1); if (lane == 0) P3 = carry3; }
+            if (more) {
+                if (H) { carry1 = shfl4(A1, 31); carry2 = shfl4(A2, 31); }
+                if (V) carry3 = shfl4(A3, 31);
+            }
             for (int k = 0; k < tn; k++) {
                 const int its = __shfl_sync(0xffffffffu, my_its, k);
-                const float w = __shfl_sync(0xffffffffu, my_wl, k) + __shfl_sync(0xffffffffu, my_wr, k);
-                const int qs = q_last + 1 + (its >> 2) - baseq;
-                if (mine && qs >= 0 && qs < nq) step[lane * nq + qs] += w * ae;
+                const float wl = __shfl_sync(0xffffffffu, my_wl, k), wr = __shfl_sync(0xffffffffu, my_wr, k);
+                const int qrel = q + (its >> 2) - baseq;
+                if (active && qrel >= 0 && qrel < nq) {
+                    float4* a1 = acc + qrel; float4* a2 = a1 + nq; float4* a3 = a2 + nq;
+                    switch (its & 3) {
+                        case 0: tap_strips<0, H, V>(a1, a2, a3, P1, A1, P2, A2, P3, A3, wl, wr); break;
+                        case 1: tap_strips<1, H, V>(a1, a2, a3, P1, A1, P2, A2, P3, A3, wl, wr); break;
+                        case 2: tap_strips<2, H, V>(a1, a2, a3, P1, A1, P2, A2, P3, A3, wl, wr); break;
+                        default: tap_strips<3, H, V>(a1, a2, a3, P1, A1, P2, A2, P3, A3, wl, wr); break;
+                    }
+                }
+                __syncwarp();
+            }
+            if (!more) {
+                // ---- end-value repetition (sparse_trace.f90:696-703): every sample right of the last
+                // processed quad gets (wl+wr)*A_end; recorded as a step at quad q_last+1+shift, prefix-summed
+                // at the end.  Lane c owns strip c: fixed order over the taps, no two lanes share a word.
+                const int src = q_last - q0;
+                const float e1 = H ? __shfl_sync(0xffffffffu, A1.w, src) : 0.f;
+                const float e2 = H ? __shfl_sync(0xffffffffu, A2.w, src) : 0.f;
+                const float e3 = V ? __shfl_sync(0xffffffffu, A3.w, src) : 0.f;
+                const float ae = lane == 0 ? e1 : (lane == 1 ? e2 : e3);
+                const bool mine = lane < 3 && (lane < 2 ? H : V);
+                for (int k = 0; k < tn; k++) {
+                    const int its = __shfl_sync(0xffffffffu, my_its, k);
+                    const float w = __shfl_sync(0xffffffffu, my_wl, k) + __shfl_sync(0xffffffffu, my_wr, k);
+                    const int qs = q_last + 1 + (its >> 2) - baseq;
+                    if (mine && qs >= 0 && qs < nq) step[lane * nq + qs] += w * ae;
+                }
             }
         }
+        __syncwarp();
     }
-    __syncwarp();
+    cp_async_wait<0>();
 }
 
 // =================================================================================================
 // K3: synthesis.  One CTA per (candidate, receiver); every warp owns a private set of three
 // accumulator strips (displacement_ar(1), displacement_ar(2), vertical) in shared memory and works
 // through its share of the groups.  Per group and 128-sample chunk a lane owns one aligned sample
-// quad: 4 corners x ng rows are fetched with coalesced 128-bit loads from the HBM slabs, combined
+// quad: 4 corners x ng rows are staged HBM -> shared memory with 128-bit cp.async copies (a ring of
+// SYN_STAGES components per warp that keeps running across chunk and group boundaries), combined
 // bilinearly (gfdb.f90:943-948), weighted with the moment-tensor/azimuth factors (make_weights
 // seismogram.f90:316-336, precomputed by k_geometry), rotated by the centroid's back-azimuth
 // difference (:196-203), and then added nt times with the sample shift and linear sub-sample
@@ -573,7 +630,7 @@ __global__ void __launch_bounds__(256, 2) k_synth(GfdbDev db, const ReceiverDev*
     const int base = floor4(H.out0) - 4 * margin_q;   // room on the left for the rise-time fold (k_fold)
     const int baseq = base >> 2;
     const int nq = nq_alloc;   // quads per accumulator strip
-    // shared memory: per warp 3 strips of nq float4 + 3 step rows of nq floats
+    // shared memory: per warp 3 strips of nq float4 + 3 step rows of nq floats, 3 group records, the cp.async ring
     float4* acc_all = reinterpret_cast<float4*>(smem_raw);
     float* step_all = reinterpret_cast<float*>(acc_all + (size_t)nwarps * 3 * nq);
     float4* acc = acc_all + (size_t)warp * 3 * nq;
@@ -586,23 +643,17 @@ __global__ void __launch_bounds__(256, 2) k_synth(GfdbDev db, const ReceiverDev*
     const bool ng10 = db.ng == 10;
     const GeoRec* myrecs = recs + (size_t)pair * rec_stride;
     (void)ngroups_total; (void)interpolate; (void)xunder; (void)zunder;
+    // 16-byte aligned carve-up behind the step rows (3*nq floats per warp may end on an 8-byte boundary)
+    unsigned char* tail = reinterpret_cast<unsigned char*>(step_all + (size_t)nwarps * 3 * nq);
+    tail += (16 - (reinterpret_cast<size_t>(tail) & 15)) & 15;
+    GeoRec* slot = reinterpret_cast<GeoRec*>(tail) + 3 * warp;
+    float4* ring = reinterpret_cast<float4*>(reinterpret_cast<GeoRec*>(tail) + 3 * nwarps) + (size_t)warp * SYN_STAGES * 4 * 32;
 
-    // the 128-byte group records are prefetched one group ahead into a per-warp shared-memory slot with
-    // cp.async, so that the data loads of a group can start as soon as the previous group is done
-    GeoRec* slot = reinterpret_cast<GeoRec*>(step_all + (size_t)nwarps * 3 * nq) + 2 * warp;
-    rec_prefetch(myrecs, warp, cand.ngroups, slot, lane);
-    int buf = 0;
-    for (int ip = warp; ip < cand.ngroups; ip += nwarps, buf ^= 1) {
-        rec_prefetch(myrecs, ip + nwarps, cand.ngroups, slot + (buf ^ 1), lane);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        __syncwarp();
-        const GeoRec& rec = slot[buf];   // read field by field from shared memory (stays valid: the next prefetch fills the other slot)
-        if (rec.flags & GEO_SKIP) continue;
-        const int gi = cand.group_begin + ip;
-        if (need_h && need_v) synth_group<true, true>(db, rec, g, taps, gi, ng10, R.sd, acc, step, nq, baseq, lane);
-        else if (need_h) synth_group<true, false>(db, rec, g, taps, gi, ng10, R.sd, acc, step, nq, baseq, lane);
-        else if (need_v) synth_group<false, true>(db, rec, g, taps, gi, ng10, R.sd, acc, step, nq, baseq, lane);
-    }
+#define KIWI_SYNTH(HH, VV, NG) synth_warp<HH, VV, NG>(db, myrecs, cand.ngroups, cand.group_begin, g, taps, R.sd, acc, step, nq, baseq, slot, ring, warp, nwarps, lane)
+    if (need_h && need_v) { if (ng10) KIWI_SYNTH(true, true, true); else KIWI_SYNTH(true, true, false); }
+    else if (need_h) { if (ng10) KIWI_SYNTH(true, false, true); else KIWI_SYNTH(true, false, false); }
+    else if (need_v) { if (ng10) KIWI_SYNTH(false, true, true); else KIWI_SYNTH(false, true, false); }
+#undef KIWI_SYNTH
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     // ---- reduce the warps' strips (fixed order: deterministic) -------------------------------------
@@ -1375,7 +1426,10 @@ void launch_geometry(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev
                      int interpolate, int xunder, int zunder, GeoRec* recs, size_t rec_stride, PairHdr* hdrs, int* tmax, cudaStream_t st) {
     k_geometry<<<ncand * nrcv, 256, 0, st>>>(db, rcv, nrcv, cands, g, ngroups_total, interpolate, xunder, zunder, recs, rec_stride, hdrs, tmax);
 }
-size_t synth_smem_bytes(int nwarps, int nq) { return (size_t)nwarps * 3 * nq * (sizeof(float4) + sizeof(float)) + (size_t)nwarps * 2 * sizeof(GeoRec); }
+size_t synth_smem_bytes(int nwarps, int nq) {
+    return (size_t)nwarps * 3 * nq * (sizeof(float4) + sizeof(float)) + 16 + (size_t)nwarps * 3 * sizeof(GeoRec) +
+           (size_t)nwarps * SYN_STAGES * 4 * 32 * sizeof(float4);
+}
 cudaError_t launch_synth(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, TapSoA taps,
                          int ngroups_total, int interpolate, int xunder, int zunder, const GeoRec* recs, size_t rec_stride,
                          const PairHdr* hdrs, int nq_alloc, int margin_q, int nwarps, float* seis, size_t seis_stride, SeisHdr* shdrs,
