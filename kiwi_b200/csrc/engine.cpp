@@ -711,7 +711,7 @@ int kiwi_set_database(kiwi_ctx* c, kiwi_gfdb* db) {
         }
         NodeInfo& ni = c->h_nodes[inode];
         if (!all) { ni.off = ~0ull; ni.w0 = 0; ni.wn = 0; continue; }   // node unusable: the centroid is skipped (seismogram.f90:172)
-        const int w0 = (int)(floor((double)lo / 4.0)) * 4;
+        const int w0 = (int)(floor((double)lo / 4.0)) * 4 - 4;             // first quad = zeros only (left continuation)
         const int wend = (int)(floor((double)hi / 4.0)) * 4 + 8;      // exclusive, multiple of 4; last quad = continuation only
         ni.off = total; ni.w0 = w0; ni.wn = wend - w0;
         total += (unsigned long long)ni.wn * ng;

@@ -13,6 +13,7 @@
 #include "kernels.cuh"
 #include <cfloat>
 #include <climits>
+#include <cstdlib>
 
 // ---- exactly-rounded fp32 helpers: never contracted into FMA by ptxas -------------------------
 __device__ __forceinline__ float A_(float a, float b) { return __fadd_rn(a, b); }
@@ -423,7 +424,8 @@ __device__ __forceinline__ ChunkSrc chunk_src(const float* slabs, const NodeInfo
 }
 __device__ __forceinline__ void window_quads(const NodeInfo& n0, const NodeInfo& n1, const NodeInfo& n2, const NodeInfo& n3, int& q_first,
                                              int& q_last) {
-    q_first = min(min(n0.w0, n1.w0), min(n2.w0, n3.w0)) >> 2;
+    // every window starts with one quad of zeros (left continuation): the earliest window's zero quad need not be read
+    q_first = (min(min(n0.w0, n1.w0), min(n2.w0, n3.w0)) >> 2) + 1;
     // last quad of the longest window: continuation only, for every corner
     q_last = (max(max(n0.w0 + n0.wn, n1.w0 + n1.wn), max(n2.w0 + n2.wn, n3.w0 + n3.wn)) >> 2) - 1;
 }
@@ -439,13 +441,16 @@ __device__ __forceinline__ void issue_item(const ChunkSrc& c, int comp, float4* 
 }
 
 // One warp works through its share of the groups of one (candidate, receiver) pair.
-template <bool H, bool V, bool NG10>
+template <bool H, bool V, bool NG10, bool PAD>
 __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __restrict__ myrecs, int ngroups, int group_begin,
                                            const GroupSoA& g, const TapSoA& taps, float sd, float4* __restrict__ acc,
                                            float* __restrict__ step, int nq, int baseq, GeoRec* slot /* [3] */, float4* ring, int warp,
                                            int nwarps, int lane) {
     typedef CompSeq<H, V, NG10> Seq;
     constexpr int N = Seq::N, S = SYN_STAGES;
+    // PAD: items per chunk padded with empty commit groups to a multiple of S, so that the slot of item j is the
+    // compile-time constant j % S; otherwise the slot index rotates at run time
+    constexpr int NP = PAD ? (N + S - 1) / S * S : N;
     static_assert(N >= S, "ring deeper than the component list");
     const float dt = db.dt;
     // records of the first two groups synchronously; from then on two groups ahead
@@ -454,8 +459,8 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
     cp_async_commit();
     cp_async_wait<0>();
     __syncwarp();
-    int stage = 0;          // ring slot of the next item to consume
     bool primed = false;    // the first S items of the chunk about to be processed are already in flight
+    int stage0 = 0;         // ring slot of item 0 of the current chunk (always 0 with PAD)
     int sl = 0;             // slot of the current group's record
     for (int ip = warp; ip < ngroups; ip += nwarps, sl = (sl + 1) % 3) {
         // record of the group after next; rides in the next commit group
@@ -499,23 +504,21 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
             const bool active = cur.active;
             if (!primed) {   // pipeline (re)start: first S items of this chunk
 #pragma unroll
-                for (int j = 0; j < S; j++) { issue_item(cur, Seq::comp(j), ring, (stage + j) % S, lane); cp_async_commit(); }
+                for (int j = 0; j < S; j++) { issue_item(cur, Seq::comp(j), ring, (stage0 + j) % S, lane); cp_async_commit(); }
             }
             const bool more = q0 + 32 <= q_last;
             const bool have_next = more || next_ok;
             ChunkSrc nxt = cur;
-            // left of a corner's window the trace is zero
-            const float c0 = q < (n0.w0 >> 2) ? 0.f : wc0, c1 = q < (n1.w0 >> 2) ? 0.f : wc1, c2 = q < (n2.w0 >> 2) ? 0.f : wc2,
-                        c3 = q < (n3.w0 >> 2) ? 0.f : wc3;
             float4 A1 = f4zero(), A2 = f4zero(), A3 = f4zero(), Rr = f4zero(), Tt = f4zero();
 #pragma unroll
-            for (int j = 0; j < N; j++) {
+            for (int j = 0; j < NP; j++) {
+                const int stage = PAD ? j % S : (stage0 + j) % S;   // compile-time after unrolling when PAD
                 cp_async_wait<S - 1>();    // item j has landed (this lane's own copies; no other lane reads them)
-                if (active) {
+                if (j < N && active) {
                     const float4* src = ring + (stage * 4) * 32 + lane;
                     const float4 t0 = src[0], t1 = src[32], t2 = src[64], t3 = src[96];
                     float4 r = f4zero();
-                    fma4(r, c0, t0); fma4(r, c1, t1); fma4(r, c2, t2); fma4(r, c3, t3);
+                    fma4(r, wc0, t0); fma4(r, wc1, t1); fma4(r, wc2, t2); fma4(r, wc3, t3);   // a read clamped to quad 0 of a row returns the zeros left of the trace
                     const int k = Seq::comp(j);   // constant after unrolling
                     if (k == 0) fma4(Rr, f1, r);
                     else if (k == 1) fma4(Rr, f2, r);
@@ -528,10 +531,11 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
                     else if (k == 8) fma4(Rr, f6, r);
                     else fma4(A3, f6 * sd, r);
                 }
-                // refill the slot just consumed: a later item of this chunk, or the first items of the next chunk
+                // refill the slot just consumed: a later item of this chunk, nothing (padding), or one of the first
+                // S items of the next chunk
                 if (j + S < N) issue_item(cur, Seq::comp(j + S), ring, stage, lane);
-                else if (have_next) {
-                    const int jj = j + S - N;     // constant after unrolling
+                else if (j + S >= NP && have_next) {
+                    const int jj = j + S - NP;     // constant after unrolling, < S
                     if (jj == 0) {
                         if (more) nxt = chunk_src(db.slabs, n0, n1, n2, n3, q + 32, q_last);
                         else {
@@ -544,8 +548,8 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
                     issue_item(nxt, Seq::comp(jj), ring, stage, lane);
                 }
                 cp_async_commit();
-                stage = (stage + 1) % S;
             }
+            if (!PAD) stage0 = (stage0 + N) % S;
             primed = have_next;
             if (H) {   // seismogram.f90:200-203: ar1 += cl*temp1 - sl*temp2; ar2 += cl*temp2 + sl*temp1
                 fma4(A1, cl, Rr); fma4(A1, -sl_, Tt);
@@ -563,7 +567,7 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
                 const int its = __shfl_sync(0xffffffffu, my_its, k);
                 const float wl = __shfl_sync(0xffffffffu, my_wl, k), wr = __shfl_sync(0xffffffffu, my_wr, k);
                 const int qrel = q + (its >> 2) - baseq;
-                if (active && qrel >= 0 && qrel < nq) {
+                if (active && (unsigned)qrel < (unsigned)nq) {
                     float4* a1 = acc + qrel; float4* a2 = a1 + nq; float4* a3 = a2 + nq;
                     switch (its & 3) {
                         case 0: tap_strips<0, H, V>(a1, a2, a3, P1, A1, P2, A2, P3, A3, wl, wr); break;
@@ -612,7 +616,7 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
 __global__ void __launch_bounds__(256, 2) k_synth(GfdbDev db, const ReceiverDev* __restrict__ rcv, int nrcv,
                                                    const CandDev* __restrict__ cands, GroupSoA g, TapSoA taps, int ngroups_total,
                                                    int interpolate, int xunder, int zunder, const GeoRec* __restrict__ recs,
-                                                   size_t rec_stride, const PairHdr* __restrict__ hdrs, int nq_alloc, int margin_q,
+                                                   size_t rec_stride, const PairHdr* __restrict__ hdrs, int nq_alloc, int margin_q, int variant,
                                                    float* __restrict__ seis, size_t seis_stride /* floats per component row */,
                                                    SeisHdr* __restrict__ shdrs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -649,7 +653,7 @@ __global__ void __launch_bounds__(256, 2) k_synth(GfdbDev db, const ReceiverDev*
     GeoRec* slot = reinterpret_cast<GeoRec*>(tail) + 3 * warp;
     float4* ring = reinterpret_cast<float4*>(reinterpret_cast<GeoRec*>(tail) + 3 * nwarps) + (size_t)warp * SYN_STAGES * 4 * 32;
 
-#define KIWI_SYNTH(HH, VV, NG) synth_warp<HH, VV, NG>(db, myrecs, cand.ngroups, cand.group_begin, g, taps, R.sd, acc, step, nq, baseq, slot, ring, warp, nwarps, lane)
+#define KIWI_SYNTH(HH, VV, NG) if (variant & 1) synth_warp<HH, VV, NG, true>(db, myrecs, cand.ngroups, cand.group_begin, g, taps, R.sd, acc, step, nq, baseq, slot, ring, warp, nwarps, lane); else synth_warp<HH, VV, NG, false>(db, myrecs, cand.ngroups, cand.group_begin, g, taps, R.sd, acc, step, nq, baseq, slot, ring, warp, nwarps, lane)
     if (need_h && need_v) { if (ng10) KIWI_SYNTH(true, true, true); else KIWI_SYNTH(true, true, false); }
     else if (need_h) { if (ng10) KIWI_SYNTH(true, false, true); else KIWI_SYNTH(true, false, false); }
     else if (need_v) { if (ng10) KIWI_SYNTH(false, true, true); else KIWI_SYNTH(false, true, false); }
@@ -1435,10 +1439,12 @@ cudaError_t launch_synth(GfdbDev db, const ReceiverDev* rcv, int nrcv, const Can
                          const PairHdr* hdrs, int nq_alloc, int margin_q, int nwarps, float* seis, size_t seis_stride, SeisHdr* shdrs,
                          cudaStream_t st) {
     size_t smem = synth_smem_bytes(nwarps, nq_alloc);
+    static int variant = -1;   // KIWI_SYNTH_VARIANT: tuning switch for A/B measurements (bit 0: padded item list)
+    if (variant < 0) { const char* e = getenv("KIWI_SYNTH_VARIANT"); variant = e ? atoi(e) : 0; }
     cudaError_t e = cudaFuncSetAttribute(k_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k_synth<<<ncand * nrcv, nwarps * 32, smem, st>>>(db, rcv, nrcv, cands, g, taps, ngroups_total, interpolate, xunder, zunder, recs,
-                                                    rec_stride, hdrs, nq_alloc, margin_q, seis, seis_stride, shdrs);
+                                                    rec_stride, hdrs, nq_alloc, margin_q, variant, seis, seis_stride, shdrs);
     return cudaGetLastError();
 }
 void launch_misfit_td(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, const float* seis, size_t seis_stride,
