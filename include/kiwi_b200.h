@@ -151,7 +151,7 @@ int kiwi_get_n_source_params(int sourcetype);
  * (minimizer_engine.f90:500-523, 876-945, 1130-1172), every candidate evaluated with fresh-state
  * semantics.  params: [ns][nparams] host floats.  misfits: [ns][nmisfits][2] host
  * floats, (misfit, norm factor) interleaved, receiver-major, enabled receivers only.
- * status: [ns] (may be NULL).  This replaces the candidate loop of
+ * status: [ns] (may be NULL); misfits may be NULL when only kiwi_outer_misfits is wanted.  This replaces the candidate loop of
  * python/tunguska/seismosizer.py:682-722 (make_misfits_for_sources). */
 int kiwi_eval_sources(kiwi_ctx* ctx, int sourcetype, int ns, int nparams, const float* params, float* misfits,
                       int* status);
@@ -162,6 +162,18 @@ int kiwi_eval_sources_device(kiwi_ctx* ctx, int sourcetype, int ns, int nparams,
 /* global misfit per candidate, sqrt(sum m^2)/sqrt(sum n^2) (minimizer_engine.f90:939-942), from a
  * host misfit block as returned by kiwi_eval_sources */
 int kiwi_global_misfits(int ns, int nmisfits, const float* misfits, float* global_misfits);
+
+/* Outer misfit and best candidate on the device: make_global_misfits (python/tunguska/seismosizer.py:843-922)
+ * followed by nanargmin (gridsearch.py:250-266).  d_misfits: device block [ns][nmisfits][2] as written by
+ * kiwi_eval_sources_device, or NULL for the block the last kiwi_eval_sources call left on the GPU (pass
+ * misfits = NULL there to skip the download of the cube altogether).  receiver_weights: [nreceivers] (all
+ * receivers, disabled ones ignored) or NULL for 1; outer_norm: KIWI_L2NORM or KIWI_L1NORM; anarchy: weights
+ * divided by each receiver's norm; bweights: [nboot][nreceivers] bootstrap multiplicities (the caller draws
+ * them: numpy bincount of randint, seismosizer.py:871-873) or NULL.  Row 0 of the outputs is the plain result,
+ * rows 1..nboot the bootstrap realisations: misfits_by_s [nboot+1][ns] (may be NULL), best / best_value
+ * [nboot+1] index and value of the smallest non-NaN misfit (-1 / NaN if none).  All in double like numpy. */
+int kiwi_outer_misfits(kiwi_ctx* ctx, int ns, const float* d_misfits, const double* receiver_weights, int outer_norm, int anarchy,
+                       int nboot, const double* bweights, double* misfits_by_s, int* best, double* best_value);
 
 /* ns = 1 convenience pair with the reference's names and change detection
  * (minimizer_engine.f90:500-523: identical parameters are a no-op) */

@@ -50,6 +50,7 @@ SIGNATURES = {
     "kiwi_eval_sources": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p, c_int_p]),
     "kiwi_eval_sources_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_float_p, C.c_void_p, c_int_p]),
     "kiwi_global_misfits": (C.c_int, [C.c_int, C.c_int, c_float_p, c_float_p]),
+    "kiwi_outer_misfits": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_double_p, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_int_p, c_double_p]),
     "kiwi_set_source_params": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p]),
     "kiwi_get_misfits": (C.c_int, [C.c_void_p, c_float_p, C.c_int, c_int_p]),
     "kiwi_get_global_misfit": (C.c_int, [C.c_void_p, c_float_p]),

@@ -117,7 +117,8 @@ struct kiwi_ctx {
     float thickness_limit = 0.f;
     std::string prep_error;                  // message of the last failed discretisation
     bool mt_grid_enabled = true;             // point moment-tensor grid searches go through the tcgen05 contraction
-    DevBuf d_mtlocs, d_mts, d_candof;
+    DevBuf d_mtlocs, d_mts, d_candof, d_orc, d_orw, d_obw, d_oout, d_obest, d_obestv;
+    int last_eval_ns = 0;                    // candidates whose misfit block sits in d_out (kiwi_eval_sources)
     // description of the last chunk evaluated (inspection entry points, accounting)
     struct Last {
         bool valid = false;
@@ -681,7 +682,7 @@ void kiwi_destroy(kiwi_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->d_slabs, &c->d_nodes, &c->d_tspan, &c->d_rcv, &c->d_refdata, &c->d_taper, &c->d_cands, &c->d_bilat, &c->d_gf, &c->d_gi,
-                      &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift, &c->d_mtlocs, &c->d_mts, &c->d_candof})
+                      &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift, &c->d_mtlocs, &c->d_mts, &c->d_candof, &c->d_orc, &c->d_orw, &c->d_obw, &c->d_oout, &c->d_obest, &c->d_obestv})
         b->release();
     c->h_stage.release(); c->h_out.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -955,8 +956,10 @@ int kiwi_eval_sources(kiwi_ctx* c, int sourcetype, int ns, int nparams, const fl
     const size_t nfl = (size_t)ns * std::max(c->nmisfits, 1) * 2;
     CU_OK(c->d_out.ensure(sizeof(float) * std::max<size_t>(nfl, 2)));
     c->src_dirty = true;
+    c->last_eval_ns = 0;
     if (eval_batch(c, sourcetype, ns, nparams, params, c->d_out.as<float>(), status, true)) return 1;
-    if (ns > 0 && c->nmisfits > 0)
+    c->last_eval_ns = ns;
+    if (ns > 0 && c->nmisfits > 0 && misfits)
         CU_OK(cudaMemcpy(misfits, c->d_out.p, sizeof(float) * (size_t)ns * c->nmisfits * 2, cudaMemcpyDeviceToHost));
     return 0;
 }
@@ -969,6 +972,46 @@ int kiwi_global_misfits(int ns, int nmisfits, const float* misfits, float* globa
         for (int i = 0; i < nmisfits; i++) { m = m + p[2 * i] * p[2 * i]; nf = nf + p[2 * i + 1] * p[2 * i + 1]; }
         global_misfits[s] = sqrtf(m) / sqrtf(nf);
     }
+    return 0;
+}
+
+// make_global_misfits (python/tunguska/seismosizer.py:843-922) + nanargmin (gridsearch.py:250-266) on the device
+int kiwi_outer_misfits(kiwi_ctx* c, int ns, const float* d_misfits, const double* receiver_weights, int outer_norm, int anarchy, int nboot,
+                       const double* bweights, double* misfits_by_s, int* best, double* best_value) {
+    if (!c) return kiwi_set_error("null context");
+    CU_OK(cudaSetDevice(c->device));
+    if (outer_norm != KIWI_L2NORM && outer_norm != KIWI_L1NORM) return kiwi_set_error("unknown norm method");
+    if (nboot < 0 || (nboot > 0 && !bweights)) return kiwi_set_error("bootstrap weights missing");
+    if (upload_receivers(c)) return 1;
+    if (!d_misfits) {
+        if (ns != c->last_eval_ns || ns == 0) return kiwi_set_error("no misfit block of %d candidates from kiwi_eval_sources on the device", ns);
+        d_misfits = c->d_out.as<float>();
+    }
+    const int nr = (int)c->rcv.size(), nrows = nboot + 1;
+    std::vector<int> rc((size_t)2 * std::max(nr, 1), 0);
+    for (int i = 0; i < nr; i++) { rc[2 * i] = c->h_rcvdev[i].misfit_base; rc[2 * i + 1] = c->h_rcvdev[i].enabled ? c->h_rcvdev[i].ncomp : 0; }
+    CU_OK(c->d_orc.ensure(sizeof(int) * rc.size()));
+    CU_OK(cudaMemcpyAsync(c->d_orc.p, rc.data(), sizeof(int) * rc.size(), cudaMemcpyHostToDevice, c->stream));
+    if (receiver_weights) {
+        CU_OK(c->d_orw.ensure(sizeof(double) * nr));
+        CU_OK(cudaMemcpyAsync(c->d_orw.p, receiver_weights, sizeof(double) * nr, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (nboot > 0) {
+        CU_OK(c->d_obw.ensure(sizeof(double) * (size_t)nboot * nr));
+        CU_OK(cudaMemcpyAsync(c->d_obw.p, bweights, sizeof(double) * (size_t)nboot * nr, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU_OK(c->d_oout.ensure(sizeof(double) * (size_t)nrows * std::max(ns, 1)));
+    CU_OK(c->d_obest.ensure(sizeof(int) * nrows));
+    CU_OK(c->d_obestv.ensure(sizeof(double) * nrows));
+    if ((size_t)2 * nr * sizeof(double) > (size_t)200 * 1024) return kiwi_set_error("too many receivers for the outer-misfit kernel");
+    cudaError_t e = launch_outer_misfits(d_misfits, c->nmisfits, c->d_orc.p, nr, receiver_weights ? c->d_orw.as<double>() : nullptr,
+                                         outer_norm == KIWI_L1NORM, anarchy != 0, nrows, nboot > 0 ? c->d_obw.as<double>() : nullptr,
+                                         c->d_oout.as<double>(), ns, c->d_obest.as<int>(), c->d_obestv.as<double>(), c->stream);
+    if (e != cudaSuccess) return kiwi_set_error("CUDA error in the outer-misfit kernel: %s", cudaGetErrorString(e));
+    if (misfits_by_s && ns > 0) CU_OK(cudaMemcpyAsync(misfits_by_s, c->d_oout.p, sizeof(double) * (size_t)nrows * ns, cudaMemcpyDeviceToHost, c->stream));
+    if (best && ns > 0) CU_OK(cudaMemcpyAsync(best, c->d_obest.p, sizeof(int) * nrows, cudaMemcpyDeviceToHost, c->stream));
+    if (best_value && ns > 0) CU_OK(cudaMemcpyAsync(best_value, c->d_obestv.p, sizeof(double) * nrows, cudaMemcpyDeviceToHost, c->stream));
+    CU_OK(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

@@ -1415,6 +1415,81 @@ __global__ void __launch_bounds__(128) k_mt_contract(const ReceiverDev* __restri
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(MTC_N) : "memory");
 }
 
+// =================================================================================================
+// Outer misfit (python/tunguska/seismosizer.py:843-922 make_global_misfits): per-receiver norms over
+// components, receiver weights, optional "anarchy" normalisation, optional bootstrap re-weighting of
+// the receivers, global misfit per candidate; then the best candidate per bootstrap row.  Doing it
+// here keeps the [ns, nmisfits, 2] cube on the GPU: only [rows, ns] (or just the minima) goes back.
+// The reference does this in numpy float64, so it is done in fp64 here too.
+// Linear form: both outer norms are dot products of the bootstrap counts with per-receiver terms
+//   l2: a_r = (m_sr w_r)^2, b_r = (n_sr w_r)^2, misfit = sqrt(sum bw_r a_r / sum bw_r b_r)
+//   l1: a_r =  m_sr w_r,    b_r =  n_sr w_r,    misfit =      sum bw_r a_r / sum bw_r b_r
+// =================================================================================================
+struct OuterRcv { int misfit_base, ncomp; };   // enabled receivers only: ncomp > 0; disabled: ncomp = 0
+
+__global__ void __launch_bounds__(128) k_outer_misfits(const float* __restrict__ mis /* [ns][nm][2] */, int nm, const OuterRcv* __restrict__ rc,
+                                                        int nr, const double* __restrict__ rweights /* [nr] or null */, int l1, int anarchy,
+                                                        int nrows, const double* __restrict__ bweights /* [nrows-1][nr] or null */,
+                                                        double* __restrict__ out /* [nrows][ns] */, int ns) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* a = reinterpret_cast<double*>(smem_raw);
+    double* b = a + nr;
+    __shared__ double red[2][4];
+    const int s = blockIdx.x;
+    const float* m = mis + (size_t)s * nm * 2;
+    for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+        double ms = 0., ns_ = 0.;
+        const OuterRcv R = rc[r];
+        for (int c = 0; c < R.ncomp; c++) {
+            const double mv = (double)m[(size_t)(R.misfit_base + c) * 2], nv = (double)m[(size_t)(R.misfit_base + c) * 2 + 1];
+            if (l1) { ms += mv; ns_ += nv; } else { ms += mv * mv; ns_ += nv * nv; }
+        }
+        if (!l1) { ms = sqrt(ms); ns_ = sqrt(ns_); }
+        double w = rweights ? rweights[r] : 1.0;
+        if (anarchy) w = fmax(w / (ns_ != 0. ? ns_ : -1.), 0.);
+        const double mw = ms * w, nw = ns_ * w;
+        a[r] = l1 ? mw : mw * mw;
+        b[r] = l1 ? nw : nw * nw;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int row = 0; row < nrows; row++) {
+        const double* bw = (row == 0 || !bweights) ? nullptr : bweights + (size_t)(row - 1) * nr;
+        double sa = 0., sb = 0.;
+        for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+            const double k = bw ? bw[r] : 1.0;
+            sa += k * a[r]; sb += k * b[r];
+        }
+        for (int o = 16; o; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
+        if (lane == 0) { red[0][warp] = sa; red[1][warp] = sb; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const double A = red[0][0] + red[0][1] + red[0][2] + red[0][3], B = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+            double g = B > 0. ? (l1 ? A / B : sqrt(A / B)) : -1.;
+            if (g < 0. || !(g == g)) g = nan("");
+            out[(size_t)row * ns + s] = g;
+        }
+        __syncthreads();
+    }
+}
+// nanargmin per row (gridsearch.py:250-266)
+__global__ void __launch_bounds__(256) k_row_argmin(const double* __restrict__ v, int ns, int* __restrict__ best, double* __restrict__ bestv) {
+    __shared__ double sv[256]; __shared__ int si[256];
+    const double* row = v + (size_t)blockIdx.x * ns;
+    double mv = INFINITY; int mi = -1;
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) { const double x = row[i]; if (x == x && (x < mv || mi < 0)) { mv = x; mi = i; } }
+    sv[threadIdx.x] = mv; si[threadIdx.x] = mi;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            const int j = threadIdx.x + o;
+            if (si[j] >= 0 && (si[threadIdx.x] < 0 || sv[j] < sv[threadIdx.x] || (sv[j] == sv[threadIdx.x] && si[j] < si[threadIdx.x]))) { sv[threadIdx.x] = sv[j]; si[threadIdx.x] = si[j]; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { best[blockIdx.x] = si[0]; bestv[blockIdx.x] = si[0] >= 0 ? sv[0] : nan(""); }
+}
+
 // ---- host-callable launch wrappers ---------------------------------------------------------------
 void launch_bilat_groups(const BilatCand* d_cands, int ncand, GroupSoA g, TapSoA taps, float dt, int ngroups_total, cudaStream_t st) {
     if (ncand > 0) k_bilat_groups<<<ncand, 128, 0, st>>>(d_cands, g, taps, dt, ngroups_total);
@@ -1488,5 +1563,17 @@ cudaError_t launch_fold(const ReceiverDev* rcv, int nrcv, const CandDev* cands, 
     if (e != cudaSuccess) return e;
     const long long items = (long long)ncand * nrcv * KIWI_MAX_COMP;
     if (items > 0) k_fold<<<(unsigned)items, 256, smem, st>>>(rcv, nrcv, cands, seis, seis_stride, shdrs, dt);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_outer_misfits(const float* mis, int nm, const void* rc, int nr, const double* rweights, int l1, int anarchy, int nrows,
+                                 const double* bweights, double* out, int ns, int* best, double* bestv, cudaStream_t st) {
+    const size_t smem = (size_t)2 * nr * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(k_outer_misfits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (ns > 0) {
+        k_outer_misfits<<<ns, 128, smem, st>>>(mis, nm, (const OuterRcv*)rc, nr, rweights, l1, anarchy, nrows, bweights, out, ns);
+        k_row_argmin<<<nrows, 256, 0, st>>>(out, ns, best, bestv);
+    }
     return cudaGetLastError();
 }

@@ -253,7 +253,39 @@ class Engine:
         out = np.empty((ns, nm, 2), dtype=np.float32)
         status = np.zeros(ns, dtype=np.int32)
         _check(lib.kiwi_eval_sources(self._h, sourcetype, ns, nparams, _fp(p), _fp(out), status.ctypes.data_as(c_int_p)))
+        self._last_ns = ns
         return out, status
+
+    def eval_sources_on_device(self, sourcetype, params):
+        """Evaluate and leave the misfit cube on the GPU (for outer_misfits); returns status[ns]."""
+        if isinstance(sourcetype, str):
+            sourcetype = SOURCE_TYPES[sourcetype]
+        p = _f32(params)
+        if p.ndim == 1:
+            p = p[None, :]
+        status = np.zeros(p.shape[0], dtype=np.int32)
+        _check(lib.kiwi_eval_sources(self._h, sourcetype, p.shape[0], p.shape[1], _fp(p), None, status.ctypes.data_as(c_int_p)))
+        self._last_ns = p.shape[0]
+        return status
+
+    def outer_misfits(self, ns=None, receiver_weights=None, outer_norm="l2norm", anarchy=False, bweights=None, d_misfits_ptr=None,
+                      want_matrix=True):
+        """make_global_misfits + best source (seismosizer.py:843-922, gridsearch.py:250-266) on the device:
+        (misfits_by_s[nboot+1, ns] or None, best[nboot+1], best_value[nboot+1])."""
+        if ns is None:
+            ns = getattr(self, "_last_ns", 0)
+        rw = None if receiver_weights is None else np.ascontiguousarray(receiver_weights, dtype=np.float64)
+        bw = None if bweights is None else np.ascontiguousarray(bweights, dtype=np.float64)
+        nboot = 0 if bw is None else bw.shape[0]
+        out = np.empty((nboot + 1, ns), dtype=np.float64) if want_matrix else None
+        best = np.zeros(nboot + 1, dtype=np.int32); bestv = np.zeros(nboot + 1, dtype=np.float64)
+        norm = NORMS[outer_norm] if isinstance(outer_norm, str) else outer_norm
+        _check(lib.kiwi_outer_misfits(self._h, ns, C.c_void_p(d_misfits_ptr) if d_misfits_ptr else None,
+                                      rw.ctypes.data_as(c_double_p) if rw is not None else None, norm, int(bool(anarchy)), nboot,
+                                      bw.ctypes.data_as(c_double_p) if bw is not None else None,
+                                      out.ctypes.data_as(c_double_p) if out is not None else None, best.ctypes.data_as(c_int_p),
+                                      bestv.ctypes.data_as(c_double_p)))
+        return out, best, bestv
 
     def eval_sources_device(self, sourcetype, params, d_misfits_ptr):
         """Same, results left at the device address d_misfits_ptr ([ns][nmisfits][2] fp32)."""
