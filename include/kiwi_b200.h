@@ -141,6 +141,12 @@ int kiwi_set_floating_shiftrange(kiwi_ctx* ctx, int ireceiver, float shift_lo, f
  * enabled = 0 forces the direct per-candidate path (same results within rounding). */
 int kiwi_set_mt_grid(kiwi_ctx* ctx, int enabled);
 
+/* Candidates of one kiwi_eval_sources batch that differ only in the scalar moment (bilateral, eikonal,
+ * mt_eikonal: parameter 5) share one synthesis and differ only in the scaling + misfit stage -- the batched
+ * form of the reference's `only_moment_changed` shortcut (minimizer_engine.f90:511-521).  On by default;
+ * enabled = 0 synthesises every candidate separately (same results). */
+int kiwi_set_share_syntheses(kiwi_ctx* ctx, int enabled);
+
 /* number of (misfit, norm-factor) pairs get_misfits returns: components of enabled receivers
  * (minimizer_engine.f90:1141-1148) */
 int kiwi_get_nmisfits(kiwi_ctx* ctx);

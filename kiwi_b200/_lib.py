@@ -43,6 +43,7 @@ SIGNATURES = {
     "kiwi_set_misfit_taper": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, c_float_p]),
     "kiwi_set_misfit_filter": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, c_float_p]),
     "kiwi_set_synthetics_factor": (C.c_int, [C.c_void_p, C.c_float]),
+    "kiwi_set_share_syntheses": (C.c_int, [C.c_void_p, C.c_int]),
     "kiwi_set_mt_grid": (C.c_int, [C.c_void_p, C.c_int]),
     "kiwi_set_floating_shiftrange": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float]),
     "kiwi_get_nmisfits": (C.c_int, [C.c_void_p]),

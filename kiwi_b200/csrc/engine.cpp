@@ -16,6 +16,7 @@
 #include <climits>
 #include <unordered_set>
 #include <unordered_map>
+#include <string>
 #include <functional>
 
 #define CU_OK(call)                                                                                          \
@@ -117,6 +118,8 @@ struct kiwi_ctx {
     float thickness_limit = 0.f;
     std::string prep_error;                  // message of the last failed discretisation
     bool mt_grid_enabled = true;             // point moment-tensor grid searches go through the tcgen05 contraction
+    DevBuf d_map, d_status_out;
+    bool dedup_enabled = true;               // candidates that differ only in the moment share one synthesis
     DevBuf d_mtlocs, d_mts, d_candof, d_orc, d_orw, d_obw, d_oout, d_obest, d_obestv;
     int last_eval_ns = 0;                    // candidates whose misfit block sits in d_out (kiwi_eval_sources)
     // description of the last chunk evaluated (inspection entry points, accounting)
@@ -258,10 +261,20 @@ struct SynthHook {
 
 int eval_mt_grid(kiwi_ctx* c, int n, const float* params, float* d_out, int* h_status, bool* used);
 
+// Candidates that differ only in the scalar moment share one synthesis (minimizer_engine.f90:511-521
+// `only_moment_changed`: the reference then reruns only scale_seismograms + calculate_misfits): the pipeline
+// runs over the distinct syntheses, the misfit stage over all candidates ("slots", sorted by synthesis).
+struct Dedup {
+    int n_out = 0;
+    std::vector<int> first;       // [nu+1]: slots of synthesis u are [first[u], first[u+1])
+    std::vector<int> out_of;      // [n_out]: original candidate of a slot
+    std::vector<float> moment;    // [n_out]: its moment
+};
+
 // Evaluate candidates [0,n) of `params`; d_out: device [n][nmisfits][2]; h_status: host [n] or null.
 // want_misfits = false stops after synthesis (used by the seismogram getters).
 int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* params, float* d_out, int* h_status, bool want_misfits,
-               const SynthHook* hook = nullptr) {
+               const SynthHook* hook = nullptr, const Dedup* dd = nullptr) {
     if (require_db(c)) return 1;
     if (require_receivers(c)) return 1;
     if (!c->loc_set) return kiwi_set_error("no source location set");                   // minimizer_engine.f90:1378
@@ -282,6 +295,42 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         bool used = false;
         const int rc = eval_mt_grid(c, n, params, d_out, h_status, &used);
         if (rc || used) return rc;
+    }
+    if (!hook && !dd && want_misfits && n >= 2 && c->dedup_enabled &&
+        (sourcetype == KIWI_SOURCE_BILATERAL || sourcetype == KIWI_SOURCE_EIKONAL || sourcetype == KIWI_SOURCE_MT_EIKONAL)) {
+        // key = all parameters except the moment (index 4 in all three layouts: source_bilat.f90:206, source_eikonal.f90:219-224)
+        struct KeyHash { size_t operator()(const std::string& k) const { return std::hash<std::string>()(k); } };
+        std::unordered_map<std::string, int, KeyHash> ids;
+        std::vector<int> syn_of(n), first_of;
+        std::string key((size_t)nparams * 4, '\0');
+        for (int i = 0; i < n; i++) {
+            memcpy(&key[0], params + (size_t)i * nparams, (size_t)nparams * 4);
+            memset(&key[16], 0, 4);
+            auto it = ids.find(key);
+            if (it == ids.end()) { it = ids.emplace(key, (int)first_of.size()).first; first_of.push_back(i); }
+            syn_of[i] = it->second;
+        }
+        const int nu = (int)first_of.size();
+        if (nu < n) {
+            Dedup d;
+            d.n_out = n;
+            d.first.assign(nu + 1, 0);
+            for (int i = 0; i < n; i++) d.first[syn_of[i] + 1]++;
+            for (int u = 0; u < nu; u++) d.first[u + 1] += d.first[u];
+            d.out_of.assign(n, 0); d.moment.assign(n, 0.f);
+            std::vector<int> fill(d.first.begin(), d.first.end() - 1);
+            for (int i = 0; i < n; i++) { const int j = fill[syn_of[i]]++; d.out_of[j] = i; d.moment[j] = params[(size_t)i * nparams + 4]; }
+            std::vector<float> up((size_t)nu * nparams);
+            for (int u = 0; u < nu; u++) memcpy(&up[(size_t)u * nparams], params + (size_t)first_of[u] * nparams, (size_t)nparams * 4);
+            std::vector<int> ustatus(nu, 0), ostatus(n, 0);
+            CU_OK(c->d_status_out.ensure(sizeof(int) * n));
+            CU_OK(cudaMemset(c->d_status_out.p, 0, sizeof(int) * n));
+            if (eval_batch(c, sourcetype, nu, nparams, up.data(), d_out, ustatus.data(), true, nullptr, &d)) return 1;
+            CU_OK(cudaMemcpy(ostatus.data(), c->d_status_out.p, sizeof(int) * n, cudaMemcpyDeviceToHost));
+            if (h_status) for (int i = 0; i < n; i++) h_status[i] = std::max(ostatus[i], ustatus[syn_of[i]]);
+            c->last.valid = false;   // the tables describe the distinct syntheses, not the candidates
+            return 0;
+        }
     }
     const int nrcv = (int)c->rcv.size();
     const int nm = c->nmisfits;
@@ -478,10 +527,30 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
                 if (hook->fn(b0 + s0, ns_, c->d_seis.as<float>(), seis_stride, c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP)) return 1;
                 c->launches[3] += 1;
             }
+            // misfit stage: one slot per candidate; with shared syntheses the slots of this sub-chunk come with a map
+            int nslots = ns_;
+            const CandMap* d_map = nullptr;
+            float* out_base = d_out + ((size_t)(b0 + s0) * nm) * 2;
+            int* status_base = c->d_status.as<int>() + s0;
+            size_t fshift_off = poff;
+            if (dd && want_misfits) {
+                const int j0 = dd->first[b0 + s0], j1 = dd->first[b0 + s0 + ns_];
+                nslots = j1 - j0;
+                std::vector<CandMap> hm(std::max(nslots, 1));
+                for (int j = j0; j < j1; j++) {
+                    int u = (int)(std::upper_bound(dd->first.begin(), dd->first.end(), j) - dd->first.begin()) - 1;
+                    hm[j - j0] = CandMap{dd->out_of[j], u - (b0 + s0), dd->moment[j], 0};
+                }
+                CU_OK(c->d_map.ensure(sizeof(CandMap) * hm.size()));
+                CU_OK(cudaMemcpyAsync(c->d_map.p, hm.data(), sizeof(CandMap) * hm.size(), cudaMemcpyHostToDevice, st));
+                CU_OK(cudaStreamSynchronize(st));
+                d_map = c->d_map.as<CandMap>();
+                out_base = d_out; status_base = c->d_status_out.as<int>(); fshift_off = 0;
+            }
             if (want_misfits && nm > 0 && !general) {
-                launch_misfit_td(c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>() + s0, ns_, c->d_seis.as<float>(), seis_stride,
+                launch_misfit_td(c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>() + s0, nslots, c->d_seis.as<float>(), seis_stride,
                                  c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, c->d_refdata.as<float>(), c->d_taper.as<float>(),
-                                 c->misfit_method, c->db.dt, c->syn_factor, nm, d_out + ((size_t)(b0 + s0) * nm) * 2, c->d_status.as<int>() + s0, st);
+                                 c->misfit_method, c->db.dt, c->syn_factor, nm, out_base, status_base, d_map, st);
                 c->launches[3] += 1;
             } else if (want_misfits && nm > 0) {
                 // bound of the padded probe span (comparator.f90:1092-1109) over this chunk: union of all synthetic
@@ -518,12 +587,11 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
                     }
                 }
                 if (misfit_general_smem_bytes(n_alloc, nshift) > (size_t)200 * 1024) return kiwi_set_error("floating shift range too large");
-                CU_OK(c->d_fshift.ensure(sizeof(int) * (size_t)nc * nrcv));
-                cudaError_t e = launch_misfit_general(c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>() + s0, ns_, c->d_seis.as<float>(), seis_stride,
+                CU_OK(c->d_fshift.ensure(sizeof(int) * (size_t)(dd ? dd->n_out : nc) * nrcv));
+                cudaError_t e = launch_misfit_general(c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>() + s0, nslots, c->d_seis.as<float>(), seis_stride,
                                                       c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, c->d_refdata.as<float>(), c->d_taper.as<float>(),
                                                       (const float2*)c->d_tw.p, c->tw_n > 0 ? c->tw_n : 2, c->misfit_method, c->db.dt, c->syn_factor, nm,
-                                                      d_out + ((size_t)(b0 + s0) * nm) * 2, c->d_status.as<int>() + s0, c->d_fshift.as<int>() + poff, n_alloc,
-                                                      nshift, st);
+                                                      out_base, status_base, c->d_fshift.as<int>() + fshift_off, n_alloc, nshift, d_map, st);
                 if (e != cudaSuccess) return kiwi_set_error("CUDA error launching the misfit kernel: %s", cudaGetErrorString(e));
                 c->launches[3] += 1;
             }
@@ -682,7 +750,7 @@ void kiwi_destroy(kiwi_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->d_slabs, &c->d_nodes, &c->d_tspan, &c->d_rcv, &c->d_refdata, &c->d_taper, &c->d_cands, &c->d_bilat, &c->d_gf, &c->d_gi,
-                      &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift, &c->d_mtlocs, &c->d_mts, &c->d_candof, &c->d_orc, &c->d_orw, &c->d_obw, &c->d_oout, &c->d_obest, &c->d_obestv})
+                      &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift, &c->d_map, &c->d_status_out, &c->d_mtlocs, &c->d_mts, &c->d_candof, &c->d_orc, &c->d_orw, &c->d_obw, &c->d_oout, &c->d_obest, &c->d_obestv})
         b->release();
     c->h_stage.release(); c->h_out.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -905,6 +973,12 @@ int kiwi_set_source_crustal_thickness_limit(kiwi_ctx* c, float limit) {   // par
     c->thickness_limit = limit;
     if (c->crust.loaded && c->loc_set) { kh::default_constraints(c->crust, c->olat, c->olon, c->thickness_limit, &c->constraints); c->user_constraints = false; }
     c->src_dirty = true;
+    return 0;
+}
+
+int kiwi_set_share_syntheses(kiwi_ctx* c, int enabled) {
+    if (!c) return kiwi_set_error("null context");
+    c->dedup_enabled = enabled != 0;
     return 0;
 }
 

@@ -841,17 +841,19 @@ __global__ void __launch_bounds__(128) k_misfit_td(const ReceiverDev* __restrict
                                                     const SeisHdr* __restrict__ shdrs, const float* __restrict__ refdata,
                                                     const float* __restrict__ taperdata, int method, float dt, float syn_factor,
                                                     int nmisfits, float* __restrict__ out /* [ncand][nmisfits][2] */,
-                                                    int* __restrict__ status) {
+                                                    int* __restrict__ status, const CandMap* __restrict__ map) {
     const int lane = threadIdx.x & 31;
     const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nitems = (long long)ncand * nrcv * KIWI_MAX_COMP;
     if (item >= nitems) return;
     const int ic = (int)(item % KIWI_MAX_COMP);
-    const int pair = (int)(item / KIWI_MAX_COMP);
-    const int b = pair / nrcv, ir = pair % nrcv;
+    const int slot = (int)(item / KIWI_MAX_COMP) / nrcv, ir = (int)(item / KIWI_MAX_COMP) % nrcv;
     const ReceiverDev& R = rcv[ir];
     if (!R.enabled || ic >= R.ncomp) return;
-    const CandDev cand = cands[b];
+    const int b = map ? map[slot].out : slot;         // where the result goes
+    const int bs = map ? map[slot].syn : slot;        // whose synthetics are used
+    const int pair = bs * nrcv + ir;
+    const CandDev cand = cands[bs];
     float* o = out + ((size_t)b * nmisfits + R.misfit_base + ic) * 2;
     const SeisHdr sh = shdrs[(size_t)pair * KIWI_MAX_COMP + ic];
     if (cand.status != 0 || sh.hi < sh.lo) {
@@ -859,7 +861,7 @@ __global__ void __launch_bounds__(128) k_misfit_td(const ReceiverDev* __restrict
         return;
     }
     const float* srow = seis + ((size_t)pair * KIWI_MAX_COMP + ic) * seis_stride;
-    const float moment = cand.moment;
+    const float moment = map ? map[slot].moment : cand.moment;
     const int sds0 = sh.lo, sds1 = sh.hi;
     const int rds0 = R.ref_ds0[ic], rds1 = R.ref_ds1[ic];
     const float* rdat = refdata + R.ref_off[ic];
@@ -1026,17 +1028,21 @@ __global__ void __launch_bounds__(256) k_misfit_general(const ReceiverDev* __res
                                                          const SeisHdr* __restrict__ shdrs, const float* __restrict__ refdata,
                                                          const float* __restrict__ taperdata, const float2* __restrict__ tw, int tw_n,
                                                          int method, float dt, float syn_factor, int nmisfits, float* __restrict__ out,
-                                                         int* __restrict__ status, int* __restrict__ fshift, int n_alloc, int nshift_alloc) {
+                                                         int* __restrict__ status, int* __restrict__ fshift, int n_alloc, int nshift_alloc,
+                                                         const CandMap* __restrict__ map) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* z = reinterpret_cast<float2*>(smem_raw);
     float* sm_m = reinterpret_cast<float*>(z + n_alloc);
     float* sm_n = sm_m + (size_t)nshift_alloc * KIWI_MAX_COMP;
     __shared__ double scratch[64];
-    const int pair = blockIdx.x;
-    const int b = pair / nrcv, ir = pair % nrcv;
+    const int slot = blockIdx.x / nrcv, ir = blockIdx.x % nrcv;
     const ReceiverDev& R = rcv[ir];
     if (!R.enabled || R.ncomp == 0) return;
-    const CandDev cand = cands[b];
+    const int b = map ? map[slot].out : slot;
+    const int bs = map ? map[slot].syn : slot;
+    const int pair = bs * nrcv + ir;                  // rows of the synthetics
+    const int opair = b * nrcv + ir;                  // floating shift of this candidate
+    const CandDev cand = cands[bs];
     float* o = out + ((size_t)b * nmisfits + R.misfit_base) * 2;
     const bool floating = method >= 7;
     const int bm = method == 7 ? 1 : (method == 8 ? 2 : (method == 3 ? 1 : (method == 4 ? 2 : method)));   // norm applied
@@ -1046,13 +1052,13 @@ __global__ void __launch_bounds__(256) k_misfit_general(const ReceiverDev* __res
     for (int ic = 0; ic < R.ncomp && !fail; ic++) if (shdrs[(size_t)pair * KIWI_MAX_COMP + ic].hi < shdrs[(size_t)pair * KIWI_MAX_COMP + ic].lo) fail = true;
     if (fail) {
         if (threadIdx.x < R.ncomp) { o[2 * threadIdx.x] = nanf(""); o[2 * threadIdx.x + 1] = nanf(""); }
-        if (threadIdx.x == 0) { if (cand.status == 0) atomicMax(&status[b], 1); if (fshift) fshift[pair] = 0; }
+        if (threadIdx.x == 0) { if (cand.status == 0) atomicMax(&status[b], 1); if (fshift) fshift[opair] = 0; }
         return;
     }
     const float* tp = taperdata + R.taper_off;
     const float fa = 1.f, fb = syn_factor;
     const bool unit = (fa == 1.f && fb == 1.f);
-    const float moment = cand.moment;
+    const float moment = map ? map[slot].moment : cand.moment;
     const bool tapered = R.has_taper != 0, filtered = R.has_filter != 0;
 
     for (int ic = 0; ic < R.ncomp; ic++) {
@@ -1170,8 +1176,8 @@ __global__ void __launch_bounds__(256) k_misfit_general(const ReceiverDev* __res
                 for (int ic = 0; ic < R.ncomp; ic++) { const float m = sm_m[i * KIWI_MAX_COMP + ic]; s = s + (bm == 2 ? m : m * m); }
                 if (i == 0 || s < best) { best = s; iloc = i; }
             }
-            if (fshift) fshift[pair] = R.fs0 + iloc;
-        } else if (fshift) fshift[pair] = 0;
+            if (fshift) fshift[opair] = R.fs0 + iloc;
+        } else if (fshift) fshift[opair] = 0;
         for (int ic = 0; ic < R.ncomp; ic++) {
             const float mis = sm_m[iloc * KIWI_MAX_COMP + ic];
             float nf;
@@ -1524,12 +1530,12 @@ cudaError_t launch_synth(GfdbDev db, const ReceiverDev* rcv, int nrcv, const Can
 }
 void launch_misfit_td(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, const float* seis, size_t seis_stride,
                       const SeisHdr* shdrs, const float* refdata, const float* taperdata, int method, float dt, float syn_factor,
-                      int nmisfits, float* out, int* status, cudaStream_t st) {
+                      int nmisfits, float* out, int* status, const CandMap* map, cudaStream_t st) {
     long long nitems = (long long)ncand * nrcv * KIWI_MAX_COMP;
     int blocks = (int)((nitems + 3) / 4);
     if (blocks > 0)
         k_misfit_td<<<blocks, 128, 0, st>>>(rcv, nrcv, cands, ncand, seis, seis_stride, shdrs, refdata, taperdata, method, dt, syn_factor,
-                                            nmisfits, out, status);
+                                            nmisfits, out, status, map);
 }
 
 size_t misfit_general_smem_bytes(int n_alloc, int nshift_alloc) {
@@ -1538,13 +1544,13 @@ size_t misfit_general_smem_bytes(int n_alloc, int nshift_alloc) {
 cudaError_t launch_misfit_general(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, const float* seis, size_t seis_stride,
                                   const SeisHdr* shdrs, const float* refdata, const float* taperdata, const float2* tw, int tw_n, int method,
                                   float dt, float syn_factor, int nmisfits, float* out, int* status, int* fshift, int n_alloc,
-                                  int nshift_alloc, cudaStream_t st) {
+                                  int nshift_alloc, const CandMap* map, cudaStream_t st) {
     const size_t smem = misfit_general_smem_bytes(n_alloc, nshift_alloc);
     cudaError_t e = cudaFuncSetAttribute(k_misfit_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (ncand * nrcv > 0)
         k_misfit_general<<<ncand * nrcv, 256, smem, st>>>(rcv, nrcv, cands, seis, seis_stride, shdrs, refdata, taperdata, tw, tw_n, method, dt,
-                                                         syn_factor, nmisfits, out, status, fshift, n_alloc, nshift_alloc);
+                                                         syn_factor, nmisfits, out, status, fshift, n_alloc, nshift_alloc, map);
     return cudaGetLastError();
 }
 

@@ -101,6 +101,15 @@ struct MtLoc {
     int mt_begin, mt_count;
 };
 
+// misfit-stage view of a candidate whose synthesis is shared with others (only the moment differs,
+// minimizer_engine.f90:511-521 `only_moment_changed`): where its results go, whose synthetics it uses, its moment
+struct CandMap {
+    int out;        // candidate index for the misfit block / status (relative to the pointers passed)
+    int syn;        // synthesised candidate whose rows are read (relative to cands / seis / shdrs passed)
+    float moment;   // psm%moment of this candidate (receiver.f90:853-904)
+    int pad;
+};
+
 // per (candidate, receiver) header
 struct PairHdr {
     int s1lo, s1hi;     // span of displacement_ar(1)

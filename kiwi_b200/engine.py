@@ -229,6 +229,10 @@ class Engine:
     def set_synthetics_factor(self, factor):
         _check(lib.kiwi_set_synthetics_factor(self._h, factor))
 
+    def set_share_syntheses(self, enabled):
+        """candidates differing only in the moment share one synthesis (default on)"""
+        _check(lib.kiwi_set_share_syntheses(self._h, int(bool(enabled))))
+
     def set_mt_grid(self, enabled):
         """tensor-core path for point moment-tensor grid searches on (default) / off"""
         _check(lib.kiwi_set_mt_grid(self._h, int(bool(enabled))))

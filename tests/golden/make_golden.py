@@ -43,7 +43,7 @@ def build(engine_factory=OracleEngine):
             out["grid_" + name] = np.asarray(grid[:3], np.int32)      # nx, ny, nt (source_bilat.f90:266-268)
         elif name == "eikonal":
             out["grid_" + name] = np.asarray(grid[:2], np.int32)      # nx, ny (source_eikonal.f90:311-312)
-    o.eval_sources("bilateral", sc.BILAT_SMALL)
+    o.set_source_params("bilateral", sc.BILAT_SMALL)
     for ir, ic in ((1, 1), (1, 3), (2, 2), (6, 1)):
         first, data = o.get_seismogram(ir, ic, 0)
         out["seis_%d_%d_first" % (ir, ic)] = np.int32(first)

@@ -167,6 +167,10 @@ class OracleEngine:
                                                out.ctypes.data_as(fp), status.ctypes.data_as(ip)))
         return out, status
 
+    def set_source_params(self, sourcetype, params):
+        """set_source_params + synthesis (the oracle evaluates eagerly; without references the status is 1)"""
+        self.eval_sources(sourcetype, params)
+
     def time_eval(self, sourcetype, params):
         if isinstance(sourcetype, str):
             sourcetype = SOURCE_TYPES[sourcetype]

@@ -400,3 +400,33 @@ def test_eikonal_user_constraints_and_thickness_limit():
     to, _, no = o.discretize_source("eikonal", EIK)
     assert ng == no and np.array_equal(tg.view(np.uint32), to.view(np.uint32))
     assert tg[:, 2].min() >= 2500.0 and tg[:, 1].min() >= -300.0
+
+
+@pytest.mark.parametrize("stype,base,norm", [("bilateral", sc.BILAT_SMALL, "l1norm"), ("eikonal", EIK, "floating_l2norm"), ("bilateral", sc.BILAT_SMALL, "ampspec_l2norm")])
+def test_moment_axis_shares_syntheses(stype, base, norm):
+    """A grid axis over the moment (python/examples/kiwi: moment x0.1..3.0) multiplies misfit evaluations, not syntheses:
+    minimizer_engine.f90:511-521 `only_moment_changed`.  Same numbers as synthesising every candidate."""
+    g, o = engines(sc.small_db(), COMPS6)
+    ncomps = [len(c) for c in COMPS6]
+    o.eval_sources(stype, base)
+    sc.set_refs_from(o, [g, o], ncomps)
+    for e in (g, o):
+        e.set_misfit_method(norm)
+        if norm.startswith("floating"):
+            e.set_floating_shiftrange(-0.3, 0.3)
+        if stype == "eikonal":      # untapered norms of a folded synthetic inherit its noise-dependent strip end (see the fold test)
+            for ir in range(1, 7):
+                e.set_misfit_taper(ir, *TAPER)
+    p = np.tile(base, (8, 1))
+    p[[1, 4, 6], 5] += 20                       # a second geometry, interleaved with the first
+    p[:, 4] *= np.array([1.0, 0.6, 1.4, 2.0, 1.0, 0.8, 1.7, 0.3], np.float32)
+    mg, sg = g.eval_sources(stype, p)
+    t_shared = g.last_timing()
+    mo, so = o.eval_sources(stype, p)
+    assert not sg.any() and not so.any()
+    tol = misfit_tol(mo, 0.25 if norm.startswith("ampspec") else 0.1)
+    assert np.all(np.abs(mg - mo) <= tol), np.abs((mg - mo) / tol).max()
+    g.set_share_syntheses(False)
+    md, sd = g.eval_sources(stype, p)
+    assert np.array_equal(mg, md) and np.array_equal(sg, sd)      # identical arithmetic per candidate, shared or not
+    assert t_shared["launches"][2] >= 1
