@@ -39,7 +39,7 @@ def setup(eng, db, lat, lon, dep, comps, interpolation="bilinear", effective_dt=
     eng.set_effective_dt(effective_dt)
 
 
-def set_refs_from(eng_src, engines, ncomps, scale=1.07, shift=0):
+def set_refs_from(eng_src, engines, ncomps, scale=1.07, shift=0, dt=0.1):
     """Reference traces = synthetics of the source currently held by eng_src (what
     set_synthetic_reference does, python/tunguska/seismosizer.py:523-527) scaled by `scale`."""
     refs = {}
@@ -49,7 +49,6 @@ def set_refs_from(eng_src, engines, ncomps, scale=1.07, shift=0):
             # sample i of a strip sits at index i; set_ref_seismogram places sample 0 at nint(tbegin/dt)+1
             refs[(ir, ic)] = (first, data * np.float32(scale))
     for e in engines:
-        dt = e._dt if hasattr(e, "_dt") else 0.1
         for (ir, ic), (first, data) in refs.items():
             e.set_ref_seismogram(ir, ic, (first - 1 + shift) * dt, data)
     return refs

@@ -51,33 +51,41 @@ def test_c1_grid_sizes_on_the_oracle():
 @pytest.mark.gpu
 def test_c1_block1_izmit_receivers():
     from kiwi_b200 import Engine
-    g, o = Engine(0), OracleEngine()
-    for e in (g, o):
+    g, o, ow = Engine(0), OracleEngine(), OracleEngine(wide=True)
+    for e in (g, o, ow):
         setup_block1(e)
     tg, gg, ng = g.discretize_source("bilateral", SRC_91)
     to, go, no = o.discretize_source("bilateral", SRC_91)
     assert ng == no == 1050 and np.array_equal(tg.view(np.uint32), to.view(np.uint32))
     # output_seismograms ... synthetics plain: every trace of every receiver
+    # 1050 centroids x 10 components summed sequentially in fp32: the reference path's own accumulation noise is
+    # close to 1e-5 here, so the traces are also held against the restatement with strips carried in double
     o.set_source_params("bilateral", SRC_91)
+    ow.set_source_params("bilateral", SRC_91)
     g.set_source_params("bilateral", SRC_91)
     for ir in range(1, 12):
         for ic in range(1, 4):
-            (fg, dg), (fo, do) = g.get_seismogram(ir, ic, 1), o.get_seismogram(ir, ic, 1)
+            (fg, dg), (fo, do), (fw, dw) = g.get_seismogram(ir, ic, 1), o.get_seismogram(ir, ic, 1), ow.get_seismogram(ir, ic, 1)
             assert (fg, dg.size) == (fo, do.size)
-            assert np.abs(dg - do).max() <= 1e-5 * np.abs(do).max(), (ir, ic)
-    # L2 misfit of the alternating sources of mini.inp against each other
-    sc.set_refs_from(o, [g, o], [3] * 11, scale=1.0)
-    for e in (g, o):
+            peak = np.abs(dw).max()
+            noise = np.abs(do - dw).max() / peak
+            assert np.abs(dg - dw).max() <= 1e-5 * peak, (ir, ic)
+            assert np.abs(dg - do).max() <= max(1e-5, 2 * noise) * peak, (ir, ic, noise)
+    # L2 misfit of the alternating sources of mini.inp against each other (references = the 91-degree source)
+    sc.set_refs_from(ow, [g, o, ow], [3] * 11, scale=1.0, dt=0.5)
+    for e in (g, o, ow):
         e.set_misfit_method("l2norm")
-    mg, sg = g.eval_sources("bilateral", np.stack([SRC_92, SRC_91]))
-    mo, so = o.eval_sources("bilateral", np.stack([SRC_92, SRC_91]))
-    assert not sg.any() and not so.any()
-    tol = 1e-5 * np.maximum(np.abs(mo), 0.1 * np.abs(mo[..., 1:2]))
-    assert np.all(np.abs(mg[0] - mo[0]) <= tol[0])
-    assert np.all(mg[1, :, 0] <= 1e-5 * mg[1, :, 1])                   # the reference source itself: zero misfit
-    g.set_source_params("bilateral", SRC_92)
-    o.eval_sources("bilateral", SRC_92)
-    assert abs(g.get_global_misfit() - o.get_global_misfit()) <= 1e-5 * o.get_global_misfit()
+    pair = np.stack([SRC_92, SRC_91])
+    mg, sg = g.eval_sources("bilateral", pair)
+    mo, so = o.eval_sources("bilateral", pair)
+    mw, sw = ow.eval_sources("bilateral", pair)
+    assert not sg.any() and not so.any() and not sw.any()
+    dev = lambda a, b: float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 0.1 * np.abs(b[..., 1:2]))))
+    d32, dw, d32w = dev(mg[0], mo[0]), dev(mg[0], mw[0]), dev(mo[0], mw[0])
+    assert dw <= 1e-5 and d32 <= max(1e-5, 2.0 * d32w), (d32, dw, d32w)
+    from kiwi_b200 import global_misfits
+    assert global_misfits(mg[1:2])[0] <= 1e-5          # the reference source itself
+    assert abs(global_misfits(mg[0:1])[0] - global_misfits(mw[0:1])[0]) <= 1e-5 * global_misfits(mw[0:1])[0]
 
 
 @pytest.mark.gpu

@@ -81,6 +81,9 @@ def test_c2_grid_path_is_linear_in_the_tensor_and_matches_the_direct_path():
     md, sd = g.eval_sources(stype, cands[sel])
     tol = 1e-5 * np.maximum(np.abs(md), 0.1 * np.abs(md[..., 1:2]))
     assert np.all(np.abs(m[sel] - md) <= tol), np.abs((m[sel] - md) / tol).max()
-    # the base source is in the list: zero misfit there
+    # the base source is in the list (its references were synthesised by the direct path): zero misfit.  Per trace
+    # the bound is relative to the size of the six tensor contributions, not to the trace itself: on a nodal
+    # component they cancel by factors of 10^3, so the check is made on the global misfit (minimizer_engine.f90:939-942)
+    from kiwi_b200 import global_misfits
     k = int(np.where((cands == base).all(1))[0][0])
-    assert np.all(m[k, :, 0] <= 1e-5 * m[k, :, 1])
+    assert global_misfits(m[k:k + 1])[0] <= 1e-5
