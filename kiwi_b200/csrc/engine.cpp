@@ -487,8 +487,8 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         }
         const int nq = (tmax + 6) / 4 + 1 + 2 * margin_q;
         const size_t seis_stride = (size_t)4 * nq;
-        int nwarps = 8;
-        while (nwarps > 1 && synth_smem_bytes(nwarps, nq) > (size_t)110 * 1024) nwarps--;
+        int nwarps = (int)std::min<size_t>(8, std::max<size_t>(1, rec_stride));   // no more warps than groups per candidate
+        while (nwarps > 1 && synth_smem_bytes(nwarps, nq) > (size_t)112 * 1024) nwarps--;   // two CTAs per SM
         if (synth_smem_bytes(nwarps, nq) > (size_t)220 * 1024)
             return kiwi_set_error("synthetic window of %d samples does not fit the shared-memory accumulators", tmax);
         const size_t per_cand_seis = (size_t)nrcv * KIWI_MAX_COMP * seis_stride * sizeof(float);

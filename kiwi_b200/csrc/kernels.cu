@@ -14,6 +14,7 @@
 #include <cfloat>
 #include <climits>
 #include <cstdlib>
+#include <algorithm>
 
 // ---- exactly-rounded fp32 helpers: never contracted into FMA by ptxas -------------------------
 __device__ __forceinline__ float A_(float a, float b) { return __fadd_rn(a, b); }
@@ -441,16 +442,16 @@ __device__ __forceinline__ void issue_item(const ChunkSrc& c, int comp, float4* 
 }
 
 // One warp works through its share of the groups of one (candidate, receiver) pair.
-template <bool H, bool V, bool NG10, bool PAD>
+template <bool H, bool V, bool NG10>
 __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __restrict__ myrecs, int ngroups, int group_begin,
                                            const GroupSoA& g, const TapSoA& taps, float sd, float4* __restrict__ acc,
                                            float* __restrict__ step, int nq, int baseq, GeoRec* slot /* [3] */, float4* ring, int warp,
                                            int nwarps, int lane) {
     typedef CompSeq<H, V, NG10> Seq;
     constexpr int N = Seq::N, S = SYN_STAGES;
-    // PAD: items per chunk padded with empty commit groups to a multiple of S, so that the slot of item j is the
-    // compile-time constant j % S; otherwise the slot index rotates at run time
-    constexpr int NP = PAD ? (N + S - 1) / S * S : N;
+    // (measured without gain and removed again: padding the item list to a multiple of S for compile-time ring slots;
+    //  keeping accumulator quads in registers across taps that hit the same output quad)
+    constexpr int NP = N;
     static_assert(N >= S, "ring deeper than the component list");
     const float dt = db.dt;
     // records of the first two groups synchronously; from then on two groups ahead
@@ -460,7 +461,7 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
     cp_async_wait<0>();
     __syncwarp();
     bool primed = false;    // the first S items of the chunk about to be processed are already in flight
-    int stage0 = 0;         // ring slot of item 0 of the current chunk (always 0 with PAD)
+    int stage0 = 0;         // ring slot of item 0 of the current chunk
     int sl = 0;             // slot of the current group's record
     for (int ip = warp; ip < ngroups; ip += nwarps, sl = (sl + 1) % 3) {
         // record of the group after next; rides in the next commit group
@@ -512,7 +513,7 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
             float4 A1 = f4zero(), A2 = f4zero(), A3 = f4zero(), Rr = f4zero(), Tt = f4zero();
 #pragma unroll
             for (int j = 0; j < NP; j++) {
-                const int stage = PAD ? j % S : (stage0 + j) % S;   // compile-time after unrolling when PAD
+                const int stage = (stage0 + j) % S;
                 cp_async_wait<S - 1>();    // item j has landed (this lane's own copies; no other lane reads them)
                 if (j < N && active) {
                     const float4* src = ring + (stage * 4) * 32 + lane;
@@ -549,7 +550,7 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
                 }
                 cp_async_commit();
             }
-            if (!PAD) stage0 = (stage0 + N) % S;
+            stage0 = (stage0 + N) % S;
             primed = have_next;
             if (H) {   // seismogram.f90:200-203: ar1 += cl*temp1 - sl*temp2; ar2 += cl*temp2 + sl*temp1
                 fma4(A1, cl, Rr); fma4(A1, -sl_, Tt);
@@ -616,7 +617,7 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
 __global__ void __launch_bounds__(256, 2) k_synth(GfdbDev db, const ReceiverDev* __restrict__ rcv, int nrcv,
                                                    const CandDev* __restrict__ cands, GroupSoA g, TapSoA taps, int ngroups_total,
                                                    int interpolate, int xunder, int zunder, const GeoRec* __restrict__ recs,
-                                                   size_t rec_stride, const PairHdr* __restrict__ hdrs, int nq_alloc, int margin_q, int variant,
+                                                   size_t rec_stride, const PairHdr* __restrict__ hdrs, int nq_alloc, int margin_q,
                                                    float* __restrict__ seis, size_t seis_stride /* floats per component row */,
                                                    SeisHdr* __restrict__ shdrs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -653,7 +654,7 @@ __global__ void __launch_bounds__(256, 2) k_synth(GfdbDev db, const ReceiverDev*
     GeoRec* slot = reinterpret_cast<GeoRec*>(tail) + 3 * warp;
     float4* ring = reinterpret_cast<float4*>(reinterpret_cast<GeoRec*>(tail) + 3 * nwarps) + (size_t)warp * SYN_STAGES * 4 * 32;
 
-#define KIWI_SYNTH(HH, VV, NG) if (variant & 1) synth_warp<HH, VV, NG, true>(db, myrecs, cand.ngroups, cand.group_begin, g, taps, R.sd, acc, step, nq, baseq, slot, ring, warp, nwarps, lane); else synth_warp<HH, VV, NG, false>(db, myrecs, cand.ngroups, cand.group_begin, g, taps, R.sd, acc, step, nq, baseq, slot, ring, warp, nwarps, lane)
+#define KIWI_SYNTH(HH, VV, NG) synth_warp<HH, VV, NG>(db, myrecs, cand.ngroups, cand.group_begin, g, taps, R.sd, acc, step, nq, baseq, slot, ring, warp, nwarps, lane)
     if (need_h && need_v) { if (ng10) KIWI_SYNTH(true, true, true); else KIWI_SYNTH(true, true, false); }
     else if (need_h) { if (ng10) KIWI_SYNTH(true, false, true); else KIWI_SYNTH(true, false, false); }
     else if (need_v) { if (ng10) KIWI_SYNTH(false, true, true); else KIWI_SYNTH(false, true, false); }
@@ -672,8 +673,8 @@ __global__ void __launch_bounds__(256, 2) k_synth(GfdbDev db, const ReceiverDev*
     }
     __syncthreads();
     // inclusive prefix sum of the steps over quads, one warp per strip
-    if (warp < 3) {
-        float* st = step_all + (size_t)warp * nq;
+    for (int strip = warp; strip < 3; strip += nwarps) {
+        float* st = step_all + (size_t)strip * nq;
         float run = 0.f;
         for (int q0 = 0; q0 < nq; q0 += 32) {
             const int q = q0 + lane;
@@ -1275,15 +1276,16 @@ __global__ void __launch_bounds__(128) k_mt_contract(const ReceiverDev* __restri
             float m[6];
 #pragma unroll
             for (int k = 0; k < 6; k++) m[k] = have ? __ldg(&mts[(size_t)(L.mt_begin + j) * 6 + k]) : 0.f;
-            char* a = reinterpret_cast<char*>(sA);
+            // row `tid` of the K-major tile: k-core c (4 values = one 16-byte store) at (c*(rows/8) + row/8)*128 + (row%8)*16
+            float hi[6], lo[6];
 #pragma unroll
-            for (int k = 0; k < 6; k++) {
-                const float hi = tf32_hi(m[k]), lo = tf32_hi(m[k] - hi);
-                *reinterpret_cast<float*>(a + operand_off(tid, k, MTC_M)) = hi;
-                *reinterpret_cast<float*>(a + operand_off(tid, 6 + k, MTC_M)) = hi;
-                *reinterpret_cast<float*>(a + operand_off(tid, 12 + k, MTC_M)) = lo;
-                *reinterpret_cast<float*>(a + operand_off(tid, 18 + k, MTC_M)) = 0.f;
-            }
+            for (int k = 0; k < 6; k++) { hi[k] = tf32_hi(m[k]); lo[k] = tf32_hi(m[k] - hi[k]); }
+            char* a = reinterpret_cast<char*>(sA);
+            const float v24[24] = {hi[0], hi[1], hi[2], hi[3], hi[4], hi[5], hi[0], hi[1], hi[2], hi[3], hi[4], hi[5],
+                                   lo[0], lo[1], lo[2], lo[3], lo[4], lo[5], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c4 = 0; c4 < 6; c4++)
+                *reinterpret_cast<float4*>(a + operand_off(tid, 4 * c4, MTC_M)) = make_float4(v24[4 * c4], v24[4 * c4 + 1], v24[4 * c4 + 2], v24[4 * c4 + 3]);
         }
         for (int ic = 0; ic < R.ncomp; ic++) {
             const size_t item0 = ((size_t)(loc * 6) * nrcv + ir) * KIWI_MAX_COMP + ic;     // basis tensor 0 of this location
@@ -1319,15 +1321,17 @@ __global__ void __launch_bounds__(128) k_mt_contract(const ReceiverDev* __restri
                     const int x = c0 + tid;
                     const bool in = x <= xe;
                     char* bsm = reinterpret_cast<char*>(sB);
+                    float hi[6], lo[6];
 #pragma unroll
                     for (int k = 0; k < 6; k++) {
                         const float v = in ? __ldg(seis + (item0 + (size_t)k * item_stride) * seis_stride + (x - sh.base)) : 0.f;
-                        const float hi = tf32_hi(v), lo = tf32_hi(v - hi);
-                        *reinterpret_cast<float*>(bsm + operand_off(tid, k, MTC_N)) = hi;
-                        *reinterpret_cast<float*>(bsm + operand_off(tid, 6 + k, MTC_N)) = lo;
-                        *reinterpret_cast<float*>(bsm + operand_off(tid, 12 + k, MTC_N)) = hi;
-                        *reinterpret_cast<float*>(bsm + operand_off(tid, 18 + k, MTC_N)) = 0.f;
+                        hi[k] = tf32_hi(v); lo[k] = tf32_hi(v - hi[k]);
                     }
+                    const float v24[24] = {hi[0], hi[1], hi[2], hi[3], hi[4], hi[5], lo[0], lo[1], lo[2], lo[3], lo[4], lo[5],
+                                           hi[0], hi[1], hi[2], hi[3], hi[4], hi[5], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int c4 = 0; c4 < 6; c4++)
+                        *reinterpret_cast<float4*>(bsm + operand_off(tid, 4 * c4, MTC_N)) = make_float4(v24[4 * c4], v24[4 * c4 + 1], v24[4 * c4 + 2], v24[4 * c4 + 3]);
                     s_ref[tid] = in ? refval(x) : 0.f;
                     s_tap[tid] = in ? tapval(x) : 0.f;
                 }
@@ -1379,6 +1383,7 @@ __global__ void __launch_bounds__(128) k_mt_contract(const ReceiverDev* __restri
                         : "r"(taddr)
                         : "memory");
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    float part = 0.f;   // 32 terms in fp32, then into the fp64 sum (comparator.f90:639-659 sums in double)
 #pragma unroll
                     for (int u = 0; u < 32; u++) {
                         if (cc + u < ncol) {
@@ -1386,10 +1391,11 @@ __global__ void __launch_bounds__(128) k_mt_contract(const ReceiverDev* __restri
                             const float b = d * s_tap[cc + u];       // moment = 1 for a moment-tensor source (source_moment_tensor.f90:199)
                             const float a = s_ref[cc + u];
                             const float r = fa * a - fb * b;
-                            acc += l1 ? (double)fabsf(r) : (double)r * (double)r;
+                            part += l1 ? fabsf(r) : r * r;
                             if (c0 + cc + u == sds1) e_last = d;
                         }
                     }
+                    acc += (double)part;
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncthreads();      // accumulator and operand tiles are free again
@@ -1509,7 +1515,9 @@ void launch_expand_centroids(CandDev cand, GroupSoA g, TapSoA taps, int ngroups_
 }
 void launch_geometry(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, int ngroups_total,
                      int interpolate, int xunder, int zunder, GeoRec* recs, size_t rec_stride, PairHdr* hdrs, int* tmax, cudaStream_t st) {
-    k_geometry<<<ncand * nrcv, 256, 0, st>>>(db, rcv, nrcv, cands, g, ngroups_total, interpolate, xunder, zunder, recs, rec_stride, hdrs, tmax);
+    // one thread per group: a CTA no wider than the longest group list (a point moment tensor has one group)
+    const int threads = (int)std::min<size_t>(256, std::max<size_t>(32, (rec_stride + 31) / 32 * 32));
+    k_geometry<<<ncand * nrcv, threads, 0, st>>>(db, rcv, nrcv, cands, g, ngroups_total, interpolate, xunder, zunder, recs, rec_stride, hdrs, tmax);
 }
 size_t synth_smem_bytes(int nwarps, int nq) {
     return (size_t)nwarps * 3 * nq * (sizeof(float4) + sizeof(float)) + 16 + (size_t)nwarps * 3 * sizeof(GeoRec) +
@@ -1520,12 +1528,10 @@ cudaError_t launch_synth(GfdbDev db, const ReceiverDev* rcv, int nrcv, const Can
                          const PairHdr* hdrs, int nq_alloc, int margin_q, int nwarps, float* seis, size_t seis_stride, SeisHdr* shdrs,
                          cudaStream_t st) {
     size_t smem = synth_smem_bytes(nwarps, nq_alloc);
-    static int variant = -1;   // KIWI_SYNTH_VARIANT: tuning switch for A/B measurements (bit 0: padded item list)
-    if (variant < 0) { const char* e = getenv("KIWI_SYNTH_VARIANT"); variant = e ? atoi(e) : 0; }
     cudaError_t e = cudaFuncSetAttribute(k_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k_synth<<<ncand * nrcv, nwarps * 32, smem, st>>>(db, rcv, nrcv, cands, g, taps, ngroups_total, interpolate, xunder, zunder, recs,
-                                                    rec_stride, hdrs, nq_alloc, margin_q, variant, seis, seis_stride, shdrs);
+                                                    rec_stride, hdrs, nq_alloc, margin_q, seis, seis_stride, shdrs);
     return cudaGetLastError();
 }
 void launch_misfit_td(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, const float* seis, size_t seis_stride,
