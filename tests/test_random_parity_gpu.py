@@ -1,0 +1,90 @@
+"""Seeded random sweep: random sources, receiver geometries (incl. receiver depth, components, disabled receivers,
+centroids that leave the database), interpolation / undersampling settings, norms, tapers, filters and factors --
+CUDA path against the oracle on every case."""
+import numpy as np
+import pytest
+
+import scenario as sc
+from oracle_lib import OracleEngine
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+ALL_COMPS = ["ned", "swu", "ar", "cl", "d", "u", "ne", "rd", "nedar", "wsucl", "a", "e"]
+NORMS = ["l2norm", "l1norm", "scalar_product", "peak", "ampspec_l2norm", "ampspec_l1norm", "floating_l2norm", "floating_l1norm"]
+
+
+def random_case(seed):
+    rng = np.random.default_rng(seed)
+    nr = int(rng.integers(2, 7))
+    lat, lon, dep = sc.small_receivers(nr, seed=int(rng.integers(1, 10 ** 6)), dmin=float(rng.uniform(1.5e3, 9e3)), dmax=float(rng.uniform(10e3, 17e3)))
+    dep = rng.choice([0.0, 0.0, 250.0, 600.0], nr).astype(np.float32)
+    comps = [ALL_COMPS[int(i)] for i in rng.integers(0, len(ALL_COMPS), nr)]
+    stype = ["bilateral", "moment_tensor", "eikonal", "bilateral"][int(rng.integers(0, 4))]
+    if stype == "bilateral":
+        base = np.array([rng.uniform(-0.5, 1.0), rng.uniform(-800, 800), rng.uniform(-800, 800), rng.uniform(1200, 4200), 10 ** rng.uniform(17, 19),
+                         rng.uniform(0, 360), rng.uniform(5, 90), rng.uniform(-180, 180), rng.uniform(-90, 90), rng.uniform(0, 3000),
+                         rng.uniform(0, 3000), rng.uniform(0, 2500), rng.uniform(2000, 3500), rng.uniform(0, 1.0)], np.float32)
+        if rng.random() < 0.2:
+            base[9:12] = 0          # point-like: nx = ny = 1
+    elif stype == "moment_tensor":
+        base = np.concatenate([[rng.uniform(-0.5, 1.0), rng.uniform(-800, 800), rng.uniform(-800, 800), rng.uniform(800, 4800)],
+                               rng.normal(0, 1e18, 6), [rng.uniform(0.05, 1.2)]]).astype(np.float32)
+    else:
+        base = np.array([rng.uniform(-0.3, 0.5), rng.uniform(-500, 500), rng.uniform(-500, 500), rng.uniform(2500, 4000), 10 ** rng.uniform(17, 19),
+                         rng.uniform(0, 360), rng.uniform(20, 90), rng.uniform(-180, 180), rng.uniform(-300, 300), rng.uniform(-300, 300),
+                         rng.uniform(600, 2000), 0, 0, rng.uniform(0.6, 0.95), rng.choice([0.0, 0.3, 0.6])], np.float32)
+    cfg = dict(interp=["bilinear", "nearest_neighbor"][int(rng.random() < 0.25)], under=(int(rng.integers(1, 3)), int(rng.integers(1, 3))),
+               eff_dt=float(rng.choice([0.1, 0.2, 0.35])), norm=NORMS[int(rng.integers(0, len(NORMS)))], taper=bool(rng.random() < 0.6),
+               filt=bool(rng.random() < 0.4), factor=float(rng.choice([1.0, 1.0, 0.8])), disable=int(rng.integers(0, nr + 1)),
+               db=["small_db", "small_db_ng8"][int(rng.random() < 0.2)])
+    if stype == "eikonal":
+        cfg["taper"] = True          # untapered norms of folded synthetics: see test_eikonal_seismograms_with_rise_time_fold
+    n = int(rng.integers(2, 6))
+    cands = np.tile(base, (n, 1))
+    for i in range(1, n):
+        k = int(rng.integers(0, 6)) if stype != "moment_tensor" else int(rng.integers(1, 10))
+        cands[i, k] += np.float32(rng.normal(0, 1) * (10.0 if k >= 5 and stype != "moment_tensor" else (200.0 if k in (1, 2, 3) else (0.2 if k == 0 else abs(base[k]) * 0.3))))
+    return lat, lon, dep, comps, stype, base, cands, cfg
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_case(seed):
+    from kiwi_b200 import Engine
+    lat, lon, dep, comps, stype, base, cands, cfg = random_case(seed)
+    db = getattr(sc, cfg["db"])()
+    g, o = Engine(0), OracleEngine()
+    for e in (g, o):
+        sc.setup(e, db, lat, lon, dep, comps, interpolation=cfg["interp"], effective_dt=cfg["eff_dt"], under=cfg["under"])
+    to, go, no = o.discretize_source(stype, base)
+    tg, gg, ng = g.discretize_source(stype, base)
+    assert ng == no and np.array_equal(tg.view(np.uint32), to.view(np.uint32)), "centroid table"
+    o.set_source_params(stype, base)
+    ncomps = [len(c) for c in comps]
+    try:
+        sc.set_refs_from(o, [g, o], ncomps)
+    except Exception:
+        pytest.skip("base source leaves the database at some receiver (no synthetic to use as reference)")
+    for e in (g, o):
+        e.set_misfit_method(cfg["norm"])
+        e.set_synthetics_factor(cfg["factor"])
+        if cfg["norm"].startswith("floating"):
+            e.set_floating_shiftrange(-0.4, 0.3)
+        if cfg["taper"]:
+            for ir in range(1, len(comps) + 1):
+                e.set_misfit_taper(ir, [0.8, 1.5, 4.5, 5.5], [0, 1, 1, 0])
+        if cfg["filt"]:
+            e.set_misfit_filter([0.2, 0.5, 2.0, 3.0], [0, 1, 1, 0])
+        if cfg["disable"]:
+            e.switch_receiver(cfg["disable"], False)
+    if g.nmisfits == 0:
+        pytest.skip("all receivers disabled")
+    mg, sg = g.eval_sources(stype, cands)
+    mo, so = o.eval_sources(stype, cands)
+    assert np.array_equal(sg > 0, so > 0), (sg, so)
+    ok = so == 0
+    floor = 0.25 if cfg["norm"].startswith("ampspec") else 0.1
+    if cfg["norm"] in ("scalar_product", "peak"):
+        tol = RTOL * np.maximum(np.abs(mo), floor * np.abs(mo).max(axis=(0, 1), keepdims=True))
+    else:
+        tol = RTOL * np.maximum(np.abs(mo), floor * np.abs(mo[..., 1:2]))
+    assert np.all(np.abs(mg[ok] - mo[ok]) <= tol[ok]), (cfg, stype, float(np.abs((mg[ok] - mo[ok]) / tol[ok]).max()))
