@@ -431,13 +431,17 @@ __device__ __forceinline__ void window_quads(const NodeInfo& n0, const NodeInfo&
     q_last = (max(max(n0.w0 + n0.wn, n1.w0 + n1.wn), max(n2.w0 + n2.wn, n3.w0 + n3.wn)) >> 2) - 1;
 }
 // one item = GF component `comp` of the chunk -> ring slot `stage` (4 corners x 32 lanes x 16 bytes)
-__device__ __forceinline__ void issue_item(const ChunkSrc& c, int comp, float4* ring, int stage, int lane) {
+__device__ __forceinline__ void cp_async16s(unsigned smem_addr, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem_src) : "memory");
+}
+// ring_lane: shared-window address of this lane's first slot (stage 0, corner 0)
+__device__ __forceinline__ void issue_item(const ChunkSrc& c, int comp, unsigned ring_lane, int stage) {
     if (c.active) {
-        float4* dst = ring + (stage * 4) * 32 + lane;
-        cp_async16(dst, c.r0 + comp * c.s0);
-        cp_async16(dst + 32, c.r1 + comp * c.s1);
-        cp_async16(dst + 64, c.r2 + comp * c.s2);
-        cp_async16(dst + 96, c.r3 + comp * c.s3);
+        const unsigned dst = ring_lane + (unsigned)stage * (4 * 32 * 16);
+        cp_async16s(dst, c.r0 + comp * c.s0);
+        cp_async16s(dst + 32 * 16, c.r1 + comp * c.s1);
+        cp_async16s(dst + 64 * 16, c.r2 + comp * c.s2);
+        cp_async16s(dst + 96 * 16, c.r3 + comp * c.s3);
     }
 }
 
@@ -461,6 +465,9 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
     cp_async_wait<0>();
     __syncwarp();
     bool primed = false;    // the first S items of the chunk about to be processed are already in flight
+    const unsigned ring_lane = (unsigned)__cvta_generic_to_shared(ring + lane);
+    ChunkSrc nxt;           // source of the chunk whose first items are already in flight (valid when primed)
+    nxt.active = false;
     int stage0 = 0;         // ring slot of item 0 of the current chunk
     int sl = 0;             // slot of the current group's record
     for (int ip = warp; ip < ngroups; ip += nwarps, sl = (sl + 1) % 3) {
@@ -501,15 +508,14 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
         float4 carry1 = f4zero(), carry2 = f4zero(), carry3 = f4zero();   // quad left of the chunk (zeros left of the windows)
         for (int q0 = q_first; q0 <= q_last; q0 += 32) {
             const int q = q0 + lane;
-            const ChunkSrc cur = chunk_src(db.slabs, n0, n1, n2, n3, q, q_last);
+            const ChunkSrc cur = primed ? nxt : chunk_src(db.slabs, n0, n1, n2, n3, q, q_last);
             const bool active = cur.active;
             if (!primed) {   // pipeline (re)start: first S items of this chunk
 #pragma unroll
-                for (int j = 0; j < S; j++) { issue_item(cur, Seq::comp(j), ring, (stage0 + j) % S, lane); cp_async_commit(); }
+                for (int j = 0; j < S; j++) { issue_item(cur, Seq::comp(j), ring_lane, (stage0 + j) % S); cp_async_commit(); }
             }
             const bool more = q0 + 32 <= q_last;
             const bool have_next = more || next_ok;
-            ChunkSrc nxt = cur;
             float4 A1 = f4zero(), A2 = f4zero(), A3 = f4zero(), Rr = f4zero(), Tt = f4zero();
 #pragma unroll
             for (int j = 0; j < NP; j++) {
@@ -534,7 +540,7 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
                 }
                 // refill the slot just consumed: a later item of this chunk, nothing (padding), or one of the first
                 // S items of the next chunk
-                if (j + S < N) issue_item(cur, Seq::comp(j + S), ring, stage, lane);
+                if (j + S < N) issue_item(cur, Seq::comp(j + S), ring_lane, stage);
                 else if (j + S >= NP && have_next) {
                     const int jj = j + S - NP;     // constant after unrolling, < S
                     if (jj == 0) {
@@ -546,7 +552,7 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
                             nxt = chunk_src(db.slabs, m0, m1, m2, m3, qf + lane, ql);
                         }
                     }
-                    issue_item(nxt, Seq::comp(jj), ring, stage, lane);
+                    issue_item(nxt, Seq::comp(jj), ring_lane, stage);
                 }
                 cp_async_commit();
             }
