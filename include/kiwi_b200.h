@@ -31,8 +31,8 @@ typedef struct kiwi_gfdb kiwi_gfdb;
 
 /* source type ids (parameterized_source.f90 / source_all.f90:58-60) */
 #define KIWI_SOURCE_BILATERAL 1      /* source_bilat.f90, 14 parameters          */
-#define KIWI_SOURCE_CIRCULAR 2       /* not built (out of scope) */
-#define KIWI_SOURCE_POINT_LP 3       /* not built                                 */
+#define KIWI_SOURCE_CIRCULAR 2       /* source_circular.f90, 11 parameters        */
+#define KIWI_SOURCE_POINT_LP 3       /* source_point_lp.f90, 13 parameters        */
 #define KIWI_SOURCE_EIKONAL 4        /* source_eikonal.f90, 15 parameters         */
 #define KIWI_SOURCE_MT_EIKONAL 5     /* source_mt_eikonal.f90, 20 parameters      */
 #define KIWI_SOURCE_MOMENT_TENSOR 6  /* source_moment_tensor.f90, 11 parameters   */

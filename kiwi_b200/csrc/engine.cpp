@@ -228,6 +228,8 @@ bool all_refs_set(const kiwi_ctx* c) {
 int prep_candidate(kiwi_ctx* c, int sourcetype, const float* p, float effective_dt, kh::SourcePrep* sp, std::string* err) {
     if (sourcetype == KIWI_SOURCE_BILATERAL) return kh::prep_bilateral(p, effective_dt, sp) ? 0 : 1;
     if (sourcetype == KIWI_SOURCE_MOMENT_TENSOR) return kh::prep_moment_tensor(p, effective_dt, sp) ? 0 : 1;
+    if (sourcetype == KIWI_SOURCE_CIRCULAR) return kh::prep_circular(p, effective_dt, sp) ? 0 : 1;
+    if (sourcetype == KIWI_SOURCE_POINT_LP) return kh::prep_point_lp(p, effective_dt, sp) ? 0 : 1;
     if (sourcetype == KIWI_SOURCE_EIKONAL || sourcetype == KIWI_SOURCE_MT_EIKONAL) {
         kh::EikonalPrep e;
         if (!kh::prep_eikonal(p, sourcetype == KIWI_SOURCE_MT_EIKONAL, effective_dt, c->olat, c->olon, c->crust, c->constraints, &e)) {
@@ -244,7 +246,7 @@ int prep_candidate(kiwi_ctx* c, int sourcetype, const float* p, float effective_
         o.nt = 0;
         for (const kh::EikonalGroup& g : e.groups) {
             o.g_north.push_back(g.north); o.g_east.push_back(g.east); o.g_depth.push_back(g.depth); o.g_gw.push_back(g.gw);
-            o.g_tap_begin.push_back(g.tap_begin); o.g_tap_count.push_back(g.tap_count);
+            o.g_tap_begin.push_back(g.tap_begin); o.g_tap_count.push_back(g.tap_count); o.g_tbase.push_back(0.f);
             o.nt = std::max(o.nt, g.tap_count);
         }
         return 0;
@@ -279,8 +281,7 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
     if (require_receivers(c)) return 1;
     if (!c->loc_set) return kiwi_set_error("no source location set");                   // minimizer_engine.f90:1378
     if (nparams != kiwi_get_n_source_params(sourcetype) || nparams == 0) return kiwi_set_error("wrong number of source parameters or source type not available");
-    if (sourcetype != KIWI_SOURCE_BILATERAL && sourcetype != KIWI_SOURCE_MOMENT_TENSOR && sourcetype != KIWI_SOURCE_EIKONAL &&
-        sourcetype != KIWI_SOURCE_MT_EIKONAL) return kiwi_set_error("source type not available in this build");
+    if (sourcetype < KIWI_SOURCE_BILATERAL || sourcetype > KIWI_SOURCE_MOMENT_TENSOR) return kiwi_set_error("unknown source type");
     if ((sourcetype == KIWI_SOURCE_EIKONAL || sourcetype == KIWI_SOURCE_MT_EIKONAL) && !c->crust.loaded) return kiwi_set_error("crust2x2 model not loaded");
     if (want_misfits && !all_refs_set(c)) return kiwi_set_error("no reference seismograms set");   // :1428
     bool general = false;   // anything beyond plain time-domain norms goes through k_misfit_general
@@ -297,7 +298,8 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         if (rc || used) return rc;
     }
     if (!hook && !dd && want_misfits && n >= 2 && c->dedup_enabled &&
-        (sourcetype == KIWI_SOURCE_BILATERAL || sourcetype == KIWI_SOURCE_EIKONAL || sourcetype == KIWI_SOURCE_MT_EIKONAL)) {
+        (sourcetype == KIWI_SOURCE_BILATERAL || sourcetype == KIWI_SOURCE_EIKONAL || sourcetype == KIWI_SOURCE_MT_EIKONAL ||
+         sourcetype == KIWI_SOURCE_CIRCULAR || sourcetype == KIWI_SOURCE_POINT_LP)) {
         // key = all parameters except the moment (index 4 in all three layouts: source_bilat.f90:206, source_eikonal.f90:219-224)
         struct KeyHash { size_t operator()(const std::string& k) const { return std::hash<std::string>()(k); } };
         std::unordered_map<std::string, int, KeyHash> ids;
@@ -372,7 +374,7 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
             const kh::SourcePrep& sp = prep[b0 + i];
             CandDev& cd = cands[i];
             cd.group_begin = G; cd.ngroups = sp.ngroups; cd.tap_begin = Tp;
-            cd.ntaps_total = sp.explicit_groups ? (int)sp.toff.size() : sp.nt * (sp.ngroups > 0 ? 1 : 0);
+            cd.ntaps_total = (int)sp.toff.size();
             cd.moment = sp.moment; cd.risetime = sp.risetime; cd.nx = sp.nx; cd.ny = sp.ny; cd.nt = sp.nt;
             cd.status = bad[b0 + i] ? KIWI_STATUS_BAD_PARAMS : KIWI_STATUS_OK;
             G += sp.ngroups; Tp += (int)sp.toff.size();
@@ -432,7 +434,7 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
                     const size_t gi = (size_t)gi0 + k;
                     if (sp.explicit_groups) {
                         hf[gi] = sp.g_north[k]; hf[(size_t)Galloc + gi] = sp.g_east[k]; hf[2 * (size_t)Galloc + gi] = sp.g_depth[k];
-                        hf[3 * (size_t)Galloc + gi] = 0.f;                       // taps carry the complete centroid time
+                        hf[3 * (size_t)Galloc + gi] = sp.g_tbase[k];             // 0 where the taps carry the complete centroid time
                         hf[10 * (size_t)Galloc + gi] = sp.g_gw[k];
                         hi[gi] = cands[i].tap_begin + sp.g_tap_begin[k]; hi[(size_t)Galloc + gi] = sp.g_tap_count[k];
                     } else {
@@ -726,6 +728,8 @@ int kiwi_get_n_source_params(int sourcetype) {   // source_all.f90:97-121
     switch (sourcetype) {
         case KIWI_SOURCE_BILATERAL: return 14;
         case KIWI_SOURCE_MOMENT_TENSOR: return 11;
+        case KIWI_SOURCE_CIRCULAR: return 11;      // source_circular.f90:32
+        case KIWI_SOURCE_POINT_LP: return 13;      // source_point_lp.f90:14
         case KIWI_SOURCE_EIKONAL: return 15;       // source_eikonal.f90:36
         case KIWI_SOURCE_MT_EIKONAL: return 20;    // source_mt_eikonal.f90:36
         default: return 0;

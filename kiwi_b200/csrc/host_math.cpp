@@ -224,4 +224,114 @@ bool prep_moment_tensor(const float* p, float shortest_doi, SourcePrep* out) {
     return true;
 }
 
+// ---- source_circular.f90: circular rupture with constant rupture velocity ---------------------------
+// 11 parameters: time north east depth moment strike dip rake radius rupture-velocity rise-time
+bool prep_circular(const float* p, float shortest_doi, SourcePrep* out) {
+    SourcePrep& o = *out;
+    o = SourcePrep();
+    for (int i = 0; i < 11; i++) if (!std::isfinite(p[i])) return false;
+    // psm_update_dep_params_circular :209-232 -- note that it takes params(9), the radius, as rupture direction
+    const float strike = d2r_r(p[5]), dip = d2r_r(p[6]), rake = d2r_r(p[7]), rupdir = d2r_r(p[8]);
+    float rot_slip[9];
+    init_euler(dip, strike, -rupdir, o.rot_rup);
+    init_euler(dip, strike, -rake, rot_slip);
+    o.moment = p[4]; o.risetime = 0.f;
+    const float time = p[0], north = p[1], east = p[2], depth = p[3], radius = p[8], rupvel = p[9], risetime = p[10];
+    if (!(rupvel > 0.f)) return false;
+    // psm_to_tdsm_size_circular :267-302
+    const float maxdt = shortest_doi, maxdx = 0.5f * shortest_doi * rupvel;
+    const float length = radius * 2.f;
+    const float fx = length / maxdx;
+    if (!(fabsf(fx) < 3000.f)) return false;
+    int nx = (int)floorf(fx) + 1;
+    if (nx <= 1) nx = 2;
+    if (length == 0.f) nx = 1;
+    const int ny = nx;
+    float dursf = length / (float)nx / rupvel;
+    float durfull = risetime + dursf;
+    const float ft = durfull / maxdt;
+    if (!(fabsf(ft) < 1e6f)) return false;
+    int nt = (int)floorf(ft) + 1;
+    if (nt <= 1) nt = 2;
+    // psm_to_tdsm_table_circular :305-444
+    for (int ix = 1; ix <= nx; ix++)
+        for (int iy = 1; iy <= ny; iy++) {
+            const float x = (2.f * ((float)ix - 1.f) - (float)nx + 1.f) / (2.f * (float)nx) * length;
+            const float y = (2.f * ((float)iy - 1.f) - (float)ny + 1.f) / (2.f * (float)ny) * length;
+            const float r = sqrtf(x * x + y * y);
+            if (r <= radius) {
+                const float g[3] = {x, y, 0.f};
+                float q[3];
+                for (int i = 0; i < 3; i++) { float a = 0.f; for (int j = 0; j < 3; j++) a = a + o.rot_rup[i * 3 + j] * g[j]; q[i] = a; }
+                o.g_north.push_back(q[0] + north); o.g_east.push_back(q[1] + east); o.g_depth.push_back(q[2] + depth);
+                o.g_tbase.push_back(r / rupvel + time);
+                o.g_gw.push_back(1.f); o.g_tap_begin.push_back(0); o.g_tap_count.push_back(nt);
+            }
+        }
+    const int np = (int)o.g_north.size();
+    if (np == 0) return false;
+    dursf = length / (float)nx / rupvel;
+    float sx[4], sy[4];
+    if (risetime < dursf) {
+        sx[0] = (-dursf - risetime) / 2.f; sx[1] = (-dursf + risetime) / 2.f; sx[2] = (dursf - risetime) / 2.f; sx[3] = (dursf + risetime) / 2.f;
+        sy[0] = 0.f; sy[1] = 1.f / dursf; sy[2] = 1.f / dursf; sy[3] = 0.f;
+    } else {
+        sx[0] = (-risetime - dursf) / 2.f; sx[1] = (-risetime + dursf) / 2.f; sx[2] = (risetime - dursf) / 2.f; sx[3] = (risetime + dursf) / 2.f;
+        sy[0] = 0.f; sy[1] = 1.f / risetime; sy[2] = 1.f / risetime; sy[3] = 0.f;
+    }
+    durfull = dursf + risetime;
+    const float tbeg = sx[0], dt = durfull / (float)nt;
+    o.toff.resize(nt); o.wt.resize(nt);
+    for (int it = 1; it <= nt; it++) plf_integrate_and_centroid(sx, sy, 4, tbeg + dt * (float)(it - 1), tbeg + dt * (float)it, &o.wt[it - 1], &o.toff[it - 1]);
+    const float m_unrot[9] = {0, 0, -1, 0, 0, 0, -1, 0, 0};
+    float trot[9], tmp[9], m_rot[9];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) trot[i * 3 + j] = rot_slip[j * 3 + i];
+    auto matmul3 = [](const float* a, const float* b, float* c) {
+        for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) { float v = 0.f; for (int j = 0; j < 3; j++) v = v + a[i * 3 + j] * b[j * 3 + k]; c[i * 3 + k] = v; }
+    };
+    matmul3(m_unrot, trot, tmp);
+    matmul3(rot_slip, tmp, m_rot);
+    for (int i = 0; i < 9; i++) m_rot[i] = m_rot[i] / (float)np;
+    o.mhat[0] = m_rot[0]; o.mhat[1] = m_rot[4]; o.mhat[2] = m_rot[8]; o.mhat[3] = m_rot[1]; o.mhat[4] = m_rot[2]; o.mhat[5] = m_rot[5];
+    o.explicit_groups = true;
+    o.nx = nx; o.ny = ny; o.nt = nt; o.ngroups = np;
+    return true;
+}
+
+// ---- source_point_lp.f90: long-period point source with an analytic source time function ---------------
+// 13 parameters: time north east depth moment mxx myy mzz mxy mxz myz duration-of-excitation period
+static float stf_point_lp(float reltime, float prd, float dur_exc) {   // :412-421
+    const float t1 = 2.f;
+    const float t2 = t1 + dur_exc - 5.f;
+    const float t3 = t2 / 4.f;
+    return expf(-((reltime - t3) * (reltime - t3)) / (2.f * pi * dur_exc)) * 1.f / (1.f + expf(-2.f * (reltime - t1))) * 1.f /
+           (1.f + expf(0.5f * (reltime - t2))) * sinf(2.f * pi / prd * reltime);
+}
+bool prep_point_lp(const float* p, float shortest_doi, SourcePrep* out) {
+    SourcePrep& o = *out;
+    o = SourcePrep();
+    for (int i = 0; i < 13; i++) if (!std::isfinite(p[i])) return false;
+    const float maxdt = shortest_doi, dur_exc = p[11], prd = p[12];
+    const float ft = dur_exc / maxdt;
+    if (!(fabsf(ft) < 4096.f)) return false;
+    int nt = (int)floorf(ft) + 1;   // :238-241
+    if (nt <= 1) nt = 2;
+    o.moment = p[4]; o.risetime = 0.f;
+    for (int i = 0; i < 6; i++) o.mhat[i] = p[5 + i];
+    o.toff.resize(nt); o.wt.resize(nt);
+    for (int it = 1; it <= nt; it++) {   // :303-316
+        const float rel_time = (float)(it - 1) * maxdt;
+        o.wt[it - 1] = stf_point_lp(rel_time, prd, dur_exc);
+        o.toff[it - 1] = p[0] + (float)it * maxdt;
+    }
+    // one position; at most 32 time centroids per device group
+    for (int t0 = 0; t0 < nt; t0 += 32) {
+        o.g_north.push_back(p[1]); o.g_east.push_back(p[2]); o.g_depth.push_back(p[3]); o.g_tbase.push_back(0.f); o.g_gw.push_back(1.f);
+        o.g_tap_begin.push_back(t0); o.g_tap_count.push_back(std::min(32, nt - t0));
+    }
+    o.explicit_groups = true;
+    o.nx = 1; o.ny = 1; o.nt = std::min(nt, 32); o.ngroups = (int)o.g_north.size();
+    return true;
+}
+
 }  // namespace kh

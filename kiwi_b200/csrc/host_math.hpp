@@ -28,7 +28,7 @@ struct SourcePrep {
     float point[3] = {0}, time = 0.f;
     std::vector<float> toff, wt;
     // eikonal sources: explicit groups with their own taps (toff = absolute centroid time)
-    std::vector<float> g_north, g_east, g_depth, g_gw;
+    std::vector<float> g_north, g_east, g_depth, g_gw, g_tbase;
     std::vector<int> g_tap_begin, g_tap_count;
     bool explicit_groups = false;
 };
@@ -62,5 +62,7 @@ bool prep_eikonal(const float* params, bool mt_variant, float shortest_doi, doub
 
 bool prep_bilateral(const float* params14, float shortest_doi, SourcePrep* out);
 bool prep_moment_tensor(const float* params11, float shortest_doi, SourcePrep* out);
+bool prep_circular(const float* params11, float shortest_doi, SourcePrep* out);
+bool prep_point_lp(const float* params13, float shortest_doi, SourcePrep* out);
 
 }  // namespace kh

@@ -189,6 +189,109 @@ static inline void psm_to_tdsm_moment_tensor(Psm& psm, Tdsm& tdsm, float shortes
     }
 }
 
+// ---- source_circular.f90 ---------------------------------------------------------------------------------
+static const int n_source_params_circular = 11;   // :33
+// :166-232 (note: psm_update_dep_params_circular reads params(9), the radius, as the rupture direction)
+static inline void psm_set_circular(Psm& psm, const float* params, bool& only_moment_changed) {
+    only_moment_changed = false;
+    psm.params.assign(params, params + n_source_params_circular);
+    psm.sourcetype = PSM_CIRCULAR;
+    psm.moment = psm.params[4];
+    psm.risetime = 0.0f;
+    float strike = d2r_r(psm.params[5]), dip = d2r_r(psm.params[6]), rake = d2r_r(psm.params[7]), rupdir = d2r_r(psm.params[8]);
+    init_euler(dip, strike, -rupdir, psm.rotmat_rup);
+    init_euler(dip, strike, -rake, psm.rotmat_slip);
+}
+// :235-444
+static inline void psm_to_tdsm_circular(Psm& psm, Tdsm& out, float shortest_doi, bool& ok) {
+    ok = true;
+    float time = psm.params[0], north = psm.params[1], east = psm.params[2], depth = psm.params[3];
+    float radius = psm.params[8], rupvel = psm.params[9], risetime = psm.params[10];
+    float maxdt = shortest_doi, maxdx = 0.5f * shortest_doi * rupvel;
+    float length = radius * 2;
+    int nx = f_floor(length / maxdx) + 1;
+    if (nx <= 1) nx = 2;
+    if (length == 0.f) nx = 1;
+    int ny = nx;
+    float dursf = length / (float)nx / rupvel;
+    float durfull = risetime + dursf;
+    int nt = f_floor(durfull / maxdt) + 1;
+    if (nt <= 1) nt = 2;
+    std::vector<float> tshift, grid;
+    for (int ix = 1; ix <= nx; ix++)
+        for (int iy = 1; iy <= ny; iy++) {
+            float x = (2.f * ((float)ix - 1.f) - (float)nx + 1.f) / (2.f * (float)nx) * length;
+            float y = (2.f * ((float)iy - 1.f) - (float)ny + 1.f) / (2.f * (float)ny) * length;
+            float r = sqrtf(x * x + y * y);
+            float g[3] = {x, y, 0.f}, p[3];
+            matvec3(psm.rotmat_rup, g, p);
+            if (r <= radius) {
+                grid.push_back(p[0] + north); grid.push_back(p[1] + east); grid.push_back(p[2] + depth);
+                tshift.push_back(r / rupvel + time);
+            }
+        }
+    int np = (int)tshift.size();
+    if (np == 0) { ok = false; return; }
+    dursf = length / (float)nx / rupvel;
+    Plf stf;
+    if (risetime < dursf) plf_make(stf, {(-dursf - risetime) / 2.f, (-dursf + risetime) / 2.f, (dursf - risetime) / 2.f, (dursf + risetime) / 2.f}, {0.f, 1.f / dursf, 1.f / dursf, 0.f});
+    else plf_make(stf, {(-risetime - dursf) / 2.f, (-risetime + dursf) / 2.f, (risetime - dursf) / 2.f, (risetime + dursf) / 2.f}, {0.f, 1.f / risetime, 1.f / risetime, 0.f});
+    durfull = dursf + risetime;
+    float tbeg = stf.x[0], dt = durfull / (float)nt;
+    std::vector<float> wt(nt), toff(nt);
+    for (int it = 1; it <= nt; it++) plf_integrate_and_centroid(stf, tbeg + dt * (float)(it - 1), tbeg + dt * (float)it, wt[it - 1], toff[it - 1]);
+    float m_unrot[3][3] = {{0, 0, -1}, {0, 0, 0}, {-1, 0, 0}}, trotmat[3][3], tmp[3][3], m_rot[3][3];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) trotmat[i][j] = psm.rotmat_slip[j][i];
+    matmul3(m_unrot, trotmat, tmp);
+    matmul3(psm.rotmat_slip, tmp, m_rot);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) m_rot[i][j] = m_rot[i][j] / (float)np;
+    out.centroids.assign((size_t)np * nt, Centroid());
+    int id = 0;
+    for (int ip = 0; ip < np; ip++)
+        for (int it = 0; it < nt; it++) {
+            Centroid& c = out.centroids[id++];
+            c.north = grid[3 * ip]; c.east = grid[3 * ip + 1]; c.depth = grid[3 * ip + 2];
+            c.time = tshift[ip] + toff[it];
+            c.m[0] = m_rot[0][0] * wt[it]; c.m[1] = m_rot[1][1] * wt[it]; c.m[2] = m_rot[2][2] * wt[it];
+            c.m[3] = m_rot[0][1] * wt[it]; c.m[4] = m_rot[0][2] * wt[it]; c.m[5] = m_rot[1][2] * wt[it];
+        }
+    psm.grid_size = {nx, ny, nt};
+}
+
+// ---- source_point_lp.f90 ---------------------------------------------------------------------------------
+static const int n_source_params_point_lp = 13;   // :14
+static inline void psm_set_point_lp(Psm& psm, const float* params, bool& only_moment_changed) {   // :184-215
+    only_moment_changed = false;
+    psm.params.assign(params, params + n_source_params_point_lp);
+    psm.sourcetype = PSM_POINT_LP;
+    psm.moment = psm.params[4];
+    psm.risetime = 0.0f;
+}
+static inline float stf_point_lp(float reltime, float prd, float dur_exc) {   // :412-421
+    float t1 = 2.f;
+    float t2 = t1 + dur_exc - 5;
+    float t3 = t2 / 4.f;
+    return expf(-((reltime - t3) * (reltime - t3)) / (2 * pi * dur_exc)) * 1.f / (1.f + expf(-2.f * (reltime - t1))) * 1.f /
+           (1.f + expf(0.5f * (reltime - t2))) * sinf(2.f * pi / prd * reltime);
+}
+static inline void psm_to_tdsm_point_lp(Psm& psm, Tdsm& out, float shortest_doi, bool& ok) {   // :217-337
+    ok = true;
+    float maxdt = shortest_doi, dur_exc = psm.params[11], prd = psm.params[12];
+    int nt = f_floor(dur_exc / maxdt) + 1;
+    if (nt <= 1) nt = 2;
+    float timestepsize = maxdt;
+    out.centroids.assign(nt, Centroid());
+    for (int it = 1; it <= nt; it++) {
+        float rel_time = (float)(it - 1) * timestepsize;
+        float tfactor = stf_point_lp(rel_time, prd, dur_exc);
+        Centroid& c = out.centroids[it - 1];
+        c.north = psm.params[1]; c.east = psm.params[2]; c.depth = psm.params[3];
+        c.time = psm.params[0] + (float)it * timestepsize;
+        for (int k = 0; k < 6; k++) c.m[k] = psm.params[5 + k] * tfactor;
+    }
+    psm.grid_size = {1, 1, nt};
+}
+
 // source_all.f90:216-261 / :431-465 (dispatch; only the source types in scope)
 static inline bool psm_set(Psm& psm, int sourcetype, const float* params, int nparams, bool& only_moment_changed) {
     only_moment_changed = false;
@@ -202,6 +305,16 @@ static inline bool psm_set(Psm& psm, int sourcetype, const float* params, int np
         psm_set_moment_tensor(psm, params, only_moment_changed);
         return true;
     }
+    if (sourcetype == PSM_CIRCULAR) {
+        if (nparams != n_source_params_circular) return false;
+        psm_set_circular(psm, params, only_moment_changed);
+        return true;
+    }
+    if (sourcetype == PSM_POINT_LP) {
+        if (nparams != n_source_params_point_lp) return false;
+        psm_set_point_lp(psm, params, only_moment_changed);
+        return true;
+    }
     return false;
 }
 static inline void psm_to_tdsm(Psm& psm, Tdsm& tdsm, float shortest_doi, bool& ok) {
@@ -209,6 +322,8 @@ static inline void psm_to_tdsm(Psm& psm, Tdsm& tdsm, float shortest_doi, bool& o
     ok = false;
     if (psm.sourcetype == PSM_BILAT) psm_to_tdsm_bilat(psm, tdsm, shortest_doi, ok);
     else if (psm.sourcetype == PSM_MOMENT_TENSOR) psm_to_tdsm_moment_tensor(psm, tdsm, shortest_doi, ok);
+    else if (psm.sourcetype == PSM_CIRCULAR) psm_to_tdsm_circular(psm, tdsm, shortest_doi, ok);
+    else if (psm.sourcetype == PSM_POINT_LP) psm_to_tdsm_point_lp(psm, tdsm, shortest_doi, ok);
     tdsm.origin = psm.origin;
     tdsm.ref_time = psm.ref_time;
 }

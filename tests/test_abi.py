@@ -30,7 +30,9 @@ def test_version_and_parameter_counts():
     assert b"sm_100a" in _lib.lib.kiwi_version()
     assert n_source_params("bilateral") == 14          # source_bilat.f90:32
     assert n_source_params("moment_tensor") == 11      # source_moment_tensor.f90
-    assert n_source_params("circular") == 0            # out of scope
+    assert n_source_params("circular") == 11           # source_circular.f90:33
+    assert n_source_params("point_lp") == 13           # source_point_lp.f90:14
+    assert n_source_params("eikonal") == 15 and n_source_params("mt_eikonal") == 20
 
 
 def test_no_cpu_fallback_without_gpu():

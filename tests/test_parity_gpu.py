@@ -430,3 +430,39 @@ def test_moment_axis_shares_syntheses(stype, base, norm):
     md, sd = g.eval_sources(stype, p)
     assert np.array_equal(mg, md) and np.array_equal(sg, sd)      # identical arithmetic per candidate, shared or not
     assert t_shared["launches"][2] >= 1
+
+
+# circular: time north east depth moment strike dip rake radius rupture-velocity rise-time (source_circular.f90)
+CIRC = np.array([0.2, 100, -150, 3000, 1.2e18, 60, 70, 30, 1200, 2800, 0.4], np.float32)
+# point_lp: time north east depth moment mxx myy mzz mxy mxz myz duration-of-excitation period (source_point_lp.f90)
+PLP = np.array([0.1, 50, -80, 2500, 1.0, 1e17, -0.4e17, -0.6e17, 0.3e17, 0.2e17, -0.5e17, 9.0, 2.0], np.float32)
+
+
+@pytest.mark.parametrize("stype,params", [("circular", CIRC), ("point_lp", PLP)])
+@pytest.mark.parametrize("norm", ["l2norm", "ampspec_l1norm"])
+def test_circular_and_point_lp_sources(stype, params, norm):
+    """the remaining two source types of source_all.f90:216-261: centroid table bit-exact
+    (point_lp has 46 time centroids: more than one device group), synthetics and misfits within the bars"""
+    g, o = engines(sc.small_db(), COMPS6)
+    tg, gg, ng = g.discretize_source(stype, params)
+    to, go, no = o.discretize_source(stype, params)
+    assert ng == no and ng > 40 and np.array_equal(tg.view(np.uint32), to.view(np.uint32))
+    o.set_source_params(stype, params)
+    g.set_source_params(stype, params)
+    for ir in range(1, 7):
+        for ic in range(1, len(COMPS6[ir - 1]) + 1):
+            assert_seis_close(g.get_seismogram(ir, ic, 1), o.get_seismogram(ir, ic, 1), "rcv %d comp %d" % (ir, ic))
+    sc.set_refs_from(o, [g, o], [len(c) for c in COMPS6])
+    for e in (g, o):
+        e.set_misfit_method(norm)
+        for ir in range(1, 7):
+            e.set_misfit_taper(ir, *TAPER)
+    p = np.tile(params, (4, 1))
+    p[1, 1] += 300; p[2, 3] -= 400; p[3, 4] *= 1.5
+    if stype == "circular":
+        p[2, 8] = 1500
+    mg, sg = g.eval_sources(stype, p)
+    mo, so = o.eval_sources(stype, p)
+    assert not sg.any() and not so.any()
+    tol = misfit_tol(mo, 0.25 if norm.startswith("ampspec") else 0.1)
+    assert np.all(np.abs(mg - mo) <= tol), np.abs((mg - mo) / tol).max()
