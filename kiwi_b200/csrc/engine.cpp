@@ -119,6 +119,7 @@ struct kiwi_ctx {
     std::string prep_error;                  // message of the last failed discretisation
     bool mt_grid_enabled = true;             // point moment-tensor grid searches go through the tcgen05 contraction
     DevBuf d_map, d_status_out;
+    DevBuf d_taprec, d_stepw;     // shift tables of the current batch (k_tap_table)
     bool dedup_enabled = true;               // candidates that differ only in the moment share one synthesis
     DevBuf d_mtlocs, d_mts, d_candof, d_orc, d_orw, d_obw, d_oout, d_obest, d_obestv;
     int last_eval_ns = 0;                    // candidates whose misfit block sits in d_out (kiwi_eval_sources)
@@ -369,6 +370,8 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         // ---- candidate / group / tap tables ---------------------------------------------------------
         std::vector<CandDev> cands(nc);
         int G = 0, Tp = 0;
+        long long TT = 0;               // entries of the shift table: one per (group, tap)
+        std::vector<int> tt_of(nc, 0);
         size_t rec_stride = 1;
         for (int i = 0; i < nc; i++) {
             const kh::SourcePrep& sp = prep[b0 + i];
@@ -379,11 +382,17 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
             cd.status = bad[b0 + i] ? KIWI_STATUS_BAD_PARAMS : KIWI_STATUS_OK;
             G += sp.ngroups; Tp += (int)sp.toff.size();
             rec_stride = std::max(rec_stride, (size_t)sp.ngroups);
+            tt_of[i] = (int)TT;
+            if (sp.explicit_groups) for (int k = 0; k < sp.ngroups; k++) TT += sp.g_tap_count[k];
+            else TT += (long long)sp.ngroups * sp.nt;
         }
+        if (TT > 0x7fffff00LL) return kiwi_set_error("too many (sub-source, time) pairs in one batch");
         const int Galloc = std::max(G, 1), Talloc = std::max(Tp, 1);
         CU_OK(c->d_cands.ensure(sizeof(CandDev) * nc));
         CU_OK(c->d_gf.ensure(sizeof(float) * 11 * (size_t)Galloc));
-        CU_OK(c->d_gi.ensure(sizeof(int) * 4 * (size_t)Galloc));
+        CU_OK(c->d_gi.ensure(sizeof(int) * 7 * (size_t)Galloc));
+        CU_OK(c->d_taprec.ensure(sizeof(float4) * ((size_t)TT + 1)));
+        CU_OK(c->d_stepw.ensure(sizeof(float2) * ((size_t)TT + 1)));
         CU_OK(c->d_tf.ensure(sizeof(float) * 2 * (size_t)Talloc));
         GroupSoA g;
         float* gf = c->d_gf.as<float>();
@@ -391,6 +400,8 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         g.gw = gf + 10 * (size_t)Galloc;
         int* gi = c->d_gi.as<int>();
         g.tap_begin = gi; g.tap_count = gi + Galloc; g.its_min = gi + 2 * (size_t)Galloc; g.its_max = gi + 3 * (size_t)Galloc;
+        g.tt_begin = gi + 4 * (size_t)Galloc; g.tap_cls = gi + 5 * (size_t)Galloc; g.nstep = gi + 6 * (size_t)Galloc;
+        g.taprec = c->d_taprec.as<float4>(); g.stepw = c->d_stepw.as<float2>();
         TapSoA taps; taps.toff = c->d_tf.as<float>(); taps.wt = taps.toff + Talloc;
         std::vector<float> toff(Talloc, 0.f), wt(Talloc, 0.f);
         for (int i = 0; i < nc; i++) {
@@ -416,6 +427,7 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
                 memcpy(b.mhat, sp.mhat, sizeof b.mhat);
                 b.nx = sp.ngroups ? sp.nx : 0; b.ny = sp.ngroups ? sp.ny : 0; b.nt = sp.nt;
                 b.group_begin = cands[i].group_begin; b.tap_begin = cands[i].tap_begin;
+                b.tt_begin = tt_of[i];
             }
             CU_OK(c->d_bilat.ensure(sizeof(BilatCand) * nc));
             CU_OK(cudaMemcpyAsync(c->d_bilat.p, bc.data(), sizeof(BilatCand) * nc, cudaMemcpyHostToDevice, st));
@@ -425,13 +437,16 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         } else {   // groups defined on the host: the single group of a point moment tensor
                    // (source_moment_tensor.f90:256-263), the sub-faults of an eikonal source (source_eikonal.f90:684-707)
             std::vector<float> hf((size_t)11 * Galloc, 0.f);
-            std::vector<int> hi((size_t)4 * Galloc, 0);
+            std::vector<int> hi((size_t)7 * Galloc, 0);
             for (int i = 0; i < nc; i++) {
                 const kh::SourcePrep& sp = prep[b0 + i];
                 if (sp.ngroups == 0) continue;
                 const int gi0 = cands[i].group_begin;
+                int tt = tt_of[i];
                 for (int k = 0; k < sp.ngroups; k++) {
                     const size_t gi = (size_t)gi0 + k;
+                    hi[4 * (size_t)Galloc + gi] = tt;
+                    tt += sp.explicit_groups ? sp.g_tap_count[k] : sp.nt;
                     if (sp.explicit_groups) {
                         hf[gi] = sp.g_north[k]; hf[(size_t)Galloc + gi] = sp.g_east[k]; hf[2 * (size_t)Galloc + gi] = sp.g_depth[k];
                         hf[3 * (size_t)Galloc + gi] = sp.g_tbase[k];             // 0 where the taps carry the complete centroid time
@@ -449,9 +464,9 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
             CU_OK(cudaMemcpyAsync(c->d_gf.p, hf.data(), sizeof(float) * hf.size(), cudaMemcpyHostToDevice, st));
             CU_OK(cudaMemcpyAsync(c->d_gi.p, hi.data(), sizeof(int) * hi.size(), cudaMemcpyHostToDevice, st));
             CU_OK(cudaStreamSynchronize(st));
-            launch_group_tap_range(g, taps, c->db.dt, 0, G, st);
-            c->launches[0] += 1;
         }
+        launch_tap_table(g, taps, c->db.dt, G, st);   // also the groups' sample-shift ranges
+        c->launches[0] += 1;
         cudaEventRecord(c->ev[2], st);
         // ---- K2: geometry + indices + spans ---------------------------------------------------------
         const size_t npairs = (size_t)nc * nrcv;
@@ -509,10 +524,9 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
             const size_t poff = (size_t)s0 * nrcv;
             cudaEventRecord(c->ev[3], st);
             if (tmax > 0) {
-                cudaError_t e = launch_synth(c->db, c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>() + s0, ns_, g, taps, Galloc,
-                                             c->interpolate ? 1 : 0, c->xunder, c->zunder, c->d_recs.as<GeoRec>() + poff * rec_stride, rec_stride,
-                                             c->d_hdrs.as<PairHdr>() + poff, nq, margin_q, nwarps, c->d_seis.as<float>(), seis_stride,
-                                             c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, st);
+                cudaError_t e = launch_synth(c->db, c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>() + s0, ns_, g,
+                                             c->d_recs.as<GeoRec>() + poff * rec_stride, rec_stride, c->d_hdrs.as<PairHdr>() + poff, nq, margin_q,
+                                             nwarps, c->d_seis.as<float>(), seis_stride, c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, st);
                 if (e != cudaSuccess) return kiwi_set_error("CUDA error launching synthesis: %s", cudaGetErrorString(e));
                 c->launches[2] += 1;
                 if (max_rise > 0.f) {
@@ -754,7 +768,7 @@ void kiwi_destroy(kiwi_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->d_slabs, &c->d_nodes, &c->d_tspan, &c->d_rcv, &c->d_refdata, &c->d_taper, &c->d_cands, &c->d_bilat, &c->d_gf, &c->d_gi,
-                      &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift, &c->d_map, &c->d_status_out, &c->d_mtlocs, &c->d_mts, &c->d_candof, &c->d_orc, &c->d_orw, &c->d_obw, &c->d_oout, &c->d_obest, &c->d_obestv})
+                      &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift, &c->d_map, &c->d_status_out, &c->d_taprec, &c->d_stepw, &c->d_mtlocs, &c->d_mts, &c->d_candof, &c->d_orc, &c->d_orw, &c->d_obw, &c->d_oout, &c->d_obest, &c->d_obestv})
         b->release();
     c->h_stage.release(); c->h_out.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);

@@ -27,6 +27,8 @@ __device__ __forceinline__ NodeInfo ld_node(const NodeInfo* p) {
     NodeInfo n; n.off = ((unsigned long long)u.y << 32) | u.x; n.w0 = (int)u.z; n.wn = (int)u.w;
     return n;
 }
+__device__ __forceinline__ int warp_min_i(int v) { for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
+__device__ __forceinline__ int warp_max_i(int v) { for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
 __device__ __forceinline__ int floordiv4(int x) { return x >> 2; }            // arithmetic shift = floor
 __device__ __forceinline__ int floor4(int x) { return x & ~3; }
 
@@ -63,6 +65,7 @@ __global__ void k_bilat_groups(const BilatCand* __restrict__ cands, GroupSoA g, 
         g.gw[gi] = 1.f;
         g.tap_begin[gi] = c.tap_begin;
         g.tap_count[gi] = c.nt;
+        g.tt_begin[gi] = c.tt_begin + ip * c.nt;
         int lo = INT_MAX, hi = INT_MIN;
         for (int k = 0; k < c.nt; k++) {
             // time = tshift(ip) + toff(it) (source_bilat.f90:446); rshift = time/dt (seismogram.f90:139)
@@ -85,6 +88,51 @@ __global__ void k_group_tap_range(GroupSoA g, TapSoA taps, float dt, int gbegin,
         lo = min(lo, its); hi = max(hi, its);
     }
     g.its_min[gi] = lo; g.its_max[gi] = hi;
+}
+
+// Shift table: one warp per group, lane k = tap k.  What trace_multiply_add derives from the centroid time
+// (sparse_trace.f90:639-646: rshift = time/dt, its = floor(rshift), wr = rshift-its, wl = 1-wr, both times the
+// weight) does not depend on the receiver, so it is tabulated once per candidate.  Entries are ordered by
+// (its mod 4) so that k_synth runs four loops with a compile-time sub-quad shift; taps that repeat their end
+// value from the same quad on (:696-703) are merged into one step entry (summed in tap order).
+__global__ void __launch_bounds__(256) k_tap_table(GroupSoA g, TapSoA taps, float dt, int ngroups) {
+    const int gi = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (gi >= ngroups) return;
+    const int tb = g.tap_begin[gi], tn = min(g.tap_count[gi], 32), tt = g.tt_begin[gi];
+    const bool on = lane < tn;
+    int its = 0; float wl = 0.f, wr = 0.f;
+    if (on) {
+        const float time = A_(g.tbase[gi], taps.toff[tb + lane]);
+        const float rshift = D_(time, dt);
+        its = (int)floorf(rshift);
+        const float wr0 = S_(rshift, (float)its);
+        const float wl0 = S_(1.f, wr0);
+        const float wt = taps.wt[tb + lane];
+        wr = M_(wr0, wt); wl = M_(wl0, wt);
+    }
+    const int cls = its & 3, qoff = its >> 2;
+    const unsigned lt = (1u << lane) - 1u;
+    int base = 0, pos = 0, packed = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const unsigned m = __ballot_sync(0xffffffffu, on && cls == c);
+        if (cls == c) pos = base + __popc(m & lt);
+        base += __popc(m);
+        packed |= __popc(m) << (8 * c);
+    }
+    if (on) g.taprec[tt + pos] = make_float4(__int_as_float(qoff), wl, wr, 0.f);
+    // steps: leader = first tap of every distinct quad shift
+    const float w = wl + wr;
+    float W = 0.f; bool leader = on;
+    for (int j = 0; j < tn; j++) {
+        const float wj = __shfl_sync(0xffffffffu, w, j);
+        const int qj = __shfl_sync(0xffffffffu, qoff, j);
+        if (qj == qoff) { W += wj; if (j < lane) leader = false; }
+    }
+    const unsigned lm = __ballot_sync(0xffffffffu, leader);
+    if (leader) g.stepw[tt + __popc(lm & lt)] = make_float2(__int_as_float(qoff), W);
+    const int lo = warp_min_i(on ? its : INT_MAX), hi = warp_max_i(on ? its : INT_MIN);
+    if (lane == 0) { g.tap_cls[gi] = packed; g.nstep[gi] = __popc(lm); g.its_min[gi] = lo; g.its_max[gi] = hi; }
 }
 
 // expand the SoA of one candidate back into the reference's centroid table (test/inspection only)
@@ -205,7 +253,7 @@ __global__ void __launch_bounds__(256) k_geometry(GfdbDev db, const ReceiverDev*
                 rec.f[3] = 0.5f * (m[1] - m[0]) * s2a + m[3] * c2a;
                 rec.f[4] = m[5] * ca - m[4] * sa;
                 rec.f[5] = m[0] * (sa * sa) + m[1] * (ca * ca) - m[3] * s2a;
-                rec.pad[0] = rec.pad[1] = rec.pad[2] = 0;
+                rec.tt_begin = g.tt_begin[gi]; rec.tap_cls = g.tap_cls[gi]; rec.nstep = g.nstep[gi];
             }
             const float x = (float)dist;
             const float z = S_(depth, R.depth);
@@ -333,61 +381,64 @@ __global__ void __launch_bounds__(256) k_geometry(GfdbDev db, const ReceiverDev*
 // K3: synthesis.  One CTA per (candidate, receiver); every warp owns a private set of three
 // accumulator strips (displacement_ar(1), displacement_ar(2), vertical) in shared memory and works
 // through its share of the groups.  Per group and 128-sample chunk a lane owns one aligned sample
-// quad: 4 corners x ng rows are fetched with coalesced 128-bit loads from the HBM slabs, combined
+// quad: 4 corners x ng rows are staged HBM -> shared memory with 128-bit cp.async copies (a ring of
+// SYN_STAGES components per warp that keeps running across chunk and group boundaries), combined
 // bilinearly (gfdb.f90:943-948), weighted with the moment-tensor/azimuth factors (make_weights
-// seismogram.f90:316-336), rotated by the centroid's back-azimuth difference (:196-203), and then
-// added nt times with the sample shift and linear sub-sample interpolation of trace_multiply_add
-// (sparse_trace.f90:639-705).  The "last sample repeats for ever" rule (:696-703) becomes a step
-// per (group, tap) that is prefix-summed once at the end.
+// seismogram.f90:316-336, precomputed by k_geometry), rotated by the centroid's back-azimuth
+// difference (:196-203), and then added nt times with the sample shift and linear sub-sample
+// interpolation of trace_multiply_add (sparse_trace.f90:639-705; shifts and weights tabulated by
+// k_tap_table).  The "last sample repeats for ever" rule (:696-703) becomes a step per distinct quad
+// shift of the group that is prefix-summed once at the end.
+// All fp32 arithmetic of the inner loops is issued as packed pairs (FFMA2, fma.rn.f32x2): same
+// roundings as the scalar fma, half the issue slots.
 // =================================================================================================
 #define SYN_MAXTAPS 32
+#define SYN_STAGES 3      // ring depth per warp: items (one GF component x four corners) in flight
+#define SYN_ITEM_BYTES (4 * 32 * 16)
 
+typedef unsigned long long u64;
 __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
-__device__ __forceinline__ void fma4(float4& a, float s, const float4& v) {
-    a.x = fmaf(s, v.x, a.x); a.y = fmaf(s, v.y, a.y); a.z = fmaf(s, v.z, a.z); a.w = fmaf(s, v.w, a.w);
-}
-__device__ __forceinline__ float4 shfl_up4(const float4& v, int d) {
-    float4 r;
-    r.x = __shfl_up_sync(0xffffffffu, v.x, d); r.y = __shfl_up_sync(0xffffffffu, v.y, d);
-    r.z = __shfl_up_sync(0xffffffffu, v.z, d); r.w = __shfl_up_sync(0xffffffffu, v.w, d);
-    return r;
-}
-__device__ __forceinline__ float4 shfl4(const float4& v, int src) {
-    float4 r;
-    r.x = __shfl_sync(0xffffffffu, v.x, src); r.y = __shfl_sync(0xffffffffu, v.y, src);
-    r.z = __shfl_sync(0xffffffffu, v.z, src); r.w = __shfl_sync(0xffffffffu, v.w, src);
-    return r;
-}
+struct Q2 { u64 lo, hi; };   // one sample quad as two packed fp32 pairs (x,y) (z,w)
 
-// out quad += wl * A(y - its) + wr * A(y - its - 1) for the four samples of one output quad;
-// P = A(4q-4..4q-1), C = A(4q..4q+3), S = its mod 4 (warp-uniform)
-template <int S>
-__device__ __forceinline__ void tap_quad(float4& o, const float4& P, const float4& C, float wl, float wr) {
-    // E[i] = A(4q-4+i), i=0..7;  o[j] += wl*E[4-S+j] + wr*E[3-S+j]
-    const float E[8] = {P.x, P.y, P.z, P.w, C.x, C.y, C.z, C.w};
-    o.x = fmaf(wl, E[4 - S], o.x); o.x = fmaf(wr, E[3 - S], o.x);
-    o.y = fmaf(wl, E[5 - S], o.y); o.y = fmaf(wr, E[4 - S], o.y);
-    o.z = fmaf(wl, E[6 - S], o.z); o.z = fmaf(wr, E[5 - S], o.z);
-    o.w = fmaf(wl, E[7 - S], o.w); o.w = fmaf(wr, E[6 - S], o.w);
+__device__ __forceinline__ u64 pk2(float a, float b) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpk2(u64 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+// acc (+)= (s,s) * v, both halves rounded like fmaf
+__device__ __forceinline__ void ffma2(u64& acc, float s, u64 v) {
+    asm("{\n\t.reg .b64 ss;\n\tmov.b64 ss, {%1, %1};\n\tfma.rn.f32x2 %0, ss, %2, %0;\n\t}" : "+l"(acc) : "f"(s), "l"(v));
 }
-// one tap applied to the strips the receiver needs; the sub-quad shift is resolved once per tap
-template <int S, bool H, bool V>
-__device__ __forceinline__ void tap_strips(float4* a1, float4* a2, float4* a3, const float4& P1, const float4& A1, const float4& P2,
-                                           const float4& A2, const float4& P3, const float4& A3, float wl, float wr) {
-    if (H) {
-        float4 o = *a1; tap_quad<S>(o, P1, A1, wl, wr); *a1 = o;
-        o = *a2; tap_quad<S>(o, P2, A2, wl, wr); *a2 = o;
-    }
-    if (V) { float4 o = *a3; tap_quad<S>(o, P3, A3, wl, wr); *a3 = o; }
+__device__ __forceinline__ void q2_fma(Q2& a, float s, const Q2& v) { ffma2(a.lo, s, v.lo); ffma2(a.hi, s, v.hi); }
+__device__ __forceinline__ Q2 q2_zero() { Q2 r; r.lo = 0ull; r.hi = 0ull; return r; }
+template <int OFF>
+__device__ __forceinline__ Q2 lds_q2(unsigned addr) {
+    Q2 r;
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+%3];" : "=l"(r.lo), "=l"(r.hi) : "r"(addr), "n"(OFF) : "memory");
+    return r;
+}
+__device__ __forceinline__ float4 lds_f4(unsigned addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
+    return r;
+}
+__device__ __forceinline__ void sts_q2(unsigned addr, const Q2& v) {
+    asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(addr), "l"(v.lo), "l"(v.hi) : "memory");
+}
+__device__ __forceinline__ u64 shfl_up_u64(u64 v, int d) {
+    float a, b; unpk2(v, a, b);
+    return pk2(__shfl_up_sync(0xffffffffu, a, d), __shfl_up_sync(0xffffffffu, b, d));
+}
+__device__ __forceinline__ u64 shfl_u64(u64 v, int src) {
+    float a, b; unpk2(v, a, b);
+    return pk2(__shfl_sync(0xffffffffu, a, src), __shfl_sync(0xffffffffu, b, src));
 }
 
 // ---- asynchronous staging (cp.async): group records and GF quads travel HBM -> shared memory without
 // passing through registers, so a warp keeps SYN_STAGES x 4 128-bit loads in flight also while it is
 // busy with the tap phase of the previous chunk -------------------------------------------------------------
-#define SYN_STAGES 3      // ring depth per warp: items (one GF component x four corners) in flight
-
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async16s(unsigned smem_addr, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -403,25 +454,22 @@ template <bool H, bool V, bool NG10>
 struct CompSeq {
     static constexpr int N = (H && V) ? (NG10 ? 10 : 8) : (H ? (NG10 ? 6 : 5) : (NG10 ? 4 : 3));
     __host__ __device__ static constexpr int comp(int j) { return (H && V) ? j : (H ? (j < 5 ? j : 8) : (j < 3 ? 5 + j : 9)); }
+    __host__ __device__ static constexpr int step(int j) { return j + 1 < N ? comp(j + 1) - comp(j) : 0; }   // rows from item j to item j+1
 };
 
-// where a lane reads one chunk from: row pointers of GF component 1 at the lane's quad for the four
-// corners (clamped into each window: the last quad is the continuation), row strides in quads
+// where a lane reads a chunk from: for the four corners the address of the lane's quad in the row of the
+// component that is issued next (clamped into each window: quad 0 holds zeros, the last quad the continuation)
+// and the row strides in bytes
 struct ChunkSrc {
-    const float4 *r0, *r1, *r2, *r3;
-    int s0, s1, s2, s3;
+    const char *p0, *p1, *p2, *p3;
+    unsigned s0, s1, s2, s3;
     bool active;
 };
-__device__ __forceinline__ ChunkSrc chunk_src(const float* slabs, const NodeInfo& n0, const NodeInfo& n1, const NodeInfo& n2, const NodeInfo& n3,
-                                              int q, int q_last) {
-    ChunkSrc c;
-    c.s0 = n0.wn >> 2; c.s1 = n1.wn >> 2; c.s2 = n2.wn >> 2; c.s3 = n3.wn >> 2;
-    c.r0 = reinterpret_cast<const float4*>(slabs + n0.off) + min(max(q - (n0.w0 >> 2), 0), c.s0 - 1);
-    c.r1 = reinterpret_cast<const float4*>(slabs + n1.off) + min(max(q - (n1.w0 >> 2), 0), c.s1 - 1);
-    c.r2 = reinterpret_cast<const float4*>(slabs + n2.off) + min(max(q - (n2.w0 >> 2), 0), c.s2 - 1);
-    c.r3 = reinterpret_cast<const float4*>(slabs + n3.off) + min(max(q - (n3.w0 >> 2), 0), c.s3 - 1);
-    c.active = q <= q_last;
-    return c;
+__device__ __forceinline__ const char* corner_ptr(const float* slabs, const NodeInfo& n, int q, int comp0, unsigned& stride_bytes) {
+    const int nq = n.wn >> 2;
+    stride_bytes = (unsigned)nq << 4;
+    const int qi = min(max(q - (n.w0 >> 2), 0), nq - 1) + comp0 * nq;
+    return reinterpret_cast<const char*>(slabs + n.off) + ((size_t)(unsigned)qi << 4);
 }
 __device__ __forceinline__ void window_quads(const NodeInfo& n0, const NodeInfo& n1, const NodeInfo& n2, const NodeInfo& n3, int& q_first,
                                              int& q_last) {
@@ -430,176 +478,224 @@ __device__ __forceinline__ void window_quads(const NodeInfo& n0, const NodeInfo&
     // last quad of the longest window: continuation only, for every corner
     q_last = (max(max(n0.w0 + n0.wn, n1.w0 + n1.wn), max(n2.w0 + n2.wn, n3.w0 + n3.wn)) >> 2) - 1;
 }
-// one item = GF component `comp` of the chunk -> ring slot `stage` (4 corners x 32 lanes x 16 bytes)
-__device__ __forceinline__ void cp_async16s(unsigned smem_addr, const void* gmem_src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem_src) : "memory");
+// source of the chunk starting at quad q0 (or, q0 < 0, of the first chunk) of the group whose record is *rec;
+// also returns the group's quad range.  Lane 0 re-reads the quad left of the chunk (for the first chunk: the zeros
+// left of the windows), lanes 1..31 own the chunk's 31 quads.
+__device__ __forceinline__ void chunk_src(ChunkSrc& c, const float* slabs, const GeoRec* rec, int q0, int lane, int comp0, int& q_first, int& q_last) {
+    const NodeInfo n0 = rec->node[0], n1 = rec->node[1], n2 = rec->node[2], n3 = rec->node[3];
+    window_quads(n0, n1, n2, n3, q_first, q_last);
+    const int q = (q0 < 0 ? q_first : q0) + lane - 1;
+    c.p0 = corner_ptr(slabs, n0, q, comp0, c.s0);
+    c.p1 = corner_ptr(slabs, n1, q, comp0, c.s1);
+    c.p2 = corner_ptr(slabs, n2, q, comp0, c.s2);
+    c.p3 = corner_ptr(slabs, n3, q, comp0, c.s3);
+    c.active = q <= q_last;
 }
-// ring_lane: shared-window address of this lane's first slot (stage 0, corner 0)
-__device__ __forceinline__ void issue_item(const ChunkSrc& c, int comp, unsigned ring_lane, int stage) {
+__device__ __forceinline__ void advance_rows(const char*& p, unsigned stride_bytes, int rows) {
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(p) : "r"(stride_bytes), "r"((unsigned)rows));
+}
+// one item = the next GF component of the chunk -> ring slot (4 corners x 32 lanes x 16 bytes); the source then moves
+// on by `dcomp` rows
+__device__ __forceinline__ void issue_item(ChunkSrc& c, unsigned slot, int dcomp /* constant after unrolling */) {
     if (c.active) {
-        const unsigned dst = ring_lane + (unsigned)stage * (4 * 32 * 16);
-        cp_async16s(dst, c.r0 + comp * c.s0);
-        cp_async16s(dst + 32 * 16, c.r1 + comp * c.s1);
-        cp_async16s(dst + 64 * 16, c.r2 + comp * c.s2);
-        cp_async16s(dst + 96 * 16, c.r3 + comp * c.s3);
+        cp_async16s(slot, c.p0);
+        cp_async16s(slot + 32 * 16, c.p1);
+        cp_async16s(slot + 64 * 16, c.p2);
+        cp_async16s(slot + 96 * 16, c.p3);
     }
+    if (dcomp != 0) {   // running pointers (opaque to the compiler, which would otherwise re-derive every address from the chunk base)
+        advance_rows(c.p0, c.s0, dcomp); advance_rows(c.p1, c.s1, dcomp); advance_rows(c.p2, c.s2, dcomp); advance_rows(c.p3, c.s3, dcomp);
+    }
+}
+
+// out quad (+)= wl * A(y - its) + wr * A(y - its - 1), S = its mod 4.
+// E[i] = samples 2i, 2i+1 of the eight samples (previous quad, own quad); G[i] = samples 2i+1, 2i+2
+template <int S>
+__device__ __forceinline__ void tap_fma(ulonglong2& o, const u64* E, const u64* G, float wl, float wr) {
+    if (S == 0) { ffma2(o.x, wl, E[2]); ffma2(o.y, wl, E[3]); ffma2(o.x, wr, G[1]); ffma2(o.y, wr, G[2]); }
+    else if (S == 1) { ffma2(o.x, wl, G[1]); ffma2(o.y, wl, G[2]); ffma2(o.x, wr, E[1]); ffma2(o.y, wr, E[2]); }
+    else if (S == 2) { ffma2(o.x, wl, E[1]); ffma2(o.y, wl, E[2]); ffma2(o.x, wr, G[0]); ffma2(o.y, wr, G[1]); }
+    else { ffma2(o.x, wl, G[0]); ffma2(o.y, wl, G[1]); ffma2(o.x, wr, E[0]); ffma2(o.y, wr, E[1]); }
+}
+// the taps of one sub-quad shift class (sparse_trace.f90:647-695).  A quad that falls outside the strips, or belongs to
+// a lane right of the windows (qb huge), goes to the dummy quad behind each strip.
+template <int S, bool H, bool V>
+__device__ __forceinline__ void tap_class(int cnt, int& t, int my_q, float my_wl, float my_wr, int qb, int nq, ulonglong2* __restrict__ acc, int nqs,
+                                          const u64* E1, const u64* G1, const u64* E2, const u64* G2, const u64* E3, const u64* G3) {
+    for (int k = 0; k < cnt; k++, t++) {
+        const int qoff = __shfl_sync(0xffffffffu, my_q, t);
+        const float wl = __shfl_sync(0xffffffffu, my_wl, t), wr = __shfl_sync(0xffffffffu, my_wr, t);
+        const int qrel = qb + qoff;
+        const unsigned idx = (unsigned)qrel < (unsigned)nq ? (unsigned)qrel : (unsigned)nq;
+        ulonglong2 *p1 = acc + idx, *p2 = p1 + nqs, *p3 = p2 + nqs;
+        if (H) {
+            // (one quad at a time: with two quads in flight the assembler renames the second and copies it back for the store)
+            ulonglong2 o1 = *p1; tap_fma<S>(o1, E1, G1, wl, wr); *p1 = o1;
+            ulonglong2 o2 = *p2; tap_fma<S>(o2, E2, G2, wl, wr); *p2 = o2;
+        }
+        if (V) { ulonglong2 o3 = *p3; tap_fma<S>(o3, E3, G3, wl, wr); *p3 = o3; }
+        __syncwarp();
+    }
+}
+// nz = -0.0f handed in as a kernel argument: x + nz == x bit for bit, but the assembler cannot see that and so gives the
+// odd pairs registers of their own once per chunk, instead of re-assembling them from the halves of E at every use
+__device__ __forceinline__ void make_pairs(const Q2& P, const Q2& A, u64* E, u64* G, float nz) {
+    float p0, p1, p2, p3, a0, a1, a2, a3;
+    unpk2(P.lo, p0, p1); unpk2(P.hi, p2, p3); unpk2(A.lo, a0, a1); unpk2(A.hi, a2, a3);
+    E[0] = P.lo; E[1] = P.hi; E[2] = A.lo; E[3] = A.hi;
+    G[0] = pk2(__fadd_rn(p1, nz), __fadd_rn(p2, nz)); G[1] = pk2(__fadd_rn(p3, nz), __fadd_rn(a0, nz)); G[2] = pk2(__fadd_rn(a1, nz), __fadd_rn(a2, nz));
+    (void)p0; (void)a3;
 }
 
 // One warp works through its share of the groups of one (candidate, receiver) pair.
 template <bool H, bool V, bool NG10>
-__device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __restrict__ myrecs, int ngroups, int group_begin,
-                                           const GroupSoA& g, const TapSoA& taps, float sd, float4* __restrict__ acc,
-                                           float* __restrict__ step, int nq, int baseq, GeoRec* slot /* [3] */, float4* ring, int warp,
-                                           int nwarps, int lane) {
+__device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __restrict__ myrecs, int ngroups, const float4* __restrict__ taprec,
+                                           const float2* __restrict__ stepw, float sd, ulonglong2* __restrict__ acc /* the warp's strips */,
+                                           float* __restrict__ step, int nq, int baseq, GeoRec* slot /* [3] */,
+                                           unsigned ring_s /* shared address of the warp's ring */, int warp, int nwarps, int lane, float nz) {
     typedef CompSeq<H, V, NG10> Seq;
     constexpr int N = Seq::N, S = SYN_STAGES;
-    // (measured without gain and removed again: padding the item list to a multiple of S for compile-time ring slots;
-    //  keeping accumulator quads in registers across taps that hit the same output quad)
-    constexpr int NP = N;
-    static_assert(N >= S, "ring deeper than the component list");
-    const float dt = db.dt;
+    static_assert(N >= S && S == 3, "ring depth");
     // records of the first two groups synchronously; from then on two groups ahead
     rec_copy_async(myrecs, warp, ngroups, slot, lane);
     rec_copy_async(myrecs, warp + nwarps, ngroups, slot + 1, lane);
     cp_async_commit();
     cp_async_wait<0>();
     __syncwarp();
+    // ring slots of this lane in the order the next items use them (rotated after every chunk)
+    unsigned r0 = ring_s + lane * 16, r1 = r0 + SYN_ITEM_BYTES, r2 = r1 + SYN_ITEM_BYTES;
     bool primed = false;    // the first S items of the chunk about to be processed are already in flight
-    const unsigned ring_lane = (unsigned)__cvta_generic_to_shared(ring + lane);
-    ChunkSrc nxt;           // source of the chunk whose first items are already in flight (valid when primed)
-    nxt.active = false;
-    int stage0 = 0;         // ring slot of item 0 of the current chunk
+    ChunkSrc src;           // where the items still to be issued come from
+    src.active = false;
+    int qf_n = 0, ql_n = 0; // quad range of the group the look-ahead has started
     int sl = 0;             // slot of the current group's record
-    for (int ip = warp; ip < ngroups; ip += nwarps, sl = (sl + 1) % 3) {
+    for (int ip = warp; ip < ngroups; ip += nwarps, sl = (sl == 2 ? 0 : sl + 1)) {
         // record of the group after next; rides in the next commit group
-        rec_copy_async(myrecs, ip + 2 * nwarps, ngroups, slot + (sl + 2) % 3, lane);
-        const GeoRec& rec = slot[sl];
-        if (rec.flags & GEO_SKIP) {   // (never primed: the look-ahead does not cross skipped groups)
+        rec_copy_async(myrecs, ip + 2 * nwarps, ngroups, slot + (sl == 0 ? 2 : sl - 1), lane);
+        const GeoRec* rec = slot + sl;
+        const int flags = rec->flags;
+        if (flags & GEO_SKIP) {   // (never primed: the look-ahead does not cross skipped groups)
             cp_async_commit(); cp_async_wait<0>(); __syncwarp();   // rare path: make sure the records fetched ahead have landed
             continue;
         }
-        const int gi = group_begin + ip;
         // ---- corners (gfdb.f90:943-948 weights in the reference's association) -------------------------
-        const bool single = rec.flags & GEO_SINGLE;
-        const float dix = rec.dix, diz = rec.diz;
-        const float wc0 = single ? 1.f : (1.f - dix) * (1.f - diz), wc1 = single ? 0.f : (1.f - dix) * diz,
-                    wc2 = single ? 0.f : dix * (1.f - diz), wc3 = single ? 0.f : dix * diz;
-        const NodeInfo n0 = rec.node[0], n1 = rec.node[1], n2 = rec.node[2], n3 = rec.node[3];
-        int q_first, q_last;
-        window_quads(n0, n1, n2, n3, q_first, q_last);
         // next group of this warp (for the look-ahead at the end of this group's last chunk)
-        const GeoRec& nrec = slot[(sl + 1) % 3];
-        const bool next_ok = (ip + nwarps < ngroups) && !(nrec.flags & GEO_SKIP);
-        // ---- taps: lane k prepares tap k (sparse_trace.f90:639-646) ---------------------------------------
-        const int tb = g.tap_begin[gi], tn = min(g.tap_count[gi], SYN_MAXTAPS);
-        int my_its = 0; float my_wl = 0.f, my_wr = 0.f;
-        if (lane < tn) {
-            const float time = A_(g.tbase[gi], taps.toff[tb + lane]);
-            const float rshift = D_(time, dt);
-            my_its = (int)floorf(rshift);
-            const float wr0 = S_(rshift, (float)my_its);
-            const float wl0 = S_(1.f, wr0);
-            const float wt = taps.wt[tb + lane];
-            my_wr = M_(wr0, wt); my_wl = M_(wl0, wt);
+        const GeoRec* nrec = slot + (sl == 2 ? 0 : sl + 1);
+        const bool next_ok = (ip + nwarps < ngroups) && !(nrec->flags & GEO_SKIP);
+        const int tt = rec->tt_begin, cls = rec->tap_cls, nstep = rec->nstep;
+        const unsigned rec_s = (unsigned)__cvta_generic_to_shared(rec);
+        int q_first = qf_n, q_last = ql_n;
+        if (!primed) {   // pipeline (re)start: first S items of this group
+            chunk_src(src, db.slabs, rec, -1, lane, Seq::comp(0), q_first, q_last);
+            issue_item(src, r0, Seq::step(0)); cp_async_commit();
+            issue_item(src, r1, Seq::step(1)); cp_async_commit();
+            issue_item(src, r2, Seq::step(2)); cp_async_commit();
         }
-        const float f1 = rec.f[0], f2 = rec.f[1], f3 = rec.f[2], f4 = rec.f[3], f5 = rec.f[4], f6 = rec.f[5];
-        const float cl = rec.cl, sl_ = rec.sl;
 
-        float4 carry1 = f4zero(), carry2 = f4zero(), carry3 = f4zero();   // quad left of the chunk (zeros left of the windows)
-        for (int q0 = q_first; q0 <= q_last; q0 += 32) {
-            const int q = q0 + lane;
-            const ChunkSrc cur = primed ? nxt : chunk_src(db.slabs, n0, n1, n2, n3, q, q_last);
-            const bool active = cur.active;
-            if (!primed) {   // pipeline (re)start: first S items of this chunk
-#pragma unroll
-                for (int j = 0; j < S; j++) { issue_item(cur, Seq::comp(j), ring_lane, (stage0 + j) % S); cp_async_commit(); }
-            }
-            const bool more = q0 + 32 <= q_last;
+        // lane k keeps tap k / step k of the group (tabulated by k_tap_table); broadcast by shuffles in the tap loops
+        int my_q = 0; float my_wl = 0.f, my_wr = 0.f;
+        {
+            const int ntap = (cls & 255) + ((cls >> 8) & 255) + ((cls >> 16) & 255) + ((cls >> 24) & 255);
+            if (lane < ntap) { const float4 tr = __ldg(taprec + tt + lane); my_q = __float_as_int(tr.x); my_wl = tr.y; my_wr = tr.z; }
+        }
+        float2 my_step = make_float2(0.f, 0.f);
+        if (lane < nstep) my_step = __ldg(stepw + tt + lane);
+
+        for (int q0 = q_first; q0 <= q_last; q0 += 31) {
+            const int q = q0 + lane - 1;   // lane 0: the quad left of the chunk, only read
+            const bool active = lane > 0 && q <= q_last;
+            const bool more = q0 + 31 <= q_last;
             const bool have_next = more || next_ok;
-            float4 A1 = f4zero(), A2 = f4zero(), A3 = f4zero(), Rr = f4zero(), Tt = f4zero();
+            // the group's weights are re-read from its record for every chunk rather than kept in registers across the tap loops
+            float wc0, wc1, wc2, wc3, f1, f2, f3, f4, f5, f6, cl, sl_;
+            {
+                const float4 ra = lds_f4(rec_s), rb = lds_f4(rec_s + 16), rc = lds_f4(rec_s + 32);
+                // corners (gfdb.f90:943-948 weights in the reference's association)
+                const bool single = flags & GEO_SINGLE;
+                const float dix = ra.z, diz = ra.w;
+                wc0 = single ? 1.f : (1.f - dix) * (1.f - diz); wc1 = single ? 0.f : (1.f - dix) * diz;
+                wc2 = single ? 0.f : dix * (1.f - diz); wc3 = single ? 0.f : dix * diz;
+                f1 = rb.x; f2 = rb.y; f3 = rb.z; f4 = rb.w; f5 = rc.x; f6 = rc.y; cl = rc.z; sl_ = rc.w;
+            }
+            Q2 A1 = q2_zero(), A2 = q2_zero(), A3 = q2_zero(), Rr = q2_zero(), Tt = q2_zero();
 #pragma unroll
-            for (int j = 0; j < NP; j++) {
-                const int stage = (stage0 + j) % S;
+            for (int j = 0; j < N; j++) {
+                const unsigned rs = (j % 3 == 0) ? r0 : (j % 3 == 1 ? r1 : r2);
                 cp_async_wait<S - 1>();    // item j has landed (this lane's own copies; no other lane reads them)
-                if (j < N && active) {
-                    const float4* src = ring + (stage * 4) * 32 + lane;
-                    const float4 t0 = src[0], t1 = src[32], t2 = src[64], t3 = src[96];
-                    float4 r = f4zero();
-                    fma4(r, wc0, t0); fma4(r, wc1, t1); fma4(r, wc2, t2); fma4(r, wc3, t3);   // a read clamped to quad 0 of a row returns the zeros left of the trace
+                {   // (lanes right of the windows combine whatever their slots hold; their quads go to the dummy quad below)
+                    const Q2 t0 = lds_q2<0>(rs), t1 = lds_q2<32 * 16>(rs), t2 = lds_q2<64 * 16>(rs), t3 = lds_q2<96 * 16>(rs);
+                    Q2 r = q2_zero();
+                    q2_fma(r, wc0, t0); q2_fma(r, wc1, t1); q2_fma(r, wc2, t2); q2_fma(r, wc3, t3);   // a read clamped to quad 0 of a row returns the zeros left of the trace
                     const int k = Seq::comp(j);   // constant after unrolling
-                    if (k == 0) fma4(Rr, f1, r);
-                    else if (k == 1) fma4(Rr, f2, r);
-                    else if (k == 2) fma4(Rr, f3, r);
-                    else if (k == 3) fma4(Tt, f4, r);
-                    else if (k == 4) fma4(Tt, f5, r);
-                    else if (k == 5) fma4(A3, f1 * sd, r);
-                    else if (k == 6) fma4(A3, f2 * sd, r);
-                    else if (k == 7) fma4(A3, f3 * sd, r);
-                    else if (k == 8) fma4(Rr, f6, r);
-                    else fma4(A3, f6 * sd, r);
+                    if (k == 0) q2_fma(Rr, f1, r);
+                    else if (k == 1) q2_fma(Rr, f2, r);
+                    else if (k == 2) q2_fma(Rr, f3, r);
+                    else if (k == 3) q2_fma(Tt, f4, r);
+                    else if (k == 4) q2_fma(Tt, f5, r);
+                    else if (k == 5) q2_fma(A3, f1 * sd, r);
+                    else if (k == 6) q2_fma(A3, f2 * sd, r);
+                    else if (k == 7) q2_fma(A3, f3 * sd, r);
+                    else if (k == 8) q2_fma(Rr, f6, r);
+                    else q2_fma(A3, f6 * sd, r);
                 }
-                // refill the slot just consumed: a later item of this chunk, nothing (padding), or one of the first
-                // S items of the next chunk
-                if (j + S < N) issue_item(cur, Seq::comp(j + S), ring_lane, stage);
-                else if (j + S >= NP && have_next) {
-                    const int jj = j + S - NP;     // constant after unrolling, < S
-                    if (jj == 0) {
-                        if (more) nxt = chunk_src(db.slabs, n0, n1, n2, n3, q + 32, q_last);
-                        else {
-                            const NodeInfo m0 = nrec.node[0], m1 = nrec.node[1], m2 = nrec.node[2], m3 = nrec.node[3];
-                            int qf, ql;
-                            window_quads(m0, m1, m2, m3, qf, ql);
-                            nxt = chunk_src(db.slabs, m0, m1, m2, m3, qf + lane, ql);
-                        }
+                // refill the slot just consumed: a later item of this chunk, or one of the first S items of the next chunk
+                if (j + S < N) {
+                    issue_item(src, rs, Seq::step(j + S));
+                } else if (have_next) {
+                    const int jj = j + S - N;     // constant after unrolling, < S
+                    if (jj == 0) {                // all items of this chunk are on their way: move the source on
+                        int qf, ql;
+                        chunk_src(src, db.slabs, more ? rec : nrec, more ? q0 + 31 : -1, lane, Seq::comp(0), qf, ql);
+                        if (!more) { qf_n = qf; ql_n = ql; }
                     }
-                    issue_item(nxt, Seq::comp(jj), ring_lane, stage);
+                    issue_item(src, rs, Seq::step(jj));
                 }
                 cp_async_commit();
             }
-            stage0 = (stage0 + N) % S;
+            {   // the next chunk's item 0 uses the slot after the one item N-1 used
+                const unsigned a = r0, b = r1, c = r2;
+                if (N % 3 == 1) { r0 = b; r1 = c; r2 = a; }
+                else if (N % 3 == 2) { r0 = c; r1 = a; r2 = b; }
+            }
             primed = have_next;
             if (H) {   // seismogram.f90:200-203: ar1 += cl*temp1 - sl*temp2; ar2 += cl*temp2 + sl*temp1
-                fma4(A1, cl, Rr); fma4(A1, -sl_, Tt);
-                fma4(A2, cl, Tt); fma4(A2, sl_, Rr);
+                q2_fma(A1, cl, Rr); q2_fma(A1, -sl_, Tt);
+                q2_fma(A2, cl, Tt); q2_fma(A2, sl_, Rr);
             }
-            // previous quad: lane-1; lane 0 takes the carry of the previous chunk
-            float4 P1, P2, P3;
-            if (H) { P1 = shfl_up4(A1, 1); P2 = shfl_up4(A2, 1); if (lane == 0) { P1 = carry1; P2 = carry2; } }
-            if (V) { P3 = shfl_up4(A3, 1); if (lane == 0) P3 = carry3; }
-            if (more) {
-                if (H) { carry1 = shfl4(A1, 31); carry2 = shfl4(A2, 31); }
-                if (V) carry3 = shfl4(A3, 31);
+            // previous quad: lane-1
+            u64 E1[4], G1[3], E2[4], G2[3], E3[4], G3[3];
+            if (H) {
+                Q2 P1, P2;
+                P1.lo = shfl_up_u64(A1.lo, 1); P1.hi = shfl_up_u64(A1.hi, 1); P2.lo = shfl_up_u64(A2.lo, 1); P2.hi = shfl_up_u64(A2.hi, 1);
+                make_pairs(P1, A1, E1, G1, nz); make_pairs(P2, A2, E2, G2, nz);
             }
-            for (int k = 0; k < tn; k++) {
-                const int its = __shfl_sync(0xffffffffu, my_its, k);
-                const float wl = __shfl_sync(0xffffffffu, my_wl, k), wr = __shfl_sync(0xffffffffu, my_wr, k);
-                const int qrel = q + (its >> 2) - baseq;
-                if (active && (unsigned)qrel < (unsigned)nq) {
-                    float4* a1 = acc + qrel; float4* a2 = a1 + nq; float4* a3 = a2 + nq;
-                    switch (its & 3) {
-                        case 0: tap_strips<0, H, V>(a1, a2, a3, P1, A1, P2, A2, P3, A3, wl, wr); break;
-                        case 1: tap_strips<1, H, V>(a1, a2, a3, P1, A1, P2, A2, P3, A3, wl, wr); break;
-                        case 2: tap_strips<2, H, V>(a1, a2, a3, P1, A1, P2, A2, P3, A3, wl, wr); break;
-                        default: tap_strips<3, H, V>(a1, a2, a3, P1, A1, P2, A2, P3, A3, wl, wr); break;
-                    }
-                }
-                __syncwarp();
+            if (V) {
+                Q2 P3;
+                P3.lo = shfl_up_u64(A3.lo, 1); P3.hi = shfl_up_u64(A3.hi, 1);
+                make_pairs(P3, A3, E3, G3, nz);
+            }
+            // ---- taps: four loops with a compile-time sub-quad shift ------------------------------------------
+            {
+                const int qb = active ? q - baseq : 0x40000000;
+                int t = 0;
+                tap_class<0, H, V>(cls & 255, t, my_q, my_wl, my_wr, qb, nq, acc, nq + 1, E1, G1, E2, G2, E3, G3);
+                tap_class<1, H, V>((cls >> 8) & 255, t, my_q, my_wl, my_wr, qb, nq, acc, nq + 1, E1, G1, E2, G2, E3, G3);
+                tap_class<2, H, V>((cls >> 16) & 255, t, my_q, my_wl, my_wr, qb, nq, acc, nq + 1, E1, G1, E2, G2, E3, G3);
+                tap_class<3, H, V>((cls >> 24) & 255, t, my_q, my_wl, my_wr, qb, nq, acc, nq + 1, E1, G1, E2, G2, E3, G3);
             }
             if (!more) {
-                // ---- end-value repetition (sparse_trace.f90:696-703): every sample right of the last
-                // processed quad gets (wl+wr)*A_end; recorded as a step at quad q_last+1+shift, prefix-summed
-                // at the end.  Lane c owns strip c: fixed order over the taps, no two lanes share a word.
-                const int src = q_last - q0;
-                const float e1 = H ? __shfl_sync(0xffffffffu, A1.w, src) : 0.f;
-                const float e2 = H ? __shfl_sync(0xffffffffu, A2.w, src) : 0.f;
-                const float e3 = V ? __shfl_sync(0xffffffffu, A3.w, src) : 0.f;
-                const float ae = lane == 0 ? e1 : (lane == 1 ? e2 : e3);
-                const bool mine = lane < 3 && (lane < 2 ? H : V);
-                for (int k = 0; k < tn; k++) {
-                    const int its = __shfl_sync(0xffffffffu, my_its, k);
-                    const float w = __shfl_sync(0xffffffffu, my_wl, k) + __shfl_sync(0xffffffffu, my_wr, k);
-                    const int qs = q_last + 1 + (its >> 2) - baseq;
-                    if (mine && qs >= 0 && qs < nq) step[lane * nq + qs] += w * ae;
+                // ---- end-value repetition (sparse_trace.f90:696-703): every sample right of the last processed quad gets
+                // (wl+wr)*A_end; recorded as a step at quad q_last+1+shift, prefix-summed at the end.  Lane j owns the j-th
+                // distinct quad shift of the group: no two lanes share a word.
+                const int srcl = q_last - q0 + 1;
+                float d0, e1 = 0.f, e2 = 0.f, e3 = 0.f;
+                if (H) { unpk2(A1.hi, d0, e1); unpk2(A2.hi, d0, e2); e1 = __shfl_sync(0xffffffffu, e1, srcl); e2 = __shfl_sync(0xffffffffu, e2, srcl); }
+                if (V) { unpk2(A3.hi, d0, e3); e3 = __shfl_sync(0xffffffffu, e3, srcl); }
+                (void)d0;
+                const int qs = q_last + 1 + __float_as_int(my_step.x) - baseq;
+                if (lane < nstep && (unsigned)qs < (unsigned)nq) {
+                    if (H) { step[qs] += my_step.y * e1; step[nq + qs] += my_step.y * e2; }
+                    if (V) step[2 * nq + qs] += my_step.y * e3;
                 }
             }
         }
@@ -608,27 +704,17 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
     cp_async_wait<0>();
 }
 
-// =================================================================================================
-// K3: synthesis.  One CTA per (candidate, receiver); every warp owns a private set of three
-// accumulator strips (displacement_ar(1), displacement_ar(2), vertical) in shared memory and works
-// through its share of the groups.  Per group and 128-sample chunk a lane owns one aligned sample
-// quad: 4 corners x ng rows are staged HBM -> shared memory with 128-bit cp.async copies (a ring of
-// SYN_STAGES components per warp that keeps running across chunk and group boundaries), combined
-// bilinearly (gfdb.f90:943-948), weighted with the moment-tensor/azimuth factors (make_weights
-// seismogram.f90:316-336, precomputed by k_geometry), rotated by the centroid's back-azimuth
-// difference (:196-203), and then added nt times with the sample shift and linear sub-sample
-// interpolation of trace_multiply_add (sparse_trace.f90:639-705).  The "last sample repeats for
-// ever" rule (:696-703) becomes a step per (group, tap) that is prefix-summed once at the end.
-// =================================================================================================
 __global__ void __launch_bounds__(256, 2) k_synth(GfdbDev db, const ReceiverDev* __restrict__ rcv, int nrcv,
-                                                   const CandDev* __restrict__ cands, GroupSoA g, TapSoA taps, int ngroups_total,
-                                                   int interpolate, int xunder, int zunder, const GeoRec* __restrict__ recs,
+                                                   const CandDev* __restrict__ cands, GroupSoA g, const GeoRec* __restrict__ recs,
                                                    size_t rec_stride, const PairHdr* __restrict__ hdrs, int nq_alloc, int margin_q,
                                                    float* __restrict__ seis, size_t seis_stride /* floats per component row */,
-                                                   SeisHdr* __restrict__ shdrs) {
+                                                   SeisHdr* __restrict__ shdrs, float neg_zero /* -0.0f, see make_pairs */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int pair = blockIdx.x;
-    const int b = pair / nrcv, ir = pair % nrcv;
+    // CTAs that run at the same time work on the same receiver for neighbouring candidates: candidates of a grid search
+    // that share (part of) their sub-fault geometry then find each other's Green's function rows in L2
+    const int ncand = gridDim.x / nrcv;
+    const int ir = blockIdx.x / ncand, b = blockIdx.x % ncand;
+    const int pair = b * nrcv + ir;
     const ReceiverDev& R = rcv[ir];
     const CandDev cand = cands[b];
     const PairHdr H = hdrs[pair];
@@ -640,27 +726,30 @@ __global__ void __launch_bounds__(256, 2) k_synth(GfdbDev db, const ReceiverDev*
     }
     const int base = floor4(H.out0) - 4 * margin_q;   // room on the left for the rise-time fold (k_fold)
     const int baseq = base >> 2;
-    const int nq = nq_alloc;   // quads per accumulator strip
-    // shared memory: per warp 3 strips of nq float4 + 3 step rows of nq floats, 3 group records, the cp.async ring
+    const int nq = nq_alloc;    // quads per accumulator strip
+    const int nqs = nq + 1;     // + the dummy quad
+    // shared memory: per warp 3 strips of nqs float4 + 3 step rows of nq floats, 3 group records, the cp.async ring
     float4* acc_all = reinterpret_cast<float4*>(smem_raw);
-    float* step_all = reinterpret_cast<float*>(acc_all + (size_t)nwarps * 3 * nq);
-    float4* acc = acc_all + (size_t)warp * 3 * nq;
+    float* step_all = reinterpret_cast<float*>(acc_all + (size_t)nwarps * 3 * nqs);
+    float4* acc = acc_all + (size_t)warp * 3 * nqs;
     float* step = step_all + (size_t)warp * 3 * nq;
-    for (int i = lane; i < 3 * nq; i += 32) { acc[i] = f4zero(); step[i] = 0.f; }
+    for (int i = lane; i < 3 * nqs; i += 32) acc[i] = f4zero();
+    for (int i = lane; i < 3 * nq; i += 32) step[i] = 0.f;
     __syncwarp();
 
     const bool need_h = (R.ja | R.jr | R.jn | R.je) != 0;
     const bool need_v = R.jd != 0;
     const bool ng10 = db.ng == 10;
     const GeoRec* myrecs = recs + (size_t)pair * rec_stride;
-    (void)ngroups_total; (void)interpolate; (void)xunder; (void)zunder;
     // 16-byte aligned carve-up behind the step rows (3*nq floats per warp may end on an 8-byte boundary)
     unsigned char* tail = reinterpret_cast<unsigned char*>(step_all + (size_t)nwarps * 3 * nq);
     tail += (16 - (reinterpret_cast<size_t>(tail) & 15)) & 15;
     GeoRec* slot = reinterpret_cast<GeoRec*>(tail) + 3 * warp;
     float4* ring = reinterpret_cast<float4*>(reinterpret_cast<GeoRec*>(tail) + 3 * nwarps) + (size_t)warp * SYN_STAGES * 4 * 32;
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
 
-#define KIWI_SYNTH(HH, VV, NG) synth_warp<HH, VV, NG>(db, myrecs, cand.ngroups, cand.group_begin, g, taps, R.sd, acc, step, nq, baseq, slot, ring, warp, nwarps, lane)
+#define KIWI_SYNTH(HH, VV, NG) \
+    synth_warp<HH, VV, NG>(db, myrecs, cand.ngroups, g.taprec, g.stepw, R.sd, reinterpret_cast<ulonglong2*>(acc), step, nq, baseq, slot, ring_s, warp, nwarps, lane, neg_zero)
     if (need_h && need_v) { if (ng10) KIWI_SYNTH(true, true, true); else KIWI_SYNTH(true, true, false); }
     else if (need_h) { if (ng10) KIWI_SYNTH(true, false, true); else KIWI_SYNTH(true, false, false); }
     else if (need_v) { if (ng10) KIWI_SYNTH(false, true, true); else KIWI_SYNTH(false, true, false); }
@@ -668,14 +757,18 @@ __global__ void __launch_bounds__(256, 2) k_synth(GfdbDev db, const ReceiverDev*
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     // ---- reduce the warps' strips (fixed order: deterministic) -------------------------------------
-    for (int i = threadIdx.x; i < 3 * nq; i += blockDim.x) {
-        float4 s = acc_all[i]; float st = step_all[i];
+    for (int i = threadIdx.x; i < 3 * nqs; i += blockDim.x) {
+        float4 s = acc_all[i];
         for (int w = 1; w < nwarps; w++) {
-            const float4 v = acc_all[(size_t)w * 3 * nq + i];
+            const float4 v = acc_all[(size_t)w * 3 * nqs + i];
             s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-            st += step_all[(size_t)w * 3 * nq + i];
         }
-        acc_all[i] = s; step_all[i] = st;
+        acc_all[i] = s;
+    }
+    for (int i = threadIdx.x; i < 3 * nq; i += blockDim.x) {
+        float st = step_all[i];
+        for (int w = 1; w < nwarps; w++) st += step_all[(size_t)w * 3 * nq + i];
+        step_all[i] = st;
     }
     __syncthreads();
     // inclusive prefix sum of the steps over quads, one warp per strip
@@ -694,8 +787,8 @@ __global__ void __launch_bounds__(256, 2) k_synth(GfdbDev db, const ReceiverDev*
     __syncthreads();
     // ---- components: signs and the (away,right) -> (north,east) rotation, seismogram.f90:256-289 ----
     const float* a1 = reinterpret_cast<const float*>(acc_all);
-    const float* a2 = a1 + (size_t)4 * nq;
-    const float* a3 = a2 + (size_t)4 * nq;
+    const float* a2 = a1 + (size_t)4 * nqs;
+    const float* a3 = a2 + (size_t)4 * nqs;
     const float* st1 = step_all; const float* st2 = step_all + nq; const float* st3 = step_all + 2 * nq;
     const int nsamp = 4 * nq;
     const int s12lo = min(H.s1lo, H.s2lo), s12hi = max(H.s1hi, H.s2hi);
@@ -1516,6 +1609,9 @@ void launch_group_tap_range(GroupSoA g, TapSoA taps, float dt, int gbegin, int g
     int n = gend - gbegin;
     if (n > 0) k_group_tap_range<<<(n + 127) / 128, 128, 0, st>>>(g, taps, dt, gbegin, gend);
 }
+void launch_tap_table(GroupSoA g, TapSoA taps, float dt, int ngroups, cudaStream_t st) {
+    if (ngroups > 0) k_tap_table<<<(ngroups + 7) / 8, 256, 0, st>>>(g, taps, dt, ngroups);
+}
 void launch_expand_centroids(CandDev cand, GroupSoA g, TapSoA taps, int ngroups_total, float* d_table, int cap, cudaStream_t st) {
     k_expand_centroids<<<(cand.ngroups + 127) / 128, 128, 0, st>>>(cand, g, taps, ngroups_total, d_table, cap);
 }
@@ -1526,18 +1622,16 @@ void launch_geometry(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev
     k_geometry<<<ncand * nrcv, threads, 0, st>>>(db, rcv, nrcv, cands, g, ngroups_total, interpolate, xunder, zunder, recs, rec_stride, hdrs, tmax);
 }
 size_t synth_smem_bytes(int nwarps, int nq) {
-    return (size_t)nwarps * 3 * nq * (sizeof(float4) + sizeof(float)) + 16 + (size_t)nwarps * 3 * sizeof(GeoRec) +
+    return (size_t)nwarps * 3 * ((nq + 1) * sizeof(float4) + nq * sizeof(float)) + 16 + (size_t)nwarps * 3 * sizeof(GeoRec) +
            (size_t)nwarps * SYN_STAGES * 4 * 32 * sizeof(float4);
 }
-cudaError_t launch_synth(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, TapSoA taps,
-                         int ngroups_total, int interpolate, int xunder, int zunder, const GeoRec* recs, size_t rec_stride,
-                         const PairHdr* hdrs, int nq_alloc, int margin_q, int nwarps, float* seis, size_t seis_stride, SeisHdr* shdrs,
-                         cudaStream_t st) {
+cudaError_t launch_synth(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, const GeoRec* recs,
+                         size_t rec_stride, const PairHdr* hdrs, int nq_alloc, int margin_q, int nwarps, float* seis, size_t seis_stride,
+                         SeisHdr* shdrs, cudaStream_t st) {
     size_t smem = synth_smem_bytes(nwarps, nq_alloc);
     cudaError_t e = cudaFuncSetAttribute(k_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_synth<<<ncand * nrcv, nwarps * 32, smem, st>>>(db, rcv, nrcv, cands, g, taps, ngroups_total, interpolate, xunder, zunder, recs,
-                                                    rec_stride, hdrs, nq_alloc, margin_q, seis, seis_stride, shdrs);
+    k_synth<<<ncand * nrcv, nwarps * 32, smem, st>>>(db, rcv, nrcv, cands, g, recs, rec_stride, hdrs, nq_alloc, margin_q, seis, seis_stride, shdrs, -0.0f);
     return cudaGetLastError();
 }
 void launch_misfit_td(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, const float* seis, size_t seis_stride,

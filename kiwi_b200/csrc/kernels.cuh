@@ -12,18 +12,19 @@ struct BilatCand {
     float mhat[6];      // m_rot/np: (1,1) (2,2) (3,3) (1,2) (1,3) (2,3)
     int nx, ny, nt;
     int group_begin, tap_begin;
+    int tt_begin;       // first shift-table entry of the candidate (ngroups x nt entries)
 };
 
 void launch_bilat_groups(const BilatCand* d_cands, int ncand, GroupSoA g, TapSoA taps, float dt, int ngroups_total, cudaStream_t st);
 void launch_group_tap_range(GroupSoA g, TapSoA taps, float dt, int gbegin, int gend, cudaStream_t st);
+void launch_tap_table(GroupSoA g, TapSoA taps, float dt, int ngroups, cudaStream_t st);
 void launch_expand_centroids(CandDev cand, GroupSoA g, TapSoA taps, int ngroups_total, float* d_table, int cap, cudaStream_t st);
 void launch_geometry(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, int ngroups_total,
                      int interpolate, int xunder, int zunder, GeoRec* recs, size_t rec_stride, PairHdr* hdrs, int* tmax, cudaStream_t st);
 size_t synth_smem_bytes(int nwarps, int nq);
-cudaError_t launch_synth(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, TapSoA taps,
-                         int ngroups_total, int interpolate, int xunder, int zunder, const GeoRec* recs, size_t rec_stride,
-                         const PairHdr* hdrs, int nq_alloc, int margin_q, int nwarps, float* seis, size_t seis_stride, SeisHdr* shdrs,
-                         cudaStream_t st);
+cudaError_t launch_synth(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, const GeoRec* recs,
+                         size_t rec_stride, const PairHdr* hdrs, int nq_alloc, int margin_q, int nwarps, float* seis, size_t seis_stride,
+                         SeisHdr* shdrs, cudaStream_t st);
 cudaError_t launch_fold(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, float* seis, size_t seis_stride, SeisHdr* shdrs,
                         float dt, cudaStream_t st);
 void launch_misfit_td(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, const float* seis, size_t seis_stride,

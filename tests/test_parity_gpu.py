@@ -208,19 +208,25 @@ FILTER = ([0.2, 0.5, 2.0, 3.0], [0, 1, 1, 0])      # band-pass, Hz (shape of pyt
 TAPER = ([1.0, 1.6, 4.0, 5.2], [0, 1, 1, 0])
 
 
-def _spectral_setup(norm, taper, filt, comps=COMPS6):
+def _spectral_setup(norm, taper, filt, comps=COMPS6, wide=False):
     g, o = engines(sc.small_db(), comps)
     ncomps = [len(c) for c in comps]
     o.eval_sources("bilateral", sc.BILAT_SMALL)
-    sc.set_refs_from(o, [g, o], ncomps)
-    for e in (g, o):
+    es = [g, o]
+    if wide:   # the restatement with strips carried in double: arbiter where the fp32 path's own rounding noise is near the bar
+        lat, lon, dep = sc.small_receivers(len(comps))
+        w = OracleEngine(wide=True)
+        sc.setup(w, sc.small_db(), lat, lon, dep, comps)
+        es.append(w)
+    sc.set_refs_from(o, es, ncomps)
+    for e in es:
         e.set_misfit_method(norm)
         if taper:
             for ir in range(1, len(comps) + 1):
                 e.set_misfit_taper(ir, *TAPER)
         if filt:
             e.set_misfit_filter(*FILTER)
-    return g, o
+    return es
 
 
 @pytest.mark.parametrize("norm", ["ampspec_l2norm", "ampspec_l1norm"])
@@ -243,13 +249,19 @@ def test_amplitude_spectrum_misfits(norm, taper, filt):
 @pytest.mark.parametrize("taper", [False, True])
 def test_filtered_time_domain_misfits(norm, taper):
     """make_spectrum_filtered / make_array_filtered (comparator.f90:1217-1263): r2c -> filter -> c2r -> norm"""
-    g, o = _spectral_setup(norm, taper, True)
+    g, o, w = _spectral_setup(norm, taper, True, wide=True)
     p = _candidates()
     mg, sg = g.eval_sources("bilateral", p)
     mo, so = o.eval_sources("bilateral", p)
-    assert not sg.any() and not so.any()
-    tol = misfit_tol(mo)
-    assert np.all(np.abs(mg - mo) <= tol), np.abs((mg - mo) / tol).max()
+    mw, sw = w.eval_sources("bilateral", p)
+    assert not sg.any() and not so.any() and not sw.any()
+    # candidate 0 is the source the references were made from (x 1.07): m = 0.065 nf is a difference of nearly equal
+    # traces, and without a taper the filter spreads every rounding of the synthetic over the whole padded span.  The fp32
+    # restatement itself sits at ~1e-5 of its double-accumulated twin there, so the bar is 1e-5 against the latter and
+    # twice the fp32 path's own distance against the former.
+    tol = misfit_tol(mw)
+    assert np.all(np.abs(mg - mw) <= tol), np.abs((mg - mw) / tol).max()
+    assert np.all(np.abs(mg - mo) <= np.maximum(tol, 2.0 * np.abs(mo - mw))), np.abs((mg - mo) / tol).max()
 
 
 @pytest.mark.parametrize("norm", ["floating_l2norm", "floating_l1norm"])
