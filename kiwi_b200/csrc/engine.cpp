@@ -119,7 +119,7 @@ struct kiwi_ctx {
     std::string prep_error;                  // message of the last failed discretisation
     bool mt_grid_enabled = true;             // point moment-tensor grid searches go through the tcgen05 contraction
     DevBuf d_map, d_status_out;
-    DevBuf d_taprec, d_stepw;     // shift tables of the current batch (k_tap_table)
+    DevBuf d_taprec;              // shift table of the current batch (k_tap_table)
     bool dedup_enabled = true;               // candidates that differ only in the moment share one synthesis
     DevBuf d_mtlocs, d_mts, d_candof, d_orc, d_orw, d_obw, d_oout, d_obest, d_obestv;
     int last_eval_ns = 0;                    // candidates whose misfit block sits in d_out (kiwi_eval_sources)
@@ -390,9 +390,8 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         const int Galloc = std::max(G, 1), Talloc = std::max(Tp, 1);
         CU_OK(c->d_cands.ensure(sizeof(CandDev) * nc));
         CU_OK(c->d_gf.ensure(sizeof(float) * 11 * (size_t)Galloc));
-        CU_OK(c->d_gi.ensure(sizeof(int) * 7 * (size_t)Galloc));
-        CU_OK(c->d_taprec.ensure(sizeof(float4) * ((size_t)TT + 1)));
-        CU_OK(c->d_stepw.ensure(sizeof(float2) * ((size_t)TT + 1)));
+        CU_OK(c->d_gi.ensure(sizeof(int) * 6 * (size_t)Galloc));
+        CU_OK(c->d_taprec.ensure(sizeof(float4) * 2 * ((size_t)TT + 1)));
         CU_OK(c->d_tf.ensure(sizeof(float) * 2 * (size_t)Talloc));
         GroupSoA g;
         float* gf = c->d_gf.as<float>();
@@ -400,8 +399,8 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         g.gw = gf + 10 * (size_t)Galloc;
         int* gi = c->d_gi.as<int>();
         g.tap_begin = gi; g.tap_count = gi + Galloc; g.its_min = gi + 2 * (size_t)Galloc; g.its_max = gi + 3 * (size_t)Galloc;
-        g.tt_begin = gi + 4 * (size_t)Galloc; g.tap_cls = gi + 5 * (size_t)Galloc; g.nstep = gi + 6 * (size_t)Galloc;
-        g.taprec = c->d_taprec.as<float4>(); g.stepw = c->d_stepw.as<float2>();
+        g.tt_begin = gi + 4 * (size_t)Galloc; g.nstep = gi + 5 * (size_t)Galloc;
+        g.taprec = c->d_taprec.as<float4>();
         TapSoA taps; taps.toff = c->d_tf.as<float>(); taps.wt = taps.toff + Talloc;
         std::vector<float> toff(Talloc, 0.f), wt(Talloc, 0.f);
         for (int i = 0; i < nc; i++) {
@@ -437,7 +436,7 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         } else {   // groups defined on the host: the single group of a point moment tensor
                    // (source_moment_tensor.f90:256-263), the sub-faults of an eikonal source (source_eikonal.f90:684-707)
             std::vector<float> hf((size_t)11 * Galloc, 0.f);
-            std::vector<int> hi((size_t)7 * Galloc, 0);
+            std::vector<int> hi((size_t)6 * Galloc, 0);
             for (int i = 0; i < nc; i++) {
                 const kh::SourcePrep& sp = prep[b0 + i];
                 if (sp.ngroups == 0) continue;
@@ -768,7 +767,7 @@ void kiwi_destroy(kiwi_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->d_slabs, &c->d_nodes, &c->d_tspan, &c->d_rcv, &c->d_refdata, &c->d_taper, &c->d_cands, &c->d_bilat, &c->d_gf, &c->d_gi,
-                      &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift, &c->d_map, &c->d_status_out, &c->d_taprec, &c->d_stepw, &c->d_mtlocs, &c->d_mts, &c->d_candof, &c->d_orc, &c->d_orw, &c->d_obw, &c->d_oout, &c->d_obest, &c->d_obestv})
+                      &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift, &c->d_map, &c->d_status_out, &c->d_taprec, &c->d_mtlocs, &c->d_mts, &c->d_candof, &c->d_orc, &c->d_orw, &c->d_obw, &c->d_oout, &c->d_obest, &c->d_obestv})
         b->release();
     c->h_stage.release(); c->h_out.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);

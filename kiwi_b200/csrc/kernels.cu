@@ -92,9 +92,11 @@ __global__ void k_group_tap_range(GroupSoA g, TapSoA taps, float dt, int gbegin,
 
 // Shift table: one warp per group, lane k = tap k.  What trace_multiply_add derives from the centroid time
 // (sparse_trace.f90:639-646: rshift = time/dt, its = floor(rshift), wr = rshift-its, wl = 1-wr, both times the
-// weight) does not depend on the receiver, so it is tabulated once per candidate.  Entries are ordered by
-// (its mod 4) so that k_synth runs four loops with a compile-time sub-quad shift; taps that repeat their end
-// value from the same quad on (:696-703) are merged into one step entry (summed in tap order).
+// weight) does not depend on the receiver, so it is tabulated once per candidate -- per distinct quad shift
+// m = its div 4 of the group, because the taps of one m update the same output quad of a lane:
+//     out(4(q+m)+j) += sum_t h[t] * A(4q+j-t),  t = 0..4,   h[s] += wl, h[s+1] += wr for a tap with its mod 4 = s
+// (summed in tap order), so k_synth reads and writes that quad once instead of once per tap.  W = sum of (wl+wr):
+// the step every sample right of the group's window receives (:696-703).
 __global__ void __launch_bounds__(256) k_tap_table(GroupSoA g, TapSoA taps, float dt, int ngroups) {
     const int gi = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (gi >= ngroups) return;
@@ -112,27 +114,27 @@ __global__ void __launch_bounds__(256) k_tap_table(GroupSoA g, TapSoA taps, floa
     }
     const int cls = its & 3, qoff = its >> 2;
     const unsigned lt = (1u << lane) - 1u;
-    int base = 0, pos = 0, packed = 0;
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-        const unsigned m = __ballot_sync(0xffffffffu, on && cls == c);
-        if (cls == c) pos = base + __popc(m & lt);
-        base += __popc(m);
-        packed |= __popc(m) << (8 * c);
-    }
-    if (on) g.taprec[tt + pos] = make_float4(__int_as_float(qoff), wl, wr, 0.f);
-    // steps: leader = first tap of every distinct quad shift
-    const float w = wl + wr;
-    float W = 0.f; bool leader = on;
+    // leader = first tap of every distinct quad shift; it gathers the taps of its quad shift in tap order
+    float h[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, W = 0.f;
+    bool leader = on;
     for (int j = 0; j < tn; j++) {
-        const float wj = __shfl_sync(0xffffffffu, w, j);
-        const int qj = __shfl_sync(0xffffffffu, qoff, j);
-        if (qj == qoff) { W += wj; if (j < lane) leader = false; }
+        const float wlj = __shfl_sync(0xffffffffu, wl, j), wrj = __shfl_sync(0xffffffffu, wr, j);
+        const int qj = __shfl_sync(0xffffffffu, qoff, j), sj = __shfl_sync(0xffffffffu, cls, j);
+        if (qj == qoff) {
+            if (j < lane) leader = false;
+#pragma unroll
+            for (int t = 0; t < 5; t++) { if (sj == t) h[t] += wlj; if (sj + 1 == t) h[t] += wrj; }
+            W += wlj + wrj;
+        }
     }
     const unsigned lm = __ballot_sync(0xffffffffu, leader);
-    if (leader) g.stepw[tt + __popc(lm & lt)] = make_float2(__int_as_float(qoff), W);
+    if (leader) {
+        float4* e = g.taprec + 2 * ((size_t)tt + __popc(lm & lt));
+        e[0] = make_float4(__int_as_float(qoff), h[0], h[1], h[2]);
+        e[1] = make_float4(h[3], h[4], W, 0.f);
+    }
     const int lo = warp_min_i(on ? its : INT_MAX), hi = warp_max_i(on ? its : INT_MIN);
-    if (lane == 0) { g.tap_cls[gi] = packed; g.nstep[gi] = __popc(lm); g.its_min[gi] = lo; g.its_max[gi] = hi; }
+    if (lane == 0) { g.nstep[gi] = __popc(lm); g.its_min[gi] = lo; g.its_max[gi] = hi; }
 }
 
 // expand the SoA of one candidate back into the reference's centroid table (test/inspection only)
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(256) k_geometry(GfdbDev db, const ReceiverDev*
                 rec.f[3] = 0.5f * (m[1] - m[0]) * s2a + m[3] * c2a;
                 rec.f[4] = m[5] * ca - m[4] * sa;
                 rec.f[5] = m[0] * (sa * sa) + m[1] * (ca * ca) - m[3] * s2a;
-                rec.tt_begin = g.tt_begin[gi]; rec.tap_cls = g.tap_cls[gi]; rec.nstep = g.nstep[gi];
+                rec.tt_begin = g.tt_begin[gi]; rec.nstep = g.nstep[gi]; rec.pad[0] = 0;
             }
             const float x = (float)dist;
             const float z = S_(depth, R.depth);
@@ -414,6 +416,16 @@ __device__ __forceinline__ Q2 lds_q2(unsigned addr) {
     asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+%3];" : "=l"(r.lo), "=l"(r.hi) : "r"(addr), "n"(OFF) : "memory");
     return r;
 }
+// the four corner quads of one ring slot; lanes with on == 0 do not read (and keep what t0..t3 held)
+__device__ __forceinline__ void lds_ring(unsigned addr, int on, Q2& t0, Q2& t1, Q2& t2, Q2& t3) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %9, 0;\n\t"
+        "@p ld.shared.v2.b64 {%0, %1}, [%8];\n\t@p ld.shared.v2.b64 {%2, %3}, [%8+512];\n\t"
+        "@p ld.shared.v2.b64 {%4, %5}, [%8+1024];\n\t@p ld.shared.v2.b64 {%6, %7}, [%8+1536];\n\t}"
+        : "+l"(t0.lo), "+l"(t0.hi), "+l"(t1.lo), "+l"(t1.hi), "+l"(t2.lo), "+l"(t2.hi), "+l"(t3.lo), "+l"(t3.hi)
+        : "r"(addr), "r"(on)
+        : "memory");
+}
 __device__ __forceinline__ float4 lds_f4(unsigned addr) {
     float4 r;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
@@ -459,15 +471,15 @@ struct CompSeq {
 
 // where a lane reads a chunk from: for the four corners the address of the lane's quad in the row of the
 // component that is issued next (clamped into each window: quad 0 holds zeros, the last quad the continuation)
-// and the row strides in bytes
+// and the row strides in quads
 struct ChunkSrc {
     const char *p0, *p1, *p2, *p3;
     unsigned s0, s1, s2, s3;
     bool active;
 };
-__device__ __forceinline__ const char* corner_ptr(const float* slabs, const NodeInfo& n, int q, int comp0, unsigned& stride_bytes) {
+__device__ __forceinline__ const char* corner_ptr(const float* slabs, const NodeInfo& n, int q, int comp0, unsigned& stride_quads) {
     const int nq = n.wn >> 2;
-    stride_bytes = (unsigned)nq << 4;
+    stride_quads = (unsigned)nq;
     const int qi = min(max(q - (n.w0 >> 2), 0), nq - 1) + comp0 * nq;
     return reinterpret_cast<const char*>(slabs + n.off) + ((size_t)(unsigned)qi << 4);
 }
@@ -491,8 +503,9 @@ __device__ __forceinline__ void chunk_src(ChunkSrc& c, const float* slabs, const
     c.p3 = corner_ptr(slabs, n3, q, comp0, c.s3);
     c.active = q <= q_last;
 }
-__device__ __forceinline__ void advance_rows(const char*& p, unsigned stride_bytes, int rows) {
-    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(p) : "r"(stride_bytes), "r"((unsigned)rows));
+// (multiply-add on the whole 64-bit pointer: the result is a register pair the copy can use as it is)
+__device__ __forceinline__ void advance_rows(const char*& p, unsigned stride_quads, int rows) {
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(p) : "r"(stride_quads), "r"(16u * (unsigned)rows));
 }
 // one item = the next GF component of the chunk -> ring slot (4 corners x 32 lanes x 16 bytes); the source then moves
 // on by `dcomp` rows
@@ -508,34 +521,22 @@ __device__ __forceinline__ void issue_item(ChunkSrc& c, unsigned slot, int dcomp
     }
 }
 
-// out quad (+)= wl * A(y - its) + wr * A(y - its - 1), S = its mod 4.
-// E[i] = samples 2i, 2i+1 of the eight samples (previous quad, own quad); G[i] = samples 2i+1, 2i+2
-template <int S>
-__device__ __forceinline__ void tap_fma(ulonglong2& o, const u64* E, const u64* G, float wl, float wr) {
-    if (S == 0) { ffma2(o.x, wl, E[2]); ffma2(o.y, wl, E[3]); ffma2(o.x, wr, G[1]); ffma2(o.y, wr, G[2]); }
-    else if (S == 1) { ffma2(o.x, wl, G[1]); ffma2(o.y, wl, G[2]); ffma2(o.x, wr, E[1]); ffma2(o.y, wr, E[2]); }
-    else if (S == 2) { ffma2(o.x, wl, E[1]); ffma2(o.y, wl, E[2]); ffma2(o.x, wr, G[0]); ffma2(o.y, wr, G[1]); }
-    else { ffma2(o.x, wl, G[0]); ffma2(o.y, wl, G[1]); ffma2(o.x, wr, E[0]); ffma2(o.y, wr, E[1]); }
-}
-// the taps of one sub-quad shift class (sparse_trace.f90:647-695).  A quad that falls outside the strips, or belongs to
-// a lane right of the windows (qb huge), goes to the dummy quad behind each strip.
-template <int S, bool H, bool V>
-__device__ __forceinline__ void tap_class(int cnt, int& t, int my_q, float my_wl, float my_wr, int qb, int nq, ulonglong2* __restrict__ acc, int nqs,
-                                          const u64* E1, const u64* G1, const u64* E2, const u64* G2, const u64* E3, const u64* G3) {
-    for (int k = 0; k < cnt; k++, t++) {
-        const int qoff = __shfl_sync(0xffffffffu, my_q, t);
-        const float wl = __shfl_sync(0xffffffffu, my_wl, t), wr = __shfl_sync(0xffffffffu, my_wr, t);
-        const int qrel = qb + qoff;
-        const unsigned idx = (unsigned)qrel < (unsigned)nq ? (unsigned)qrel : (unsigned)nq;
-        ulonglong2 *p1 = acc + idx, *p2 = p1 + nqs, *p3 = p2 + nqs;
-        if (H) {
-            // (one quad at a time: with two quads in flight the assembler renames the second and copies it back for the store)
-            ulonglong2 o1 = *p1; tap_fma<S>(o1, E1, G1, wl, wr); *p1 = o1;
-            ulonglong2 o2 = *p2; tap_fma<S>(o2, E2, G2, wl, wr); *p2 = o2;
-        }
-        if (V) { ulonglong2 o3 = *p3; tap_fma<S>(o3, E3, G3, wl, wr); *p3 = o3; }
-        __syncwarp();
-    }
+// out quad(q + m) (+)= sum_t h[t] * A(4q + j - t): E[i] = samples 2i, 2i+1 of the eight samples (previous quad, own quad),
+// G[i] = samples 2i+1, 2i+2.  Lanes without a quad of their own (right of the windows, lane 0, outside the strips) read
+// a quad next to their neighbours' (no extra wavefront) and do not store.
+__device__ __forceinline__ void rmw_quad(unsigned addr, int ok, const u64* E, const u64* G, float h0, float h1, float h2, float h3, float h4) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 a0, a1, w;\n\t"
+        "setp.ne.s32 p, %1, 0;\n\t"
+        "ld.shared.v2.b64 {a0, a1}, [%0];\n\t"
+        "mov.b64 w, {%2, %2};\n\tfma.rn.f32x2 a0, w, %9, a0;\n\tfma.rn.f32x2 a1, w, %10, a1;\n\t"
+        "mov.b64 w, {%3, %3};\n\tfma.rn.f32x2 a0, w, %12, a0;\n\tfma.rn.f32x2 a1, w, %13, a1;\n\t"
+        "mov.b64 w, {%4, %4};\n\tfma.rn.f32x2 a0, w, %8, a0;\n\tfma.rn.f32x2 a1, w, %9, a1;\n\t"
+        "mov.b64 w, {%5, %5};\n\tfma.rn.f32x2 a0, w, %11, a0;\n\tfma.rn.f32x2 a1, w, %12, a1;\n\t"
+        "mov.b64 w, {%6, %6};\n\tfma.rn.f32x2 a0, w, %7, a0;\n\tfma.rn.f32x2 a1, w, %8, a1;\n\t"
+        "@p st.shared.v2.b64 [%0], {a0, a1};\n\t}"
+        ::"r"(addr), "r"(ok), "f"(h0), "f"(h1), "f"(h2), "f"(h3), "f"(h4), "l"(E[0]), "l"(E[1]), "l"(E[2]), "l"(E[3]), "l"(G[0]), "l"(G[1]), "l"(G[2])
+        : "memory");
 }
 // nz = -0.0f handed in as a kernel argument: x + nz == x bit for bit, but the assembler cannot see that and so gives the
 // odd pairs registers of their own once per chunk, instead of re-assembling them from the halves of E at every use
@@ -550,7 +551,7 @@ __device__ __forceinline__ void make_pairs(const Q2& P, const Q2& A, u64* E, u64
 // One warp works through its share of the groups of one (candidate, receiver) pair.
 template <bool H, bool V, bool NG10>
 __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __restrict__ myrecs, int ngroups, const float4* __restrict__ taprec,
-                                           const float2* __restrict__ stepw, float sd, ulonglong2* __restrict__ acc /* the warp's strips */,
+                                           float sd, unsigned acc_s /* shared address of the warp's strips */, unsigned strip_bytes,
                                            float* __restrict__ step, int nq, int baseq, GeoRec* slot /* [3] */,
                                            unsigned ring_s /* shared address of the warp's ring */, int warp, int nwarps, int lane, float nz) {
     typedef CompSeq<H, V, NG10> Seq;
@@ -582,7 +583,7 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
         // next group of this warp (for the look-ahead at the end of this group's last chunk)
         const GeoRec* nrec = slot + (sl == 2 ? 0 : sl + 1);
         const bool next_ok = (ip + nwarps < ngroups) && !(nrec->flags & GEO_SKIP);
-        const int tt = rec->tt_begin, cls = rec->tap_cls, nstep = rec->nstep;
+        const int tt = rec->tt_begin, nstep = rec->nstep;
         const unsigned rec_s = (unsigned)__cvta_generic_to_shared(rec);
         int q_first = qf_n, q_last = ql_n;
         if (!primed) {   // pipeline (re)start: first S items of this group
@@ -592,20 +593,19 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
             issue_item(src, r2, Seq::step(2)); cp_async_commit();
         }
 
-        // lane k keeps tap k / step k of the group (tabulated by k_tap_table); broadcast by shuffles in the tap loops
-        int my_q = 0; float my_wl = 0.f, my_wr = 0.f;
-        {
-            const int ntap = (cls & 255) + ((cls >> 8) & 255) + ((cls >> 16) & 255) + ((cls >> 24) & 255);
-            if (lane < ntap) { const float4 tr = __ldg(taprec + tt + lane); my_q = __float_as_int(tr.x); my_wl = tr.y; my_wr = tr.z; }
+        // lane m keeps the m-th distinct quad shift of the group (tabulated by k_tap_table); broadcast by shuffles below
+        int my_q = 0; float my_h0 = 0.f, my_h1 = 0.f, my_h2 = 0.f, my_h3 = 0.f, my_h4 = 0.f, my_W = 0.f;
+        if (lane < nstep) {
+            const float4 ta = __ldg(taprec + 2 * ((size_t)tt + lane)), tb = __ldg(taprec + 2 * ((size_t)tt + lane) + 1);
+            my_q = __float_as_int(ta.x); my_h0 = ta.y; my_h1 = ta.z; my_h2 = ta.w; my_h3 = tb.x; my_h4 = tb.y; my_W = tb.z;
         }
-        float2 my_step = make_float2(0.f, 0.f);
-        if (lane < nstep) my_step = __ldg(stepw + tt + lane);
 
         for (int q0 = q_first; q0 <= q_last; q0 += 31) {
             const int q = q0 + lane - 1;   // lane 0: the quad left of the chunk, only read
             const bool active = lane > 0 && q <= q_last;
             const bool more = q0 + 31 <= q_last;
             const bool have_next = more || next_ok;
+            const int lane_on = q <= q_last;   // lanes that hold a quad of the windows (lane 0: the quad left of the chunk)
             // the group's weights are re-read from its record for every chunk rather than kept in registers across the tap loops
             float wc0, wc1, wc2, wc3, f1, f2, f3, f4, f5, f6, cl, sl_;
             {
@@ -618,12 +618,13 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
                 f1 = rb.x; f2 = rb.y; f3 = rb.z; f4 = rb.w; f5 = rc.x; f6 = rc.y; cl = rc.z; sl_ = rc.w;
             }
             Q2 A1 = q2_zero(), A2 = q2_zero(), A3 = q2_zero(), Rr = q2_zero(), Tt = q2_zero();
+            Q2 t0 = q2_zero(), t1 = q2_zero(), t2 = q2_zero(), t3 = q2_zero();   // (defined here so that the predicated reads below do not keep them alive across chunks)
 #pragma unroll
             for (int j = 0; j < N; j++) {
                 const unsigned rs = (j % 3 == 0) ? r0 : (j % 3 == 1 ? r1 : r2);
                 cp_async_wait<S - 1>();    // item j has landed (this lane's own copies; no other lane reads them)
-                {   // (lanes right of the windows combine whatever their slots hold; their quads go to the dummy quad below)
-                    const Q2 t0 = lds_q2<0>(rs), t1 = lds_q2<32 * 16>(rs), t2 = lds_q2<64 * 16>(rs), t3 = lds_q2<96 * 16>(rs);
+                {   // (lanes right of the windows skip the reads and combine whatever their registers hold; nothing of it is stored)
+                    lds_ring(rs, lane_on, t0, t1, t2, t3);
                     Q2 r = q2_zero();
                     q2_fma(r, wc0, t0); q2_fma(r, wc1, t1); q2_fma(r, wc2, t2); q2_fma(r, wc3, t3);   // a read clamped to quad 0 of a row returns the zeros left of the trace
                     const int k = Seq::comp(j);   // constant after unrolling
@@ -674,14 +675,19 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
                 P3.lo = shfl_up_u64(A3.lo, 1); P3.hi = shfl_up_u64(A3.hi, 1);
                 make_pairs(P3, A3, E3, G3, nz);
             }
-            // ---- taps: four loops with a compile-time sub-quad shift ------------------------------------------
+            // ---- taps (sparse_trace.f90:647-695): one read-modify-write of the strips per distinct quad shift ----------
             {
-                const int qb = active ? q - baseq : 0x40000000;
-                int t = 0;
-                tap_class<0, H, V>(cls & 255, t, my_q, my_wl, my_wr, qb, nq, acc, nq + 1, E1, G1, E2, G2, E3, G3);
-                tap_class<1, H, V>((cls >> 8) & 255, t, my_q, my_wl, my_wr, qb, nq, acc, nq + 1, E1, G1, E2, G2, E3, G3);
-                tap_class<2, H, V>((cls >> 16) & 255, t, my_q, my_wl, my_wr, qb, nq, acc, nq + 1, E1, G1, E2, G2, E3, G3);
-                tap_class<3, H, V>((cls >> 24) & 255, t, my_q, my_wl, my_wr, qb, nq, acc, nq + 1, E1, G1, E2, G2, E3, G3);
+                const int qb = q - baseq;
+                for (int m = 0; m < nstep; m++) {
+                    const int qrel = qb + __shfl_sync(0xffffffffu, my_q, m);
+                    const float h0 = __shfl_sync(0xffffffffu, my_h0, m), h1 = __shfl_sync(0xffffffffu, my_h1, m), h2 = __shfl_sync(0xffffffffu, my_h2, m),
+                                h3 = __shfl_sync(0xffffffffu, my_h3, m), h4 = __shfl_sync(0xffffffffu, my_h4, m);
+                    const int ok = active && (unsigned)qrel < (unsigned)nq;
+                    const unsigned a = acc_s + (min((unsigned)qrel, (unsigned)nq - 1u) << 4);
+                    if (H) { rmw_quad(a, ok, E1, G1, h0, h1, h2, h3, h4); rmw_quad(a + strip_bytes, ok, E2, G2, h0, h1, h2, h3, h4); }
+                    if (V) rmw_quad(a + 2 * strip_bytes, ok, E3, G3, h0, h1, h2, h3, h4);
+                    __syncwarp();
+                }
             }
             if (!more) {
                 // ---- end-value repetition (sparse_trace.f90:696-703): every sample right of the last processed quad gets
@@ -692,10 +698,10 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
                 if (H) { unpk2(A1.hi, d0, e1); unpk2(A2.hi, d0, e2); e1 = __shfl_sync(0xffffffffu, e1, srcl); e2 = __shfl_sync(0xffffffffu, e2, srcl); }
                 if (V) { unpk2(A3.hi, d0, e3); e3 = __shfl_sync(0xffffffffu, e3, srcl); }
                 (void)d0;
-                const int qs = q_last + 1 + __float_as_int(my_step.x) - baseq;
+                const int qs = q_last + 1 + my_q - baseq;
                 if (lane < nstep && (unsigned)qs < (unsigned)nq) {
-                    if (H) { step[qs] += my_step.y * e1; step[nq + qs] += my_step.y * e2; }
-                    if (V) step[2 * nq + qs] += my_step.y * e3;
+                    if (H) { step[qs] += my_W * e1; step[nq + qs] += my_W * e2; }
+                    if (V) step[2 * nq + qs] += my_W * e3;
                 }
             }
         }
@@ -727,7 +733,7 @@ __global__ void __launch_bounds__(256, 2) k_synth(GfdbDev db, const ReceiverDev*
     const int base = floor4(H.out0) - 4 * margin_q;   // room on the left for the rise-time fold (k_fold)
     const int baseq = base >> 2;
     const int nq = nq_alloc;    // quads per accumulator strip
-    const int nqs = nq + 1;     // + the dummy quad
+    const int nqs = nq;
     // shared memory: per warp 3 strips of nqs float4 + 3 step rows of nq floats, 3 group records, the cp.async ring
     float4* acc_all = reinterpret_cast<float4*>(smem_raw);
     float* step_all = reinterpret_cast<float*>(acc_all + (size_t)nwarps * 3 * nqs);
@@ -749,7 +755,7 @@ __global__ void __launch_bounds__(256, 2) k_synth(GfdbDev db, const ReceiverDev*
     const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
 
 #define KIWI_SYNTH(HH, VV, NG) \
-    synth_warp<HH, VV, NG>(db, myrecs, cand.ngroups, g.taprec, g.stepw, R.sd, reinterpret_cast<ulonglong2*>(acc), step, nq, baseq, slot, ring_s, warp, nwarps, lane, neg_zero)
+    synth_warp<HH, VV, NG>(db, myrecs, cand.ngroups, g.taprec, R.sd, (unsigned)__cvta_generic_to_shared(acc), (unsigned)nq * 16u, step, nq, baseq, slot, ring_s, warp, nwarps, lane, neg_zero)
     if (need_h && need_v) { if (ng10) KIWI_SYNTH(true, true, true); else KIWI_SYNTH(true, true, false); }
     else if (need_h) { if (ng10) KIWI_SYNTH(true, false, true); else KIWI_SYNTH(true, false, false); }
     else if (need_v) { if (ng10) KIWI_SYNTH(false, true, true); else KIWI_SYNTH(false, true, false); }
@@ -1622,7 +1628,7 @@ void launch_geometry(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev
     k_geometry<<<ncand * nrcv, threads, 0, st>>>(db, rcv, nrcv, cands, g, ngroups_total, interpolate, xunder, zunder, recs, rec_stride, hdrs, tmax);
 }
 size_t synth_smem_bytes(int nwarps, int nq) {
-    return (size_t)nwarps * 3 * ((nq + 1) * sizeof(float4) + nq * sizeof(float)) + 16 + (size_t)nwarps * 3 * sizeof(GeoRec) +
+    return (size_t)nwarps * 3 * nq * (sizeof(float4) + sizeof(float)) + 16 + (size_t)nwarps * 3 * sizeof(GeoRec) +
            (size_t)nwarps * SYN_STAGES * 4 * 32 * sizeof(float4);
 }
 cudaError_t launch_synth(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, const GeoRec* recs,

@@ -78,11 +78,9 @@ struct GroupSoA {
     int *its_min, *its_max;     // min/max of floor((tbase (+) toff)/dt) over the taps
     // receiver-independent shift table of the group (k_tap_table): what trace_multiply_add derives from
     // (time, weight) of every centroid, sparse_trace.f90:639-646
-    int* tt_begin;              // first entry of the group in taprec / stepw
-    int* tap_cls;               // entries are ordered by (sample shift mod 4); counts of the four classes, one byte each
-    int* nstep;                 // entries of stepw: distinct quad shifts of the group
-    float4* taprec;             // {sample shift div 4 (int bits), wl*wt, wr*wt, -}
-    float2* stepw;              // {quad shift (int bits), sum of (wl+wr)*wt over the taps with that quad shift}
+    int* tt_begin;              // first entry of the group in taprec (room for one entry per tap)
+    int* nstep;                 // entries of the group: distinct quad shifts (sample shift div 4) of its taps
+    float4* taprec;             // two per entry: {quad shift (int bits), h0, h1, h2} {h3, h4, W, -}, see k_tap_table
 };
 struct TapSoA {
     float *toff, *wt;
@@ -95,7 +93,8 @@ struct __align__(16) GeoRec {   // 128 bytes: everything k_synth needs to start 
     float f[6];         // make_weights(real(azi), mhat) seismogram.f90:316-336 (tap weight applied later)
     float cl, sl;       // real(cos/sin(bazi - bazi0)), seismogram.f90:163-164
     int flags;
-    int tt_begin, tap_cls, nstep;   // copy of the group's shift-table header (GroupSoA), so that it arrives with the record
+    int tt_begin, nstep;    // copy of the group's shift-table header (GroupSoA), so that it arrives with the record
+    int pad[1];
     NodeInfo node[4];   // slabs of the corners (ix1,iz1) (ix1,iz2) (ix2,iz1) (ix2,iz2); all = corner 0 if GEO_SINGLE
 };
 #define GEO_SKIP 1      // a needed node is outside the database: centroid skipped (seismogram.f90:172)
