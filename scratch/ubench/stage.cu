@@ -1,0 +1,89 @@
+// microbenchmark: HBM -> shared staging of 512-byte row pieces, per-lane cp.async (LDGSTS) vs one-lane cp.async.bulk
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#define CHECK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
+constexpr int STAGES = 3, PIECE = 512, WARPS = 8;
+
+__device__ __forceinline__ unsigned su32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(256, 2) k_ldgsts(const char* __restrict__ src, size_t npieces_per_warp, size_t stride, float* out) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t gw = (size_t)blockIdx.x * WARPS + warp;
+    const char* p = src + gw * npieces_per_warp * stride + lane * 16;
+    unsigned ring = su32(smem) + warp * STAGES * PIECE + lane * 16;
+    float4 acc = make_float4(0, 0, 0, 0);
+    for (int s = 0; s < STAGES; s++) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + s * PIECE), "l"(p + (size_t)s * stride) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    int st = 0;
+    for (size_t i = 0; i < npieces_per_warp; i++) {
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ring + st * PIECE) : "memory");
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        if (i + STAGES < npieces_per_warp)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + st * PIECE), "l"(p + (i + STAGES) * stride) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        st = st == STAGES - 1 ? 0 : st + 1;
+    }
+    if (acc.x + acc.y + acc.z + acc.w == 12345.f) out[0] = 1.f;
+}
+
+__global__ void __launch_bounds__(256, 2) k_bulk(const char* __restrict__ src, size_t npieces_per_warp, size_t stride, float* out) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t gw = (size_t)blockIdx.x * WARPS + warp;
+    const char* p = src + gw * npieces_per_warp * stride;
+    unsigned ring = su32(smem) + warp * STAGES * PIECE;
+    unsigned bar = su32(smem) + WARPS * STAGES * PIECE + warp * STAGES * 8;
+    if (lane == 0) for (int s = 0; s < STAGES; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar + s * 8));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    float4 acc = make_float4(0, 0, 0, 0);
+    if (lane == 0)
+        for (int s = 0; s < STAGES; s++) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar + s * 8), "r"(PIECE) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ring + s * PIECE), "l"(p + (size_t)s * stride), "r"(PIECE), "r"(bar + s * 8) : "memory");
+        }
+    int st = 0; unsigned phase = 0;
+    for (size_t i = 0; i < npieces_per_warp; i++) {
+        unsigned par = (phase >> st) & 1u;
+        asm volatile("{\n\t.reg .pred p;\n\tW: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra W;\n\t}" ::"r"(bar + st * 8), "r"(par) : "memory");
+        phase ^= 1u << st;
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ring + st * PIECE + lane * 16) : "memory");
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        __syncwarp();
+        if (lane == 0 && i + STAGES < npieces_per_warp) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar + st * 8), "r"(PIECE) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ring + st * PIECE), "l"(p + (i + STAGES) * stride), "r"(PIECE), "r"(bar + st * 8) : "memory");
+        }
+        st = st == STAGES - 1 ? 0 : st + 1;
+    }
+    if (acc.x + acc.y + acc.z + acc.w == 12345.f) out[0] = 1.f;
+}
+
+int main(int argc, char** argv) {
+    const size_t stride = argc > 1 ? atol(argv[1]) : 816;    // bytes between pieces (a row of ~204 samples)
+    const int blocks = 148 * 2 * 8;
+    const size_t npw = 2048;
+    const size_t bytes = (size_t)blocks * WARPS * npw * stride + 4096;
+    char* d; float* o;
+    CHECK(cudaMalloc(&d, bytes)); CHECK(cudaMemset(d, 0, bytes)); CHECK(cudaMalloc(&o, 4));
+    const int smem = WARPS * STAGES * PIECE + WARPS * STAGES * 8;
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    for (int which = 0; which < 2; which++)
+        for (int rep = 0; rep < 3; rep++) {
+            cudaEventRecord(a);
+            if (which == 0) k_ldgsts<<<blocks, 256, smem>>>(d, npw, stride, o);
+            else k_bulk<<<blocks, 256, smem>>>(d, npw, stride, o);
+            cudaEventRecord(b); CHECK(cudaEventSynchronize(b));
+            float ms; cudaEventElapsedTime(&ms, a, b);
+            printf("%s stride %zu: %.3f ms  %.1f GB/s (useful 512 B per piece)\n", which ? "bulk  " : "ldgsts", stride, ms, (double)blocks * WARPS * npw * PIECE / ms / 1e6);
+        }
+    CHECK(cudaGetLastError());
+    return 0;
+}
