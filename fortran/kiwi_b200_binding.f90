@@ -184,6 +184,48 @@ module kiwi_b200_binding
             integer(c_int) :: rc
         end function
 
+        function kiwi_set_source_params_mask(ctx, mask, n) bind(C, name="kiwi_set_source_params_mask") result(rc)
+            import :: c_ptr, c_int
+            type(c_ptr), value :: ctx
+            integer(c_int), intent(in) :: mask(*)          ! 0 / 1
+            integer(c_int), value :: n
+            integer(c_int) :: rc
+        end function
+
+        function kiwi_set_source_subparams(ctx, subparams, n) bind(C, name="kiwi_set_source_subparams") result(rc)
+            import :: c_ptr, c_int, c_float
+            type(c_ptr), value :: ctx
+            real(c_float), intent(in) :: subparams(*)
+            integer(c_int), value :: n
+            integer(c_int) :: rc
+        end function
+
+        function kiwi_set_source_subparams_limits(ctx, mins, maxs, n) bind(C, name="kiwi_set_source_subparams_limits") result(rc)
+            import :: c_ptr, c_int, c_float
+            type(c_ptr), value :: ctx
+            real(c_float), intent(in) :: mins(*), maxs(*)
+            integer(c_int), value :: n
+            integer(c_int) :: rc
+        end function
+
+        function kiwi_get_source_subparams(ctx, subparams, cap, n) bind(C, name="kiwi_get_source_subparams") result(rc)
+            import :: c_ptr, c_int, c_float
+            type(c_ptr), value :: ctx
+            real(c_float), intent(out) :: subparams(*)
+            integer(c_int), value :: cap
+            integer(c_int), intent(out) :: n
+            integer(c_int) :: rc
+        end function
+
+        ! replaces minimize_lm (minimizer_engine.f90:729-806): lmdif with the Jacobian sources as one batch
+        function kiwi_minimize_lm(ctx, info, iterations, misfit) bind(C, name="kiwi_minimize_lm") result(rc)
+            import :: c_ptr, c_int, c_float
+            type(c_ptr), value :: ctx
+            integer(c_int), intent(out) :: info, iterations
+            real(c_float), intent(out) :: misfit
+            integer(c_int) :: rc
+        end function
+
         function kiwi_get_seismogram(ctx, ireceiver, icomponent, which, first_index, n, buf, cap) bind(C, name="kiwi_get_seismogram") result(rc)
             import :: c_ptr, c_int, c_float
             type(c_ptr), value :: ctx

@@ -186,6 +186,26 @@ int kiwi_outer_misfits(kiwi_ctx* ctx, int ns, const float* d_misfits, const doub
 int kiwi_set_source_params(kiwi_ctx* ctx, int sourcetype, int nparams, const float* params);
 int kiwi_get_misfits(kiwi_ctx* ctx, float* misfits, int cap_pairs, int* nmisfits);   /* minimizer_engine.f90:1130-1172 */
 int kiwi_get_global_misfit(kiwi_ctx* ctx, float* misfit);                            /* minimizer_engine.f90:1083-1093 */
+
+/* ---- Levenberg-Marquardt inversion ----------------------------------------
+ * The sub-parameter machinery of the parameterised source (parameterized_source.f90:244-309,
+ * source_all.f90:377-428) and minimize_lm (minimizer_engine.f90:729-874): MINPACK lmdif on the
+ * per-trace misfits of the masked, normalised source parameters.  The n finite-difference sources
+ * of every Jacobian (sminpack/fdjac2.f) are evaluated as ONE batch on the GPU; everything else of
+ * lmdif/lmpar/qrfac/qrsolv/enorm runs on the host in the reference's single precision.
+ * As in the reference the source is left at the LAST model evaluated, `iterations` counts the
+ * forward evaluations and `misfit` is the global misfit of that last model. */
+int kiwi_set_source_params_mask(kiwi_ctx* ctx, const int* mask, int n);                   /* minimizer_engine.f90:525-543 */
+int kiwi_set_source_subparams(kiwi_ctx* ctx, const float* subparams, int n);              /* minimizer_engine.f90:545-566 */
+int kiwi_set_source_subparams_limits(kiwi_ctx* ctx, const float* mins, const float* maxs, int n);   /* :580-610 */
+int kiwi_get_source_subparams(kiwi_ctx* ctx, float* subparams, int cap, int* n);          /* minimizer_engine.f90:1069-1081 */
+int kiwi_minimize_lm(kiwi_ctx* ctx, int* info, int* iterations, float* misfit);           /* minimizer_engine.f90:729-874 */
+/* lmdif on a caller-supplied function, Jacobian columns in one batch (also what the known-answer tests drive).
+ * fcn(user, ncols, n, m, xs[ncols][n] (may be changed in place), fvecs[ncols][m]) returns the number of leading
+ * columns evaluated successfully.  mode/diag/factor/tolerances as in sminpack/lmdif.f; x, fvec, diag are in/out. */
+typedef int (*kiwi_lm_fcn)(void* user, int ncols, int n, int m, float* xs, float* fvecs);
+int kiwi_lmdif_batched(kiwi_lm_fcn fcn, void* user, int m, int n, float* x, float* fvec, float ftol, float xtol, float gtol, int maxfev,
+                       float epsfcn, float* diag, int mode, float factor, int* info, int* nfev);
 int kiwi_get_floating_shifts(kiwi_ctx* ctx, int* shifts, int cap, int* n);           /* minimizer_engine.f90:1095-1128, in samples */
 /* In-memory replacement for output_seismograms (minimizer_engine.f90:947-1012; the reference only
  * writes files): synthetic trace of the source set by kiwi_set_source_params.

@@ -8,7 +8,7 @@ The names below resolve lazily so that `python -m kiwi_b200.build` can run befor
 library exists; anything else fails loudly if the library is missing (kiwi_b200/_lib.py).
 """
 __all__ = ["Engine", "Gfdb", "KiwiError", "SOURCE_TYPES", "NORMS", "KIWIBENCH_STF", "n_source_params",
-           "global_misfits"]
+           "global_misfits", "lmdif_batched"]
 
 
 def __getattr__(name):

@@ -55,6 +55,13 @@ SIGNATURES = {
     "kiwi_set_source_params": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p]),
     "kiwi_get_misfits": (C.c_int, [C.c_void_p, c_float_p, C.c_int, c_int_p]),
     "kiwi_get_global_misfit": (C.c_int, [C.c_void_p, c_float_p]),
+    "kiwi_set_source_params_mask": (C.c_int, [C.c_void_p, c_int_p, C.c_int]),
+    "kiwi_set_source_subparams": (C.c_int, [C.c_void_p, c_float_p, C.c_int]),
+    "kiwi_set_source_subparams_limits": (C.c_int, [C.c_void_p, c_float_p, c_float_p, C.c_int]),
+    "kiwi_get_source_subparams": (C.c_int, [C.c_void_p, c_float_p, C.c_int, c_int_p]),
+    "kiwi_minimize_lm": (C.c_int, [C.c_void_p, c_int_p, c_int_p, c_float_p]),
+    "kiwi_lmdif_batched": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, c_float_p, c_float_p, C.c_float, C.c_float, C.c_float, C.c_int,
+                                     C.c_float, c_float_p, C.c_int, C.c_float, c_int_p, c_int_p]),
     "kiwi_get_floating_shifts": (C.c_int, [C.c_void_p, c_int_p, C.c_int, c_int_p]),
     "kiwi_get_seismogram": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_float_p, C.c_int]),
     "kiwi_discretize_source": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, c_float_p, C.c_int, c_int_p, c_int_p]),
@@ -64,6 +71,10 @@ SIGNATURES = {
     "kiwi_last_batch_bytes": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, c_int_p, c_ll_p]),
     "kiwi_last_timing": (C.c_int, [C.c_void_p, c_float_p, c_int_p]),
 }
+
+
+# kiwi_lm_fcn: int fcn(void* user, int ncols, int n, int m, float* xs, float* fvecs)
+LM_FCN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p)
 
 
 def load():

@@ -10,6 +10,7 @@
 #include "kiwi_internal.hpp"
 #include "kernels.cuh"
 #include "host_math.hpp"
+#include "lm_host.hpp"
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -143,6 +144,9 @@ struct kiwi_ctx {
     int src_type = 0;
     std::vector<float> src_params, src_misfits;
     int src_status = 0;
+    // sub-parameter view of the source (psm%params_mask, g_subparam_mins/maxs minimizer_engine.f90:89-90)
+    std::vector<char> src_mask;               // empty = all true (source_all.f90:251)
+    std::vector<float> sub_mins, sub_maxs;    // empty = no limits
 };
 
 namespace {
@@ -1113,6 +1117,7 @@ int kiwi_set_source_params(kiwi_ctx* c, int sourcetype, int nparams, const float
     // minimizer_engine.f90:511-513: identical parameters are a no-op
     if (c->src_set && c->src_type == sourcetype && (int)c->src_params.size() == nparams &&
         memcmp(c->src_params.data(), params, sizeof(float) * nparams) == 0) return 0;
+    if (c->src_type != sourcetype) c->src_mask.clear();   // psm_set: a new source type selects every parameter (source_all.f90:249-253)
     c->src_type = sourcetype; c->src_params.assign(params, params + nparams);
     c->src_set = true; c->src_dirty = true;
     return 0;
@@ -1136,6 +1141,175 @@ int kiwi_get_global_misfit(kiwi_ctx* c, float* misfit) {
     CU_OK(cudaSetDevice(c->device));
     if (ensure_single(c, true)) return 1;
     return kiwi_global_misfits(1, c->nmisfits, c->src_misfits.data(), misfit);
+}
+
+// ---- sub-parameters and Levenberg-Marquardt -------------------------------------------------
+namespace {
+// psm_params_norm_* (source_bilat.f90:45-46, source_circular.f90:44-45, source_point_lp.f90:54-55, source_eikonal.f90:48-49,
+// source_mt_eikonal.f90:48-50, source_moment_tensor.f90:42-43)
+const std::vector<float>& params_norm(int sourcetype) {
+    static const std::vector<float> bilat = {1.f, 10000.f, 10000.f, 10000.f, 7e18f, 360.f, 90.f, 360.f, 360.f, 10000.f, 10000.f, 10000.f, 3000.f, 1.f};
+    static const std::vector<float> circular = {1.f, 10000.f, 10000.f, 10000.f, 7e18f, 360.f, 90.f, 360.f, 10000.f, 3000.f, 1.f};
+    static const std::vector<float> point_lp = {1.f, 10000.f, 10000.f, 10000.f, 7e18f, 1.f, 0.f, -1.f, 1.f, 1.f, 1.f, 20.f, 1.f};
+    static const std::vector<float> eikonal = {1.f, 10000.f, 10000.f, 10000.f, 7e18f, 360.f, 90.f, 360.f, 10000.f, 10000.f, 10000.f, 360.f, 10000.f, 1.f, 1.f};
+    static const std::vector<float> mt_eikonal = {1.f, 10000.f, 10000.f, 10000.f, 7e18f, 360.f, 90.f, 10000.f, 10000.f, 10000.f, 360.f, 10000.f, 1.f, 7e18f,
+                                                  7e18f, 7e18f, 7e18f, 7e18f, 7e18f, 1.f};
+    static const std::vector<float> mt = {1.f, 10000.f, 10000.f, 10000.f, 7e18f, 7e18f, 7e18f, 7e18f, 7e18f, 7e18f, 1.f};
+    static const std::vector<float> none;
+    switch (sourcetype) {
+        case KIWI_SOURCE_BILATERAL: return bilat;
+        case KIWI_SOURCE_CIRCULAR: return circular;
+        case KIWI_SOURCE_POINT_LP: return point_lp;
+        case KIWI_SOURCE_EIKONAL: return eikonal;
+        case KIWI_SOURCE_MT_EIKONAL: return mt_eikonal;
+        case KIWI_SOURCE_MOMENT_TENSOR: return mt;
+    }
+    return none;
+}
+bool masked(const kiwi_ctx* c, size_t i) { return c->src_mask.empty() || c->src_mask[i]; }
+int count_mask(const kiwi_ctx* c) {
+    int k = 0;
+    for (size_t i = 0; i < c->src_params.size(); i++) k += masked(c, i) ? 1 : 0;
+    return k;
+}
+// psm_set_subparams (source_all.f90:377-428): ALL parameters make the round trip through the normalised
+// representation when `normalized` (params/norm, masked ones replaced, times norm), as in the reference
+std::vector<float> apply_subparams(const kiwi_ctx* c, const std::vector<float>& params, const float* sub, bool normalized) {
+    const std::vector<float>& norm = params_norm(c->src_type);
+    std::vector<float> copy(params.size());
+    for (size_t i = 0; i < params.size(); i++) copy[i] = normalized ? params[i] / norm[i] : params[i];
+    size_t isub = 0;
+    for (size_t i = 0; i < params.size(); i++) if (masked(c, i)) copy[i] = sub[isub++];
+    if (normalized) for (size_t i = 0; i < params.size(); i++) copy[i] = copy[i] * norm[i];
+    return copy;
+}
+}  // namespace
+
+int kiwi_set_source_params_mask(kiwi_ctx* c, const int* mask, int n) {
+    if (!c) return kiwi_set_error("null context");
+    if (!c->src_set) return kiwi_set_error("no source parameters set");
+    if (n != (int)c->src_params.size()) return kiwi_set_error("wrong number of elements in source params mask");   // minimizer_engine.f90:533-537
+    c->src_mask.assign(n, 0);
+    for (int i = 0; i < n; i++) c->src_mask[i] = mask[i] ? 1 : 0;
+    c->sub_mins.clear(); c->sub_maxs.clear();   // reset_subparam_limits, :541
+    return 0;
+}
+
+int kiwi_set_source_subparams(kiwi_ctx* c, const float* sub, int n) {
+    if (!c) return kiwi_set_error("null context");
+    if (!c->src_set) return kiwi_set_error("no source parameters set");
+    if (n != count_mask(c)) return kiwi_set_error("wrong number of subparams");   // minimizer_engine.f90:557-561
+    const std::vector<float> p = apply_subparams(c, c->src_params, sub, false);
+    return kiwi_set_source_params(c, c->src_type, (int)p.size(), p.data());
+}
+
+int kiwi_set_source_subparams_limits(kiwi_ctx* c, const float* mins, const float* maxs, int n) {
+    if (!c) return kiwi_set_error("null context");
+    if (!c->src_set) return kiwi_set_error("no source parameters set");
+    if (n != count_mask(c)) return kiwi_set_error("wrong number of subparam_mins");   // minimizer_engine.f90:590-600
+    c->sub_mins.assign(mins, mins + n); c->sub_maxs.assign(maxs, maxs + n);
+    return 0;
+}
+
+int kiwi_get_source_subparams(kiwi_ctx* c, float* sub, int cap, int* n) {
+    if (!c) return kiwi_set_error("null context");
+    if (!c->src_set) return kiwi_set_error("no source parameters set");
+    const int k = count_mask(c);
+    if (n) *n = k;
+    if (cap < k) return kiwi_set_error("subparams buffer too small: need %d", k);
+    int isub = 0;
+    for (size_t i = 0; i < c->src_params.size(); i++) if (masked(c, i)) sub[isub++] = c->src_params[i];
+    return 0;
+}
+
+int kiwi_lmdif_batched(kiwi_lm_fcn fcn, void* user, int m, int n, float* x, float* fvec, float ftol, float xtol, float gtol, int maxfev, float epsfcn,
+                       float* diag, int mode, float factor, int* info, int* nfev) {
+    if (!fcn || !x || !fvec || !diag) return kiwi_set_error("null argument");
+    const klm::Result r = klm::lmdif_batched([&](int ncols, float* xs, float* fs) { return fcn(user, ncols, n, m, xs, fs); }, m, n, x, fvec, ftol,
+                                             xtol, gtol, maxfev, epsfcn, diag, mode, factor);
+    if (info) *info = r.info;
+    if (nfev) *nfev = r.nfev;
+    return 0;
+}
+
+int kiwi_minimize_lm(kiwi_ctx* c, int* info_out, int* iterations_out, float* misfit_out) {
+    if (!c) return kiwi_set_error("null context");
+    CU_OK(cudaSetDevice(c->device));
+    if (ensure_single(c, true)) return 1;   // update_misfits, minimizer_engine.f90:735
+    const int n = count_mask(c);
+    int m = 0;                              // get_nmisfits: components of ALL receivers (disabled ones hold zeros, receiver.f90:430)
+    for (const HostReceiver& h : c->rcv) m += h.ncomp;
+    if (n <= 0 || m < n) return kiwi_set_error("something went wrong in minimize_lm");   // the reference dies here (:778-780)
+    const std::vector<float>& norm = params_norm(c->src_type);
+    const size_t np = c->src_params.size();
+    std::vector<float> snorm;               // psm_get_subparams_norm
+    for (size_t i = 0; i < np; i++) if (masked(c, i)) snorm.push_back(norm[i]);
+    std::vector<float> x(n), fvec(m), diag(n, 1.f);
+    { int k = 0; for (size_t i = 0; i < np; i++) if (masked(c, i)) x[k++] = c->src_params[i] / norm[i]; }   // psm_get_subparams(normalized)
+    const bool limits = !c->sub_mins.empty() && !c->sub_maxs.empty();
+    const int nm = c->nmisfits;
+    int iterations = 0;
+    bool failed_hard = false;
+    // lm_forward_step (minimizer_engine.f90:808-874) for `ncols` vectors at once
+    auto forward = [&](int ncols, float* xs, float* fs) -> int {
+        std::vector<float> penalty(ncols, 0.f), params((size_t)ncols * np);
+        std::vector<float> cur = c->src_params;   // psm%params as the sequential reference would hold them before each step
+        for (int col = 0; col < ncols; col++) {
+            float* xc = xs + (size_t)col * n;
+            if (limits)
+                for (int i = 0; i < n; i++) {
+                    if (xc[i] * snorm[i] < c->sub_mins[i]) {
+                        penalty[col] = penalty[col] + fabsf(xc[i] * snorm[i] - c->sub_mins[i]) / fabsf(c->sub_maxs[i] - c->sub_mins[i]);
+                        xc[i] = c->sub_mins[i] / snorm[i];
+                    }
+                    if (xc[i] * snorm[i] > c->sub_maxs[i]) {
+                        penalty[col] = penalty[col] + fabsf(xc[i] * snorm[i] - c->sub_maxs[i]) / fabsf(c->sub_maxs[i] - c->sub_mins[i]);
+                        xc[i] = c->sub_maxs[i] / snorm[i];
+                    }
+                }
+            cur = apply_subparams(c, cur, xc, true);   // every step starts from the parameters the previous one left
+            std::copy(cur.begin(), cur.end(), params.begin() + (size_t)col * np);
+        }
+        std::vector<int> status(ncols, 0);
+        CU_OK(c->d_out.ensure(sizeof(float) * 2 * (size_t)std::max(nm, 1) * ncols));
+        if (eval_batch(c, c->src_type, ncols, (int)np, params.data(), c->d_out.as<float>(), status.data(), true)) { failed_hard = true; return 0; }
+        std::vector<float> mis((size_t)2 * nm * ncols, 0.f);
+        if (nm > 0) CU_OK(cudaMemcpy(mis.data(), c->d_out.p, sizeof(float) * mis.size(), cudaMemcpyDeviceToHost));
+        int nok = 0;
+        for (; nok < ncols; nok++) {
+            // update_misfits fails (discretisation) or a misfit is not finite (get_misfits :1163): the forward step reports iflag = -2
+            if (status[nok] != KIWI_STATUS_OK) break;
+            float* f = fs + (size_t)nok * m;
+            const float* mm = mis.data() + (size_t)nok * 2 * nm;
+            int k = 0;
+            for (size_t ir = 0; ir < c->rcv.size(); ir++) {
+                const HostReceiver& h = c->rcv[ir];
+                for (int ic = 0; ic < h.ncomp; ic++) f[k++] = (h.enabled ? mm[2 * (c->h_rcvdev[ir].misfit_base + ic)] : 0.f) * (1.0f + penalty[nok]);
+            }
+            iterations++;
+        }
+        // the source and its misfits stay at the last model evaluated (the sequential reference stops at the first failure)
+        const int last = std::min(nok, ncols - 1);
+        c->src_params.assign(params.begin() + (size_t)last * np, params.begin() + (size_t)(last + 1) * np);
+        c->src_misfits.assign(mis.begin() + (size_t)last * 2 * nm, mis.begin() + (size_t)(last + 1) * 2 * nm);
+        c->src_status = status[last];
+        c->src_dirty = ncols > 1 || nok < ncols;   // the single-source tables (seismograms, indices) describe a batch: rebuild on demand
+        c->last.valid = c->last.valid && ncols == 1;
+        return nok;
+    };
+    const float tol = sqrtf(1.192091E-07f);   // sqrt(spmpar(1)), minimizer_engine.f90:773
+    const int maxfev = 500 * (n + 1);
+    const klm::Result r = klm::lmdif_batched(forward, m, n, x.data(), fvec.data(), tol, tol, 0.f, maxfev, 0.f, diag.data(), 2, 0.01f);
+    if (failed_hard) return 1;
+    int info = r.info;
+    if (info == 8) info = 4;                  // :799
+    if (info_out) *info_out = info;
+    if (iterations_out) *iterations_out = iterations;
+    if (misfit_out) {
+        if (c->src_misfits.empty()) *misfit_out = NAN;
+        else kiwi_global_misfits(1, nm, c->src_misfits.data(), misfit_out);
+    }
+    return 0;
 }
 
 int kiwi_get_floating_shifts(kiwi_ctx* c, int* shifts, int cap, int* n) {   // minimizer_engine.f90:1095-1128

@@ -96,7 +96,8 @@ bool do_command(State& S, const std::string& cmd, const std::vector<std::string>
                                   "set_source_location", "set_source_constraints", "set_source_crustal_thickness_limit", "set_source_params",
                                   "set_effective_dt", "set_ref_seismograms", "set_misfit_method", "set_misfit_taper", "set_misfit_filter",
                                   "set_synthetics_factor", "set_floating_shiftrange", "get_misfits", "get_global_misfit", "get_floating_shifts",
-                                  "output_seismograms", "eval_sources"};
+                                  "output_seismograms", "eval_sources", "set_source_params_mask", "set_source_subparams",
+                                  "set_source_subparams_limits", "get_source_subparams", "minimize_lm"};
     bool is_known = false;
     for (const char* k : known) if (cmd == k) is_known = true;
     if (!is_known) return fail("unknown command: " + cmd);   // minimizer.f90:1809-1811
@@ -231,6 +232,40 @@ bool do_command(State& S, const std::string& cmd, const std::vector<std::string>
         float g;
         if (kiwi_get_global_misfit(S.ctx, &g)) return cfail();
         *answer = fmt_floats(&g, 1);
+        return true;
+    }
+    if (cmd == "set_source_params_mask") {   // minimizer.f90:694-736: logicals T/F (list-directed input also takes .true. / .false.)
+        std::vector<int> mask;
+        for (size_t i = 1; i < w.size(); i++) {
+            std::string t = w[i];
+            while (!t.empty() && t[0] == '.') t.erase(0, 1);
+            if (t.empty() || !strchr("TtFf", t[0])) return fail("failed to parse source params mask");
+            mask.push_back(t[0] == 'T' || t[0] == 't');
+        }
+        if (kiwi_set_source_params_mask(S.ctx, mask.data(), (int)mask.size())) return cfail();
+        return true;
+    }
+    if (cmd == "set_source_subparams") {   // minimizer.f90:738-770
+        if (!to_floats(w, 1, &v)) return fail("failed to parse subparams");
+        if (kiwi_set_source_subparams(S.ctx, v.data(), (int)v.size())) return cfail();
+        return true;
+    }
+    if (cmd == "set_source_subparams_limits") {   // minimizer.f90:772-812: all minima, then all maxima
+        if (!to_floats(w, 1, &v) || v.size() % 2) return fail("failed to parse subparam limits");
+        const int n = (int)v.size() / 2;
+        if (kiwi_set_source_subparams_limits(S.ctx, v.data(), v.data() + n, n)) return cfail();
+        return true;
+    }
+    if (cmd == "get_source_subparams") {   // minimizer.f90:1199-1224
+        float sub[64]; int n = 0;
+        if (kiwi_get_source_subparams(S.ctx, sub, 64, &n)) return cfail();
+        *answer = fmt_floats(sub, (size_t)n);
+        return true;
+    }
+    if (cmd == "minimize_lm") {   // minimizer.f90:1048-1081: answer = info iterations misfit
+        int info = 0, iterations = 0; float misfit = 0.f;
+        if (kiwi_minimize_lm(S.ctx, &info, &iterations, &misfit)) return cfail();
+        *answer = std::to_string(info) + " " + std::to_string(iterations) + " " + fmt_floats(&misfit, 1);
         return true;
     }
     if (cmd == "get_floating_shifts") {   // minimizer_engine.f90:1095-1128: seconds

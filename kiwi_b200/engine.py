@@ -322,6 +322,33 @@ class Engine:
         _check(lib.kiwi_get_global_misfit(self._h, v))
         return v.value
 
+    # ---- sub-parameters and Levenberg-Marquardt (minimizer_engine.f90:525-610, 729-874) ------------------
+    def set_source_params_mask(self, mask):
+        m = np.ascontiguousarray(np.asarray(mask).astype(bool), dtype=np.int32)
+        _check(lib.kiwi_set_source_params_mask(self._h, m.ctypes.data_as(c_int_p), m.size))
+
+    def set_source_subparams(self, subparams):
+        p = _f32(subparams).ravel()
+        _check(lib.kiwi_set_source_subparams(self._h, _fp(p), p.size))
+
+    def set_source_subparams_limits(self, mins, maxs):
+        a, b = _f32(mins).ravel(), _f32(maxs).ravel()
+        if a.size != b.size:
+            raise KiwiError("wrong number of subparam_maxs")
+        _check(lib.kiwi_set_source_subparams_limits(self._h, _fp(a), _fp(b), a.size))
+
+    def get_source_subparams(self):
+        out = np.zeros(64, dtype=np.float32)
+        n = C.c_int()
+        _check(lib.kiwi_get_source_subparams(self._h, _fp(out), out.size, n))
+        return out[:n.value].copy()
+
+    def minimize_lm(self):
+        """-> (info, iterations, misfit); the source is left at the last model evaluated, as in the reference."""
+        info, it, mis = C.c_int(), C.c_int(), C.c_float()
+        _check(lib.kiwi_minimize_lm(self._h, info, it, mis))
+        return info.value, it.value, mis.value
+
     def get_floating_shifts(self):
         nr = 4096
         out = np.zeros(nr, dtype=np.int32)
@@ -379,3 +406,34 @@ class Engine:
         _check(lib.kiwi_last_timing(self._h, _fp(ms), ln.ctypes.data_as(c_int_p)))
         return dict(discretise_ms=float(ms[0]), geometry_ms=float(ms[1]), synthesis_ms=float(ms[2]), misfit_ms=float(ms[3]),
                     total_ms=float(ms[4]), launches=[int(v) for v in ln])
+
+
+def lmdif_batched(fcn, x0, m, ftol=None, xtol=None, gtol=0.0, maxfev=None, epsfcn=0.0, diag=None, mode=1, factor=100.0):
+    """MINPACK lmdif (single precision) with the Jacobian columns evaluated as one batch (kiwi_lmdif_batched).
+    fcn(xs[ncols, n]) -> fvecs[ncols, m] (rows may be returned short to signal a failure at that column).
+    Returns (x, fvec, info, nfev)."""
+    from ._lib import LM_FCN
+    x = _f32(x0).ravel().copy()
+    n = x.size
+    tol = float(np.sqrt(np.float32(1.192091e-07)))
+    ftol = tol if ftol is None else ftol
+    xtol = tol if xtol is None else xtol
+    maxfev = 200 * (n + 1) if maxfev is None else maxfev
+    d = np.ones(n, dtype=np.float32) if diag is None else _f32(diag).ravel().copy()
+    fvec = np.zeros(m, dtype=np.float32)
+
+    def cb(user, ncols, n_, m_, xs, fs):
+        xa = np.ctypeslib.as_array(xs, shape=(ncols, n_))
+        fa = np.ctypeslib.as_array(fs, shape=(ncols, m_))
+        out = fcn(xa)
+        if out is None:
+            return 0
+        out = np.asarray(out, dtype=np.float32).reshape(-1, m_)
+        fa[:out.shape[0]] = out
+        return int(out.shape[0])
+
+    cfn = LM_FCN(cb)
+    info, nfev = C.c_int(), C.c_int()
+    _check(lib.kiwi_lmdif_batched(C.cast(cfn, C.c_void_p), None, m, n, _fp(x), _fp(fvec), ftol, xtol, gtol, maxfev, epsfcn, _fp(d), mode, factor,
+                                  info, nfev))
+    return x, fvec, info.value, nfev.value

@@ -11,6 +11,7 @@
 #pragma once
 #include "ko_receiver.hpp"
 #include "ko_eikonal.hpp"
+#include "ko_lm.hpp"
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -37,6 +38,12 @@ struct Engine {
     std::vector<Trace> scratch;  // per-thread bilinear scratch traces
     std::vector<std::vector<IndexRecord>> index_records;  // filled when record_indices
     bool record_indices = false;
+    // parameter vector as set, sub-parameter mask and limits (psm%params, psm%params_mask, g_subparam_mins/maxs)
+    int cur_type = 0;
+    std::vector<float> cur_params;
+    std::vector<char> params_mask;              // empty = all true (source_all.f90:251)
+    std::vector<float> sub_mins, sub_maxs;      // empty = none
+    int iterations = 0;                         // minimizer_engine.f90:104
 };
 
 // minimizer_engine.f90:165-286; coordinates in degrees as in the receivers file
@@ -113,6 +120,8 @@ static inline void set_synthetics_factor(Engine& e, float f) { for (auto& r : e.
 static inline bool set_source_params(Engine& e, int sourcetype, const float* params, int nparams) {
     if (!e.source_location_inited) { e.errstr = "no source location set"; return false; }
     bool omc;
+    if (e.cur_type != sourcetype) e.params_mask.clear();   // a new source type starts with every parameter selected
+    e.cur_type = sourcetype; e.cur_params.assign(params, params + nparams);
     if (sourcetype == PSM_EIKONAL || sourcetype == PSM_MT_EIKONAL) {
         if (nparams != (sourcetype == PSM_EIKONAL ? 15 : 20)) { e.errstr = "wrong number of source parameters"; return false; }
         if (!e.crust.loaded) { e.errstr = "crust2x2 model not loaded"; return false; }
@@ -206,6 +215,98 @@ static inline int evaluate(Engine& e, int sourcetype, const float* params, int n
         }
     }
     return n;
+}
+
+
+// ---- sub-parameters and minimize_lm (minimizer_engine.f90:525-610, 729-874; source_all.f90:377-428) ----------------
+static inline const std::vector<float>& psm_params_norm(int sourcetype) {
+    static const std::vector<float> bilat = {1.f, 10000.f, 10000.f, 10000.f, 7e18f, 360.f, 90.f, 360.f, 360.f, 10000.f, 10000.f, 10000.f, 3000.f, 1.f};
+    static const std::vector<float> circular = {1.f, 10000.f, 10000.f, 10000.f, 7e18f, 360.f, 90.f, 360.f, 10000.f, 3000.f, 1.f};
+    static const std::vector<float> point_lp = {1.f, 10000.f, 10000.f, 10000.f, 7e18f, 1.f, 0.f, -1.f, 1.f, 1.f, 1.f, 20.f, 1.f};
+    static const std::vector<float> eikonal = {1.f, 10000.f, 10000.f, 10000.f, 7e18f, 360.f, 90.f, 360.f, 10000.f, 10000.f, 10000.f, 360.f, 10000.f, 1.f, 1.f};
+    static const std::vector<float> mt_eikonal = {1.f, 10000.f, 10000.f, 10000.f, 7e18f, 360.f, 90.f, 10000.f, 10000.f, 10000.f, 360.f, 10000.f, 1.f, 7e18f,
+                                                  7e18f, 7e18f, 7e18f, 7e18f, 7e18f, 1.f};
+    static const std::vector<float> mt = {1.f, 10000.f, 10000.f, 10000.f, 7e18f, 7e18f, 7e18f, 7e18f, 7e18f, 7e18f, 1.f};
+    static const std::vector<float> none;
+    switch (sourcetype) {
+        case PSM_BILAT: return bilat;
+        case PSM_CIRCULAR: return circular;
+        case PSM_POINT_LP: return point_lp;
+        case PSM_EIKONAL: return eikonal;
+        case PSM_MT_EIKONAL: return mt_eikonal;
+        case PSM_MOMENT_TENSOR: return mt;
+    }
+    return none;
+}
+static inline bool lm_masked(const Engine& e, size_t i) { return e.params_mask.empty() || e.params_mask[i]; }
+static inline int lm_count_mask(const Engine& e) {
+    int k = 0;
+    for (size_t i = 0; i < e.cur_params.size(); i++) k += lm_masked(e, i) ? 1 : 0;
+    return k;
+}
+// psm_set_subparams: psm_get_params(normalized) -> replace the masked ones -> psm_set_*(normalized)
+static inline bool set_subparams(Engine& e, const float* sub, bool normalized) {
+    const std::vector<float>& norm = psm_params_norm(e.cur_type);
+    std::vector<float> copy(e.cur_params.size());
+    for (size_t i = 0; i < copy.size(); i++) copy[i] = normalized ? e.cur_params[i] / norm[i] : e.cur_params[i];
+    size_t isub = 0;
+    for (size_t i = 0; i < copy.size(); i++) if (lm_masked(e, i)) copy[i] = sub[isub++];
+    if (normalized) for (size_t i = 0; i < copy.size(); i++) copy[i] = copy[i] * norm[i];
+    return set_source_params(e, e.cur_type, copy.data(), (int)copy.size());
+}
+// update_misfits of the current source (fresh-state semantics)
+static inline bool update_misfits(Engine& e) {
+    if (!calculate_seismograms(e)) return false;
+    scale_seismograms(e);
+    return calculate_misfits(e);
+}
+static inline bool minimize_lm(Engine& e, int& info, int& iterations_, float& misfit_) {
+    if (!e.source_inited) { e.errstr = "no source parameters set"; return false; }
+    if (!update_misfits(e)) return false;
+    const int nsubparams = lm_count_mask(e);
+    int nmisfits = 0;
+    for (auto& r : e.receivers) nmisfits += r.ncomponents;
+    if (nsubparams <= 0 || nmisfits < nsubparams) { e.errstr = "something went wrong in minimize_lm"; return false; }
+    const std::vector<float>& norm = psm_params_norm(e.cur_type);
+    std::vector<float> subparams, subparams_norm;
+    for (size_t i = 0; i < e.cur_params.size(); i++)
+        if (lm_masked(e, i)) { subparams.push_back(e.cur_params[i] / norm[i]); subparams_norm.push_back(norm[i]); }
+    std::vector<float> misfits(nmisfits), diag(nsubparams, 1.f);
+    const float tol = sqrtf(lm_epsmch);
+    e.iterations = 0;
+    // lm_forward_step, minimizer_engine.f90:808-874
+    LmFcn forward = [&](int m, int n, float* x, float* fvec) -> int {
+        float penalty = 0.0f;
+        if (!e.sub_mins.empty() && !e.sub_maxs.empty())
+            for (int i = 0; i < n; i++) {
+                if (x[i] * subparams_norm[i] < e.sub_mins[i]) {
+                    penalty = penalty + fabsf(x[i] * subparams_norm[i] - e.sub_mins[i]) / fabsf(e.sub_maxs[i] - e.sub_mins[i]);
+                    x[i] = e.sub_mins[i] / subparams_norm[i];
+                }
+                if (x[i] * subparams_norm[i] > e.sub_maxs[i]) {
+                    penalty = penalty + fabsf(x[i] * subparams_norm[i] - e.sub_maxs[i]) / fabsf(e.sub_maxs[i] - e.sub_mins[i]);
+                    x[i] = e.sub_maxs[i] / subparams_norm[i];
+                }
+            }
+        if (!set_subparams(e, x, true)) return -2;
+        if (!update_misfits(e)) return -2;
+        int im = 0;
+        for (auto& r : e.receivers)
+            for (int c = 0; c < r.ncomponents; c++) {
+                const float v = r.enabled ? r.misfits[c] : 0.f;
+                if (!std::isfinite(v)) return -2;
+                fvec[im++] = v * (1.0f + penalty);
+            }
+        (void)m;
+        e.iterations = e.iterations + 1;
+        return 0;
+    };
+    int nfev = 0;
+    lm_lmdif(forward, nmisfits, nsubparams, subparams.data(), misfits.data(), tol, tol, 0.f, 500 * (nsubparams + 1), 0.f, diag.data(), 2, 0.01f, info, nfev);
+    if (info == 8) info = 4;
+    iterations_ = e.iterations;
+    misfit_ = e.misfit;
+    return true;
 }
 
 }  // namespace ko

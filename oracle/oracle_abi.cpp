@@ -197,6 +197,48 @@ int oracle_trace_span(void* h, int ix, int iz, int ig, int* span2, int* nstrips)
     return 0;
 }
 // time `ns` evaluations; returns seconds of wall time
+// ---- sub-parameters and Levenberg-Marquardt ----------------------------------------------------------------------
+int oracle_set_source_params_mask(void* h, const int* mask, int n) {
+    Engine& e = *(Engine*)h;
+    if (!e.source_inited) { e.errstr = "no source parameters set"; return 1; }
+    if (n != (int)e.cur_params.size()) { e.errstr = "wrong number of elements in source params mask"; return 1; }
+    e.params_mask.assign(n, 0);
+    for (int i = 0; i < n; i++) e.params_mask[i] = mask[i] ? 1 : 0;
+    e.sub_mins.clear(); e.sub_maxs.clear();
+    return 0;
+}
+int oracle_set_source_subparams(void* h, const float* sub, int n) {
+    Engine& e = *(Engine*)h;
+    if (!e.source_inited) { e.errstr = "no source parameters set"; return 1; }
+    if (n != lm_count_mask(e)) { e.errstr = "wrong number of subparams"; return 1; }
+    return set_subparams(e, sub, false) ? 0 : 1;
+}
+int oracle_set_source_subparams_limits(void* h, const float* mins, const float* maxs, int n) {
+    Engine& e = *(Engine*)h;
+    if (!e.source_inited) { e.errstr = "no source parameters set"; return 1; }
+    if (n != lm_count_mask(e)) { e.errstr = "wrong number of subparam_mins"; return 1; }
+    e.sub_mins.assign(mins, mins + n); e.sub_maxs.assign(maxs, maxs + n);
+    return 0;
+}
+int oracle_get_source_subparams(void* h, float* sub, int cap) {
+    Engine& e = *(Engine*)h;
+    int k = 0;
+    for (size_t i = 0; i < e.cur_params.size(); i++) if (lm_masked(e, i)) { if (k < cap) sub[k] = e.cur_params[i]; k++; }
+    return k;
+}
+int oracle_minimize_lm(void* h, int* info, int* iterations, float* misfit) {
+    Engine& e = *(Engine*)h;
+    return minimize_lm(e, *info, *iterations, *misfit) ? 0 : 1;
+}
+// lmdif on a caller-supplied function (sequential): fcn(user, n, m, x, fvec) returns iflag
+typedef int (*oracle_lm_fcn)(void* user, int n, int m, float* x, float* fvec);
+void oracle_lmdif(oracle_lm_fcn fcn, void* user, int m, int n, float* x, float* fvec, float ftol, float xtol, float gtol, int maxfev, float epsfcn,
+                  float* diag, int mode, float factor, int* info, int* nfev) {
+    lm_lmdif([&](int m_, int n_, float* x_, float* f_) { return fcn(user, n_, m_, x_, f_); }, m, n, x, fvec, ftol, xtol, gtol, maxfev, epsfcn, diag, mode,
+             factor, *info, *nfev);
+}
+float oracle_enorm(int n, const float* x) { return lm_enorm(n, x); }
+
 double oracle_time_eval(void* h, int sourcetype, int ns, int nparams, const float* params) {
     auto t0 = std::chrono::steady_clock::now();
     oracle_eval_sources(h, sourcetype, ns, nparams, params, nullptr, nullptr);

@@ -26,6 +26,8 @@ def lib(wide=False):
         L.oracle_last_error.argtypes = [C.c_void_p]
         L.oracle_get_global_misfit.restype = C.c_float
         L.oracle_time_eval.restype = C.c_double
+        if hasattr(L, "oracle_enorm"):
+            L.oracle_enorm.restype = C.c_float
         for name in ("oracle_destroy", "oracle_set_fresh", "oracle_set_database", "oracle_set_local_interpolation",
                      "oracle_set_spacial_undersampling", "oracle_set_receivers", "oracle_switch_receiver",
                      "oracle_set_source_location", "oracle_set_effective_dt", "oracle_set_ref_seismogram",
@@ -33,7 +35,9 @@ def lib(wide=False):
                      "oracle_set_synthetics_factor", "oracle_set_floating_shiftrange", "oracle_get_nmisfits",
                      "oracle_eval_sources", "oracle_get_global_misfit", "oracle_get_floating_shifts", "oracle_get_seismogram",
                      "oracle_get_probe_spans", "oracle_discretize_source", "oracle_record_indices", "oracle_get_indices",
-                     "oracle_receiver_geometry", "oracle_trace_span", "oracle_time_eval", "oracle_get_strip_spans"):
+                     "oracle_receiver_geometry", "oracle_trace_span", "oracle_time_eval", "oracle_get_strip_spans",
+                     "oracle_set_source_params_mask", "oracle_set_source_subparams", "oracle_set_source_subparams_limits",
+                     "oracle_get_source_subparams", "oracle_minimize_lm", "oracle_lmdif"):
             if hasattr(L, name):
                 getattr(L, name).argtypes = None
         _libs[wide] = L
@@ -182,6 +186,29 @@ class OracleEngine:
     def get_global_misfit(self):
         return float(self.L.oracle_get_global_misfit(self.h))
 
+    # ---- sub-parameters and Levenberg-Marquardt (sequential restatement) ----
+    def set_source_params_mask(self, mask):
+        m = np.ascontiguousarray(np.asarray(mask).astype(bool), dtype=np.int32)
+        self._check(self.L.oracle_set_source_params_mask(self.h, m.ctypes.data_as(ip), C.c_int(m.size)))
+
+    def set_source_subparams(self, sub):
+        p = _f32(sub).ravel()
+        self._check(self.L.oracle_set_source_subparams(self.h, p.ctypes.data_as(fp), C.c_int(p.size)))
+
+    def set_source_subparams_limits(self, mins, maxs):
+        a, b = _f32(mins).ravel(), _f32(maxs).ravel()
+        self._check(self.L.oracle_set_source_subparams_limits(self.h, a.ctypes.data_as(fp), b.ctypes.data_as(fp), C.c_int(a.size)))
+
+    def get_source_subparams(self):
+        out = np.zeros(64, np.float32)
+        n = self.L.oracle_get_source_subparams(self.h, out.ctypes.data_as(fp), C.c_int(out.size))
+        return out[:n].copy()
+
+    def minimize_lm(self):
+        info, it, mis = C.c_int(), C.c_int(), C.c_float()
+        self._check(self.L.oracle_minimize_lm(self.h, C.byref(info), C.byref(it), C.byref(mis)))
+        return info.value, it.value, mis.value
+
     def get_floating_shifts(self):
         out = np.zeros(4096, np.int32)
         n = self.L.oracle_get_floating_shifts(self.h, out.ctypes.data_as(ip))
@@ -221,3 +248,39 @@ class OracleEngine:
         s = np.zeros(2, np.int32); ns = C.c_int()
         self._check(self.L.oracle_trace_span(self.h, C.c_int(ix), C.c_int(iz), C.c_int(ig), s.ctypes.data_as(ip), C.byref(ns)))
         return s, ns.value
+
+
+ORACLE_LM_FCN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, fp, fp)
+
+
+def oracle_lmdif(fcn, x0, m, ftol=None, xtol=None, gtol=0.0, maxfev=None, epsfcn=0.0, diag=None, mode=1, factor=100.0):
+    """sequential lmdif of the oracle on a Python function fcn(x[n]) -> fvec[m] (None = failure). -> (x, fvec, info, nfev)"""
+    L = lib()
+    x = _f32(x0).ravel().copy()
+    n = x.size
+    tol = float(np.sqrt(np.float32(1.192091e-07)))
+    ftol = tol if ftol is None else ftol
+    xtol = tol if xtol is None else xtol
+    maxfev = 200 * (n + 1) if maxfev is None else maxfev
+    d = np.ones(n, np.float32) if diag is None else _f32(diag).ravel().copy()
+    fvec = np.zeros(m, np.float32)
+
+    def cb(user, n_, m_, xp, fpp):
+        xa = np.ctypeslib.as_array(xp, shape=(n_,))
+        out = fcn(xa)
+        if out is None:
+            return -2
+        np.ctypeslib.as_array(fpp, shape=(m_,))[:] = np.asarray(out, np.float32)
+        return 0
+
+    cfn = ORACLE_LM_FCN(cb)
+    info, nfev = C.c_int(), C.c_int()
+    L.oracle_lmdif(cfn, None, C.c_int(m), C.c_int(n), x.ctypes.data_as(fp), fvec.ctypes.data_as(fp), C.c_float(ftol), C.c_float(xtol),
+                   C.c_float(gtol), C.c_int(maxfev), C.c_float(epsfcn), d.ctypes.data_as(fp), C.c_int(mode), C.c_float(factor), C.byref(info),
+                   C.byref(nfev))
+    return x, fvec, info.value, nfev.value
+
+
+def oracle_enorm(x):
+    a = _f32(x).ravel()
+    return float(lib().oracle_enorm(C.c_int(a.size), a.ctypes.data_as(fp)))

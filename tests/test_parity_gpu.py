@@ -478,3 +478,36 @@ def test_circular_and_point_lp_sources(stype, params, norm):
     assert not sg.any() and not so.any()
     tol = misfit_tol(mo, 0.25 if norm.startswith("ampspec") else 0.1)
     assert np.all(np.abs(mg - mo) <= tol), np.abs((mg - mo) / tol).max()
+
+
+def test_minimize_lm_against_the_sequential_restatement():
+    """minimize_lm (minimizer_engine.f90:729-874): lmdif on the per-trace misfits of the masked, normalised parameters, the
+    Jacobian's finite-difference sources evaluated as one GPU batch.  Same start, same settings: both arrive at the source
+    the references were made from.  The two trajectories are not bitwise the same (the misfits agree to 1e-5, and
+    Levenberg-Marquardt amplifies that), so the comparison is on the end point, with the evaluation counts reported."""
+    g, o = engines(sc.small_db(), COMPS6)
+    truth = np.array(sc.BILAT_SMALL[0] if np.ndim(sc.BILAT_SMALL) > 1 else sc.BILAT_SMALL, np.float32)
+    o.eval_sources("bilateral", truth)
+    sc.set_refs_from(o, [g, o], [len(c) for c in COMPS6], scale=1.0)
+    start = truth.copy()
+    start[0] += 0.3; start[1] += 400.0; start[2] -= 300.0; start[3] += 250.0          # time north east depth
+    mask = np.zeros(14, bool); mask[:4] = True
+    res = {}
+    for name, e in (("gpu", g), ("oracle", o)):
+        e.set_misfit_method("l2norm")
+        for ir in range(1, 7):
+            e.set_misfit_taper(ir, *TAPER)
+        e.set_source_params("bilateral", start)
+        e.set_source_params_mask(mask)
+        assert np.array_equal(e.get_source_subparams(), start[:4])
+        e.set_source_subparams_limits(truth[:4] - np.array([2, 3000, 3000, 1500], np.float32), truth[:4] + np.array([2, 3000, 3000, 1500], np.float32))
+        info, iterations, misfit = e.minimize_lm()
+        res[name] = (info, iterations, misfit, e.get_source_subparams())
+    (ig, ng, mg, xg), (io, no, mo, xo) = res["gpu"], res["oracle"]
+    assert 1 <= ig <= 7 and 1 <= io <= 7, (ig, io)
+    assert mg < 2e-3 and mo < 2e-3, (mg, mo)                       # started at a misfit of order 1
+    scale = np.array([1.0, 10000.0, 10000.0, 10000.0])
+    assert np.all(np.abs(xg - truth[:4]) / scale < 2e-3) and np.all(np.abs(xo - truth[:4]) / scale < 2e-3), (xg, xo, truth[:4])
+    assert ng <= 2 * no + 10 and no <= 2 * ng + 10, (ng, no)
+    # the engine is left at the last model evaluated and answers for it
+    assert abs(g.get_global_misfit() - mg) <= 1e-6 * max(mg, 1e-3)
