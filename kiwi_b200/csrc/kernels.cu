@@ -522,8 +522,8 @@ __device__ __forceinline__ void issue_item(ChunkSrc& c, unsigned slot, int dcomp
 }
 
 // out quad(q + m) (+)= sum_t h[t] * A(4q + j - t): E[i] = samples 2i, 2i+1 of the eight samples (previous quad, own quad),
-// G[i] = samples 2i+1, 2i+2.  Lanes without a quad of their own (right of the windows, lane 0, outside the strips) read
-// a quad next to their neighbours' (no extra wavefront) and do not store.
+// G[i] = samples 2i+1, 2i+2.  Lanes without a quad of their own (right of the windows, lane 0, outside the strips; ok == 0)
+// are handed a harmless address to read and do not store.
 __device__ __forceinline__ void rmw_quad(unsigned addr, int ok, const u64* E, const u64* G, float h0, float h1, float h2, float h3, float h4) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t.reg .b64 a0, a1, w;\n\t"
@@ -582,7 +582,8 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
         // ---- corners (gfdb.f90:943-948 weights in the reference's association) -------------------------
         // next group of this warp (for the look-ahead at the end of this group's last chunk)
         const GeoRec* nrec = slot + (sl == 2 ? 0 : sl + 1);
-        const bool next_ok = (ip + nwarps < ngroups) && !(nrec->flags & GEO_SKIP);
+        // (whether the look-ahead may run into the next group is decided where it is needed, inside the last chunk: the record
+        //  after next travels with item 0 of this group's first chunk and is only complete after that item's wait)
         const int tt = rec->tt_begin, nstep = rec->nstep;
         const unsigned rec_s = (unsigned)__cvta_generic_to_shared(rec);
         int q_first = qf_n, q_last = ql_n;
@@ -604,7 +605,7 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
             const int q = q0 + lane - 1;   // lane 0: the quad left of the chunk, only read
             const bool active = lane > 0 && q <= q_last;
             const bool more = q0 + 31 <= q_last;
-            const bool have_next = more || next_ok;
+            bool have_next = more;
             const int lane_on = q <= q_last;   // lanes that hold a quad of the windows (lane 0: the quad left of the chunk)
             // the group's weights are re-read from its record for every chunk rather than kept in registers across the tap loops
             float wc0, wc1, wc2, wc3, f1, f2, f3, f4, f5, f6, cl, sl_;
@@ -642,14 +643,20 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
                 // refill the slot just consumed: a later item of this chunk, or one of the first S items of the next chunk
                 if (j + S < N) {
                     issue_item(src, rs, Seq::step(j + S));
-                } else if (have_next) {
+                } else {
                     const int jj = j + S - N;     // constant after unrolling, < S
                     if (jj == 0) {                // all items of this chunk are on their way: move the source on
-                        int qf, ql;
-                        chunk_src(src, db.slabs, more ? rec : nrec, more ? q0 + 31 : -1, lane, Seq::comp(0), qf, ql);
-                        if (!more) { qf_n = qf; ql_n = ql; }
+                        if (!more) {
+                            __syncwarp();         // lanes 0..7 have waited for their copies of the next record: visible to all lanes now
+                            have_next = (ip + nwarps < ngroups) && !(nrec->flags & GEO_SKIP);
+                        }
+                        if (have_next) {
+                            int qf, ql;
+                            chunk_src(src, db.slabs, more ? rec : nrec, more ? q0 + 31 : -1, lane, Seq::comp(0), qf, ql);
+                            if (!more) { qf_n = qf; ql_n = ql; }
+                        }
                     }
-                    issue_item(src, rs, Seq::step(jj));
+                    if (have_next) issue_item(src, rs, Seq::step(jj));
                 }
                 cp_async_commit();
             }
@@ -683,9 +690,10 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
                     const float h0 = __shfl_sync(0xffffffffu, my_h0, m), h1 = __shfl_sync(0xffffffffu, my_h1, m), h2 = __shfl_sync(0xffffffffu, my_h2, m),
                                 h3 = __shfl_sync(0xffffffffu, my_h3, m), h4 = __shfl_sync(0xffffffffu, my_h4, m);
                     const int ok = active && (unsigned)qrel < (unsigned)nq;
-                    const unsigned a = acc_s + (min((unsigned)qrel, (unsigned)nq - 1u) << 4);
-                    if (H) { rmw_quad(a, ok, E1, G1, h0, h1, h2, h3, h4); rmw_quad(a + strip_bytes, ok, E2, G2, h0, h1, h2, h3, h4); }
-                    if (V) rmw_quad(a + 2 * strip_bytes, ok, E3, G3, h0, h1, h2, h3, h4);
+                    // lanes without a quad read the group's record instead (nobody writes it now) and do not store
+                    const unsigned a = acc_s + ((unsigned)qrel << 4);
+                    if (H) { rmw_quad(ok ? a : rec_s, ok, E1, G1, h0, h1, h2, h3, h4); rmw_quad(ok ? a + strip_bytes : rec_s, ok, E2, G2, h0, h1, h2, h3, h4); }
+                    if (V) rmw_quad(ok ? a + 2 * strip_bytes : rec_s, ok, E3, G3, h0, h1, h2, h3, h4);
                     __syncwarp();
                 }
             }

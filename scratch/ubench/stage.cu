@@ -32,6 +32,40 @@ __global__ void __launch_bounds__(256, 2) k_ldgsts(const char* __restrict__ src,
     if (acc.x + acc.y + acc.z + acc.w == 12345.f) out[0] = 1.f;
 }
 
+__device__ __forceinline__ size_t hash_piece(size_t i, size_t npieces_total) {
+    unsigned long long z = i * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+    return (size_t)(z % npieces_total);
+}
+// same as k_ldgsts but every piece comes from a pseudo-random row of a region of `region_pieces` rows; 4 pieces (corners) per step
+__global__ void __launch_bounds__(256, 2) k_ldgsts_gather(const char* __restrict__ src, size_t npieces_per_warp, size_t stride, size_t region_pieces, int partial, float* out) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t gw = (size_t)blockIdx.x * WARPS + warp;
+    unsigned ring = su32(smem) + warp * STAGES * PIECE + lane * 16;
+    float4 acc = make_float4(0, 0, 0, 0);
+    const bool on = !partial || lane < 20;
+    for (int s = 0; s < STAGES; s++) {
+        const char* p = src + hash_piece(gw * npieces_per_warp + s, region_pieces) * stride + lane * 16;
+        if (on) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + s * PIECE), "l"(p) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    int st = 0;
+    for (size_t i = 0; i < npieces_per_warp; i++) {
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ring + st * PIECE) : "memory");
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        if (i + STAGES < npieces_per_warp) {
+            const char* p = src + hash_piece(gw * npieces_per_warp + i + STAGES, region_pieces) * stride + lane * 16;
+            if (on) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + st * PIECE), "l"(p) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        st = st == STAGES - 1 ? 0 : st + 1;
+    }
+    if (acc.x + acc.y + acc.z + acc.w == 12345.f) out[0] = 1.f;
+}
+
 __global__ void __launch_bounds__(256, 2) k_bulk(const char* __restrict__ src, size_t npieces_per_warp, size_t stride, float* out) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -83,6 +117,17 @@ int main(int argc, char** argv) {
             cudaEventRecord(b); CHECK(cudaEventSynchronize(b));
             float ms; cudaEventElapsedTime(&ms, a, b);
             printf("%s stride %zu: %.3f ms  %.1f GB/s (useful 512 B per piece)\n", which ? "bulk  " : "ldgsts", stride, ms, (double)blocks * WARPS * npw * PIECE / ms / 1e6);
+        }
+    // gather variants: region = whole buffer (DRAM misses), region = 64 MB (L2 hits), partial warps
+    const size_t total_pieces = (size_t)blocks * WARPS * npw;
+    const size_t regions[3] = {total_pieces, (size_t)(64u << 20) / stride, (size_t)(400u << 20) / stride};
+    for (int r = 0; r < 3; r++)
+        for (int partial = 0; partial < 2; partial++) {
+            cudaEventRecord(a);
+            k_ldgsts_gather<<<blocks, 256, smem>>>(d, npw, stride, regions[r], partial, o);
+            cudaEventRecord(b); CHECK(cudaEventSynchronize(b));
+            float ms; cudaEventElapsedTime(&ms, a, b);
+            printf("gather region %zu MB partial %d: %.3f ms %.1f GB/s\n", regions[r] * stride >> 20, partial, ms, (double)total_pieces * (partial ? 320 : 512) / ms / 1e6);
         }
     CHECK(cudaGetLastError());
     return 0;
