@@ -33,6 +33,11 @@ WORKLOADS = {
     # tensors on a Fibonacci sphere, rise time 1 s, effective_dt 0.5 -> 3 centroids per candidate
     "c2": dict(db="bench-L", nx=2000, nz=150, dx=100.0, dz=200.0, nrcv=100, effective_dt=0.5, dmin=45e3, dmax=150e3,
                norm="l2norm", batch=100000, cpu_sample=2000, source="moment_tensor"),
+    # eikonal rupture-front source (rise time -> fold kernel), cosine taper, band-pass filter,
+    # amplitude-spectrum L1 misfit (shared-memory FFT kernel); bord radius 5-12 km so that every centroid stays inside bench-L
+    "c4": dict(db="bench-L", nx=2000, nz=150, dx=100.0, dz=200.0, nrcv=200, effective_dt=0.5, dmin=45e3, dmax=150e3,
+               norm="ampspec_l1norm", batch=32, cpu_sample=1, source="eikonal",
+               taper=([2.0, 6.0, 70.0, 80.0], [0, 1, 1, 0]), filter=([0.01, 0.02, 0.1, 0.2], [0, 1, 1, 0])),
     # quick functional run (kiwibench-size pieces)
     "small": dict(db="bench-L/8", nx=1000, nz=60, dx=100.0, dz=400.0, nrcv=24, effective_dt=0.5, dmin=45e3, dmax=55e3,
                   norm="l2norm", batch=8, cpu_sample=2),
@@ -133,6 +138,11 @@ def configure(eng, db, w, rlat, rlon, rdep):
     eng.set_source_location(30.0, 70.0, 0.0)
     eng.set_effective_dt(w["effective_dt"])
     eng.set_misfit_method(w["norm"])
+    if w.get("taper"):
+        for ir in range(1, len(rlat) + 1):
+            eng.set_misfit_taper(ir, *w["taper"])
+    if w.get("filter"):
+        eng.set_misfit_filter(*w["filter"])
 
 
 def set_references(src, engines, nrcv, dt, scale=1.07):
@@ -198,10 +208,28 @@ def candidates(w, n):
         p = synthetic.moment_tensor_sweep(side, 100)
         reps = -(-n // p.shape[0])
         return "moment_tensor", np.tile(p, (reps, 1))[:n], p[p.shape[0] // 2 + 7]
+    if w.get("source") == "eikonal":
+        # time north east depth moment strike dip rake bord-x bord-y bord-radius nukl-x nukl-y rel-rupture-velocity rise-time
+        # (rise time 0: with a rise time the end of the folded strip -- and with it the padded FFT length of the amplitude-spectrum norm --
+        #  is decided by fp32 noise in the reference itself, DESIGN.md section 2, so the CPU check below would compare two coin flips)
+        base = np.array([0, 0, 0, 15000, 2e20, 91, 87, 164, 0, 0, 9000, 0, 0, 0.8, 0.0], np.float32)
+        p = np.tile(base, (n, 1))
+        i = np.arange(n)
+        p[:, 10] = np.linspace(5000.0, 12000.0, 4)[i % 4]                 # bord radius
+        p[:, 13] = np.linspace(0.7, 0.9, 3)[(i // 4) % 3]                 # relative rupture velocity
+        g5 = np.linspace(-3000.0, 3000.0, 5)
+        p[:, 11] = g5[(i // 12) % 5]; p[:, 12] = g5[(i // 60) % 5]          # nucleation point on a 5 x 5 grid
+        return "eikonal", p.astype(np.float32), base
     return "bilateral", synthetic.bilateral_sweep(n), synthetic.IZMIT
 
 
 def workload_config(w, args, batch):
+    if w.get("source") == "eikonal":
+        return {"workload": "C4 eikonal rupture-front source (bord radius 5-12 km, rupture velocity 0.7-0.9 vs, nucleation on a 5x5 grid) "
+                            "x %d receivers x ned, %s GFDB %dx%dx10, cosine taper + band-pass 0.02-0.1 Hz, %s, bilinear"
+                            % (w["nrcv"], w["db"], w["nx"], w["nz"], w["norm"]),
+                "name": args.workload, "candidates_per_step": batch, "receivers": w["nrcv"], "effective_dt": w["effective_dt"],
+                "cache": "database %s exceeds L2 (no L2 flush needed)" % w["db"]}
     if w.get("source") == "moment_tensor":
         return {"workload": "C2 point moment-tensor grid search: (north, east, depth) lattice x 100 unit tensors, 3 centroids each, x %d receivers "
                             "x ned, %s GFDB %dx%dx10, %s, bilinear" % (w["nrcv"], w["db"], w["nx"], w["nz"], w["norm"]),

@@ -12,6 +12,9 @@
 #include "host_math.hpp"
 #include "lm_host.hpp"
 #include <algorithm>
+#include <atomic>
+#include <thread>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <climits>
@@ -347,15 +350,37 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
     if (n == 0) return 0;
 
     // ---- host preparation of all candidates -------------------------------------------------------
+    static const bool trace = getenv("KIWI_TRACE") != nullptr;   // host-side wall-clock split of a batch on stderr
+    const auto tw0 = std::chrono::steady_clock::now();
     std::vector<kh::SourcePrep> prep(n);
     std::vector<int> bad(n, 0);
     size_t max_groups = 1;
-    for (int i = 0; i < n; i++) {
-        bad[i] = prep_candidate(c, sourcetype, params + (size_t)i * nparams, c->effective_dt, &prep[i], &c->prep_error);
-        if (bad[i]) { prep[i] = kh::SourcePrep(); }
-        if (prep[i].nt > 32) { bad[i] = 1; prep[i] = kh::SourcePrep(); c->prep_error = "more than 32 time centroids per sub-fault"; }   // SYN_MAXTAPS
-        max_groups = std::max(max_groups, (size_t)prep[i].ngroups);
+    {
+        // the fast-marching discretiser of the eikonal sources costs 0.05-0.3 s per candidate (25 m eikonal grid,
+        // source_eikonal.f90:435-517): candidates are independent, so the batch is spread over the host cores
+        std::vector<std::string> errs(n);
+        auto work = [&](int i) {
+            bad[i] = prep_candidate(c, sourcetype, params + (size_t)i * nparams, c->effective_dt, &prep[i], &errs[i]);
+            if (bad[i]) prep[i] = kh::SourcePrep();
+            if (prep[i].nt > 32) { bad[i] = 1; prep[i] = kh::SourcePrep(); errs[i] = "more than 32 time centroids per sub-fault"; }   // SYN_MAXTAPS
+        };
+        const bool heavy = sourcetype == KIWI_SOURCE_EIKONAL || sourcetype == KIWI_SOURCE_MT_EIKONAL;
+        const int nthreads = heavy ? (int)std::min<size_t>((size_t)n, std::max(1u, std::thread::hardware_concurrency())) : 1;
+        if (nthreads > 1) {
+            std::atomic<int> next(0);
+            std::vector<std::thread> pool;
+            for (int t = 0; t < nthreads; t++)
+                pool.emplace_back([&]() { for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) work(i); });
+            for (std::thread& t : pool) t.join();
+        } else {
+            for (int i = 0; i < n; i++) work(i);
+        }
+        for (int i = 0; i < n; i++) {
+            if (!errs[i].empty()) c->prep_error = errs[i];
+            max_groups = std::max(max_groups, (size_t)prep[i].ngroups);
+        }
     }
+    const auto tw1 = std::chrono::steady_clock::now();
     // ---- chunking by workspace budget ---------------------------------------------------------------
     if (c->work_budget == 0) {
         size_t fr = 0, tot = 0;
@@ -639,6 +664,12 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
     cudaEventRecord(c->ev[1], st);
     CU_OK(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&c->ms[4], c->ev[0], c->ev[1]);
+    if (trace) {
+        const auto tw2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[kiwi trace] batch of %d: host prep %.3f ms, rest (uploads, launches, device) %.3f ms, device stages %.3f ms\n", n,
+                std::chrono::duration<double, std::milli>(tw1 - tw0).count(), std::chrono::duration<double, std::milli>(tw2 - tw1).count(),
+                c->ms[0] + c->ms[1] + c->ms[2] + c->ms[3]);
+    }
     return 0;
 }
 
