@@ -22,6 +22,7 @@
 #ifndef KIWI_B200_H
 #define KIWI_B200_H
 
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -246,6 +247,12 @@ int kiwi_last_batch_bytes(kiwi_ctx* ctx, int max_candidates, double* b_alg, doub
  * the engine's stream: [0] discretise, [1] geometry/index pre-pass, [2] synthesis, [3] misfit,
  * [4] whole call incl. H2D/D2H; launches[0..3]: kernel launches per stage */
 int kiwi_last_timing(kiwi_ctx* ctx, float* ms5, int* launches4);
+
+/* Page-locked host memory for the buffers handed to kiwi_eval_sources (parameters in, misfit block out): the
+ * device-to-host copy of a large misfit block (10^5 candidates x 300 traces = 240 MB) then runs at the speed of
+ * the bus instead of through the driver's bounce buffers.  Plain malloc'ed buffers keep working. */
+void* kiwi_host_alloc(size_t bytes);
+void kiwi_host_free(void* p);
 
 #ifdef __cplusplus
 }

@@ -70,6 +70,8 @@ SIGNATURES = {
     "kiwi_trace_span": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_int_p]),
     "kiwi_last_batch_bytes": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, c_int_p, c_ll_p]),
     "kiwi_last_timing": (C.c_int, [C.c_void_p, c_float_p, c_int_p]),
+    "kiwi_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "kiwi_host_free": (None, [C.c_void_p]),
 }
 
 

@@ -1511,6 +1511,13 @@ int kiwi_last_batch_bytes(kiwi_ctx* c, int max_candidates, double* b_alg, double
     return 0;
 }
 
+void* kiwi_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { kiwi_set_error("cudaHostAlloc of %zu bytes failed", bytes); return nullptr; }
+    return p;
+}
+void kiwi_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 int kiwi_last_timing(kiwi_ctx* c, float* ms5, int* launches4) {
     if (!c) return kiwi_set_error("null context");
     if (ms5) for (int i = 0; i < 5; i++) ms5[i] = c->ms[i];

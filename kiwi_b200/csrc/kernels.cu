@@ -921,7 +921,7 @@ __global__ void __launch_bounds__(256) k_fold(const ReceiverDev* __restrict__ rc
 // =================================================================================================
 // K5: scaling + time-domain misfit.  One warp per (candidate, receiver, component).
 // =================================================================================================
-__device__ __forceinline__ int next_pow2(int n) { int m = 1; while (m < n) m <<= 1; return m; }   // comparator.f90:1111-1118
+__device__ __forceinline__ int next_pow2(int n) { return n <= 1 ? 1 : 1 << (32 - __clz(n - 1)); }   // comparator.f90:1111-1118
 // comparator.f90:1092-1109
 __device__ __forceinline__ void allowed_span(int s0, int s1, int minlength, int& n0, int& n1) {
     int slen = s1 - s0 + 1;
@@ -1319,7 +1319,7 @@ __global__ void __launch_bounds__(256) k_misfit_general(const ReceiverDev* __res
 // =================================================================================================
 #define MTC_M 128          // candidates (TMEM lanes) per tile
 #define MTC_N 128          // samples (TMEM columns) per chunk
-#define MTC_K 24           // 3 x 6 split components, padded to 3 MMA k-steps of 8
+#define MTC_K 24           // 4 x 6 split products (hi*hi, hi*lo, lo*hi, lo*lo) = 3 MMA k-steps of 8
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
@@ -1346,17 +1346,18 @@ __global__ void __launch_bounds__(128) k_mt_contract(const ReceiverDev* __restri
                                                       const float* __restrict__ seis, size_t seis_stride,
                                                       const SeisHdr* __restrict__ shdrs, const float* __restrict__ refdata,
                                                       const float* __restrict__ taperdata, int method, float dt, float syn_factor,
-                                                      int nmisfits, float* __restrict__ out) {
+                                                      int nmisfits, float* __restrict__ out, int rcv_per_cta) {
     __shared__ __align__(128) float sA[MTC_M * MTC_K];       // 12 KiB
     __shared__ __align__(128) float sB[MTC_N * MTC_K];       // 12 KiB
-    __shared__ float s_ref[MTC_N], s_tap[MTC_N];
+    __shared__ __align__(16) float s_ref[MTC_N];             // fa * (tapered) reference of the chunk's columns, 0 beyond the chunk
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ unsigned s_tmem;
     __shared__ double s_red[2][4];
 
-    const int loc = blockIdx.x / nrcv, ir = blockIdx.x % nrcv;
-    const ReceiverDev& R = rcv[ir];
-    if (!R.enabled || R.ncomp == 0) return;
+    // one CTA per (grid location, block of receivers): tensor memory, barrier and the candidates' operand tile are set up
+    // once and reused for every receiver of the block
+    const int nrblk = (nrcv + rcv_per_cta - 1) / rcv_per_cta;
+    const int loc = blockIdx.x / nrblk, ir_begin = (blockIdx.x % nrblk) * rcv_per_cta, ir_end = min(nrcv, ir_begin + rcv_per_cta);
     const MtLoc L = locs[loc];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool l1 = method == 2;
@@ -1378,8 +1379,7 @@ __global__ void __launch_bounds__(128) k_mt_contract(const ReceiverDev* __restri
     // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
     const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(MTC_N >> 3) << 17) | ((unsigned)(MTC_M >> 4) << 24);
     const float fa = 1.f, fb = syn_factor;
-    const float* tp = taperdata + R.taper_off;
-    const bool tapered = R.has_taper != 0;
+    unsigned nred = 0;
 
     for (int m0 = 0; m0 < L.mt_count; m0 += MTC_M) {
         // ---- A tile: this thread's candidate tensor, split hi/lo, zero rows beyond the list ----------
@@ -1395,11 +1395,16 @@ __global__ void __launch_bounds__(128) k_mt_contract(const ReceiverDev* __restri
             for (int k = 0; k < 6; k++) { hi[k] = tf32_hi(m[k]); lo[k] = tf32_hi(m[k] - hi[k]); }
             char* a = reinterpret_cast<char*>(sA);
             const float v24[24] = {hi[0], hi[1], hi[2], hi[3], hi[4], hi[5], hi[0], hi[1], hi[2], hi[3], hi[4], hi[5],
-                                   lo[0], lo[1], lo[2], lo[3], lo[4], lo[5], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                                   lo[0], lo[1], lo[2], lo[3], lo[4], lo[5], lo[0], lo[1], lo[2], lo[3], lo[4], lo[5]};
 #pragma unroll
             for (int c4 = 0; c4 < 6; c4++)
                 *reinterpret_cast<float4*>(a + operand_off(tid, 4 * c4, MTC_M)) = make_float4(v24[4 * c4], v24[4 * c4 + 1], v24[4 * c4 + 2], v24[4 * c4 + 3]);
         }
+        for (int ir = ir_begin; ir < ir_end; ir++) {
+        const ReceiverDev& R = rcv[ir];
+        if (!R.enabled || R.ncomp == 0) continue;
+        const float* tp = taperdata + R.taper_off;
+        const bool tapered = R.has_taper != 0;
         for (int ic = 0; ic < R.ncomp; ic++) {
             const size_t item0 = ((size_t)(loc * 6) * nrcv + ir) * KIWI_MAX_COMP + ic;     // basis tensor 0 of this location
             const size_t item_stride = (size_t)nrcv * KIWI_MAX_COMP;                        // next basis tensor
@@ -1427,27 +1432,41 @@ __global__ void __launch_bounds__(128) k_mt_contract(const ReceiverDev* __restri
             // (ii) columns x in [xs, xe] come out of the tensor-core contraction, 128 at a time; xe = sds1 is
             // always included when the span reaches past it, its value is the continuation (comparator.f90:264-267)
             const int xs = max(p0, sds0), xe = min(p1, sds1) < xs ? -1 : ((p1 > sds1) ? sds1 : min(p1, sds1));
+            // last sample of this thread's candidate (continued to the right, comparator.f90:264-267): six fp32 fmas
             float e_last = 0.f;
+            if (p1 > sds1 && sds1 >= sds0 && have) {
+#pragma unroll
+                for (int k = 0; k < 6; k++)
+                    e_last = fmaf(__ldg(&mts[(size_t)(L.mt_begin + j) * 6 + k]), __ldg(seis + (item0 + (size_t)k * item_stride) * seis_stride + (sds1 - sh.base)), e_last);
+            }
+            // column x = c0 + tid of the chunk: six basis samples, already multiplied by the taper and the synthetics factor
+            // (moment = 1 for a moment-tensor source, source_moment_tensor.f90:199), and fa * reference: the epilogue is
+            // r = fa*ref - acc and nothing else.  The next chunk's column is fetched while this chunk is in the tensor core.
+            float colv[6], colref;
+            auto fetch_col = [&](int c0) {
+                const int x = c0 + tid;
+                const bool in = x <= xe;
+                const float scale = in ? fb * tapval(x) : 0.f;
+#pragma unroll
+                for (int k = 0; k < 6; k++) colv[k] = in ? __ldg(seis + (item0 + (size_t)k * item_stride) * seis_stride + (x - sh.base)) * scale : 0.f;
+                colref = in ? fa * refval(x) : 0.f;
+            };
+            if (xe >= xs) fetch_col(xs);
             for (int c0 = xs; xe >= xs && c0 <= xe; c0 += MTC_N) {
                 // ---- B chunk: six basis rows, split hi/lo -------------------------------------------------
                 {
-                    const int x = c0 + tid;
-                    const bool in = x <= xe;
                     char* bsm = reinterpret_cast<char*>(sB);
                     float hi[6], lo[6];
 #pragma unroll
-                    for (int k = 0; k < 6; k++) {
-                        const float v = in ? __ldg(seis + (item0 + (size_t)k * item_stride) * seis_stride + (x - sh.base)) : 0.f;
-                        hi[k] = tf32_hi(v); lo[k] = tf32_hi(v - hi[k]);
-                    }
+                    for (int k = 0; k < 6; k++) { hi[k] = tf32_hi(colv[k]); lo[k] = tf32_hi(colv[k] - hi[k]); }
                     const float v24[24] = {hi[0], hi[1], hi[2], hi[3], hi[4], hi[5], lo[0], lo[1], lo[2], lo[3], lo[4], lo[5],
-                                           hi[0], hi[1], hi[2], hi[3], hi[4], hi[5], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                                           hi[0], hi[1], hi[2], hi[3], hi[4], hi[5], lo[0], lo[1], lo[2], lo[3], lo[4], lo[5]};
 #pragma unroll
                     for (int c4 = 0; c4 < 6; c4++)
                         *reinterpret_cast<float4*>(bsm + operand_off(tid, 4 * c4, MTC_N)) = make_float4(v24[4 * c4], v24[4 * c4 + 1], v24[4 * c4 + 2], v24[4 * c4 + 3]);
-                    s_ref[tid] = in ? refval(x) : 0.f;
-                    s_tap[tid] = in ? tapval(x) : 0.f;
+                    s_ref[tid] = colref;
                 }
+                if (c0 + MTC_N <= xe) fetch_col(c0 + MTC_N);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> async proxy (tensor core)
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncthreads();
@@ -1483,7 +1502,7 @@ __global__ void __launch_bounds__(128) k_mt_contract(const ReceiverDev* __restri
                 }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const int ncol = min(MTC_N, xe - c0 + 1);
-                for (int cc = 0; cc < ncol; cc += 32) {
+                for (int cc = 0; cc < ncol; cc += 32) {   // (columns beyond ncol: zero basis rows and zero reference, r = 0)
                     unsigned v[32];
                     const unsigned taddr = tmem + ((unsigned)(warp * 32) << 16) + (unsigned)cc;
                     asm volatile(
@@ -1496,19 +1515,27 @@ __global__ void __launch_bounds__(128) k_mt_contract(const ReceiverDev* __restri
                         : "r"(taddr)
                         : "memory");
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    float part = 0.f;   // 32 terms in fp32, then into the fp64 sum (comparator.f90:639-659 sums in double)
+                    // 32 terms in fp32 (two interleaved partial sums, packed arithmetic), then into the fp64 sum
+                    // (comparator.f90:639-659 sums in double)
+                    u64 part2 = 0ull;
+                    const float4* rp = reinterpret_cast<const float4*>(s_ref + cc);
 #pragma unroll
-                    for (int u = 0; u < 32; u++) {
-                        if (cc + u < ncol) {
-                            const float d = __uint_as_float(v[u]);
-                            const float b = d * s_tap[cc + u];       // moment = 1 for a moment-tensor source (source_moment_tensor.f90:199)
-                            const float a = s_ref[cc + u];
-                            const float r = fa * a - fb * b;
-                            part += l1 ? fabsf(r) : r * r;
-                            if (c0 + cc + u == sds1) e_last = d;
+                    for (int u4 = 0; u4 < 8; u4++) {
+                        const float4 a4 = rp[u4];
+                        u64 r01 = pk2(a4.x, a4.y), r23 = pk2(a4.z, a4.w);
+                        ffma2(r01, -1.f, pk2(__uint_as_float(v[4 * u4]), __uint_as_float(v[4 * u4 + 1])));
+                        ffma2(r23, -1.f, pk2(__uint_as_float(v[4 * u4 + 2]), __uint_as_float(v[4 * u4 + 3])));
+                        if (l1) {
+                            r01 &= 0x7fffffff7fffffffull; r23 &= 0x7fffffff7fffffffull;
+                            ffma2(part2, 1.f, r01); ffma2(part2, 1.f, r23);
+                        } else {
+                            asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(part2) : "l"(r01));
+                            asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(part2) : "l"(r23));
                         }
                     }
-                    acc += (double)part;
+                    float pa, pb;
+                    unpk2(part2, pa, pb);
+                    acc += (double)(pa + pb);
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncthreads();      // accumulator and operand tiles are free again
@@ -1522,9 +1549,10 @@ __global__ void __launch_bounds__(128) k_mt_contract(const ReceiverDev* __restri
             double accn = 0.;
             for (int x = q0 + tid; x <= q1; x += MTC_M) { const float a = refval(x); accn += l1 ? (double)fabsf(a) : (double)a * (double)a; }
             for (int ofs = 16; ofs; ofs >>= 1) accn += __shfl_xor_sync(0xffffffffu, accn, ofs);
-            if (lane == 0) s_red[ic & 1][warp] = accn;
+            const unsigned rb = nred++ & 1u;   // alternating buffers: one barrier between the writes and the reads is enough
+            if (lane == 0) s_red[rb][warp] = accn;
             __syncthreads();
-            accn = s_red[ic & 1][0] + s_red[ic & 1][1] + s_red[ic & 1][2] + s_red[ic & 1][3];
+            accn = s_red[rb][0] + s_red[rb][1] + s_red[rb][2] + s_red[rb][3];
             if (o) {
                 float mis, nf;
                 if (l1) { mis = (float)((double)dt * acc); nf = fa * (float)((double)dt * accn); }
@@ -1532,6 +1560,7 @@ __global__ void __launch_bounds__(128) k_mt_contract(const ReceiverDev* __restri
                 if (p1 < p0) mis = 0.f;
                 o[0] = mis; o[1] = nf;
             }
+        }
         }
         __syncthreads();   // before the next A tile overwrites sA
     }
@@ -1678,8 +1707,14 @@ void launch_mt_contract(const ReceiverDev* rcv, int nrcv, const MtLoc* locs, int
                         size_t seis_stride, const SeisHdr* shdrs, const float* refdata, const float* taperdata, int method, float dt,
                         float syn_factor, int nmisfits, float* out, cudaStream_t st) {
     if (nloc * nrcv > 0)
-        k_mt_contract<<<nloc * nrcv, 128, 0, st>>>(rcv, nrcv, locs, mts, cand_of, seis, seis_stride, shdrs, refdata, taperdata, method, dt,
-                                                  syn_factor, nmisfits, out);
+    {
+        // receivers per CTA: enough CTAs for a few waves over the 148 SMs x 4 resident CTAs, as few set-ups as possible
+        int rpc = 1;
+        while (rpc < nrcv && (long long)nloc * ((nrcv + 2 * rpc - 1) / (2 * rpc)) >= 148LL * 4 * 6) rpc *= 2;
+        const int nrblk = (nrcv + rpc - 1) / rpc;
+        k_mt_contract<<<nloc * nrblk, 128, 0, st>>>(rcv, nrcv, locs, mts, cand_of, seis, seis_stride, shdrs, refdata, taperdata, method, dt,
+                                                   syn_factor, nmisfits, out, rpc);
+    }
 }
 
 cudaError_t launch_fold(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, float* seis, size_t seis_stride, SeisHdr* shdrs,

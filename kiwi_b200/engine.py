@@ -133,6 +133,9 @@ class Engine:
             self.set_crust2x2(CRUST2X2_TABLE)
 
     def close(self):
+        if getattr(self, "_pin_ptr", None):
+            lib.kiwi_host_free(self._pin_ptr)
+            self._pin_ptr, self._pin_bytes = None, 0
         if self._h:
             lib.kiwi_destroy(self._h)
             self._h = None
@@ -245,8 +248,10 @@ class Engine:
     def nmisfits(self):
         return lib.kiwi_get_nmisfits(self._h)
 
-    def eval_sources(self, sourcetype, params):
-        """Batched set_source_params + get_misfits: returns (misfits[ns, nmisfits, 2], status[ns])."""
+    def eval_sources(self, sourcetype, params, pinned=False):
+        """Batched set_source_params + get_misfits: returns (misfits[ns, nmisfits, 2], status[ns]).
+        pinned=True returns the block in page-locked memory owned by the engine (valid until the next pinned call):
+        the device-to-host copy of a large block then runs at bus speed."""
         if isinstance(sourcetype, str):
             sourcetype = SOURCE_TYPES[sourcetype]
         p = _f32(params)
@@ -254,11 +259,24 @@ class Engine:
             p = p[None, :]
         ns, nparams = p.shape
         nm = self.nmisfits
-        out = np.empty((ns, nm, 2), dtype=np.float32)
+        out = self._pinned_out(ns, nm) if pinned else np.empty((ns, nm, 2), dtype=np.float32)
         status = np.zeros(ns, dtype=np.int32)
         _check(lib.kiwi_eval_sources(self._h, sourcetype, ns, nparams, _fp(p), _fp(out), status.ctypes.data_as(c_int_p)))
         self._last_ns = ns
         return out, status
+
+    def _pinned_out(self, ns, nm):
+        """misfit block in page-locked memory owned by the engine (kiwi_host_alloc), reused by the next pinned call"""
+        need = max(ns * nm * 2, 1) * 4
+        if getattr(self, "_pin_bytes", 0) < need:
+            if getattr(self, "_pin_ptr", None):
+                lib.kiwi_host_free(self._pin_ptr)
+            self._pin_ptr = lib.kiwi_host_alloc(need)
+            if not self._pin_ptr:
+                raise KiwiError(lib.kiwi_last_error().decode())
+            self._pin_bytes = need
+        buf = (C.c_float * (ns * nm * 2)).from_address(self._pin_ptr)
+        return np.frombuffer(buf, dtype=np.float32).reshape(ns, nm, 2)
 
     def eval_sources_on_device(self, sourcetype, params):
         """Evaluate and leave the misfit cube on the GPU (for outer_misfits); returns status[ns]."""
