@@ -212,11 +212,16 @@ __device__ __forceinline__ void set_span(const GfdbDev& db, const int inode[4], 
         }
 }
 
+// SINGLE: every candidate has one group (point sources: the 6 x nloc x nrcv basis syntheses of a moment-tensor grid search are
+// 6e5 pairs of one group each): one THREAD per (candidate, receiver) instead of one CTA, no block reductions.
+template <bool SINGLE>
 __global__ void __launch_bounds__(256) k_geometry(GfdbDev db, const ReceiverDev* __restrict__ rcv, int nrcv,
                                                    const CandDev* __restrict__ cands, GroupSoA g, int ngroups_total, int interpolate,
                                                    int xunder, int zunder, GeoRec* __restrict__ recs, size_t rec_stride,
-                                                   PairHdr* __restrict__ hdrs, int* __restrict__ tmax) {
-    const int pair = blockIdx.x;
+                                                   PairHdr* __restrict__ hdrs, int* __restrict__ tmax, int npairs) {
+    const int pair_ = SINGLE ? (int)(blockIdx.x * blockDim.x + threadIdx.x) : (int)blockIdx.x;
+    const bool valid = !SINGLE || pair_ < npairs;      // (threads past the end stay for the warp shuffles at the bottom)
+    const int pair = valid ? pair_ : 0;
     const int b = pair / nrcv, ir = pair % nrcv;
     const ReceiverDev& R = rcv[ir];
     const CandDev cand = cands[b];
@@ -232,8 +237,8 @@ __global__ void __launch_bounds__(256) k_geometry(GfdbDev db, const ReceiverDev*
     SpanAcc urot, n1all, n2all, s3; urot.init(); n1all.init(); n2all.init(); s3.init();
     int last_rot = -1, any_nonrot = 0;
 
-    if (R.enabled && cand.status == 0) {
-        for (int ip = threadIdx.x; ip < cand.ngroups; ip += blockDim.x) {
+    if (valid && R.enabled && cand.status == 0) {
+        for (int ip = SINGLE ? 0 : (int)threadIdx.x; ip < (SINGLE ? min(cand.ngroups, 1) : cand.ngroups); ip += SINGLE ? 1 : (int)blockDim.x) {
             const int gi = cand.group_begin + ip;
             const float dnorth = g.north[gi], deast = g.east[gi], depth = g.depth[gi];
             double azi, bazi, dist;
@@ -318,6 +323,18 @@ __global__ void __launch_bounds__(256) k_geometry(GfdbDev db, const ReceiverDev*
                 if (need_v) { set_span(db, inode, ncorner, set3, n3, lo, hi); s3.add(lo + smin, hi + smax + 1); }
             }
         }
+    }
+    if (SINGLE) {   // the pair's header straight from this thread's spans (S1 = Urot u N1, S2 = Urot u N2, see below)
+        PairHdr h;
+        h.s1lo = min(urot.lo, n1all.lo); h.s1hi = max(urot.hi, n1all.hi);
+        h.s2lo = min(urot.lo, n2all.lo); h.s2hi = max(urot.hi, n2all.hi);
+        h.s3lo = s3.lo; h.s3hi = s3.hi;
+        const int lo = min(min(h.s1lo, h.s2lo), h.s3lo), hi = max(max(h.s1hi, h.s2hi), h.s3hi);
+        if (hi < lo || !valid) { h.out0 = 0; h.T = 0; } else { h.out0 = lo; h.T = hi - lo + 1; }
+        if (valid) hdrs[pair] = h;
+        const int wt = warp_max(h.T), wlo = warp_min(h.T > 0 ? lo : INT_MAX), whi = warp_max(h.T > 0 ? hi : INT_MIN);
+        if ((threadIdx.x & 31) == 0 && wt > 0) { atomicMax(tmax, wt); atomicMin(tmax + 1, wlo); atomicMax(tmax + 2, whi); }
+        return;
     }
     // block reduction
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1660,9 +1677,17 @@ void launch_expand_centroids(CandDev cand, GroupSoA g, TapSoA taps, int ngroups_
 }
 void launch_geometry(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, int ngroups_total,
                      int interpolate, int xunder, int zunder, GeoRec* recs, size_t rec_stride, PairHdr* hdrs, int* tmax, cudaStream_t st) {
-    // one thread per group: a CTA no wider than the longest group list (a point moment tensor has one group)
+    const int npairs = ncand * nrcv;
+    if (npairs <= 0) return;
+    if (rec_stride == 1) {   // single-group candidates: one thread per pair
+        k_geometry<true><<<(npairs + 127) / 128, 128, 0, st>>>(db, rcv, nrcv, cands, g, ngroups_total, interpolate, xunder, zunder, recs, rec_stride, hdrs,
+                                                           tmax, npairs);
+        return;
+    }
+    // one thread per group: a CTA no wider than the longest group list
     const int threads = (int)std::min<size_t>(256, std::max<size_t>(32, (rec_stride + 31) / 32 * 32));
-    k_geometry<<<ncand * nrcv, threads, 0, st>>>(db, rcv, nrcv, cands, g, ngroups_total, interpolate, xunder, zunder, recs, rec_stride, hdrs, tmax);
+    k_geometry<false><<<npairs, threads, 0, st>>>(db, rcv, nrcv, cands, g, ngroups_total, interpolate, xunder, zunder, recs, rec_stride, hdrs, tmax,
+                                                 npairs);
 }
 size_t synth_smem_bytes(int nwarps, int nq) {
     return (size_t)nwarps * 3 * nq * (sizeof(float4) + sizeof(float)) + 16 + (size_t)nwarps * 3 * sizeof(GeoRec) +
