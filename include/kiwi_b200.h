@@ -81,6 +81,14 @@ int kiwi_gfdb_build_ahfull(kiwi_gfdb* db, float rho, float alpha, float beta, co
 /* flat binary file "KGF1" (this repo's own format) */
 int kiwi_gfdb_write(const kiwi_gfdb* db, const char* path);
 kiwi_gfdb* kiwi_gfdb_read(const char* path);
+/* Kiwi's own HDF5 database <basepath>.index + <basepath>.<i>.chunk (gfdb_io_hdf.f90:119-180, 429-605; gfdb.f90:1437-1467)
+ * through a minimal parser of the published HDF5 file format (no libhdf5): files as HDF5 1.6/1.8 write them by default. */
+kiwi_gfdb* kiwi_gfdb_read_hdf(const char* basepath);
+/* One dataset of the root group of an HDF5 file through the same parser (the index file of a database is a set of these,
+ * h5_open_scalar gfdb_io_hdf.f90:63-83).  name == NULL: buf receives the NUL-separated names of the root group's members.
+ * dtype_class: 0 integer, 1 float, 7 reference ...; dims8: up to 8 extents; *nbytes: size of the data / of the name list. */
+int kiwi_h5_read_root_dataset(const char* path, const char* name, int* dtype_class, int* dtype_size, int* rank, long long* dims8, void* buf,
+                              long long cap, long long* nbytes, int* nattrs);
 /* gfdb_info: grid metadata */
 int kiwi_gfdb_meta(const kiwi_gfdb* db, int* nx, int* nz, int* ng, float* dt, float* dx, float* dz, float* firstx,
                    float* firstz, long long* ntraces, long long* nsamples);

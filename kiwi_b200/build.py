@@ -25,7 +25,7 @@ CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math"
              "-I" + os.path.join(CUDA_HOME, "include"), "-Wall", "-Wno-unused-function", "-Wno-misleading-indentation"]
 
 CU_SOURCES = ["kernels.cu"]
-CXX_SOURCES = ["engine.cpp", "host_math.cpp", "gfdb_host.cpp", "source_eikonal_host.cpp", "lm_host.cpp"]
+CXX_SOURCES = ["engine.cpp", "host_math.cpp", "gfdb_host.cpp", "source_eikonal_host.cpp", "lm_host.cpp", "gfdb_hdf_host.cpp"]
 
 
 def _newer(target, deps):

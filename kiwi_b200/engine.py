@@ -75,6 +75,11 @@ class Gfdb:
     def read(cls, path):
         return cls(lib.kiwi_gfdb_read(str(path).encode()))
 
+    @classmethod
+    def read_hdf(cls, basepath):
+        """Kiwi's own HDF5 database <basepath>.index + <basepath>.<i>.chunk (gfdb_io_hdf.f90), no libhdf5 needed."""
+        return cls(lib.kiwi_gfdb_read_hdf(str(basepath).encode()))
+
     def write(self, path):
         _check(lib.kiwi_gfdb_write(self._h, str(path).encode()))
 
@@ -455,3 +460,28 @@ def lmdif_batched(fcn, x0, m, ftol=None, xtol=None, gtol=0.0, maxfev=None, epsfc
     _check(lib.kiwi_lmdif_batched(C.cast(cfn, C.c_void_p), None, m, n, _fp(x), _fp(fvec), ftol, xtol, gtol, maxfev, epsfcn, _fp(d), mode, factor,
                                   info, nfev))
     return x, fvec, info.value, nfev.value
+
+
+def h5_root_members(path):
+    """names of the members of the root group of an HDF5 file (kiwi_h5_read_root_dataset with name = NULL)"""
+    n = C.c_longlong()
+    _check(lib.kiwi_h5_read_root_dataset(str(path).encode(), None, None, None, None, None, None, 0, n, None))
+    buf = C.create_string_buffer(max(int(n.value), 1))
+    _check(lib.kiwi_h5_read_root_dataset(str(path).encode(), None, None, None, None, None, buf, n.value, n, None))
+    return [s.decode() for s in buf.raw[:n.value].split(b"\0") if s]
+
+
+def h5_read_root_dataset(path, name):
+    """-> (array, nattrs) of a dataset in the root group of an HDF5 file, through the library's minimal parser"""
+    cls, sz, rank, na = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    dims = (C.c_longlong * 8)()
+    nb = C.c_longlong()
+    _check(lib.kiwi_h5_read_root_dataset(str(path).encode(), name.encode(), cls, sz, rank, dims, None, 0, nb, na))
+    raw = np.zeros(max(int(nb.value), 1), dtype=np.uint8)
+    _check(lib.kiwi_h5_read_root_dataset(str(path).encode(), name.encode(), cls, sz, rank, dims, raw.ctypes.data_as(C.c_void_p), raw.size, nb, na))
+    kinds = {(0, 4): np.int32, (0, 8): np.int64, (0, 2): np.int16, (0, 1): np.int8, (1, 4): np.float32, (1, 8): np.float64, (7, 8): np.uint64}
+    dt = kinds.get((cls.value, sz.value))
+    if dt is None:
+        raise KiwiError("unsupported element type: class %d, %d bytes" % (cls.value, sz.value))
+    shape = tuple(int(dims[i]) for i in range(rank.value))
+    return raw[:nb.value].view(dt).reshape(shape), na.value
