@@ -111,7 +111,10 @@ bool do_command(State& S, const std::string& cmd, const std::vector<std::string>
     if (cmd == "set_database") {
         if (w.size() < 2) return fail("usage: set_database dbpath [ nipx nipz ]");
         if (w.size() >= 4 && (atoi(w[2].c_str()) != 1 || atoi(w[3].c_str()) != 1)) return fail("set_database: trace interpolation (nipx, nipz > 1) is not available");
-        kiwi_gfdb* db = kiwi_gfdb_read(w[1].c_str());
+        // a Kiwi database is <dbpath>.index + <dbpath>.<i>.chunk (HDF5, gfdb.f90:209-211); a single file is this library's KGF1 dump
+        kiwi_gfdb* db = nullptr;
+        if (FILE* probe = fopen((w[1] + ".index").c_str(), "rb")) { fclose(probe); db = kiwi_gfdb_read_hdf(w[1].c_str()); }
+        else db = kiwi_gfdb_read(w[1].c_str());
         if (!db) return cfail();
         if (kiwi_set_database(S.ctx, db)) { kiwi_gfdb_destroy(db); return cfail(); }
         if (S.db) kiwi_gfdb_destroy(S.db);
