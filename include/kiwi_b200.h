@@ -196,6 +196,16 @@ int kiwi_set_source_params(kiwi_ctx* ctx, int sourcetype, int nparams, const flo
 int kiwi_get_misfits(kiwi_ctx* ctx, float* misfits, int cap_pairs, int* nmisfits);   /* minimizer_engine.f90:1130-1172 */
 int kiwi_get_global_misfit(kiwi_ctx* ctx, float* misfit);                            /* minimizer_engine.f90:1083-1093 */
 
+/* ---- ground-motion diagnostics of the synthetics -----------------------------------
+ * get_peak_amplitudes (minimizer_engine.f90:1174-1212, differentiate 1 = velocity, 2 = acceleration) and
+ * get_arias_intensities (:1214-1245): one value per enabled receiver, over its vertical and/or complete
+ * horizontal pair of components (receiver.f90:505-596), for the source set by kiwi_set_source_params;
+ * kiwi_eval_ground_motion does all three for a batch: out[ns][enabled receivers][3] = peak velocity, peak
+ * acceleration, Arias intensity.  Probe spans as in a fresh process; not available with a misfit filter set. */
+int kiwi_get_peak_amplitudes(kiwi_ctx* ctx, int differentiate, float* maxabs, int cap, int* n);
+int kiwi_get_arias_intensities(kiwi_ctx* ctx, float* intensities, int cap, int* n);
+int kiwi_eval_ground_motion(kiwi_ctx* ctx, int sourcetype, int ns, int nparams, const float* params, float* out, int* status);
+
 /* ---- Levenberg-Marquardt inversion ----------------------------------------
  * The sub-parameter machinery of the parameterised source (parameterized_source.f90:244-309,
  * source_all.f90:377-428) and minimize_lm (minimizer_engine.f90:729-874): MINPACK lmdif on the

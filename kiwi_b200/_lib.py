@@ -57,6 +57,9 @@ SIGNATURES = {
     "kiwi_set_source_params": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p]),
     "kiwi_get_misfits": (C.c_int, [C.c_void_p, c_float_p, C.c_int, c_int_p]),
     "kiwi_get_global_misfit": (C.c_int, [C.c_void_p, c_float_p]),
+    "kiwi_get_peak_amplitudes": (C.c_int, [C.c_void_p, C.c_int, c_float_p, C.c_int, c_int_p]),
+    "kiwi_get_arias_intensities": (C.c_int, [C.c_void_p, c_float_p, C.c_int, c_int_p]),
+    "kiwi_eval_ground_motion": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p, c_int_p]),
     "kiwi_set_source_params_mask": (C.c_int, [C.c_void_p, c_int_p, C.c_int]),
     "kiwi_set_source_subparams": (C.c_int, [C.c_void_p, c_float_p, C.c_int]),
     "kiwi_set_source_subparams_limits": (C.c_int, [C.c_void_p, c_float_p, c_float_p, C.c_int]),

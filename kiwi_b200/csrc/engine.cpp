@@ -124,6 +124,7 @@ struct kiwi_ctx {
     bool mt_grid_enabled = true;             // point moment-tensor grid searches go through the tcgen05 contraction
     DevBuf d_map, d_status_out;
     DevBuf d_taprec;              // shift table of the current batch (k_tap_table)
+    DevBuf d_gm;                  // ground-motion values [cand][rcv][3]
     bool dedup_enabled = true;               // candidates that differ only in the moment share one synthesis
     DevBuf d_mtlocs, d_mts, d_candof, d_orc, d_orw, d_obw, d_oout, d_obest, d_obestv;
     int last_eval_ns = 0;                    // candidates whose misfit block sits in d_out (kiwi_eval_sources)
@@ -266,7 +267,7 @@ int prep_candidate(kiwi_ctx* c, int sourcetype, const float* p, float effective_
 // (point moment-tensor grid search): candidates [cand0, cand0+ncand) of the batch, their rows in `seis`
 struct SynthHook {
     int align = 1;   // sub-chunks hold a multiple of `align` candidates
-    std::function<int(int cand0, int ncand, const float* seis, size_t seis_stride, const SeisHdr* shdrs)> fn;
+    std::function<int(int cand0, int ncand, const float* seis, size_t seis_stride, const SeisHdr* shdrs, const CandDev* d_cands)> fn;
 };
 
 int eval_mt_grid(kiwi_ctx* c, int n, const float* params, float* d_out, int* h_status, bool* used);
@@ -568,7 +569,7 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
             }
             cudaEventRecord(c->ev[4], st);
             if (hook && hook->fn) {
-                if (hook->fn(b0 + s0, ns_, c->d_seis.as<float>(), seis_stride, c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP)) return 1;
+                if (hook->fn(b0 + s0, ns_, c->d_seis.as<float>(), seis_stride, c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, c->d_cands.as<CandDev>() + s0)) return 1;
                 c->launches[3] += 1;
             }
             // misfit stage: one slot per candidate; with shared syntheses the slots of this sub-chunk come with a map
@@ -728,7 +729,7 @@ int eval_mt_grid(kiwi_ctx* c, int n, const float* params, float* d_out, int* h_s
     const int nrcv = (int)c->rcv.size();
     SynthHook hook;
     hook.align = 6;
-    hook.fn = [&](int cand0, int ncand, const float* seis, size_t seis_stride, const SeisHdr* shdrs) -> int {
+    hook.fn = [&](int cand0, int ncand, const float* seis, size_t seis_stride, const SeisHdr* shdrs, const CandDev*) -> int {
         const int l0 = cand0 / 6, nl = ncand / 6;
         launch_mt_contract(c->d_rcv.as<ReceiverDev>(), nrcv, reinterpret_cast<const MtLoc*>(c->d_mtlocs.p) + l0, nl, c->d_mts.as<float>(),
                            c->d_candof.as<int>(), seis, seis_stride, shdrs, c->d_refdata.as<float>(), c->d_taper.as<float>(), c->misfit_method,
@@ -802,7 +803,7 @@ void kiwi_destroy(kiwi_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->d_slabs, &c->d_nodes, &c->d_tspan, &c->d_rcv, &c->d_refdata, &c->d_taper, &c->d_cands, &c->d_bilat, &c->d_gf, &c->d_gi,
-                      &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift, &c->d_map, &c->d_status_out, &c->d_taprec, &c->d_mtlocs, &c->d_mts, &c->d_candof, &c->d_orc, &c->d_orw, &c->d_obw, &c->d_oout, &c->d_obest, &c->d_obestv})
+                      &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift, &c->d_map, &c->d_status_out, &c->d_taprec, &c->d_gm, &c->d_mtlocs, &c->d_mts, &c->d_candof, &c->d_orc, &c->d_orw, &c->d_obw, &c->d_oout, &c->d_obest, &c->d_obestv})
         b->release();
     c->h_stage.release(); c->h_out.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -1172,6 +1173,84 @@ int kiwi_get_global_misfit(kiwi_ctx* c, float* misfit) {
     CU_OK(cudaSetDevice(c->device));
     if (ensure_single(c, true)) return 1;
     return kiwi_global_misfits(1, c->nmisfits, c->src_misfits.data(), misfit);
+}
+
+// ---- ground-motion diagnostics: get_peak_amplitudes / get_arias_intensities ------------------------
+namespace {
+int require_no_filter(kiwi_ctx* c) {
+    for (const HostReceiver& h : c->rcv)
+        if (h.enabled && !h.filter_x.empty()) return kiwi_set_error("peak amplitudes / Arias intensities of band-pass filtered synthetics are not available");
+    return 0;
+}
+// values of the enabled receivers, in order, from a [nrcv][3] block
+int pick_enabled(kiwi_ctx* c, const float* gm3, int which, float* out, int cap, int* n) {
+    int k = 0;
+    for (size_t ir = 0; ir < c->rcv.size(); ir++) {
+        if (!c->rcv[ir].enabled) continue;
+        if (k < cap) out[k] = gm3[3 * ir + (which - 1)];
+        k++;
+    }
+    if (n) *n = k;
+    return k <= cap ? 0 : kiwi_set_error("buffer too small: need %d values", k);
+}
+int single_ground_motion(kiwi_ctx* c, int which, float* out, int cap, int* n) {
+    if (!c) return kiwi_set_error("null context");
+    CU_OK(cudaSetDevice(c->device));
+    if (require_no_filter(c)) return 1;
+    if (ensure_single(c, false)) return 1;   // update_syn_probes
+    const int nrcv = (int)c->rcv.size();
+    std::vector<float> gm((size_t)3 * std::max(nrcv, 1), 0.f);
+    if (c->last.seis_valid) {
+        CU_OK(c->d_gm.ensure(sizeof(float) * 3 * (size_t)nrcv));
+        launch_ground_motion(c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>(), 1, c->d_seis.as<float>(), c->last.seis_stride,
+                             c->d_shdrs.as<SeisHdr>(), c->d_taper.as<float>(), c->db.dt, c->syn_factor, c->d_gm.as<float>(), c->stream);
+        CU_OK(cudaMemcpyAsync(gm.data(), c->d_gm.p, sizeof(float) * 3 * (size_t)nrcv, cudaMemcpyDeviceToHost, c->stream));
+        CU_OK(cudaStreamSynchronize(c->stream));
+    }
+    return pick_enabled(c, gm.data(), which, out, cap, n);
+}
+}  // namespace
+
+int kiwi_get_peak_amplitudes(kiwi_ctx* c, int differentiate, float* maxabs, int cap, int* n) {
+    if (differentiate != 1 && differentiate != 2)
+        return kiwi_set_error("differentiate argument must be 1 for velocity or 2 for acceleration");   // minimizer_engine.f90:1185-1189
+    return single_ground_motion(c, differentiate, maxabs, cap, n);
+}
+
+int kiwi_get_arias_intensities(kiwi_ctx* c, float* intensities, int cap, int* n) { return single_ground_motion(c, 3, intensities, cap, n); }
+
+// batched: [ns][enabled receivers][3] = peak velocity, peak acceleration, Arias intensity of every candidate (no references needed)
+int kiwi_eval_ground_motion(kiwi_ctx* c, int sourcetype, int ns, int nparams, const float* params, float* out, int* status) {
+    if (!c) return kiwi_set_error("null context");
+    CU_OK(cudaSetDevice(c->device));
+    if (ns < 0) return kiwi_set_error("negative number of sources");
+    if (require_no_filter(c)) return 1;
+    if (upload_receivers(c)) return 1;
+    const int nrcv = (int)c->rcv.size();
+    CU_OK(c->d_gm.ensure(sizeof(float) * 3 * (size_t)std::max(nrcv, 1) * std::max(ns, 1)));
+    SynthHook hook;
+    hook.fn = [&](int cand0, int ncand, const float* seis, size_t seis_stride, const SeisHdr* shdrs, const CandDev* d_cands) -> int {
+        launch_ground_motion(c->d_rcv.as<ReceiverDev>(), nrcv, d_cands, ncand, seis, seis_stride, shdrs, c->d_taper.as<float>(), c->db.dt, c->syn_factor,
+                             c->d_gm.as<float>() + (size_t)cand0 * nrcv * 3, c->stream);
+        return 0;
+    };
+    c->src_dirty = true;
+    if (eval_batch(c, sourcetype, ns, nparams, params, nullptr, status, false, &hook)) return 1;
+    if (ns == 0) return 0;
+    std::vector<float> gm((size_t)3 * nrcv * ns);
+    CU_OK(cudaMemcpy(gm.data(), c->d_gm.p, sizeof(float) * gm.size(), cudaMemcpyDeviceToHost));
+    int nen = 0;
+    for (const HostReceiver& h : c->rcv) nen += h.enabled ? 1 : 0;
+    for (int s = 0; s < ns; s++) {
+        int k = 0;
+        for (int ir = 0; ir < nrcv; ir++) {
+            if (!c->rcv[ir].enabled) continue;
+            for (int q = 0; q < 3; q++) out[((size_t)s * nen + k) * 3 + q] = gm[((size_t)s * nrcv + ir) * 3 + q];
+            k++;
+        }
+    }
+    c->last.valid = false;
+    return 0;
 }
 
 // ---- sub-parameters and Levenberg-Marquardt -------------------------------------------------

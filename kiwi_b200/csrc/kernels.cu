@@ -1587,6 +1587,90 @@ __global__ void __launch_bounds__(128) k_mt_contract(const ReceiverDev* __restri
 }
 
 // =================================================================================================
+// Ground-motion diagnostics of the synthetics (get_peak_amplitudes / get_arias_intensities, minimizer_engine.f90:1174-1245;
+// receiver_get_maxabs / receiver_get_arias_intensity receiver.f90:544-596; max_vecnorm_d1/d2_*, arias_intensity_*
+// comparator.f90:519-625 through probes_norm_timedomain[_3] :700-765).  One warp per (candidate, receiver):
+// out[pair][0..2] = peak vector norm of the velocity, of the acceleration, Arias intensity, over the vertical and/or
+// the complete horizontal pair of components (get_component_ids receiver.f90:505-542).  Fresh-state probe spans.
+// =================================================================================================
+__global__ void __launch_bounds__(128) k_ground_motion(const ReceiverDev* __restrict__ rcv, int nrcv, const CandDev* __restrict__ cands, int ncand,
+                                                        const float* __restrict__ seis, size_t seis_stride, const SeisHdr* __restrict__ shdrs,
+                                                        const float* __restrict__ taperdata, float dt, float syn_factor,
+                                                        float* __restrict__ out /* [ncand][nrcv][3] */) {
+    const int lane = threadIdx.x & 31;
+    const long long pair = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pair >= (long long)ncand * nrcv) return;
+    const int b = (int)(pair / nrcv), ir = (int)(pair % nrcv);
+    const ReceiverDev& R = rcv[ir];
+    float* o = out + (size_t)pair * 3;
+    const CandDev cand = cands[b];
+    if (lane == 0) { o[0] = 0.f; o[1] = 0.f; o[2] = 0.f; }
+    if (!R.enabled || cand.status != 0) { if (lane == 0 && cand.status != 0) { o[0] = nanf(""); o[1] = nanf(""); o[2] = nanf(""); } return; }
+    // components: vertical, and the horizontal pair a/c + r/l or else n/s + e/w (only if complete)
+    int iver = -1, ih1 = -1, ih2 = -1;
+    for (int ic = 0; ic < R.ncomp; ic++) { const int t = abs(R.comp[ic]); if (t == 1) ih1 = ic; if (t == 2) ih2 = ic; if (t == 3) iver = ic; }
+    if (ih1 < 0 || ih2 < 0) for (int ic = 0; ic < R.ncomp; ic++) { const int t = abs(R.comp[ic]); if (t == 4) ih1 = ic; if (t == 5) ih2 = ic; }
+    if (ih1 < 0 || ih2 < 0) { ih1 = -1; ih2 = -1; }
+    int comp[3], nc = 0;
+    if (iver >= 0) comp[nc++] = iver;
+    if (ih1 >= 0) { comp[nc++] = ih1; comp[nc++] = ih2; }
+    if (nc == 0) return;
+    const float* row[3]; int ds0[3], ds1[3], rbase[3];
+    for (int k = 0; k < nc; k++) {
+        const SeisHdr sh = shdrs[(size_t)pair * KIWI_MAX_COMP + comp[k]];
+        if (sh.hi < sh.lo) return;                 // nothing synthesised for a component: leave the zeros
+        row[k] = seis + ((size_t)pair * KIWI_MAX_COMP + comp[k]) * seis_stride;
+        ds0[k] = sh.lo; ds1[k] = sh.hi; rbase[k] = sh.base;
+    }
+    // common probe span F (probe_set_array comparator.f90:240-256, probes_adjust_spans[_3] :464-517)
+    int u0 = ds0[0], u1 = ds1[0], minlength = 0, F0, F1;
+    int sp0[3], sp1[3];
+    for (int k = 0; k < nc; k++) {
+        allowed_span(ds0[k], ds1[k], ceil_len2(ds1[k] - ds0[k] + 1), sp0[k], sp1[k]);
+        u0 = min(u0, ds0[k]); u1 = max(u1, ds1[k]); minlength = max(minlength, ceil_len2(ds1[k] - ds0[k] + 1));
+    }
+    allowed_span(u0, u1, minlength, F0, F1);
+    bool same = (sp1[0] - sp0[0]) == (F1 - F0);
+    for (int k = 1; k < nc; k++) same = same && sp0[k] == sp0[0] && sp1[k] == sp1[0];
+    for (int k = 0; k < nc; k++) for (int j = 0; j < nc; j++) same = same && sp0[k] <= ds0[j] && ds1[j] <= sp1[k];
+    if (same || nc == 1) { F0 = sp0[0]; F1 = sp1[0]; }
+    int s0, s1;
+    if (R.has_taper) { s0 = max(R.dps0, F0); s1 = min(R.dps1, F1); } else { s0 = u0; s1 = u1; }
+    if (s1 < s0) return;                           // "applying timedomain norm to empty region": 0
+    const float* tp = taperdata + R.taper_off;
+    const float moment = cand.moment;
+    auto val = [&](int k, int x) -> float {      // probe array with the continuation rule (:264-267), tapered (:1173-1184)
+        if (x < ds0[k]) return 0.f;
+        float v = row[k][min(x, ds1[k]) - rbase[k]] * moment;
+        if (R.has_taper) v = (x >= R.tp0 && x <= R.tp1) ? v * tp[x - R.tp0] : 0.f;
+        return v;
+    };
+    const double f2 = (double)(syn_factor * syn_factor);
+    double m1 = -DBL_MAX, m2 = -DBL_MAX, sum2 = 0.;
+    for (int x = s0 + lane; x < s1; x += 32) {
+        double a1 = 0., a2 = 0.;
+        for (int k = 0; k < nc; k++) {
+            const float v0 = val(k, x), v1 = val(k, x + 1);
+            const double d1 = (double)(v0 - v1);
+            a1 += f2 * (d1 * d1);
+            if (x + 2 <= s1) { const double d2 = (double)(v0 - 2.0f * v1 + val(k, x + 2)); a2 += f2 * (d2 * d2); }
+        }
+        m1 = fmax(m1, a1);
+        if (x + 2 <= s1) { m2 = fmax(m2, a2); sum2 += a2; }
+    }
+    m1 = warp_max_d(m1); m2 = warp_max_d(m2); sum2 = warp_sum_d(sum2);
+    if (lane == 0) {
+        const int n = s1 - s0 + 1;
+        const float pi_f = 3.14159265358979f;
+        if (n >= 2) o[0] = (float)(sqrt(m1) / (double)dt);
+        if (n >= 3) {
+            o[1] = (float)(sqrt(m2) / (double)(dt * dt));
+            o[2] = (float)((double)(pi_f / (2.f * 9.81f) * dt) * sum2 / (double)(dt * dt));
+        }
+    }
+}
+
+// =================================================================================================
 // Outer misfit (python/tunguska/seismosizer.py:843-922 make_global_misfits): per-receiver norms over
 // components, receiver weights, optional "anarchy" normalisation, optional bootstrap re-weighting of
 // the receivers, global misfit per candidate; then the best candidate per bootstrap row.  Doing it
@@ -1710,6 +1794,12 @@ void launch_misfit_td(const ReceiverDev* rcv, int nrcv, const CandDev* cands, in
     if (blocks > 0)
         k_misfit_td<<<blocks, 128, 0, st>>>(rcv, nrcv, cands, ncand, seis, seis_stride, shdrs, refdata, taperdata, method, dt, syn_factor,
                                             nmisfits, out, status, map);
+}
+
+void launch_ground_motion(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, const float* seis, size_t seis_stride,
+                          const SeisHdr* shdrs, const float* taperdata, float dt, float syn_factor, float* out, cudaStream_t st) {
+    const long long npairs = (long long)ncand * nrcv;
+    if (npairs > 0) k_ground_motion<<<(int)((npairs + 3) / 4), 128, 0, st>>>(rcv, nrcv, cands, ncand, seis, seis_stride, shdrs, taperdata, dt, syn_factor, out);
 }
 
 size_t misfit_general_smem_bytes(int n_alloc, int nshift_alloc) {

@@ -30,6 +30,8 @@ cudaError_t launch_fold(const ReceiverDev* rcv, int nrcv, const CandDev* cands, 
 void launch_misfit_td(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, const float* seis, size_t seis_stride,
                       const SeisHdr* shdrs, const float* refdata, const float* taperdata, int method, float dt, float syn_factor,
                       int nmisfits, float* out, int* status, const CandMap* map, cudaStream_t st);
+void launch_ground_motion(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, const float* seis, size_t seis_stride,
+                          const SeisHdr* shdrs, const float* taperdata, float dt, float syn_factor, float* out, cudaStream_t st);
 size_t misfit_general_smem_bytes(int n_alloc, int nshift_alloc);
 cudaError_t launch_misfit_general(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, const float* seis, size_t seis_stride,
                                   const SeisHdr* shdrs, const float* refdata, const float* taperdata, const float2* tw, int tw_n, int method,

@@ -97,7 +97,7 @@ bool do_command(State& S, const std::string& cmd, const std::vector<std::string>
                                   "set_effective_dt", "set_ref_seismograms", "set_misfit_method", "set_misfit_taper", "set_misfit_filter",
                                   "set_synthetics_factor", "set_floating_shiftrange", "get_misfits", "get_global_misfit", "get_floating_shifts",
                                   "output_seismograms", "eval_sources", "set_source_params_mask", "set_source_subparams",
-                                  "set_source_subparams_limits", "get_source_subparams", "minimize_lm"};
+                                  "set_source_subparams_limits", "get_source_subparams", "minimize_lm", "get_peak_amplitudes", "get_arias_intensities"};
     bool is_known = false;
     for (const char* k : known) if (cmd == k) is_known = true;
     if (!is_known) return fail("unknown command: " + cmd);   // minimizer.f90:1809-1811
@@ -263,6 +263,15 @@ bool do_command(State& S, const std::string& cmd, const std::vector<std::string>
         float sub[64]; int n = 0;
         if (kiwi_get_source_subparams(S.ctx, sub, 64, &n)) return cfail();
         *answer = fmt_floats(sub, (size_t)n);
+        return true;
+    }
+    if (cmd == "get_peak_amplitudes" || cmd == "get_arias_intensities") {   // minimizer.f90 do_get_peak_amplitudes / do_get_arias_intensities
+        std::vector<float> val(S.comps.size() + 1); int n = 0;
+        if (cmd == "get_peak_amplitudes") {
+            if (w.size() != 2) return fail("usage: get_peak_amplitudes differentiate");
+            if (kiwi_get_peak_amplitudes(S.ctx, atoi(w[1].c_str()), val.data(), (int)val.size(), &n)) return cfail();
+        } else if (kiwi_get_arias_intensities(S.ctx, val.data(), (int)val.size(), &n)) return cfail();
+        *answer = fmt_floats(val.data(), (size_t)n);
         return true;
     }
     if (cmd == "minimize_lm") {   // minimizer.f90:1048-1081: answer = info iterations misfit

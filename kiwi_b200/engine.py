@@ -345,6 +345,31 @@ class Engine:
         _check(lib.kiwi_get_global_misfit(self._h, v))
         return v.value
 
+    # ---- ground-motion diagnostics (minimizer_engine.f90:1174-1245) ---------------------------------------
+    def get_peak_amplitudes(self, differentiate):
+        out = np.zeros(8192, dtype=np.float32)
+        n = C.c_int()
+        _check(lib.kiwi_get_peak_amplitudes(self._h, differentiate, _fp(out), out.size, n))
+        return out[:n.value].copy()
+
+    def get_arias_intensities(self):
+        out = np.zeros(8192, dtype=np.float32)
+        n = C.c_int()
+        _check(lib.kiwi_get_arias_intensities(self._h, _fp(out), out.size, n))
+        return out[:n.value].copy()
+
+    def eval_ground_motion(self, sourcetype, params, nenabled):
+        """-> (values[ns, nenabled, 3] = peak velocity, peak acceleration, Arias intensity; status[ns])"""
+        if isinstance(sourcetype, str):
+            sourcetype = SOURCE_TYPES[sourcetype]
+        p = _f32(params)
+        if p.ndim == 1:
+            p = p[None, :]
+        out = np.zeros((p.shape[0], nenabled, 3), dtype=np.float32)
+        status = np.zeros(p.shape[0], dtype=np.int32)
+        _check(lib.kiwi_eval_ground_motion(self._h, sourcetype, p.shape[0], p.shape[1], _fp(p), _fp(out), status.ctypes.data_as(c_int_p)))
+        return out, status
+
     # ---- sub-parameters and Levenberg-Marquardt (minimizer_engine.f90:525-610, 729-874) ------------------
     def set_source_params_mask(self, mask):
         m = np.ascontiguousarray(np.asarray(mask).astype(bool), dtype=np.int32)

@@ -317,6 +317,82 @@ static inline float probe_norm_timedomain(Probe& a, normfn1 fn) {
     else if (a.taper.defined) { update_array_tapered(a); return fn(&a.array_tapered.d[span[0] - a.array_tapered.lo], n, a.dt, a.factor); }
     return fn(&a.array.d[span[0] - a.array.lo], n, a.dt, a.factor);
 }
+// ---- ground-motion diagnostics (comparator.f90:488-517 probes_adjust_spans_3, :519-625 norm functions, :700-765) ----
+static inline void probes_adjust_spans_3(Probe& a, Probe& b, Probe& c) {
+    int t[2], newspan[2];
+    span_union(a.dataspan, b.dataspan, t);
+    int u[2]; span_union(t, c.dataspan, u);
+    const int minlength = std::max(std::max(f_ceiling((float)slen(a.dataspan) * a.paddingfactor), f_ceiling((float)slen(b.dataspan) * b.paddingfactor)),
+                                   f_ceiling((float)slen(c.dataspan) * c.paddingfactor));
+    allowed_span(u, minlength, newspan);
+    const bool same = a.span[0] == b.span[0] && a.span[1] == b.span[1] && a.span[0] == c.span[0] && a.span[1] == c.span[1] &&
+                      slen(a.span) == slen(newspan) && containing(a.span, b.dataspan) && containing(b.span, a.dataspan) &&
+                      containing(a.span, c.dataspan) && containing(c.span, a.dataspan) && containing(b.span, c.dataspan) && containing(c.span, b.dataspan);
+    if (same) return;
+    probe_extend_span(a, newspan); probe_extend_span(b, newspan); probe_extend_span(c, newspan);
+}
+// which == 1: max_vecnorm_d1_*, 2: max_vecnorm_d2_*, 3: arias_intensity_* over nc = 1..3 arrays of n samples
+static inline float ground_motion_func(int which, const sreal* const* arr, const float* fac, int nc, int n, float dt) {
+    if (which == 1) {
+        double m = -std::numeric_limits<double>::max();
+        for (int i = 0; i + 1 < n; i++) {
+            double s = 0.;
+            for (int c = 0; c < nc; c++) { const double d = (double)(arr[c][i] - arr[c][i + 1]); s += (double)(fac[c] * fac[c]) * (d * d); }
+            m = std::max(m, s);
+        }
+        if (n < 2) return 0.f;
+        return (float)(sqrt(m) / (double)dt);
+    }
+    double acc = which == 2 ? -std::numeric_limits<double>::max() : 0.;
+    for (int i = 0; i + 2 < n; i++) {
+        double s = 0.;
+        for (int c = 0; c < nc; c++) {
+            const double d = (double)(arr[c][i] - (sreal)2.0f * arr[c][i + 1] + arr[c][i + 2]);
+            s += (double)(fac[c] * fac[c]) * (d * d);
+        }
+        if (which == 2) acc = std::max(acc, s); else acc += s;
+    }
+    if (n < 3) return 0.f;
+    if (which == 2) return (float)(sqrt(acc) / (double)(dt * dt));
+    return (float)((double)(pi / (2.f * 9.81f) * dt) * acc / (double)(dt * dt));
+}
+// probe_norm_timedomain / probes_norm_timedomain / probes_norm_timedomain_3 with one of the functions above
+static inline float probes_ground_motion(Probe** p, int nc, int which) {
+    if (nc == 2) probes_adjust_spans(*p[0], *p[1]);
+    if (nc == 3) probes_adjust_spans_3(*p[0], *p[1], *p[2]);
+    bool tapered = true, filtered = true;
+    for (int c = 0; c < nc; c++) { tapered = tapered && p[c]->taper.defined; filtered = filtered && p[c]->filter.defined; }
+    int span[2] = {0, -1};
+    if (tapered) {
+        int ts[3][2];
+        for (int c = 0; c < nc; c++) { int d[2]; discrete_plf_span(p[c]->taper, p[c]->dt, d); span_intersection(d, p[c]->span, ts[c]); }
+        if (nc == 1) { span[0] = ts[0][0]; span[1] = ts[0][1]; }
+        else if (nc == 2) {
+            if (ts[0][0] > ts[0][1]) { span[0] = ts[1][0]; span[1] = ts[1][1]; }
+            else if (ts[1][0] > ts[1][1]) { span[0] = ts[0][0]; span[1] = ts[0][1]; }
+            else span_union(ts[0], ts[1], span);
+        } else {
+            if (ts[0][0] > ts[0][1]) { span[0] = ts[1][0]; span[1] = ts[1][1]; }
+            else if (ts[1][0] > ts[1][1]) { span[0] = ts[0][0]; span[1] = ts[0][1]; }
+            else if (ts[2][0] > ts[2][1]) { span[0] = ts[2][0]; span[1] = ts[2][1]; }
+            else { int t[2]; span_union(ts[0], ts[1], t); span_union(t, ts[2], span); }
+        }
+    } else {
+        span[0] = p[0]->dataspan[0]; span[1] = p[0]->dataspan[1];
+        for (int c = 1; c < nc; c++) { int t[2] = {span[0], span[1]}; span_union(t, p[c]->dataspan, span); }
+    }
+    if (span[0] > span[1]) { g_warn_empty_region++; return 0.f; }
+    const int n = slen(span);
+    const sreal* arr[3]; float fac[3];
+    for (int c = 0; c < nc; c++) {
+        fac[c] = p[c]->factor;
+        if (filtered) { update_array_filtered(*p[c]); arr[c] = &p[c]->array_filtered.d[span[0] - p[c]->array_filtered.lo]; }
+        else if (tapered) { update_array_tapered(*p[c]); arr[c] = &p[c]->array_tapered.d[span[0] - p[c]->array_tapered.lo]; }
+        else arr[c] = &p[c]->array.d[span[0] - p[c]->array.lo];
+    }
+    return ground_motion_func(which, arr, fac, nc, n, p[0]->dt);
+}
+
 // :861-886
 typedef float (*normfn2f)(const float*, const float*, int, float, float, float);
 typedef float (*normfn1f)(const float*, int, float, float);

@@ -111,6 +111,45 @@ static inline void receiver_calculate_floating_misfits(Receiver& self, int misfi
     for (int ic = 0; ic < nc; ic++) probe_shift(self.ref_probes[ic], -shiftrange[1]);
 }
 // receiver.f90:407-437
+// receiver.f90:505-542: horizontal components preferably a/c and r/l, else n/s and e/w; none if incomplete
+static inline void get_component_ids(const Receiver& self, int& iver, int& ihor1, int& ihor2) {
+    iver = ihor1 = ihor2 = 0;
+    for (int ic = 1; ic <= self.ncomponents; ic++) {
+        const int ict = abs(self.components[ic - 1]);
+        if (ict == 1) ihor1 = ic;
+        if (ict == 2) ihor2 = ic;
+        if (ict == 3) iver = ic;
+    }
+    if (ihor1 == 0 || ihor2 == 0)
+        for (int ic = 1; ic <= self.ncomponents; ic++) {
+            const int ict = abs(self.components[ic - 1]);
+            if (ict == 4) ihor1 = ic;
+            if (ict == 5) ihor2 = ic;
+        }
+    if (ihor1 == 0 || ihor2 == 0) { ihor1 = 0; ihor2 = 0; }
+}
+// receiver.f90:544-576: peak of the vector norm of the velocity (differentiate 1) or acceleration (2) of the synthetics
+static inline float receiver_get_maxabs(Receiver& self, int differentiate) {
+    if (!self.enabled) return 0.f;
+    int ic[3];
+    get_component_ids(self, ic[0], ic[1], ic[2]);
+    Probe* p[3]; int n = 0;
+    for (int i = 0; i < 3; i++) if (ic[i] != 0) p[n++] = &self.syn_probes[ic[i] - 1];
+    if (n == 0) return 0.f;
+    return probes_ground_motion(p, n, differentiate);
+}
+// receiver.f90:578-596
+static inline float receiver_get_arias_intensity(Receiver& self) {
+    if (!self.enabled) return 0.f;
+    int iver, ihor1, ihor2;
+    get_component_ids(self, iver, ihor1, ihor2);
+    Probe* p[3];
+    if (iver != 0 && ihor1 != 0 && ihor2 != 0) { p[0] = &self.syn_probes[iver - 1]; p[1] = &self.syn_probes[ihor1 - 1]; p[2] = &self.syn_probes[ihor2 - 1]; return probes_ground_motion(p, 3, 3); }
+    if (ihor1 != 0 && ihor2 != 0) { p[0] = &self.syn_probes[ihor1 - 1]; p[1] = &self.syn_probes[ihor2 - 1]; return probes_ground_motion(p, 2, 3); }
+    if (iver != 0) { p[0] = &self.syn_probes[iver - 1]; return probes_ground_motion(p, 1, 3); }
+    return 0.f;
+}
+
 static inline void receiver_calculate_misfits(Receiver& self, int misfit_method) {
     if (misfit_method == FLOATING_L1NORM || misfit_method == FLOATING_L2NORM) {
         receiver_calculate_floating_misfits(self, misfit_method, self.floating_shiftrange);

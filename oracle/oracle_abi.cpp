@@ -197,6 +197,24 @@ int oracle_trace_span(void* h, int ix, int iz, int ig, int* span2, int* nstrips)
     return 0;
 }
 // time `ns` evaluations; returns seconds of wall time
+// ---- ground-motion diagnostics of the current source (minimizer_engine.f90:1174-1245), enabled receivers in order ----
+// which: 1 peak velocity, 2 peak acceleration, 3 Arias intensity.  update_syn_probes of the given source in a fresh state
+// (no misfit calculation before: that would widen the probe spans, comparator.f90:464-486), then the receivers' values
+int oracle_get_ground_motion(void* h, int sourcetype, const float* params, int nparams, int which, float* out, int cap) {
+    Engine& e = *(Engine*)h;
+    if (!set_source_params(e, sourcetype, params, nparams)) return -1;
+    if (!calculate_seismograms(e)) return -1;
+    scale_seismograms(e);
+    int n = 0;
+    for (auto& r : e.receivers) {
+        if (!r.enabled) continue;
+        const float v = which == 3 ? receiver_get_arias_intensity(r) : receiver_get_maxabs(r, which);
+        if (n < cap) out[n] = v;
+        n++;
+    }
+    return n;
+}
+
 // ---- sub-parameters and Levenberg-Marquardt ----------------------------------------------------------------------
 int oracle_set_source_params_mask(void* h, const int* mask, int n) {
     Engine& e = *(Engine*)h;

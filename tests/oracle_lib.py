@@ -37,7 +37,7 @@ def lib(wide=False):
                      "oracle_get_probe_spans", "oracle_discretize_source", "oracle_record_indices", "oracle_get_indices",
                      "oracle_receiver_geometry", "oracle_trace_span", "oracle_time_eval", "oracle_get_strip_spans",
                      "oracle_set_source_params_mask", "oracle_set_source_subparams", "oracle_set_source_subparams_limits",
-                     "oracle_get_source_subparams", "oracle_minimize_lm", "oracle_lmdif"):
+                     "oracle_get_source_subparams", "oracle_minimize_lm", "oracle_lmdif", "oracle_get_ground_motion"):
             if hasattr(L, name):
                 getattr(L, name).argtypes = None
         _libs[wide] = L
@@ -185,6 +185,18 @@ class OracleEngine:
 
     def get_global_misfit(self):
         return float(self.L.oracle_get_global_misfit(self.h))
+
+    def get_ground_motion(self, sourcetype, params, which):
+        """which: 1 peak velocity, 2 peak acceleration, 3 Arias intensity -> values of the enabled receivers"""
+        if isinstance(sourcetype, str):
+            sourcetype = SOURCE_TYPES[sourcetype]
+        p = _f32(params).ravel()
+        out = np.zeros(4096, np.float32)
+        n = self.L.oracle_get_ground_motion(self.h, C.c_int(sourcetype), p.ctypes.data_as(fp), C.c_int(p.size), C.c_int(which), out.ctypes.data_as(fp),
+                                            C.c_int(out.size))
+        if n < 0:
+            self._check(1)
+        return out[:n].copy()
 
     # ---- sub-parameters and Levenberg-Marquardt (sequential restatement) ----
     def set_source_params_mask(self, mask):

@@ -511,3 +511,34 @@ def test_minimize_lm_against_the_sequential_restatement():
     assert ng <= 2 * no + 10 and no <= 2 * ng + 10, (ng, no)
     # the engine is left at the last model evaluated and answers for it
     assert abs(g.get_global_misfit() - mg) <= 1e-6 * max(mg, 1e-3)
+
+
+@pytest.mark.parametrize("taper", [False, True])
+@pytest.mark.parametrize("stype,params", [("bilateral", sc.BILAT_SMALL), ("moment_tensor", sc.MT_SMALL)])
+def test_peak_amplitudes_and_arias_intensities(stype, params, taper):
+    """get_peak_amplitudes / get_arias_intensities (minimizer_engine.f90:1174-1245): peak vector norm of velocity and acceleration
+    and Arias intensity of the synthetics per receiver, over the components receiver.f90:505-542 picks (three, the horizontal
+    pair, the vertical alone: the six receivers of COMPS6 cover all cases); single source and batched."""
+    g, o = engines(sc.small_db(), COMPS6)
+    if taper:
+        for e in (g, o):
+            for ir in range(1, 7):
+                e.set_misfit_taper(ir, *TAPER)
+    g.set_source_params(stype, params)
+    want = [o.get_ground_motion(stype, params, w) for w in (1, 2, 3)]
+    got = [g.get_peak_amplitudes(1), g.get_peak_amplitudes(2), g.get_arias_intensities()]
+    # first differences of traces that agree to ~1e-6 of their peak: 2e-5; second differences (acceleration, and its sum of
+    # squares in the Arias intensity) take the same absolute trace error relative to a much smaller quantity: 2e-4
+    rtol = {1: 2e-5, 2: 2e-4, 3: 2e-4}
+    for w, a, b in zip((1, 2, 3), got, want):
+        assert a.shape == b.shape == (6,) and np.all(b > 0)
+        assert np.all(np.abs(a - b) <= rtol[w] * np.abs(b)), (w, a, b)
+    p = np.tile(params, (3, 1)); p[1, 1] += 250; p[2, 3] += 300
+    vals, st = g.eval_ground_motion(stype, p, 6)
+    assert not st.any() and np.array_equal(vals[0], np.stack(got, 1))
+    for i in (1, 2):
+        for w in (1, 2, 3):
+            b = o.get_ground_motion(stype, p[i], w)
+            assert np.all(np.abs(vals[i, :, w - 1] - b) <= rtol[w] * np.abs(b)), (i, w)
+    with pytest.raises(Exception, match="differentiate argument must be 1"):
+        g.get_peak_amplitudes(3)
