@@ -132,6 +132,17 @@ int kiwi_set_effective_dt(kiwi_ctx* ctx, float effective_dt);
  * stripped: n samples of component icomponent at receiver ireceiver, first sample at time tbegin
  * [s] relative to the source reference time */
 int kiwi_set_ref_seismogram(kiwi_ctx* ctx, int ireceiver, int icomponent, float tbegin, int n, const float* data);
+/* shift_ref_seismogram (minimizer_engine.f90:354-378): move the reference traces of one receiver by nint(shift/dt) samples */
+int kiwi_shift_ref_seismogram(kiwi_ctx* ctx, int ireceiver, float shift);
+/* autoshift_ref_seismogram (minimizer_engine.f90:380-416, receiver.f90:816-832): cross-correlate the synthetics of the current
+ * source with the references pulled through [shift_lo, shift_hi] seconds (probes_windowed_cross_corr comparator.f90:1061-1090,
+ * taper / filter applied as set) and move the references of receiver ireceiver (0 = all) to the best shift.  shifts: the
+ * applied shifts in seconds, one per receiver addressed (disabled receivers: 0). */
+int kiwi_autoshift_ref_seismogram(kiwi_ctx* ctx, int ireceiver, float shift_lo, float shift_hi, float* shifts, int cap, int* n);
+/* In-memory replacement of output_cross_correlations (minimizer_engine.f90:1283-1306, receiver.f90:597-616; the reference
+ * only writes files): cc[component][shift] of receiver ireceiver for the source set by kiwi_set_source_params, shifts
+ * nint(shift_lo/dt)..nint(shift_hi/dt) samples. */
+int kiwi_get_cross_correlations(kiwi_ctx* ctx, int ireceiver, float shift_lo, float shift_hi, float* cc, int cap, int* ncomp, int* nshift);
 /* set_misfit_method (minimizer_engine.f90:620-628) */
 int kiwi_set_misfit_method(kiwi_ctx* ctx, int norm_id);
 /* set_misfit_taper (minimizer_engine.f90:668-698): ireceiver in 1..n */

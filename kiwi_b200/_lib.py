@@ -68,6 +68,9 @@ SIGNATURES = {
     "kiwi_lmdif_batched": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, c_float_p, c_float_p, C.c_float, C.c_float, C.c_float, C.c_int,
                                      C.c_float, c_float_p, C.c_int, C.c_float, c_int_p, c_int_p]),
     "kiwi_get_floating_shifts": (C.c_int, [C.c_void_p, c_int_p, C.c_int, c_int_p]),
+    "kiwi_shift_ref_seismogram": (C.c_int, [C.c_void_p, C.c_int, C.c_float]),
+    "kiwi_get_cross_correlations": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float, c_float_p, C.c_int, c_int_p, c_int_p]),
+    "kiwi_autoshift_ref_seismogram": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float, c_float_p, C.c_int, c_int_p]),
     "kiwi_get_seismogram": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_float_p, C.c_int]),
     "kiwi_discretize_source": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, c_float_p, C.c_int, c_int_p, c_int_p]),
     "kiwi_get_indices": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_int_p, c_int_p, c_float_p, c_float_p, c_int_p, C.c_int, c_int_p]),

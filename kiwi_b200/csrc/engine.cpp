@@ -125,6 +125,7 @@ struct kiwi_ctx {
     DevBuf d_map, d_status_out;
     DevBuf d_taprec;              // shift table of the current batch (k_tap_table)
     DevBuf d_gm;                  // ground-motion values [cand][rcv][3]
+    DevBuf d_xcorr;               // cross-correlations [rcv][component][shift] (autoshift_ref_seismogram)
     bool dedup_enabled = true;               // candidates that differ only in the moment share one synthesis
     DevBuf d_mtlocs, d_mts, d_candof, d_orc, d_orw, d_obw, d_oout, d_obest, d_obestv;
     int last_eval_ns = 0;                    // candidates whose misfit block sits in d_out (kiwi_eval_sources)
@@ -140,6 +141,7 @@ struct kiwi_ctx {
         std::vector<float> toff, wt;
         std::vector<int> g0_tap_begin, g0_tap_count;   // taps of the groups of candidate 0
         bool seis_valid = false;
+        int syn_lo = 0, syn_hi = 0, tmax = 0;   // bounds of the synthetic spans of the chunk
     } last;
     float ms[5] = {0, 0, 0, 0, 0};
     int launches[4] = {0, 0, 0, 0};
@@ -281,6 +283,58 @@ struct Dedup {
     std::vector<int> out_of;      // [n_out]: original candidate of a slot
     std::vector<float> moment;    // [n_out]: its moment
 };
+
+// k_misfit_general on nslots (candidate, receiver-set) slots: sizes the shared-memory FFT from the bound of the padded probe span
+// (comparator.f90:1092-1109) over the chunk -- union of all synthetic and (shifted) reference spans, at least twice the longest data
+// span, next power of two.  method = KIWI_INTERNAL_XCORR: cross-correlation over the shifts xs0..xs1 (autoshift_ref_seismogram).
+int run_misfit_general(kiwi_ctx* c, int method, int xs0, int xs1, int syn_lo, int syn_hi, int tmax, const CandDev* d_cands, int nslots, size_t seis_stride,
+                       const SeisHdr* d_shdrs, int nm, float* out_base, int* status_base, int* d_fshift, const CandMap* d_map, int premethod = 0) {
+    const int nrcv = (int)c->rcv.size();
+    int lo = syn_lo, hi = syn_hi, rlen = 1, nshift = 1;
+    const bool xcorr = method == KIWI_INTERNAL_XCORR;
+    const bool floating = xcorr ? premethod >= KIWI_FLOATING_L2NORM : c->misfit_method >= KIWI_FLOATING_L2NORM;   // span history in cross-correlation mode
+    bool need_fft = (method == KIWI_AMPSPEC_L2NORM || method == KIWI_AMPSPEC_L1NORM);
+    if (xcorr) nshift = xs1 - xs0 + 1;
+    for (const ReceiverDev& r : c->h_rcvdev) {
+        if (!r.enabled) continue;
+        if (r.has_filter) need_fft = true;
+        if (floating && !xcorr) nshift = std::max(nshift, r.fs1 - r.fs0 + 1);
+        int s_lo = 0, s_hi = 0;
+        if (floating) { s_lo = std::min(s_lo, r.fs0); s_hi = std::max(s_hi, r.fs1); }
+        if (xcorr) { s_lo = std::min(s_lo, xs0); s_hi = std::max(s_hi, xs1); }
+        for (int k = 0; k < r.ncomp; k++) {
+            lo = std::min(lo, std::min(r.ref_sp0[k], r.ref_ds0[k] + s_lo));
+            hi = std::max(hi, std::max(r.ref_sp1[k], r.ref_ds1[k] + s_hi));
+            rlen = std::max(rlen, r.ref_ds1[k] - r.ref_ds0[k] + 1);
+        }
+    }
+    if (nshift < 1) return kiwi_set_error("empty shift range");
+    int n_alloc = 2;
+    if (need_fft) {
+        const long long want = std::max<long long>((long long)hi - lo + 1, 2LL * std::max(tmax, rlen));
+        while (n_alloc < want) n_alloc <<= 1;
+        n_alloc <<= 1;   // head room for re-centred unions
+        if (n_alloc > 16384) n_alloc = 16384;   // 128 KiB of shared memory; longer spans are flagged per candidate
+        if (c->tw_n == 0) {   // twiddles rounded from double, as an fp32 FFT library tabulates them
+            const int N = 32768;
+            std::vector<float> twh((size_t)N);
+            for (int k = 0; k < N / 2; k++) {
+                const double a = -2.0 * M_PI * (double)k / (double)N;
+                twh[2 * (size_t)k] = (float)cos(a); twh[2 * (size_t)k + 1] = (float)sin(a);
+            }
+            CU_OK(c->d_tw.ensure(sizeof(float) * N));
+            CU_OK(cudaMemcpy(c->d_tw.p, twh.data(), sizeof(float) * N, cudaMemcpyHostToDevice));
+            c->tw_n = N;
+        }
+    }
+    if (misfit_general_smem_bytes(n_alloc, nshift) > (size_t)200 * 1024) return kiwi_set_error("floating shift range too large");
+    cudaError_t e = launch_misfit_general(c->d_rcv.as<ReceiverDev>(), nrcv, d_cands, nslots, c->d_seis.as<float>(), seis_stride, d_shdrs,
+                                          c->d_refdata.as<float>(), c->d_taper.as<float>(), (const float2*)c->d_tw.p, c->tw_n > 0 ? c->tw_n : 2, method,
+                                          c->db.dt, c->syn_factor, nm, out_base, status_base, d_fshift, n_alloc, nshift, d_map, c->stream, xs0, xs1,
+                                          premethod);
+    if (e != cudaSuccess) return kiwi_set_error("CUDA error launching the misfit kernel: %s", cudaGetErrorString(e));
+    return 0;
+}
 
 // Evaluate candidates [0,n) of `params`; d_out: device [n][nmisfits][2]; h_status: host [n] or null.
 // want_misfits = false stops after synthesis (used by the seismogram getters).
@@ -598,46 +652,10 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
                                  c->misfit_method, c->db.dt, c->syn_factor, nm, out_base, status_base, d_map, st);
                 c->launches[3] += 1;
             } else if (want_misfits && nm > 0) {
-                // bound of the padded probe span (comparator.f90:1092-1109) over this chunk: union of all synthetic
-                // and (shifted) reference spans, at least twice the longest data span, next power of two
-                int lo = tm3[1], hi = tm3[2], rlen = 1, nshift = 1;
-                const bool floating = c->misfit_method >= KIWI_FLOATING_L2NORM;
-                bool need_fft = (c->misfit_method == KIWI_AMPSPEC_L2NORM || c->misfit_method == KIWI_AMPSPEC_L1NORM);
-                for (const ReceiverDev& r : c->h_rcvdev) {
-                    if (!r.enabled) continue;
-                    if (r.has_filter) need_fft = true;
-                    if (floating) nshift = std::max(nshift, r.fs1 - r.fs0 + 1);
-                    for (int k = 0; k < r.ncomp; k++) {
-                        lo = std::min(lo, std::min(r.ref_sp0[k], r.ref_ds0[k] + (floating ? r.fs0 : 0)));
-                        hi = std::max(hi, std::max(r.ref_sp1[k], r.ref_ds1[k] + (floating ? r.fs1 : 0)));
-                        rlen = std::max(rlen, r.ref_ds1[k] - r.ref_ds0[k] + 1);
-                    }
-                }
-                int n_alloc = 2;
-                if (need_fft) {
-                    const long long want = std::max<long long>((long long)hi - lo + 1, 2LL * std::max(tmax, rlen));
-                    while (n_alloc < want) n_alloc <<= 1;
-                    n_alloc <<= 1;   // head room for re-centred unions
-                    if (n_alloc > 16384) n_alloc = 16384;   // 128 KiB of shared memory; longer spans are flagged per candidate
-                    if (c->tw_n == 0) {   // twiddles rounded from double, as an fp32 FFT library tabulates them
-                        const int N = 32768;
-                        std::vector<float> twh((size_t)N);
-                        for (int k = 0; k < N / 2; k++) {
-                            const double a = -2.0 * M_PI * (double)k / (double)N;
-                            twh[2 * (size_t)k] = (float)cos(a); twh[2 * (size_t)k + 1] = (float)sin(a);
-                        }
-                        CU_OK(c->d_tw.ensure(sizeof(float) * N));
-                        CU_OK(cudaMemcpy(c->d_tw.p, twh.data(), sizeof(float) * N, cudaMemcpyHostToDevice));
-                        c->tw_n = N;
-                    }
-                }
-                if (misfit_general_smem_bytes(n_alloc, nshift) > (size_t)200 * 1024) return kiwi_set_error("floating shift range too large");
                 CU_OK(c->d_fshift.ensure(sizeof(int) * (size_t)(dd ? dd->n_out : nc) * nrcv));
-                cudaError_t e = launch_misfit_general(c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>() + s0, nslots, c->d_seis.as<float>(), seis_stride,
-                                                      c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, c->d_refdata.as<float>(), c->d_taper.as<float>(),
-                                                      (const float2*)c->d_tw.p, c->tw_n > 0 ? c->tw_n : 2, c->misfit_method, c->db.dt, c->syn_factor, nm,
-                                                      out_base, status_base, c->d_fshift.as<int>() + fshift_off, n_alloc, nshift, d_map, st);
-                if (e != cudaSuccess) return kiwi_set_error("CUDA error launching the misfit kernel: %s", cudaGetErrorString(e));
+                if (run_misfit_general(c, c->misfit_method, 0, 0, tm3[1], tm3[2], tmax, c->d_cands.as<CandDev>() + s0, nslots, seis_stride,
+                                       c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, nm, out_base, status_base, c->d_fshift.as<int>() + fshift_off, d_map))
+                    return 1;
                 c->launches[3] += 1;
             }
             cudaEventRecord(c->ev[5], st);
@@ -656,6 +674,7 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         L.valid = true; L.sourcetype = sourcetype; L.n = nc; L.nrcv = nrcv; L.rec_stride = rec_stride; L.seis_stride = seis_stride;
         L.ngroups_total = Galloc; L.cands = cands; L.g = g; L.taps = taps; L.toff = toff; L.wt = wt;
         L.seis_valid = (sub >= nc) && tmax > 0;
+        L.syn_lo = tm3[1]; L.syn_hi = tm3[2]; L.tmax = tmax;
         {
             const kh::SourcePrep& sp0 = prep[b0];
             L.g0_tap_begin.assign(sp0.ngroups, cands[0].tap_begin); L.g0_tap_count.assign(sp0.ngroups, sp0.nt);
@@ -803,7 +822,7 @@ void kiwi_destroy(kiwi_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->d_slabs, &c->d_nodes, &c->d_tspan, &c->d_rcv, &c->d_refdata, &c->d_taper, &c->d_cands, &c->d_bilat, &c->d_gf, &c->d_gi,
-                      &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift, &c->d_map, &c->d_status_out, &c->d_taprec, &c->d_gm, &c->d_mtlocs, &c->d_mts, &c->d_candof, &c->d_orc, &c->d_orw, &c->d_obw, &c->d_oout, &c->d_obest, &c->d_obestv})
+                      &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift, &c->d_map, &c->d_status_out, &c->d_taprec, &c->d_gm, &c->d_xcorr, &c->d_mtlocs, &c->d_mts, &c->d_candof, &c->d_orc, &c->d_orw, &c->d_obw, &c->d_oout, &c->d_obest, &c->d_obestv})
         b->release();
     c->h_stage.release(); c->h_out.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -1434,6 +1453,91 @@ int kiwi_get_floating_shifts(kiwi_ctx* c, int* shifts, int cap, int* n) {   // m
         k++;
     }
     if (n) *n = k;
+    return 0;
+}
+
+namespace {
+// receiver_shift_ref_seismogram (receiver.f90:802-814) under the fresh-state semantics: the data span of every component moves
+void shift_refs(kiwi_ctx* c, int ir, int ishift) {
+    HostReceiver& h = c->rcv[ir];
+    for (int k = 0; k < h.ncomp; k++) if (h.has_ref[k]) { h.ref_ds0[k] += ishift; h.ref_ds1[k] += ishift; }
+    c->receivers_dirty = true; c->src_dirty = true;   // dirtyfy_ref_probes
+}
+}  // namespace
+
+int kiwi_shift_ref_seismogram(kiwi_ctx* c, int ireceiver, float shift) {   // minimizer_engine.f90:354-378
+    if (!c) return kiwi_set_error("null context");
+    if (require_receivers(c)) return 1;
+    if (!all_refs_set(c)) return kiwi_set_error("no reference seismograms set");
+    if (ireceiver < 1 || ireceiver > (int)c->rcv.size()) return kiwi_set_error("receiver index out of range");
+    shift_refs(c, ireceiver - 1, (int)lroundf(shift / c->db.dt));
+    return 0;
+}
+
+namespace {
+// receiver_calculate_cross_correlations (receiver.f90:597-616) for all receivers of the ns = 1 source on the device; ish: best shift per
+// receiver by the rule of receiver.f90:827, cc: [receiver][KIWI_MAX_COMP][nshift] (may be null)
+int cross_correlate(kiwi_ctx* c, int xs0, int xs1, int premethod, std::vector<int>* ish, std::vector<float>* cc) {
+    const int nrcv = (int)c->rcv.size();
+    const int nshift = xs1 - xs0 + 1;
+    if (nshift < 1) return kiwi_set_error("empty shift range");
+    if (ish) ish->assign((size_t)nrcv, 0);
+    if (cc) cc->assign((size_t)nrcv * KIWI_MAX_COMP * nshift, 0.f);
+    if (!c->last.seis_valid || nrcv == 0) return 0;
+    const size_t ncc = (size_t)nrcv * KIWI_MAX_COMP * nshift;
+    CU_OK(c->d_fshift.ensure(sizeof(int) * (size_t)nrcv));
+    CU_OK(c->d_xcorr.ensure(sizeof(float) * ncc));
+    CU_OK(cudaMemsetAsync(c->d_fshift.p, 0, sizeof(int) * (size_t)nrcv, c->stream));
+    CU_OK(cudaMemsetAsync(c->d_xcorr.p, 0, sizeof(float) * ncc, c->stream));
+    if (run_misfit_general(c, KIWI_INTERNAL_XCORR, xs0, xs1, c->last.syn_lo, c->last.syn_hi, c->last.tmax, c->d_cands.as<CandDev>(), 1,
+                           c->last.seis_stride, c->d_shdrs.as<SeisHdr>(), c->nmisfits, c->d_xcorr.as<float>(), c->d_status.as<int>(),
+                           c->d_fshift.as<int>(), nullptr, premethod))
+        return 1;
+    if (ish) CU_OK(cudaMemcpyAsync(ish->data(), c->d_fshift.p, sizeof(int) * (size_t)nrcv, cudaMemcpyDeviceToHost, c->stream));
+    if (cc) CU_OK(cudaMemcpyAsync(cc->data(), c->d_xcorr.p, sizeof(float) * ncc, cudaMemcpyDeviceToHost, c->stream));
+    CU_OK(cudaStreamSynchronize(c->stream));
+    CU_OK(cudaGetLastError());
+    return 0;
+}
+}  // namespace
+
+int kiwi_autoshift_ref_seismogram(kiwi_ctx* c, int ireceiver, float shift_lo, float shift_hi, float* shifts, int cap, int* n) {   // :380-416
+    if (!c) return kiwi_set_error("null context");
+    CU_OK(cudaSetDevice(c->device));
+    if (ensure_single(c, true)) return 1;   // update_misfits
+    const int nrcv = (int)c->rcv.size();
+    if (ireceiver != 0 && (ireceiver < 1 || ireceiver > nrcv)) return kiwi_set_error("receiver index out of range");
+    std::vector<int> ish;
+    if (cross_correlate(c, (int)lroundf(shift_lo / c->db.dt), (int)lroundf(shift_hi / c->db.dt), c->misfit_method, &ish, nullptr)) return 1;
+    const int i0 = ireceiver == 0 ? 0 : ireceiver - 1, i1 = ireceiver == 0 ? nrcv : ireceiver;
+    int k = 0;
+    for (int i = i0; i < i1; i++) {
+        const int ishift = c->rcv[i].enabled ? ish[i] : 0;   // receiver.f90:823-824
+        if (k < cap && shifts) shifts[k] = (float)ishift * c->db.dt;
+        k++;
+        if (c->rcv[i].enabled) shift_refs(c, i, ishift);
+    }
+    if (n) *n = k;
+    c->receivers_dirty = true; c->src_dirty = true;
+    return 0;
+}
+
+// In-memory replacement of output_cross_correlations (minimizer_engine.f90:1283-1306; the reference only writes files)
+int kiwi_get_cross_correlations(kiwi_ctx* c, int ireceiver, float shift_lo, float shift_hi, float* cc_out, int cap, int* ncomp, int* nshift) {
+    if (!c) return kiwi_set_error("null context");
+    CU_OK(cudaSetDevice(c->device));
+    if (ensure_single(c, false)) return 1;   // update_syn_probes
+    if (!all_refs_set(c)) return kiwi_set_error("no reference seismograms set");
+    const int nrcv = (int)c->rcv.size();
+    if (ireceiver < 1 || ireceiver > nrcv) return kiwi_set_error("receiver index out of range");
+    const int xs0 = (int)lroundf(shift_lo / c->db.dt), xs1 = (int)lroundf(shift_hi / c->db.dt);
+    std::vector<float> cc;
+    if (cross_correlate(c, xs0, xs1, -1, nullptr, &cc)) return 1;
+    const int ns = xs1 - xs0 + 1, nc = c->rcv[ireceiver - 1].enabled ? c->rcv[ireceiver - 1].ncomp : 0;
+    if (cap < nc * ns) return kiwi_set_error("buffer too small for the cross-correlations");
+    for (int k = 0; k < nc * ns; k++) cc_out[k] = cc[(size_t)(ireceiver - 1) * KIWI_MAX_COMP * ns + k];
+    if (ncomp) *ncomp = nc;
+    if (nshift) *nshift = ns;
     return 0;
 }
 

@@ -1160,7 +1160,7 @@ __global__ void __launch_bounds__(256) k_misfit_general(const ReceiverDev* __res
                                                          const float* __restrict__ taperdata, const float2* __restrict__ tw, int tw_n,
                                                          int method, float dt, float syn_factor, int nmisfits, float* __restrict__ out,
                                                          int* __restrict__ status, int* __restrict__ fshift, int n_alloc, int nshift_alloc,
-                                                         const CandMap* __restrict__ map) {
+                                                         const CandMap* __restrict__ map, int xs0, int xs1, int premethod) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* z = reinterpret_cast<float2*>(smem_raw);
     float* sm_m = reinterpret_cast<float*>(z + n_alloc);
@@ -1176,11 +1176,20 @@ __global__ void __launch_bounds__(256) k_misfit_general(const ReceiverDev* __res
     const CandDev cand = cands[bs];
     float* o = out + ((size_t)b * nmisfits + R.misfit_base) * 2;
     const bool floating = method >= 7;
-    const int bm = method == 7 ? 1 : (method == 8 ? 2 : (method == 3 ? 1 : (method == 4 ? 2 : method)));   // norm applied
+    // method 9 (internal): windowed cross-correlation of the synthetics with the references pulled through the shifts xs0..xs1
+    // (probes_windowed_cross_corr comparator.f90:1061-1090), best shift by receiver_autoshift_ref_seismogram's rule into fshift
+    const bool xcorr = method == KIWI_INTERNAL_XCORR;
+    const int bm = xcorr ? 5 : (method == 7 ? 1 : (method == 8 ? 2 : (method == 3 ? 1 : (method == 4 ? 2 : method))));   // norm applied
     const bool freq = method == 3 || method == 4;
-    const int nshift = floating ? (R.fs1 - R.fs0 + 1) : 1;
+    const int fs0 = xcorr ? xs0 : R.fs0, fs1 = xcorr ? xs1 : R.fs1;
+    const int nshift = floating ? (fs1 - fs0 + 1) : 1;
     bool fail = cand.status != 0 || nshift < 1 || nshift > nshift_alloc;
     for (int ic = 0; ic < R.ncomp && !fail; ic++) if (shdrs[(size_t)pair * KIWI_MAX_COMP + ic].hi < shdrs[(size_t)pair * KIWI_MAX_COMP + ic].lo) fail = true;
+    if (fail && xcorr) {
+        if (threadIdx.x == 0) fshift[opair] = 0;
+        for (int j = threadIdx.x; j < R.ncomp * max(nshift, 0); j += blockDim.x) out[(size_t)opair * KIWI_MAX_COMP * nshift + j] = nanf("");
+        return;
+    }
     if (fail) {
         if (threadIdx.x < R.ncomp) { o[2 * threadIdx.x] = nanf(""); o[2 * threadIdx.x + 1] = nanf(""); }
         if (threadIdx.x == 0) { if (cand.status == 0) atomicMax(&status[b], 1); if (fshift) fshift[opair] = 0; }
@@ -1202,23 +1211,29 @@ __global__ void __launch_bounds__(256) k_misfit_general(const ReceiverDev* __res
         int ssp0, ssp1;
         allowed_span(sds0, sds1, ceil_len2(sds1 - sds0 + 1), ssp0, ssp1);   // probe_set_array(syn) on a fresh probe
         const int rlen = rds1 - rds0 + 1;
-        int shift_total = 0;
+        auto shift_ref = [&](int ishift) {   // probe_shift (comparator.f90:273-288): the span only grows (:245-249)
+            rds0 += ishift; rds1 += ishift;
+            allowed_span(min(rds0, rsp0), max(rds1, rsp1), ceil_len2(rlen), rsp0, rsp1);
+        };
+        auto adjust_spans = [&]() {   // probes_adjust_spans (comparator.f90:464-486)
+            const int u0 = min(rds0, sds0), u1 = max(rds1, sds1);
+            const int minlength = max(ceil_len2(rlen), ceil_len2(sds1 - sds0 + 1));
+            int n0, n1;
+            allowed_span(u0, u1, minlength, n0, n1);
+            const bool same = (rsp0 == ssp0 && rsp1 == ssp1) && ((rsp1 - rsp0) == (n1 - n0)) && (rsp0 <= sds0 && sds1 <= rsp1) &&
+                              (ssp0 <= rds0 && rds1 <= ssp1);
+            if (!same) { rsp0 = ssp0 = n0; rsp1 = ssp1 = n1; }
+        };
+        if (xcorr) {   // the probe spans as update_misfits (minimizer_engine.f90:390) leaves them in a fresh process
+            if (premethod < 0) {
+            } else if (premethod >= 7) {
+                for (int i = 0; i <= R.fs1 - R.fs0; i++) { shift_ref(i == 0 ? R.fs0 : 1); adjust_spans(); }
+                shift_ref(-R.fs1);
+            } else adjust_spans();
+        }
         for (int i = 0; i < nshift; i++) {
-            if (floating) {   // probe_shift (comparator.f90:273-288): the span only grows (:245-249)
-                const int ishift = (i == 0) ? R.fs0 : 1;
-                shift_total += ishift;
-                rds0 += ishift; rds1 += ishift;
-                allowed_span(min(rds0, rsp0), max(rds1, rsp1), ceil_len2(rlen), rsp0, rsp1);
-            }
-            {   // probes_adjust_spans (comparator.f90:464-486)
-                const int u0 = min(rds0, sds0), u1 = max(rds1, sds1);
-                const int minlength = max(ceil_len2(rlen), ceil_len2(sds1 - sds0 + 1));
-                int n0, n1;
-                allowed_span(u0, u1, minlength, n0, n1);
-                const bool same = (rsp0 == ssp0 && rsp1 == ssp1) && ((rsp1 - rsp0) == (n1 - n0)) && (rsp0 <= sds0 && sds1 <= rsp1) &&
-                                  (ssp0 <= rds0 && rds1 <= ssp1);
-                if (!same) { rsp0 = ssp0 = n0; rsp1 = ssp1 = n1; }
-            }
+            if (floating) shift_ref((i == 0) ? fs0 : 1);
+            adjust_spans();
             const int F0 = rsp0, F1 = rsp1, n = F1 - F0 + 1;
             // element x of the probe arrays with the continuation rule (comparator.f90:264-267) and the taper
             auto refval = [&](int x) -> float {
@@ -1241,7 +1256,8 @@ __global__ void __launch_bounds__(256) k_misfit_general(const ReceiverDev* __res
             float dx = dt;
             bool bad = false;
             if (!freq && !filtered) {
-                for (int x = p0 + threadIdx.x; x <= p1; x += blockDim.x) norm_accum2(bm, refval(x), synval(x), fa, fb, unit, acc);
+                if (xcorr) for (int x = p0 + threadIdx.x; x <= p1; x += blockDim.x) norm_accum2(bm, synval(x), refval(x), fb, fa, unit, acc);   // (syn, ref) order
+                else for (int x = p0 + threadIdx.x; x <= p1; x += blockDim.x) norm_accum2(bm, refval(x), synval(x), fa, fb, unit, acc);
                 for (int x = q0 + threadIdx.x; x <= q1; x += blockDim.x) norm_accum1(bm, refval(x), accn);
             } else if (n > n_alloc || n < 2 || (n & (n - 1)) != 0) {
                 bad = true;
@@ -1282,7 +1298,8 @@ __global__ void __launch_bounds__(256) k_misfit_general(const ReceiverDev* __res
                         z[j] = v;
                     }
                     __syncthreads();
-                    for (int x = p0 + threadIdx.x; x <= p1; x += blockDim.x) { const float2 v = z[x - F0]; norm_accum2(bm, v.x, v.y, fa, fb, unit, acc); }
+                    if (xcorr) for (int x = p0 + threadIdx.x; x <= p1; x += blockDim.x) { const float2 v = z[x - F0]; norm_accum2(bm, v.y, v.x, fb, fa, unit, acc); }
+                    else for (int x = p0 + threadIdx.x; x <= p1; x += blockDim.x) { const float2 v = z[x - F0]; norm_accum2(bm, v.x, v.y, fa, fb, unit, acc); }
                     for (int x = q0 + threadIdx.x; x <= q1; x += blockDim.x) norm_accum1(bm, z[x - F0].x, accn);
                 }
             }
@@ -1298,6 +1315,21 @@ __global__ void __launch_bounds__(256) k_misfit_general(const ReceiverDev* __res
             __syncthreads();
         }
     }
+    if (threadIdx.x == 0 && xcorr) {   // receiver.f90:827: maxloc(sum(max(cc/max(1.,maxval(cc)),0.)**2,2),1), first maximum
+        float mx = -FLT_MAX;
+        for (int i = 0; i < nshift; i++) for (int ic = 0; ic < R.ncomp; ic++) mx = fmaxf(mx, sm_m[i * KIWI_MAX_COMP + ic]);
+        const float den = fmaxf(1.f, mx);
+        int iloc = 0; float best = 0.f;
+        for (int i = 0; i < nshift; i++) {
+            float s = 0.f;
+            for (int ic = 0; ic < R.ncomp; ic++) { const float v = fmaxf(__fdiv_rn(sm_m[i * KIWI_MAX_COMP + ic], den), 0.f); s = __fadd_rn(s, __fmul_rn(v, v)); }
+            if (i == 0 || s > best) { best = s; iloc = i; }
+        }
+        fshift[opair] = fs0 + iloc;
+        for (int ic = 0; ic < R.ncomp; ic++)   // the correlations themselves: out[pair][component][shift] (output_cross_correlations)
+            for (int i = 0; i < nshift; i++) out[((size_t)opair * KIWI_MAX_COMP + ic) * nshift + i] = sm_m[i * KIWI_MAX_COMP + ic];
+        return;
+    }
     if (threadIdx.x == 0) {
         int iloc = 0;
         if (floating) {   // minloc(sum(misfits[**2],1),1): first minimum (receiver.f90:486-494)
@@ -1307,7 +1339,7 @@ __global__ void __launch_bounds__(256) k_misfit_general(const ReceiverDev* __res
                 for (int ic = 0; ic < R.ncomp; ic++) { const float m = sm_m[i * KIWI_MAX_COMP + ic]; s = s + (bm == 2 ? m : m * m); }
                 if (i == 0 || s < best) { best = s; iloc = i; }
             }
-            if (fshift) fshift[opair] = R.fs0 + iloc;
+            if (fshift) fshift[opair] = fs0 + iloc;
         } else if (fshift) fshift[opair] = 0;
         for (int ic = 0; ic < R.ncomp; ic++) {
             const float mis = sm_m[iloc * KIWI_MAX_COMP + ic];
@@ -1808,13 +1840,13 @@ size_t misfit_general_smem_bytes(int n_alloc, int nshift_alloc) {
 cudaError_t launch_misfit_general(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, const float* seis, size_t seis_stride,
                                   const SeisHdr* shdrs, const float* refdata, const float* taperdata, const float2* tw, int tw_n, int method,
                                   float dt, float syn_factor, int nmisfits, float* out, int* status, int* fshift, int n_alloc,
-                                  int nshift_alloc, const CandMap* map, cudaStream_t st) {
+                                  int nshift_alloc, const CandMap* map, cudaStream_t st, int xs0, int xs1, int premethod) {
     const size_t smem = misfit_general_smem_bytes(n_alloc, nshift_alloc);
     cudaError_t e = cudaFuncSetAttribute(k_misfit_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (ncand * nrcv > 0)
         k_misfit_general<<<ncand * nrcv, 256, smem, st>>>(rcv, nrcv, cands, seis, seis_stride, shdrs, refdata, taperdata, tw, tw_n, method, dt,
-                                                         syn_factor, nmisfits, out, status, fshift, n_alloc, nshift_alloc, map);
+                                                         syn_factor, nmisfits, out, status, fshift, n_alloc, nshift_alloc, map, xs0, xs1, premethod);
     return cudaGetLastError();
 }
 

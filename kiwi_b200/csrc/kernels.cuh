@@ -36,7 +36,7 @@ size_t misfit_general_smem_bytes(int n_alloc, int nshift_alloc);
 cudaError_t launch_misfit_general(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, const float* seis, size_t seis_stride,
                                   const SeisHdr* shdrs, const float* refdata, const float* taperdata, const float2* tw, int tw_n, int method,
                                   float dt, float syn_factor, int nmisfits, float* out, int* status, int* fshift, int n_alloc,
-                                  int nshift_alloc, const CandMap* map, cudaStream_t st);
+                                  int nshift_alloc, const CandMap* map, cudaStream_t st, int xs0 = 0, int xs1 = 0, int premethod = 0);
 void launch_mt_contract(const ReceiverDev* rcv, int nrcv, const MtLoc* locs, int nloc, const float* mts, const int* cand_of, const float* seis,
                         size_t seis_stride, const SeisHdr* shdrs, const float* refdata, const float* taperdata, int method, float dt,
                         float syn_factor, int nmisfits, float* out, cudaStream_t st);

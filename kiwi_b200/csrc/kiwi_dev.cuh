@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#define KIWI_INTERNAL_XCORR 9     // k_misfit_general: cross-correlation mode (autoshift_ref_seismogram), not a norm id of the ABI
 #define KIWI_MAX_COMP 5          // receiver.f90:35-48: at most a/c r/l d/u n/s e/w
 #define KIWI_NG_MAX 10
 #define KIWI_MAX_PLF 8           // points of a taper / filter piecewise linear function kept on the device

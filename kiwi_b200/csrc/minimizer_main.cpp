@@ -97,7 +97,8 @@ bool do_command(State& S, const std::string& cmd, const std::vector<std::string>
                                   "set_effective_dt", "set_ref_seismograms", "set_misfit_method", "set_misfit_taper", "set_misfit_filter",
                                   "set_synthetics_factor", "set_floating_shiftrange", "get_misfits", "get_global_misfit", "get_floating_shifts",
                                   "output_seismograms", "eval_sources", "set_source_params_mask", "set_source_subparams",
-                                  "set_source_subparams_limits", "get_source_subparams", "minimize_lm", "get_peak_amplitudes", "get_arias_intensities"};
+                                  "set_source_subparams_limits", "get_source_subparams", "minimize_lm", "get_peak_amplitudes", "get_arias_intensities",
+                                  "shift_ref_seismogram", "autoshift_ref_seismogram"};
     bool is_known = false;
     for (const char* k : known) if (cmd == k) is_known = true;
     if (!is_known) return fail("unknown command: " + cmd);   // minimizer.f90:1809-1811
@@ -278,6 +279,17 @@ bool do_command(State& S, const std::string& cmd, const std::vector<std::string>
         int info = 0, iterations = 0; float misfit = 0.f;
         if (kiwi_minimize_lm(S.ctx, &info, &iterations, &misfit)) return cfail();
         *answer = std::to_string(info) + " " + std::to_string(iterations) + " " + fmt_floats(&misfit, 1);
+        return true;
+    }
+    if (cmd == "shift_ref_seismogram") {   // minimizer.f90:356-386
+        if (!to_floats(w, 1, &v) || v.size() != 2) return fail("usage: shift_ref_seismogram ireceiver shift");
+        return kiwi_shift_ref_seismogram(S.ctx, (int)v[0], v[1]) ? cfail() : true;
+    }
+    if (cmd == "autoshift_ref_seismogram") {   // minimizer.f90:447-483: the applied shifts in seconds
+        if (!to_floats(w, 1, &v) || v.size() != 3) return fail("usage: autoshift_ref_seismogram ireceiver min-shift max-shift");
+        std::vector<float> f(S.comps.size() + 1); int n = 0;
+        if (kiwi_autoshift_ref_seismogram(S.ctx, (int)v[0], v[1], v[2], f.data(), (int)f.size(), &n)) return cfail();
+        *answer = fmt_floats(f.data(), (size_t)n);
         return true;
     }
     if (cmd == "get_floating_shifts") {   // minimizer_engine.f90:1095-1128: seconds

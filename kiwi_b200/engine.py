@@ -177,6 +177,7 @@ class Engine:
             components = [components] * n
         arr = (C.c_char_p * n)(*[c.encode() for c in components])
         _check(lib.kiwi_set_receivers(self._h, n, lat.ctypes.data_as(c_double_p), lon.ctypes.data_as(c_double_p), _fp(dep), arr))
+        self._nreceivers = n
 
     def set_receivers_file(self, path, has_depth=False):
         """set_receivers <file> [has_depth]: lat lon [depth] [components] per line (minimizer_engine.f90:165-286)."""
@@ -403,6 +404,24 @@ class Engine:
         n = C.c_int()
         _check(lib.kiwi_get_floating_shifts(self._h, out.ctypes.data_as(c_int_p), nr, n))
         return out[:n.value]
+
+    def shift_ref_seismogram(self, ireceiver, shift):
+        """shift_ref_seismogram (minimizer_engine.f90:354-378): seconds."""
+        _check(lib.kiwi_shift_ref_seismogram(self._h, ireceiver, shift))
+
+    def autoshift_ref_seismogram(self, ireceiver, shift_lo, shift_hi):
+        """autoshift_ref_seismogram (minimizer_engine.f90:380-416): the applied shifts in seconds (ireceiver 0 = all)."""
+        out = np.zeros(max(1, getattr(self, "_nreceivers", 4096) if ireceiver == 0 else 1), dtype=np.float32)
+        n = C.c_int()
+        _check(lib.kiwi_autoshift_ref_seismogram(self._h, ireceiver, shift_lo, shift_hi, out.ctypes.data_as(c_float_p), out.size, n))
+        return out[:n.value]
+
+    def get_cross_correlations(self, ireceiver, shift_lo, shift_hi):
+        """In-memory replacement of output_cross_correlations: array [component][shift]."""
+        out = np.zeros(5 * 8192, dtype=np.float32)
+        nc, ns = C.c_int(), C.c_int()
+        _check(lib.kiwi_get_cross_correlations(self._h, ireceiver, shift_lo, shift_hi, out.ctypes.data_as(c_float_p), out.size, nc, ns))
+        return out[:nc.value * ns.value].reshape(nc.value, ns.value).copy()
 
     def get_seismogram(self, ireceiver, icomponent, which=0):
         """In-memory replacement of output_seismograms: (first_index, samples)."""

@@ -150,6 +150,38 @@ static inline float receiver_get_arias_intensity(Receiver& self) {
     return 0.f;
 }
 
+// receiver.f90:597-616
+static inline void receiver_calculate_cross_correlations(Receiver& self, const int shiftrange[2], std::vector<float>& cross_corr /* [ncomp][nshift] */) {
+    const int ns = slen(shiftrange);
+    cross_corr.assign((size_t)self.ncomponents * ns, 0.f);
+    for (int ic = 0; ic < self.ncomponents; ic++)
+        probes_windowed_cross_corr(self.syn_probes[ic], self.ref_probes[ic], shiftrange, &cross_corr[(size_t)ic * ns]);
+}
+// receiver.f90:802-814
+static inline void receiver_shift_ref_seismogram(Receiver& self, int ishift) {
+    for (int ic = 0; ic < self.ncomponents; ic++) probe_shift(self.ref_probes[ic], ishift);
+}
+// receiver.f90:816-832: shift of the references that maximises the summed squared positive normalised cross-correlation
+static inline int receiver_autoshift_ref_seismogram(Receiver& self, const int ishiftrange[2]) {
+    int ishift = 0;
+    if (!self.enabled) return ishift;
+    std::vector<float> cc;
+    receiver_calculate_cross_correlations(self, ishiftrange, cc);
+    const int ns = slen(ishiftrange);
+    float mx = -std::numeric_limits<float>::max();
+    for (float v : cc) mx = std::max(mx, v);
+    const float den = std::max(1.f, mx);
+    int imax = 0; float best = 0.f;
+    for (int i = 0; i < ns; i++) {   // maxloc(sum(max(cc/den,0.)**2, 2), 1): first maximum
+        float sum = 0.f;
+        for (int ic = 0; ic < self.ncomponents; ic++) { const float v = std::max(cc[(size_t)ic * ns + i] / den, 0.f); sum = sum + v * v; }
+        if (i == 0 || sum > best) { best = sum; imax = i; }
+    }
+    ishift = imax + ishiftrange[0];
+    receiver_shift_ref_seismogram(self, ishift);
+    return ishift;
+}
+
 static inline void receiver_calculate_misfits(Receiver& self, int misfit_method) {
     if (misfit_method == FLOATING_L1NORM || misfit_method == FLOATING_L2NORM) {
         receiver_calculate_floating_misfits(self, misfit_method, self.floating_shiftrange);

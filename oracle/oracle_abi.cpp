@@ -72,6 +72,65 @@ int oracle_set_floating_shiftrange(void* h, int irec, float lo, float hi) {  // 
     else { e.receivers[irec - 1].floating_shiftrange[0] = r[0]; e.receivers[irec - 1].floating_shiftrange[1] = r[1]; }
     return 0;
 }
+// Under the fresh-state semantics a shifted reference is a reference set anew with its first sample moved by ishift samples
+static void reinit_shifted_ref(Engine& e, int ir, int ishift) {
+    Receiver& r = e.receivers[ir];
+    for (int c = 0; c < r.ncomponents; c++) {
+        const Probe& old = e.ref_probes_initial[ir][c];
+        Probe np; probe_init(np, r.dt);
+        np.taper = old.taper; np.filter = old.filter; np.factor = old.factor;
+        if (old.array.alloc) {
+            Strip strip;
+            strip_init(old.dataspan[0] + ishift, old.dataspan[1] + ishift, &old.array.d[old.dataspan[0] - old.array.lo], slen(old.dataspan), strip);
+            probe_set_array(np, strip);
+        }
+        e.ref_probes_initial[ir][c] = np;
+        r.ref_probes[c] = np;
+    }
+}
+// shift_ref_seismogram (minimizer_engine.f90:354-378)
+int oracle_shift_ref_seismogram(void* h, int irec, float shift) {
+    Engine& e = *(Engine*)h;
+    if (!e.ref_probes_inited) { e.errstr = "no reference seismograms set"; return 1; }
+    if (irec < 1 || irec > (int)e.receivers.size()) { e.errstr = "receiver index out of range"; return 1; }
+    reinit_shifted_ref(e, irec - 1, f_nint(shift / e.db.dt));
+    return 0;
+}
+// autoshift_ref_seismogram (minimizer_engine.f90:380-416): update_misfits of the current source (as the first evaluation of a fresh
+// process), then receiver_autoshift_ref_seismogram; shifts[] in seconds, one per receiver (irec = 0) or one
+int oracle_autoshift_ref_seismogram(void* h, int irec, float lo, float hi, float* shifts) {
+    Engine& e = *(Engine*)h;
+    if (e.cur_params.empty()) { e.errstr = "no source parameters set"; return 1; }
+    std::vector<float> params = e.cur_params;
+    if (evaluate(e, e.cur_type, params.data(), (int)params.size(), nullptr, 0) < 0) return 1;
+    const int r[2] = {f_nint(lo / e.db.dt), f_nint(hi / e.db.dt)};
+    if (irec != 0 && (irec < 1 || irec > (int)e.receivers.size())) { e.errstr = "receiver index out of range"; return 1; }
+    const int i0 = irec == 0 ? 0 : irec - 1, i1 = irec == 0 ? (int)e.receivers.size() : irec;
+    for (int i = i0; i < i1; i++) {
+        const int ishift = receiver_autoshift_ref_seismogram(e.receivers[i], r);
+        shifts[i - i0] = ishift * e.db.dt;
+        reinit_shifted_ref(e, i, ishift);
+    }
+    return 0;
+}
+// output_cross_correlations (minimizer_engine.f90:1283-1306) in memory: update_syn_probes of the current source in a fresh process,
+// then receiver_calculate_cross_correlations; cc[component][shift]
+int oracle_get_cross_correlations(void* h, int irec, float lo, float hi, float* cc, int* ncomp, int* nshift) {
+    Engine& e = *(Engine*)h;
+    if (e.cur_params.empty()) { e.errstr = "no source parameters set"; return 1; }
+    if (irec < 1 || irec > (int)e.receivers.size()) { e.errstr = "receiver index out of range"; return 1; }
+    std::vector<float> params = e.cur_params;
+    if (!set_source_params(e, e.cur_type, params.data(), (int)params.size())) return 1;
+    if (!calculate_seismograms(e)) return 1;
+    scale_seismograms(e);
+    const int r[2] = {f_nint(lo / e.db.dt), f_nint(hi / e.db.dt)};
+    Receiver& rc = e.receivers[irec - 1];
+    std::vector<float> v;
+    if (rc.enabled) receiver_calculate_cross_correlations(rc, r, v);
+    for (size_t i = 0; i < v.size(); i++) cc[i] = v[i];
+    *ncomp = rc.enabled ? rc.ncomponents : 0; *nshift = slen(r);
+    return 0;
+}
 int oracle_set_crust2x2(void* h, const char* path) {
     Engine& e = *(Engine*)h;
     if (!crust2x2_load(path, e.crust)) { e.errstr = "can't load crust2x2 table"; return 1; }

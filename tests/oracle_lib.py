@@ -37,7 +37,8 @@ def lib(wide=False):
                      "oracle_get_probe_spans", "oracle_discretize_source", "oracle_record_indices", "oracle_get_indices",
                      "oracle_receiver_geometry", "oracle_trace_span", "oracle_time_eval", "oracle_get_strip_spans",
                      "oracle_set_source_params_mask", "oracle_set_source_subparams", "oracle_set_source_subparams_limits",
-                     "oracle_get_source_subparams", "oracle_minimize_lm", "oracle_lmdif", "oracle_get_ground_motion"):
+                     "oracle_get_source_subparams", "oracle_minimize_lm", "oracle_lmdif", "oracle_get_ground_motion",
+                     "oracle_shift_ref_seismogram", "oracle_autoshift_ref_seismogram", "oracle_get_cross_correlations"):
             if hasattr(L, name):
                 getattr(L, name).argtypes = None
         _libs[wide] = L
@@ -120,6 +121,7 @@ class OracleEngine:
             components = [components] * n
         arr = (C.c_char_p * n)(*[c.encode() for c in components])
         self._check(self.L.oracle_set_receivers(self.h, C.c_int(n), lat.ctypes.data_as(dp), lon.ctypes.data_as(dp), dep.ctypes.data_as(fp), arr))
+        self.nreceivers = n
 
     def switch_receiver(self, irec, state):
         self._check(self.L.oracle_switch_receiver(self.h, C.c_int(irec), C.c_int(int(bool(state)))))
@@ -225,6 +227,20 @@ class OracleEngine:
         out = np.zeros(4096, np.int32)
         n = self.L.oracle_get_floating_shifts(self.h, out.ctypes.data_as(ip))
         return out[:n]
+
+    def shift_ref_seismogram(self, irec, shift):
+        self._check(self.L.oracle_shift_ref_seismogram(self.h, C.c_int(irec), C.c_float(shift)))
+
+    def autoshift_ref_seismogram(self, irec, lo, hi):
+        out = np.zeros(4096, np.float32)
+        self._check(self.L.oracle_autoshift_ref_seismogram(self.h, C.c_int(irec), C.c_float(lo), C.c_float(hi), out.ctypes.data_as(fp)))
+        return out[:(self.nreceivers if irec == 0 else 1)]
+
+    def get_cross_correlations(self, irec, lo, hi):
+        out = np.zeros(5 * 8192, np.float32)
+        nc, ns = C.c_int(), C.c_int()
+        self._check(self.L.oracle_get_cross_correlations(self.h, C.c_int(irec), C.c_float(lo), C.c_float(hi), out.ctypes.data_as(fp), C.byref(nc), C.byref(ns)))
+        return out[:nc.value * ns.value].reshape(nc.value, ns.value).copy()
 
     def get_seismogram(self, irec, icomp, which=0):
         first, n = C.c_int(), C.c_int()

@@ -121,3 +121,26 @@ def test_eikonal_source_properties():
     p2 = p.copy(); p2[11] = 9000
     _, st = o.eval_sources("eikonal", p2)
     assert st[0] == 1
+
+
+def test_autoshift_finds_the_delay_of_the_references():
+    """receiver_autoshift_ref_seismogram (receiver.f90:816-832) has no reference test: references that are the synthetics delayed
+    by k samples must be moved back by k, after which the misfit is that of the unshifted references"""
+    ncomps = [len(c) for c in COMPS]
+    lat, lon, dep = sc.small_receivers(len(COMPS))
+    a, b = OracleEngine(), OracleEngine()
+    for o in (a, b):   # far-field terms only: the traces return to zero, so the cross-correlation peaks at the true delay
+        sc.setup(o, sc.small_db_ng8(), lat, lon, dep, COMPS)
+    a.eval_sources("bilateral", sc.BILAT_SMALL)
+    sc.set_refs_from(a, [a], ncomps, shift=0)
+    sc.set_refs_from(a, [b], ncomps, shift=4)
+    m0, _ = a.eval_sources("bilateral", sc.BILAT_SMALL)
+    m_late, _ = b.eval_sources("bilateral", sc.BILAT_SMALL)
+    assert m_late[0, :, 0].sum() > 2 * m0[0, :, 0].sum()
+    b.shift_ref_seismogram(6, -0.1)                      # receiver 6: late by 3 only
+    shifts = b.autoshift_ref_seismogram(0, -0.7, 0.7)
+    assert np.allclose(shifts, [-0.4] * 5 + [-0.3], atol=1e-6)
+    m1, _ = b.eval_sources("bilateral", sc.BILAT_SMALL)
+    assert np.array_equal(m0, m1)
+    # a second pass finds nothing left to do
+    assert np.allclose(b.autoshift_ref_seismogram(0, -0.7, 0.7), 0.0)

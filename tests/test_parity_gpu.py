@@ -294,6 +294,73 @@ def test_floating_misfits(norm, taper, filt):
     assert list(g.get_floating_shifts())[0] == -3
 
 
+@pytest.mark.parametrize("premethod", ["l2norm", "floating_l2norm"])
+@pytest.mark.parametrize("taper,filt", [(False, False), (True, False), (True, True)])
+def test_autoshift_ref_seismogram(premethod, taper, filt):
+    """autoshift_ref_seismogram (minimizer_engine.f90:380-416, receiver.f90:816-832): the references move to the maximum of the
+    windowed cross-correlation with the synthetics; shift_ref_seismogram (:354-378) moves them by hand.  Far-field database:
+    with the static near-field offsets the continuation rule makes the correlation double-peaked with an exact tie."""
+    g, o = engines(sc.small_db_ng8(), COMPS6)
+    ncomps = [len(c) for c in COMPS6]
+    o.eval_sources("bilateral", sc.BILAT_SMALL)
+    sc.set_refs_from(o, [g, o], ncomps, shift=3)          # references late by 3 samples
+    for e in (g, o):
+        e.set_misfit_method(premethod)
+        if premethod.startswith("floating"):
+            e.set_floating_shiftrange(-0.2, 0.2)
+        if taper:
+            for ir in range(1, 7):
+                e.set_misfit_taper(ir, *TAPER)
+        if filt:
+            e.set_misfit_filter(*FILTER)
+        e.switch_receiver(4, False)
+        e.shift_ref_seismogram(5, 0.2)                    # receiver 5: late by 5 samples now
+    p = _candidates()
+    o.eval_sources("bilateral", p[0])
+    g.set_source_params("bilateral", p[0])
+    sg = g.autoshift_ref_seismogram(2, -0.1, 0.9)          # one receiver, a range that excludes the true shift
+    so = o.autoshift_ref_seismogram(2, -0.1, 0.9)
+    assert np.array_equal(sg, so) and sg.size == 1
+    sg = g.autoshift_ref_seismogram(0, -0.8, 0.6)
+    so = o.autoshift_ref_seismogram(0, -0.8, 0.6)
+    assert np.array_equal(sg, so) and sg.size == 6
+    assert sg[3] == 0.0                                   # disabled receiver
+    if not taper:
+        assert abs(sg[0] + 0.3) < 1e-6 and abs(sg[4] + 0.5) < 1e-6
+    # the shifted references are what the next evaluations see
+    mg, stg = g.eval_sources("bilateral", p)
+    mo, sto = o.eval_sources("bilateral", p)
+    assert not stg.any() and not sto.any()
+    assert np.all(np.abs(mg - mo) <= misfit_tol(mo)), np.abs((mg - mo) / misfit_tol(mo)).max()
+    with pytest.raises(Exception, match="receiver index out of range"):
+        g.autoshift_ref_seismogram(7, -0.1, 0.1)
+
+
+@pytest.mark.parametrize("taper,filt", [(False, False), (True, False), (True, True)])
+def test_cross_correlations(taper, filt):
+    """receiver_calculate_cross_correlations (receiver.f90:597-616, comparator.f90:1061-1090) as output_cross_correlations returns them"""
+    g, o = engines(sc.small_db(), COMPS6)
+    ncomps = [len(c) for c in COMPS6]
+    o.eval_sources("bilateral", sc.BILAT_SMALL)
+    sc.set_refs_from(o, [g, o], ncomps, shift=-2)
+    for e in (g, o):
+        e.set_synthetics_factor(0.9)
+        if taper:
+            for ir in range(1, 7):
+                e.set_misfit_taper(ir, *TAPER)
+        if filt:
+            e.set_misfit_filter(*FILTER)
+    p = _candidates()[1]
+    o.eval_sources("bilateral", p)
+    g.set_source_params("bilateral", p)
+    for ir in range(1, 7):
+        cg = g.get_cross_correlations(ir, -0.5, 0.7)
+        co = o.get_cross_correlations(ir, -0.5, 0.7)
+        assert cg.shape == co.shape == (ncomps[ir - 1], 13)
+        scale = np.abs(co).max(axis=1, keepdims=True)
+        assert np.all(np.abs(cg - co) <= (4 if filt else 1) * RTOL * scale), (ir, (np.abs(cg - co) / scale).max())
+
+
 def _mt_grid(nloc=3, nmt=45):
     from kiwi_b200 import synthetic
     mts = synthetic.fibonacci_moment_tensors(nmt) * 1e18
