@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the Kiwi source-inversion hot path on B200 (contract: see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|small] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4|c5|small] [--batch B]
     python bench.py --impl reference ...      # the CPU restatement of the reference on the host cores
 
 A "step" is one batched evaluation (kiwi_eval_sources) of B candidate bilateral sources: source
@@ -38,6 +38,9 @@ WORKLOADS = {
     "c4": dict(db="bench-L", nx=2000, nz=150, dx=100.0, dz=200.0, nrcv=200, effective_dt=0.5, dmin=45e3, dmax=150e3,
                norm="ampspec_l1norm", batch=32, cpu_sample=1, source="eikonal",
                taper=([2.0, 6.0, 70.0, 80.0], [0, 1, 1, 0]), filter=([0.01, 0.02, 0.1, 0.2], [0, 1, 1, 0])),
+    # the dense-array sweep -- the C3 source and candidate grid on 2000 receivers
+    "c5": dict(db="bench-L", nx=2000, nz=150, dx=100.0, dz=200.0, nrcv=2000, effective_dt=0.35, dmin=45e3, dmax=150e3,
+               norm="l2norm", batch=8, cpu_sample=1),
     # quick functional run (kiwibench-size pieces)
     "small": dict(db="bench-L/8", nx=1000, nz=60, dx=100.0, dz=400.0, nrcv=24, effective_dt=0.5, dmin=45e3, dmax=55e3,
                   norm="l2norm", batch=8, cpu_sample=2),
