@@ -89,6 +89,14 @@ kiwi_gfdb* kiwi_gfdb_read_hdf(const char* basepath);
  * dtype_class: 0 integer, 1 float, 7 reference ...; dims8: up to 8 extents; *nbytes: size of the data / of the name list. */
 int kiwi_h5_read_root_dataset(const char* path, const char* name, int* dtype_class, int* dtype_size, int* rank, long long* dims8, void* buf,
                               long long cap, long long* nbytes, int* nattrs);
+/* set_database dbpath nipx nipz (minimizer.f90:89-135; gfdb_init gfdb.f90:205-246): Gulunay's generalised f-k interpolation of
+ * the database (gfdb_interpolate_block gfdb.f90:1109-1232, interpolate3d :1234-1310, interpolation.f90) on GPU `device`.  Returns a
+ * new database with nx*nipx x nz*nipz traces at dx/nipx, dz/nipz; every interpolation block is filled eagerly (the reference fills
+ * a block on first access).  nipx, nipz in {1, 2, 4, 8, 16}; every trace of the source database must be present. */
+kiwi_gfdb* kiwi_gfdb_interpolate(const kiwi_gfdb* db, int nipx, int nipz, int device);
+/* the interpolation operator itself (gulunay2d / gulunay3d, interpolation.f90:29-311) on `batch` fields a[batch][s2][s1][t]
+ * (tapered in place like the reference's A) -> out[batch][s2*l2][s1*l1][t]; l1, l2 in {1, l}; margins as in the reference */
+int kiwi_gulunay(int device, float* a, int batch, int t, int s1, int s2, int l1, int l2, int ntmargin, int margin1, int margin2, float* out);
 /* gfdb_info: grid metadata */
 int kiwi_gfdb_meta(const kiwi_gfdb* db, int* nx, int* nz, int* ng, float* dt, float* dx, float* dz, float* firstx,
                    float* firstz, long long* ntraces, long long* nsamples);
@@ -102,7 +110,7 @@ kiwi_ctx* kiwi_create(int device);
 void kiwi_destroy(kiwi_ctx* ctx);
 
 /* set_database (minimizer_engine.f90:114-139): packs the database into 16-byte aligned slabs and
- * uploads it to HBM once.  nipx/nipz (Gulunay interpolation) are not supported (out of scope). */
+ * uploads it to HBM once.  For nipx/nipz (Gulunay interpolation) pass the result of kiwi_gfdb_interpolate. */
 int kiwi_set_database(kiwi_ctx* ctx, kiwi_gfdb* db);
 /* set_local_interpolation (minimizer_engine.f90:140-145): 0 nearest neighbour, 1 bilinear */
 int kiwi_set_local_interpolation(kiwi_ctx* ctx, int bilinear);

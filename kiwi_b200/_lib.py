@@ -26,6 +26,8 @@ SIGNATURES = {
     "kiwi_gfdb_read": (C.c_void_p, [C.c_char_p]),
     "kiwi_gfdb_read_hdf": (C.c_void_p, [C.c_char_p]),
     "kiwi_h5_read_root_dataset": (C.c_int, [C.c_char_p, C.c_char_p, c_int_p, c_int_p, c_int_p, c_ll_p, C.c_void_p, C.c_longlong, c_ll_p, c_int_p]),
+    "kiwi_gfdb_interpolate": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "kiwi_gulunay": (C.c_int, [C.c_int, c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p]),
     "kiwi_gfdb_meta": (C.c_int, [C.c_void_p, c_int_p, c_int_p, c_int_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_ll_p, c_ll_p]),
     "kiwi_gfdb_view": (C.c_int, [C.c_void_p, C.POINTER(c_int_p), C.POINTER(c_int_p), C.POINTER(c_ll_p), C.POINTER(c_float_p)]),
     "kiwi_create": (C.c_void_p, [C.c_int]),

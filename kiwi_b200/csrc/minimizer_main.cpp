@@ -111,12 +111,17 @@ bool do_command(State& S, const std::string& cmd, const std::vector<std::string>
     std::vector<float> v;
     if (cmd == "set_database") {
         if (w.size() < 2) return fail("usage: set_database dbpath [ nipx nipz ]");
-        if (w.size() >= 4 && (atoi(w[2].c_str()) != 1 || atoi(w[3].c_str()) != 1)) return fail("set_database: trace interpolation (nipx, nipz > 1) is not available");
         // a Kiwi database is <dbpath>.index + <dbpath>.<i>.chunk (HDF5, gfdb.f90:209-211); a single file is this library's KGF1 dump
         kiwi_gfdb* db = nullptr;
         if (FILE* probe = fopen((w[1] + ".index").c_str(), "rb")) { fclose(probe); db = kiwi_gfdb_read_hdf(w[1].c_str()); }
         else db = kiwi_gfdb_read(w[1].c_str());
         if (!db) return cfail();
+        if (w.size() >= 4 && (atoi(w[2].c_str()) != 1 || atoi(w[3].c_str()) != 1)) {   // Gulunay interpolation (minimizer.f90:98-112)
+            kiwi_gfdb* ip = kiwi_gfdb_interpolate(db, atoi(w[2].c_str()), atoi(w[3].c_str()), 0);
+            kiwi_gfdb_destroy(db);
+            if (!ip) return cfail();
+            db = ip;
+        }
         if (kiwi_set_database(S.ctx, db)) { kiwi_gfdb_destroy(db); return cfail(); }
         if (S.db) kiwi_gfdb_destroy(S.db);
         S.db = db;

@@ -93,6 +93,10 @@ class Gfdb:
         _check(lib.kiwi_gfdb_build_ahfull(self._h, rho, alpha, beta, _fp(s), s.size, int(nfflag), int(ffflag), nthreads))
         return self
 
+    def interpolate(self, nipx, nipz, device=0):
+        """The database `set_database dbpath nipx nipz` works on: Gulunay f-k interpolation on the GPU (gfdb.f90:1109-1310)."""
+        return Gfdb(lib.kiwi_gfdb_interpolate(self._h, nipx, nipz, device))
+
     def meta(self):
         nx, nz, ng = C.c_int(), C.c_int(), C.c_int()
         dt, dx, dz, fx, fz = C.c_float(), C.c_float(), C.c_float(), C.c_float(), C.c_float()
@@ -134,6 +138,7 @@ class Engine:
             raise KiwiError(lib.kiwi_last_error().decode())
         self._h = C.c_void_p(h)
         self._db = None
+        self._device = device
         if os.path.exists(CRUST2X2_TABLE):          # minimizer loads crust2x2 at start-up (minimizer.f90:1669-1674)
             self.set_crust2x2(CRUST2X2_TABLE)
 
@@ -152,7 +157,10 @@ class Engine:
             pass
 
     # ---- setters (one per reference command) --------------------------------------------------------
-    def set_database(self, db):
+    def set_database(self, db, nipx=1, nipz=1):
+        """set_database dbpath [nipx nipz] (minimizer.f90:89-135): nipx, nipz > 1 turn on Gulunay's interpolation of the database."""
+        if nipx != 1 or nipz != 1:
+            db = db.interpolate(nipx, nipz, self._device)
         _check(lib.kiwi_set_database(self._h, db._h))
         self._db = db
 
@@ -473,6 +481,15 @@ class Engine:
         _check(lib.kiwi_last_timing(self._h, _fp(ms), ln.ctypes.data_as(c_int_p)))
         return dict(discretise_ms=float(ms[0]), geometry_ms=float(ms[1]), synthesis_ms=float(ms[2]), misfit_ms=float(ms[3]),
                     total_ms=float(ms[4]), launches=[int(v) for v in ln])
+
+
+def gulunay(a, l1, l2, ntmargin, margin1, margin2, device=0):
+    """gulunay2d / gulunay3d (interpolation.f90) on fields a[batch][s2][s1][t]: returns (tapered a, out[batch][s2*l2][s1*l1][t])."""
+    a = np.ascontiguousarray(a, dtype=np.float32).copy()
+    batch, s2, s1, t = a.shape
+    out = np.zeros((batch, s2 * l2, s1 * l1, t), dtype=np.float32)
+    _check(lib.kiwi_gulunay(device, _fp(a), batch, t, s1, s2, l1, l2, ntmargin, margin1, margin2, _fp(out)))
+    return a, out
 
 
 def lmdif_batched(fcn, x0, m, ftol=None, xtol=None, gtol=0.0, maxfev=None, epsfcn=0.0, diag=None, mode=1, factor=100.0):

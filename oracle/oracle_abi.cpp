@@ -2,6 +2,7 @@
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs can drive it.
 // The entry points deliberately mirror include/kiwi_b200.h one to one.
 #include "ko_engine.hpp"
+#include "ko_interp.hpp"
 #include <chrono>
 
 using namespace ko;
@@ -129,6 +130,37 @@ int oracle_get_cross_correlations(void* h, int irec, float lo, float hi, float* 
     if (rc.enabled) receiver_calculate_cross_correlations(rc, r, v);
     for (size_t i = 0; i < v.size(); i++) cc[i] = v[i];
     *ncomp = rc.enabled ? rc.ncomponents : 0; *nshift = slen(r);
+    return 0;
+}
+// ---- Gulunay interpolation of a database (gfdb.f90:1109-1310, interpolation.f90), every block eagerly ----------------
+static InterpGfdb g_interp;
+int oracle_gfdb_interpolate(int nx, int nz, int ng, float dt, float dx, float dz, float firstx, float firstz, const int* span0, const int* len,
+                            const long long* offset, const float* data, int nipx, int nipz) {
+    Gfdb src;
+    gfdb_from_arrays(src, nx, nz, ng, dt, dx, dz, firstx, firstz, span0, len, offset, data);
+    interp_gfdb_init(g_interp, src, nipx, nipz);
+    gfdb_interpolate_all(g_interp);
+    return 0;
+}
+int oracle_interp_meta(int* nx, int* nz, float* dx, float* dz) {
+    *nx = g_interp.db.nx; *nz = g_interp.db.nz; *dx = g_interp.db.dx; *dz = g_interp.db.dz; return 0;
+}
+// dense samples of trace (ix, iz, ig) of the interpolated database over its span (gaps between strips are zeros)
+int oracle_interp_trace(int ix, int iz, int ig, int* span0, int* len, float* buf, int cap) {
+    Trace* t = gfdb_get_trace(g_interp.db, ix, iz, ig);
+    if (!t) { *span0 = 0; *len = 0; return 0; }
+    *span0 = t->span[0]; *len = t->span[1] - t->span[0] + 1;
+    if (*len > cap) return 1;
+    for (int i = 0; i < *len; i++) buf[i] = 0.f;
+    for (const Strip& st : t->strips) for (int i = st.lo; i <= st.hi(); i++) buf[i - t->span[0]] = (float)st.at(i);
+    return 0;
+}
+// gulunay on a caller-provided field (t, s1, s2) -> (t, s1*l1, s2*l2); a is tapered in place
+int oracle_gulunay(float* a, int t, int s1, int s2, int l1, int l2, float* out, int ntmargin, int margin1, int margin2) {
+    std::vector<float> A(a, a + (size_t)t * s1 * s2), I;
+    gulunay(A, t, s1, s2, l1, l2, I, ntmargin, margin1, margin2);
+    for (size_t i = 0; i < A.size(); i++) a[i] = A[i];
+    for (size_t i = 0; i < I.size(); i++) out[i] = I[i];
     return 0;
 }
 int oracle_set_crust2x2(void* h, const char* path) {

@@ -312,3 +312,41 @@ def oracle_lmdif(fcn, x0, m, ftol=None, xtol=None, gtol=0.0, maxfev=None, epsfcn
 def oracle_enorm(x):
     a = _f32(x).ravel()
     return float(lib().oracle_enorm(C.c_int(a.size), a.ctypes.data_as(fp)))
+
+
+def gfdb_interpolate(db, nipx, nipz, wide=False):
+    """Gulunay-interpolated database (gfdb.f90:1109-1310, interpolation.f90) through the oracle: dict (ix, iz, ig) -> (span0, samples)
+    plus the meta of the interpolated grid."""
+    L = lib(wide)
+    m = db.meta()
+    span0, length, offset, data = db.view()
+    lp = C.POINTER(C.c_longlong)
+    rc = L.oracle_gfdb_interpolate(C.c_int(m["nx"]), C.c_int(m["nz"]), C.c_int(m["ng"]), C.c_float(m["dt"]), C.c_float(m["dx"]), C.c_float(m["dz"]),
+                                   C.c_float(m["firstx"]), C.c_float(m["firstz"]), span0.ctypes.data_as(ip), length.ctypes.data_as(ip),
+                                   offset.ctypes.data_as(lp), data.ctypes.data_as(fp), C.c_int(nipx), C.c_int(nipz))
+    assert rc == 0
+    nx, nz, dx, dz = C.c_int(), C.c_int(), C.c_float(), C.c_float()
+    L.oracle_interp_meta(C.byref(nx), C.byref(nz), C.byref(dx), C.byref(dz))
+    out = {}
+    buf = np.empty(1 << 16, np.float32)
+    s0, n = C.c_int(), C.c_int()
+    for ix in range(1, nx.value + 1):
+        for iz in range(1, nz.value + 1):
+            for ig in range(1, m["ng"] + 1):
+                rc = L.oracle_interp_trace(C.c_int(ix), C.c_int(iz), C.c_int(ig), C.byref(s0), C.byref(n), buf.ctypes.data_as(fp), C.c_int(buf.size))
+                assert rc == 0
+                if n.value > 0:
+                    out[(ix, iz, ig)] = (s0.value, buf[:n.value].copy())
+    return dict(nx=nx.value, nz=nz.value, dx=dx.value, dz=dz.value), out
+
+
+def gulunay(a, l1, l2, ntmargin, margin1, margin2, wide=False):
+    """interpolation.f90 gulunay2d / gulunay3d on a field a[s2][s1][t] (C order; Fortran (t, s1, s2)); returns (tapered a, out[s2*l2][s1*l1][t])"""
+    L = lib(wide)
+    a = np.ascontiguousarray(a, np.float32).copy()
+    s2, s1, t = a.shape
+    out = np.zeros((s2 * l2, s1 * l1, t), np.float32)
+    rc = L.oracle_gulunay(a.ctypes.data_as(fp), C.c_int(t), C.c_int(s1), C.c_int(s2), C.c_int(l1), C.c_int(l2), out.ctypes.data_as(fp),
+                          C.c_int(ntmargin), C.c_int(margin1), C.c_int(margin2))
+    assert rc == 0
+    return a, out
