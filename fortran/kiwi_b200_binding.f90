@@ -143,6 +143,43 @@ module kiwi_b200_binding
             integer(c_int) :: rc
         end function
 
+        function kiwi_shift_ref_seismogram(ctx, ireceiver, shift) bind(C, name="kiwi_shift_ref_seismogram") result(rc)
+            import :: c_ptr, c_int, c_float
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: ireceiver
+            real(c_float), value :: shift
+            integer(c_int) :: rc
+        end function
+
+        function kiwi_autoshift_ref_seismogram(ctx, ireceiver, shift_lo, shift_hi, shifts, cap, n) &
+                bind(C, name="kiwi_autoshift_ref_seismogram") result(rc)
+            import :: c_ptr, c_int, c_float
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: ireceiver, cap
+            real(c_float), value :: shift_lo, shift_hi
+            real(c_float), dimension(*), intent(out) :: shifts
+            integer(c_int), intent(out) :: n
+            integer(c_int) :: rc
+        end function
+
+        function kiwi_get_cross_correlations(ctx, ireceiver, shift_lo, shift_hi, cc, cap, ncomp, nshift) &
+                bind(C, name="kiwi_get_cross_correlations") result(rc)
+            import :: c_ptr, c_int, c_float
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: ireceiver, cap
+            real(c_float), value :: shift_lo, shift_hi
+            real(c_float), dimension(*), intent(out) :: cc      ! (nshift, ncomp)
+            integer(c_int), intent(out) :: ncomp, nshift
+            integer(c_int) :: rc
+        end function
+
+        function kiwi_gfdb_interpolate(db, nipx, nipz, device) bind(C, name="kiwi_gfdb_interpolate") result(newdb)
+            import :: c_ptr, c_int
+            type(c_ptr), value :: db
+            integer(c_int), value :: nipx, nipz, device
+            type(c_ptr) :: newdb
+        end function
+
         function kiwi_get_nmisfits(ctx) bind(C, name="kiwi_get_nmisfits") result(n)
             import :: c_ptr, c_int
             type(c_ptr), value :: ctx

@@ -215,7 +215,7 @@ __device__ __forceinline__ void set_span(const GfdbDev& db, const int inode[4], 
 // SINGLE: every candidate has one group (point sources: the 6 x nloc x nrcv basis syntheses of a moment-tensor grid search are
 // 6e5 pairs of one group each): one THREAD per (candidate, receiver) instead of one CTA, no block reductions.
 template <bool SINGLE>
-__global__ void __launch_bounds__(256) k_geometry(GfdbDev db, const ReceiverDev* __restrict__ rcv, int nrcv,
+__global__ void __launch_bounds__(256, 3) k_geometry(GfdbDev db, const ReceiverDev* __restrict__ rcv, int nrcv,
                                                    const CandDev* __restrict__ cands, GroupSoA g, int ngroups_total, int interpolate,
                                                    int xunder, int zunder, GeoRec* __restrict__ recs, size_t rec_stride,
                                                    PairHdr* __restrict__ hdrs, int* __restrict__ tmax, int npairs) {
