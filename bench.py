@@ -7,6 +7,11 @@
 A "step" is one batched evaluation (kiwi_eval_sources) of B candidate bilateral sources: source
 discretisation -> synthesis at all receivers -> scaling -> misfits.  Metric: source evaluations per
 second, whole job over all ranks.  One JSON line is printed by rank 0.
+
+Default workload: c5, the configuration BASELINE.json's metric ("... @1/2/4/8 B200; HBM GB/s") is quoted on -- the dense-array
+sweep of bilateral candidates over 2000 receivers, sharded over the GPUs (configs[4]); it is also the largest configuration
+that fits one GPU.  c3 is the same source and sweep on 200 receivers, c2 the tensor-core moment-tensor grid search, c4 the
+eikonal / amplitude-spectrum case.
 """
 import argparse
 import json
@@ -238,8 +243,9 @@ def workload_config(w, args, batch):
                             "x ned, %s GFDB %dx%dx10, %s, bilinear" % (w["nrcv"], w["db"], w["nx"], w["nz"], w["norm"]),
                 "name": args.workload, "candidates_per_step": batch, "receivers": w["nrcv"], "effective_dt": w["effective_dt"],
                 "cache": "database %s exceeds L2 (no L2 flush needed)" % w["db"]}
-    return {"workload": "C3/C5 bilateral (Izmit, minimizer.f90:1632) ~1e4 sub-sources x %d receivers x ned, %s GFDB %dx%dx10, %s, "
-                        "bilinear, candidates swept in strike/dip/rake/depth/length" % (w["nrcv"], w["db"], w["nx"], w["nz"], w["norm"]),
+    return {"workload": "%s bilateral (Izmit, minimizer.f90:1632) ~1e4 sub-sources x %d receivers x ned, %s GFDB %dx%dx10, %s, "
+                        "bilinear, candidates = lattice points of the strike/dip/rake/depth/length sweep of SURVEY.md 8d"
+                        % ("C5 dense-array sweep:" if w["nrcv"] >= 2000 else "C3", w["nrcv"], w["db"], w["nx"], w["nz"], w["norm"]),
             "name": args.workload, "candidates_per_step": batch, "receivers": w["nrcv"], "effective_dt": w["effective_dt"],
             "cache": "database %s exceeds L2; every candidate streams its own node set (no L2 flush needed)" % w["db"]}
 
@@ -250,7 +256,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="kiwi_b200", choices=["kiwi_b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="candidates per step and per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
