@@ -89,3 +89,42 @@ def test_session_matches_python_binding(tmp_path):
     assert abs(gm - e.get_global_misfit()) <= 1e-6 * gm
     assert abs(gms[1] - gm) <= 1e-6 * gm and gms[0] < 1e-3 * gm       # candidate 0 is the reference itself
     assert mis_off.shape == (8, 2)
+
+
+@pytest.mark.gpu
+def test_session_with_interpolated_database_and_autoshift(tmp_path):
+    """`set_database dbpath nipx nipz`, `shift_ref_seismogram`, `autoshift_ref_seismogram` (minimizer.f90:89-135, 356-386, 447-483)"""
+    from kiwi_b200 import Engine
+    db = sc.small_db_ng8()
+    dbfile = tmp_path / "db.kgf1"
+    db.write(dbfile)
+    lat, lon, dep = sc.small_receivers(3)
+    rfile = tmp_path / "receivers.table"
+    with open(rfile, "w") as f:
+        for a, b, c in zip(lat, lon, dep):
+            f.write("%.10f %.10f %g ned\n" % (a, b, c))
+    p = " ".join("%.9g" % v for v in sc.BILAT_SMALL)
+    base = str(tmp_path / "ref")
+    out = talk(["set_database %s 2 1" % dbfile, "set_local_interpolation bilinear", "set_receivers %s has_depth" % rfile,
+                "set_source_location %g %g 0" % sc.ORIGIN, "set_effective_dt 0.2", "set_source_params bilateral " + p,
+                "output_seismograms %s table synthetics plain" % base, "set_ref_seismograms %s table" % base,
+                "shift_ref_seismogram 2 0.3", "get_global_misfit", "autoshift_ref_seismogram 0 -0.5 0.5", "get_global_misfit",
+                "autoshift_ref_seismogram 9 -0.5 0.5", "shift_ref_seismogram 1"])
+    it = iter(out)
+    for _ in range(9):
+        assert next(it).endswith(": ok"), out
+    assert next(it) == "get_global_misfit: ok >"
+    gm_shifted = float(next(it))
+    assert next(it) == "autoshift_ref_seismogram: ok >"
+    shifts = np.array(next(it).split(), np.float32)
+    assert next(it) == "get_global_misfit: ok >"
+    gm_back = float(next(it))
+    assert next(it) == "autoshift_ref_seismogram: nok >" and next(it) == "receiver index out of range"
+    assert next(it) == "shift_ref_seismogram: nok >" and next(it).startswith("usage: shift_ref_seismogram")
+    assert np.allclose(shifts, [0.0, -0.3, 0.0], atol=1e-6)          # the far-field traces correlate best where they came from
+    assert gm_shifted > 0.1 and gm_back < 1e-4
+    # the interpolated database is the one the binding builds
+    e = Engine(0)
+    e.set_database(db, 2, 1)
+    m = e._db.meta()
+    assert m["nx"] == 2 * db.meta()["nx"] and abs(m["dx"] - db.meta()["dx"] / 2) < 1e-3
