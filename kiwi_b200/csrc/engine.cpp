@@ -323,7 +323,10 @@ int run_misfit_general(kiwi_ctx* c, int method, int xs0, int xs1, int syn_lo, in
                 twh[2 * (size_t)k] = (float)cos(a); twh[2 * (size_t)k + 1] = (float)sin(a);
             }
             CU_OK(c->d_tw.ensure(sizeof(float) * N));
-            CU_OK(cudaMemcpy(c->d_tw.p, twh.data(), sizeof(float) * N, cudaMemcpyHostToDevice));
+            // on the engine's stream and waited for: a plain cudaMemcpy from pageable memory may return before the DMA has landed, and the
+            // non-blocking stream the kernels run on is not ordered against the default stream
+            CU_OK(cudaMemcpyAsync(c->d_tw.p, twh.data(), sizeof(float) * N, cudaMemcpyHostToDevice, c->stream));
+            CU_OK(cudaStreamSynchronize(c->stream));
             c->tw_n = N;
         }
     }
@@ -389,7 +392,8 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
             for (int u = 0; u < nu; u++) memcpy(&up[(size_t)u * nparams], params + (size_t)first_of[u] * nparams, (size_t)nparams * 4);
             std::vector<int> ustatus(nu, 0), ostatus(n, 0);
             CU_OK(c->d_status_out.ensure(sizeof(int) * n));
-            CU_OK(cudaMemset(c->d_status_out.p, 0, sizeof(int) * n));
+            // (on the engine's stream: it is a non-blocking stream, work on the default stream is not ordered against its kernels)
+            CU_OK(cudaMemsetAsync(c->d_status_out.p, 0, sizeof(int) * n, c->stream));
             if (eval_batch(c, sourcetype, nu, nparams, up.data(), d_out, ustatus.data(), true, nullptr, &d)) return 1;
             CU_OK(cudaMemcpy(ostatus.data(), c->d_status_out.p, sizeof(int) * n, cudaMemcpyDeviceToHost));
             if (h_status) for (int i = 0; i < n; i++) h_status[i] = std::max(ostatus[i], ustatus[syn_of[i]]);
@@ -766,6 +770,9 @@ int eval_mt_grid(kiwi_ctx* c, int n, const float* params, float* d_out, int* h_s
 
 int ensure_single(kiwi_ctx* c, bool want_misfits) {
     if (!c->src_set) return kiwi_set_error("no source parameters set");   // minimizer_engine.f90:1394
+    // anything set on the receiver side since the last evaluation (references, tapers, filters, switches, shifts) has not reached the
+    // device yet: evaluate again rather than let a getter work on the receivers of the previous evaluation
+    if (c->receivers_dirty) c->src_dirty = true;
     if (!c->src_dirty && (!want_misfits || !c->src_misfits.empty()) && c->last.valid && c->last.n == 1) return 0;
     if (upload_receivers(c)) return 1;
     const int nm = c->nmisfits;
@@ -897,8 +904,9 @@ int kiwi_set_database(kiwi_ctx* c, kiwi_gfdb* db) {
             CU_OK(cudaStreamSynchronize(c->stream));
         }
     }
-    CU_OK(cudaMemcpy(c->d_nodes.p, c->h_nodes.data(), sizeof(NodeInfo) * nnodes, cudaMemcpyHostToDevice));
-    CU_OK(cudaMemcpy(c->d_tspan.p, c->h_tspan.data(), sizeof(int2) * nnodes * ng, cudaMemcpyHostToDevice));
+    CU_OK(cudaMemcpyAsync(c->d_nodes.p, c->h_nodes.data(), sizeof(NodeInfo) * nnodes, cudaMemcpyHostToDevice, c->stream));
+    CU_OK(cudaMemcpyAsync(c->d_tspan.p, c->h_tspan.data(), sizeof(int2) * nnodes * ng, cudaMemcpyHostToDevice, c->stream));
+    CU_OK(cudaStreamSynchronize(c->stream));
     GfdbDev& d = c->db;
     d.dt = db->dt; d.dx = db->dx; d.dz = db->dz; d.firstx = db->firstx; d.firstz = db->firstz;
     d.nx = db->nx; d.nz = db->nz; d.ng = db->ng;

@@ -182,8 +182,15 @@ static inline bool calculate_seismograms(Engine& e) {
     return true;
 }
 // minimizer_engine.f90:909-921
-static inline void scale_seismograms(Engine& e) {
+// An enabled receiver none of whose centroids found its Green's functions has no displacement strip; the reference then takes
+// strip_span of an unallocated array (undefined).  Reported as a failed evaluation here, as the CUDA engine does.
+static inline bool scale_seismograms(Engine& e) {
+    for (auto& r : e.receivers)
+        if (r.enabled)
+            for (int c = 0; c < r.ncomponents; c++)
+                if (!r.displacement[c].alloc) { e.errstr = "no synthetic seismogram: every centroid is outside the database"; return false; }
     for (auto& r : e.receivers) receiver_scaled_seismograms_to_probes(r, e.psm.risetime, e.psm.moment);
+    return true;
 }
 // minimizer_engine.f90:924-945
 static inline bool calculate_misfits(Engine& e) {
@@ -204,7 +211,7 @@ static inline bool calculate_misfits(Engine& e) {
 static inline int evaluate(Engine& e, int sourcetype, const float* params, int nparams, float* out, int cap) {
     if (!set_source_params(e, sourcetype, params, nparams)) return -1;
     if (!calculate_seismograms(e)) return -1;
-    scale_seismograms(e);
+    if (!scale_seismograms(e)) return -1;
     if (!calculate_misfits(e)) return -1;
     int n = 0;
     for (auto& r : e.receivers) {
@@ -257,7 +264,7 @@ static inline bool set_subparams(Engine& e, const float* sub, bool normalized) {
 // update_misfits of the current source (fresh-state semantics)
 static inline bool update_misfits(Engine& e) {
     if (!calculate_seismograms(e)) return false;
-    scale_seismograms(e);
+    if (!scale_seismograms(e)) return false;
     return calculate_misfits(e);
 }
 static inline bool minimize_lm(Engine& e, int& info, int& iterations_, float& misfit_) {

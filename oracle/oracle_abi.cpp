@@ -123,7 +123,7 @@ int oracle_get_cross_correlations(void* h, int irec, float lo, float hi, float* 
     std::vector<float> params = e.cur_params;
     if (!set_source_params(e, e.cur_type, params.data(), (int)params.size())) return 1;
     if (!calculate_seismograms(e)) return 1;
-    scale_seismograms(e);
+    if (!scale_seismograms(e)) return 1;
     const int r[2] = {f_nint(lo / e.db.dt), f_nint(hi / e.db.dt)};
     Receiver& rc = e.receivers[irec - 1];
     std::vector<float> v;
@@ -220,10 +220,12 @@ int oracle_get_seismogram(void* h, int irec, int icomp, int which, int* first_in
     if (icomp < 1 || icomp > r.ncomponents) return 1;
     if (which == 0) {
         const Strip& s = r.displacement[icomp - 1];
+        if (!s.alloc) { e.errstr = "no synthetic seismogram available"; return 1; }
         *first_index = s.lo; *n = strip_length(s);
         for (int i = 0; i < std::min(*n, cap); i++) buf[i] = s.d[i];
     } else {
         const Probe& p = r.syn_probes[icomp - 1];
+        if (!p.array.alloc) { e.errstr = "no synthetic seismogram available"; return 1; }
         *first_index = p.dataspan[0]; *n = slen(p.dataspan);
         for (int i = 0; i < std::min(*n, cap); i++) buf[i] = p.array.at(p.dataspan[0] + i);
     }
@@ -295,7 +297,7 @@ int oracle_get_ground_motion(void* h, int sourcetype, const float* params, int n
     Engine& e = *(Engine*)h;
     if (!set_source_params(e, sourcetype, params, nparams)) return -1;
     if (!calculate_seismograms(e)) return -1;
-    scale_seismograms(e);
+    if (!scale_seismograms(e)) return -1;
     int n = 0;
     for (auto& r : e.receivers) {
         if (!r.enabled) continue;

