@@ -148,3 +148,92 @@ def test_random_case(seed):
     assert np.all(np.abs(mg[ok] - mw[ok]) <= tolw[ok]), (cfg, stype, float(np.abs((mg[ok] - mw[ok]) / tolw[ok]).max()))
     lim = np.maximum(tol, 2.0 * np.abs(mo - mw))
     assert np.all(np.abs(mg[ok] - mo[ok]) <= lim[ok]), (cfg, stype, float(np.abs((mg[ok] - mo[ok]) / lim[ok]).max()))
+
+
+def random_grid_case(seed):
+    rng = np.random.default_rng(5000 + seed)
+    nr = int(rng.integers(2, 7))
+    lat, lon, dep = sc.small_receivers(nr, seed=int(rng.integers(1, 10 ** 6)), dmin=float(rng.uniform(3e3, 9e3)), dmax=float(rng.uniform(10e3, 16e3)))
+    comps = [ALL_COMPS[int(i)] for i in rng.integers(0, len(ALL_COMPS), nr)]
+    nloc, nmt = int(rng.integers(1, 6)), int(rng.integers(8, 160))
+    mts = rng.normal(0, 1e18, (nmt, 6)).astype(np.float32)
+    if rng.random() < 0.3:
+        mts[int(rng.integers(0, nmt))] = 0.0                 # a zero tensor among the candidates
+    p = np.zeros((nloc, nmt, 11), np.float32)
+    for l in range(nloc):
+        p[l, :, 0] = rng.uniform(-0.3, 0.8); p[l, :, 1] = rng.uniform(-700, 700); p[l, :, 2] = rng.uniform(-700, 700)
+        p[l, :, 3] = rng.uniform(900, 4200); p[l, :, 4:10] = mts; p[l, :, 10] = rng.choice([0.0, 0.3, 0.7, 1.1])
+    p = p.reshape(-1, 11)
+    p = p[rng.permutation(p.shape[0])]
+    if rng.random() < 0.5:
+        p = p[: max(8, int(p.shape[0] * rng.uniform(0.5, 1.0)))]      # ragged: locations with different numbers of tensors
+    cfg = dict(norm=["l2norm", "l1norm"][int(rng.integers(0, 2))], taper=bool(rng.random() < 0.5), factor=float(rng.choice([1.0, 1.0, 0.7])),
+               eff_dt=float(rng.choice([0.2, 0.5])), disable=int(rng.integers(0, nr + 1)), interp=["bilinear", "nearest_neighbor"][int(rng.random() < 0.2)],
+               db=["small_db", "small_db_ng8"][int(rng.random() < 0.25)])
+    return lat, lon, dep, comps, p, cfg
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("KIWI_RANDOM_GRID_CASES", "16"))))
+def test_random_moment_tensor_grid(seed):
+    """point moment-tensor grid searches of random shape through the tcgen05 contraction: against the oracle and the direct path"""
+    from kiwi_b200 import Engine
+    lat, lon, dep, comps, p, cfg = random_grid_case(seed)
+    db = getattr(sc, cfg["db"])()
+    g, o = Engine(0), OracleEngine()
+    for e in (g, o):
+        sc.setup(e, db, lat, lon, dep, comps, interpolation=cfg["interp"], effective_dt=cfg["eff_dt"])
+    o.set_source_params("moment_tensor", sc.MT_SMALL)
+    try:
+        sc.set_refs_from(o, [g, o], [len(c) for c in comps])
+    except Exception:
+        pytest.skip("the reference source leaves the database")
+    for e in (g, o):
+        e.set_misfit_method(cfg["norm"]); e.set_synthetics_factor(cfg["factor"])
+        if cfg["taper"]:
+            for ir in range(1, len(comps) + 1):
+                e.set_misfit_taper(ir, [0.8, 1.5, 4.5, 5.5], [0, 1, 1, 0])
+        if cfg["disable"]:
+            e.switch_receiver(cfg["disable"], False)
+    if g.nmisfits == 0:
+        pytest.skip("all receivers disabled")
+    mg, sg = g.eval_sources("moment_tensor", p)
+    used_grid = g.last_timing()["launches"][3] >= 1
+    g.set_mt_grid(False)
+    md, sd = g.eval_sources("moment_tensor", p)
+    mo, so = o.eval_sources("moment_tensor", p)
+    assert np.array_equal(sg > 0, so > 0) and np.array_equal(sd > 0, so > 0), (sg, sd, so)
+    ok = so == 0
+    tol = RTOL * np.maximum(np.abs(mo), 0.1 * np.abs(mo[..., 1:2]))
+    assert np.all(np.abs(md[ok] - mo[ok]) <= tol[ok]), ("direct", cfg, float(np.abs((md[ok] - mo[ok]) / tol[ok]).max()))
+    assert np.all(np.abs(mg[ok] - mo[ok]) <= tol[ok]), ("grid" if used_grid else "direct (no grid found)", cfg, float(np.abs((mg[ok] - mo[ok]) / tol[ok]).max()))
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("KIWI_RANDOM_SHARE_CASES", "8"))))
+def test_random_shared_syntheses(seed):
+    """batches in which random subsets of candidates differ only in the moment (the batched only_moment_changed shortcut):
+    bit-identical to evaluating every candidate on its own"""
+    from kiwi_b200 import Engine
+    rng = np.random.default_rng(9000 + seed)
+    lat, lon, dep, comps, stype, base, cands, cfg = random_case(int(rng.integers(24, 400)))
+    if stype == "moment_tensor":
+        stype, base = "bilateral", sc.BILAT_SMALL.copy()
+    db = getattr(sc, cfg["db"])()
+    g, o = Engine(0), OracleEngine()
+    for e in (g, o):
+        sc.setup(e, db, lat, lon, dep, comps, interpolation=cfg["interp"], effective_dt=cfg["eff_dt"], under=cfg["under"])
+    o.set_source_params(stype, base)
+    try:
+        sc.set_refs_from(o, [g], [len(c) for c in comps])
+    except Exception:
+        pytest.skip("base source leaves the database")
+    g.set_misfit_method(cfg["norm"] if not cfg["norm"].startswith("floating") else "l2norm")
+    n = int(rng.integers(3, 12))
+    distinct = np.tile(base, (int(rng.integers(1, 4)), 1))
+    for i in range(1, distinct.shape[0]):
+        distinct[i, 5 if stype != "point_lp" else 1] += np.float32(7.0 * i)
+    p = distinct[rng.integers(0, distinct.shape[0], n)].copy()
+    p[:, 4] *= rng.uniform(0.2, 3.0, n).astype(np.float32)
+    shared, s1 = g.eval_sources(stype, p)
+    g.set_share_syntheses(False)
+    single, s2 = g.eval_sources(stype, p)
+    assert np.array_equal(s1, s2) and np.array_equal(shared.view(np.uint32), single.view(np.uint32))
