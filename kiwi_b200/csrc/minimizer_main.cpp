@@ -98,7 +98,8 @@ bool do_command(State& S, const std::string& cmd, const std::vector<std::string>
                                   "set_synthetics_factor", "set_floating_shiftrange", "get_misfits", "get_global_misfit", "get_floating_shifts",
                                   "output_seismograms", "eval_sources", "set_source_params_mask", "set_source_subparams",
                                   "set_source_subparams_limits", "get_source_subparams", "minimize_lm", "get_peak_amplitudes", "get_arias_intensities",
-                                  "shift_ref_seismogram", "autoshift_ref_seismogram"};
+                                  "shift_ref_seismogram", "autoshift_ref_seismogram", "set_misfit_filter_1", "output_cross_correlations",
+                                  "get_cached_traces_memory", "set_cached_traces_memory_limit", "set_verbose", "set_ignore_sigint"};
     bool is_known = false;
     for (const char* k : known) if (cmd == k) is_known = true;
     if (!is_known) return fail("unknown command: " + cmd);   // minimizer.f90:1809-1811
@@ -221,6 +222,36 @@ bool do_command(State& S, const std::string& cmd, const std::vector<std::string>
         for (size_t i = 0; i + 1 < v.size(); i += 2) { x.push_back(v[i]); y.push_back(v[i + 1]); }
         return kiwi_set_misfit_filter(S.ctx, 0, (int)x.size(), x.data(), y.data()) ? cfail() : true;
     }
+    if (cmd == "set_misfit_filter_1") {   // minimizer.f90:922-969: per-receiver filter, 0 = all
+        if (!to_floats(w, 1, &v) || v.size() < 5 || v.size() % 2 != 1) return fail("failed to parse values");
+        std::vector<float> x, y;
+        for (size_t i = 1; i + 1 < v.size(); i += 2) { x.push_back(v[i]); y.push_back(v[i + 1]); }
+        return kiwi_set_misfit_filter(S.ctx, (int)v[0], (int)x.size(), x.data(), y.data()) ? cfail() : true;
+    }
+    if (cmd == "output_cross_correlations") {   // minimizer.f90:1442-1482, minimizer_engine.f90:1283-1306: <base>-<ireceiver>-<component>.table
+        if (!to_floats(w, 2, &v) || v.size() != 2) return fail("usage: output_cross_correlations filenamebase shift-min shift-max");
+        std::vector<float> cc(5 * 8192);
+        for (size_t ir = 0; ir < S.comps.size(); ir++) {
+            int nc = 0, ns = 0;
+            if (kiwi_get_cross_correlations(S.ctx, (int)ir + 1, v[0], v[1], cc.data(), (int)cc.size(), &nc, &ns)) return cfail();
+            const long s0 = lroundf(v[0] / S.dt);
+            for (int ic = 0; ic < nc; ic++) {   // disabled receivers write nothing (receiver.f90:721)
+                const std::string fn = w[1] + "-" + std::to_string(ir + 1) + "-" + S.comps[ir][ic] + ".table";
+                FILE* f = fopen(fn.c_str(), "w");
+                if (!f) return fail("failed to write output file: " + fn);
+                for (int i = 0; i < ns; i++) fprintf(f, "%.9g %.9g\n", (double)(s0 + i) * (double)S.dt, cc[(size_t)ic * ns + i]);   // receiver.f90:731-733
+                fclose(f);
+            }
+        }
+        return true;
+    }
+    if (cmd == "get_cached_traces_memory") {   // minimizer.f90:1484-1508: here the whole database is resident, in HBM
+        long long nsamples = 0;
+        if (S.db) kiwi_gfdb_meta(S.db, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &nsamples);
+        *answer = std::to_string(nsamples * 4);
+        return true;
+    }
+    if (cmd == "set_cached_traces_memory_limit" || cmd == "set_verbose" || cmd == "set_ignore_sigint") return true;   // nothing to steer here
     if (cmd == "set_synthetics_factor") {
         if (!to_floats(w, 1, &v) || v.size() != 1) return fail("usage: set_synthetics_factor factor");
         return kiwi_set_synthetics_factor(S.ctx, v[0]) ? cfail() : true;

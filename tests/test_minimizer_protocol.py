@@ -109,7 +109,9 @@ def test_session_with_interpolated_database_and_autoshift(tmp_path):
                 "set_source_location %g %g 0" % sc.ORIGIN, "set_effective_dt 0.2", "set_source_params bilateral " + p,
                 "output_seismograms %s table synthetics plain" % base, "set_ref_seismograms %s table" % base,
                 "shift_ref_seismogram 2 0.3", "get_global_misfit", "autoshift_ref_seismogram 0 -0.5 0.5", "get_global_misfit",
-                "autoshift_ref_seismogram 9 -0.5 0.5", "shift_ref_seismogram 1"])
+                "autoshift_ref_seismogram 9 -0.5 0.5", "shift_ref_seismogram 1",
+                "output_cross_correlations %s -0.2 0.2" % (base + "cc"), "get_cached_traces_memory", "set_verbose T",
+                "set_misfit_filter_1 2 0.2 0 0.5 1 2.0 1 3.0 0", "get_global_misfit"])
     it = iter(out)
     for _ in range(9):
         assert next(it).endswith(": ok"), out
@@ -121,6 +123,12 @@ def test_session_with_interpolated_database_and_autoshift(tmp_path):
     gm_back = float(next(it))
     assert next(it) == "autoshift_ref_seismogram: nok >" and next(it) == "receiver index out of range"
     assert next(it) == "shift_ref_seismogram: nok >" and next(it).startswith("usage: shift_ref_seismogram")
+    assert next(it) == "output_cross_correlations: ok"
+    assert next(it) == "get_cached_traces_memory: ok >" and int(next(it)) > 4 * db.meta()["nsamples"] * 1.9      # interpolated: twice the traces
+    assert next(it) == "set_verbose: ok" and next(it) == "set_misfit_filter_1: ok"
+    assert next(it) == "get_global_misfit: ok >" and float(next(it)) < 1e-3
+    cc = np.loadtxt(base + "cc-2-e.table")
+    assert cc.shape == (5, 2) and np.allclose(cc[:, 0], [-0.2, -0.1, 0.0, 0.1, 0.2], atol=1e-6) and np.argmax(cc[:, 1]) == 2
     assert np.allclose(shifts, [0.0, -0.3, 0.0], atol=1e-6)          # the far-field traces correlate best where they came from
     assert gm_shifted > 0.1 and gm_back < 1e-4
     # the interpolated database is the one the binding builds
