@@ -67,7 +67,7 @@ def test_gulunay_operator_bit_exact(l1, l2, s1, s2, m1, m2):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("nipx,nipz,ng", [(2, 1, 10), (1, 2, 8), (2, 2, 8), (4, 2, 8), (4, 4, 8)])
+@pytest.mark.parametrize("nipx,nipz,ng", [(2, 1, 10), (1, 2, 8), (2, 2, 8), (4, 2, 8), (4, 4, 8), (8, 1, 8), (1, 4, 8), (16, 1, 8)])
 def test_database_interpolation_against_the_oracle(nipx, nipz, ng):
     db = small_db(36, 5, ng)
     meta, tr = ol.gfdb_interpolate(db, nipx, nipz)
