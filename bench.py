@@ -292,12 +292,13 @@ def main():
     eng = kiwi_b200.Engine(local)
     configure(eng, db, w, rlat, rlon, rdep)
     B = args.batch
-    # candidates are block-partitioned over the ranks; weak scaling: B per GPU
+    # candidates are partitioned over the ranks; weak scaling: B per GPU
     stype, allc, base = candidates(w, max(B * world, 32))
     eng.set_source_params(stype, base)
     set_references(eng, [eng], w["nrcv"], dt)
     nm = eng.nmisfits
-    mine = np.ascontiguousarray(allc[rank * B:(rank + 1) * B])
+    # dealt out in turn (kiwi_b200.sharding.cyclic_partition): the sweep's candidates differ in fault length, i.e. in work
+    mine = np.ascontiguousarray(allc[:B * world][rank::world])
     d_out = torch.empty((B, nm, 2), dtype=torch.float32, device="cuda")
     gathered = torch.empty((world * B, nm, 2), dtype=torch.float32, device="cuda") if world > 1 else None
 

@@ -3,7 +3,7 @@
 The reference parallelises over receivers by running one `minimizer` process per group of receivers
 and merging their text answers (python/tunguska/seismosizer.py:659-673, 785-827).  Here the
 database, receivers and references are replicated in every GPU's HBM and the *candidates* of a
-grid search are block-partitioned over the ranks; the only data that crosses NVLink is the small
+grid search are partitioned over the ranks (contiguous blocks, or dealt out in turn to even out the work); the only data that crosses NVLink is the small
 per-candidate misfit block [ns_local, nmisfits, 2] (+ status), gathered with one all_gather.
 """
 import numpy as np
@@ -20,7 +20,14 @@ def block_partition(n, world):
     return out
 
 
-def eval_sources_sharded(engine, sourcetype, params, group=None, device=None):
+def cyclic_partition(n, world):
+    """index arrays per rank: candidate i goes to rank i mod world.  Grid searches list their candidates with the
+    parameters varying in a fixed nesting, so cost (e.g. fault length -> number of sub-sources) varies slowly along the
+    list; dealing the candidates out in turn evens the work out where contiguous blocks would not."""
+    return [np.arange(r, int(n), int(world)) for r in range(int(world))]
+
+
+def eval_sources_sharded(engine, sourcetype, params, group=None, device=None, partition="block"):
     """Evaluate params[ns, nparams] with the candidates split over the ranks of `group`
     (torch.distributed, NCCL on GPUs / gloo on CPU).  Every rank returns the full
     (misfits[ns, nmisfits, 2], status[ns]).  `engine` is this rank's Engine (one GPU)."""
@@ -33,26 +40,35 @@ def eval_sources_sharded(engine, sourcetype, params, group=None, device=None):
     if not (dist.is_available() and dist.is_initialized()):
         return engine.eval_sources(sourcetype, p)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    parts = block_partition(ns, world)
-    b, e = parts[rank]
+    if partition == "cyclic":
+        idx = cyclic_partition(ns, world)
+    elif partition == "block":
+        idx = [np.arange(pb, pe) for pb, pe in block_partition(ns, world)]
+    else:
+        raise ValueError("partition must be 'block' or 'cyclic'")
+    mine = p[idx[rank]]
+    b, e = 0, mine.shape[0]
     nm = engine.nmisfits
-    width = max(pe - pb for pb, pe in parts)            # all_gather needs equal shapes: pad the short blocks
+    width = max(len(i) for i in idx)                    # all_gather needs equal shapes: pad the short shares
     backend = dist.get_backend(group)
     dev = device if device is not None else ("cuda" if backend == "nccl" else "cpu")
     local = torch.zeros((width, nm * 2 + 1), dtype=torch.float32, device=dev)
     if e > b:
         if dev != "cpu" and hasattr(engine, "eval_sources_device"):
             block = torch.empty((e - b, nm, 2), dtype=torch.float32, device=dev)
-            st = engine.eval_sources_device(sourcetype, p[b:e], block.data_ptr())   # results never leave the GPU
+            st = engine.eval_sources_device(sourcetype, mine, block.data_ptr())   # results never leave the GPU
             local[:e - b, :nm * 2] = block.reshape(e - b, nm * 2)
             local[:e - b, nm * 2] = torch.from_numpy(st.astype(np.float32)).to(dev)
         else:
-            m, st = engine.eval_sources(sourcetype, p[b:e])
+            m, st = engine.eval_sources(sourcetype, mine)
             local[:e - b, :nm * 2] = torch.from_numpy(m.reshape(e - b, nm * 2)).to(dev)
             local[:e - b, nm * 2] = torch.from_numpy(st.astype(np.float32)).to(dev)
     gathered = torch.empty((world * width, nm * 2 + 1), dtype=torch.float32, device=dev)
     dist.all_gather_into_tensor(gathered, local, group=group)
     g = gathered.cpu().numpy().reshape(world, width, nm * 2 + 1)
-    mis = np.concatenate([g[r, :pe - pb, :nm * 2] for r, (pb, pe) in enumerate(parts)], 0).reshape(ns, nm, 2)
-    status = np.concatenate([g[r, :pe - pb, nm * 2] for r, (pb, pe) in enumerate(parts)], 0).astype(np.int32)
-    return mis, status
+    mis = np.zeros((ns, nm * 2), np.float32)
+    status = np.zeros(ns, np.int32)
+    for r, i in enumerate(idx):
+        mis[i] = g[r, :len(i), :nm * 2]
+        status[i] = g[r, :len(i), nm * 2].astype(np.int32)
+    return mis.reshape(ns, nm, 2), status

@@ -23,6 +23,17 @@ def test_block_partition():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_cyclic_partition():
+    from kiwi_b200.sharding import cyclic_partition
+    assert [list(i) for i in cyclic_partition(7, 3)] == [[0, 3, 6], [1, 4], [2, 5]]
+    assert [list(i) for i in cyclic_partition(2, 4)] == [[0], [1], [], []]
+    for n in (0, 1, 9, 64):
+        for w in (1, 2, 8):
+            parts = cyclic_partition(n, w)
+            assert sorted(int(v) for i in parts for v in i) == list(range(n))
+            assert max(len(i) for i in parts) - min(len(i) for i in parts) <= 1
+
+
 def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch.distributed as dist
@@ -38,8 +49,9 @@ def _worker(rank, world, port, q):
     sc.set_refs_from(o, [o], [3, 1, 2])
     p = np.tile(sc.BILAT_SMALL, (5, 1)); p[:, 5] += np.arange(5) * 7.0      # 5 candidates over 2 ranks: blocks of 3 and 2
     mis, st = eval_sources_sharded(o, "bilateral", p)
+    misc, stc = eval_sources_sharded(o, "bilateral", p, partition="cyclic")      # ranks get candidates 0,2,4 and 1,3
     ref, rst = o.eval_sources("bilateral", p)
-    q.put((rank, bool(np.array_equal(mis, ref)), bool(np.array_equal(st, rst)), mis.shape))
+    q.put((rank, bool(np.array_equal(mis, ref) and np.array_equal(misc, ref)), bool(np.array_equal(st, rst) and np.array_equal(stc, rst)), mis.shape))
     dist.barrier()
     dist.destroy_process_group()
 
