@@ -297,8 +297,12 @@ def main():
     eng.set_source_params(stype, base)
     set_references(eng, [eng], w["nrcv"], dt)
     nm = eng.nmisfits
-    # dealt out in turn (kiwi_b200.sharding.cyclic_partition): the sweep's candidates differ in fault length, i.e. in work
-    mine = np.ascontiguousarray(allc[:B * world][rank::world])
+    # equal counts and equal summed fault area per rank (kiwi_b200.sharding.balanced_partition): the sweep's candidates differ in
+    # fault length, i.e. in the number of sub-sources, and the step time is the slowest rank's
+    from kiwi_b200.sharding import balanced_partition
+    pool = allc[:B * world]
+    cost = (pool[:, 9] + pool[:, 10]) * pool[:, 11] if stype == "bilateral" else np.ones(pool.shape[0])
+    mine = np.ascontiguousarray(pool[balanced_partition(cost, world)[rank]])
     d_out = torch.empty((B, nm, 2), dtype=torch.float32, device="cuda")
     gathered = torch.empty((world * B, nm, 2), dtype=torch.float32, device="cuda") if world > 1 else None
 

@@ -27,6 +27,21 @@ def cyclic_partition(n, world):
     return [np.arange(r, int(n), int(world)) for r in range(int(world))]
 
 
+def balanced_partition(costs, world):
+    """index arrays per rank with (nearly) equal counts AND (nearly) equal summed cost: the candidates in order of decreasing
+    cost each go to the rank with the smallest sum so far that still has room (longest-processing-time rule).  `costs`: any
+    per-candidate proxy of the work, e.g. the fault area of a rupture (number of sub-sources)."""
+    costs = np.asarray(costs, dtype=np.float64)
+    n, world = costs.size, int(world)
+    room = [(n + world - 1 - r) // world for r in range(world)]      # sizes differing by at most one
+    total = np.zeros(world)
+    out = [[] for _ in range(world)]
+    for i in np.argsort(-costs, kind="stable"):
+        r = min((r for r in range(world) if len(out[r]) < room[r]), key=lambda r: (total[r], r))
+        out[r].append(int(i)); total[r] += costs[i]
+    return [np.array(sorted(o), dtype=np.int64) for o in out]
+
+
 def eval_sources_sharded(engine, sourcetype, params, group=None, device=None, partition="block"):
     """Evaluate params[ns, nparams] with the candidates split over the ranks of `group`
     (torch.distributed, NCCL on GPUs / gloo on CPU).  Every rank returns the full
@@ -40,12 +55,16 @@ def eval_sources_sharded(engine, sourcetype, params, group=None, device=None, pa
     if not (dist.is_available() and dist.is_initialized()):
         return engine.eval_sources(sourcetype, p)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    if partition == "cyclic":
+    if not isinstance(partition, str):      # explicit shares, e.g. from balanced_partition
+        idx = [np.asarray(i, dtype=np.int64) for i in partition]
+        if len(idx) != world or sorted(int(v) for i in idx for v in i) != list(range(ns)):
+            raise ValueError("partition must give every candidate to exactly one of the %d ranks" % world)
+    elif partition == "cyclic":
         idx = cyclic_partition(ns, world)
     elif partition == "block":
         idx = [np.arange(pb, pe) for pb, pe in block_partition(ns, world)]
     else:
-        raise ValueError("partition must be 'block' or 'cyclic'")
+        raise ValueError("partition must be 'block', 'cyclic' or a list of index arrays")
     mine = p[idx[rank]]
     b, e = 0, mine.shape[0]
     nm = engine.nmisfits

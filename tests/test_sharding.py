@@ -34,6 +34,24 @@ def test_cyclic_partition():
             assert max(len(i) for i in parts) - min(len(i) for i in parts) <= 1
 
 
+def test_balanced_partition():
+    from kiwi_b200.sharding import balanced_partition
+    # a sweep whose fastest parameter alternates between a cheap and an expensive value: dealing out in turn would give
+    # one of two ranks all the expensive ones
+    costs = np.tile([30.0, 50.0], 8)
+    parts = balanced_partition(costs, 2)
+    assert [len(i) for i in parts] == [8, 8] and [float(costs[i].sum()) for i in parts] == [320.0, 320.0]
+    rng = np.random.default_rng(1)
+    for n, w in ((64, 8), (7, 3), (5, 8), (0, 2)):
+        c = rng.uniform(1.0, 2.0, n)
+        parts = balanced_partition(c, w)
+        assert sorted(int(v) for i in parts for v in i) == list(range(n))
+        assert max(len(i) for i in parts) - min(len(i) for i in parts) <= 1
+        if n == 64:
+            sums = [c[i].sum() for i in parts]
+            assert max(sums) / min(sums) < 1.02
+
+
 def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch.distributed as dist
@@ -50,6 +68,8 @@ def _worker(rank, world, port, q):
     p = np.tile(sc.BILAT_SMALL, (5, 1)); p[:, 5] += np.arange(5) * 7.0      # 5 candidates over 2 ranks: blocks of 3 and 2
     mis, st = eval_sources_sharded(o, "bilateral", p)
     misc, stc = eval_sources_sharded(o, "bilateral", p, partition="cyclic")      # ranks get candidates 0,2,4 and 1,3
+    misb, stb = eval_sources_sharded(o, "bilateral", p, partition=[[4, 0], [1, 2, 3]])
+    assert np.array_equal(misb, misc) and np.array_equal(stb, stc)
     ref, rst = o.eval_sources("bilateral", p)
     q.put((rank, bool(np.array_equal(mis, ref) and np.array_equal(misc, ref)), bool(np.array_equal(st, rst) and np.array_equal(stc, rst)), mis.shape))
     dist.barrier()
