@@ -252,6 +252,15 @@ int kiwi_get_floating_shifts(kiwi_ctx* ctx, int* shifts, int cap, int* n);      
 int kiwi_get_seismogram(kiwi_ctx* ctx, int ireceiver, int icomponent, int which, int* first_index, int* n,
                         float* buf, int cap);
 
+/* get_distances (minimizer_engine.f90:1260-1281; command output_distances): distance [m] and azimuth [rad] of every receiver */
+int kiwi_get_distances(kiwi_ctx* ctx, double* distances, double* azimuths, int cap, int* n);
+/* get_source_crustal_thickness (minimizer_engine.f90:488-498): crust2x2 thickness [m] under the source location, limited by
+ * set_source_crustal_thickness_limit */
+int kiwi_get_source_crustal_thickness(kiwi_ctx* ctx, float* thickness);
+/* get_principal_axes (minimizer_engine.f90:1248-1258): (azimuth, polar angle) in degrees of the p- and the t-axis of the source set by
+ * kiwi_set_source_params (bilateral, circular, eikonal; zeros for the source types without a slip direction) */
+int kiwi_get_principal_axes(kiwi_ctx* ctx, float* pax2, float* tax2);
+
 /* ---- inspection entry points used by the parity tests (bit-exact integer contract) ---------- */
 /* discretise one source on the device; table: [cap][10] floats north east depth time m(6) in the
  * reference's centroid order (discrete_source.f90:27-30); grid3: nx,ny,nt.  Returns through

@@ -73,6 +73,9 @@ SIGNATURES = {
     "kiwi_shift_ref_seismogram": (C.c_int, [C.c_void_p, C.c_int, C.c_float]),
     "kiwi_get_cross_correlations": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float, c_float_p, C.c_int, c_int_p, c_int_p]),
     "kiwi_autoshift_ref_seismogram": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float, c_float_p, C.c_int, c_int_p]),
+    "kiwi_get_distances": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int, c_int_p]),
+    "kiwi_get_source_crustal_thickness": (C.c_int, [C.c_void_p, c_float_p]),
+    "kiwi_get_principal_axes": (C.c_int, [C.c_void_p, c_float_p, c_float_p]),
     "kiwi_get_seismogram": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_float_p, C.c_int]),
     "kiwi_discretize_source": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, c_float_p, C.c_int, c_int_p, c_int_p]),
     "kiwi_get_indices": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_int_p, c_int_p, c_float_p, c_float_p, c_int_p, C.c_int, c_int_p]),

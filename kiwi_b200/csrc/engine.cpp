@@ -1549,6 +1549,46 @@ int kiwi_get_cross_correlations(kiwi_ctx* c, int ireceiver, float shift_lo, floa
     return 0;
 }
 
+// get_distances (minimizer_engine.f90:1260-1281): epicentral distance [m] and azimuth [rad] of every receiver, in double
+int kiwi_get_distances(kiwi_ctx* c, double* distances, double* azimuths, int cap, int* n) {
+    if (!c) return kiwi_set_error("null context");
+    if (!c->loc_set) return kiwi_set_error("no source location set");
+    if (require_receivers(c)) return 1;
+    const int nr = (int)c->rcv.size();
+    for (int i = 0; i < nr && i < cap; i++) {
+        double azi, bazi;
+        kh::azibazi(c->olat, c->olon, c->rcv[i].lat, c->rcv[i].lon, &azi, &bazi);
+        if (azimuths) azimuths[i] = azi;
+        if (distances) distances[i] = kh::distance_accurate50m(c->olat, c->olon, c->rcv[i].lat, c->rcv[i].lon);
+    }
+    if (n) *n = nr;
+    return 0;
+}
+
+// get_source_crustal_thickness (minimizer_engine.f90:488-498, parameterized_source.f90:207-221)
+int kiwi_get_source_crustal_thickness(kiwi_ctx* c, float* thickness) {
+    if (!c) return kiwi_set_error("null context");
+    if (!c->loc_set) return kiwi_set_error("no source location set");
+    if (!c->crust.loaded) return kiwi_set_error("crust2x2 model not loaded");
+    std::vector<kh::Halfspace> hs;
+    kh::default_constraints(c->crust, c->olat, c->olon, c->thickness_limit, &hs);   // the second half-space sits at that depth
+    *thickness = hs[1].point[2];
+    return 0;
+}
+
+// get_principal_axes (minimizer_engine.f90:1248-1258): p- and t-axis (azimuth, polar angle; degrees) of the source set by
+// kiwi_set_source_params.  Only the sources with a slip direction have them (bilateral, circular, eikonal); the others answer zeros,
+// as psm%pax / psm%tax are never set for them.
+int kiwi_get_principal_axes(kiwi_ctx* c, float* pax2, float* tax2) {
+    if (!c) return kiwi_set_error("null context");
+    if (!c->src_set) return kiwi_set_error("no source parameters set");
+    pax2[0] = pax2[1] = tax2[0] = tax2[1] = 0.f;
+    const int t = c->src_type;
+    if (t == KIWI_SOURCE_BILATERAL || t == KIWI_SOURCE_CIRCULAR || t == KIWI_SOURCE_EIKONAL)
+        kh::principal_axes(c->src_params[5], c->src_params[6], c->src_params[7], pax2, tax2);
+    return 0;
+}
+
 int kiwi_get_seismogram(kiwi_ctx* c, int ireceiver, int icomponent, int which, int* first_index, int* n, float* buf, int cap) {
     if (!c) return kiwi_set_error("null context");
     CU_OK(cudaSetDevice(c->device));

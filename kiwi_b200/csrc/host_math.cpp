@@ -334,4 +334,34 @@ bool prep_point_lp(const float* p, float shortest_doi, SourcePrep* out) {
     return true;
 }
 
+
+// source_bilat.f90:565-594
+static void polar3(const float xyz[3], float pol[3]) {
+    pol[0] = sqrtf(xyz[0] * xyz[0] + xyz[1] * xyz[1] + xyz[2] * xyz[2]);
+    pol[1] = atan2f(xyz[1], xyz[0]);
+    pol[2] = acosf(xyz[2] / pol[0]);
+}
+static float wrap_r(float x, float mi, float ma) { return x - floorf((x - mi) / (ma - mi)) * (ma - mi); }
+static void domeshot3(const float pol[3], float out[3]) {
+    const float pi = 3.14159265358979f;
+    out[0] = pol[0];
+    out[1] = wrap_r(pol[1], pi, -pi); out[2] = wrap_r(pol[2], pi, -pi);
+    if (out[2] > pi / 2.f) { out[1] = wrap_r(out[1] + pi, -pi, pi); out[2] = pi - out[2]; }
+}
+void principal_axes(float strike_deg, float dip_deg, float rake_deg, float pax[2], float tax[2]) {
+    const float pi = 3.14159265358979f;
+    float rot[9];
+    init_euler(d2r_r(dip_deg), d2r_r(strike_deg), -d2r_r(rake_deg), rot);
+    const float r2 = sqrtf(2.f);
+    const float vp[3] = {r2, 0.f, -r2}, vt[3] = {-r2, 0.f, -r2};
+    for (int which = 0; which < 2; which++) {
+        const float* v = which == 0 ? vp : vt;
+        float x[3], pol[3], ds[3];
+        for (int i = 0; i < 3; i++) { float a = 0.f; for (int j = 0; j < 3; j++) a = a + rot[i * 3 + j] * v[j]; x[i] = a; }
+        polar3(x, pol); domeshot3(pol, ds);
+        float* out = which == 0 ? pax : tax;
+        out[0] = 360.f / 2.f / pi * ds[1]; out[1] = 360.f / 2.f / pi * ds[2];   // r2d
+    }
+}
+
 }  // namespace kh

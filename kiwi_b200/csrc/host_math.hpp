@@ -12,6 +12,9 @@ void azibazi(double alat, double alon, double blat, double blon, double* azi, do
 double distance_accurate50m(double alat, double alon, double blat, double blon);
 void final_rotation(double bazi0, float* cl0, float* sl0);
 void init_euler(float alpha, float beta, float gamma, float* mat9);
+// p- and t-axis (azimuth, polar angle in degrees) of a shear source (source_bilat.f90:232-237 and the same lines of the circular and
+// eikonal sources; polar / domeshot / wrap :565-594)
+void principal_axes(float strike_deg, float dip_deg, float rake_deg, float pax[2], float tax[2]);
 void plf_integrate_and_centroid(const float* px, const float* py, int n, float a, float b, float* area, float* centroid);
 void taper_table(const std::vector<float>& x, const std::vector<float>& y, float dt, int* tp0, int* tp1, std::vector<float>* tab);
 void discrete_plf_span(const std::vector<float>& x, float dt, int* s0, int* s1);

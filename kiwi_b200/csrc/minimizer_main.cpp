@@ -99,7 +99,8 @@ bool do_command(State& S, const std::string& cmd, const std::vector<std::string>
                                   "output_seismograms", "eval_sources", "set_source_params_mask", "set_source_subparams",
                                   "set_source_subparams_limits", "get_source_subparams", "minimize_lm", "get_peak_amplitudes", "get_arias_intensities",
                                   "shift_ref_seismogram", "autoshift_ref_seismogram", "set_misfit_filter_1", "output_cross_correlations",
-                                  "get_cached_traces_memory", "set_cached_traces_memory_limit", "set_verbose", "set_ignore_sigint"};
+                                  "get_cached_traces_memory", "set_cached_traces_memory_limit", "set_verbose", "set_ignore_sigint",
+                                  "get_principal_axes", "get_source_crustal_thickness", "output_distances"};
     bool is_known = false;
     for (const char* k : known) if (cmd == k) is_known = true;
     if (!is_known) return fail("unknown command: " + cmd);   // minimizer.f90:1809-1811
@@ -243,6 +244,31 @@ bool do_command(State& S, const std::string& cmd, const std::vector<std::string>
                 fclose(f);
             }
         }
+        return true;
+    }
+    if (cmd == "get_principal_axes") {   // minimizer.f90:1374-1402: pax(1) pax(2) tax(1) tax(2)
+        float pax[2], tax[2];
+        if (kiwi_get_principal_axes(S.ctx, pax, tax)) return cfail();
+        const float v4[4] = {pax[0], pax[1], tax[0], tax[1]};
+        *answer = fmt_floats(v4, 4);
+        return true;
+    }
+    if (cmd == "get_source_crustal_thickness") {   // minimizer.f90 do_get_source_crustal_thickness
+        float t = 0.f;
+        if (kiwi_get_source_crustal_thickness(S.ctx, &t)) return cfail();
+        *answer = fmt_floats(&t, 1);
+        return true;
+    }
+    if (cmd == "output_distances") {   // minimizer.f90:1404-1440: distance [deg], distance [m], azimuth [deg] per receiver
+        if (w.size() != 2) return fail("usage: output_distances filename");
+        std::vector<double> d(S.comps.size() + 1), a(S.comps.size() + 1);
+        int n = 0;
+        if (kiwi_get_distances(S.ctx, d.data(), a.data(), (int)d.size(), &n)) return cfail();
+        FILE* f = fopen(w[1].c_str(), "w");
+        if (!f) return fail("failed to open file for output: " + w[1]);
+        const double r2d = (double)(360.f / 2.f / 3.14159265358979f), earthradius = (double)(6371.f * 1000.f);   // orthodrome.f90:343-350, constants.f90:24
+        for (int i = 0; i < n; i++) fprintf(f, "%.17g %.17g %.17g\n", r2d * (d[i] / earthradius), d[i], r2d * a[i]);
+        fclose(f);
         return true;
     }
     if (cmd == "get_cached_traces_memory") {   // minimizer.f90:1484-1508: here the whole database is resident, in HBM

@@ -431,6 +431,25 @@ class Engine:
         _check(lib.kiwi_get_cross_correlations(self._h, ireceiver, shift_lo, shift_hi, out.ctypes.data_as(c_float_p), out.size, nc, ns))
         return out[:nc.value * ns.value].reshape(nc.value, ns.value).copy()
 
+    def get_distances(self):
+        """get_distances (minimizer_engine.f90:1260-1281): (distances [m], azimuths [rad]) of all receivers."""
+        nr = getattr(self, "_nreceivers", 4096)
+        d, a = np.zeros(nr), np.zeros(nr)
+        n = C.c_int()
+        _check(lib.kiwi_get_distances(self._h, d.ctypes.data_as(c_double_p), a.ctypes.data_as(c_double_p), nr, n))
+        return d[:n.value], a[:n.value]
+
+    def get_source_crustal_thickness(self):
+        t = C.c_float()
+        _check(lib.kiwi_get_source_crustal_thickness(self._h, t))
+        return t.value
+
+    def get_principal_axes(self):
+        """(pax, tax), each (azimuth, polar angle) in degrees."""
+        p, t = np.zeros(2, np.float32), np.zeros(2, np.float32)
+        _check(lib.kiwi_get_principal_axes(self._h, _fp(p), _fp(t)))
+        return p, t
+
     def get_seismogram(self, ireceiver, icomponent, which=0):
         """In-memory replacement of output_seismograms: (first_index, samples)."""
         first, n = C.c_int(), C.c_int()

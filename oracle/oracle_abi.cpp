@@ -163,6 +163,44 @@ int oracle_gulunay(float* a, int t, int s1, int s2, int l1, int l2, float* out, 
     for (size_t i = 0; i < I.size(); i++) out[i] = I[i];
     return 0;
 }
+// get_distances (minimizer_engine.f90:1260-1281)
+int oracle_get_distances(void* h, double* distances, double* azimuths) {
+    Engine& e = *(Engine*)h;
+    for (size_t i = 0; i < e.receivers.size(); i++) {
+        azimuths[i] = azimuth(e.psm.origin, e.receivers[i].origin);
+        distances[i] = distance_accurate50m(e.psm.origin, e.receivers[i].origin);
+    }
+    return (int)e.receivers.size();
+}
+// psm_get_crustal_thickness (parameterized_source.f90:207-221)
+int oracle_get_source_crustal_thickness(void* h, float* thickness) {
+    Engine& e = *(Engine*)h;
+    if (!e.crust.loaded) { e.errstr = "crust2x2 model not loaded"; return 1; }
+    Crust1dProfile profile = crust2x2_get_profile(e.crust, r2d_tgc(e.psme.origin));
+    float vp, vs, vrho;
+    crust2x2_get_profile_averages(profile, vp, vs, vrho, *thickness);
+    if (e.psme.crustal_thickness_limit > 0) *thickness = std::min(e.psme.crustal_thickness_limit, *thickness);
+    return 0;
+}
+// p- and t-axis of a shear source: source_bilat.f90:232-237 with polar / domeshot / wrap (:565-594)
+static inline float wrap_f(float x, float mi, float ma) { return x - std::floor((x - mi) / (ma - mi)) * (ma - mi); }
+int oracle_principal_axes(float strike_deg, float dip_deg, float rake_deg, float* pax, float* tax) {
+    float rot[3][3];
+    init_euler(d2r_r(dip_deg), d2r_r(strike_deg), -d2r_r(rake_deg), rot);
+    const float sq = std::sqrt(2.f);
+    for (int which = 0; which < 2; which++) {
+        const float v[3] = {which == 0 ? sq : -sq, 0.f, -sq};
+        float x[3];
+        for (int i = 0; i < 3; i++) { float a = 0.f; for (int j = 0; j < 3; j++) a = a + rot[i][j] * v[j]; x[i] = a; }
+        float pol[3] = {std::sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]), std::atan2(x[1], x[0]), 0.f};
+        pol[2] = std::acos(x[2] / pol[0]);
+        float d[3] = {pol[0], wrap_f(pol[1], pi, -pi), wrap_f(pol[2], pi, -pi)};
+        if (d[2] > pi / 2.f) { d[1] = wrap_f(d[1] + pi, -pi, pi); d[2] = pi - d[2]; }
+        float* out = which == 0 ? pax : tax;
+        out[0] = r2d_r(d[1]); out[1] = r2d_r(d[2]);
+    }
+    return 0;
+}
 int oracle_set_crust2x2(void* h, const char* path) {
     Engine& e = *(Engine*)h;
     if (!crust2x2_load(path, e.crust)) { e.errstr = "can't load crust2x2 table"; return 1; }

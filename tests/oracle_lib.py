@@ -38,7 +38,8 @@ def lib(wide=False):
                      "oracle_receiver_geometry", "oracle_trace_span", "oracle_time_eval", "oracle_get_strip_spans",
                      "oracle_set_source_params_mask", "oracle_set_source_subparams", "oracle_set_source_subparams_limits",
                      "oracle_get_source_subparams", "oracle_minimize_lm", "oracle_lmdif", "oracle_get_ground_motion",
-                     "oracle_shift_ref_seismogram", "oracle_autoshift_ref_seismogram", "oracle_get_cross_correlations"):
+                     "oracle_shift_ref_seismogram", "oracle_autoshift_ref_seismogram", "oracle_get_cross_correlations",
+                     "oracle_get_distances", "oracle_get_source_crustal_thickness", "oracle_principal_axes"):
             if hasattr(L, name):
                 getattr(L, name).argtypes = None
         _libs[wide] = L
@@ -241,6 +242,21 @@ class OracleEngine:
         nc, ns = C.c_int(), C.c_int()
         self._check(self.L.oracle_get_cross_correlations(self.h, C.c_int(irec), C.c_float(lo), C.c_float(hi), out.ctypes.data_as(fp), C.byref(nc), C.byref(ns)))
         return out[:nc.value * ns.value].reshape(nc.value, ns.value).copy()
+
+    def get_distances(self):
+        d, a = np.zeros(4096), np.zeros(4096)
+        n = self.L.oracle_get_distances(self.h, d.ctypes.data_as(dp), a.ctypes.data_as(dp))
+        return d[:n], a[:n]
+
+    def get_source_crustal_thickness(self):
+        t = C.c_float()
+        self._check(self.L.oracle_get_source_crustal_thickness(self.h, C.byref(t)))
+        return t.value
+
+    def principal_axes(self, strike, dip, rake):
+        p, t = np.zeros(2, np.float32), np.zeros(2, np.float32)
+        self.L.oracle_principal_axes(C.c_float(strike), C.c_float(dip), C.c_float(rake), p.ctypes.data_as(fp), t.ctypes.data_as(fp))
+        return p, t
 
     def get_seismogram(self, irec, icomp, which=0):
         first, n = C.c_int(), C.c_int()

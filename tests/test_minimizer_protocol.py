@@ -111,7 +111,8 @@ def test_session_with_interpolated_database_and_autoshift(tmp_path):
                 "shift_ref_seismogram 2 0.3", "get_global_misfit", "autoshift_ref_seismogram 0 -0.5 0.5", "get_global_misfit",
                 "autoshift_ref_seismogram 9 -0.5 0.5", "shift_ref_seismogram 1",
                 "output_cross_correlations %s -0.2 0.2" % (base + "cc"), "get_cached_traces_memory", "set_verbose T",
-                "set_misfit_filter_1 2 0.2 0 0.5 1 2.0 1 3.0 0", "get_global_misfit"])
+                "set_misfit_filter_1 2 0.2 0 0.5 1 2.0 1 3.0 0", "get_global_misfit", "get_principal_axes",
+                "output_distances %s" % (base + ".distances")])
     it = iter(out)
     for _ in range(9):
         assert next(it).endswith(": ok"), out
@@ -127,6 +128,10 @@ def test_session_with_interpolated_database_and_autoshift(tmp_path):
     assert next(it) == "get_cached_traces_memory: ok >" and int(next(it)) > 4 * db.meta()["nsamples"] * 1.9      # interpolated: twice the traces
     assert next(it) == "set_verbose: ok" and next(it) == "set_misfit_filter_1: ok"
     assert next(it) == "get_global_misfit: ok >" and float(next(it)) < 1e-3
+    assert next(it) == "get_principal_axes: ok >" and len(next(it).split()) == 4
+    assert next(it) == "output_distances: ok"
+    dist = np.loadtxt(base + ".distances")
+    assert dist.shape == (3, 3) and np.all((dist[:, 1] > 7e3) & (dist[:, 1] < 15e3)) and np.allclose(dist[:, 0], dist[:, 1] / 6371e3 * 180 / np.pi, rtol=1e-6)
     cc = np.loadtxt(base + "cc-2-e.table")
     assert cc.shape == (5, 2) and np.allclose(cc[:, 0], [-0.2, -0.1, 0.0, 0.1, 0.2], atol=1e-6) and np.argmax(cc[:, 1]) == 2
     assert np.allclose(shifts, [0.0, -0.3, 0.0], atol=1e-6)          # the far-field traces correlate best where they came from

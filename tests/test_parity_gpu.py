@@ -361,6 +361,27 @@ def test_cross_correlations(taper, filt):
         assert np.all(np.abs(cg - co) <= (4 if filt else 1) * RTOL * scale), (ir, (np.abs(cg - co) / scale).max())
 
 
+def test_distances_crustal_thickness_and_principal_axes():
+    """get_distances (minimizer_engine.f90:1260-1281), get_source_crustal_thickness (:488-498), get_principal_axes (:1248-1258): host
+    arithmetic of the reference, exact against the restatement"""
+    g, o = engines(sc.small_db(), COMPS6)
+    dg, ag = g.get_distances()
+    do, ao = o.get_distances()
+    assert dg.size == 6 and np.array_equal(dg, do) and np.array_equal(ag, ao)
+    assert g.get_source_crustal_thickness() == o.get_source_crustal_thickness() > 5000.0
+    for e in (g, o):
+        e.set_source_crustal_thickness_limit(12345.0)
+    assert g.get_source_crustal_thickness() == o.get_source_crustal_thickness() == 12345.0
+    for stype, p in (("bilateral", sc.BILAT_SMALL), ("circular", CIRC), ("eikonal", EIK)):
+        g.set_source_params(stype, p)
+        pg, tg = g.get_principal_axes()
+        po, to = o.principal_axes(float(p[5]), float(p[6]), float(p[7]))
+        assert np.array_equal(pg, po) and np.array_equal(tg, to) and np.all(np.abs(pg) <= 180.0)
+    g.set_source_params("moment_tensor", sc.MT_SMALL)
+    pg, tg = g.get_principal_axes()
+    assert not pg.any() and not tg.any()
+
+
 def _mt_grid(nloc=3, nmt=45):
     from kiwi_b200 import synthetic
     mts = synthetic.fibonacci_moment_tensors(nmt) * 1e18
