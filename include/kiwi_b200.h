@@ -261,6 +261,13 @@ int kiwi_get_source_crustal_thickness(kiwi_ctx* ctx, float* thickness);
  * kiwi_set_source_params (bilateral, circular, eikonal; zeros for the source types without a slip direction) */
 int kiwi_get_principal_axes(kiwi_ctx* ctx, float* pax2, float* tax2);
 
+/* In-memory replacements of output_seismograms in all its variants (minimizer_engine.f90:947-1012; probe_get comparator.f90:356-433) and of
+ * output_seismogram_spectra (:1014-1067; probe_get_amp_spectrum comparator.f90:332-354) for the source set by kiwi_set_source_params:
+ * which_probe 0 synthetics / 1 references; which_processing 0 plain / 1 tapered / 2 filtered.  The probes carry the spans of a fresh
+ * process (no misfit has been evaluated before).  Trace: first_index = sample index of buf[0]; spectrum: n amplitudes at k * df. */
+int kiwi_get_probe(kiwi_ctx* ctx, int ireceiver, int icomponent, int which_probe, int which_processing, int* first_index, int* n, float* buf, int cap);
+int kiwi_get_probe_spectrum(kiwi_ctx* ctx, int ireceiver, int icomponent, int which_probe, int which_processing, float* df, int* n, float* buf, int cap);
+
 /* ---- inspection entry points used by the parity tests (bit-exact integer contract) ---------- */
 /* discretise one source on the device; table: [cap][10] floats north east depth time m(6) in the
  * reference's centroid order (discrete_source.f90:27-30); grid3: nx,ny,nt.  Returns through

@@ -76,6 +76,8 @@ SIGNATURES = {
     "kiwi_get_distances": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int, c_int_p]),
     "kiwi_get_source_crustal_thickness": (C.c_int, [C.c_void_p, c_float_p]),
     "kiwi_get_principal_axes": (C.c_int, [C.c_void_p, c_float_p, c_float_p]),
+    "kiwi_get_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_float_p, C.c_int]),
+    "kiwi_get_probe_spectrum": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p, c_int_p, c_float_p, C.c_int]),
     "kiwi_get_seismogram": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_float_p, C.c_int]),
     "kiwi_discretize_source": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, c_float_p, C.c_int, c_int_p, c_int_p]),
     "kiwi_get_indices": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_int_p, c_int_p, c_float_p, c_float_p, c_int_p, C.c_int, c_int_p]),

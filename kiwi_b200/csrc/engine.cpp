@@ -284,6 +284,24 @@ struct Dedup {
     std::vector<float> moment;    // [n_out]: its moment
 };
 
+// twiddle table of the shared-memory FFTs: exp(-2 pi i k / 32768), rounded from double as an fp32 FFT library tabulates them
+int ensure_twiddles(kiwi_ctx* c) {
+    if (c->tw_n != 0) return 0;
+    const int N = 32768;
+    std::vector<float> twh((size_t)N);
+    for (int k = 0; k < N / 2; k++) {
+        const double a = -2.0 * M_PI * (double)k / (double)N;
+        twh[2 * (size_t)k] = (float)cos(a); twh[2 * (size_t)k + 1] = (float)sin(a);
+    }
+    CU_OK(c->d_tw.ensure(sizeof(float) * N));
+    // on the engine's stream and waited for: a plain cudaMemcpy from pageable memory may return before the DMA has landed, and the
+    // non-blocking stream the kernels run on is not ordered against the default stream
+    CU_OK(cudaMemcpyAsync(c->d_tw.p, twh.data(), sizeof(float) * N, cudaMemcpyHostToDevice, c->stream));
+    CU_OK(cudaStreamSynchronize(c->stream));
+    c->tw_n = N;
+    return 0;
+}
+
 // k_misfit_general on nslots (candidate, receiver-set) slots: sizes the shared-memory FFT from the bound of the padded probe span
 // (comparator.f90:1092-1109) over the chunk -- union of all synthetic and (shifted) reference spans, at least twice the longest data
 // span, next power of two.  method = KIWI_INTERNAL_XCORR: cross-correlation over the shifts xs0..xs1 (autoshift_ref_seismogram).
@@ -315,20 +333,7 @@ int run_misfit_general(kiwi_ctx* c, int method, int xs0, int xs1, int syn_lo, in
         while (n_alloc < want) n_alloc <<= 1;
         n_alloc <<= 1;   // head room for re-centred unions
         if (n_alloc > 16384) n_alloc = 16384;   // 128 KiB of shared memory; longer spans are flagged per candidate
-        if (c->tw_n == 0) {   // twiddles rounded from double, as an fp32 FFT library tabulates them
-            const int N = 32768;
-            std::vector<float> twh((size_t)N);
-            for (int k = 0; k < N / 2; k++) {
-                const double a = -2.0 * M_PI * (double)k / (double)N;
-                twh[2 * (size_t)k] = (float)cos(a); twh[2 * (size_t)k + 1] = (float)sin(a);
-            }
-            CU_OK(c->d_tw.ensure(sizeof(float) * N));
-            // on the engine's stream and waited for: a plain cudaMemcpy from pageable memory may return before the DMA has landed, and the
-            // non-blocking stream the kernels run on is not ordered against the default stream
-            CU_OK(cudaMemcpyAsync(c->d_tw.p, twh.data(), sizeof(float) * N, cudaMemcpyHostToDevice, c->stream));
-            CU_OK(cudaStreamSynchronize(c->stream));
-            c->tw_n = N;
-        }
+        if (ensure_twiddles(c)) return 1;
     }
     if (misfit_general_smem_bytes(n_alloc, nshift) > (size_t)200 * 1024) return kiwi_set_error("floating shift range too large");
     cudaError_t e = launch_misfit_general(c->d_rcv.as<ReceiverDev>(), nrcv, d_cands, nslots, c->d_seis.as<float>(), seis_stride, d_shdrs,
@@ -1547,6 +1552,54 @@ int kiwi_get_cross_correlations(kiwi_ctx* c, int ireceiver, float shift_lo, floa
     if (ncomp) *ncomp = nc;
     if (nshift) *nshift = ns;
     return 0;
+}
+
+namespace {
+int export_probe(kiwi_ctx* c, int ireceiver, int icomponent, int which_probe, int which_processing, int spectrum, int* first_index, int* n, float* df,
+                 float* buf, int cap) {
+    if (!c) return kiwi_set_error("null context");
+    CU_OK(cudaSetDevice(c->device));
+    if (which_probe != 0 && which_probe != 1) return kiwi_set_error("unknown probe: use 0 (synthetics) or 1 (references)");
+    if (which_processing < 0 || which_processing > 2) return kiwi_set_error("unknown processing: use 0 (plain), 1 (tapered) or 2 (filtered)");
+    if (ensure_single(c, false)) return 1;   // update_syn_probes
+    const int nrcv = (int)c->rcv.size();
+    if (ireceiver < 1 || ireceiver > nrcv) return kiwi_set_error("receiver index out of range");
+    const HostReceiver& h = c->rcv[ireceiver - 1];
+    if (icomponent < 1 || icomponent > h.ncomp) return kiwi_set_error("component index out of range");
+    if (which_probe == 1 && !h.has_ref[icomponent - 1]) return kiwi_set_error("no reference seismograms set");
+    if (which_probe == 0 && !c->last.seis_valid) return kiwi_set_error("no synthetic seismogram available");
+    if (ensure_twiddles(c)) return 1;
+    const int n_alloc = 16384;   // 128 KiB of shared memory
+    CU_OK(c->d_xcorr.ensure(sizeof(float) * (size_t)n_alloc));
+    CU_OK(c->d_fshift.ensure(sizeof(int) * 4));
+    cudaError_t e = launch_probe_export(c->d_rcv.as<ReceiverDev>(), ireceiver - 1, icomponent - 1, c->d_cands.as<CandDev>(), c->d_seis.as<float>(),
+                                        c->last.seis_stride, c->d_shdrs.as<SeisHdr>(), nrcv, c->d_refdata.as<float>(), c->d_taper.as<float>(),
+                                        (const float2*)c->d_tw.p, c->tw_n, which_probe, which_processing, spectrum, c->db.dt, n_alloc,
+                                        c->d_fshift.as<int>(), c->d_xcorr.as<float>(), c->stream);
+    if (e != cudaSuccess) return kiwi_set_error("CUDA error launching the probe export: %s", cudaGetErrorString(e));
+    int hdr[4] = {0, 0, 0, 0};
+    CU_OK(cudaMemcpyAsync(hdr, c->d_fshift.p, sizeof hdr, cudaMemcpyDeviceToHost, c->stream));
+    CU_OK(cudaStreamSynchronize(c->stream));
+    CU_OK(cudaGetLastError());
+    if (hdr[3] == 1) return kiwi_set_error("no synthetic seismogram available");
+    if (hdr[3] == 2) return kiwi_set_error("probe span does not fit the shared-memory transform");
+    if (first_index) *first_index = hdr[0];
+    if (n) *n = hdr[1];
+    if (df) memcpy(df, &hdr[2], sizeof(float));
+    if (hdr[1] > cap) return kiwi_set_error("buffer too small: need %d samples", hdr[1]);
+    if (hdr[1] > 0) CU_OK(cudaMemcpy(buf, c->d_xcorr.p, sizeof(float) * (size_t)hdr[1], cudaMemcpyDeviceToHost));
+    return 0;
+}
+}  // namespace
+
+// In-memory replacement of output_seismograms for all its variants (minimizer_engine.f90:947-1012, receiver.f90:616-661, probe_get
+// comparator.f90:356-433): which_probe 0 synthetics / 1 references, which_processing 0 plain / 1 tapered / 2 filtered
+int kiwi_get_probe(kiwi_ctx* c, int ireceiver, int icomponent, int which_probe, int which_processing, int* first_index, int* n, float* buf, int cap) {
+    return export_probe(c, ireceiver, icomponent, which_probe, which_processing, 0, first_index, n, nullptr, buf, cap);
+}
+// ... and of output_seismogram_spectra (minimizer_engine.f90:1014-1067, probe_get_amp_spectrum comparator.f90:332-354): n amplitudes at k * df
+int kiwi_get_probe_spectrum(kiwi_ctx* c, int ireceiver, int icomponent, int which_probe, int which_processing, float* df, int* n, float* buf, int cap) {
+    return export_probe(c, ireceiver, icomponent, which_probe, which_processing, 1, nullptr, n, df, buf, cap);
 }
 
 // get_distances (minimizer_engine.f90:1260-1281): epicentral distance [m] and azimuth [rad] of every receiver, in double

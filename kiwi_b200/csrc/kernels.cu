@@ -1352,6 +1352,85 @@ __global__ void __launch_bounds__(256) k_misfit_general(const ReceiverDev* __res
     }
 }
 
+// probe_get / probe_get_amp_spectrum (comparator.f90:332-433) of ONE probe: the synthetic (which_probe 0) or the reference (1) of
+// component ic of receiver ir, with the probe's own span as in a fresh process (no probes_adjust_spans has run).  processing 0 plain,
+// 1 tapered, 2 filtered; spectrum != 0: amplitude spectrum instead of the trace.  hdr: [0] first index, [1] length, [2] df (bits),
+// [3] status (0 ok, 1 no trace, 2 span does not fit).  One CTA.
+__global__ void __launch_bounds__(256) k_probe_export(const ReceiverDev* __restrict__ rcv, int ir, int ic, const CandDev* __restrict__ cands,
+                                                       const float* __restrict__ seis, size_t seis_stride, const SeisHdr* __restrict__ shdrs, int nrcv,
+                                                       const float* __restrict__ refdata, const float* __restrict__ taperdata,
+                                                       const float2* __restrict__ tw, int tw_n, int which_probe, int processing, int spectrum, float dt,
+                                                       int n_alloc, int* __restrict__ hdr, float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* z = reinterpret_cast<float2*>(smem_raw);
+    const ReceiverDev& R = rcv[ir];
+    const CandDev cand = cands[0];
+    const SeisHdr sh = shdrs[(size_t)ir * KIWI_MAX_COMP + ic];
+    const float* srow = seis + ((size_t)ir * KIWI_MAX_COMP + ic) * seis_stride;
+    const float* rdat = refdata + R.ref_off[ic];
+    const float* tp = taperdata + R.taper_off;
+    const bool tapered = R.has_taper != 0, filtered = R.has_filter != 0;
+    int ds0, ds1, sp0, sp1;
+    if (which_probe == 0) {
+        ds0 = sh.lo; ds1 = sh.hi;
+        if (ds1 >= ds0) allowed_span(ds0, ds1, ceil_len2(ds1 - ds0 + 1), sp0, sp1);
+    } else {
+        ds0 = R.ref_ds0[ic]; ds1 = R.ref_ds1[ic]; sp0 = R.ref_sp0[ic]; sp1 = R.ref_sp1[ic];
+    }
+    if (ds1 < ds0 || cand.status != 0) { if (threadIdx.x == 0) { hdr[0] = 1; hdr[1] = 0; hdr[2] = 0; hdr[3] = 1; } return; }
+    auto plain = [&](int x) -> float {   // element x of probe%array (comparator.f90:264-267)
+        if (x < ds0) return 0.f;
+        return which_probe == 0 ? srow[min(x, ds1) - sh.base] * cand.moment : rdat[min(x, ds1) - ds0];
+    };
+    auto tap = [&](int x) -> float {     // element x of probe%array_tapered
+        const float v = plain(x);
+        if (!tapered) return v;
+        return (x >= R.tp0 && x <= R.tp1) ? v * tp[x - R.tp0] : 0.f;
+    };
+    const int n = sp1 - sp0 + 1;
+    const bool need_fft = spectrum || (processing == 2 && filtered);
+    if (need_fft && (n > n_alloc || n < 2 || (n & (n - 1)) != 0)) { if (threadIdx.x == 0) { hdr[0] = 1; hdr[1] = 0; hdr[2] = 0; hdr[3] = 2; } return; }
+    if (!need_fft) {
+        int e0 = ds0, e1 = ds1;
+        if (processing >= 1 && tapered) { e0 = max(R.dps0, ds0); e1 = min(R.dps1, ds1); if (e0 > e1) { e0 = ds0; e1 = ds1; } }   // :385-386
+        for (int x = e0 + threadIdx.x; x <= e1; x += blockDim.x) out[x - e0] = (processing >= 1) ? tap(x) : plain(x);
+        if (threadIdx.x == 0) { hdr[0] = e0; hdr[1] = e1 - e0 + 1; hdr[2] = 0; hdr[3] = 0; }
+        return;
+    }
+    for (int j = threadIdx.x; j < n; j += blockDim.x) z[j] = make_float2(tap(sp0 + j), 0.f);   // make_spectrum transforms the tapered array (:1206-1210)
+    __syncthreads();
+    fft_dif_forward(z, n, tw, tw_n);
+    int log2n = 0; while ((1 << log2n) < n) log2n++;
+    const float df = 1.f / ((float)n * dt);
+    if (spectrum) {
+        for (int k = threadIdx.x; k <= (n >> 1); k += blockDim.x) {
+            const float2 v = z[(int)(__brev((unsigned)k) >> (32 - log2n))];
+            float a = sqrtf(v.x * v.x + v.y * v.y);
+            if (filtered && processing == 2) a *= plf_factor(R.fpx, R.fpy, R.nfp, df, k, false);
+            out[k] = a;
+        }
+        if (threadIdx.x == 0) { hdr[0] = 1; hdr[1] = (n >> 1) + 1; hdr[2] = __float_as_int(df); hdr[3] = 0; }
+        return;
+    }
+    for (int pz = threadIdx.x; pz < n; pz += blockDim.x) {   // spectrum_filtered, as in k_misfit_general
+        const int k = (int)(__brev((unsigned)pz) >> (32 - log2n));
+        const int kk = k <= (n >> 1) ? k : n - k;
+        const float hfac = plf_factor(R.fpx, R.fpy, R.nfp, df, kk, false);
+        z[pz].x *= hfac; z[pz].y *= hfac;
+    }
+    __syncthreads();
+    fft_dit_inverse(z, n, tw, tw_n);
+    int e0 = ds0, e1 = ds1;
+    if (tapered) { e0 = max(R.dps0, sp0); e1 = min(R.dps1, sp1); if (e0 > e1) { e0 = ds0; e1 = ds1; } }   // :408-413
+    const float fn = (float)n;
+    for (int x = e0 + threadIdx.x; x <= e1; x += blockDim.x) {
+        float v = z[x - sp0].x / fn;
+        if (tapered) v *= plf_factor(R.tpx, R.tpy, R.ntp, dt, x, true);
+        out[x - e0] = v;
+    }
+    if (threadIdx.x == 0) { hdr[0] = e0; hdr[1] = e1 - e0 + 1; hdr[2] = 0; hdr[3] = 0; }
+}
+
 // =================================================================================================
 // K8: point moment-tensor grid search (config C2).  For a point source the synthetic is linear in the
 // six moment-tensor components (make_weights seismogram.f90:316-336 is linear in m, everything after
@@ -1847,6 +1926,17 @@ cudaError_t launch_misfit_general(const ReceiverDev* rcv, int nrcv, const CandDe
     if (ncand * nrcv > 0)
         k_misfit_general<<<ncand * nrcv, 256, smem, st>>>(rcv, nrcv, cands, seis, seis_stride, shdrs, refdata, taperdata, tw, tw_n, method, dt,
                                                          syn_factor, nmisfits, out, status, fshift, n_alloc, nshift_alloc, map, xs0, xs1, premethod);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_probe_export(const ReceiverDev* rcv, int ir, int ic, const CandDev* cands, const float* seis, size_t seis_stride, const SeisHdr* shdrs, int nrcv,
+                                const float* refdata, const float* taperdata, const float2* tw, int tw_n, int which_probe, int processing, int spectrum,
+                                float dt, int n_alloc, int* hdr, float* out, cudaStream_t st) {
+    const size_t smem = sizeof(float2) * (size_t)n_alloc;
+    cudaError_t e = cudaFuncSetAttribute(k_probe_export, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_probe_export<<<1, 256, smem, st>>>(rcv, ir, ic, cands, seis, seis_stride, shdrs, nrcv, refdata, taperdata, tw, tw_n, which_probe, processing, spectrum, dt,
+                                         n_alloc, hdr, out);
     return cudaGetLastError();
 }
 

@@ -37,6 +37,9 @@ cudaError_t launch_misfit_general(const ReceiverDev* rcv, int nrcv, const CandDe
                                   const SeisHdr* shdrs, const float* refdata, const float* taperdata, const float2* tw, int tw_n, int method,
                                   float dt, float syn_factor, int nmisfits, float* out, int* status, int* fshift, int n_alloc,
                                   int nshift_alloc, const CandMap* map, cudaStream_t st, int xs0 = 0, int xs1 = 0, int premethod = 0);
+cudaError_t launch_probe_export(const ReceiverDev* rcv, int ir, int ic, const CandDev* cands, const float* seis, size_t seis_stride, const SeisHdr* shdrs, int nrcv,
+                                const float* refdata, const float* taperdata, const float2* tw, int tw_n, int which_probe, int processing, int spectrum,
+                                float dt, int n_alloc, int* hdr, float* out, cudaStream_t st);
 void launch_mt_contract(const ReceiverDev* rcv, int nrcv, const MtLoc* locs, int nloc, const float* mts, const int* cand_of, const float* seis,
                         size_t seis_stride, const SeisHdr* shdrs, const float* refdata, const float* taperdata, int method, float dt,
                         float syn_factor, int nmisfits, float* out, cudaStream_t st);

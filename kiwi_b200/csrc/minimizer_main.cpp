@@ -100,7 +100,7 @@ bool do_command(State& S, const std::string& cmd, const std::vector<std::string>
                                   "set_source_subparams_limits", "get_source_subparams", "minimize_lm", "get_peak_amplitudes", "get_arias_intensities",
                                   "shift_ref_seismogram", "autoshift_ref_seismogram", "set_misfit_filter_1", "output_cross_correlations",
                                   "get_cached_traces_memory", "set_cached_traces_memory_limit", "set_verbose", "set_ignore_sigint",
-                                  "get_principal_axes", "get_source_crustal_thickness", "output_distances"};
+                                  "get_principal_axes", "get_source_crustal_thickness", "output_distances", "output_seismogram_spectra"};
     bool is_known = false;
     for (const char* k : known) if (cmd == k) is_known = true;
     if (!is_known) return fail("unknown command: " + cmd);   // minimizer.f90:1809-1811
@@ -362,19 +362,28 @@ bool do_command(State& S, const std::string& cmd, const std::vector<std::string>
         *answer = fmt_floats(f.data(), f.size());
         return true;
     }
-    if (cmd == "output_seismograms") {   // minimizer_engine.f90:947-1012, `table` format, synthetics plain only
-        if (w.size() < 3) return fail("usage: output_seismograms filenamebase fileformat (synthetics|references) (plain|tapered|filtered)");
-        if (w[2] != "table") return fail("file format not available: " + w[2]);
-        if ((w.size() > 3 && w[3] != "synthetics") || (w.size() > 4 && w[4] != "plain")) return fail("only plain synthetics can be written by this front-end");
-        std::vector<float> buf(1 << 20);
+    if (cmd == "output_seismograms" || cmd == "output_seismogram_spectra") {   // minimizer_engine.f90:947-1067, `table` format
+        const bool spec = cmd == "output_seismogram_spectra";
+        if (w.size() < (spec ? 2u : 3u)) return fail(spec ? "usage: output_seismogram_spectra filenamebase (synthetics|references) (plain|tapered|filtered)"
+                                                          : "usage: output_seismograms filenamebase fileformat (synthetics|references) (plain|tapered|filtered)");
+        const size_t o = spec ? 2 : 3;   // index of the probe word
+        if (!spec && w[2] != "table") return fail("file format not available: " + w[2]);
+        const std::string probe = w.size() > o ? w[o] : "synthetics", proc = w.size() > o + 1 ? w[o + 1] : "plain";
+        const int wp = probe == "synthetics" ? 0 : (probe == "references" ? 1 : -1);
+        const int pr = proc == "plain" ? 0 : (proc == "tapered" ? 1 : (proc == "filtered" ? 2 : -1));
+        if (wp < 0) return fail("unknown probe name: " + probe);
+        if (pr < 0) return fail("unknown processing name: " + proc);
+        std::vector<float> buf(1 << 16);
         for (size_t ir = 0; ir < S.comps.size(); ir++)
             for (size_t ic = 0; ic < S.comps[ir].size(); ic++) {
-                int first = 0, n = 0;
-                if (kiwi_get_seismogram(S.ctx, (int)ir + 1, (int)ic + 1, 1, &first, &n, buf.data(), (int)buf.size())) return cfail();
-                const std::string fn = w[1] + "-" + std::to_string(ir + 1) + "-" + S.comps[ir][ic] + "." + w[2];
+                int first = 0, n = 0; float df = 0.f;
+                if (spec ? kiwi_get_probe_spectrum(S.ctx, (int)ir + 1, (int)ic + 1, wp, pr, &df, &n, buf.data(), (int)buf.size())
+                         : kiwi_get_probe(S.ctx, (int)ir + 1, (int)ic + 1, wp, pr, &first, &n, buf.data(), (int)buf.size())) return cfail();
+                const std::string fn = w[1] + "-" + std::to_string(ir + 1) + "-" + S.comps[ir][ic] + "." + (spec ? "table" : w[2]);
                 FILE* f = fopen(fn.c_str(), "w");
-                if (!f) return fail("can't open file: " + fn);
-                for (int i = 0; i < n; i++) fprintf(f, "%.9g %.9g\n", S.ref_time + (double)(first - 1 + i) * (double)S.dt, buf[i]);   // receiver.f90:649
+                if (!f) return fail("failed to write output file: " + fn);
+                for (int i = 0; i < n; i++)   // receiver.f90:649 (time of sample `first`: reftime + (first-1) dt) and :688 (frequency k df)
+                    fprintf(f, "%.9g %.9g\n", spec ? (double)i * (double)df : S.ref_time + (double)(first - 1 + i) * (double)S.dt, buf[i]);
                 fclose(f);
             }
         return true;

@@ -450,6 +450,19 @@ class Engine:
         _check(lib.kiwi_get_principal_axes(self._h, _fp(p), _fp(t)))
         return p, t
 
+    def get_probe(self, ireceiver, icomponent, which_probe="synthetics", processing="plain", spectrum=False):
+        """output_seismograms / output_seismogram_spectra in memory: (first index, samples) or (df, amplitudes)."""
+        wp, pr = ["synthetics", "references"].index(which_probe), ["plain", "tapered", "filtered"].index(processing)
+        buf = np.empty(1 << 15, dtype=np.float32)
+        n = C.c_int()
+        if spectrum:
+            df = C.c_float()
+            _check(lib.kiwi_get_probe_spectrum(self._h, ireceiver, icomponent, wp, pr, df, n, _fp(buf), buf.size))
+            return df.value, buf[:n.value].copy()
+        first = C.c_int()
+        _check(lib.kiwi_get_probe(self._h, ireceiver, icomponent, wp, pr, first, n, _fp(buf), buf.size))
+        return first.value, buf[:n.value].copy()
+
     def get_seismogram(self, ireceiver, icomponent, which=0):
         """In-memory replacement of output_seismograms: (first_index, samples)."""
         first, n = C.c_int(), C.c_int()

@@ -226,6 +226,37 @@ static inline void update_spectrum(Probe& p) { update_array_tapered(p); if (p.sp
 static inline void update_spectrum_filtered(Probe& p) { update_spectrum(p); if (p.spectrum_filtered_dirty) make_spectrum_filtered(p); p.spectrum_filtered_dirty = false; }
 static inline void update_array_filtered(Probe& p) { update_spectrum_filtered(p); if (p.array_filtered_dirty) make_array_filtered(p); p.array_filtered_dirty = false; }
 
+// probe_get_plain / _tapered / _filtered (:356-433) and probe_get_amp_spectrum (:332-354): the samples over the span the reference
+// hands out; which_processing 0 plain, 1 tapered, 2 filtered
+static inline void probe_get(Probe& self, int which_processing, int& first, std::vector<float>& out) {
+    out.clear(); first = 1;
+    if (!self.array.alloc) { out.push_back(0.f); return; }
+    int span[2] = {self.dataspan[0], self.dataspan[1]};
+    const Strip* src = &self.array;
+    if (which_processing == 2 && self.filter.defined) {
+        update_array_filtered(self);
+        if (self.taper.defined) {
+            int d[2]; discrete_plf_span(self.taper, self.dt, d); span_intersection(d, self.span, span);
+            if (span[0] > span[1]) { span[0] = self.dataspan[0]; span[1] = self.dataspan[1]; }
+        }
+        src = &self.array_filtered;
+    } else if (which_processing >= 1 && self.taper.defined) {
+        update_array_tapered(self);
+        int d[2]; discrete_plf_span(self.taper, self.dt, d); span_intersection(d, self.dataspan, span);
+        if (span[0] > span[1]) { span[0] = self.dataspan[0]; span[1] = self.dataspan[1]; }
+        src = &self.array_tapered;
+    }
+    first = span[0];
+    for (int i = span[0]; i <= span[1]; i++) out.push_back((float)src->at(i));
+}
+static inline void probe_get_amp_spectrum(Probe& self, int which_processing, float& df, std::vector<float>& out) {
+    out.clear(); df = 0.f;
+    if (!self.array.alloc) { out.push_back(0.f); return; }
+    update_spectrum_filtered(self);
+    df = self.df;
+    out = (self.filter.defined && which_processing == 2) ? self.amp_spectrum_filtered : self.amp_spectrum;
+}
+
 // norm functions, :627-697: element arithmetic in fp32, sum in fp64, result fp32
 struct Norm2 { virtual float f(const float* a, const float* b, int n, float dt, float fa, float fb) const = 0; virtual ~Norm2() {} };
 template <class T>

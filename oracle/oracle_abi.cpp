@@ -201,6 +201,26 @@ int oracle_principal_axes(float strike_deg, float dip_deg, float rake_deg, float
     }
     return 0;
 }
+// output_seismograms / output_seismogram_spectra (minimizer_engine.f90:947-1067) in memory: update_syn_probes of the current source in a
+// fresh process, then probe_get / probe_get_amp_spectrum of the synthetic (which_probe 0) or reference (1) probe
+int oracle_get_probe(void* h, int irec, int icomp, int which_probe, int which_processing, int spectrum, int* first, int* n, float* df, float* buf, int cap) {
+    Engine& e = *(Engine*)h;
+    if (e.cur_params.empty()) { e.errstr = "no source parameters set"; return 1; }
+    if (irec < 1 || irec > (int)e.receivers.size()) { e.errstr = "receiver index out of range"; return 1; }
+    std::vector<float> params = e.cur_params;
+    if (!set_source_params(e, e.cur_type, params.data(), (int)params.size())) return 1;
+    if (!calculate_seismograms(e)) return 1;
+    if (!scale_seismograms(e)) return 1;
+    Receiver& rc = e.receivers[irec - 1];
+    if (icomp < 1 || icomp > rc.ncomponents) { e.errstr = "component index out of range"; return 1; }
+    Probe& p = which_probe == 0 ? rc.syn_probes[icomp - 1] : rc.ref_probes[icomp - 1];
+    std::vector<float> v;
+    *first = 1; *df = 0.f;
+    if (spectrum) probe_get_amp_spectrum(p, which_processing, *df, v); else probe_get(p, which_processing, *first, v);
+    *n = (int)v.size();
+    for (int i = 0; i < std::min(*n, cap); i++) buf[i] = v[i];
+    return 0;
+}
 int oracle_set_crust2x2(void* h, const char* path) {
     Engine& e = *(Engine*)h;
     if (!crust2x2_load(path, e.crust)) { e.errstr = "can't load crust2x2 table"; return 1; }

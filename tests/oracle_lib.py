@@ -39,7 +39,7 @@ def lib(wide=False):
                      "oracle_set_source_params_mask", "oracle_set_source_subparams", "oracle_set_source_subparams_limits",
                      "oracle_get_source_subparams", "oracle_minimize_lm", "oracle_lmdif", "oracle_get_ground_motion",
                      "oracle_shift_ref_seismogram", "oracle_autoshift_ref_seismogram", "oracle_get_cross_correlations",
-                     "oracle_get_distances", "oracle_get_source_crustal_thickness", "oracle_principal_axes"):
+                     "oracle_get_distances", "oracle_get_source_crustal_thickness", "oracle_principal_axes", "oracle_get_probe"):
             if hasattr(L, name):
                 getattr(L, name).argtypes = None
         _libs[wide] = L
@@ -257,6 +257,15 @@ class OracleEngine:
         p, t = np.zeros(2, np.float32), np.zeros(2, np.float32)
         self.L.oracle_principal_axes(C.c_float(strike), C.c_float(dip), C.c_float(rake), p.ctypes.data_as(fp), t.ctypes.data_as(fp))
         return p, t
+
+    def get_probe(self, irec, icomp, which_probe="synthetics", processing="plain", spectrum=False):
+        """(first index, samples) of probe_get, or (df, amplitudes) of probe_get_amp_spectrum"""
+        first, n, df = C.c_int(), C.c_int(), C.c_float()
+        buf = np.empty(1 << 16, np.float32)
+        self._check(self.L.oracle_get_probe(self.h, C.c_int(irec), C.c_int(icomp), C.c_int(["synthetics", "references"].index(which_probe)),
+                                            C.c_int(["plain", "tapered", "filtered"].index(processing)), C.c_int(int(spectrum)), C.byref(first), C.byref(n),
+                                            C.byref(df), buf.ctypes.data_as(fp), C.c_int(buf.size)))
+        return (df.value if spectrum else first.value), buf[:n.value].copy()
 
     def get_seismogram(self, irec, icomp, which=0):
         first, n = C.c_int(), C.c_int()

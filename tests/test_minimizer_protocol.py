@@ -112,7 +112,9 @@ def test_session_with_interpolated_database_and_autoshift(tmp_path):
                 "autoshift_ref_seismogram 9 -0.5 0.5", "shift_ref_seismogram 1",
                 "output_cross_correlations %s -0.2 0.2" % (base + "cc"), "get_cached_traces_memory", "set_verbose T",
                 "set_misfit_filter_1 2 0.2 0 0.5 1 2.0 1 3.0 0", "get_global_misfit", "get_principal_axes",
-                "output_distances %s" % (base + ".distances")])
+                "output_distances %s" % (base + ".distances"), "set_misfit_taper 1 1.0 0 1.6 1 4.0 1 5.2 0",
+                "output_seismograms %s table references tapered" % (base + "rt"), "output_seismogram_spectra %s synthetics filtered" % (base + "sp"),
+                "output_seismograms %s table nonsense plain" % base])
     it = iter(out)
     for _ in range(9):
         assert next(it).endswith(": ok"), out
@@ -132,6 +134,12 @@ def test_session_with_interpolated_database_and_autoshift(tmp_path):
     assert next(it) == "output_distances: ok"
     dist = np.loadtxt(base + ".distances")
     assert dist.shape == (3, 3) and np.all((dist[:, 1] > 7e3) & (dist[:, 1] < 15e3)) and np.allclose(dist[:, 0], dist[:, 1] / 6371e3 * 180 / np.pi, rtol=1e-6)
+    assert next(it) == "set_misfit_taper: ok" and next(it) == "output_seismograms: ok" and next(it) == "output_seismogram_spectra: ok"
+    assert next(it) == "output_seismograms: nok >" and next(it) == "unknown probe name: nonsense"
+    rt, plain = np.loadtxt(base + "rt-1-n.table"), np.loadtxt(base + "-1-n.table")
+    assert rt[0, 0] >= 1.0 - 1e-6 and rt[-1, 0] <= 5.2 + 1e-6 and rt.shape[0] < plain.shape[0] and np.abs(rt[:, 1]).max() <= np.abs(plain[:, 1]).max() * 1.07 * (1 + 1e-6)
+    sp = np.loadtxt(base + "sp-2-e.table")
+    assert sp[0, 0] == 0.0 and np.all(np.diff(sp[:, 0]) > 0) and sp[-1, 0] == pytest.approx(5.0) and sp[np.argmax(sp[:, 1]), 0] < 3.0
     cc = np.loadtxt(base + "cc-2-e.table")
     assert cc.shape == (5, 2) and np.allclose(cc[:, 0], [-0.2, -0.1, 0.0, 0.1, 0.2], atol=1e-6) and np.argmax(cc[:, 1]) == 2
     assert np.allclose(shifts, [0.0, -0.3, 0.0], atol=1e-6)          # the far-field traces correlate best where they came from

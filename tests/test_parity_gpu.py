@@ -361,6 +361,42 @@ def test_cross_correlations(taper, filt):
         assert np.all(np.abs(cg - co) <= (4 if filt else 1) * RTOL * scale), (ir, (np.abs(cg - co) / scale).max())
 
 
+@pytest.mark.parametrize("taper,filt", [(False, False), (True, False), (False, True), (True, True)])
+def test_probe_export_all_variants(taper, filt):
+    """output_seismograms / output_seismogram_spectra in memory (probe_get, probe_get_amp_spectrum comparator.f90:332-433): synthetics and
+    references, plain / tapered / filtered, with the spans of a fresh process"""
+    g, o = engines(sc.small_db(), COMPS6)
+    ncomps = [len(c) for c in COMPS6]
+    o.eval_sources("bilateral", sc.BILAT_SMALL)
+    sc.set_refs_from(o, [g, o], ncomps, shift=2)
+    for e in (g, o):
+        if taper:
+            for ir in range(1, 7):
+                e.set_misfit_taper(ir, *TAPER)
+        if filt:
+            e.set_misfit_filter(*FILTER)
+    p = _candidates()[6]                     # with a rise time: the folded synthetic
+    o.eval_sources("bilateral", p)
+    g.set_source_params("bilateral", p)
+    for ir, ic in ((1, 1), (2, 2), (3, 1), (5, 2), (6, 3)):
+        for which in ("synthetics", "references"):
+            for proc in ("plain", "tapered", "filtered"):
+                fg, dg = g.get_probe(ir, ic, which, proc)
+                fo, do = o.get_probe(ir, ic, which, proc)
+                assert fg == fo and dg.size == do.size, (ir, ic, which, proc, fg, fo, dg.size, do.size)
+                scale = np.abs(do).max()
+                lim = (4 if (filt and proc == "filtered") else 1) * RTOL * scale
+                assert np.abs(dg - do).max() <= lim, (ir, ic, which, proc, np.abs(dg - do).max() / scale)
+                if not (filt and proc == "filtered") and which == "references":
+                    assert np.array_equal(dg, do)          # no arithmetic but one multiplication
+                dfg, ag = g.get_probe(ir, ic, which, proc, spectrum=True)
+                dfo, ao = o.get_probe(ir, ic, which, proc, spectrum=True)
+                assert dfg == dfo and ag.size == ao.size
+                assert np.abs(ag - ao).max() <= 4 * RTOL * np.abs(ao).max(), (ir, ic, which, proc, np.abs(ag - ao).max() / np.abs(ao).max())
+    with pytest.raises(Exception, match="component index out of range"):
+        g.get_probe(3, 2)
+
+
 def test_distances_crustal_thickness_and_principal_axes():
     """get_distances (minimizer_engine.f90:1260-1281), get_source_crustal_thickness (:488-498), get_principal_axes (:1248-1258): host
     arithmetic of the reference, exact against the restatement"""
