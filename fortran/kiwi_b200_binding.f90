@@ -272,6 +272,156 @@ module kiwi_b200_binding
             integer(c_int) :: rc
         end function
 
+        ! ---- the remaining engine-facing entry points ------------------------------------------------------------------
+
+        function kiwi_gfdb_read(path) bind(C, name="kiwi_gfdb_read") result(db)          ! KGF1 file of this library
+            import :: c_ptr, c_char
+            character(kind=c_char), intent(in) :: path(*)                                 ! NUL terminated
+            type(c_ptr) :: db
+        end function
+
+        function kiwi_gfdb_read_hdf(basepath) bind(C, name="kiwi_gfdb_read_hdf") result(db)   ! <base>.index + <base>.<i>.chunk
+            import :: c_ptr, c_char
+            character(kind=c_char), intent(in) :: basepath(*)
+            type(c_ptr) :: db
+        end function
+
+        subroutine kiwi_gfdb_destroy(db) bind(C, name="kiwi_gfdb_destroy")
+            import :: c_ptr
+            type(c_ptr), value :: db
+        end subroutine
+
+        function kiwi_set_crust2x2(ctx, path) bind(C, name="kiwi_set_crust2x2") result(rc)    ! crust2x2_load, minimizer.f90:1669-1674
+            import :: c_ptr, c_int, c_char
+            type(c_ptr), value :: ctx
+            character(kind=c_char), intent(in) :: path(*)
+            integer(c_int) :: rc
+        end function
+
+        function kiwi_set_source_constraints(ctx, n, points, normals) bind(C, name="kiwi_set_source_constraints") result(rc)
+            import :: c_ptr, c_int, c_float
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: n
+            real(c_float), intent(in) :: points(3,*), normals(3,*)
+            integer(c_int) :: rc
+        end function
+
+        function kiwi_set_source_crustal_thickness_limit(ctx, limit) bind(C, name="kiwi_set_source_crustal_thickness_limit") result(rc)
+            import :: c_ptr, c_int, c_float
+            type(c_ptr), value :: ctx
+            real(c_float), value :: limit
+            integer(c_int) :: rc
+        end function
+
+        function kiwi_get_source_crustal_thickness(ctx, thickness) bind(C, name="kiwi_get_source_crustal_thickness") result(rc)
+            import :: c_ptr, c_int, c_float
+            type(c_ptr), value :: ctx
+            real(c_float), intent(out) :: thickness
+            integer(c_int) :: rc
+        end function
+
+        function kiwi_get_distances(ctx, distances, azimuths, cap, n) bind(C, name="kiwi_get_distances") result(rc)
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value :: ctx
+            real(c_double), intent(out) :: distances(*), azimuths(*)
+            integer(c_int), value :: cap
+            integer(c_int), intent(out) :: n
+            integer(c_int) :: rc
+        end function
+
+        function kiwi_get_principal_axes(ctx, pax, tax) bind(C, name="kiwi_get_principal_axes") result(rc)
+            import :: c_ptr, c_int, c_float
+            type(c_ptr), value :: ctx
+            real(c_float), intent(out) :: pax(2), tax(2)
+            integer(c_int) :: rc
+        end function
+
+        function kiwi_get_floating_shifts(ctx, shifts, cap, n) bind(C, name="kiwi_get_floating_shifts") result(rc)   ! in samples
+            import :: c_ptr, c_int
+            type(c_ptr), value :: ctx
+            integer(c_int), intent(out) :: shifts(*)
+            integer(c_int), value :: cap
+            integer(c_int), intent(out) :: n
+            integer(c_int) :: rc
+        end function
+
+        function kiwi_get_peak_amplitudes(ctx, differentiate, maxabs, cap, n) bind(C, name="kiwi_get_peak_amplitudes") result(rc)
+            import :: c_ptr, c_int, c_float
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: differentiate, cap
+            real(c_float), intent(out) :: maxabs(*)
+            integer(c_int), intent(out) :: n
+            integer(c_int) :: rc
+        end function
+
+        function kiwi_get_arias_intensities(ctx, intensities, cap, n) bind(C, name="kiwi_get_arias_intensities") result(rc)
+            import :: c_ptr, c_int, c_float
+            type(c_ptr), value :: ctx
+            real(c_float), intent(out) :: intensities(*)
+            integer(c_int), value :: cap
+            integer(c_int), intent(out) :: n
+            integer(c_int) :: rc
+        end function
+
+        ! probe_get / probe_get_amp_spectrum for output_seismograms and output_seismogram_spectra:
+        ! which_probe 0 synthetics, 1 references; which_processing 0 plain, 1 tapered, 2 filtered
+        function kiwi_get_probe(ctx, ireceiver, icomponent, which_probe, which_processing, first_index, n, buf, cap) &
+                bind(C, name="kiwi_get_probe") result(rc)
+            import :: c_ptr, c_int, c_float
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: ireceiver, icomponent, which_probe, which_processing, cap
+            integer(c_int), intent(out) :: first_index, n
+            real(c_float), intent(out) :: buf(*)
+            integer(c_int) :: rc
+        end function
+
+        function kiwi_get_probe_spectrum(ctx, ireceiver, icomponent, which_probe, which_processing, df, n, buf, cap) &
+                bind(C, name="kiwi_get_probe_spectrum") result(rc)
+            import :: c_ptr, c_int, c_float
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: ireceiver, icomponent, which_probe, which_processing, cap
+            real(c_float), intent(out) :: df
+            integer(c_int), intent(out) :: n
+            real(c_float), intent(out) :: buf(*)
+            integer(c_int) :: rc
+        end function
+
+        ! batched ground-motion diagnostics: out(3, nenabled, ns) = peak velocity, peak acceleration, Arias intensity
+        function kiwi_eval_ground_motion(ctx, sourcetype, ns, nparams, params, out, status) bind(C, name="kiwi_eval_ground_motion") result(rc)
+            import :: c_ptr, c_int, c_float
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: sourcetype, ns, nparams
+            real(c_float), intent(in) :: params(*)
+            real(c_float), intent(out) :: out(*)
+            integer(c_int), intent(out) :: status(*)
+            integer(c_int) :: rc
+        end function
+
+        ! make_global_misfits + best candidate on the device (seismosizer.py:843-922); pass c_null_ptr for d_misfits to use the block
+        ! the last kiwi_eval_sources call left on the GPU, and for the optional arrays that are not wanted
+        function kiwi_outer_misfits(ctx, ns, d_misfits, receiver_weights, outer_norm, anarchy, nboot, bweights, misfits_by_s, best, best_value) &
+                bind(C, name="kiwi_outer_misfits") result(rc)
+            import :: c_ptr, c_int
+            type(c_ptr), value :: ctx, d_misfits, receiver_weights, bweights, misfits_by_s, best, best_value
+            integer(c_int), value :: ns, outer_norm, anarchy, nboot
+            integer(c_int) :: rc
+        end function
+
+        function kiwi_set_mt_grid(ctx, enabled) bind(C, name="kiwi_set_mt_grid") result(rc)
+            import :: c_ptr, c_int
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: enabled
+            integer(c_int) :: rc
+        end function
+
+        function kiwi_set_share_syntheses(ctx, enabled) bind(C, name="kiwi_set_share_syntheses") result(rc)
+            import :: c_ptr, c_int
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: enabled
+            integer(c_int) :: rc
+        end function
+
+
     end interface
 
 end module
