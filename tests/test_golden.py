@@ -36,3 +36,31 @@ def test_cuda_path_against_golden_fixtures():
             floor = 0.25 if "ampspec" in k else 0.1
             tol = 1e-5 * np.maximum(np.abs(b), floor * np.abs(b[..., 1:2]))
             assert np.all(np.abs(a - b) <= tol), (k, np.abs((a - b) / tol).max())
+
+
+EXTRAS = np.load(os.path.join(HERE, "golden", "round1_extras.npz"))
+
+
+def test_oracle_reproduces_the_round1_extras_bit_exact():
+    now = mg.build_extras()
+    assert sorted(now) == sorted(EXTRAS.files)
+    for k in EXTRAS.files:
+        a, b = np.asarray(now[k]), EXTRAS[k]
+        assert a.shape == b.shape and a.dtype == b.dtype, (k, a.dtype, b.dtype)
+        assert np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a, b.view(np.uint32) if b.dtype == np.float32 else b), k
+
+
+@pytest.mark.gpu
+def test_cuda_path_against_the_round1_extras():
+    from kiwi_b200 import Engine
+    now = mg.build_extras(lambda: Engine(0))
+    for k in EXTRAS.files:
+        a, b = np.asarray(now[k]), EXTRAS[k]
+        assert a.shape == b.shape, k
+        if k.endswith("_first") or k in ("autoshift", "distances", "azimuths", "principal_axes", "spectrum_df") or k.startswith("interp_"):
+            assert np.array_equal(a, b), k                     # integers, host arithmetic, the bit-exact interpolation
+        elif k.startswith("misfits_"):
+            tol = 1e-5 * np.maximum(np.abs(b), 0.25 * np.abs(b[..., 1:2]))      # filtered norm: through two fp32 FFTs
+            assert np.all(np.abs(a - b) <= tol), (k, np.abs((a - b) / tol).max())
+        else:                                                  # cross-correlations, probes, spectrum
+            assert np.abs(a - b).max() <= 4e-5 * np.abs(b).max(), (k, np.abs(a - b).max() / np.abs(b).max())
