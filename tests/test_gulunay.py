@@ -104,3 +104,19 @@ def test_engine_runs_on_an_interpolated_database():
         lo, hi = max(fa, fb), min(fa + da.size, fb + dbb.size)
         x, y = da[lo - fa:hi - fa], dbb[lo - fb:hi - fb]
         assert np.dot(x, y) / np.sqrt(np.dot(x, x) * np.dot(y, y)) > 0.95
+
+
+@pytest.mark.gpu
+def test_interpolation_refuses_what_the_reference_cannot_do():
+    from kiwi_b200 import KiwiError, engine
+    db = small_db(12, 2, 8)
+    with pytest.raises(KiwiError, match="interpolation factors must be"):
+        db.interpolate(3, 1)
+    holed = Gfdb.create(12, 2, 8, 0.1, 400.0, 400.0, 4000.0, 2000.0)
+    holed.save_array(1, 1, 1, 10, np.ones(8, np.float32))              # one trace only
+    with pytest.raises(KiwiError, match="[Mm]issing trace"):
+        holed.interpolate(2, 1)
+    with pytest.raises(KiwiError, match="powers of two"):
+        engine.gulunay(np.zeros((1, 1, 12, 100), np.float32), 2, 1, 8, 4, 0)
+    with pytest.raises(KiwiError, match="margins overlap"):
+        engine.gulunay(np.zeros((1, 1, 4, 64), np.float32), 2, 1, 8, 16, 0)

@@ -395,6 +395,17 @@ def test_probe_export_all_variants(taper, filt):
                 assert np.abs(ag - ao).max() <= 4 * RTOL * np.abs(ao).max(), (ir, ic, which, proc, np.abs(ag - ao).max() / np.abs(ao).max())
     with pytest.raises(Exception, match="component index out of range"):
         g.get_probe(3, 2)
+    with pytest.raises(Exception, match="receiver index out of range"):
+        g.get_cross_correlations(0, -0.1, 0.1)
+    with pytest.raises(Exception, match="empty shift range"):
+        g.get_cross_correlations(1, 0.3, 0.1)
+    fresh, _ = engines(sc.small_db(), COMPS6)
+    fresh.set_source_params("bilateral", p)
+    with pytest.raises(Exception, match="no reference seismograms set"):
+        fresh.get_probe(1, 1, "references")
+    with pytest.raises(Exception, match="no reference seismograms set"):
+        fresh.autoshift_ref_seismogram(0, -0.1, 0.1)
+    assert fresh.get_probe(1, 1, "synthetics")[1].size > 10
 
 
 def test_distances_crustal_thickness_and_principal_axes():
