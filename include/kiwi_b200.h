@@ -286,6 +286,10 @@ int kiwi_get_spans(kiwi_ctx* ctx, int ireceiver, int* spans6);
 /* stored span of one GF trace in the HBM slab layout */
 int kiwi_trace_span(kiwi_ctx* ctx, int ix, int iz, int ig, int* span2);
 
+/* the fast-marching solver of the eikonal sources (eikonal.f90:29-199, heap.f90) as the host runs it per candidate: arrival times on a
+ * grid (nx, ny), ix fastest, of a front starting at initialpoint.  Host only, no GPU needed. */
+int kiwi_eikonal_fmm(int nx, int ny, const float* speed, const float* origin2, const float* delta2, const float* initialpoint2, float* times);
+
 /* ---- measurement support -------------------------------------------------------------------- */
 /* algorithmic / logical bytes per evaluation of the last kiwi_eval_sources batch (SURVEY.md
  * section 8d), averaged over the first min(max_candidates, chunk) candidates of its last chunk:

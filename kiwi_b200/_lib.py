@@ -78,6 +78,7 @@ SIGNATURES = {
     "kiwi_get_principal_axes": (C.c_int, [C.c_void_p, c_float_p, c_float_p]),
     "kiwi_get_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_float_p, C.c_int]),
     "kiwi_get_probe_spectrum": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p, c_int_p, c_float_p, C.c_int]),
+    "kiwi_eikonal_fmm": (C.c_int, [C.c_int, C.c_int, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p]),
     "kiwi_get_seismogram": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_float_p, C.c_int]),
     "kiwi_discretize_source": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, c_float_p, C.c_int, c_int_p, c_int_p]),
     "kiwi_get_indices": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_int_p, c_int_p, c_float_p, c_float_p, c_int_p, C.c_int, c_int_p]),

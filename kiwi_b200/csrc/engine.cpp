@@ -1602,6 +1602,14 @@ int kiwi_get_probe_spectrum(kiwi_ctx* c, int ireceiver, int icomponent, int whic
     return export_probe(c, ireceiver, icomponent, which_probe, which_processing, 1, nullptr, n, df, buf, cap);
 }
 
+// eikonal_solver_fmm (eikonal.f90:29-199) as the eikonal sources run it on the host; speed and times are (nx, ny) with ix fastest.
+// Needs no GPU (used by the CPU tests: the reference's own test_eikonal.f90 and bit-exactness against the restatement).
+int kiwi_eikonal_fmm(int nx, int ny, const float* speed, const float* origin2, const float* delta2, const float* initialpoint2, float* times) {
+    if (nx < 1 || ny < 1 || !speed || !times) return kiwi_set_error("kiwi_eikonal_fmm: invalid grid");
+    kh::eikonal_solver_fmm(speed, nx, ny, origin2, delta2, initialpoint2, times);
+    return 0;
+}
+
 // get_distances (minimizer_engine.f90:1260-1281): epicentral distance [m] and azimuth [rad] of every receiver, in double
 int kiwi_get_distances(kiwi_ctx* c, double* distances, double* azimuths, int cap, int* n) {
     if (!c) return kiwi_set_error("null context");

@@ -166,63 +166,74 @@ static void trim_polygon_more(const Polygon& poly, const std::vector<Halfspace>&
 }
 
 // ---- heap.f90: index heap with back-pointers (1-based indices as in the reference) ----------------------
+// The heap holds (key, index) pairs instead of indices into the key array: every comparison of heap.f90 reads the same values, so the
+// pop order -- which the solver's result depends on, see below -- is the reference's, but the sift loops stay in one array.
+struct HeapItem { float key; int idx; };
 struct IndexHeap {
-    std::vector<int> iheap;   // iheap[1..n]
+    std::vector<HeapItem> item;   // item[1..n]
     int n = 0, cap = 0;
-    void init(int maxsize) { iheap.assign((size_t)maxsize + 1, 0); n = 0; cap = maxsize; }
+    void init(int maxsize) { item.assign((size_t)maxsize + 1, HeapItem{0.f, 0}); n = 0; cap = maxsize; }
 };
-static void upheap(IndexHeap& h, int element, const float* keys, int* bp) {   // :210-232
+static inline void upheap(IndexHeap& h, int element, int* bp) {   // :210-232
+    HeapItem* a = h.item.data();
     int v = element;
     while (v > 1) {
         const int u = (v - 2) / 2 + 1;
-        if (keys[h.iheap[u]] <= keys[h.iheap[v]]) return;
-        std::swap(h.iheap[u], h.iheap[v]);
-        std::swap(bp[h.iheap[u]], bp[h.iheap[v]]);
+        if (a[u].key <= a[v].key) return;
+        std::swap(a[u], a[v]);
+        bp[a[u].idx] = u; bp[a[v].idx] = v;
         v = u;
     }
 }
-static void downheap(IndexHeap& h, int element, const float* keys, int* bp) {   // :176-208
+static inline void downheap(IndexHeap& h, int element, int* bp) {   // :176-208
+    HeapItem* a = h.item.data();
     int v = element;
     int w = 2 * (v - 1) + 2;
     while (w <= h.n) {
-        if (w + 1 <= h.n && keys[h.iheap[w + 1]] < keys[h.iheap[w]]) w = w + 1;
-        if (keys[h.iheap[v]] <= keys[h.iheap[w]]) return;
-        std::swap(h.iheap[v], h.iheap[w]);
-        std::swap(bp[h.iheap[v]], bp[h.iheap[w]]);
+        if (w + 1 <= h.n && a[w + 1].key < a[w].key) w = w + 1;
+        if (a[v].key <= a[w].key) return;
+        std::swap(a[v], a[w]);
+        bp[a[v].idx] = v; bp[a[w].idx] = w;
         v = w;
         w = 2 * (v - 1) + 2;
     }
 }
-static void pushheap(IndexHeap& h, int keyindex, const float* keys, int* bp) {   // :70-93
+static inline void pushheap(IndexHeap& h, int keyindex, const float* keys, int* bp) {   // :70-93
     if (h.n + 1 > h.cap) return;
     h.n = h.n + 1;
-    h.iheap[h.n] = keyindex;
+    h.item[h.n] = HeapItem{keys[keyindex], keyindex};
     bp[keyindex] = h.n;
-    upheap(h, h.n, keys, bp);
+    upheap(h, h.n, bp);
 }
-static int popheap(IndexHeap& h, const float* keys, int* bp) {   // :95-124
+static inline int popheap(IndexHeap& h, int* bp) {   // :95-124
     if (h.n == 0) return 0;
-    std::swap(h.iheap[1], h.iheap[h.n]);
-    std::swap(bp[h.iheap[1]], bp[h.iheap[h.n]]);
-    bp[h.iheap[h.n]] = 0;
-    const int keyindex = h.iheap[h.n];
+    std::swap(h.item[1], h.item[h.n]);
+    bp[h.item[1].idx] = 1;
+    const int keyindex = h.item[h.n].idx;
+    bp[keyindex] = 0;
     h.n = h.n - 1;
-    downheap(h, 1, keys, bp);
+    downheap(h, 1, bp);
     return keyindex;
 }
-static void updateheap(IndexHeap& h, int keyindex, float newkey, float* keys, int* bp) {   // :126-150
+static inline void updateheap(IndexHeap& h, int keyindex, float newkey, float* keys, int* bp) {   // :126-150
     const float oldkey = keys[keyindex];
     keys[keyindex] = newkey;
-    if (newkey < oldkey) upheap(h, bp[keyindex], keys, bp);
-    if (newkey > oldkey) downheap(h, bp[keyindex], keys, bp);
+    h.item[bp[keyindex]].key = newkey;
+    if (newkey < oldkey) upheap(h, bp[keyindex], bp);
+    if (newkey > oldkey) downheap(h, bp[keyindex], bp);
 }
 
 // ---- eikonal.f90:29-199: fast marching; arrays are (ix,iy) column-major, 1-based linear index i=(iy-1)*nx+ix ----
+// Neighbour times enter an update whether they are final or still tentative (:151-155), so the result depends on the order in which the
+// heap hands out equal and near-equal keys: the solver cannot be reordered or parallelised without changing the sub-source table, and
+// runs per candidate on the host.  The loop-invariant products of :163-166 are formed once; they are the same operations on the same
+// operands.
 void eikonal_solver_fmm(const float* speed, int nx, int ny, const float origin[2], const float delta[2], const float initialpoint[2],
                         float* times) {
     const int FARAWAY = -1, ALIVE = 0;
     const float infinity = std::numeric_limits<float>::max() * 0.1f;
     const float dx = delta[0], dy = delta[1];
+    const float dx2 = dx * dx, dy2 = dy * dy, dx2dy2 = dx2 * dy2, dx2pdy2 = dx2 + dy2;
     std::vector<int> bpv((size_t)nx * ny + 1, FARAWAY);
     int* bp = bpv.data();               // bp[1..nx*ny]
     float* T = times - 1;               // T[1..nx*ny]
@@ -250,29 +261,28 @@ void eikonal_solver_fmm(const float* speed, int nx, int ny, const float origin[2
     if (1 < iy) pushheap(heap, ind(ix, iy - 1), T, bp);
     if (iy < ny) pushheap(heap, ind(ix, iy + 1), T, bp);
 
-    auto update_neighbor = [&](int jx, int jy) {   // :134-190
-        const int i = (jy - 1) * nx + jx;
+    auto update_neighbor = [&](int jx, int jy, int i) {   // :134-190, i = ind(jx, jy)
         if (bp[i] == ALIVE) return;
         if (bp[i] == FARAWAY) pushheap(heap, i, T, bp);
         float a = infinity, b = infinity, c = infinity, d = infinity;
         const float told = T[i];
-        if (1 < jx) a = T[ind(jx - 1, jy)];
-        if (jx < nx) b = T[ind(jx + 1, jy)];
-        if (1 < jy) c = T[ind(jx, jy - 1)];
-        if (jy < ny) d = T[ind(jx, jy + 1)];
+        if (1 < jx) a = T[i - 1];
+        if (jx < nx) b = T[i + 1];
+        if (1 < jy) c = T[i - nx];
+        if (jy < ny) d = T[i + nx];
         float t = 0.f;
         const float aa = std::min(a, b), cc = std::min(c, d);
         const float sp = S[i];
         if (std::max(aa, cc) != infinity) {
             const float q = (aa - cc) * sp;
-            const float s = (dx * dx) * (dy * dy) * ((dx * dx) + (dy * dy) - q * q);
-            if (s >= 0.f) t = std::max(t, ((aa * (dy * dy) + cc * (dx * dx)) * sp + sqrtf(s)) / (sp * ((dx * dx) + (dy * dy))));
+            const float s = dx2dy2 * (dx2pdy2 - q * q);
+            if (s >= 0.f) t = std::max(t, ((aa * dy2 + cc * dx2) * sp + sqrtf(s)) / (sp * dx2pdy2));
         }
-        if (std::min(c, d) == infinity) {
+        if (cc == infinity) {
             if (a < infinity) t = std::max(t, a + dx / sp);
             if (b < infinity) t = std::max(t, b + dx / sp);
         }
-        if (std::min(a, b) == infinity) {
+        if (aa == infinity) {
             if (c < infinity) t = std::max(t, c + dy / sp);
             if (d < infinity) t = std::max(t, d + dy / sp);
         }
@@ -286,16 +296,16 @@ void eikonal_solver_fmm(const float* speed, int nx, int ny, const float origin[2
         if (t != 0.f && told != t) updateheap(heap, i, t, T, bp);
     };
     while (nalive <= nx * ny) {
-        const int imin = popheap(heap, T, bp);
+        const int imin = popheap(heap, bp);
         if (imin == 0) break;
-        ix = (imin - 1) % nx + 1;
         iy = (imin - 1) / nx + 1;
+        ix = imin - (iy - 1) * nx;
         bp[imin] = ALIVE;
         nalive = nalive + 1;
-        if (1 < ix) update_neighbor(ix - 1, iy);
-        if (ix < nx) update_neighbor(ix + 1, iy);
-        if (1 < iy) update_neighbor(ix, iy - 1);
-        if (iy < ny) update_neighbor(ix, iy + 1);
+        if (1 < ix) update_neighbor(ix - 1, iy, imin - 1);
+        if (ix < nx) update_neighbor(ix + 1, iy, imin + 1);
+        if (1 < iy) update_neighbor(ix, iy - 1, imin - nx);
+        if (iy < ny) update_neighbor(ix, iy + 1, imin + nx);
     }
 }
 

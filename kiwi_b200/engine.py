@@ -524,6 +524,16 @@ def gulunay(a, l1, l2, ntmargin, margin1, margin2, device=0):
     return a, out
 
 
+def eikonal_fmm(speed, origin, delta, initialpoint):
+    """eikonal_solver_fmm (eikonal.f90:29-199) on the host: speed[ny][nx] -> times[ny][nx]."""
+    sp = np.ascontiguousarray(speed, dtype=np.float32)
+    ny, nx = sp.shape
+    times = np.zeros_like(sp)
+    o, d, p = _f32(origin), _f32(delta), _f32(initialpoint)
+    _check(lib.kiwi_eikonal_fmm(nx, ny, _fp(sp), _fp(o), _fp(d), _fp(p), _fp(times)))
+    return times
+
+
 def lmdif_batched(fcn, x0, m, ftol=None, xtol=None, gtol=0.0, maxfev=None, epsfcn=0.0, diag=None, mode=1, factor=100.0):
     """MINPACK lmdif (single precision) with the Jacobian columns evaluated as one batch (kiwi_lmdif_batched).
     fcn(xs[ncols, n]) -> fvecs[ncols, m] (rows may be returned short to signal a failure at that column).
