@@ -482,11 +482,13 @@ bool prep_eikonal(const float* p, bool mt_variant, float shortest_doi, double ol
         *iyc = (int)floorf((rc[1] - first[1]) / cdelta[1]) + 1;
         return !(*ixc < 1 || *iyc < 1 || *ixc > nxc || *iyc > nyc);   // else: "orphaned point in fine grid"
     };
+    std::vector<int> cell_of(speed.size(), -1);   // coarse cell of every valid fine point (the second pass below needs it again)
     for (size_t c = 0; c < speed.size(); c++) {   // iyf outer, ixf inner = linear order
         if (times[c] < 0.f) continue;
         int ixc, iyc;
         if (!coarse_cell(c, &ixc, &iyc)) continue;
         const size_t k = (size_t)(iyc - 1) * nxc + (ixc - 1);
+        cell_of[c] = (int)k;
         ntimes[k] = ntimes[k] + 1.f;
         if (ctimes[k] == -1.f) ctimes[k] = 0.f;
         ctimes[k] = ctimes[k] + times[c];
@@ -502,10 +504,8 @@ bool prep_eikonal(const float* p, bool mt_variant, float shortest_doi, double ol
         }
     for (size_t k = 0; k < nc; k++) cweights[k] = ntimes[k] / (float)npf;
     for (size_t c = 0; c < speed.size(); c++) {
-        if (times[c] < 0.f) continue;
-        int ixc, iyc;
-        if (!coarse_cell(c, &ixc, &iyc)) continue;
-        const size_t k = (size_t)(iyc - 1) * nxc + (ixc - 1);
+        if (cell_of[c] < 0) continue;
+        const size_t k = (size_t)cell_of[c];
         cdur[k] = cdur[k] + fabsf(times[c] - ctimes[k]);
     }
     for (size_t k = 0; k < nc; k++) if (ntimes[k] > 0.f) cdur[k] = 4.f / ntimes[k] * cdur[k];
