@@ -8,10 +8,13 @@ The names below resolve lazily so that `python -m kiwi_b200.build` can run befor
 library exists; anything else fails loudly if the library is missing (kiwi_b200/_lib.py).
 """
 __all__ = ["Engine", "Gfdb", "KiwiError", "SOURCE_TYPES", "NORMS", "KIWIBENCH_STF", "n_source_params",
-           "global_misfits", "lmdif_batched", "h5_root_members", "h5_read_root_dataset"]
+           "global_misfits", "lmdif_batched", "h5_root_members", "h5_read_root_dataset", "MisfitGrid"]
 
 
 def __getattr__(name):
+    if name == "MisfitGrid":
+        from .gridsearch import MisfitGrid
+        return MisfitGrid
     if name in __all__:
         from . import engine
         return getattr(engine, name)

@@ -186,6 +186,8 @@ class Engine:
         arr = (C.c_char_p * n)(*[c.encode() for c in components])
         _check(lib.kiwi_set_receivers(self._h, n, lat.ctypes.data_as(c_double_p), lon.ctypes.data_as(c_double_p), _fp(dep), arr))
         self._nreceivers = n
+        self._components = list(components)
+        self._enabled = [True] * n
 
     def set_receivers_file(self, path, has_depth=False):
         """set_receivers <file> [has_depth]: lat lon [depth] [components] per line (minimizer_engine.f90:165-286)."""
@@ -207,6 +209,7 @@ class Engine:
 
     def switch_receiver(self, ireceiver, state):
         _check(lib.kiwi_switch_receiver(self._h, ireceiver, int(bool(state))))
+        self._enabled[ireceiver - 1] = bool(state)
 
     def set_source_location(self, lat_deg, lon_deg, ref_time=0.0):
         _check(lib.kiwi_set_source_location(self._h, lat_deg, lon_deg, ref_time))
