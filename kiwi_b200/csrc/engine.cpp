@@ -230,9 +230,12 @@ int upload_receivers(kiwi_ctx* c) {
     return 0;
 }
 
+// references are read for the enabled receivers only (receiver_set_ref_seismogram returns at once for a disabled one, receiver.f90:764),
+// so they are required of those only
 bool all_refs_set(const kiwi_ctx* c) {
     for (const HostReceiver& h : c->rcv)
-        for (int k = 0; k < h.ncomp; k++) if (!h.has_ref[k]) return false;
+        if (h.enabled)
+            for (int k = 0; k < h.ncomp; k++) if (!h.has_ref[k]) return false;
     return true;
 }
 

@@ -466,6 +466,41 @@ class Engine:
         _check(lib.kiwi_get_probe(self._h, ireceiver, icomponent, wp, pr, first, n, _fp(buf), buf.size))
         return first.value, buf[:n.value].copy()
 
+    def set_synthetic_reference(self, scale=1.0):
+        """Calculate seismograms of the current source and use these as reference (seismosizer.py:523-527)."""
+        for ir, comps in enumerate(self._components, start=1):
+            if not self._enabled[ir - 1]:
+                continue
+            for ic in range(1, len(comps) + 1):
+                first, data = self.get_probe(ir, ic, "synthetics", "plain")
+                self.set_ref_seismogram(ir, ic, (first - 1) * self._dt(), data * np.float32(scale))
+
+    def get_receivers_snapshot(self, which_seismograms=("syn", "ref"), which_spectra=("syn", "ref"), which_processing="filtered"):
+        """Seismograms and amplitude spectra of all enabled receivers as the Python driver of the reference collects them through
+        output_seismograms / output_seismogram_spectra (seismosizer.py:541-610): a list (one dict per receiver, None for disabled
+        ones) with keys 'syn_seismograms', 'ref_seismograms' -> [(t0, dt, samples) per component] and 'syn_spectra',
+        'ref_spectra' -> [(df, amplitudes) per component]."""
+        dt = self._dt()
+        out = []
+        for ir, comps in enumerate(self._components, start=1):
+            if not self._enabled[ir - 1]:
+                out.append(None)
+                continue
+            rec = {}
+            for key, probe in (("syn", "synthetics"), ("ref", "references")):
+                if key in which_seismograms:
+                    rec[key + "_seismograms"] = []
+                    for ic in range(1, len(comps) + 1):
+                        first, data = self.get_probe(ir, ic, probe, which_processing)
+                        rec[key + "_seismograms"].append(((first - 1) * dt, dt, data))
+                if key in which_spectra:
+                    rec[key + "_spectra"] = [self.get_probe(ir, ic, probe, which_processing, spectrum=True) for ic in range(1, len(comps) + 1)]
+            out.append(rec)
+        return out
+
+    def _dt(self):
+        return self._db.meta()["dt"]
+
     def get_seismogram(self, ireceiver, icomponent, which=0):
         """In-memory replacement of output_seismograms: (first_index, samples)."""
         first, n = C.c_int(), C.c_int()

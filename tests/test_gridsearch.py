@@ -62,3 +62,28 @@ def test_grid_search_against_the_restatement(outer_norm, anarchy):
         assert np.array_equal(grid.bootstrap_sources[b], grid.sources[np.nanargmin(wb)])
     st = grid.stats["strike"]
     assert st.best == truth[5] and st.distribution.size == 64 and st.percentile16 <= truth[5] <= st.percentile84
+
+
+@pytest.mark.gpu
+def test_synthetic_reference_and_receivers_snapshot():
+    """set_synthetic_reference (seismosizer.py:523-527) and get_receivers_snapshot (:541-610) on the in-memory getters"""
+    from kiwi_b200 import Engine
+    comps = ["ned", "ar", "d"]
+    lat, lon, dep = sc.small_receivers(3)
+    g = Engine(0)
+    sc.setup(g, sc.small_db(), lat, lon, dep, comps)
+    g.set_source_params("bilateral", sc.BILAT_SMALL)
+    g.switch_receiver(2, False)
+    g.set_synthetic_reference()
+    g.set_misfit_filter([0.2, 0.5, 2.0, 3.0], [0, 1, 1, 0])
+    assert g.get_global_misfit() < 1e-6                       # the references are the synthetics (both go through one complex FFT)
+    p2 = sc.BILAT_SMALL.copy(); p2[5] += 25
+    g.set_source_params("bilateral", p2)
+    assert g.get_global_misfit() > 0.05
+    snap = g.get_receivers_snapshot()
+    assert snap[1] is None and len(snap[0]["syn_seismograms"]) == 3 and len(snap[2]["ref_spectra"]) == 1
+    t0, dt, syn = snap[0]["syn_seismograms"][0]
+    df, amp = snap[0]["syn_spectra"][0]
+    assert dt == pytest.approx(0.1) and syn.size > 20 and amp.size > 16 and df > 0 and np.argmax(amp) * df < 3.0
+    r0, _, ref = snap[0]["ref_seismograms"][0]
+    assert ref.size > 20 and not np.array_equal(ref[:10], syn[:10])
