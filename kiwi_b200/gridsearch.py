@@ -127,6 +127,54 @@ def global_misfit_of_one_source(block, components, enabled, receiver_weights=Non
     return float(np.sqrt(ms / ns)) if ns > 0. else float("nan")
 
 
+def merge_best(parts):
+    """parts[rank] = [[global candidate number or -1 per realisation], [its misfit or NaN]] -> (best, value) per realisation over all
+    ranks: the smallest non-NaN misfit, the lowest candidate number among equals (what nanargmin over the whole grid returns)"""
+    parts = np.asarray(parts, dtype=np.float64)
+    idx, val = parts[:, 0, :], parts[:, 1, :]
+    val = np.where((idx >= 0) & np.isfinite(val), val, np.inf)
+    key_idx = np.where(np.isfinite(val), idx, np.inf)
+    order = np.lexsort((key_idx, val), axis=0)[0]                       # per realisation: by misfit, then by candidate number
+    cols = np.arange(idx.shape[1])
+    best = np.where(np.isfinite(val[order, cols]), idx[order, cols], -1).astype(np.int64)
+    bestv = np.where(best >= 0, val[order, cols], np.nan)
+    return best, bestv
+
+
+def _world(group):
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(group), dist.get_rank(group)
+    except ImportError:
+        pass
+    return 1, 0
+
+
+def _all_gather(arr, group):
+    """[world, ...] of equally shaped float64 arrays (NCCL: through the GPU)"""
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64)).to(dev)
+    world = dist.get_world_size(group)
+    out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=torch.float64, device=dev)      # concatenated along the first axis
+    dist.all_gather_into_tensor(out, t, group=group)
+    return out.cpu().numpy().reshape((world,) + tuple(t.shape))
+
+
+def _gather_rows(local, shares, ns, group):
+    """local[k][n_local] per rank -> [k][ns] with every rank's columns at its candidates' places"""
+    width = max(len(i) for i in shares)
+    pad = np.full((local.shape[0], width), np.nan)
+    pad[:, :local.shape[1]] = local
+    g = _all_gather(pad, group)
+    out = np.full((local.shape[0], ns), np.nan)
+    for r, i in enumerate(shares):
+        out[:, i] = g[r][:, :len(i)]
+    return out
+
+
 class MisfitGrid:
     """Brute force grid search minimizer with built-in bootstrapping (gridsearch.py:112-305).
 
@@ -151,39 +199,67 @@ class MisfitGrid:
         self.status = self.ref_misfit = self.best_source = self.misfits_by_s = self.bootstrap_sources = self.stats = None
         self._engine = None
 
-    def compute(self, engine):
-        """Let the engine calculate the trace misfits (gridsearch.py:159-203): the whole grid in one batched call."""
+    def compute(self, engine, group=None, costs=None):
+        """Let the engine calculate the trace misfits (gridsearch.py:159-203): the whole grid in one batched call.  With an
+        initialised torch.distributed process group (one rank per GPU) every rank evaluates its share of the grid
+        (kiwi_b200.sharding.balanced_partition over `costs`, default equal costs); postprocess() then exchanges only per-candidate
+        global misfits and per-realisation best candidates."""
         self._engine = engine
         ref_block, ref_status = engine.eval_sources(self.sourcetype, self.ref_source)
         self._ref_block = ref_block.astype(np.float64)
-        self.status = engine.eval_sources_on_device(self.sourcetype, self.sources)      # failed sources: status != 0, NaN misfits
+        self._group, self._share = group, None
+        world, rank = _world(group)
+        if world > 1:
+            from .sharding import balanced_partition
+            c = np.ones(self.sources.shape[0]) if costs is None else np.asarray(costs, dtype=float)
+            self._shares = balanced_partition(c, world)
+            self._share = self._shares[rank]
+        mine = self.sources if self._share is None else np.ascontiguousarray(self.sources[self._share])
+        status = engine.eval_sources_on_device(self.sourcetype, mine) if mine.shape[0] else np.zeros(0, np.int32)   # failed: status != 0, NaN misfits
+        self._nlocal = mine.shape[0]
+        self.status = status if self._share is None else _gather_rows(status.astype(np.float64)[None, :], self._shares, self.sources.shape[0],
+                                                                   group)[0].astype(np.int32)
         self.best_source = self.misfits_by_s = self.bootstrap_sources = self.stats = None
 
-    def postprocess(self, receiver_weights=None, outer_norm="l2norm", anarchy=False, bootstrap_iterations=1000, seed=None, enabled=None):
+    def postprocess(self, receiver_weights=None, outer_norm="l2norm", anarchy=False, bootstrap_iterations=1000, seed=0, enabled=None):
         """Combine trace misfits to global misfits, find the best source, make statistics (gridsearch.py:205-219).
-        enabled: receiver mask (default: all receivers that have misfits, i.e. what the engine was configured with)."""
+        enabled: receiver mask (default: the receivers enabled in the engine).  seed: of the bootstrap draws (all ranks of a sharded
+        search must use the same)."""
         e = self._engine
         if e is None:
             raise RuntimeError("compute() first")
-        nrcv = e._nreceivers
         mask = np.asarray(e._enabled, dtype=bool) if enabled is None else (np.asarray(enabled, dtype=bool) & np.asarray(e._enabled, dtype=bool))
         w = None if receiver_weights is None else np.asarray(receiver_weights, dtype=np.float64)
         rng = np.random.default_rng(seed)
-        bw = bootstrap_weights(mask, w, bootstrap_iterations, rng) if bootstrap_iterations > 0 else None
-        out, best, bestv = e.outer_misfits(ns=self.sources.shape[0], receiver_weights=w, outer_norm=outer_norm, anarchy=anarchy, bweights=bw,
-                                           want_matrix=True)
-        self.ref_misfit = global_misfit_of_one_source(self._ref_block[0], e._components, [a and b for a, b in zip(e._enabled, mask)],
-                                                      receiver_weights=w, outer_norm=outer_norm, anarchy=anarchy)
-        self.misfits_by_s = out[0]
+        nb = int(bootstrap_iterations)
+        ns = self.sources.shape[0]
+        kw = dict(receiver_weights=w, outer_norm=outer_norm, anarchy=anarchy)
+        # two reductions of the cube on the device: the plain misfits of all candidates, and the best candidate of every bootstrap
+        # realisation (the [realisations x candidates] matrix never leaves the GPU)
+        if self._nlocal:
+            plain, best0, bestv0 = e.outer_misfits(ns=self._nlocal, want_matrix=True, **kw)
+            if nb > 0:
+                _, bestb, bestvb = e.outer_misfits(ns=self._nlocal, bweights=bootstrap_weights(mask, w, nb, rng), want_matrix=False, **kw)
+                best, bestv = np.concatenate([best0[:1], bestb[1:]]), np.concatenate([bestv0[:1], bestvb[1:]])
+            else:
+                best, bestv = best0[:1], bestv0[:1]
+        else:
+            plain, best, bestv = np.zeros((1, 0)), np.full(nb + 1, -1, np.int32), np.full(nb + 1, np.nan)
+        if self._share is not None:      # sharded: local -> global candidate numbers, then the best over the ranks
+            gbest = np.where(best >= 0, self._share[np.maximum(best, 0)] if self._nlocal else -1, -1).astype(np.float64)
+            plain = _gather_rows(plain[:1], self._shares, ns, self._group)
+            best, bestv = merge_best(_all_gather(np.stack([gbest, bestv]), self._group))
+        self.ref_misfit = global_misfit_of_one_source(self._ref_block[0], e._components, [a and b for a, b in zip(e._enabled, mask)], **kw)
+        self.misfits_by_s = plain[0]
         ibest = int(best[0]) if best[0] >= 0 else 0                      # gridsearch.py:255-257
         self.best_source = self.sources[ibest].copy()
         self.best_misfit = float(bestv[0])
-        self.bootstrap_sources = self.sources[np.maximum(best[1:], 0)] if bootstrap_iterations > 0 else self.sources[:0]
+        self.bootstrap_sources = self.sources[np.maximum(best[1:], 0)] if nb > 0 else self.sources[:0]
         names = PARAM_NAMES[self.sourcetype]
         self.stats = {}
         for p, gvalues in self.param_values:                             # gridsearch.py:285-294
             col = names.index(p)
-            dist = self.bootstrap_sources[:, col].astype(float) if bootstrap_iterations > 0 else np.array([self.best_source[col]], dtype=float)
+            dist = self.bootstrap_sources[:, col].astype(float) if nb > 0 else np.array([self.best_source[col]], dtype=float)
             self.stats[p] = MisfitGridStats(p, float(self.best_source[col]), dist, tested_values=gvalues)
         return self.best_source
 

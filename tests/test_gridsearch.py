@@ -87,3 +87,119 @@ def test_synthetic_reference_and_receivers_snapshot():
     assert dt == pytest.approx(0.1) and syn.size > 20 and amp.size > 16 and df > 0 and np.argmax(amp) * df < 3.0
     r0, _, ref = snap[0]["ref_seismograms"][0]
     assert ref.size > 20 and not np.array_equal(ref[:10], syn[:10])
+
+
+def test_merge_of_sharded_results():
+    from kiwi_b200.gridsearch import merge_best
+    nan = np.nan
+    best, val = merge_best([[[3, -1, 7, -1], [0.5, nan, 0.2, nan]], [[1, 4, 2, -1], [0.5, 0.9, 0.3, nan]]])
+    assert best.tolist() == [1, 4, 7, -1]                  # equal misfits: the lower candidate number, as nanargmin over the whole grid
+    assert val[:3].tolist() == [0.5, 0.9, 0.2] and np.isnan(val[3])
+
+
+def _gather_worker(rank, world, port, q):
+    import os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import torch.distributed as dist
+    from kiwi_b200.gridsearch import _gather_rows
+    from kiwi_b200.sharding import balanced_partition
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    shares = balanced_partition(np.arange(7, dtype=float), world)
+    local = np.stack([shares[rank] * 10.0, shares[rank] + 0.5])
+    out = _gather_rows(local, shares, 7, None)
+    q.put((rank, out.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_gather_of_sharded_rows_two_ranks_gloo():
+    import os
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, out in res:
+        assert out == [[0.0, 10.0, 20.0, 30.0, 40.0, 50.0, 60.0], [0.5, 1.5, 2.5, 3.5, 4.5, 5.5, 6.5]], (rank, out)
+
+
+def _sharded_worker(rank, world, port, q):
+    import os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests"))
+    import torch
+    import torch.distributed as dist
+    import scenario as sc_
+    from kiwi_b200 import Engine, MisfitGrid
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    comps = ["ned", "ar", "d", "neu"]
+    lat, lon, dep = sc_.small_receivers(4)
+    g = Engine(rank)
+    sc_.setup(g, sc_.small_db(), lat, lon, dep, comps)
+    truth = sc_.BILAT_SMALL.copy()
+    g.set_source_params("bilateral", truth)
+    g.set_synthetic_reference(scale=1.05)
+    ranges = [("strike", truth[5] - 30., truth[5] + 30., 10.), ("length-a", 1000., 5000., 1000.)]
+    grid = MisfitGrid("bilateral", truth, param_ranges=ranges)
+    grid.compute(g, costs=grid.sources[:, 9] + grid.sources[:, 10])
+    grid.postprocess(bootstrap_iterations=32, seed=7)
+    res = (grid.best_source.tolist(), grid.misfits_by_s.tolist(), grid.bootstrap_sources.tolist(), grid.status.tolist())
+    if rank == 0:      # the same search on one GPU
+        dist.barrier()
+        single = MisfitGrid("bilateral", truth, param_ranges=ranges)
+        g1 = Engine(0)
+        sc_.setup(g1, sc_.small_db(), lat, lon, dep, comps)
+        g1.set_source_params("bilateral", truth)
+        g1.set_synthetic_reference(scale=1.05)
+        block, status = g1.eval_sources("bilateral", single.sources)
+        q.put((rank, res, block.tolist()))
+    else:
+        dist.barrier()
+        q.put((rank, res, None))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+def test_sharded_grid_search_two_gpus():
+    import os
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    from kiwi_b200.gridsearch import bootstrap_weights
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 32500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=500) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, a, block), (r1, b, _) = res
+    assert a == b                                          # every rank ends with the same result
+    best, misfits, boots, status = a
+    block = np.array(block, dtype=np.float64)
+    m, n = cube_from_block(block, [True] * 4, [3, 2, 1, 3])
+    want, _ = make_global_misfits(m, n)
+    assert np.allclose(misfits, want, rtol=1e-12) and not any(status)
+    bw = bootstrap_weights([True] * 4, None, 32, np.random.default_rng(7))
+    from kiwi_b200.gridsearch import source_grid, mimainc_to_gvals
+    truth = sc.BILAT_SMALL
+    grid_sources = source_grid("bilateral", truth, [("strike", mimainc_to_gvals(truth[5] - 30., truth[5] + 30., 10.)), ("length-a", mimainc_to_gvals(1000., 5000., 1000.))])
+    assert np.array_equal(np.array(best, np.float32), grid_sources[np.nanargmin(want)])
+    for k in range(32):
+        wb, _ = make_global_misfits(m, n, bweights=bw[k][None, :])
+        assert np.array_equal(np.array(boots[k], np.float32), grid_sources[np.nanargmin(wb)])
