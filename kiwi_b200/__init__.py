@@ -13,7 +13,7 @@ __all__ = ["Engine", "Gfdb", "KiwiError", "SOURCE_TYPES", "NORMS", "KIWIBENCH_ST
 
 def __getattr__(name):
     if name == "MisfitGrid":
-        from .gridsearch import MisfitGrid
+        from .grid_search import MisfitGrid
         return MisfitGrid
     if name in __all__:
         from . import engine

@@ -1,5 +1,5 @@
 """Brute-force grid search with built-in bootstrapping on the batched engine: the driver the reference has in
-python/tunguska/gridsearch.py (`MisfitGrid`: compute / postprocess / stats, plotting left out), rebuilt on
+python/tunguska/gridsearch.py (`MisfitGrid`: compute / postprocess / stats, plotting left out), built anew on
 `Engine.eval_sources_on_device` + `Engine.outer_misfits`.
 
 Where the reference evaluates the grid one source at a time through the `minimizer` text pipe
@@ -29,20 +29,21 @@ PARAM_NAMES = {
 
 
 def mimainc_to_gvals(mi, ma, inc):
-    """gridsearch.py:18-22: the increment is adjusted so that the range is hit exactly"""
-    vmin, vmax, vinc = float(mi), float(ma), float(inc)
-    n = int(round((vmax - vmin) / vinc)) + 1
-    if n == 1:
-        return np.array([vmin], dtype=float)
-    vinc = (vmax - vmin) / (n - 1)
-    return np.array([vmin + i * vinc for i in range(n)], dtype=float)
+    """grid values from (min, max, increment) as the reference's driver makes them (python/tunguska/gridsearch.py:18-22): the number of
+    steps is rounded and the increment re-derived, so that both ends of the range are grid values"""
+    lo, hi = float(mi), float(ma)
+    nsteps = int(round((hi - lo) / float(inc)))
+    if nsteps == 0:
+        return np.array([lo])
+    return lo + np.arange(nsteps + 1) * ((hi - lo) / nsteps)
 
 
-def step_at(values, value):   # gridsearch.py:24-27
-    if len(values) <= 1:
+def step_at(values, value):
+    """width of the grid step that contains `value` (python/tunguska/gridsearch.py:24-27); 1 for a single grid value"""
+    if len(values) < 2:
         return 1.
-    i = np.clip(np.searchsorted(values, value), 1, len(values) - 1)
-    return values[i] - values[i - 1]
+    k = min(max(int(np.searchsorted(values, value)), 1), len(values) - 1)
+    return values[k] - values[k - 1]
 
 
 def source_grid(sourcetype, base_params, param_values):
@@ -81,10 +82,11 @@ class MisfitGridStats:
             self.percentile16_warn = self.percentile84_warn = False
 
     def str_best_and_confidence(self, factor=1., unit=''):
-        lw = ' (?)' if self.percentile16_warn else ''
-        uw = '(?) ' if self.percentile84_warn else ''
-        return '%s = %.3g %s  (confidence interval 68%%) = [ %.3g%s, %.3g %s] %s' % (
-            self.paramname.title(), self.best * factor, unit, self.percentile16 * factor, lw, self.percentile84 * factor, uw, unit)
+        """one line in the wording of the reference's reports (python/tunguska/gridsearch.py:66-73)"""
+        marks = (' (?)' if self.percentile16_warn else '', '(?) ' if self.percentile84_warn else '')
+        head = '%s = %.3g %s' % (self.paramname.title(), self.best * factor, unit)
+        interval = '[ %.3g%s, %.3g %s]' % (self.percentile16 * factor, marks[0], self.percentile84 * factor, marks[1])
+        return head + '  (confidence interval 68%) = ' + interval + ' ' + unit
 
 
 def bootstrap_weights(enabled, weights, iterations, rng):

@@ -1,4 +1,4 @@
-"""The grid-search driver (kiwi_b200/gridsearch.py, after python/tunguska/gridsearch.py MisfitGrid): grid construction and statistics
+"""The grid-search driver (kiwi_b200/grid_search.py, after python/tunguska/gridsearch.py MisfitGrid): grid construction and statistics
 on the CPU, the whole search on the GPU against the numpy restatement of make_global_misfits."""
 import numpy as np
 import pytest
@@ -8,7 +8,7 @@ from oracle_outer import cube_from_block, make_global_misfits
 
 
 def test_grid_construction_and_stats():
-    from kiwi_b200 import gridsearch as gs
+    from kiwi_b200 import grid_search as gs
     assert np.allclose(gs.mimainc_to_gvals(0., 1., 0.3), [0., 1. / 3, 2. / 3, 1.])       # the increment is adjusted (gridsearch.py:18-22)
     assert gs.mimainc_to_gvals(5., 5., 1.).tolist() == [5.]
     g = gs.source_grid("bilateral", sc.BILAT_SMALL, [("strike", [10., 20., 30.]), ("depth", [1e3, 2e3])])
@@ -32,7 +32,7 @@ def test_grid_construction_and_stats():
 @pytest.mark.parametrize("outer_norm,anarchy", [("l2norm", False), ("l1norm", True)])
 def test_grid_search_against_the_restatement(outer_norm, anarchy):
     from kiwi_b200 import Engine, MisfitGrid
-    from kiwi_b200.gridsearch import bootstrap_weights
+    from kiwi_b200.grid_search import bootstrap_weights
     from oracle_lib import OracleEngine
     comps = ["ned", "ar", "d", "neu", "cl", "wsd"]
     lat, lon, dep = sc.small_receivers(6)
@@ -90,7 +90,7 @@ def test_synthetic_reference_and_receivers_snapshot():
 
 
 def test_merge_of_sharded_results():
-    from kiwi_b200.gridsearch import merge_best
+    from kiwi_b200.grid_search import merge_best
     nan = np.nan
     best, val = merge_best([[[3, -1, 7, -1], [0.5, nan, 0.2, nan]], [[1, 4, 2, -1], [0.5, 0.9, 0.3, nan]]])
     assert best.tolist() == [1, 4, 7, -1]                  # equal misfits: the lower candidate number, as nanargmin over the whole grid
@@ -102,7 +102,7 @@ def _gather_worker(rank, world, port, q):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, root)
     import torch.distributed as dist
-    from kiwi_b200.gridsearch import _gather_rows
+    from kiwi_b200.grid_search import _gather_rows
     from kiwi_b200.sharding import balanced_partition
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
     shares = balanced_partition(np.arange(7, dtype=float), world)
@@ -177,7 +177,7 @@ def test_sharded_grid_search_two_gpus():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     import torch.multiprocessing as mp
-    from kiwi_b200.gridsearch import bootstrap_weights
+    from kiwi_b200.grid_search import bootstrap_weights
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 32500 + (os.getpid() % 2000)
@@ -196,7 +196,7 @@ def test_sharded_grid_search_two_gpus():
     want, _ = make_global_misfits(m, n)
     assert np.allclose(misfits, want, rtol=1e-12) and not any(status)
     bw = bootstrap_weights([True] * 4, None, 32, np.random.default_rng(7))
-    from kiwi_b200.gridsearch import source_grid, mimainc_to_gvals
+    from kiwi_b200.grid_search import source_grid, mimainc_to_gvals
     truth = sc.BILAT_SMALL
     grid_sources = source_grid("bilateral", truth, [("strike", mimainc_to_gvals(truth[5] - 30., truth[5] + 30., 10.)), ("length-a", mimainc_to_gvals(1000., 5000., 1000.))])
     assert np.array_equal(np.array(best, np.float32), grid_sources[np.nanargmin(want)])
