@@ -81,3 +81,30 @@ def test_near_field_static_offset_is_stored_as_last_sample():
     i = ((8 - 1) * m["nz"] + (6 - 1)) * 10 + 0
     tr = data[offset[i]:offset[i] + length[i]]
     assert tr[-1] != 0.0 and abs(tr[-1] - tr[-2]) < 1e-3 * abs(tr[-1])   # static displacement reached
+
+
+def test_reference_round_trip_known_answer(tmp_path):
+    """test_gfdb.f90:33-80: a 2-chunk 3 x 2 x 8 database, one trace of two strips [11,17] = 1 0 0 0 1 1 1 and [23,24] = 1 1 saved at
+    (1, 2, 2) and recovered -- here through the host container, the KGF1 file and (via the independent writer) Kiwi's HDF5 layout;
+    the container holds the trace densely over its span with the gap between the strips as zeros"""
+    import h5mini_writer as h5w
+    s1, s2 = np.array([1, 0, 0, 0, 1, 1, 1], np.float32), np.array([1, 1], np.float32)
+    dense = np.zeros(24 - 11 + 1, np.float32)
+    dense[0:7] = s1; dense[23 - 11:] = s2
+    db = Gfdb.create(3, 2, 8, 1.0, 1.0, 1.0, 0.0, 0.0)
+    db.save_array(1, 2, 2, 11, dense)
+    path = tmp_path / "test-db.kgf1"
+    db.write(path)
+    h5w.write_kiwi_gfdb(str(tmp_path / "test-db"), 3, 2, 8, 1.0, 1.0, 1.0, 0.0, 0.0, 2, {(1, 2, 2): [(11, s1), (23, s2)]})     # nchunks = 2
+    for got in (db, Gfdb.read(path), Gfdb.read_hdf(str(tmp_path / "test-db"))):
+        m = got.meta()
+        assert (m["nx"], m["nz"], m["ng"]) == (3, 2, 8) and m["ntraces"] == 1            # "reopen index"
+        span0, length, offset, data = got.view()
+        i = ((1 - 1) * 2 + (2 - 1)) * 8 + (2 - 1)
+        assert (span0[i], length[i]) == (11, 14)
+        assert np.array_equal(data[offset[i]:offset[i] + 14], dense)                      # "recover 2" .. "recover 5"
+        assert length[((2 - 1) * 2 + (2 - 1)) * 8 + 1] == 0                               # a trace that was never saved stays absent
+    o = OracleEngine()
+    o.set_database(db)
+    (a, b), nstrips = o.trace_span(1, 2, 2)
+    assert (a, b, nstrips) == (11, 24, 1)      # same span; one strip: a gap of 5 zeros does not exceed maxgap (sparse_trace.f90:24, :466-470)
