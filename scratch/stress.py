@@ -1,5 +1,10 @@
+"""Stress of the first evaluation of fresh engine contexts under concurrent load (run several copies at once on one GPU):
+    for i in 1 2 3 4; do python scratch/stress.py 60 340 161 & done; wait
+Every repetition builds a new engine, evaluates a seeded random case (tests/test_random_parity_gpu.py) twice and compares with the
+oracle; a mismatch of the FIRST evaluation only is how the stream-ordering bug of profiles/r01_sanitizer.md showed."""
 import sys, os
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import scenario as sc
 import test_random_parity_gpu as t
