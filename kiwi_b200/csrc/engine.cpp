@@ -124,6 +124,7 @@ struct kiwi_ctx {
     bool mt_grid_enabled = true;             // point moment-tensor grid searches go through the tcgen05 contraction
     DevBuf d_map, d_status_out;
     DevBuf d_taprec;              // shift table of the current batch (k_tap_table)
+    DevBuf d_partial;             // running strip sums of the depth bands of k_synth
     DevBuf d_gm;                  // ground-motion values [cand][rcv][3]
     DevBuf d_xcorr;               // cross-correlations [rcv][component][shift] (autoshift_ref_seismogram)
     bool dedup_enabled = true;               // candidates that differ only in the moment share one synthesis
@@ -603,6 +604,8 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         while (nwarps > 1 && synth_smem_bytes(nwarps, nq) > (size_t)112 * 1024) nwarps--;   // two CTAs per SM
         if (synth_smem_bytes(nwarps, nq) > (size_t)220 * 1024)
             return kiwi_set_error("synthetic window of %d samples does not fit the shared-memory accumulators", tmax);
+        int nbands = 1;
+        if (const char* ev = getenv("KIWI_SYNTH_BANDS")) nbands = std::max(1, atoi(ev));
         const size_t per_cand_seis = (size_t)nrcv * KIWI_MAX_COMP * seis_stride * sizeof(float);
         int sub = (int)std::max<size_t>(1, std::min<size_t>((size_t)nc, (c->work_budget / 2) / std::max<size_t>(per_cand_seis, 1)));
         if (sub < nc) sub = std::max(align, sub / align * align);
@@ -619,9 +622,11 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
             const size_t poff = (size_t)s0 * nrcv;
             cudaEventRecord(c->ev[3], st);
             if (tmax > 0) {
+                if (nbands > 1) CU_OK(c->d_partial.ensure(synth_partial_bytes(nq) * (size_t)ns_ * nrcv));
                 cudaError_t e = launch_synth(c->db, c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>() + s0, ns_, g,
                                              c->d_recs.as<GeoRec>() + poff * rec_stride, rec_stride, c->d_hdrs.as<PairHdr>() + poff, nq, margin_q,
-                                             nwarps, c->d_seis.as<float>(), seis_stride, c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, st);
+                                             nwarps, c->d_seis.as<float>(), seis_stride, c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, nbands,
+                                             c->d_partial.as<float>(), st);
                 if (e != cudaSuccess) return kiwi_set_error("CUDA error launching synthesis: %s", cudaGetErrorString(e));
                 c->launches[2] += 1;
                 if (max_rise > 0.f) {
@@ -837,7 +842,7 @@ void kiwi_destroy(kiwi_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->d_slabs, &c->d_nodes, &c->d_tspan, &c->d_rcv, &c->d_refdata, &c->d_taper, &c->d_cands, &c->d_bilat, &c->d_gf, &c->d_gi,
-                      &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift, &c->d_map, &c->d_status_out, &c->d_taprec, &c->d_gm, &c->d_xcorr, &c->d_mtlocs, &c->d_mts, &c->d_candof, &c->d_orc, &c->d_orw, &c->d_obw, &c->d_oout, &c->d_obest, &c->d_obestv})
+                      &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift, &c->d_map, &c->d_status_out, &c->d_taprec, &c->d_partial, &c->d_gm, &c->d_xcorr, &c->d_mtlocs, &c->d_mts, &c->d_candof, &c->d_orc, &c->d_orw, &c->d_obw, &c->d_oout, &c->d_obest, &c->d_obestv})
         b->release();
     c->h_stage.release(); c->h_out.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);

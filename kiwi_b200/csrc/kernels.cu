@@ -472,9 +472,18 @@ __device__ __forceinline__ void cp_async16s(unsigned smem_addr, const void* gmem
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// The order in which a CTA walks the groups of its candidate.  ny == 0: all of them, as listed.  ny > 0 (the groups form an
+// nx x ny lattice listed with the second index fastest, source_bilat.f90:349-371): only the lattice rows [row0, row0 + rows) --
+// sub-faults of (nearly) one depth, i.e. of a few depth rows of the database -- so that all CTAs of a launch work on a slice of the
+// database that stays resident in L2.
+struct GroupWalk {
+    int n;              // groups walked
+    int ny, row0, rows;
+    __device__ __forceinline__ int rec(int idx) const { return ny > 0 ? (idx / rows) * ny + row0 + idx % rows : idx; }
+};
 // copy of one 128-byte group record (lanes 0..7, 16 bytes each); not committed here
-__device__ __forceinline__ void rec_copy_async(const GeoRec* __restrict__ recs, int ip, int ngroups, GeoRec* dst_slot, int lane) {
-    if (ip < ngroups && lane < 8) cp_async16(reinterpret_cast<uint4*>(dst_slot) + lane, reinterpret_cast<const uint4*>(recs + ip) + lane);
+__device__ __forceinline__ void rec_copy_async(const GeoRec* __restrict__ recs, int idx, const GroupWalk& gw, GeoRec* dst_slot, int lane) {
+    if (idx < gw.n && lane < 8) cp_async16(reinterpret_cast<uint4*>(dst_slot) + lane, reinterpret_cast<const uint4*>(recs + gw.rec(idx)) + lane);
 }
 
 // GF components a receiver with horizontal (H) / vertical (V) components needs, in the reference's order of
@@ -567,7 +576,7 @@ __device__ __forceinline__ void make_pairs(const Q2& P, const Q2& A, u64* E, u64
 
 // One warp works through its share of the groups of one (candidate, receiver) pair.
 template <bool H, bool V, bool NG10>
-__device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __restrict__ myrecs, int ngroups, const float4* __restrict__ taprec,
+__device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __restrict__ myrecs, const GroupWalk walk, const float4* __restrict__ taprec,
                                            float sd, unsigned acc_s /* shared address of the warp's strips */, unsigned strip_bytes,
                                            float* __restrict__ step, int nq, int baseq, GeoRec* slot /* [3] */,
                                            unsigned ring_s /* shared address of the warp's ring */, int warp, int nwarps, int lane, float nz) {
@@ -575,8 +584,9 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
     constexpr int N = Seq::N, S = SYN_STAGES;
     static_assert(N >= S && S == 3, "ring depth");
     // records of the first two groups synchronously; from then on two groups ahead
-    rec_copy_async(myrecs, warp, ngroups, slot, lane);
-    rec_copy_async(myrecs, warp + nwarps, ngroups, slot + 1, lane);
+    const int ngroups = walk.n;
+    rec_copy_async(myrecs, warp, walk, slot, lane);
+    rec_copy_async(myrecs, warp + nwarps, walk, slot + 1, lane);
     cp_async_commit();
     cp_async_wait<0>();
     __syncwarp();
@@ -589,7 +599,7 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
     int sl = 0;             // slot of the current group's record
     for (int ip = warp; ip < ngroups; ip += nwarps, sl = (sl == 2 ? 0 : sl + 1)) {
         // record of the group after next; rides in the next commit group
-        rec_copy_async(myrecs, ip + 2 * nwarps, ngroups, slot + (sl == 0 ? 2 : sl - 1), lane);
+        rec_copy_async(myrecs, ip + 2 * nwarps, walk, slot + (sl == 0 ? 2 : sl - 1), lane);
         const GeoRec* rec = slot + sl;
         const int flags = rec->flags;
         if (flags & GEO_SKIP) {   // (never primed: the look-ahead does not cross skipped groups)
@@ -739,7 +749,8 @@ __global__ void __launch_bounds__(256, 2) k_synth(GfdbDev db, const ReceiverDev*
                                                    const CandDev* __restrict__ cands, GroupSoA g, const GeoRec* __restrict__ recs,
                                                    size_t rec_stride, const PairHdr* __restrict__ hdrs, int nq_alloc, int margin_q,
                                                    float* __restrict__ seis, size_t seis_stride /* floats per component row */,
-                                                   SeisHdr* __restrict__ shdrs, float neg_zero /* -0.0f, see make_pairs */) {
+                                                   SeisHdr* __restrict__ shdrs, float neg_zero /* -0.0f, see make_pairs */,
+                                                   int band, int nbands, float4* __restrict__ partial /* [pair][3*nq float4 + 3*nq float] */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // CTAs that run at the same time work on the same receiver for neighbouring candidates: candidates of a grid search
     // that share (part of) their sub-fault geometry then find each other's Green's function rows in L2
@@ -754,6 +765,18 @@ __global__ void __launch_bounds__(256, 2) k_synth(GfdbDev db, const ReceiverDev*
     if (H.T <= 0 || !R.enabled) {
         if (threadIdx.x < KIWI_MAX_COMP) { SeisHdr e; e.lo = 0; e.hi = -1; e.base = 0; e.pad = 0; myshdr[threadIdx.x] = e; }
         return;
+    }
+    // depth bands (nbands > 1): this launch adds the lattice rows [ny*band/nbands, ny*(band+1)/nbands) of every candidate to the
+    // pair's partial strips; a candidate whose groups are no nx x ny lattice is done completely by band 0
+    GroupWalk walk;
+    walk.n = cand.ngroups; walk.ny = 0; walk.row0 = 0; walk.rows = 1;
+    if (nbands > 1) {
+        if (cand.ny > 0 && cand.nx * cand.ny == cand.ngroups) {
+            walk.ny = cand.ny; walk.row0 = (int)(((long long)cand.ny * band) / nbands);
+            walk.rows = (int)(((long long)cand.ny * (band + 1)) / nbands) - walk.row0;
+            walk.n = cand.nx * walk.rows;
+            if (walk.rows <= 0) { walk.rows = 1; walk.n = 0; }
+        } else if (band > 0) walk.n = 0;
     }
     const int base = floor4(H.out0) - 4 * margin_q;   // room on the left for the rise-time fold (k_fold)
     const int baseq = base >> 2;
@@ -780,7 +803,7 @@ __global__ void __launch_bounds__(256, 2) k_synth(GfdbDev db, const ReceiverDev*
     const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
 
 #define KIWI_SYNTH(HH, VV, NG) \
-    synth_warp<HH, VV, NG>(db, myrecs, cand.ngroups, g.taprec, R.sd, (unsigned)__cvta_generic_to_shared(acc), (unsigned)nq * 16u, step, nq, baseq, slot, ring_s, warp, nwarps, lane, neg_zero)
+    synth_warp<HH, VV, NG>(db, myrecs, walk, g.taprec, R.sd, (unsigned)__cvta_generic_to_shared(acc), (unsigned)nq * 16u, step, nq, baseq, slot, ring_s, warp, nwarps, lane, neg_zero)
     if (need_h && need_v) { if (ng10) KIWI_SYNTH(true, true, true); else KIWI_SYNTH(true, true, false); }
     else if (need_h) { if (ng10) KIWI_SYNTH(true, false, true); else KIWI_SYNTH(true, false, false); }
     else if (need_v) { if (ng10) KIWI_SYNTH(false, true, true); else KIWI_SYNTH(false, true, false); }
@@ -800,6 +823,22 @@ __global__ void __launch_bounds__(256, 2) k_synth(GfdbDev db, const ReceiverDev*
         float st = step_all[i];
         for (int w = 1; w < nwarps; w++) st += step_all[(size_t)w * 3 * nq + i];
         step_all[i] = st;
+    }
+    if (nbands > 1) {   // running sums of the bands in global memory (one CTA per pair and launch, launches in stream order)
+        float4* pacc = partial + (size_t)pair * (3 * (size_t)nqs + (3 * (size_t)nq + 3) / 4);
+        float* pstep = reinterpret_cast<float*>(pacc + 3 * (size_t)nqs);
+        __syncthreads();
+        for (int i = threadIdx.x; i < 3 * nqs; i += blockDim.x) {
+            float4 s = acc_all[i];
+            if (band > 0) { const float4 v = pacc[i]; s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+            if (band + 1 < nbands) pacc[i] = s; else acc_all[i] = s;
+        }
+        for (int i = threadIdx.x; i < 3 * nq; i += blockDim.x) {
+            float st = step_all[i];
+            if (band > 0) st += pstep[i];
+            if (band + 1 < nbands) pstep[i] = st; else step_all[i] = st;
+        }
+        if (band + 1 < nbands) return;
     }
     __syncthreads();
     // inclusive prefix sum of the steps over quads, one warp per strip
@@ -1888,13 +1927,16 @@ size_t synth_smem_bytes(int nwarps, int nq) {
     return (size_t)nwarps * 3 * nq * (sizeof(float4) + sizeof(float)) + 16 + (size_t)nwarps * 3 * sizeof(GeoRec) +
            (size_t)nwarps * SYN_STAGES * 4 * 32 * sizeof(float4);
 }
+size_t synth_partial_bytes(int nq) { return (3 * (size_t)nq + (3 * (size_t)nq + 3) / 4) * sizeof(float4); }
 cudaError_t launch_synth(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, const GeoRec* recs,
                          size_t rec_stride, const PairHdr* hdrs, int nq_alloc, int margin_q, int nwarps, float* seis, size_t seis_stride,
-                         SeisHdr* shdrs, cudaStream_t st) {
+                         SeisHdr* shdrs, int nbands, float* partial, cudaStream_t st) {
     size_t smem = synth_smem_bytes(nwarps, nq_alloc);
     cudaError_t e = cudaFuncSetAttribute(k_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_synth<<<ncand * nrcv, nwarps * 32, smem, st>>>(db, rcv, nrcv, cands, g, recs, rec_stride, hdrs, nq_alloc, margin_q, seis, seis_stride, shdrs, -0.0f);
+    for (int band = 0; band < nbands; band++)
+        k_synth<<<ncand * nrcv, nwarps * 32, smem, st>>>(db, rcv, nrcv, cands, g, recs, rec_stride, hdrs, nq_alloc, margin_q, seis, seis_stride, shdrs, -0.0f,
+                                                         band, nbands, reinterpret_cast<float4*>(partial));
     return cudaGetLastError();
 }
 void launch_misfit_td(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, const float* seis, size_t seis_stride,

@@ -22,9 +22,10 @@ void launch_expand_centroids(CandDev cand, GroupSoA g, TapSoA taps, int ngroups_
 void launch_geometry(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, int ngroups_total,
                      int interpolate, int xunder, int zunder, GeoRec* recs, size_t rec_stride, PairHdr* hdrs, int* tmax, cudaStream_t st);
 size_t synth_smem_bytes(int nwarps, int nq);
+size_t synth_partial_bytes(int nq);   // per (candidate, receiver): running sums of the depth bands (nbands > 1)
 cudaError_t launch_synth(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, const GeoRec* recs,
                          size_t rec_stride, const PairHdr* hdrs, int nq_alloc, int margin_q, int nwarps, float* seis, size_t seis_stride,
-                         SeisHdr* shdrs, cudaStream_t st);
+                         SeisHdr* shdrs, int nbands, float* partial, cudaStream_t st);
 cudaError_t launch_fold(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, float* seis, size_t seis_stride, SeisHdr* shdrs,
                         float dt, cudaStream_t st);
 void launch_misfit_td(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, const float* seis, size_t seis_stride,
