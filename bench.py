@@ -155,12 +155,15 @@ def configure(eng, db, w, rlat, rlon, rdep):
 
 def set_references(src, engines, nrcv, dt, scale=1.07):
     """reference = synthetics of the base source with +7 % moment."""
+    # (all traces are fetched before the first one is set: setting a reference on `src` itself invalidates its evaluation)
+    REFS.clear()
     for ir in range(1, nrcv + 1):
         for ic in range(1, 4):
             first, data = src.get_seismogram(ir, ic, 1)
             REFS[(ir, ic)] = (first, data * np.float32(scale))
-            for e in engines:
-                e.set_ref_seismogram(ir, ic, (first - 1) * dt, REFS[(ir, ic)][1])
+    for (ir, ic), (first, data) in REFS.items():
+        for e in engines:
+            e.set_ref_seismogram(ir, ic, (first - 1) * dt, data)
 
 
 REFS = {}

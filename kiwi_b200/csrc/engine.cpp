@@ -125,6 +125,9 @@ struct kiwi_ctx {
     DevBuf d_map, d_status_out;
     DevBuf d_taprec;              // shift table of the current batch (k_tap_table)
     DevBuf d_partial;             // running strip sums of the depth bands of k_synth
+    size_t l2_bytes = 0;          // cudaDevAttrL2CacheSize (choose_bands)
+    double rcv_dmin = 0., rcv_dmax = 0., rcv_depmin = 0., rcv_depmax = 0.;   // distance / depth range of the enabled receivers (upload_receivers)
+    size_t slab_floats = 0;       // floats of the database slabs in HBM
     DevBuf d_gm;                  // ground-motion values [cand][rcv][3]
     DevBuf d_xcorr;               // cross-correlations [rcv][component][shift] (autoshift_ref_seismogram)
     bool dedup_enabled = true;               // candidates that differ only in the moment share one synthesis
@@ -218,6 +221,11 @@ int upload_receivers(kiwi_ctx* c) {
         for (int k = 0; k < r.nfp; k++) { r.fpx[k] = h.filter_x[k]; r.fpy[k] = h.filter_y[k]; }
     }
     c->nmisfits = nm;
+    c->rcv_dmin = c->rcv_depmin = 1e300; c->rcv_dmax = c->rcv_depmax = -1e300;   // (all receivers, enabled or not: see choose_bands)
+    for (int i = 0; i < n; i++) {
+        c->rcv_dmin = std::min(c->rcv_dmin, c->h_rcvdev[i].dist0); c->rcv_dmax = std::max(c->rcv_dmax, c->h_rcvdev[i].dist0);
+        c->rcv_depmin = std::min(c->rcv_depmin, (double)c->h_rcvdev[i].depth); c->rcv_depmax = std::max(c->rcv_depmax, (double)c->h_rcvdev[i].depth);
+    }
     if (refdata.empty()) refdata.push_back(0.f);
     if (taperdata.empty()) taperdata.push_back(0.f);
     CU_OK(c->d_rcv.ensure(sizeof(ReceiverDev) * std::max(n, 1)));
@@ -267,6 +275,76 @@ int prep_candidate(kiwi_ctx* c, int sourcetype, const float* p, float effective_
         return 0;
     }
     return 1;
+}
+
+// Depth bands of k_synth.  A launch over all groups of its candidates gathers from the whole depth range of the sources: for a
+// database larger than L2 every (candidate, receiver) pair then streams its node blocks from HBM although the launch as a whole
+// touches each of them hundreds of times (2000 receivers x 1470 sub-faults x 4 corners over ~4e4 distinct nodes at config C5).
+// Launching band by band -- the sub-faults of a few depth rows at a time -- keeps the slice of the database a launch touches
+// resident in L2.  The band count of a candidate is the smallest one whose largest slice (distinct depth rows of the database its
+// groups touch x bytes per depth row x fraction of the distance range the receivers span) fits a third of L2 (candidates of a search
+// that run side by side differ in depth, so two or three such slices are live at a time), with at least 16 groups per warp and
+// band.  It depends on the candidate, the database and the receivers only: a candidate's result (the order of its partial sums)
+// does not depend on what else is in the batch.  KIWI_SYNTH_BANDS=n forces n.
+int choose_bands(kiwi_ctx* c, const kh::SourcePrep& sp, int nwarps) {
+    if (sp.ngroups <= 0) return 1;
+    if (const char* ev = getenv("KIWI_SYNTH_BANDS")) { const int v = atoi(ev); if (v > 0) return v; }
+    const GfdbDev& db = c->db;
+    if (c->l2_bytes == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, c->device) != cudaSuccess || v <= 0) v = 32 << 20;
+        c->l2_bytes = (size_t)v;
+    }
+    const double slab_bytes = (double)c->slab_floats * 4.0;
+    if (slab_bytes < 0.8 * (double)c->l2_bytes || db.nz <= 0) return 1;
+    const bool lattice = !sp.explicit_groups && sp.ny > 1 && sp.nx * sp.ny == sp.ngroups;
+    const int rows = lattice ? sp.ny : sp.ngroups;
+    const int maxbands = std::min(rows, sp.ngroups / std::max(1, 16 * nwarps));
+    if (maxbands < 2) return 1;
+    // depth of every group, horizontal reach of the source
+    std::vector<float> depth((size_t)sp.ngroups);
+    double rmax = 0.;
+    if (sp.explicit_groups) {
+        for (int k = 0; k < sp.ngroups; k++) { depth[k] = sp.g_depth[k]; rmax = std::max(rmax, (double)hypotf(sp.g_north[k], sp.g_east[k])); }
+    } else if (lattice) {   // source_bilat.f90:349-377 (positions only; exactness is not needed here)
+        const float length = sp.p[9] + sp.p[10], width = sp.p[11];
+        for (int ix = 0; ix < sp.nx; ix++)
+            for (int iy = 0; iy < sp.ny; iy++) {
+                const float g0 = (2.f * ix - sp.nx + 1.f) / (2.f * sp.nx) * length, g1 = (2.f * iy - sp.ny + 1.f) / (2.f * sp.ny) * width;
+                depth[(size_t)ix * sp.ny + iy] = sp.rot_rup[6] * g0 + sp.rot_rup[7] * g1 + sp.p[3];
+                rmax = std::max(rmax, (double)hypotf(sp.rot_rup[0] * g0 + sp.rot_rup[1] * g1 + sp.p[1], sp.rot_rup[3] * g0 + sp.rot_rup[4] * g1 + sp.p[2]));
+            }
+    } else return 1;
+    const double xlo = std::max((double)db.firstx, c->rcv_dmin - rmax), xhi = std::min((double)db.firstx + (double)db.dx * db.nx, c->rcv_dmax + rmax);
+    const double xfrac = std::min(1.0, std::max(0.05, (xhi - xlo) / ((double)db.dx * db.nx)));
+    const double row_bytes = slab_bytes / db.nz * xfrac;
+    const double budget = 0.33 * (double)c->l2_bytes;
+    std::vector<char> mark((size_t)db.nz);
+    int best = 1;
+    for (int nb : {1, 2, 3, 4, 5, 6, 8, 10, 12, 15, 16, 20, 24, 32}) {
+        if (nb > maxbands) break;
+        best = nb;
+        double worst = 0.;
+        for (int b = 0; b < nb; b++) {
+            std::fill(mark.begin(), mark.end(), 0);
+            auto touch = [&](float d) {
+                const int z0 = (int)floor(((double)d - c->rcv_depmax - db.firstz) / db.dz), z1 = (int)floor(((double)d - c->rcv_depmin - db.firstz) / db.dz) + 1;
+                for (int z = std::max(z0, 0); z <= std::min(z1, db.nz - 1); z++) mark[z] = 1;
+            };
+            if (lattice) {
+                const int r0 = (int)((long long)rows * b / nb), r1 = (int)((long long)rows * (b + 1) / nb);
+                for (int iy = r0; iy < r1; iy++) { touch(depth[iy]); touch(depth[(size_t)(sp.nx - 1) * rows + iy]); }
+            } else {
+                const int k0 = (int)((long long)sp.ngroups * b / nb), k1 = (int)((long long)sp.ngroups * (b + 1) / nb);
+                for (int k = k0; k < k1; k++) touch(depth[k]);
+            }
+            int cnt = 0;
+            for (char m : mark) cnt += m;
+            worst = std::max(worst, cnt * row_bytes);
+        }
+        if (worst <= budget) break;
+    }
+    return best;
 }
 
 // called after the synthesis of every sub-chunk when the caller consumes the synthetics itself
@@ -476,6 +554,7 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
             cd.group_begin = G; cd.ngroups = sp.ngroups; cd.tap_begin = Tp;
             cd.ntaps_total = (int)sp.toff.size();
             cd.moment = sp.moment; cd.risetime = sp.risetime; cd.nx = sp.nx; cd.ny = sp.ny; cd.nt = sp.nt;
+            cd.walk_ny = (!sp.explicit_groups && sp.ny > 1 && sp.nx * sp.ny == sp.ngroups) ? sp.ny : 0; cd.nbands = 1;
             cd.status = bad[b0 + i] ? KIWI_STATUS_BAD_PARAMS : KIWI_STATUS_OK;
             G += sp.ngroups; Tp += (int)sp.toff.size();
             rec_stride = std::max(rec_stride, (size_t)sp.ngroups);
@@ -604,8 +683,16 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         while (nwarps > 1 && synth_smem_bytes(nwarps, nq) > (size_t)112 * 1024) nwarps--;   // two CTAs per SM
         if (synth_smem_bytes(nwarps, nq) > (size_t)220 * 1024)
             return kiwi_set_error("synthetic window of %d samples does not fit the shared-memory accumulators", tmax);
-        int nbands = 1;
-        if (const char* ev = getenv("KIWI_SYNTH_BANDS")) nbands = std::max(1, atoi(ev));
+        int nbands = 1;   // launches: the largest band count of a candidate of this chunk
+        {
+            bool changed = false;
+            for (int i = 0; i < nc; i++) {
+                const int nb = cands[i].status == KIWI_STATUS_OK ? choose_bands(c, prep[b0 + i], 8) : 1;
+                if (nb != cands[i].nbands) { cands[i].nbands = nb; changed = true; }
+                nbands = std::max(nbands, nb);
+            }
+            if (changed) CU_OK(cudaMemcpyAsync(c->d_cands.p, cands.data(), sizeof(CandDev) * nc, cudaMemcpyHostToDevice, st));
+        }
         const size_t per_cand_seis = (size_t)nrcv * KIWI_MAX_COMP * seis_stride * sizeof(float);
         int sub = (int)std::max<size_t>(1, std::min<size_t>((size_t)nc, (c->work_budget / 2) / std::max<size_t>(per_cand_seis, 1)));
         if (sub < nc) sub = std::max(align, sub / align * align);
@@ -878,7 +965,7 @@ int kiwi_set_database(kiwi_ctx* c, kiwi_gfdb* db) {
         total += (unsigned long long)ni.wn * ng;
         tmin = std::min(tmin, lo); tmax = std::max(tmax, hi);
     }
-    c->db_tmin = tmin; c->db_tmax = tmax;
+    c->db_tmin = tmin; c->db_tmax = tmax; c->slab_floats = (size_t)total;
     // fill the slabs through a bounded pinned staging buffer
     CU_OK(c->d_slabs.ensure(sizeof(float) * std::max<unsigned long long>(total, 4)));
     CU_OK(c->d_nodes.ensure(sizeof(NodeInfo) * nnodes));

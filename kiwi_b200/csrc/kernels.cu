@@ -472,14 +472,14 @@ __device__ __forceinline__ void cp_async16s(unsigned smem_addr, const void* gmem
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// The order in which a CTA walks the groups of its candidate.  ny == 0: all of them, as listed.  ny > 0 (the groups form an
-// nx x ny lattice listed with the second index fastest, source_bilat.f90:349-371): only the lattice rows [row0, row0 + rows) --
-// sub-faults of (nearly) one depth, i.e. of a few depth rows of the database -- so that all CTAs of a launch work on a slice of the
-// database that stays resident in L2.
+// The groups a CTA walks in one launch.  k_synth can be launched in `nbands` depth bands: every launch then covers the sub-faults of
+// a few depth rows of the database only, so that the slice all its CTAs gather from stays resident in L2.
+// ny > 0 (the groups form an nx x ny lattice listed with the down-dip index fastest, source_bilat.f90:349-371): the lattice rows
+// [row0, row0 + rows); ny == 0 (listed row by row, or in no particular order): the slice [first, first + n) of the list.
 struct GroupWalk {
     int n;              // groups walked
-    int ny, row0, rows;
-    __device__ __forceinline__ int rec(int idx) const { return ny > 0 ? (idx / rows) * ny + row0 + idx % rows : idx; }
+    int ny, row0, rows, first;
+    __device__ __forceinline__ int rec(int idx) const { return ny > 0 ? (idx / rows) * ny + row0 + idx % rows : first + idx; }
 };
 // copy of one 128-byte group record (lanes 0..7, 16 bytes each); not committed here
 __device__ __forceinline__ void rec_copy_async(const GeoRec* __restrict__ recs, int idx, const GroupWalk& gw, GeoRec* dst_slot, int lane) {
@@ -750,7 +750,7 @@ __global__ void __launch_bounds__(256, 2) k_synth(GfdbDev db, const ReceiverDev*
                                                    size_t rec_stride, const PairHdr* __restrict__ hdrs, int nq_alloc, int margin_q,
                                                    float* __restrict__ seis, size_t seis_stride /* floats per component row */,
                                                    SeisHdr* __restrict__ shdrs, float neg_zero /* -0.0f, see make_pairs */,
-                                                   int band, int nbands, float4* __restrict__ partial /* [pair][3*nq float4 + 3*nq float] */) {
+                                                   int band, float4* __restrict__ partial /* [pair][3*nq float4 + 3*nq float] */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // CTAs that run at the same time work on the same receiver for neighbouring candidates: candidates of a grid search
     // that share (part of) their sub-fault geometry then find each other's Green's function rows in L2
@@ -766,17 +766,23 @@ __global__ void __launch_bounds__(256, 2) k_synth(GfdbDev db, const ReceiverDev*
         if (threadIdx.x < KIWI_MAX_COMP) { SeisHdr e; e.lo = 0; e.hi = -1; e.base = 0; e.pad = 0; myshdr[threadIdx.x] = e; }
         return;
     }
-    // depth bands (nbands > 1): this launch adds the lattice rows [ny*band/nbands, ny*(band+1)/nbands) of every candidate to the
-    // pair's partial strips; a candidate whose groups are no nx x ny lattice is done completely by band 0
+    // depth bands: launch `band` adds band `band` of every candidate that has that many to the pair's partial strips; the launch of
+    // a candidate's last band finishes its seismograms
+    const int nbands = cand.nbands;
+    if (band >= nbands) return;
     GroupWalk walk;
-    walk.n = cand.ngroups; walk.ny = 0; walk.row0 = 0; walk.rows = 1;
+    walk.n = cand.ngroups; walk.ny = 0; walk.row0 = 0; walk.rows = 1; walk.first = 0;
     if (nbands > 1) {
-        if (cand.ny > 0 && cand.nx * cand.ny == cand.ngroups) {
-            walk.ny = cand.ny; walk.row0 = (int)(((long long)cand.ny * band) / nbands);
-            walk.rows = (int)(((long long)cand.ny * (band + 1)) / nbands) - walk.row0;
-            walk.n = cand.nx * walk.rows;
+        if (cand.walk_ny > 0) {
+            const int nx = cand.ngroups / cand.walk_ny;
+            walk.ny = cand.walk_ny; walk.row0 = (int)(((long long)walk.ny * band) / nbands);
+            walk.rows = (int)(((long long)walk.ny * (band + 1)) / nbands) - walk.row0;
+            walk.n = nx * walk.rows;
             if (walk.rows <= 0) { walk.rows = 1; walk.n = 0; }
-        } else if (band > 0) walk.n = 0;
+        } else {
+            walk.first = (int)(((long long)cand.ngroups * band) / nbands);
+            walk.n = (int)(((long long)cand.ngroups * (band + 1)) / nbands) - walk.first;
+        }
     }
     const int base = floor4(H.out0) - 4 * margin_q;   // room on the left for the rise-time fold (k_fold)
     const int baseq = base >> 2;
@@ -1936,7 +1942,7 @@ cudaError_t launch_synth(GfdbDev db, const ReceiverDev* rcv, int nrcv, const Can
     if (e != cudaSuccess) return e;
     for (int band = 0; band < nbands; band++)
         k_synth<<<ncand * nrcv, nwarps * 32, smem, st>>>(db, rcv, nrcv, cands, g, recs, rec_stride, hdrs, nq_alloc, margin_q, seis, seis_stride, shdrs, -0.0f,
-                                                         band, nbands, reinterpret_cast<float4*>(partial));
+                                                         band, reinterpret_cast<float4*>(partial));
     return cudaGetLastError();
 }
 void launch_misfit_td(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, const float* seis, size_t seis_stride,

@@ -70,6 +70,10 @@ struct CandDev {
     float moment, risetime;     // psm%moment / psm%risetime applied after synthesis (receiver.f90:853-904)
     int nx, ny, nt;             // grid_size (source_bilat.f90:266-268)
     int status;
+    int walk_ny;                // > 0: the groups are an nx x walk_ny lattice listed with the second (down-dip) index fastest
+                                // (source_bilat.f90:349-371); 0: listed row by row or without order (depth bands of k_synth = slices)
+    int nbands;                 // depth bands k_synth works through this candidate in (>= 1): a function of the candidate, the
+                                // database and the receivers only, so that a result does not depend on the rest of the batch
 };
 struct GroupSoA {
     float *north, *east, *depth, *tbase;

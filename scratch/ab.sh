@@ -1,11 +1,11 @@
 #!/bin/bash
-# A/B bench of library variants in one box: scratch/ab.sh libA.so libB.so ...
-# each variant is copied over kiwi_b200/libkiwi_b200.so and benched twice, interleaved
-cp kiwi_b200/libkiwi_b200.so scratch/_orig.so
+# A/B of library variants in one box: scratch/ab.sh "<band settings>" libA.so libB.so ...   (variants live in scratch/; "cur" = the built library)
+bands=$1; shift
+cp kiwi_b200/libkiwi_b200.so scratch/_cur.so
 for rep in 1 2; do
   for v in "$@"; do
-    cp scratch/$v kiwi_b200/libkiwi_b200.so
-    python bench.py --steps 6 --warmup 3 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$v', round(d['value'],1), 'evals/s  synth ms', round(d['stage_ms_per_step']['synthesis'],2), 'clk', d['clocks']['sm_mhz'])"
+    if [ "$v" = cur ]; then cp scratch/_cur.so kiwi_b200/libkiwi_b200.so; else cp scratch/$v kiwi_b200/libkiwi_b200.so; fi
+    echo "== $v"; python scratch/band_sweep.py c5 $bands 2>&1 | tail -n +1
   done
 done
-cp scratch/_orig.so kiwi_b200/libkiwi_b200.so
+cp scratch/_cur.so kiwi_b200/libkiwi_b200.so
