@@ -253,6 +253,49 @@ def workload_config(w, args, batch):
             "cache": "database %s exceeds L2; every candidate streams its own node set (no L2 flush needed)" % w["db"]}
 
 
+def roofline(wname, w, B, steps, stage, nsynth, synth_ms, b_alg, b_log):
+    """roofline object of the dominant kernel of a workload"""
+    peak, peak_kind = peaks()
+    if w.get("source") == "moment_tensor" and stage[3] > stage[2]:
+        # grid-search path: the tensor-core contraction + misfit epilogue dominates.  Algorithmic flops:
+        # 2 * Ncand * 6 * (samples of all traces) (SURVEY.md 8d with the taps folded into the basis); the
+        # 3xTF32 split executes 4x that (K = 24).  Peak: measured dense bf16 / 2 (TF32 runs at half the bf16 rate).
+        sum_t = sum(d.size for (f, d) in REFS.values())
+        flops = 2.0 * B * 6.0 * sum_t
+        ms_launch = stage[3] / max(steps, 1)
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", 1400.0) / 2.0 if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 700.0
+        ach = flops / (ms_launch * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "k_mt_contract", "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk,
+                "peak_kind": "measured bf16 sustained / 2 (tf32)", "traffic": None, "algorithmic_flops_per_step": flops,
+                "executed_flops_per_step": 4.0 * flops, "ms_per_launch_group": ms_launch,
+                "note": "K = 6 contraction: the kernel is bound by its misfit epilogue (TMEM -> registers -> fp64 norm), not by the tensor pipe"}
+    else:
+        # one "launch" = the depth-band launches of k_synth that together synthesise a sub-chunk of candidates
+        ms_per_step = synth_ms / max(steps, 1)
+        achieved = b_alg * B / (ms_per_step * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "k_synth", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_kind": peak_kind, "traffic": None, "algorithmic_bytes_per_eval": b_alg, "logical_bytes_per_eval": b_log,
+                "evals_per_launch": float(B), "launches_per_step": nsynth / max(steps, 1), "ms_per_launch": ms_per_step,
+                "note": "achieved = SURVEY.md 8(d) algorithmic bytes (no reuse assumed across receivers or candidates) over the "
+                        "kernel time: with the depth-band launches the gather is served from L2, so this is the rate at which "
+                        "node blocks reach the SMs, not DRAM traffic (dram_frac is)"}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            ent = json.load(open(tpath)).get(wname + ":" + roof["kernel"])
+            if ent:   # ncu DRAM bytes per evaluation (one --set full capture per depth band) x evaluations per step
+                roof["traffic"] = ent["bytes_per_eval"] * B
+                roof["traffic_source"] = ent.get("source")
+                if roof["bound"] == "hbm":
+                    roof["dram_frac"] = roof["traffic"] / (roof["ms_per_launch"] * 1e-3) / 1e9 / peak
+                    roof["traffic_over_algorithmic"] = ent["bytes_per_eval"] / b_alg
+                    if "l2_hit_rate" in ent:
+                        roof["l2_hit_rate"] = ent["l2_hit_rate"]
+        except Exception:
+            pass
+    return roof
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -262,6 +305,7 @@ def main():
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="candidates per step and per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short C3 / C4 / C2 legs appended to the default C5 line")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.batch <= 0:
@@ -300,28 +344,26 @@ def main():
     eng.set_source_params(stype, base)
     set_references(eng, [eng], w["nrcv"], dt)
     nm = eng.nmisfits
-    # equal counts and equal summed fault area per rank (kiwi_b200.sharding.balanced_partition): the sweep's candidates differ in
-    # fault length, i.e. in the number of sub-sources, and the step time is the slowest rank's
-    from kiwi_b200.sharding import balanced_partition
-    pool = allc[:B * world]
+    # the product's sharded evaluator (kiwi_b200.sharding.ShardedEngine): equal counts and equal summed fault area per rank
+    # (balanced_partition) -- the sweep's candidates differ in fault length, i.e. in the number of sub-sources, and the step time is
+    # the slowest rank's -- then one all_gather of the misfit block over NCCL; the gathered block stays on the device
+    from kiwi_b200.sharding import ShardedEngine, balanced_partition
+    sharded = ShardedEngine(eng)
+    pool = np.ascontiguousarray(allc[:B * world])
     cost = (pool[:, 9] + pool[:, 10]) * pool[:, 11] if stype == "bilateral" else np.ones(pool.shape[0])
-    mine = np.ascontiguousarray(pool[balanced_partition(cost, world)[rank]])
-    d_out = torch.empty((B, nm, 2), dtype=torch.float32, device="cuda")
-    gathered = torch.empty((world * B, nm, 2), dtype=torch.float32, device="cuda") if world > 1 else None
+    shares = balanced_partition(cost, world)
+    mine = np.ascontiguousarray(pool[shares[rank]])
 
     def step_device():
-        st = eng.eval_sources_device(stype, mine, d_out.data_ptr())
-        t = eng.last_timing()
-        if world > 1:   # only the small misfit block crosses NVLink
-            dist.all_gather_into_tensor(gathered, d_out)
-        return st, t
+        d_mis, d_st = sharded.eval_sources_device(stype, pool, partition=shares)
+        return d_st, eng.last_timing()
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     for _ in range(max(args.warmup, 3)):
         st, _t = step_device()
-    assert not st.any(), "candidate evaluation failed: %s" % st
+    assert not bool(st.any()), "candidate evaluation failed: %s" % st
     b_alg, b_log, nsamp, nskip = eng.last_batch_bytes(4)
     assert nskip == 0, "%d centroids fell outside the database" % nskip
     if w.get("source") == "moment_tensor":
@@ -353,17 +395,23 @@ def main():
     value = world * B * args.steps / (dev_ms_max * 1e-3)
 
     # ---- timed region 2: end to end through the C ABI with host buffers (e2e) ----------------------------
-    eng.eval_sources(stype, mine, pinned=True)                  # untimed: allocates the page-locked result buffer
+    def step_e2e():
+        if world == 1:
+            return eng.eval_sources(stype, mine, pinned=True)        # page-locked result buffer (kiwi_host_alloc)
+        return sharded.eval_sources(stype, pool, partition=shares)   # host buffers in, the complete answer out on every rank
+    step_e2e()                                                       # untimed: allocates the page-locked result buffer
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        mis, st = eng.eval_sources(stype, mine, pinned=True)     # page-locked result buffer (kiwi_host_alloc)
+        mis, st = step_e2e()
     barrier()
     e2e_wall = time.perf_counter() - t0
     te = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(te.cpu()[0])
+    if world > 1:
+        mis = mis[shares[rank]]
     clocks = sampler.stop(t0_wall, t1_wall) if rank == 0 else None
     h2d = int(mine.nbytes + B * (36 + 100) + 7 * 8 * B)     # params + CandDev/BilatCand tables + STF taps
     d2h = int(mis.nbytes + st.nbytes + 4)
@@ -373,37 +421,7 @@ def main():
             dist.destroy_process_group()
         return
 
-    peak, peak_kind = peaks()
-    if w.get("source") == "moment_tensor" and stage[3] > stage[2]:
-        # grid-search path: the tensor-core contraction + misfit epilogue dominates.  Algorithmic flops:
-        # 2 * Ncand * 6 * (samples of all traces) (SURVEY.md 8d with the taps folded into the basis); the
-        # 3xTF32 split executes 4x that (K = 24).  Peak: measured dense bf16 / 2 (TF32 runs at half the bf16 rate).
-        sum_t = sum(d.size for (f, d) in REFS.values())
-        flops = 2.0 * B * 6.0 * sum_t
-        ms_launch = stage[3] / max(args.steps, 1)
-        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", 1400.0) / 2.0 if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 700.0
-        ach = flops / (ms_launch * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "k_mt_contract", "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk,
-                "peak_kind": "measured bf16 sustained / 2 (tf32)", "traffic": None, "algorithmic_flops_per_step": flops,
-                "executed_flops_per_step": 4.0 * flops, "ms_per_launch_group": ms_launch,
-                "note": "K = 6 contraction: the kernel is bound by its misfit epilogue (TMEM -> registers -> fp64 norm), not by the tensor pipe"}
-    else:
-        evals_per_launch = B * args.steps / max(nsynth, 1)
-        ms_per_launch = synth_ms / max(nsynth, 1)
-        achieved = b_alg * evals_per_launch / (ms_per_launch * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "k_synth", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_kind": peak_kind, "traffic": None, "algorithmic_bytes_per_eval": b_alg, "logical_bytes_per_eval": b_log,
-                "evals_per_launch": evals_per_launch, "ms_per_launch": ms_per_launch}
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        try:
-            ent = json.load(open(tpath)).get(args.workload + ":" + roof["kernel"])
-            if ent:   # ncu DRAM bytes per evaluation (one --set full capture) x evaluations per launch
-                per_launch = B * args.steps / max(nsynth if roof["kernel"] == "k_synth" else args.steps, 1)
-                roof["traffic"] = ent["bytes_per_eval"] * per_launch
-                roof["traffic_source"] = ent.get("source")
-        except Exception:
-            pass
+    roof = roofline(args.workload, w, B, args.steps, stage, nsynth, synth_ms, b_alg, b_log)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(w, args, B),
@@ -414,19 +432,27 @@ def main():
             "wall_ms_per_step": wall_ms_max / args.steps}
 
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(w, db, rlat, rlon, rdep, dt, stype, mine, mis)
+        line["cpu_baseline"] = cpu_baseline(w, db, rlat, rlon, rdep, dt, stype, mine, mis, eng)
+    if world == 1 and args.workload == "c5" and not args.no_secondary:
+        # the other configurations of BASELINE.json on the same database, a few steps each (the headline fields above are C5's)
+        eng.close()
+        line["secondary"] = {}
+        for name in ("c3", "c4", "c2"):
+            try:
+                line["secondary"][name] = secondary_leg(name, db, local, args.no_cpu_baseline)
+            except Exception as exc:      # a failing secondary leg must not take the headline line with it
+                line["secondary"][name] = {"error": "%s: %s" % (type(exc).__name__, exc)}
     real_stdout.write(json.dumps(line) + "\n")
     real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(w, db, rlat, rlon, rdep, dt, stype, cands, gpu_misfits):
+def cpu_baseline(w, db, rlat, rlon, rdep, dt, stype, cands, gpu_misfits, geng=None):
     """The oracle (restated CPU path) timed on the host cores on a bounded sample of the same
     workload, and used as the checker of the batch just measured."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_lib import OracleEngine, lib as olib
-    from kiwi_b200 import synthetic
     ncores = os.cpu_count() or 1
     o = OracleEngine(threads=ncores)
     configure(o, db, w, rlat, rlon, rdep)
@@ -445,13 +471,101 @@ def cpu_baseline(w, db, rlat, rlon, rdep, dt, stype, cands, gpu_misfits):
     def dev(a, b):
         return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 0.1 * np.abs(b[..., 1:2]))))
     d32, dw, d32w = dev(gpu_misfits[:n], mo), dev(gpu_misfits[:n], mw), dev(mo, mw)
+    parity = {"gpu_vs_fp32_path": d32, "gpu_vs_double_accumulation": dw, "fp32_path_vs_double_accumulation": d32w, "tol": 1e-5}
+    if geng is not None:
+        # seismograms of the last candidate of the sample against the fp32 path, trace by trace on up to 100 receivers spread over
+        # the array: max |gpu - oracle| / peak (the north_star bar; the misfits are differences of these traces)
+        geng.set_source_params(stype, cands[n - 1])
+        worst = {"seis_vs_fp32_path": 0.0, "seis_vs_double_accumulation": 0.0, "seis_fp32_path_vs_double_accumulation": 0.0}
+        ntr = 0
+        for ir in np.unique(np.linspace(1, w["nrcv"], min(w["nrcv"], 100)).astype(int)):
+            for ic in range(1, 4):
+                tg, to, tw = geng.get_seismogram(int(ir), ic), o.get_seismogram(int(ir), ic), ow.get_seismogram(int(ir), ic)
+                for key, (fa, da), (fb, dbb) in (("seis_vs_fp32_path", tg, to), ("seis_vs_double_accumulation", tg, tw),
+                                                 ("seis_fp32_path_vs_double_accumulation", to, tw)):
+                    peak = float(np.abs(dbb).max()) if dbb.size else 0.0
+                    if (fa, da.size) != (fb, dbb.size):
+                        worst[key] = float("inf")      # spans must be equal
+                    elif peak > 0:
+                        worst[key] = max(worst[key], float(np.abs(da - dbb).max()) / peak)
+                ntr += 1
+        parity.update(worst)
+        parity["seis_traces_compared"] = ntr
+    sn = parity.get("seis_fp32_path_vs_double_accumulation", 0.0)
+    parity["ok"] = bool(parity.get("seis_vs_double_accumulation", 0.0) <= 1e-5 and parity.get("seis_vs_fp32_path", 0.0) <= 1e-5 + 1.5 * sn and
+                        dw <= 1e-5 and d32 <= max(1e-5, 2.0 * d32w))
+    parity["note"] = ("seis_*: max |a - b| / trace peak over the sampled traces (spans equal), last candidate of the sample; gpu_*: "
+                      "relative misfit deviation, relative to max(misfit, 0.1 x norm factor).  Bar: 1e-5 against the restatement with "
+                      "the strips carried in double, and 1e-5 + 1.5 x the fp32 restatement's own distance from it against the fp32 "
+                      "restatement: at ~1e4 sub-sources the reference's sequential fp32 accumulation is itself ~5e-5 of the trace peak "
+                      "away from the exact sum of the same terms (tests/test_fullsize_parity_gpu.py, DESIGN.md section 5)")
     return {"value": n / t, "unit": UNIT, "cores": int(olib().oracle_max_threads()), "kind": "port",
             "sample": "first %d candidate(s) of the step, %.1f s; restated CPU path (oracle/), OpenMP over receivers" % (n, t),
-            "parity": {"gpu_vs_fp32_path": d32, "gpu_vs_double_accumulation": dw, "fp32_path_vs_double_accumulation": d32w, "tol": 1e-5,
-                       "ok": bool(dw <= 1e-5 and d32 <= max(1e-5, 2.0 * d32w)),
-                       "note": "relative misfit deviation; at ~1e4 sub-sources the fp32 reference path's own sequential "
-                               "accumulation noise exceeds 1e-5, so the bar is 1e-5 against the double-accumulated "
-                               "restatement and 2x the reference path's own noise against the fp32 restatement"}}
+            "parity": parity}
+
+
+def secondary_leg(name, db, device, no_cpu, steps=4, warmup=3):
+    """one of the other BASELINE.json configurations, a few steps on one GPU: value (device, CUDA events), e2e (host buffers through
+    the C ABI), roofline, CPU baseline + parity on a bounded sample"""
+    import kiwi_b200
+    from kiwi_b200 import synthetic
+
+    class A:
+        workload = name
+    w = dict(WORKLOADS[name])
+    B = w["batch"]
+    dt = db.meta()["dt"]
+    rlat, rlon, rdep = synthetic.receivers(w["nrcv"], (30.0, 70.0), w["dmin"], w["dmax"])
+    eng = kiwi_b200.Engine(device)
+    try:
+        configure(eng, db, w, rlat, rlon, rdep)
+        stype, allc, base = candidates(w, max(B, 32))
+        eng.set_source_params(stype, base)
+        set_references(eng, [eng], w["nrcv"], dt)
+        mine = np.ascontiguousarray(allc[:B])
+        for _ in range(warmup):
+            st = eng.eval_sources_on_device(stype, mine)
+        assert not st.any(), "candidate evaluation failed: %s" % st
+        b_alg, b_log, nsamp, nskip = eng.last_batch_bytes(4)
+        if w.get("source") == "moment_tensor":
+            nloc = len({tuple(r) for r in np.concatenate([mine[:, :4], mine[:, 10:11]], 1).tolist()})
+            scale = 6.0 * nloc / B if eng.last_timing()["launches"][3] and nloc * 8 <= B else 1.0
+            b_alg, b_log = b_alg * scale, b_log * scale
+        dev_ms = synth_ms = 0.0
+        nsynth = launches = 0
+        stage = np.zeros(4)
+        for _ in range(steps):
+            eng.eval_sources_on_device(stype, mine)
+            t = eng.last_timing()
+            dev_ms += t["total_ms"]; synth_ms += t["synthesis_ms"]; nsynth += t["launches"][2]; launches += sum(t["launches"])
+            stage += [t["discretise_ms"], t["geometry_ms"], t["synthesis_ms"], t["misfit_ms"]]
+        # end to end: host parameters in, host results out.  The moment-tensor grid search returns what its driver
+        # (kiwi_b200.grid_search.MisfitGrid) reads: the global misfit of every candidate and the best one, reduced on the device
+        grid = w.get("source") == "moment_tensor"
+
+        def e2e_step():
+            if grid:
+                eng.eval_sources_on_device(stype, mine)
+                return eng.outer_misfits(B, outer_norm="l2norm")
+            return eng.eval_sources(stype, mine, pinned=True)
+        e2e_step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            res = e2e_step()
+        e2e_s = time.perf_counter() - t0
+        d2h = int(res[0].nbytes + res[1].nbytes + (res[2].nbytes if grid else 0))
+        out = {"config": workload_config(w, A, B), "value": B * steps / (dev_ms * 1e-3), "unit": UNIT, "steps": steps, "warmup": warmup,
+               "ms_per_step": dev_ms / steps,
+               "e2e": {"value": B * steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(mine.nbytes), "d2h_bytes_per_step": d2h,
+                       "result": "global misfit per candidate + best candidate (outer l2norm on the device)" if grid else "misfit block"},
+               "gpu_launches": int(launches), "roofline": roofline(name, w, B, steps, stage, nsynth, synth_ms, b_alg, b_log),
+               "stage_ms_per_step": {k: float(v) / steps for k, v in zip(["discretise", "geometry", "synthesis", "misfit"], stage)}}
+        if not no_cpu:
+            mis, st = eng.eval_sources(stype, mine[:max(1, w["cpu_sample"])])
+            out["cpu_baseline"] = cpu_baseline(w, db, rlat, rlon, rdep, dt, stype, mine, mis, eng)
+        return out
+    finally:
+        eng.close()
 
 
 if __name__ == "__main__":

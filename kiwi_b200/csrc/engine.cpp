@@ -236,6 +236,7 @@ int upload_receivers(kiwi_ctx* c) {
     CU_OK(cudaMemcpyAsync(c->d_taper.p, taperdata.data(), sizeof(float) * taperdata.size(), cudaMemcpyHostToDevice, c->stream));
     CU_OK(cudaStreamSynchronize(c->stream));
     c->receivers_dirty = false;
+    c->last_eval_ns = 0;   // receivers, references, tapers or filters changed: a misfit block kept on the device is stale
     return 0;
 }
 
@@ -498,6 +499,9 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
     // ---- host preparation of all candidates -------------------------------------------------------
     static const bool trace = getenv("KIWI_TRACE") != nullptr;   // host-side wall-clock split of a batch on stderr
     const auto tw0 = std::chrono::steady_clock::now();
+    // the evaluation's clock starts here: source discretisation on the host (the fast-marching solve of the eikonal sources) is part
+    // of an evaluation (discretise -> synthesise -> scale -> misfit); the stream is idle, so the event marks this instant
+    cudaEventRecord(c->ev[0], st);
     std::vector<kh::SourcePrep> prep(n);
     std::vector<int> bad(n, 0);
     size_t max_groups = 1;
@@ -527,6 +531,7 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         }
     }
     const auto tw1 = std::chrono::steady_clock::now();
+    c->ms[0] += (float)std::chrono::duration<double, std::milli>(tw1 - tw0).count();   // host part of the discretisation stage
     // ---- chunking by workspace budget ---------------------------------------------------------------
     if (c->work_budget == 0) {
         size_t fr = 0, tot = 0;
@@ -539,7 +544,6 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
     const int align = hook ? std::max(1, hook->align) : 1;
     if (chunk < n) chunk = std::max(align, chunk / align * align);
 
-    cudaEventRecord(c->ev[0], st);
     for (int b0 = 0; b0 < n; b0 += chunk) {
         const int nc = std::min(chunk, n - b0);
         // ---- candidate / group / tap tables ---------------------------------------------------------
@@ -879,6 +883,7 @@ int ensure_single(kiwi_ctx* c, bool want_misfits) {
     CU_OK(c->d_out.ensure(sizeof(float) * 2 * std::max(nm, 1)));
     int status = 0;
     c->src_misfits.clear();
+    c->last_eval_ns = 0;   // d_out is rewritten: the block of an earlier kiwi_eval_sources is gone (kiwi_outer_misfits must not use it)
     if (eval_batch(c, c->src_type, 1, (int)c->src_params.size(), c->src_params.data(), c->d_out.as<float>(), &status, want_misfits)) return 1;
     if (want_misfits) {
         c->src_misfits.assign((size_t)2 * nm, 0.f);
@@ -1509,6 +1514,7 @@ int kiwi_minimize_lm(kiwi_ctx* c, int* info_out, int* iterations_out, float* mis
         }
         std::vector<int> status(ncols, 0);
         CU_OK(c->d_out.ensure(sizeof(float) * 2 * (size_t)std::max(nm, 1) * ncols));
+        c->last_eval_ns = 0;   // (d_out is rewritten)
         if (eval_batch(c, c->src_type, ncols, (int)np, params.data(), c->d_out.as<float>(), status.data(), true)) { failed_hard = true; return 0; }
         std::vector<float> mis((size_t)2 * nm * ncols, 0.f);
         if (nm > 0) CU_OK(cudaMemcpy(mis.data(), c->d_out.p, sizeof(float) * mis.size(), cudaMemcpyDeviceToHost));

@@ -124,19 +124,45 @@ int kiwi_gfdb_write(const kiwi_gfdb* cdb, const char* path) {
 kiwi_gfdb* kiwi_gfdb_read(const char* path) {
     FILE* f = fopen(path, "rb");
     if (!f) { kiwi_set_error("can't open file %s", path); return nullptr; }
-    Kgf1Header h;
-    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "KGF1", 4) != 0) { fclose(f); kiwi_set_error("%s is not a KGF1 database", path); return nullptr; }
-    kiwi_gfdb* db = new kiwi_gfdb();
-    db->nx = h.nx; db->nz = h.nz; db->ng = h.ng; db->dt = h.dt; db->dx = h.dx; db->dz = h.dz; db->firstx = h.firstx; db->firstz = h.firstz;
-    size_t n = db->ntr();
-    db->span0.resize(n); db->len.resize(n); db->offset.resize(n); db->data.resize((size_t)h.nsamples);
-    bool ok = fread(db->span0.data(), sizeof(int), n, f) == n && fread(db->len.data(), sizeof(int), n, f) == n &&
-              fread(db->offset.data(), sizeof(long long), n, f) == n &&
-              fread(db->data.data(), sizeof(float), db->data.size(), f) == db->data.size();
-    fclose(f);
-    if (!ok) { delete db; kiwi_set_error("read error on %s", path); return nullptr; }
-    db->flat = true;
-    return db;
+    kiwi_gfdb* db = nullptr;
+    auto fail = [&](const char* what) -> kiwi_gfdb* {
+        fclose(f); delete db;
+        kiwi_set_error("%s: %s", path, what);
+        return nullptr;
+    };
+    try {
+        Kgf1Header h;
+        if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "KGF1", 4) != 0) return fail("not a KGF1 database");
+        // the same rules as kiwi_gfdb_create, and sizes that agree with the length of the file
+        if (h.nx < 1 || h.nz < 1 || (h.ng != 8 && h.ng != 10) || !(h.dt > 0.f) || !(h.dx > 0.f) || !(h.dz > 0.f) || h.nsamples < 0 ||
+            !std::isfinite(h.firstx) || !std::isfinite(h.firstz))
+            return fail("invalid header");
+        const unsigned long long ntr = (unsigned long long)h.nx * (unsigned long long)h.nz * (unsigned long long)h.ng;
+        if (ntr > (1ull << 31)) return fail("invalid header (too many traces)");
+        if (fseek(f, 0, SEEK_END) != 0) return fail("read error");
+        const long long fsize = ftell(f);
+        const unsigned long long expect = sizeof h + ntr * (2 * sizeof(int) + sizeof(long long)) + (unsigned long long)h.nsamples * sizeof(float);
+        if (fsize < 0 || (unsigned long long)fsize != expect) return fail("file size does not match the header (truncated or corrupt)");
+        if (fseek(f, (long)sizeof h, SEEK_SET) != 0) return fail("read error");
+        db = new kiwi_gfdb();
+        db->nx = h.nx; db->nz = h.nz; db->ng = h.ng; db->dt = h.dt; db->dx = h.dx; db->dz = h.dz; db->firstx = h.firstx; db->firstz = h.firstz;
+        const size_t n = (size_t)ntr;
+        db->span0.resize(n); db->len.resize(n); db->offset.resize(n); db->data.resize((size_t)h.nsamples);
+        const bool ok = fread(db->span0.data(), sizeof(int), n, f) == n && fread(db->len.data(), sizeof(int), n, f) == n &&
+                        fread(db->offset.data(), sizeof(long long), n, f) == n &&
+                        fread(db->data.data(), sizeof(float), db->data.size(), f) == db->data.size();
+        if (!ok) return fail("read error");
+        for (size_t i = 0; i < n; i++) {   // every trace inside the sample block, spans that cannot overflow the index arithmetic
+            const long long len = db->len[i], off = db->offset[i];
+            if (len < 0 || off < 0 || off > h.nsamples || len > h.nsamples - off || std::abs((long long)db->span0[i]) > (1ll << 28) || len > (1ll << 28))
+                return fail("trace table out of range (corrupt file)");
+        }
+        fclose(f);
+        db->flat = true;
+        return db;
+    } catch (const std::exception& e) {
+        return fail(e.what());
+    }
 }
 
 }  // extern "C"

@@ -273,16 +273,18 @@ __global__ void __launch_bounds__(256, 3) k_geometry(GfdbDev db, const ReceiverD
                 ix2 = ix1 + xunder; iz2 = iz1 + zunder;
                 dix = D_(S_(S_(x, db.firstx), M_((float)(ix1 - 1), db.dx)), denx);
                 diz = D_(S_(S_(z, db.firstz), M_((float)(iz1 - 1), db.dz)), denz);
-                const float fx = ax - floorf(ax), fz = az - floorf(az);
-                const float tx = 4.f * 1.1920929e-7f * fmaxf(fabsf(ax), 1.f), tz = 4.f * 1.1920929e-7f * fmaxf(fabsf(az), 1.f);
-                if (fx < tx || 1.f - fx < tx || fz < tz || 1.f - fz < tz) flags |= GEO_NEAR;
+                // (only the distance goes through fp64 libm, where the device may differ from glibc in the last bits; the depth
+                //  coordinate is exactly rounded fp32 arithmetic on both sides)
+                const float fx = ax - floorf(ax);
+                const float tx = 4.f * 1.1920929e-7f * fmaxf(fabsf(ax), 1.f);
+                if (fx < tx || 1.f - fx < tx) flags |= GEO_NEAR;
             } else {            // gfdb_get_indices gfdb.f90:781-792 (nint: half away from zero)
                 const float ax = D_(S_(x, db.firstx), db.dx), az = D_(S_(z, db.firstz), db.dz);
                 ix1 = (int)roundf(ax) + 1; iz1 = (int)roundf(az) + 1;
                 ix2 = ix1 + 1; iz2 = iz1 + 1; dix = 0.f; diz = 0.f;
-                const float fx = fabsf(fabsf(ax - floorf(ax)) - 0.5f), fz = fabsf(fabsf(az - floorf(az)) - 0.5f);
-                const float tx = 4.f * 1.1920929e-7f * fmaxf(fabsf(ax), 1.f), tz = 4.f * 1.1920929e-7f * fmaxf(fabsf(az), 1.f);
-                if (fx < tx || fz < tz) flags |= GEO_NEAR;
+                const float fx = fabsf(fabsf(ax - floorf(ax)) - 0.5f);
+                const float tx = 4.f * 1.1920929e-7f * fmaxf(fabsf(ax), 1.f);
+                if (fx < tx) flags |= GEO_NEAR;
             }
             const bool single = (dix == 0.f && diz == 0.f);
             if (single) flags |= GEO_SINGLE;

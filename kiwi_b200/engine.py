@@ -211,6 +211,18 @@ class Engine:
         _check(lib.kiwi_switch_receiver(self._h, ireceiver, int(bool(state))))
         self._enabled[ireceiver - 1] = bool(state)
 
+    @property
+    def device(self):
+        return self._device
+
+    def enabled_receivers(self):
+        """[bool] per receiver (switch_receiver)"""
+        return list(self._enabled)
+
+    def components_per_receiver(self):
+        """[number of components] per receiver: the misfit pairs it contributes to get_misfits while enabled"""
+        return [len(c) for c in self._components]
+
     def set_source_location(self, lat_deg, lon_deg, ref_time=0.0):
         _check(lib.kiwi_set_source_location(self._h, lat_deg, lon_deg, ref_time))
 

@@ -123,9 +123,18 @@ class OracleEngine:
         arr = (C.c_char_p * n)(*[c.encode() for c in components])
         self._check(self.L.oracle_set_receivers(self.h, C.c_int(n), lat.ctypes.data_as(dp), lon.ctypes.data_as(dp), dep.ctypes.data_as(fp), arr))
         self.nreceivers = n
+        self._components = list(components)
+        self._enabled = [True] * n
 
     def switch_receiver(self, irec, state):
         self._check(self.L.oracle_switch_receiver(self.h, C.c_int(irec), C.c_int(int(bool(state)))))
+        self._enabled[irec - 1] = bool(state)
+
+    def enabled_receivers(self):
+        return list(self._enabled)
+
+    def components_per_receiver(self):
+        return [len(c) for c in self._components]
 
     def set_source_location(self, lat, lon, ref_time=0.0):
         self._check(self.L.oracle_set_source_location(self.h, C.c_float(lat), C.c_float(lon), C.c_double(ref_time)))

@@ -108,3 +108,32 @@ def test_reference_round_trip_known_answer(tmp_path):
     o.set_database(db)
     (a, b), nstrips = o.trace_span(1, 2, 2)
     assert (a, b, nstrips) == (11, 24, 1)      # same span; one strip: a gap of 5 zeros does not exceed maxgap (sparse_trace.f90:24, :466-470)
+
+
+def test_kgf1_reader_refuses_corrupt_files(tmp_path):
+    """a truncated or tampered dump is an error message, not a crash or an out-of-bounds read later in set_database"""
+    import struct
+    db = sc.small_db_ng8()
+    path = tmp_path / "db.kgf1"
+    db.write(path)
+    raw = path.read_bytes()
+    m = db.meta()
+    ntr = m["nx"] * m["nz"] * m["ng"]
+
+    def check(blob, what):
+        bad = tmp_path / "bad.kgf1"
+        bad.write_bytes(blob)
+        with pytest.raises(KiwiError, match=what):
+            Gfdb.read(bad)
+    check(raw[:len(raw) // 2], "file size")                                        # truncated
+    check(raw + b"\0" * 16, "file size")                                           # trailing garbage
+    check(raw[:8] + struct.pack("<i", 1 << 30) + raw[12:], "invalid header|file size")   # nx huge
+    check(raw[:8] + struct.pack("<i", -3) + raw[12:], "invalid header")            # nx negative
+    check(raw[:16] + struct.pack("<i", 9) + raw[20:], "invalid header")            # ng = 9
+    check(raw[:24] + struct.pack("<f", 0.0) + raw[28:], "invalid header")          # dt = 0
+    hdr = 56
+    off_table = hdr + 2 * 4 * ntr
+    check(raw[:off_table] + struct.pack("<q", 1 << 40) + raw[off_table + 8:], "trace table")     # offset beyond the samples
+    len_table = hdr + 4 * ntr
+    check(raw[:len_table] + struct.pack("<i", -5) + raw[len_table + 4:], "trace table")          # negative length
+    check(b"JUNK" + raw[4:], "not a KGF1")

@@ -68,3 +68,30 @@ def test_outer_misfits_on_device(outer_norm, anarchy):
     st2 = g.eval_sources_on_device("bilateral", p)
     out2, best2, _ = g.outer_misfits(receiver_weights=weights, outer_norm=outer_norm, anarchy=anarchy, bweights=bw, want_matrix=True)
     assert np.array_equal(st2, status) and np.array_equal(best2, best) and np.allclose(out2[:, ok], out[:, ok], rtol=0, atol=0)
+
+
+@pytest.mark.gpu
+def test_outer_misfits_refuses_a_stale_device_block():
+    """the misfit block kiwi_eval_sources leaves on the device is gone after anything that rewrites it (a single evaluation
+    behind get_misfits, minimize_lm) or changes the receivers; kiwi_outer_misfits(NULL) must say so instead of reducing garbage"""
+    from kiwi_b200 import Engine, KiwiError
+    from oracle_lib import OracleEngine
+    lat, lon, dep = sc.small_receivers(6)
+    g, o = Engine(0), OracleEngine()
+    for e in (g, o):
+        sc.setup(e, sc.small_db(), lat, lon, dep, COMPS)
+    o.eval_sources("bilateral", sc.BILAT_SMALL)
+    sc.set_refs_from(o, [g], [len(c) for c in COMPS])
+    p = np.tile(sc.BILAT_SMALL, (4, 1)); p[:, 5] += np.arange(4) * 5.0
+    g.eval_sources_on_device("bilateral", p)
+    out, best, _ = g.outer_misfits(4)
+    g.set_source_params("bilateral", p[2]); g.get_misfits()            # a single evaluation reuses the buffer
+    with pytest.raises(KiwiError, match="no misfit block"):
+        g.outer_misfits(4)
+    g.eval_sources_on_device("bilateral", p)
+    g.switch_receiver(2, False)                                        # the layout of the block no longer matches the receivers
+    with pytest.raises(KiwiError, match="no misfit block"):
+        g.outer_misfits(4)
+    g.eval_sources_on_device("bilateral", p)
+    out2, best2, _ = g.outer_misfits(4)
+    assert best2[0] == best[0] or np.isfinite(out2).all()

@@ -71,6 +71,22 @@ def _worker(rank, world, port, q):
     misb, stb = eval_sources_sharded(o, "bilateral", p, partition=[[4, 0], [1, 2, 3]])
     assert np.array_equal(misb, misc) and np.array_equal(stb, stc)
     ref, rst = o.eval_sources("bilateral", p)
+    # fewer candidates than ranks: the receivers are partitioned by distance instead, the answers merged by receiver
+    from kiwi_b200.sharding import ShardedEngine, receiver_partition
+    se = ShardedEngine(o)
+    one, ost = se.eval_sources("bilateral", p[:1])
+    assert np.array_equal(one, ref[:1]) and np.array_equal(ost, rst[:1]) and o.enabled_receivers() == [True, True, True]
+    shares = receiver_partition(o.get_distances()[0], [True] * 3, 2)
+    assert sorted(int(i) for s_ in shares for i in s_) == [1, 2, 3] and [len(s_) for s_ in shares] == [2, 1]
+    o.switch_receiver(2, False)                     # a disabled receiver stays out of the partition and of the answer
+    two, _ = se.eval_sources("bilateral", p[:1])
+    ref2, _ = o.eval_sources("bilateral", p[:1])
+    assert two.shape == (1, 5, 2) and np.array_equal(two, ref2) and o.enabled_receivers() == [True, False, True]
+    o.switch_receiver(2, True)
+    lm1, _ = se.eval_sources_by_receivers("bilateral", p[:3], keep_sharded=True)      # optimiser loop: the partition stays
+    lm2, _ = se.eval_sources_by_receivers("bilateral", p[:3], keep_sharded=True)
+    se.unshard_receivers()
+    assert np.array_equal(lm1, ref[:3]) and np.array_equal(lm2, ref[:3]) and o.enabled_receivers() == [True, True, True]
     q.put((rank, bool(np.array_equal(mis, ref) and np.array_equal(misc, ref)), bool(np.array_equal(st, rst) and np.array_equal(stc, rst)), mis.shape))
     dist.barrier()
     dist.destroy_process_group()
