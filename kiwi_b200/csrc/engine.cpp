@@ -125,6 +125,7 @@ struct kiwi_ctx {
     DevBuf d_map, d_status_out;
     DevBuf d_taprec;              // shift table of the current batch (k_tap_table)
     DevBuf d_partial;             // running strip sums of the depth bands of k_synth
+    DevBuf d_fftz;                // transform buffers of k_misfit_general for spans beyond 16384 samples
     size_t l2_bytes = 0;          // cudaDevAttrL2CacheSize (choose_bands)
     double rcv_dmin = 0., rcv_dmax = 0., rcv_depmin = 0., rcv_depmax = 0.;   // distance / depth range of the enabled receivers (upload_receivers)
     size_t slab_floats = 0;       // floats of the database slabs in HBM
@@ -367,15 +368,18 @@ struct Dedup {
     std::vector<float> moment;    // [n_out]: its moment
 };
 
-// twiddle table of the shared-memory FFTs: exp(-2 pi i k / 32768), rounded from double as an fp32 FFT library tabulates them
-int ensure_twiddles(kiwi_ctx* c) {
-    if (c->tw_n != 0) return 0;
-    const int N = 32768;
+// twiddle table of the FFTs: exp(-2 pi i k / N), N = 32768 or the longest transform asked for so far, rounded from double as an
+// fp32 FFT library tabulates them
+int ensure_twiddles(kiwi_ctx* c, int n_needed = 0) {
+    int N = 32768;
+    while (N < n_needed) N <<= 1;
+    if (c->tw_n >= N) return 0;
     std::vector<float> twh((size_t)N);
     for (int k = 0; k < N / 2; k++) {
         const double a = -2.0 * M_PI * (double)k / (double)N;
         twh[2 * (size_t)k] = (float)cos(a); twh[2 * (size_t)k + 1] = (float)sin(a);
     }
+    CU_OK(cudaStreamSynchronize(c->stream));
     CU_OK(c->d_tw.ensure(sizeof(float) * N));
     // on the engine's stream and waited for: a plain cudaMemcpy from pageable memory may return before the DMA has landed, and the
     // non-blocking stream the kernels run on is not ordered against the default stream
@@ -415,14 +419,21 @@ int run_misfit_general(kiwi_ctx* c, int method, int xs0, int xs1, int syn_lo, in
         const long long want = std::max<long long>((long long)hi - lo + 1, 2LL * std::max(tmax, rlen));
         while (n_alloc < want) n_alloc <<= 1;
         n_alloc <<= 1;   // head room for re-centred unions
-        if (n_alloc > 16384) n_alloc = 16384;   // 128 KiB of shared memory; longer spans are flagged per candidate
-        if (ensure_twiddles(c)) return 1;
+        if (n_alloc > (1 << 22)) return kiwi_set_error("probe span of %d samples is too long", n_alloc);
+        if (ensure_twiddles(c, n_alloc)) return 1;
     }
-    if (misfit_general_smem_bytes(n_alloc, nshift) > (size_t)200 * 1024) return kiwi_set_error("floating shift range too large");
+    // transforms of up to 16384 points run in shared memory (128 KiB); longer ones (comparator.f90:1092-1118 puts no bound on the
+    // padded span) in a global-memory buffer per CTA
+    float2* zscratch = nullptr;
+    if (n_alloc > 16384) {
+        CU_OK(c->d_fftz.ensure(sizeof(float2) * (size_t)n_alloc * nslots * nrcv));
+        zscratch = c->d_fftz.as<float2>();
+    }
+    if (misfit_general_smem_bytes(zscratch ? 0 : n_alloc, nshift) > (size_t)200 * 1024) return kiwi_set_error("floating shift range too large");
     cudaError_t e = launch_misfit_general(c->d_rcv.as<ReceiverDev>(), nrcv, d_cands, nslots, c->d_seis.as<float>(), seis_stride, d_shdrs,
                                           c->d_refdata.as<float>(), c->d_taper.as<float>(), (const float2*)c->d_tw.p, c->tw_n > 0 ? c->tw_n : 2, method,
                                           c->db.dt, c->syn_factor, nm, out_base, status_base, d_fshift, n_alloc, nshift, d_map, c->stream, xs0, xs1,
-                                          premethod);
+                                          premethod, zscratch);
     if (e != cudaSuccess) return kiwi_set_error("CUDA error launching the misfit kernel: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -512,7 +523,6 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         auto work = [&](int i) {
             bad[i] = prep_candidate(c, sourcetype, params + (size_t)i * nparams, c->effective_dt, &prep[i], &errs[i]);
             if (bad[i]) prep[i] = kh::SourcePrep();
-            if (prep[i].nt > 32) { bad[i] = 1; prep[i] = kh::SourcePrep(); errs[i] = "more than 32 time centroids per sub-fault"; }   // SYN_MAXTAPS
         };
         const bool heavy = sourcetype == KIWI_SOURCE_EIKONAL || sourcetype == KIWI_SOURCE_MT_EIKONAL;
         const int nthreads = heavy ? (int)std::min<size_t>((size_t)n, std::max(1u, std::thread::hardware_concurrency())) : 1;
@@ -678,7 +688,6 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         int margin_q = 0;
         if (max_rise > 0.f) {
             const int nshifts = 1 + 2 * (int)lroundf(0.5f * max_rise / c->db.dt);
-            if (nshifts > 1024) return kiwi_set_error("rise time too long for the fold kernel");
             margin_q = ((nshifts + 1) / 2 + 2 + 3) / 4 + 1;
         }
         const int nq = (tmax + 6) / 4 + 1 + 2 * margin_q;
@@ -934,7 +943,7 @@ void kiwi_destroy(kiwi_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->d_slabs, &c->d_nodes, &c->d_tspan, &c->d_rcv, &c->d_refdata, &c->d_taper, &c->d_cands, &c->d_bilat, &c->d_gf, &c->d_gi,
-                      &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift, &c->d_map, &c->d_status_out, &c->d_taprec, &c->d_partial, &c->d_gm, &c->d_xcorr, &c->d_mtlocs, &c->d_mts, &c->d_candof, &c->d_orc, &c->d_orw, &c->d_obw, &c->d_oout, &c->d_obest, &c->d_obestv})
+                      &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift, &c->d_map, &c->d_status_out, &c->d_taprec, &c->d_partial, &c->d_fftz, &c->d_gm, &c->d_xcorr, &c->d_mtlocs, &c->d_mts, &c->d_candof, &c->d_orc, &c->d_orw, &c->d_obw, &c->d_oout, &c->d_obest, &c->d_obestv})
         b->release();
     c->h_stage.release(); c->h_out.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);

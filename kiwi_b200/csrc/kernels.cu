@@ -100,41 +100,48 @@ __global__ void k_group_tap_range(GroupSoA g, TapSoA taps, float dt, int gbegin,
 __global__ void __launch_bounds__(256) k_tap_table(GroupSoA g, TapSoA taps, float dt, int ngroups) {
     const int gi = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (gi >= ngroups) return;
-    const int tb = g.tap_begin[gi], tn = min(g.tap_count[gi], 32), tt = g.tt_begin[gi];
-    const bool on = lane < tn;
-    int its = 0; float wl = 0.f, wr = 0.f;
-    if (on) {
-        const float time = A_(g.tbase[gi], taps.toff[tb + lane]);
-        const float rshift = D_(time, dt);
-        its = (int)floorf(rshift);
-        const float wr0 = S_(rshift, (float)its);
-        const float wl0 = S_(1.f, wr0);
-        const float wt = taps.wt[tb + lane];
-        wr = M_(wr0, wt); wl = M_(wl0, wt);
-    }
-    const int cls = its & 3, qoff = its >> 2;
+    const int tb = g.tap_begin[gi], tn_all = g.tap_count[gi], tt = g.tt_begin[gi];
     const unsigned lt = (1u << lane) - 1u;
-    // leader = first tap of every distinct quad shift; it gathers the taps of its quad shift in tap order
-    float h[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, W = 0.f;
-    bool leader = on;
-    for (int j = 0; j < tn; j++) {
-        const float wlj = __shfl_sync(0xffffffffu, wl, j), wrj = __shfl_sync(0xffffffffu, wr, j);
-        const int qj = __shfl_sync(0xffffffffu, qoff, j), sj = __shfl_sync(0xffffffffu, cls, j);
-        if (qj == qoff) {
-            if (j < lane) leader = false;
-#pragma unroll
-            for (int t = 0; t < 5; t++) { if (sj == t) h[t] += wlj; if (sj + 1 == t) h[t] += wrj; }
-            W += wlj + wrj;
+    int nentries = 0, lo = INT_MAX, hi = INT_MIN;
+    // rounds of 32 taps (source_bilat.f90:274-315 puts no bound on nt): quad shifts are merged within a round; a quad shift that
+    // straddles two rounds simply gets two entries
+    for (int t0 = 0; t0 < tn_all; t0 += 32) {
+        const int tn = min(tn_all - t0, 32);
+        const bool on = lane < tn;
+        int its = 0; float wl = 0.f, wr = 0.f;
+        if (on) {
+            const float time = A_(g.tbase[gi], taps.toff[tb + t0 + lane]);
+            const float rshift = D_(time, dt);
+            its = (int)floorf(rshift);
+            const float wr0 = S_(rshift, (float)its);
+            const float wl0 = S_(1.f, wr0);
+            const float wt = taps.wt[tb + t0 + lane];
+            wr = M_(wr0, wt); wl = M_(wl0, wt);
         }
+        const int cls = its & 3, qoff = its >> 2;
+        // leader = first tap of every distinct quad shift; it gathers the taps of its quad shift in tap order
+        float h[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, W = 0.f;
+        bool leader = on;
+        for (int j = 0; j < tn; j++) {
+            const float wlj = __shfl_sync(0xffffffffu, wl, j), wrj = __shfl_sync(0xffffffffu, wr, j);
+            const int qj = __shfl_sync(0xffffffffu, qoff, j), sj = __shfl_sync(0xffffffffu, cls, j);
+            if (qj == qoff) {
+                if (j < lane) leader = false;
+#pragma unroll
+                for (int t = 0; t < 5; t++) { if (sj == t) h[t] += wlj; if (sj + 1 == t) h[t] += wrj; }
+                W += wlj + wrj;
+            }
+        }
+        const unsigned lm = __ballot_sync(0xffffffffu, leader);
+        if (leader) {
+            float4* e = g.taprec + 2 * ((size_t)tt + nentries + __popc(lm & lt));
+            e[0] = make_float4(__int_as_float(qoff), h[0], h[1], h[2]);
+            e[1] = make_float4(h[3], h[4], W, 0.f);
+        }
+        nentries += __popc(lm);
+        lo = min(lo, warp_min_i(on ? its : INT_MAX)); hi = max(hi, warp_max_i(on ? its : INT_MIN));
     }
-    const unsigned lm = __ballot_sync(0xffffffffu, leader);
-    if (leader) {
-        float4* e = g.taprec + 2 * ((size_t)tt + __popc(lm & lt));
-        e[0] = make_float4(__int_as_float(qoff), h[0], h[1], h[2]);
-        e[1] = make_float4(h[3], h[4], W, 0.f);
-    }
-    const int lo = warp_min_i(on ? its : INT_MAX), hi = warp_max_i(on ? its : INT_MIN);
-    if (lane == 0) { g.nstep[gi] = __popc(lm); g.its_min[gi] = lo; g.its_max[gi] = hi; }
+    if (lane == 0) { g.nstep[gi] = nentries; g.its_min[gi] = lo; g.its_max[gi] = hi; }
 }
 
 // expand the SoA of one candidate back into the reference's centroid table (test/inspection only)
@@ -413,7 +420,6 @@ __global__ void __launch_bounds__(256, 3) k_geometry(GfdbDev db, const ReceiverD
 // All fp32 arithmetic of the inner loops is issued as packed pairs (FFMA2, fma.rn.f32x2): same
 // roundings as the scalar fma, half the issue slots.
 // =================================================================================================
-#define SYN_MAXTAPS 32
 #define SYN_STAGES 3      // ring depth per warp: items (one GF component x four corners) in flight
 #define SYN_ITEM_BYTES (4 * 32 * 16)
 
@@ -712,12 +718,21 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
                 make_pairs(P3, A3, E3, G3, nz);
             }
             // ---- taps (sparse_trace.f90:647-695): one read-modify-write of the strips per distinct quad shift ----------
-            {
-                const int qb = q - baseq;
-                for (int m = 0; m < nstep; m++) {
-                    const int qrel = qb + __shfl_sync(0xffffffffu, my_q, m);
-                    const float h0 = __shfl_sync(0xffffffffu, my_h0, m), h1 = __shfl_sync(0xffffffffu, my_h1, m), h2 = __shfl_sync(0xffffffffu, my_h2, m),
-                                h3 = __shfl_sync(0xffffffffu, my_h3, m), h4 = __shfl_sync(0xffffffffu, my_h4, m);
+            const int qb = q - baseq;
+            const int srcl = q_last - q0 + 1;   // lane that holds the last quad of the windows (last chunk only)
+            float e1 = 0.f, e2 = 0.f, e3 = 0.f;
+            if (!more) {
+                float d0;
+                if (H) { unpk2(A1.hi, d0, e1); unpk2(A2.hi, d0, e2); e1 = __shfl_sync(0xffffffffu, e1, srcl); e2 = __shfl_sync(0xffffffffu, e2, srcl); }
+                if (V) { unpk2(A3.hi, d0, e3); e3 = __shfl_sync(0xffffffffu, e3, srcl); }
+                (void)d0;
+            }
+            // the entries [r0, r0 + nr) of the group's shift table, entry m held by lane m
+            auto apply_steps = [&](int nr, int t_q, float t_h0, float t_h1, float t_h2, float t_h3, float t_h4, float t_W) {
+                for (int m = 0; m < nr; m++) {
+                    const int qrel = qb + __shfl_sync(0xffffffffu, t_q, m);
+                    const float h0 = __shfl_sync(0xffffffffu, t_h0, m), h1 = __shfl_sync(0xffffffffu, t_h1, m), h2 = __shfl_sync(0xffffffffu, t_h2, m),
+                                h3 = __shfl_sync(0xffffffffu, t_h3, m), h4 = __shfl_sync(0xffffffffu, t_h4, m);
                     const int ok = active && (unsigned)qrel < (unsigned)nq;
                     // lanes without a quad read the group's record instead (nobody writes it now) and do not store
                     const unsigned a = acc_s + ((unsigned)qrel << 4);
@@ -725,21 +740,26 @@ __device__ __forceinline__ void synth_warp(const GfdbDev& db, const GeoRec* __re
                     if (V) rmw_quad(ok ? a + 2 * strip_bytes : rec_s, ok, E3, G3, h0, h1, h2, h3, h4);
                     __syncwarp();
                 }
-            }
-            if (!more) {
-                // ---- end-value repetition (sparse_trace.f90:696-703): every sample right of the last processed quad gets
-                // (wl+wr)*A_end; recorded as a step at quad q_last+1+shift, prefix-summed at the end.  Lane j owns the j-th
-                // distinct quad shift of the group: no two lanes share a word.
-                const int srcl = q_last - q0 + 1;
-                float d0, e1 = 0.f, e2 = 0.f, e3 = 0.f;
-                if (H) { unpk2(A1.hi, d0, e1); unpk2(A2.hi, d0, e2); e1 = __shfl_sync(0xffffffffu, e1, srcl); e2 = __shfl_sync(0xffffffffu, e2, srcl); }
-                if (V) { unpk2(A3.hi, d0, e3); e3 = __shfl_sync(0xffffffffu, e3, srcl); }
-                (void)d0;
-                const int qs = q_last + 1 + my_q - baseq;
-                if (lane < nstep && (unsigned)qs < (unsigned)nq) {
-                    if (H) { step[qs] += my_W * e1; step[nq + qs] += my_W * e2; }
-                    if (V) step[2 * nq + qs] += my_W * e3;
+                if (!more) {
+                    // ---- end-value repetition (sparse_trace.f90:696-703): every sample right of the last processed quad gets
+                    // (wl+wr)*A_end; recorded as a step at quad q_last+1+shift, prefix-summed at the end.  Lane j owns the j-th
+                    // distinct quad shift of the round: no two lanes share a word.
+                    const int qs = q_last + 1 + t_q - baseq;
+                    if (lane < nr && (unsigned)qs < (unsigned)nq) {
+                        if (H) { step[qs] += t_W * e1; step[nq + qs] += t_W * e2; }
+                        if (V) step[2 * nq + qs] += t_W * e3;
+                    }
+                    __syncwarp();
                 }
+            };
+            apply_steps(min(nstep, 32), my_q, my_h0, my_h1, my_h2, my_h3, my_h4, my_W);
+            for (int r0 = 32; r0 < nstep; r0 += 32) {   // more than 32 distinct quad shifts (long rise times): further rounds
+                int t_q = 0; float t_h0 = 0.f, t_h1 = 0.f, t_h2 = 0.f, t_h3 = 0.f, t_h4 = 0.f, t_W = 0.f;
+                if (r0 + lane < nstep) {
+                    const float4 ta = __ldg(taprec + 2 * ((size_t)tt + r0 + lane)), tb = __ldg(taprec + 2 * ((size_t)tt + r0 + lane) + 1);
+                    t_q = __float_as_int(ta.x); t_h0 = ta.y; t_h1 = ta.z; t_h2 = ta.w; t_h3 = tb.x; t_h4 = tb.y; t_W = tb.z;
+                }
+                apply_steps(min(nstep - r0, 32), t_q, t_h0, t_h1, t_h2, t_h3, t_h4, t_W);
             }
         }
         __syncwarp();
@@ -903,14 +923,16 @@ __global__ void __launch_bounds__(256, 2) k_synth(GfdbDev db, const ReceiverDev*
 // shifted copies of the data-span part of the strip (strip_fold sparse_trace.f90:379-402, strip_dataspan
 // :347-377).  One CTA per (candidate, receiver, component); the row is rewritten in place.
 // =================================================================================================
-#define FOLD_MAXSHIFTS 1024
+#define FOLD_TILE 1024     // shifts whose weights are tabulated in shared memory at a time
 __global__ void __launch_bounds__(256) k_fold(const ReceiverDev* __restrict__ rcv, int nrcv, const CandDev* __restrict__ cands,
                                                float* __restrict__ seis, size_t seis_stride, SeisHdr* __restrict__ shdrs, float dt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* d = reinterpret_cast<float*>(smem_raw);   // copy of the strip
-    __shared__ float s_wl[FOLD_MAXSHIFTS], s_wr[FOLD_MAXSHIFTS], s_w[FOLD_MAXSHIFTS];
-    __shared__ int s_its[FOLD_MAXSHIFTS];
-    __shared__ int s_ds0, s_ds1, s_n, s_itsmin, s_itsmax;
+    float* vacc = d + seis_stride;                   // the folded row while it is being summed
+    __shared__ float s_wl[FOLD_TILE], s_wr[FOLD_TILE], s_w[FOLD_TILE];
+    __shared__ int s_its[FOLD_TILE];
+    __shared__ int s_ds0, s_ds1;
+    __shared__ float s_sum;
     const int item = blockIdx.x;
     const int ic = item % KIWI_MAX_COMP, pair = item / KIWI_MAX_COMP;
     const int b = pair / nrcv, ir = pair % nrcv;
@@ -935,50 +957,54 @@ __global__ void __launch_bounds__(256) k_fold(const ReceiverDev* __restrict__ rc
         atomicMin(&s_ds0, first);
         atomicMax(&s_ds1, lastdiff + 1);
     }
-    if (threadIdx.x == 0) {   // receiver.f90:868-885: boxcar weights of the shifted copies
-        const float r0 = -risetime / 2.f, r1 = risetime / 2.f;
-        const int nshifts = min(1 + 2 * (int)roundf(0.5f * risetime / dt), FOLD_MAXSHIFTS);
+    // receiver.f90:868-885: boxcar weights of the shifted copies
+    const float r0 = -risetime / 2.f, r1 = risetime / 2.f;
+    const int nshifts = 1 + 2 * (int)roundf(0.5f * risetime / dt);
+    auto shift_time = [&](int is /* 1-based */) { return ((float)(is - 1) - 0.5f * (float)(nshifts - 1)) * dt; };
+    auto raw_weight = [&](float ts) { const float a0 = ts - dt / 2.f, a1 = ts + dt / 2.f; return fmaxf(0.f, fminf(r1, a1) - fmaxf(r0, a0)); };
+    if (threadIdx.x == 0) {   // (summed in shift order, as the reference does)
         float sum = 0.f;
-        for (int is = 1; is <= nshifts; is++) {
-            const float ts = ((float)(is - 1) - 0.5f * (float)(nshifts - 1)) * dt;
-            const float a0 = ts - dt / 2.f, a1 = ts + dt / 2.f;
-            const float w = fmaxf(0.f, fminf(r1, a1) - fmaxf(r0, a0));
-            s_w[is - 1] = w;
-            s_wr[is - 1] = D_(ts, dt);   // shift in samples, split below
-            sum = A_(sum, w);
-        }
-        int imin = INT_MAX, imax = INT_MIN;
-        for (int i = 0; i < nshifts; i++) {
-            const float w = D_(s_w[i], sum);
-            const float rshift = s_wr[i];
-            const int its = (int)floorf(rshift);
-            const float wr0 = S_(rshift, (float)its), wl0 = S_(1.f, wr0);   // sparse_trace.f90:639-646
-            s_its[i] = its; s_w[i] = w; s_wr[i] = M_(wr0, w); s_wl[i] = M_(wl0, w);
-            imin = min(imin, its); imax = max(imax, its);
-        }
-        s_n = nshifts; s_itsmin = imin; s_itsmax = imax;
+        for (int is = 1; is <= nshifts; is++) sum = A_(sum, raw_weight(shift_time(is)));
+        s_sum = sum;
     }
     __syncthreads();
     const int ds0 = s_ds0, ds1 = s_ds1;
     if (ds1 < ds0) return;
-    const int nshifts = s_n;
+    const float sum = s_sum;
+    // sample shifts grow with the shift number: the extreme ones are the first and the last
+    const int itsmin = (int)floorf(D_(shift_time(1), dt)), itsmax = (int)floorf(D_(shift_time(nshifts), dt));
     // new strip span (growth of trace_multiply_add, sparse_trace.f90:649-668), clamped to the row
-    const int nlo = max(min(sh.lo, sh.lo + ds0 + s_itsmin), sh.base);
-    const int nhi = min(max(sh.hi, sh.lo + ds1 + s_itsmax + 1), sh.base + (int)seis_stride - 1);
+    const int nlo = max(min(sh.lo, sh.lo + ds0 + itsmin), sh.base);
+    const int nhi = min(max(sh.hi, sh.lo + ds1 + itsmax + 1), sh.base + (int)seis_stride - 1);
     const float lastval = d[ds1];
-    for (int x = nlo + (int)threadIdx.x; x <= nhi; x += blockDim.x) {
-        const int xr = x - sh.lo;   // index relative to the old strip start
-        float v = 0.f;
-        for (int i = 0; i < nshifts; i++) {
-            const int y = xr - s_its[i];          // sample of the data-span trace under the left weight
-            if (y > ds1) { if (lastval != 0.f) v = A_(v, M_(s_w[i], lastval)); }                   // :696-703
-            else if (y >= ds0) {
-                v = A_(v, M_(s_wl[i], d[y]));
-                if (y - 1 >= ds0) v = A_(v, M_(s_wr[i], d[y - 1]));
-            }
+    for (int x = nlo + (int)threadIdx.x; x <= nhi; x += blockDim.x) vacc[x - nlo] = 0.f;
+    for (int t0 = 0; t0 < nshifts; t0 += FOLD_TILE) {
+        const int nt = min(FOLD_TILE, nshifts - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nt; i += blockDim.x) {
+            const float ts = shift_time(t0 + i + 1);
+            const float w = D_(raw_weight(ts), sum);
+            const float rshift = D_(ts, dt);
+            const int its = (int)floorf(rshift);
+            const float wr0 = S_(rshift, (float)its), wl0 = S_(1.f, wr0);   // sparse_trace.f90:639-646
+            s_its[i] = its; s_w[i] = w; s_wr[i] = M_(wr0, w); s_wl[i] = M_(wl0, w);
         }
-        row[x - sh.base] = v;
+        __syncthreads();
+        for (int x = nlo + (int)threadIdx.x; x <= nhi; x += blockDim.x) {
+            const int xr = x - sh.lo;   // index relative to the old strip start
+            float v = vacc[x - nlo];
+            for (int i = 0; i < nt; i++) {
+                const int y = xr - s_its[i];          // sample of the data-span trace under the left weight
+                if (y > ds1) { if (lastval != 0.f) v = A_(v, M_(s_w[i], lastval)); }                   // :696-703
+                else if (y >= ds0) {
+                    v = A_(v, M_(s_wl[i], d[y]));
+                    if (y - 1 >= ds0) v = A_(v, M_(s_wr[i], d[y - 1]));
+                }
+            }
+            vacc[x - nlo] = v;
+        }
     }
+    for (int x = nlo + (int)threadIdx.x; x <= nhi; x += blockDim.x) row[x - sh.base] = vacc[x - nlo];
     if (threadIdx.x == 0) { sh.lo = nlo; sh.hi = nhi; shdrs[item] = sh; }
 }
 
@@ -1207,10 +1233,11 @@ __global__ void __launch_bounds__(256) k_misfit_general(const ReceiverDev* __res
                                                          const float* __restrict__ taperdata, const float2* __restrict__ tw, int tw_n,
                                                          int method, float dt, float syn_factor, int nmisfits, float* __restrict__ out,
                                                          int* __restrict__ status, int* __restrict__ fshift, int n_alloc, int nshift_alloc,
-                                                         const CandMap* __restrict__ map, int xs0, int xs1, int premethod) {
+                                                         const CandMap* __restrict__ map, int xs0, int xs1, int premethod,
+                                                         float2* __restrict__ zscratch /* transforms too long for shared memory: [CTA][n_alloc] */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* z = reinterpret_cast<float2*>(smem_raw);
-    float* sm_m = reinterpret_cast<float*>(z + n_alloc);
+    float2* z = zscratch ? zscratch + (size_t)blockIdx.x * n_alloc : reinterpret_cast<float2*>(smem_raw);
+    float* sm_m = reinterpret_cast<float*>(smem_raw) + (zscratch ? 0 : 2 * (size_t)n_alloc);
     float* sm_n = sm_m + (size_t)nshift_alloc * KIWI_MAX_COMP;
     __shared__ double scratch[64];
     const int slot = blockIdx.x / nrcv, ir = blockIdx.x % nrcv;
@@ -1963,19 +1990,20 @@ void launch_ground_motion(const ReceiverDev* rcv, int nrcv, const CandDev* cands
     if (npairs > 0) k_ground_motion<<<(int)((npairs + 3) / 4), 128, 0, st>>>(rcv, nrcv, cands, ncand, seis, seis_stride, shdrs, taperdata, dt, syn_factor, out);
 }
 
-size_t misfit_general_smem_bytes(int n_alloc, int nshift_alloc) {
+size_t misfit_general_smem_bytes(int n_alloc, int nshift_alloc) {   // n_alloc = 0: the transform buffer lives in global memory
     return (size_t)n_alloc * sizeof(float2) + (size_t)2 * nshift_alloc * KIWI_MAX_COMP * sizeof(float);
 }
 cudaError_t launch_misfit_general(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, const float* seis, size_t seis_stride,
                                   const SeisHdr* shdrs, const float* refdata, const float* taperdata, const float2* tw, int tw_n, int method,
                                   float dt, float syn_factor, int nmisfits, float* out, int* status, int* fshift, int n_alloc,
-                                  int nshift_alloc, const CandMap* map, cudaStream_t st, int xs0, int xs1, int premethod) {
-    const size_t smem = misfit_general_smem_bytes(n_alloc, nshift_alloc);
+                                  int nshift_alloc, const CandMap* map, cudaStream_t st, int xs0, int xs1, int premethod, float2* zscratch) {
+    const size_t smem = misfit_general_smem_bytes(zscratch ? 0 : n_alloc, nshift_alloc);
     cudaError_t e = cudaFuncSetAttribute(k_misfit_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (ncand * nrcv > 0)
         k_misfit_general<<<ncand * nrcv, 256, smem, st>>>(rcv, nrcv, cands, seis, seis_stride, shdrs, refdata, taperdata, tw, tw_n, method, dt,
-                                                         syn_factor, nmisfits, out, status, fshift, n_alloc, nshift_alloc, map, xs0, xs1, premethod);
+                                                         syn_factor, nmisfits, out, status, fshift, n_alloc, nshift_alloc, map, xs0, xs1, premethod,
+                                                         zscratch);
     return cudaGetLastError();
 }
 
@@ -2006,7 +2034,7 @@ void launch_mt_contract(const ReceiverDev* rcv, int nrcv, const MtLoc* locs, int
 
 cudaError_t launch_fold(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, float* seis, size_t seis_stride, SeisHdr* shdrs,
                         float dt, cudaStream_t st) {
-    const size_t smem = seis_stride * sizeof(float);
+    const size_t smem = 2 * seis_stride * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(k_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const long long items = (long long)ncand * nrcv * KIWI_MAX_COMP;

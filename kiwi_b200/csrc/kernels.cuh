@@ -37,7 +37,8 @@ size_t misfit_general_smem_bytes(int n_alloc, int nshift_alloc);
 cudaError_t launch_misfit_general(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, const float* seis, size_t seis_stride,
                                   const SeisHdr* shdrs, const float* refdata, const float* taperdata, const float2* tw, int tw_n, int method,
                                   float dt, float syn_factor, int nmisfits, float* out, int* status, int* fshift, int n_alloc,
-                                  int nshift_alloc, const CandMap* map, cudaStream_t st, int xs0 = 0, int xs1 = 0, int premethod = 0);
+                                  int nshift_alloc, const CandMap* map, cudaStream_t st, int xs0 = 0, int xs1 = 0, int premethod = 0,
+                                  float2* zscratch = nullptr);
 cudaError_t launch_probe_export(const ReceiverDev* rcv, int ir, int ic, const CandDev* cands, const float* seis, size_t seis_stride, const SeisHdr* shdrs, int nrcv,
                                 const float* refdata, const float* taperdata, const float2* tw, int tw_n, int which_probe, int processing, int spectrum,
                                 float dt, int n_alloc, int* hdr, float* out, cudaStream_t st);
