@@ -91,7 +91,7 @@ struct kiwi_ctx {
     // database (set_database)
     bool db_set = false;
     GfdbDev db{};
-    DevBuf d_slabs, d_nodes, d_tspan;
+    DevBuf d_slabs, d_nodes, d_tspan, d_nspan;
     std::vector<NodeInfo> h_nodes;
     std::vector<int2> h_tspan;
     int db_tmin = 0, db_tmax = 0;
@@ -546,7 +546,7 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
     if (c->work_budget == 0) {
         size_t fr = 0, tot = 0;
         CU_OK(cudaMemGetInfo(&fr, &tot));
-        c->work_budget = std::min<size_t>(fr / 2, (size_t)24 << 30);
+        c->work_budget = std::min<size_t>(fr / 2, (size_t)64 << 30);
         for (DevBuf* b : {&c->d_recs, &c->d_seis}) c->work_budget += b->cap;   // already ours
     }
     const size_t per_cand_geo = (size_t)nrcv * max_groups * sizeof(GeoRec) + (size_t)nrcv * (sizeof(PairHdr) + KIWI_MAX_COMP * sizeof(SeisHdr));
@@ -942,7 +942,7 @@ void kiwi_destroy(kiwi_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf* b : {&c->d_slabs, &c->d_nodes, &c->d_tspan, &c->d_rcv, &c->d_refdata, &c->d_taper, &c->d_cands, &c->d_bilat, &c->d_gf, &c->d_gi,
+    for (DevBuf* b : {&c->d_slabs, &c->d_nodes, &c->d_tspan, &c->d_nspan, &c->d_rcv, &c->d_refdata, &c->d_taper, &c->d_cands, &c->d_bilat, &c->d_gf, &c->d_gi,
                       &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift, &c->d_map, &c->d_status_out, &c->d_taprec, &c->d_partial, &c->d_fftz, &c->d_gm, &c->d_xcorr, &c->d_mtlocs, &c->d_mts, &c->d_candof, &c->d_orc, &c->d_orw, &c->d_obw, &c->d_oout, &c->d_obest, &c->d_obestv})
         b->release();
     c->h_stage.release(); c->h_out.release();
@@ -1018,13 +1018,28 @@ int kiwi_set_database(kiwi_ctx* c, kiwi_gfdb* db) {
             CU_OK(cudaStreamSynchronize(c->stream));
         }
     }
+    {   // span unions of the component sets of every node (what make_seismogram's strips grow by, seismogram.f90:167-250)
+        std::vector<int4> ns(2 * nnodes);
+        const int set_of[10] = {0, 0, 0, 1, 1, 2, 2, 2, 0, 2};   // g1 g2 g3 | g4 g5 | g6 g7 g8 | g9 | g10
+        for (size_t i = 0; i < nnodes; i++) {
+            int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+            for (int k = 0; k < ng; k++) {
+                const int2 sp = c->h_tspan[i * ng + k];
+                lo[set_of[k]] = std::min(lo[set_of[k]], sp.x); hi[set_of[k]] = std::max(hi[set_of[k]], sp.y);
+            }
+            ns[2 * i] = make_int4(lo[0], hi[0], lo[1], hi[1]); ns[2 * i + 1] = make_int4(lo[2], hi[2], 0, 0);
+        }
+        CU_OK(c->d_nspan.ensure(sizeof(int4) * ns.size()));
+        CU_OK(cudaMemcpyAsync(c->d_nspan.p, ns.data(), sizeof(int4) * ns.size(), cudaMemcpyHostToDevice, c->stream));
+        CU_OK(cudaStreamSynchronize(c->stream));
+    }
     CU_OK(cudaMemcpyAsync(c->d_nodes.p, c->h_nodes.data(), sizeof(NodeInfo) * nnodes, cudaMemcpyHostToDevice, c->stream));
     CU_OK(cudaMemcpyAsync(c->d_tspan.p, c->h_tspan.data(), sizeof(int2) * nnodes * ng, cudaMemcpyHostToDevice, c->stream));
     CU_OK(cudaStreamSynchronize(c->stream));
     GfdbDev& d = c->db;
     d.dt = db->dt; d.dx = db->dx; d.dz = db->dz; d.firstx = db->firstx; d.firstz = db->firstz;
     d.nx = db->nx; d.nz = db->nz; d.ng = db->ng;
-    d.slabs = c->d_slabs.as<float>(); d.nodes = c->d_nodes.as<NodeInfo>(); d.tspan = c->d_tspan.as<int2>(); d.lastval = nullptr;
+    d.slabs = c->d_slabs.as<float>(); d.nodes = c->d_nodes.as<NodeInfo>(); d.tspan = c->d_tspan.as<int2>(); d.nspan = c->d_nspan.as<int4>(); d.lastval = nullptr;
     c->db_set = true;
     c->receivers_dirty = true; c->src_dirty = true; c->last.valid = false; c->work_budget = 0;
     return 0;

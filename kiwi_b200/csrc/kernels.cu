@@ -209,14 +209,16 @@ struct SpanAcc {
 __device__ __forceinline__ int warp_min(int v) { for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
 __device__ __forceinline__ int warp_max(int v) { for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
 
-// trace-span union of the GF components of one set at the corners of one group
-__device__ __forceinline__ void set_span(const GfdbDev& db, const int inode[4], int ncorner, const int* igs, int nig, int& lo, int& hi) {
-    lo = INT_MAX; hi = INT_MIN;
-    for (int c = 0; c < ncorner; c++)
-        for (int k = 0; k < nig; k++) {
-            int2 s = __ldg(&db.tspan[(size_t)inode[c] * db.ng + (igs[k] - 1)]);
-            lo = min(lo, s.x); hi = max(hi, s.y);
-        }
+// trace-span unions of the three component sets over the corners of one group (tabulated per node by kiwi_set_database)
+struct SetSpans { int lo1, hi1, lo2, hi2, lo3, hi3; };
+__device__ __forceinline__ SetSpans corner_spans(const GfdbDev& db, const int inode[4], int ncorner) {
+    SetSpans u = {INT_MAX, INT_MIN, INT_MAX, INT_MIN, INT_MAX, INT_MIN};
+    for (int c = 0; c < ncorner; c++) {
+        const int4 a = __ldg(&db.nspan[2 * (size_t)inode[c]]), b = __ldg(&db.nspan[2 * (size_t)inode[c] + 1]);
+        u.lo1 = min(u.lo1, a.x); u.hi1 = max(u.hi1, a.y); u.lo2 = min(u.lo2, a.z); u.hi2 = max(u.hi2, a.w);
+        u.lo3 = min(u.lo3, b.x); u.hi3 = max(u.hi3, b.y);
+    }
+    return u;
 }
 
 // SINGLE: every candidate has one group (point sources: the 6 x nloc x nrcv basis syntheses of a moment-tensor grid search are
@@ -238,8 +240,6 @@ __global__ void __launch_bounds__(256, 3) k_geometry(GfdbDev db, const ReceiverD
 
     const bool need_h = (R.ja | R.jr | R.jn | R.je) != 0;
     const bool need_v = R.jd != 0;
-    const int set1[4] = {1, 2, 3, 9}, set2[2] = {4, 5}, set3[4] = {6, 7, 8, 10};
-    const int n1 = db.ng == 10 ? 4 : 3, n3 = db.ng == 10 ? 4 : 3;
 
     SpanAcc urot, n1all, n2all, s3; urot.init(); n1all.init(); n2all.init(); s3.init();
     int last_rot = -1, any_nonrot = 0;
@@ -320,16 +320,13 @@ __global__ void __launch_bounds__(256, 3) k_geometry(GfdbDev db, const ReceiverD
             }
             if (ok && (need_h || need_v)) {
                 const int smin = g.its_min[gi], smax = g.its_max[gi];
-                int lo, hi;
+                const SetSpans u = corner_spans(db, inode, ncorner);
                 if (need_h) {
-                    int lo1, hi1, lo2, hi2;
-                    set_span(db, inode, ncorner, set1, n1, lo1, hi1);
-                    set_span(db, inode, ncorner, set2, 2, lo2, hi2);
-                    lo1 += smin; hi1 += smax + 1; lo2 += smin; hi2 += smax + 1;   // sparse_trace.f90:649-653
+                    const int lo1 = u.lo1 + smin, hi1 = u.hi1 + smax + 1, lo2 = u.lo2 + smin, hi2 = u.hi2 + smax + 1;   // sparse_trace.f90:649-653
                     if (flags & GEO_ROT) { urot.add(lo1, hi1); urot.add(lo2, hi2); last_rot = max(last_rot, ip); }
                     else { n1all.add(lo1, hi1); n2all.add(lo2, hi2); any_nonrot = 1; }
                 }
-                if (need_v) { set_span(db, inode, ncorner, set3, n3, lo, hi); s3.add(lo + smin, hi + smax + 1); }
+                if (need_v) s3.add(u.lo3 + smin, u.hi3 + smax + 1);
             }
         }
     }
@@ -377,10 +374,8 @@ __global__ void __launch_bounds__(256, 3) k_geometry(GfdbDev db, const ReceiverD
             int inode[4]; const int ncorner = single ? 1 : 4;
             for (int c = 0; c < ncorner; c++) inode[c] = (cx[c] - 1) * db.nz + (cz[c] - 1);
             const int smin = g.its_min[gi], smax = g.its_max[gi];
-            int lo1, hi1, lo2, hi2;
-            set_span(db, inode, ncorner, set1, n1, lo1, hi1);
-            set_span(db, inode, ncorner, set2, 2, lo2, hi2);
-            n1before.add(lo1 + smin, hi1 + smax + 1); n2before.add(lo2 + smin, hi2 + smax + 1);
+            const SetSpans u = corner_spans(db, inode, ncorner);
+            n1before.add(u.lo1 + smin, u.hi1 + smax + 1); n2before.add(u.lo2 + smin, u.hi2 + smax + 1);
         }
     }
     int w4[4] = {n1before.lo, n2before.lo, n1before.hi, n2before.hi};
@@ -1967,6 +1962,7 @@ cudaError_t launch_synth(GfdbDev db, const ReceiverDev* rcv, int nrcv, const Can
                          size_t rec_stride, const PairHdr* hdrs, int nq_alloc, int margin_q, int nwarps, float* seis, size_t seis_stride,
                          SeisHdr* shdrs, int nbands, float* partial, cudaStream_t st) {
     size_t smem = synth_smem_bytes(nwarps, nq_alloc);
+    if (const char* ev = getenv("KIWI_SYNTH_SMEM_PAD")) smem += (size_t)atoi(ev);   // occupancy experiments
     cudaError_t e = cudaFuncSetAttribute(k_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     for (int band = 0; band < nbands; band++)

@@ -27,6 +27,8 @@ struct GfdbDev {
     const float* slabs;       // all slabs
     const NodeInfo* nodes;    // [nx*nz], inode = (ix-1)*nz + (iz-1)
     const int2* tspan;        // [nx*nz*ng] first/last sample index of every trace (trace%span)
+    const int4* nspan;        // [nx*nz][2] span unions of a node's component sets {lo1, hi1, lo2, hi2} {lo3, hi3, -, -}: set 1 = g1 g2 g3 (g9)
+                              // -> radial, set 2 = g4 g5 -> transverse, set 3 = g6 g7 g8 (g10) -> vertical (seismogram.f90:167-250)
     const float* lastval;     // [nx*nz*ng] last stored sample of every trace
 };
 

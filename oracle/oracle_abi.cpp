@@ -3,6 +3,7 @@
 // The entry points deliberately mirror include/kiwi_b200.h one to one.
 #include "ko_engine.hpp"
 #include "ko_interp.hpp"
+#include "ko_ahfull.hpp"
 #include <chrono>
 
 using namespace ko;
@@ -415,4 +416,21 @@ double oracle_time_eval(void* h, int sourcetype, int ns, int nparams, const floa
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+
+// the ten packed traces gfdb_build_ahfull stores for the input line "x z nfflag ffflag" (ko_ahfull.hpp), each unpacked onto its
+// span: span0[ig], len[ig], data[ig*cap ..]
+int oracle_ahfull_node(float rho, float alpha, float beta, const float* stf, int nstf, float dt, float x, float z, int nfflag, int ffflag,
+                       int* span0, int* len, float* data, int cap) {
+    const ahfull::Medium m = ahfull::make_medium(rho, alpha, beta, stf, nstf, dt);
+    Trace tr[10];
+    ahfull::addentry(m, dt, x, z, nfflag != 0, ffflag != 0, tr);
+    for (int ig = 0; ig < 10; ig++) {
+        Strip s;
+        trace_unpack(tr[ig], s);
+        span0[ig] = tr[ig].span[0]; len[ig] = s.size();
+        if (s.size() > cap) return 1;
+        for (int i = 0; i < s.size(); i++) data[(size_t)ig * cap + i] = (float)s.d[i];
+    }
+    return 0;
+}
 }  // extern "C"

@@ -384,3 +384,16 @@ def gulunay(a, l1, l2, ntmargin, margin1, margin2, wide=False):
                           C.c_int(ntmargin), C.c_int(margin1), C.c_int(margin2))
     assert rc == 0
     return a, out
+
+
+def ahfull_node(rho, alpha, beta, stf, dt, x, z, nfflag=True, ffflag=True, cap=1 << 14):
+    """the ten traces of gfdb_build_ahfull for one node, restated from the Fortran (oracle/ko_ahfull.hpp): [(span0, samples)] * 10"""
+    L = lib()
+    stf = _f32(stf).ravel()
+    span0 = np.zeros(10, np.int32); length = np.zeros(10, np.int32); data = np.zeros((10, cap), np.float32)
+    rc = L.oracle_ahfull_node(C.c_float(rho), C.c_float(alpha), C.c_float(beta), stf.ctypes.data_as(fp), C.c_int(stf.size), C.c_float(dt),
+                              C.c_float(x), C.c_float(z), C.c_int(int(nfflag)), C.c_int(int(ffflag)), span0.ctypes.data_as(ip),
+                              length.ctypes.data_as(ip), data.ctypes.data_as(fp), C.c_int(cap))
+    if rc != 0:
+        raise OracleError("oracle_ahfull_node: trace longer than %d samples" % cap)
+    return [(int(span0[i]), data[i, :length[i]].copy()) for i in range(10)]

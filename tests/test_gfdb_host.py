@@ -137,3 +137,44 @@ def test_kgf1_reader_refuses_corrupt_files(tmp_path):
     len_table = hdr + 4 * ntr
     check(raw[:len_table] + struct.pack("<i", -5) + raw[len_table + 4:], "trace table")          # negative length
     check(b"JUNK" + raw[4:], "not a KGF1")
+
+
+def test_ahfull_builder_against_the_independent_restatement():
+    """the product's fixture generator (csrc/gfdb_host.cpp) and the oracle's (oracle/ko_ahfull.hpp) were written separately from
+    gfdb_build_ahfull.f90 / elseis.f90; every trace of a node must come out bit for bit the same (span, length, samples) -- the
+    database is what BOTH the CUDA path and the oracle consume in the parity tests"""
+    from kiwi_b200.engine import KIWIBENCH_STF
+    from oracle_lib import ahfull_node
+    rng = np.random.default_rng(2)
+    for db, (rho, alpha, beta), nf in ((sc.small_db(), (2700.0, 6000.0, 3464.0), True), (sc.small_db_ng8(), (2700.0, 6000.0, 3464.0), False)):
+        m = db.meta()
+        span0, length, offset, data = db.view()
+        nodes = {(1, 1), (m["nx"], m["nz"]), (1, m["nz"]), (m["nx"], 1)} | {(int(rng.integers(1, m["nx"] + 1)), int(rng.integers(1, m["nz"] + 1))) for _ in range(40)}
+        for ix, iz in sorted(nodes):
+            x = np.float32(m["firstx"]) + np.float32(ix - 1) * np.float32(m["dx"])
+            z = np.float32(m["firstz"]) + np.float32(iz - 1) * np.float32(m["dz"])
+            want = ahfull_node(rho, alpha, beta, KIWIBENCH_STF, m["dt"], float(x), float(z), nf, True)
+            for ig in range(1, m["ng"] + 1):
+                i = ((ix - 1) * m["nz"] + (iz - 1)) * m["ng"] + (ig - 1)
+                s0, d = want[ig - 1]
+                assert (span0[i], length[i]) == (s0, d.size), (ix, iz, ig)
+                assert np.array_equal(data[offset[i]:offset[i] + length[i]].view(np.uint32), d.view(np.uint32)), (ix, iz, ig)
+
+
+def test_ahfull_builder_bench_l_nodes_against_the_restatement():
+    """the same on nodes of the benchmark database's geometry (bench-L: dx 100 m, dz 200 m, dt 0.1 s)"""
+    from kiwi_b200.engine import KIWIBENCH_STF
+    from oracle_lib import ahfull_node
+    db = Gfdb.create(40, 12, 10, 0.1, 100.0, 200.0, 100.0 + 1500 * 100.0, 0.0).build_ahfull(2700.0, 6000.0, 3464.0, KIWIBENCH_STF)
+    m = db.meta()
+    span0, length, offset, data = db.view()
+    for ix in (1, 17, 40):
+        for iz in (1, 6, 12):
+            x = np.float32(m["firstx"]) + np.float32(ix - 1) * np.float32(m["dx"])
+            z = np.float32(m["firstz"]) + np.float32(iz - 1) * np.float32(m["dz"])
+            want = ahfull_node(2700.0, 6000.0, 3464.0, KIWIBENCH_STF, 0.1, float(x), float(z), True, True)
+            for ig in range(1, 11):
+                i = ((ix - 1) * m["nz"] + (iz - 1)) * 10 + (ig - 1)
+                s0, d = want[ig - 1]
+                assert (span0[i], length[i]) == (s0, d.size), (ix, iz, ig)
+                assert np.array_equal(data[offset[i]:offset[i] + length[i]].view(np.uint32), d.view(np.uint32)), (ix, iz, ig)
