@@ -487,15 +487,23 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
             d.out_of.assign(n, 0); d.moment.assign(n, 0.f);
             std::vector<int> fill(d.first.begin(), d.first.end() - 1);
             for (int i = 0; i < n; i++) { const int j = fill[syn_of[i]]++; d.out_of[j] = i; d.moment[j] = params[(size_t)i * nparams + 4]; }
+            // the shared synthesis is made with unit moment (the moment scales the synthetics afterwards, receiver.f90:853-904, slot by
+            // slot), so that its validity does not depend on which member of the group comes first in the batch
             std::vector<float> up((size_t)nu * nparams);
-            for (int u = 0; u < nu; u++) memcpy(&up[(size_t)u * nparams], params + (size_t)first_of[u] * nparams, (size_t)nparams * 4);
+            for (int u = 0; u < nu; u++) { memcpy(&up[(size_t)u * nparams], params + (size_t)first_of[u] * nparams, (size_t)nparams * 4); up[(size_t)u * nparams + 4] = 1.f; }
             std::vector<int> ustatus(nu, 0), ostatus(n, 0);
             CU_OK(c->d_status_out.ensure(sizeof(int) * n));
             // (on the engine's stream: it is a non-blocking stream, work on the default stream is not ordered against its kernels)
             CU_OK(cudaMemsetAsync(c->d_status_out.p, 0, sizeof(int) * n, c->stream));
             if (eval_batch(c, sourcetype, nu, nparams, up.data(), d_out, ustatus.data(), true, nullptr, &d)) return 1;
             CU_OK(cudaMemcpy(ostatus.data(), c->d_status_out.p, sizeof(int) * n, cudaMemcpyDeviceToHost));
-            if (h_status) for (int i = 0; i < n; i++) h_status[i] = std::max(ostatus[i], ustatus[syn_of[i]]);
+            // a member whose own parameters the direct path would refuse: circular and point_lp sources check every parameter, the
+            // moment included (source_circular / source_point_lp set-up); the others take any moment and report what comes out
+            const bool moment_checked = sourcetype == KIWI_SOURCE_CIRCULAR || sourcetype == KIWI_SOURCE_POINT_LP;
+            if (h_status) for (int i = 0; i < n; i++) {
+                h_status[i] = std::max(ostatus[i], ustatus[syn_of[i]]);
+                if (moment_checked && !std::isfinite(params[(size_t)i * nparams + 4])) h_status[i] = KIWI_STATUS_BAD_PARAMS;
+            }
             c->last.valid = false;   // the tables describe the distinct syntheses, not the candidates
             return 0;
         }
@@ -876,7 +884,18 @@ int eval_mt_grid(kiwi_ctx* c, int n, const float* params, float* d_out, int* h_s
     };
     std::vector<int> bstatus((size_t)nloc * 6, 0);
     if (eval_batch(c, KIWI_SOURCE_MOMENT_TENSOR, nloc * 6, 11, basis.data(), nullptr, bstatus.data(), false, &hook)) return 1;
-    if (h_status) for (int i = 0; i < n; i++) h_status[i] = bstatus[(size_t)loc_of[i] * 6];
+    if (h_status) {   // status of the basis, or 2 where a misfit came out NaN/Inf (as k_misfit_td reports it on the direct path)
+        std::vector<int> nonfinite((size_t)n, 0);
+        CU_OK(c->d_status_out.ensure(sizeof(int) * (size_t)n));
+        CU_OK(cudaMemsetAsync(c->d_status_out.p, 0, sizeof(int) * (size_t)n, c->stream));
+        launch_flag_nonfinite(d_out, n, c->nmisfits * 2, c->d_status_out.as<int>(), c->stream);
+        CU_OK(cudaMemcpyAsync(nonfinite.data(), c->d_status_out.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+        CU_OK(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < n; i++) {
+            const int bs = bstatus[(size_t)loc_of[i] * 6];
+            h_status[i] = bs != KIWI_STATUS_OK ? bs : (nonfinite[i] ? KIWI_STATUS_NONFINITE : KIWI_STATUS_OK);
+        }
+    }
     *used = true;
     return 0;
 }

@@ -41,7 +41,11 @@ struct Dataset {
     uint64_t nbytes = 0;
     struct Attr { std::string name; int dtype_class; uint32_t dtype_size; std::vector<uint64_t> dims; const uint8_t* data; };
     std::vector<Attr> attrs;
-    uint64_t nelem() const { uint64_t n = 1; for (uint64_t d : dims) n *= d; return n; }
+    uint64_t nelem() const {   // (saturating: a product that overflows is larger than any file)
+        uint64_t n = 1;
+        for (uint64_t d : dims) { if (d != 0 && n > (1ull << 56) / d) return 1ull << 56; n *= d; }
+        return n;
+    }
 };
 
 class H5File {
@@ -213,28 +217,43 @@ class H5File {
     }
     // size in bytes of a datatype message (needed to step over it inside a version-2/3 attribute)
     void parse_layout(const uint8_t* p, uint64_t n, const uint8_t** data, uint64_t* nbytes) const {
-        if (n < 2) fail("gfdb: bad layout message in file: " + path_);
+        const std::string bad = "gfdb: bad layout message in file: " + path_;
+        if (n < 3) fail(bad);
         const unsigned ver = p[0];
         if (ver == 3) {
             const unsigned cls = p[1];
-            if (cls == 0) { const uint64_t sz = le(p + 2, 2); if (n < 4 + sz) fail("gfdb: bad compact layout in file: " + path_); *data = p + 4; *nbytes = sz; }
-            else if (cls == 1) {
+            if (cls == 0) {
+                if (n < 4) fail(bad);
+                const uint64_t sz = le(p + 2, 2);
+                if (n < 4 + sz) fail("gfdb: bad compact layout in file: " + path_);
+                *data = p + 4; *nbytes = sz;
+            } else if (cls == 1) {
+                if (n < 2 + (uint64_t)O_ + L_) fail(bad);
                 const uint64_t a = addr_at(p + 2), sz = le(p + 2 + O_, L_);
                 *nbytes = sz; *data = a == UNDEF ? nullptr : at(a, sz);
             } else fail("gfdb: chunked dataset layout is not supported (Kiwi writes contiguous datasets): " + path_);
         } else if (ver == 1 || ver == 2) {
             const unsigned rank = p[1], cls = p[2];
+            if (rank > 32) fail(bad);
             if (cls == 1) {
+                if (n < 8 + (uint64_t)O_ + 4 * (uint64_t)rank) fail(bad);
                 const uint64_t a = addr_at(p + 8);
                 uint64_t sz = 1;   // dimension sizes follow the address (4 bytes each); the last one is the element size
-                for (unsigned i = 0; i < rank; i++) sz *= le(p + 8 + O_ + 4 * i, 4);
+                for (unsigned i = 0; i < rank; i++) sz = mul_checked(sz, le(p + 8 + O_ + 4 * i, 4));
                 *nbytes = sz; *data = a == UNDEF ? nullptr : at(a, sz);
             } else if (cls == 0) {
                 const uint64_t q = 8 + 4 * (uint64_t)rank;
+                if (n < q + 4) fail(bad);
                 const uint64_t sz = le(p + q, 4);
+                if (n < q + 4 + sz) fail("gfdb: bad compact layout in file: " + path_);
                 *data = p + q + 4; *nbytes = sz;
             } else fail("gfdb: chunked dataset layout is not supported (Kiwi writes contiguous datasets): " + path_);
         } else fail("gfdb: unsupported layout message version in file: " + path_);
+    }
+    // products of file-controlled sizes: refuse what cannot be a size inside the file
+    uint64_t mul_checked(uint64_t a, uint64_t b) const {
+        if (a != 0 && b > (1ull << 48) / a) fail("gfdb: implausible dataset size in file: " + path_);
+        return a * b;
     }
     static uint64_t pad8(uint64_t v) { return (v + 7) & ~7ull; }
     Dataset::Attr parse_attribute(const uint8_t* p, uint64_t n) const {
@@ -255,8 +274,8 @@ class H5File {
         a.dims = parse_dataspace(p + q, ssz);
         q += padded ? pad8(ssz) : ssz;
         uint64_t ne = 1;
-        for (uint64_t d : a.dims) ne *= d;
-        if (q + ne * a.dtype_size > n) fail("gfdb: attribute data outside of its message in file: " + path_);
+        for (uint64_t d : a.dims) ne = mul_checked(ne, d);
+        if (q + mul_checked(ne, a.dtype_size) > n) fail("gfdb: attribute data outside of its message in file: " + path_);
         a.data = p + q;
         return a;
     }
@@ -320,7 +339,8 @@ extern "C" kiwi_gfdb* kiwi_gfdb_read_hdf(const char* basepath) {
                         // the reference reads attribute 0 as pofs and attribute 1 as ofs (creation order, :451-470); names are checked here
                         for (const Dataset::Attr& a : tr.attrs) { if (a.name == "pofs") pofs = &a; else if (a.name == "ofs") ofs = &a; }
                         if (!pofs || !ofs || pofs->dtype_class != 0 || ofs->dtype_class != 0 || pofs->dtype_size != 4 || ofs->dtype_size != 4 ||
-                            pofs->dims.size() != 1 || ofs->dims != pofs->dims || pofs->dims[0] < 1)
+                            pofs->dims.size() != 1 || ofs->dims != pofs->dims || pofs->dims[0] < 1 || pofs->dims[0] > (1u << 24) ||
+                            tr.dims[0] > (1ull << 28))
                             fail("gfdb: failed to get attributes of a dataset: " + cpath);
                         const int nstrips = (int)pofs->dims[0];
                         const long long npacked = (long long)tr.dims[0];
@@ -349,6 +369,10 @@ extern "C" kiwi_gfdb* kiwi_gfdb_read_hdf(const char* basepath) {
     } catch (const H5Error& e) {
         if (db) kiwi_gfdb_destroy(db);
         kiwi_set_error("%s", e.msg.c_str());
+        return nullptr;
+    } catch (const std::exception& e) {   // bad_alloc / length_error on sizes a corrupt file asks for: an error, not std::terminate
+        if (db) kiwi_gfdb_destroy(db);
+        kiwi_set_error("gfdb: %s while reading %s", e.what(), basepath);
         return nullptr;
     }
 }
@@ -382,5 +406,7 @@ extern "C" int kiwi_h5_read_root_dataset(const char* path, const char* name, int
         return 0;
     } catch (const H5Error& e) {
         return kiwi_set_error("%s", e.msg.c_str());
+    } catch (const std::exception& e) {
+        return kiwi_set_error("%s while reading %s", e.what(), path);
     }
 }

@@ -103,8 +103,7 @@ __global__ void __launch_bounds__(256) k_tap_table(GroupSoA g, TapSoA taps, floa
     const int tb = g.tap_begin[gi], tn_all = g.tap_count[gi], tt = g.tt_begin[gi];
     const unsigned lt = (1u << lane) - 1u;
     int nentries = 0, lo = INT_MAX, hi = INT_MIN;
-    // rounds of 32 taps (source_bilat.f90:274-315 puts no bound on nt): quad shifts are merged within a round; a quad shift that
-    // straddles two rounds simply gets two entries
+    // rounds of 32 taps (source_bilat.f90:274-315 puts no bound on nt)
     for (int t0 = 0; t0 < tn_all; t0 += 32) {
         const int tn = min(tn_all - t0, 32);
         const bool on = lane < tn;
@@ -132,13 +131,27 @@ __global__ void __launch_bounds__(256) k_tap_table(GroupSoA g, TapSoA taps, floa
                 W += wlj + wrj;
             }
         }
-        const unsigned lm = __ballot_sync(0xffffffffu, leader);
-        if (leader) {
+        // a quad shift that already has an entry from an earlier round is added to it (entries stay distinct: k_synth lets one lane
+        // per entry update the end-value step, and two entries of one quad shift would meet in the same word)
+        int found = -1;
+        if (leader && t0 > 0)
+            for (int i = 0; i < nentries && found < 0; i++)
+                if (__float_as_int(g.taprec[2 * ((size_t)tt + i)].x) == qoff) found = i;
+        if (leader && found >= 0) {
+            float4* e = g.taprec + 2 * ((size_t)tt + found);
+            const float4 a = e[0], b = e[1];
+            e[0] = make_float4(a.x, a.y + h[0], a.z + h[1], a.w + h[2]);
+            e[1] = make_float4(b.x + h[3], b.y + h[4], b.z + W, 0.f);
+        }
+        const bool fresh = leader && found < 0;
+        const unsigned lm = __ballot_sync(0xffffffffu, fresh);
+        if (fresh) {
             float4* e = g.taprec + 2 * ((size_t)tt + nentries + __popc(lm & lt));
             e[0] = make_float4(__int_as_float(qoff), h[0], h[1], h[2]);
             e[1] = make_float4(h[3], h[4], W, 0.f);
         }
         nentries += __popc(lm);
+        __syncwarp();   // (the entries written in this round are read by the next one)
         lo = min(lo, warp_min_i(on ? its : INT_MAX)); hi = max(hi, warp_max_i(on ? its : INT_MIN));
     }
     if (lane == 0) { g.nstep[gi] = nentries; g.its_min[gi] = lo; g.its_max[gi] = hi; }
@@ -1923,6 +1936,18 @@ __global__ void __launch_bounds__(256) k_row_argmin(const double* __restrict__ v
         __syncthreads();
     }
     if (threadIdx.x == 0) { best[blockIdx.x] = si[0]; bestv[blockIdx.x] = si[0] >= 0 ? sv[0] : nan(""); }
+}
+
+// flag[row] = 1 where row `row` of v[nrows][ncols] holds a NaN or an Inf (status 2 of a candidate, minimizer_engine.f90:1163-1166)
+__global__ void __launch_bounds__(256) k_flag_nonfinite(const float* __restrict__ v, int nrows, int ncols, int* __restrict__ flag) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= nrows) return;
+    bool bad = false;
+    for (int i = lane; i < ncols; i += 32) bad = bad || !isfinite(v[(size_t)row * ncols + i]);
+    if (__any_sync(0xffffffffu, bad) && lane == 0) flag[row] = 1;
+}
+void launch_flag_nonfinite(const float* v, int nrows, int ncols, int* flag, cudaStream_t st) {
+    if (nrows > 0 && ncols > 0) k_flag_nonfinite<<<(nrows + 7) / 8, 256, 0, st>>>(v, nrows, ncols, flag);
 }
 
 // ---- host-callable launch wrappers ---------------------------------------------------------------

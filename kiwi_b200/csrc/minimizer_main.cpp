@@ -86,6 +86,9 @@ struct State {
     std::vector<std::string> comps;   // component strings of the receivers
     float dt = 0.f;
     double ref_time = 0.;
+    float olat = 0.f, olon = 0.f;     // source location as given (degrees)
+    int src_type = 0;                 // the source set by set_source_params
+    std::vector<float> src_params;
 };
 
 // returns ok; answer / err filled
@@ -100,7 +103,8 @@ bool do_command(State& S, const std::string& cmd, const std::vector<std::string>
                                   "set_source_subparams_limits", "get_source_subparams", "minimize_lm", "get_peak_amplitudes", "get_arias_intensities",
                                   "shift_ref_seismogram", "autoshift_ref_seismogram", "set_misfit_filter_1", "output_cross_correlations",
                                   "get_cached_traces_memory", "set_cached_traces_memory_limit", "set_verbose", "set_ignore_sigint",
-                                  "get_principal_axes", "get_source_crustal_thickness", "output_distances", "output_seismogram_spectra"};
+                                  "get_principal_axes", "get_source_crustal_thickness", "output_distances", "output_seismogram_spectra",
+                                  "output_source_model"};
     bool is_known = false;
     for (const char* k : known) if (cmd == k) is_known = true;
     if (!is_known) return fail("unknown command: " + cmd);   // minimizer.f90:1809-1811
@@ -167,6 +171,7 @@ bool do_command(State& S, const std::string& cmd, const std::vector<std::string>
     if (cmd == "set_source_location") {
         if (w.size() != 4) return fail("usage: set_source_location latitude longitude reference-time");
         S.ref_time = atof(w[3].c_str());
+        S.olat = (float)atof(w[1].c_str()); S.olon = (float)atof(w[2].c_str());
         return kiwi_set_source_location(S.ctx, (float)atof(w[1].c_str()), (float)atof(w[2].c_str()), S.ref_time) ? cfail() : true;
     }
     if (cmd == "set_source_constraints") {
@@ -186,7 +191,35 @@ bool do_command(State& S, const std::string& cmd, const std::vector<std::string>
         const int np = kiwi_get_n_source_params(st);
         if (!to_floats(w, 2, &v)) return fail("failed to parse source params");
         if ((int)v.size() != np) return fail("source of type '" + w[1] + "' requires " + std::to_string(np) + " parameters.");
-        return kiwi_set_source_params(S.ctx, st, np, v.data()) ? cfail() : true;
+        if (kiwi_set_source_params(S.ctx, st, np, v.data())) return cfail();
+        S.src_type = st; S.src_params = v;
+        return true;
+    }
+    if (cmd == "output_source_model") {   // minimizer.f90:1085-1098, minimizer_engine.f90:948-978
+        if (w.size() != 2) return fail("usage: output_source_model filenamebase");
+        if (!S.src_type) return fail("no source parameters set");
+        std::vector<float> table((size_t)10 << 20);
+        int n = 0, grid[3] = {0, 0, 0};
+        if (kiwi_discretize_source(S.ctx, S.src_type, (int)S.src_params.size(), S.src_params.data(), table.data(), (int)(table.size() / 10), &n, grid)) return cfail();
+        // <base>-tdsm.info (discrete_source.f90:52-74)
+        FILE* f = fopen((w[1] + "-tdsm.info").c_str(), "w");
+        if (!f) return fail("failed to open output file: " + w[1] + "-tdsm.info");
+        fprintf(f, "ncentroids\n %d\n\n", n);
+        fclose(f);
+        // <base>-dsm.table: north east depth time m(1:6) of every centroid (minimizer_engine.f90:965-976)
+        f = fopen((w[1] + "-dsm.table").c_str(), "w");
+        if (!f) return fail("failed to open output file: " + w[1] + "-dsm.table");
+        for (int i = 0; i < n && (size_t)i < table.size() / 10; i++) fprintf(f, "%s\n", fmt_floats(&table[(size_t)i * 10], 10).c_str());
+        fclose(f);
+        // <base>-psm.info: the sections every source type writes first (origin in radians as psm%origin holds it, centre of the
+        // source: e.g. source_bilat.f90:490-496); the type-specific drawing aids that follow there (outline, rupture and slip
+        // arrows, eikonal grids) are not written
+        f = fopen((w[1] + "-psm.info").c_str(), "w");
+        if (!f) return fail("failed to open output file: " + w[1] + "-psm.info");
+        const double d2r = (double)(2.f / 360.f * 3.14159265358979f);   // orthodrome.f90:334-350
+        fprintf(f, "origin\n %.17g %.17g\n\ncenter\n%s\n\n", (double)S.olat * d2r, (double)S.olon * d2r, fmt_floats(&S.src_params[1], 3).c_str());
+        fclose(f);
+        return true;
     }
     if (cmd == "set_effective_dt") {
         if (!to_floats(w, 1, &v) || v.size() != 1) return fail("usage: set_effective_dt effective_dt");

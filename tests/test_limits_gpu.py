@@ -23,15 +23,26 @@ def test_48_time_centroids_per_sub_fault():
     assert np.array_equal(tg.view(np.uint32), to.view(np.uint32))
     o.eval_sources("bilateral", p)
     g.set_source_params("bilateral", p)
+    # ~1e4 centroids: the fp32 restatement's own accumulation noise is at the bar here (1.4e-5 of the peak against the GPU), so the
+    # restatement with the strips carried in double arbitrates, as in tests/test_fullsize_parity_gpu.py
+    lat, lon, dep = sc.small_receivers(6)
+    ow = OracleEngine(wide=True)
+    sc.setup(ow, sc.small_db(), lat, lon, dep, COMPS6)
+    ow.eval_sources("bilateral", p)
     for ir in range(1, 7):
         for ic in range(1, len(COMPS6[ir - 1]) + 1):
-            assert_seis_close(g.get_seismogram(ir, ic), o.get_seismogram(ir, ic), "rcv %d comp %d" % (ir, ic))
-    sc.set_refs_from(o, [g, o], [len(c) for c in COMPS6])
+            assert_seis_close(g.get_seismogram(ir, ic), ow.get_seismogram(ir, ic), "rcv %d comp %d" % (ir, ic))
+            (fg, dg), (fo, do), (fw, dw) = g.get_seismogram(ir, ic), o.get_seismogram(ir, ic), ow.get_seismogram(ir, ic)
+            noise = np.abs(do - dw).max()           # the fp32 restatement's own distance from the exactly accumulated sum
+            assert (fg, dg.size) == (fo, do.size) and np.abs(dg - do).max() <= RTOL * np.abs(do).max() + 1.5 * noise
+    sc.set_refs_from(o, [g, o, ow], [len(c) for c in COMPS6])
     q = np.tile(p, (3, 1)); q[1, 13] = 14.0; q[2, 5] += 10      # 71 time centroids; another strike
     mg, sg = g.eval_sources("bilateral", q)
     mo, so = o.eval_sources("bilateral", q)
+    mw, sw = ow.eval_sources("bilateral", q)
     assert np.array_equal(sg, so) and not sg.any()
-    assert np.all(np.abs(mg - mo) <= misfit_tol(mo))
+    assert np.all(np.abs(mg - mw) <= misfit_tol(mw))
+    assert np.all(np.abs(mg - mo) <= misfit_tol(mo) + 1.5 * np.abs(mo - mw))
 
 
 def test_rise_time_fold_of_1500_shifts():

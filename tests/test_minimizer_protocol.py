@@ -57,7 +57,8 @@ def test_session_matches_python_binding(tmp_path):
                 "output_seismograms %s table synthetics plain" % base, "set_ref_seismograms %s table" % base,
                 "set_misfit_method l1norm", "set_misfit_taper 1 1.0 0 1.6 1 4.0 1 5.2 0",
                 "set_source_params bilateral " + " ".join("%.9g" % v for v in p2), "get_misfits", "get_global_misfit",
-                "eval_sources bilateral %s" % cands, "switch_receiver 2 off", "get_misfits", "set_misfit_method nonsense"], env=env)
+                "eval_sources bilateral %s" % cands, "switch_receiver 2 off", "get_misfits", "set_misfit_method nonsense",
+                "output_source_model %s" % (tmp_path / "model")], env=env)
     it = iter(out)
     for _ in range(6):
         assert next(it).endswith(": ok")
@@ -74,6 +75,7 @@ def test_session_matches_python_binding(tmp_path):
     assert next(it) == "get_misfits: ok >"
     mis_off = np.array(next(it).split(), np.float32).reshape(-1, 2)
     assert next(it) == "set_misfit_method: nok >" and next(it) == "unknown norm method: nonsense"
+    assert next(it) == "output_source_model: ok"
     # the same through the Python binding: references = the table files the front-end wrote (text round trip)
     e = Engine(0)
     sc.setup(e, db, lat, lon, dep, comps)
@@ -89,6 +91,13 @@ def test_session_matches_python_binding(tmp_path):
     assert abs(gm - e.get_global_misfit()) <= 1e-6 * gm
     assert abs(gms[1] - gm) <= 1e-6 * gm and gms[0] < 1e-3 * gm       # candidate 0 is the reference itself
     assert mis_off.shape == (8, 2)
+    # output_source_model (minimizer_engine.f90:948-978): the centroid table of the current source and its size
+    table, grid, n = e.discretize_source("bilateral", p2)
+    dsm = np.loadtxt(str(tmp_path / "model") + "-dsm.table", dtype=np.float32)
+    assert dsm.shape == (n, 10) and np.array_equal(dsm, table)
+    info = open(str(tmp_path / "model") + "-tdsm.info").read().split()
+    assert info == ["ncentroids", str(n)]
+    assert open(str(tmp_path / "model") + "-psm.info").read().split()[0] == "origin"
 
 
 @pytest.mark.gpu

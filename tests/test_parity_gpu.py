@@ -677,3 +677,43 @@ def test_peak_amplitudes_and_arias_intensities(stype, params, taper):
             assert np.all(np.abs(vals[i, :, w - 1] - b) <= rtol[w] * np.abs(b)), (i, w)
     with pytest.raises(Exception, match="differentiate argument must be 1"):
         g.get_peak_amplitudes(3)
+
+
+def test_status_does_not_depend_on_batch_composition_or_fast_path():
+    """per-candidate failure statuses with the shared-synthesis and tensor-core fast paths on and off: a candidate with a
+    non-finite moment listed first must not take the candidates that share its geometry with it, and a candidate whose
+    misfits come out NaN reports status 2 on every path"""
+    g, o = engines(sc.small_db(), COMPS6)
+    ncomps = [len(c) for c in COMPS6]
+    o.eval_sources("circular", CIRC)
+    sc.set_refs_from(o, [g, o], ncomps)
+    p = np.tile(CIRC, (4, 1))
+    p[0, 4] = np.nan; p[2, 4] *= 1.3; p[3, 5] += 10          # NaN moment first; same geometry, other moment; other strike
+    g.set_share_syntheses(True)
+    ms, ss = g.eval_sources("circular", p)
+    g.set_share_syntheses(False)
+    md, sd = g.eval_sources("circular", p)
+    mo, so = o.eval_sources("circular", p)
+    assert list(ss) == list(sd) == [1, 0, 0, 0], (ss, sd, so)      # (the product refuses to discretise with a non-finite parameter)
+    assert not so[1:].any()
+    assert np.all(np.abs(ms[1:] - mo[1:]) <= misfit_tol(mo[1:])) and np.all(np.abs(md[1:] - mo[1:]) <= misfit_tol(mo[1:]))
+    # bilateral sources take any moment: the NaN comes out of the misfits (status 2), again for that candidate only
+    o.eval_sources("bilateral", sc.BILAT_SMALL)
+    sc.set_refs_from(o, [g, o], ncomps)
+    q = np.tile(sc.BILAT_SMALL, (3, 1)); q[0, 4] = np.nan; q[2, 4] *= 0.5
+    g.set_share_syntheses(True)
+    _, s1 = g.eval_sources("bilateral", q)
+    g.set_share_syntheses(False)
+    _, s2 = g.eval_sources("bilateral", q)
+    assert list(s1) == list(s2) == [2, 0, 0]
+    # moment-tensor grid: one tensor with a NaN component
+    o.eval_sources("moment_tensor", sc.MT_SMALL)
+    sc.set_refs_from(o, [g, o], ncomps)
+    r = _mt_grid()
+    r[5, 6] = np.nan
+    g.set_mt_grid(True)
+    mg, sg = g.eval_sources("moment_tensor", r)
+    assert g.last_timing()["launches"][3] >= 1
+    g.set_mt_grid(False)
+    md, sd = g.eval_sources("moment_tensor", r)
+    assert np.array_equal(sg, sd) and sg[5] == 2 and sg.sum() == 2
