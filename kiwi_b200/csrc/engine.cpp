@@ -736,7 +736,7 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
                                              nwarps, c->d_seis.as<float>(), seis_stride, c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, nbands,
                                              c->d_partial.as<float>(), st);
                 if (e != cudaSuccess) return kiwi_set_error("CUDA error launching synthesis: %s", cudaGetErrorString(e));
-                c->launches[2] += 1;
+                c->launches[2] += nbands;   // one launch of k_synth per depth band
                 if (max_rise > 0.f) {
                     e = launch_fold(c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>() + s0, ns_, c->d_seis.as<float>(), seis_stride,
                                     c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, c->db.dt, st);
