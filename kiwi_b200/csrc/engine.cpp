@@ -354,6 +354,11 @@ int choose_bands(kiwi_ctx* c, const kh::SourcePrep& sp, int nwarps) {
 struct SynthHook {
     int align = 1;   // sub-chunks hold a multiple of `align` candidates
     std::function<int(int cand0, int ncand, const float* seis, size_t seis_stride, const SeisHdr* shdrs, const CandDev* d_cands)> fn;
+    // fused: every candidate is a single-group probe source (one per grid location); instead of the synthesis launch the hook gets the
+    // geometry records and pair headers of candidates [cand0, cand0+ncand) and produces synthetics and misfits itself (k_mt_fused).
+    // Returns 0, 1 (error) or 2 (the batch does not fit that kernel: eval_batch returns 2 and the caller takes the general path).
+    bool fused = false;
+    std::function<int(int cand0, int ncand, const GeoRec* recs, const PairHdr* hdrs, const float4* taprec, int nq)> fused_fn;
 };
 
 int eval_mt_grid(kiwi_ctx* c, int n, const float* params, float* d_out, int* h_status, bool* used);
@@ -669,6 +674,7 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         const size_t npairs = (size_t)nc * nrcv;
         CU_OK(c->d_recs.ensure(sizeof(GeoRec) * npairs * rec_stride));
         CU_OK(c->d_hdrs.ensure(sizeof(PairHdr) * npairs));
+        const bool fused = hook && hook->fused;
         CU_OK(c->d_shdrs.ensure(sizeof(SeisHdr) * npairs * KIWI_MAX_COMP));
         CU_OK(c->d_tmax.ensure(sizeof(int) * 4));
         {
@@ -714,7 +720,8 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
             }
             if (changed) CU_OK(cudaMemcpyAsync(c->d_cands.p, cands.data(), sizeof(CandDev) * nc, cudaMemcpyHostToDevice, st));
         }
-        const size_t per_cand_seis = (size_t)nrcv * KIWI_MAX_COMP * seis_stride * sizeof(float);
+        if (fused && (rec_stride != 1 || max_rise > 0.f)) return 2;
+        const size_t per_cand_seis = fused ? 1 : (size_t)nrcv * KIWI_MAX_COMP * seis_stride * sizeof(float);
         int sub = (int)std::max<size_t>(1, std::min<size_t>((size_t)nc, (c->work_budget / 2) / std::max<size_t>(per_cand_seis, 1)));
         if (sub < nc) sub = std::max(align, sub / align * align);
         CU_OK(c->d_seis.ensure(per_cand_seis * sub));
@@ -729,6 +736,20 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
             const int ns_ = std::min(sub, nc - s0);
             const size_t poff = (size_t)s0 * nrcv;
             cudaEventRecord(c->ev[3], st);
+            SeisHdr* shdrs_sub = c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP;
+            if (fused) {
+                cudaEventRecord(c->ev[4], st);   // (no synthesis stage of its own: the hook's kernel is booked as the misfit stage)
+                const int rc = hook->fused_fn(b0 + s0, ns_, c->d_recs.as<GeoRec>() + poff, c->d_hdrs.as<PairHdr>() + poff, g.taprec, nq);
+                if (rc) return rc;
+                c->launches[3] += 1;
+                cudaEventRecord(c->ev[5], st);
+                CU_OK(cudaStreamSynchronize(st));
+                CU_OK(cudaGetLastError());
+                float b = 0.f;
+                cudaEventElapsedTime(&b, c->ev[4], c->ev[5]);
+                c->ms[3] += b;
+                continue;
+            }
             if (tmax > 0) {
                 if (nbands > 1) CU_OK(c->d_partial.ensure(synth_partial_bytes(nq) * (size_t)ns_ * nrcv));
                 cudaError_t e = launch_synth(c->db, c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>() + s0, ns_, g,
@@ -744,11 +765,11 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
                     c->launches[2] += 1;
                 }
             } else {
-                CU_OK(cudaMemsetAsync(c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, 0xff, sizeof(SeisHdr) * (size_t)ns_ * nrcv * KIWI_MAX_COMP, st));
+                CU_OK(cudaMemsetAsync(shdrs_sub, 0xff, sizeof(SeisHdr) * (size_t)ns_ * nrcv * KIWI_MAX_COMP, st));
             }
             cudaEventRecord(c->ev[4], st);
             if (hook && hook->fn) {
-                if (hook->fn(b0 + s0, ns_, c->d_seis.as<float>(), seis_stride, c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, c->d_cands.as<CandDev>() + s0)) return 1;
+                if (hook->fn(b0 + s0, ns_, c->d_seis.as<float>(), seis_stride, shdrs_sub, c->d_cands.as<CandDev>() + s0)) return 1;
                 c->launches[3] += 1;
             }
             // misfit stage: one slot per candidate; with shared syntheses the slots of this sub-chunk come with a map
@@ -798,7 +819,7 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         kiwi_ctx::Last& L = c->last;
         L.valid = true; L.sourcetype = sourcetype; L.n = nc; L.nrcv = nrcv; L.rec_stride = rec_stride; L.seis_stride = seis_stride;
         L.ngroups_total = Galloc; L.cands = cands; L.g = g; L.taps = taps; L.toff = toff; L.wt = wt;
-        L.seis_valid = (sub >= nc) && tmax > 0;
+        L.seis_valid = (sub >= nc) && tmax > 0 && !fused;
         L.syn_lo = tm3[1]; L.syn_hi = tm3[2]; L.tmax = tmax;
         {
             const kh::SourcePrep& sp0 = prep[b0];
@@ -872,7 +893,6 @@ int eval_mt_grid(kiwi_ctx* c, int n, const float* params, float* d_out, int* h_s
     CU_OK(cudaStreamSynchronize(c->stream));
     const int nrcv = (int)c->rcv.size();
     SynthHook hook;
-    hook.align = 6;
     hook.fn = [&](int cand0, int ncand, const float* seis, size_t seis_stride, const SeisHdr* shdrs, const CandDev*) -> int {
         const int l0 = cand0 / 6, nl = ncand / 6;
         launch_mt_contract(c->d_rcv.as<ReceiverDev>(), nrcv, reinterpret_cast<const MtLoc*>(c->d_mtlocs.p) + l0, nl, c->d_mts.as<float>(),
@@ -882,8 +902,49 @@ int eval_mt_grid(kiwi_ctx* c, int n, const float* params, float* d_out, int* h_s
         if (e != cudaSuccess) return kiwi_set_error("CUDA error launching the moment-tensor contraction: %s", cudaGetErrorString(e));
         return 0;
     };
+    // one probe source per location (mxx = mxz = 1: its azimuth factors give those of all six unit tensors), synthesis fused into the
+    // contraction kernel ...
     std::vector<int> bstatus((size_t)nloc * 6, 0);
-    if (eval_batch(c, KIWI_SOURCE_MOMENT_TENSOR, nloc * 6, 11, basis.data(), nullptr, bstatus.data(), false, &hook)) return 1;
+    {
+        std::vector<float> probe((size_t)nloc * 11, 0.f);
+        for (int l = 0; l < nloc; l++) {
+            float* b = &probe[(size_t)l * 11];
+            const float* p = params + (size_t)first_of[l] * 11;
+            b[0] = p[0]; b[1] = p[1]; b[2] = p[2]; b[3] = p[3]; b[10] = p[10];
+            b[4] = 1.f; b[8] = 1.f;
+        }
+        std::vector<int> pstatus((size_t)nloc, 0);
+        int ncomp_max = 1;
+        for (const ReceiverDev& r : c->h_rcvdev) if (r.enabled) ncomp_max = std::max(ncomp_max, r.ncomp);
+        CU_OK(c->d_tmax.ensure(sizeof(int) * 8));
+        int* d_overflow = c->d_tmax.as<int>() + 4;
+        CU_OK(cudaMemsetAsync(d_overflow, 0, sizeof(int), c->stream));
+        hook.fused = true; hook.align = 1;
+        hook.fused_fn = [&](int cand0, int ncand, const GeoRec* recs, const PairHdr* hdrs, const float4* taprec, int nq) -> int {
+            const int strip_cap = 4 * nq + 16;
+            if (mt_fused_smem_bytes(strip_cap, ncomp_max) > (size_t)100 * 1024) return 2;   // (two CTAs per SM at least)
+            cudaError_t e = launch_mt_fused(c->db, c->d_rcv.as<ReceiverDev>(), nrcv, reinterpret_cast<const MtLoc*>(c->d_mtlocs.p) + cand0, ncand,
+                                            c->d_mts.as<float>(), c->d_candof.as<int>(), recs, hdrs, taprec, strip_cap, ncomp_max,
+                                            c->d_refdata.as<float>(), c->d_taper.as<float>(), c->misfit_method, c->db.dt, c->syn_factor, c->nmisfits,
+                                            d_out, d_overflow, c->stream);
+            if (e != cudaSuccess) return kiwi_set_error("CUDA error launching the fused moment-tensor contraction: %s", cudaGetErrorString(e));
+            return 0;
+        };
+        static const bool no_fused = getenv("KIWI_NO_MT_FUSED") != nullptr;
+        int rc = no_fused ? 2 : eval_batch(c, KIWI_SOURCE_MOMENT_TENSOR, nloc, 11, probe.data(), nullptr, pstatus.data(), false, &hook);
+        if (rc == 1) return 1;
+        if (rc == 0) {
+            int overflow = 0;
+            CU_OK(cudaMemcpyAsync(&overflow, d_overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            CU_OK(cudaStreamSynchronize(c->stream));
+            if (overflow) rc = 2;
+        }
+        if (rc == 0) for (int l = 0; l < nloc; l++) for (int k = 0; k < 6; k++) bstatus[(size_t)l * 6 + k] = pstatus[l];
+        else {   // ... or, where a window or shift table does not fit that kernel, the six unit tensors through the general synthesis
+            hook.fused = false; hook.align = 6;
+            if (eval_batch(c, KIWI_SOURCE_MOMENT_TENSOR, nloc * 6, 11, basis.data(), nullptr, bstatus.data(), false, &hook)) return 1;
+        }
+    }
     if (h_status) {   // status of the basis, or 2 where a misfit came out NaN/Inf (as k_misfit_td reports it on the direct path)
         std::vector<int> nonfinite((size_t)n, 0);
         CU_OK(c->d_status_out.ensure(sizeof(int) * (size_t)n));

@@ -1780,6 +1780,412 @@ __global__ void __launch_bounds__(128) k_mt_contract(const ReceiverDev* __restri
 }
 
 // =================================================================================================
+// K8f: the same grid search with the synthesis fused in.  A point source is ONE group, so everything the candidates of a
+// (location, receiver) pair have in common is 4 corners x ng rows of one window.  Instead of writing six unit-tensor
+// seismograms per pair to HBM (k_synth, 18 rows) and reading them back (k_mt_contract), the CTA
+//   1a gathers the rows once and combines the corners bilinearly (gfdb.f90:943-948)            -> U_k, k = g1..g10, shared memory
+//   1b applies the tap filter of trace_multiply_add (sparse_trace.f90:639-705, shift table of k_tap_table) to every U_k
+//          G_k(x) = sum_m sum_t h_m[t] U_k(x - 4 q_m - t),    U_k = 0 left of the window, its last sample to the right
+//   2  and contracts on the tensor cores, per receiver component,
+//          syn_j(x) - ref(x) = sum_k a_jk G_k(x) - ref(x),
+//      where a_jk are candidate j's coefficients of the GF components: make_weights of its tensor (seismogram.f90:316-336:
+//      linear in m; the azimuth factors cos^2, sin^2, sin 2a, cos, sin come with the record of a probe source mxx = mxz = 1),
+//      the centroid rotation (:196-203) and the receiver's component sign / rotation (:256-289) -- six non-zero coefficients
+//      for a horizontal component (g1 g2 g3 g9 -> radial, g4 g5 -> transverse), four for the vertical (g6 g7 g8 g10).
+// The reference trace rides along as a seventh row against a coefficient -1, so the accumulator holds syn - ref and the
+// epilogue is one packed square-accumulate (|.| for the L1 norm) per two samples.  Operands are split hi + lo (TF32 keeps
+// 10 mantissa bits); K = [hi | hi | lo | lo] x [hi | lo | hi | lo] of the 7 values, padded to 32.
+// =================================================================================================
+#define MTF_K 32
+#define MTF_MAXSTEP 8      // distinct quad shifts of the location's taps the kernel keeps (more: general path)
+#define MTF_PAD 64         // samples the filtered strips may be longer than the unshifted ones
+#define MTF_MAXRCV 32      // receivers of one CTA (their records and headers are staged in shared memory at the start)
+
+__device__ __forceinline__ float4 f4_scale(float s, const float4& v) { return make_float4(s * v.x, s * v.y, s * v.z, s * v.w); }
+__device__ __forceinline__ void f4_axpy(float4& a, float s, const float4& v) {
+    a.x = fmaf(s, v.x, a.x); a.y = fmaf(s, v.y, a.y); a.z = fmaf(s, v.z, a.z); a.w = fmaf(s, v.w, a.w);
+}
+__device__ __forceinline__ float4 ldg_quad(const float* slabs, const NodeInfo& n, int q, int comp) {
+    unsigned stride;
+    return __ldg(reinterpret_cast<const float4*>(corner_ptr(slabs, n, q, comp, stride)));
+}
+
+__global__ void __launch_bounds__(128, 4) k_mt_fused(GfdbDev db, const ReceiverDev* __restrict__ rcv, int nrcv, const MtLoc* __restrict__ locs,
+                                                   const float* __restrict__ mts /* [n][6] sorted by location */,
+                                                   const int* __restrict__ cand_of /* [n] original candidate index */,
+                                                   const GeoRec* __restrict__ recs /* [loc][rcv], one group each */,
+                                                   const PairHdr* __restrict__ hdrs, const float4* __restrict__ taprec, int strip_cap,
+                                                   const float* __restrict__ refdata, const float* __restrict__ taperdata, int method, float dt,
+                                                   float syn_factor, int nmisfits, float* __restrict__ out, int rcv_per_cta,
+                                                   int* __restrict__ overflow) {
+    extern __shared__ __align__(128) unsigned char mtf_smem[];
+    float* sA = reinterpret_cast<float*>(mtf_smem);                 // [128 x 32] K-major core matrices, 16 KiB
+    float* sB = sA + MTC_M * MTF_K;                                 // 16 KiB
+    const int SU = strip_cap + 4, SF = strip_cap + MTF_PAD + 4;     // strip pitches: one quad of zeros, then the window
+    float* sU = sA;                                                 // [10][SU] bilinearly combined GF components, unshifted: lives where the
+                                                                    // operand tiles are built later (phase 1 is over by then)
+    float* sF = sA + max((MTC_M + MTC_N) * MTF_K, (10 * SU + 31) & ~31);   // [10][SF] the same after the tap filter
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ unsigned s_tmem;
+    __shared__ double s_red[2][4];
+    __shared__ float s_h[MTF_MAXSTEP][5];
+    __shared__ int s_q[MTF_MAXSTEP];
+    __shared__ __align__(16) GeoRec s_rec[MTF_MAXRCV];
+    __shared__ __align__(16) PairHdr s_hdr[MTF_MAXRCV];
+
+    const int nrblk = (nrcv + rcv_per_cta - 1) / rcv_per_cta;
+    const int loc = blockIdx.x / nrblk, ir_begin = (blockIdx.x % nrblk) * rcv_per_cta, ir_end = min(nrcv, ir_begin + rcv_per_cta);
+    const MtLoc L = locs[loc];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool l1 = method == 2;
+
+    // records and headers of this CTA's (location, receiver) pairs: one round trip to memory for all of them
+    for (int i = tid; i < (ir_end - ir_begin) * 8; i += MTC_M)
+        reinterpret_cast<uint4*>(s_rec)[i] = __ldg(reinterpret_cast<const uint4*>(recs + (size_t)loc * nrcv + ir_begin) + i);
+    for (int i = tid; i < (ir_end - ir_begin) * 2; i += MTC_M)
+        reinterpret_cast<uint4*>(s_hdr)[i] = __ldg(reinterpret_cast<const uint4*>(hdrs + (size_t)loc * nrcv + ir_begin) + i);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(MTC_N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem = s_tmem;
+    unsigned phase = 0;
+    const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(MTC_N >> 3) << 17) | ((unsigned)(MTC_M >> 4) << 24);
+    const float fa = 1.f, fb = syn_factor;
+    unsigned nred = 0;
+
+    for (int ir = ir_begin; ir < ir_end; ir++) {
+        const ReceiverDev& R = rcv[ir];
+        if (!R.enabled || R.ncomp == 0) continue;
+        const PairHdr H = s_hdr[ir - ir_begin];
+        const GeoRec* rec = &s_rec[ir - ir_begin];
+        const int flags = rec->flags, nstep = rec->nstep, tt = rec->tt_begin;
+        NodeInfo nd[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) nd[c] = rec->node[c];
+        int q_first = 0, q_last = -1;
+        if (H.T > 0) window_quads(nd[0], nd[1], nd[2], nd[3], q_first, q_last);
+        const int nqw = q_last - q_first + 1;       // quads of the unshifted window; the last one holds the continuation value
+        bool usable = H.T > 0 && !(flags & GEO_SKIP);
+        if (usable && (4 * nqw > strip_cap || nstep > MTF_MAXSTEP || nstep < 1)) usable = false, (void)(tid == 0 && atomicExch(overflow, 1));
+        __syncthreads();   // the previous receiver's strips and shift table are no longer read
+        if (usable && tid < nstep) {
+            const float4 ta = __ldg(taprec + 2 * ((size_t)tt + tid)), tb = __ldg(taprec + 2 * ((size_t)tt + tid) + 1);
+            s_q[tid] = __float_as_int(ta.x);
+            s_h[tid][0] = ta.y; s_h[tid][1] = ta.z; s_h[tid][2] = ta.w; s_h[tid][3] = tb.x; s_h[tid][4] = tb.y;
+        }
+        const bool need_h = (R.ja | R.jr | R.jn | R.je) != 0, need_v = R.jd != 0, ng10 = db.ng == 10;
+        if (usable) {
+            // ---- phase 1a: corners -> U_k ------------------------------------------------------------------
+            if (tid < 10) { *reinterpret_cast<float4*>(sU + (size_t)tid * SU) = f4zero(); *reinterpret_cast<float4*>(sF + (size_t)tid * SF) = f4zero(); }
+            const bool single = flags & GEO_SINGLE;
+            const float dix = rec->dix, diz = rec->diz;
+            const float wc0 = single ? 1.f : (1.f - dix) * (1.f - diz), wc1 = single ? 0.f : (1.f - dix) * diz,
+                        wc2 = single ? 0.f : dix * (1.f - diz), wc3 = single ? 0.f : dix * diz;
+            for (int qi = tid; qi < nqw; qi += MTC_M) {
+                const int q = q_first + qi;
+                // five components (twenty 128-bit loads) in flight at a time
+#pragma unroll
+                for (int kb = 0; kb < 10; kb += 5) {
+                    float4 t[5][4];
+#pragma unroll
+                    for (int kk = 0; kk < 5; kk++) {
+                        const int k = kb + kk;
+                        const bool wanted = ((k < 5 || k == 8) ? need_h : need_v) && (k < 8 || ng10);
+#pragma unroll
+                        for (int c = 0; c < 4; c++) t[kk][c] = (wanted && (c == 0 || !single)) ? ldg_quad(db.slabs, nd[c], q, k) : f4zero();
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < 5; kk++) {
+                        const int k = kb + kk;
+                        const bool wanted = ((k < 5 || k == 8) ? need_h : need_v) && (k < 8 || ng10);
+                        if (!wanted) continue;
+                        float4 r = f4_scale(wc0, t[kk][0]);
+                        f4_axpy(r, wc1, t[kk][1]); f4_axpy(r, wc2, t[kk][2]); f4_axpy(r, wc3, t[kk][3]);
+                        *reinterpret_cast<float4*>(sU + (size_t)k * SU + 4 + 4 * qi) = r;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase 1b: tap filter, one thread per output quad Q = q_first + mmin + Qi:
+        //      out(4Q + j) = sum_m sum_t h_m[t] U(4(Q - q_m) + j - t): own quad a and previous quad p of the source --------------------
+        int mmin = 0, mmax = 0;
+        if (usable) {
+            mmin = INT_MAX; mmax = INT_MIN;
+            for (int m = 0; m < nstep; m++) { mmin = min(mmin, s_q[m]); mmax = max(mmax, s_q[m]); }
+        }
+        const int nqf = nqw + 1 + (mmax - mmin);    // quads of the filtered window; the last one is constant (continuation)
+        if (usable && 4 * nqf > strip_cap + MTF_PAD) usable = false, (void)(tid == 0 && atomicExch(overflow, 1));
+        const int x0f = 4 * (q_first + mmin), Lf = 4 * nqf;
+        if (usable) {
+            for (int Qi = tid; Qi < nqf; Qi += MTC_M) {
+                float4 acc[10];
+#pragma unroll
+                for (int k = 0; k < 10; k++) acc[k] = f4zero();
+                for (int m = 0; m < nstep; m++) {
+                    const int si = Qi + mmin - s_q[m];                                 // source quad, relative to q_first
+                    const int ia = 4 + 4 * min(max(si, -1), nqw - 1), ip = 4 + 4 * min(max(si - 1, -1), nqw - 1);
+                    const float h0 = s_h[m][0], h1 = s_h[m][1], h2 = s_h[m][2], h3 = s_h[m][3], h4 = s_h[m][4];
+#pragma unroll
+                    for (int k = 0; k < 10; k++) {
+                        const bool wanted = ((k < 5 || k == 8) ? need_h : need_v) && (k < 8 || ng10);
+                        if (!wanted) continue;
+                        const float4 a = *reinterpret_cast<const float4*>(sU + (size_t)k * SU + ia), p = *reinterpret_cast<const float4*>(sU + (size_t)k * SU + ip);
+                        float4& o = acc[k];
+                        o.x = fmaf(h4, p.x, fmaf(h3, p.y, fmaf(h2, p.z, fmaf(h1, p.w, fmaf(h0, a.x, o.x)))));
+                        o.y = fmaf(h4, p.y, fmaf(h3, p.z, fmaf(h2, p.w, fmaf(h1, a.x, fmaf(h0, a.y, o.y)))));
+                        o.z = fmaf(h4, p.z, fmaf(h3, p.w, fmaf(h2, a.x, fmaf(h1, a.y, fmaf(h0, a.z, o.z)))));
+                        o.w = fmaf(h4, p.w, fmaf(h3, a.x, fmaf(h2, a.y, fmaf(h1, a.z, fmaf(h0, a.w, o.w)))));
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 10; k++) {
+                    const bool wanted = ((k < 5 || k == 8) ? need_h : need_v) && (k < 8 || ng10);
+                    if (wanted) *reinterpret_cast<float4*>(sF + (size_t)k * SF + 4 + 4 * Qi) = acc[k];
+                }
+            }
+        }
+        __syncthreads();
+        if (ir + 1 < ir_end) {   // the next receiver's rows on their way into L2 while this one is contracted: one prefetch per 128-byte line
+            const GeoRec* nrec = &s_rec[ir + 1 - ir_begin];
+            const PairHdr nH = s_hdr[ir + 1 - ir_begin];
+            const ReceiverDev& nR = rcv[ir + 1];
+            if (nH.T > 0 && !(nrec->flags & GEO_SKIP) && nR.enabled) {
+                const bool nh = (nR.ja | nR.jr | nR.jn | nR.je) != 0, nv = nR.jd != 0;
+                const int ncorner = (nrec->flags & GEO_SINGLE) ? 1 : 4;
+                for (int c = 0; c < ncorner; c++) {
+                    const NodeInfo n = nrec->node[c];
+                    const int nq = n.wn >> 2, lines = (nq + 7) >> 3;
+                    const char* base = reinterpret_cast<const char*>(db.slabs + n.off);
+                    for (int i = tid; i < lines * db.ng; i += MTC_M) {
+                        const int k = i / lines, l = i - k * lines;
+                        const bool wanted = ((k < 5 || k == 8) ? nh : nv);
+                        if (wanted) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + ((size_t)(k * nq + l * 8) << 4)));
+                    }
+                }
+            }
+        }
+        // azimuth factors of the probe source mxx = mxz = 1: f = {cos^2, cos, 0, -sin(2a)/2, -sin, sin^2}
+        const float ca2 = rec->f[0], ca = rec->f[1], s2a = -2.f * rec->f[3], sa = -rec->f[4], sa2 = rec->f[5];
+        const float c2a = ca2 - sa2;
+        const float cl = rec->cl, sl = rec->sl;
+        const float* tp = taperdata + R.taper_off;
+        const bool tapered = R.has_taper != 0;
+        const int s12lo = min(H.s1lo, H.s2lo), s12hi = max(H.s1hi, H.s2hi);
+
+        for (int m0 = 0; m0 < L.mt_count; m0 += MTC_M) {
+            const int j = m0 + tid;
+            const bool have = j < L.mt_count;
+            float f1 = 0.f, f2 = 0.f, f3 = 0.f, f4 = 0.f, f5 = 0.f, f6 = 0.f;
+            if (have) {   // make_weights of this thread's candidate tensor (seismogram.f90:316-336)
+                float mt[6];
+#pragma unroll
+                for (int k = 0; k < 6; k++) mt[k] = __ldg(&mts[(size_t)(L.mt_begin + j) * 6 + k]);
+                f1 = mt[0] * ca2 + mt[1] * sa2 + mt[3] * s2a;
+                f2 = mt[4] * ca + mt[5] * sa;
+                f3 = mt[2];
+                f4 = 0.5f * (mt[1] - mt[0]) * s2a + mt[3] * c2a;
+                f5 = mt[5] * ca - mt[4] * sa;
+                f6 = mt[0] * sa2 + mt[1] * ca2 - mt[3] * s2a;
+            }
+            for (int ic = 0; ic < R.ncomp; ic++) {
+                const int id = R.comp[ic], aid = id < 0 ? -id : id;
+                const float sg = id < 0 ? -1.f : 1.f;
+                int sds0, sds1;
+                if (aid == 1) { sds0 = H.s1lo; sds1 = H.s1hi; }
+                else if (aid == 2) { sds0 = H.s2lo; sds1 = H.s2hi; }
+                else if (aid == 3) { sds0 = H.s3lo; sds1 = H.s3hi; }
+                else { sds0 = s12lo; sds1 = s12hi; }
+                float* o = have ? out + ((size_t)cand_of[L.mt_begin + j] * nmisfits + R.misfit_base + ic) * 2 : nullptr;
+                if (!usable || sds1 < sds0) { if (o) { o[0] = nanf(""); o[1] = nanf(""); } continue; }
+                // ---- this candidate's coefficients of the six (four) GF components of the component, and their strips ------------
+                float a7[7];
+                const float* row[6];
+                if (aid == 3) {
+                    a7[0] = R.sd * f1; a7[1] = R.sd * f2; a7[2] = R.sd * f3; a7[3] = R.sd * f6; a7[4] = 0.f; a7[5] = 0.f;
+                    row[0] = sF + 5 * (size_t)SF; row[1] = sF + 6 * (size_t)SF; row[2] = sF + 7 * (size_t)SF; row[3] = sF + 9 * (size_t)SF;
+                    row[4] = row[0]; row[5] = row[0];
+                } else {
+                    // value = c1 * A1 + c2 * A2 with A1 = cl R - sl T, A2 = cl T + sl R (seismogram.f90:200-203, 256-289)
+                    const float c1 = aid == 1 ? sg : (aid == 2 ? 0.f : (aid == 4 ? sg * R.cl0 : sg * R.sl0));
+                    const float c2 = aid == 1 ? 0.f : (aid == 2 ? sg : (aid == 4 ? -sg * R.sl0 : sg * R.cl0));
+                    const float al = c1 * cl + c2 * sl, be = c2 * cl - c1 * sl;
+                    a7[0] = al * f1; a7[1] = al * f2; a7[2] = al * f3; a7[3] = al * f6; a7[4] = be * f4; a7[5] = be * f5;
+                    row[0] = sF; row[1] = sF + (size_t)SF; row[2] = sF + 2 * (size_t)SF; row[3] = sF + 8 * (size_t)SF;
+                    row[4] = sF + 3 * (size_t)SF; row[5] = sF + 4 * (size_t)SF;
+                }
+                if (!ng10) a7[3] = 0.f;                  // (no g9 / g10 in an eight-component database: their strips were not written)
+                a7[6] = have ? -1.f : 0.f;
+                {   // A tile: [hi | hi | lo | lo]
+                    float hi[7], lo[7];
+#pragma unroll
+                    for (int k = 0; k < 7; k++) { hi[k] = tf32_hi(a7[k]); lo[k] = tf32_hi(a7[k] - hi[k]); }
+                    char* a = reinterpret_cast<char*>(sA);
+#pragma unroll
+                    for (int blk = 0; blk < 4; blk++) {
+                        const float* s = blk < 2 ? hi : lo;
+                        *reinterpret_cast<float4*>(a + operand_off(tid, 8 * blk, MTC_M)) = make_float4(s[0], s[1], s[2], s[3]);
+                        *reinterpret_cast<float4*>(a + operand_off(tid, 8 * blk + 4, MTC_M)) = make_float4(s[4], s[5], s[6], 0.f);
+                    }
+                }
+                const int nrow = aid == 3 ? 4 : 6;
+                auto strip_at = [&](int k, int x) -> float { return row[k][4 + min(max(x - x0f, -1), Lf - 1)]; };
+                const int rds0 = R.ref_ds0[ic], rds1 = R.ref_ds1[ic];
+                const float* rdat = refdata + R.ref_off[ic];
+                int F0, F1;
+                probe_spans(rds0, rds1, R.ref_sp0[ic], R.ref_sp1[ic], sds0, sds1, F0, F1);
+                int p0, p1, q0, q1;
+                if (tapered) { p0 = max(R.dps0, F0); p1 = min(R.dps1, F1); q0 = p0; q1 = p1; }
+                else { p0 = min(rds0, sds0); p1 = max(rds1, sds1); q0 = rds0; q1 = rds1; }
+                auto refval = [&](int x) -> float {
+                    if (x < rds0) return 0.f;
+                    float v = rdat[min(x, rds1) - rds0];
+                    if (tapered) v = (x >= R.tp0 && x <= R.tp1) ? v * tp[x - R.tp0] : 0.f;
+                    return v;
+                };
+                auto tapval = [&](int x) -> float { return tapered ? ((x >= R.tp0 && x <= R.tp1) ? tp[x - R.tp0] : 0.f) : 1.f; };
+                double acc = 0.;
+                // (i) left of the synthetic's data span the synthetic is zero: reference only
+                for (int x = p0; x <= min(p1, sds0 - 1); x++) { const float a = refval(x); acc += l1 ? (double)fabsf(fa * a) : (double)(fa * a) * (double)(fa * a); }
+                // (ii) columns x in [xs, xe] come out of the tensor-core contraction, 128 at a time
+                const int xs = max(p0, sds0), xe = min(p1, sds1) < xs ? -1 : ((p1 > sds1) ? sds1 : min(p1, sds1));
+                // last sample of this thread's candidate (continued to the right, comparator.f90:264-267)
+                float e_last = 0.f;
+                if (p1 > sds1 && sds1 >= sds0) {
+#pragma unroll
+                    for (int k = 0; k < 6; k++) if (k < nrow) e_last = fmaf(a7[k], strip_at(k, sds1), e_last);
+                }
+                // column x = c0 + tid of the chunk: the GF component samples times taper and synthetics factor, and fa * reference
+                float colv[7];
+                auto fetch_col = [&](int c0) {
+                    const int x = c0 + tid;
+                    const bool in = x <= xe;
+                    const float scale = in ? fb * tapval(x) : 0.f;
+#pragma unroll
+                    for (int k = 0; k < 6; k++) colv[k] = (in && k < nrow) ? strip_at(k, x) * scale : 0.f;
+                    colv[6] = in ? fa * refval(x) : 0.f;
+                };
+                if (xe >= xs) fetch_col(xs);
+                for (int c0 = xs; xe >= xs && c0 <= xe; c0 += MTC_N) {
+                    {   // ---- B chunk: [hi | lo | hi | lo]
+                        char* bsm = reinterpret_cast<char*>(sB);
+                        float hi[7], lo[7];
+#pragma unroll
+                        for (int k = 0; k < 7; k++) { hi[k] = tf32_hi(colv[k]); lo[k] = tf32_hi(colv[k] - hi[k]); }
+#pragma unroll
+                        for (int blk = 0; blk < 4; blk++) {
+                            const float* s = (blk & 1) ? lo : hi;
+                            *reinterpret_cast<float4*>(bsm + operand_off(tid, 8 * blk, MTC_N)) = make_float4(s[0], s[1], s[2], s[3]);
+                            *reinterpret_cast<float4*>(bsm + operand_off(tid, 8 * blk + 4, MTC_N)) = make_float4(s[4], s[5], s[6], 0.f);
+                        }
+                    }
+                    if (c0 + MTC_N <= xe) fetch_col(c0 + MTC_N);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> async proxy (tensor core)
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncthreads();
+                    if (tid == 0) {
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const unsigned a0 = smem_u32(sA), b0 = smem_u32(sB);
+#pragma unroll
+                        for (int ks = 0; ks < MTF_K / 8; ks++) {
+                            const unsigned long long da = umma_desc(a0 + ks * 2 * (MTC_M / 8) * 128, (MTC_M / 8) * 128, 128);
+                            const unsigned long long dbb = umma_desc(b0 + ks * 2 * (MTC_N / 8) * 128, (MTC_N / 8) * 128, 128);
+                            const unsigned accum = ks > 0 ? 1u : 0u;
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem),
+                                "l"(da), "l"(dbb), "r"(idesc), "r"(accum)
+                                : "memory");
+                        }
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_bar)) : "memory");
+                    }
+                    {
+                        unsigned done = 0, spins = 0;
+                        while (!done) {
+                            if (++spins > (1u << 26)) { asm volatile("trap;"); }   // never spin for ever on a lost completion
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                                : "=r"(done)
+                                : "r"(smem_u32(&s_bar)), "r"(phase)
+                                : "memory");
+                        }
+                        phase ^= 1;
+                    }
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const int ncol = min(MTC_N, xe - c0 + 1);
+                    for (int cc = 0; cc < ncol; cc += 32) {   // (columns beyond ncol: zero rows and zero reference, residual 0)
+                        unsigned v[32];
+                        const unsigned taddr = tmem + ((unsigned)(warp * 32) << 16) + (unsigned)cc;
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                              "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                              "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                              "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                            : "r"(taddr)
+                            : "memory");
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        // 32 residuals in fp32 (interleaved partial sums), then into the fp64 sum (comparator.f90:639-659 sums in double)
+                        float pa, pb;
+                        if (l1) {
+                            pa = 0.f; pb = 0.f;
+#pragma unroll
+                            for (int u = 0; u < 16; u++) { pa += fabsf(__uint_as_float(v[2 * u])); pb += fabsf(__uint_as_float(v[2 * u + 1])); }
+                        } else {
+                            u64 p01 = 0ull, p23 = 0ull;
+#pragma unroll
+                            for (int u4 = 0; u4 < 8; u4++) {
+                                const u64 r01 = pk2(__uint_as_float(v[4 * u4]), __uint_as_float(v[4 * u4 + 1])), r23 = pk2(__uint_as_float(v[4 * u4 + 2]), __uint_as_float(v[4 * u4 + 3]));
+                                asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(p01) : "l"(r01));
+                                asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(p23) : "l"(r23));
+                            }
+                            float a0, a1, a2, a3;
+                            unpk2(p01, a0, a1); unpk2(p23, a2, a3);
+                            pa = a0 + a1; pb = a2 + a3;
+                        }
+                        acc += (double)(pa + pb);
+                    }
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncthreads();      // accumulator and operand tiles are free again
+                }
+                // (iii) right of the data span the synthetic repeats its last sample
+                for (int x = max(max(p0, sds0), sds1 + 1); x <= p1; x++) {
+                    const float r = fa * refval(x) - fb * (e_last * tapval(x));
+                    acc += l1 ? (double)fabsf(r) : (double)r * (double)r;
+                }
+                // reference-only norm (the same for all candidates): block reduction
+                double accn = 0.;
+                for (int x = q0 + tid; x <= q1; x += MTC_M) { const float a = refval(x); accn += l1 ? (double)fabsf(a) : (double)a * (double)a; }
+                for (int ofs = 16; ofs; ofs >>= 1) accn += __shfl_xor_sync(0xffffffffu, accn, ofs);
+                const unsigned rb = nred++ & 1u;   // alternating buffers: one barrier between the writes and the reads is enough
+                if (lane == 0) s_red[rb][warp] = accn;
+                __syncthreads();
+                accn = s_red[rb][0] + s_red[rb][1] + s_red[rb][2] + s_red[rb][3];
+                if (o) {
+                    float mis, nf;
+                    if (l1) { mis = (float)((double)dt * acc); nf = fa * (float)((double)dt * accn); }
+                    else { mis = (float)sqrt((double)dt * acc); nf = fa * (float)sqrt((double)dt * accn); }
+                    if (p1 < p0) mis = 0.f;
+                    o[0] = mis; o[1] = nf;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(MTC_N) : "memory");
+}
+
+// =================================================================================================
 // Ground-motion diagnostics of the synthetics (get_peak_amplitudes / get_arias_intensities, minimizer_engine.f90:1174-1245;
 // receiver_get_maxabs / receiver_get_arias_intensity receiver.f90:544-596; max_vecnorm_d1/d2_*, arias_intensity_*
 // comparator.f90:519-625 through probes_norm_timedomain[_3] :700-765).  One warp per (candidate, receiver):
@@ -2051,6 +2457,28 @@ void launch_mt_contract(const ReceiverDev* rcv, int nrcv, const MtLoc* locs, int
         k_mt_contract<<<nloc * nrblk, 128, 0, st>>>(rcv, nrcv, locs, mts, cand_of, seis, seis_stride, shdrs, refdata, taperdata, method, dt,
                                                    syn_factor, nmisfits, out, rpc);
     }
+}
+
+size_t mt_fused_smem_bytes(int strip_cap, int) {
+    const size_t tiles = (size_t)(MTC_M + MTC_N) * MTF_K, u = ((size_t)10 * (strip_cap + 4) + 31) & ~(size_t)31;
+    return (std::max(tiles, u) + (size_t)10 * (strip_cap + MTF_PAD + 4)) * sizeof(float);
+}
+int mt_fused_max_steps() { return MTF_MAXSTEP; }
+cudaError_t launch_mt_fused(GfdbDev db, const ReceiverDev* rcv, int nrcv, const MtLoc* locs, int nloc, const float* mts, const int* cand_of,
+                            const GeoRec* recs, const PairHdr* hdrs, const float4* taprec, int strip_cap, int ncomp_max, const float* refdata,
+                            const float* taperdata, int method, float dt, float syn_factor, int nmisfits, float* out, int* overflow, cudaStream_t st) {
+    const size_t smem = mt_fused_smem_bytes(strip_cap, ncomp_max);
+    cudaError_t e = cudaFuncSetAttribute(k_mt_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (nloc * nrcv > 0) {
+        // receivers per CTA: enough CTAs for a few waves over the 148 SMs x 3 resident CTAs, as few set-ups as possible
+        int rpc = 1;
+        while (rpc < nrcv && 2 * rpc <= MTF_MAXRCV && (long long)nloc * ((nrcv + 2 * rpc - 1) / (2 * rpc)) >= 148LL * 4 * 8) rpc *= 2;
+        const int nrblk = (nrcv + rpc - 1) / rpc;
+        k_mt_fused<<<nloc * nrblk, 128, smem, st>>>(db, rcv, nrcv, locs, mts, cand_of, recs, hdrs, taprec, strip_cap, refdata, taperdata, method, dt,
+                                                   syn_factor, nmisfits, out, rpc, overflow);
+    }
+    return cudaGetLastError();
 }
 
 cudaError_t launch_fold(const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, float* seis, size_t seis_stride, SeisHdr* shdrs,

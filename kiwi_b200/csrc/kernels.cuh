@@ -22,6 +22,13 @@ void launch_expand_centroids(CandDev cand, GroupSoA g, TapSoA taps, int ngroups_
 void launch_geometry(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, int ngroups_total,
                      int interpolate, int xunder, int zunder, GeoRec* recs, size_t rec_stride, PairHdr* hdrs, int* tmax, cudaStream_t st);
 size_t synth_smem_bytes(int nwarps, int nq);
+// point moment-tensor grid search with the basis synthesis fused in (one group per location): recs / hdrs of the probe sources
+// [loc][rcv]; *overflow is set where a window or shift table does not fit (the caller then takes the general path)
+size_t mt_fused_smem_bytes(int strip_cap, int ncomp);
+int mt_fused_max_steps();
+cudaError_t launch_mt_fused(GfdbDev db, const ReceiverDev* rcv, int nrcv, const MtLoc* locs, int nloc, const float* mts, const int* cand_of,
+                            const GeoRec* recs, const PairHdr* hdrs, const float4* taprec, int strip_cap, int ncomp_max, const float* refdata,
+                            const float* taperdata, int method, float dt, float syn_factor, int nmisfits, float* out, int* overflow, cudaStream_t st);
 size_t synth_partial_bytes(int nq);   // per (candidate, receiver): running sums of the depth bands (nbands > 1)
 cudaError_t launch_synth(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, const GeoRec* recs,
                          size_t rec_stride, const PairHdr* hdrs, int nq_alloc, int margin_q, int nwarps, float* seis, size_t seis_stride,
