@@ -114,7 +114,7 @@ struct kiwi_ctx {
     DevBuf d_cands, d_bilat, d_gf, d_gi, d_tf, d_recs, d_hdrs, d_seis, d_shdrs, d_out, d_status, d_tmax, d_table, d_tw, d_fshift;
     int tw_n = 0;                            // twiddle table exp(-2 pi i k / tw_n), k < tw_n/2
     std::vector<int> last_fshift;            // floating shifts of the last ns = 1 evaluation
-    PinBuf h_stage, h_out;
+    PinBuf h_stage, h_out, h_mt;
     size_t work_budget = 0;
     kh::Crust2x2 crust;                      // crust2x2 model (minimizer.f90:1669-1674), needed by the eikonal sources
     std::vector<kh::Halfspace> constraints;  // psm%constraints (parameterized_source.f90:127-166)
@@ -854,43 +854,43 @@ int eval_mt_grid(kiwi_ctx* c, int n, const float* params, float* d_out, int* h_s
     std::unordered_map<Key, int, KeyHash> ids;
     std::vector<int> loc_of(n);
     std::vector<int> first_of;
+    Key prev; int prev_loc = -1;   // grids usually list their candidates location by location: the table is asked once per run
     for (int i = 0; i < n; i++) {
         const float* p = params + (size_t)i * 11;
         Key k;
-        memcpy(&k.v[0], &p[0], 4); memcpy(&k.v[1], &p[1], 4); memcpy(&k.v[2], &p[2], 4); memcpy(&k.v[3], &p[3], 4); memcpy(&k.v[4], &p[10], 4);
+        memcpy(&k.v[0], &p[0], 16); memcpy(&k.v[4], &p[10], 4);
+        if (prev_loc >= 0 && k == prev) { loc_of[i] = prev_loc; continue; }
         auto it = ids.find(k);
         if (it == ids.end()) { it = ids.emplace(k, (int)first_of.size()).first; first_of.push_back(i); }
-        loc_of[i] = it->second;
+        loc_of[i] = prev_loc = it->second;
+        prev = k;
     }
     const int nloc = (int)first_of.size();
     if ((long long)nloc * 8 > n) return 0;   // fewer than 8 tensors per location on average: the direct path is as good
-    // candidates sorted by location
-    std::vector<MtLocHost> locs(nloc, MtLocHost{0, 0});
+    // candidates sorted by location, laid out in page-locked memory: the copies below are DMA transfers that run while eval_batch prepares
+    // the probe sources (the buffer is rewritten only after the stream has been waited for at the end of a batch)
+    const size_t off_mts = ((size_t)nloc * sizeof(MtLocHost) + 255) & ~(size_t)255, off_cand = (off_mts + sizeof(float) * 6 * (size_t)n + 255) & ~(size_t)255;
+    CU_OK(c->h_mt.ensure(off_cand + sizeof(int) * (size_t)n));
+    MtLocHost* locs = c->h_mt.as<MtLocHost>();
+    float* mts = reinterpret_cast<float*>(c->h_mt.as<char>() + off_mts);
+    int* cand_of = reinterpret_cast<int*>(c->h_mt.as<char>() + off_cand);
+    for (int l = 0; l < nloc; l++) locs[l] = MtLocHost{0, 0};
     for (int i = 0; i < n; i++) locs[loc_of[i]].mt_count++;
     for (int l = 1; l < nloc; l++) locs[l].mt_begin = locs[l - 1].mt_begin + locs[l - 1].mt_count;
-    std::vector<int> fill(nloc, 0), cand_of(n);
-    std::vector<float> mts((size_t)n * 6);
-    for (int i = 0; i < n; i++) {
-        const int l = loc_of[i], at = locs[l].mt_begin + fill[l]++;
-        cand_of[at] = i;
-        memcpy(&mts[(size_t)at * 6], params + (size_t)i * 11 + 4, sizeof(float) * 6);
-    }
-    // six unit tensors per location
-    std::vector<float> basis((size_t)nloc * 6 * 11, 0.f);
-    for (int l = 0; l < nloc; l++)
-        for (int k = 0; k < 6; k++) {
-            float* b = &basis[((size_t)l * 6 + k) * 11];
-            const float* p = params + (size_t)first_of[l] * 11;
-            b[0] = p[0]; b[1] = p[1]; b[2] = p[2]; b[3] = p[3]; b[10] = p[10];
-            b[4 + k] = 1.f;
+    {
+        std::vector<int> fill(nloc, 0);
+        for (int i = 0; i < n; i++) {
+            const int l = loc_of[i], at = locs[l].mt_begin + fill[l]++;
+            cand_of[at] = i;
+            memcpy(&mts[(size_t)at * 6], params + (size_t)i * 11 + 4, sizeof(float) * 6);
         }
+    }
     CU_OK(c->d_mtlocs.ensure(sizeof(MtLocHost) * nloc));
     CU_OK(c->d_mts.ensure(sizeof(float) * 6 * (size_t)n));
     CU_OK(c->d_candof.ensure(sizeof(int) * (size_t)n));
-    CU_OK(cudaMemcpyAsync(c->d_mtlocs.p, locs.data(), sizeof(MtLocHost) * nloc, cudaMemcpyHostToDevice, c->stream));
-    CU_OK(cudaMemcpyAsync(c->d_mts.p, mts.data(), sizeof(float) * 6 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    CU_OK(cudaMemcpyAsync(c->d_candof.p, cand_of.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    CU_OK(cudaStreamSynchronize(c->stream));
+    CU_OK(cudaMemcpyAsync(c->d_mtlocs.p, locs, sizeof(MtLocHost) * nloc, cudaMemcpyHostToDevice, c->stream));
+    CU_OK(cudaMemcpyAsync(c->d_mts.p, mts, sizeof(float) * 6 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CU_OK(cudaMemcpyAsync(c->d_candof.p, cand_of, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     const int nrcv = (int)c->rcv.size();
     SynthHook hook;
     hook.fn = [&](int cand0, int ncand, const float* seis, size_t seis_stride, const SeisHdr* shdrs, const CandDev*) -> int {
@@ -941,20 +941,34 @@ int eval_mt_grid(kiwi_ctx* c, int n, const float* params, float* d_out, int* h_s
         }
         if (rc == 0) for (int l = 0; l < nloc; l++) for (int k = 0; k < 6; k++) bstatus[(size_t)l * 6 + k] = pstatus[l];
         else {   // ... or, where a window or shift table does not fit that kernel, the six unit tensors through the general synthesis
+            std::vector<float> basis((size_t)nloc * 6 * 11, 0.f);
+            for (int l = 0; l < nloc; l++)
+                for (int k = 0; k < 6; k++) {
+                    float* b = &basis[((size_t)l * 6 + k) * 11];
+                    const float* p = params + (size_t)first_of[l] * 11;
+                    b[0] = p[0]; b[1] = p[1]; b[2] = p[2]; b[3] = p[3]; b[10] = p[10];
+                    b[4 + k] = 1.f;
+                }
             hook.fused = false; hook.align = 6;
             if (eval_batch(c, KIWI_SOURCE_MOMENT_TENSOR, nloc * 6, 11, basis.data(), nullptr, bstatus.data(), false, &hook)) return 1;
         }
     }
     if (h_status) {   // status of the basis, or 2 where a misfit came out NaN/Inf (as k_misfit_td reports it on the direct path)
-        std::vector<int> nonfinite((size_t)n, 0);
-        CU_OK(c->d_status_out.ensure(sizeof(int) * (size_t)n));
-        CU_OK(cudaMemsetAsync(c->d_status_out.p, 0, sizeof(int) * (size_t)n, c->stream));
-        launch_flag_nonfinite(d_out, n, c->nmisfits * 2, c->d_status_out.as<int>(), c->stream);
-        CU_OK(cudaMemcpyAsync(nonfinite.data(), c->d_status_out.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+        CU_OK(c->d_status_out.ensure(sizeof(int) * ((size_t)n + 1)));
+        CU_OK(cudaMemsetAsync(c->d_status_out.p, 0, sizeof(int) * ((size_t)n + 1), c->stream));
+        launch_flag_nonfinite(d_out, n, c->nmisfits * 2, c->d_status_out.as<int>(), c->d_status_out.as<int>() + n, c->stream);
+        int nbad = 0;   // (the flags themselves only where there are any)
+        CU_OK(cudaMemcpyAsync(&nbad, c->d_status_out.as<int>() + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CU_OK(cudaStreamSynchronize(c->stream));
+        std::vector<int> nonfinite;
+        if (nbad > 0) {
+            nonfinite.assign((size_t)n, 0);
+            CU_OK(cudaMemcpyAsync(nonfinite.data(), c->d_status_out.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+            CU_OK(cudaStreamSynchronize(c->stream));
+        }
         for (int i = 0; i < n; i++) {
             const int bs = bstatus[(size_t)loc_of[i] * 6];
-            h_status[i] = bs != KIWI_STATUS_OK ? bs : (nonfinite[i] ? KIWI_STATUS_NONFINITE : KIWI_STATUS_OK);
+            h_status[i] = bs != KIWI_STATUS_OK ? bs : ((nbad > 0 && nonfinite[i]) ? KIWI_STATUS_NONFINITE : KIWI_STATUS_OK);
         }
     }
     *used = true;
@@ -1025,7 +1039,7 @@ void kiwi_destroy(kiwi_ctx* c) {
     for (DevBuf* b : {&c->d_slabs, &c->d_nodes, &c->d_tspan, &c->d_nspan, &c->d_rcv, &c->d_refdata, &c->d_taper, &c->d_cands, &c->d_bilat, &c->d_gf, &c->d_gi,
                       &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift, &c->d_map, &c->d_status_out, &c->d_taprec, &c->d_partial, &c->d_fftz, &c->d_gm, &c->d_xcorr, &c->d_mtlocs, &c->d_mts, &c->d_candof, &c->d_orc, &c->d_orw, &c->d_obw, &c->d_oout, &c->d_obest, &c->d_obestv})
         b->release();
-    c->h_stage.release(); c->h_out.release();
+    c->h_stage.release(); c->h_out.release(); c->h_mt.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->stream);
     delete c;

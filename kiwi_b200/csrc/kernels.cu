@@ -2345,15 +2345,15 @@ __global__ void __launch_bounds__(256) k_row_argmin(const double* __restrict__ v
 }
 
 // flag[row] = 1 where row `row` of v[nrows][ncols] holds a NaN or an Inf (status 2 of a candidate, minimizer_engine.f90:1163-1166)
-__global__ void __launch_bounds__(256) k_flag_nonfinite(const float* __restrict__ v, int nrows, int ncols, int* __restrict__ flag) {
+__global__ void __launch_bounds__(256) k_flag_nonfinite(const float* __restrict__ v, int nrows, int ncols, int* __restrict__ flag, int* __restrict__ count) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= nrows) return;
     bool bad = false;
     for (int i = lane; i < ncols; i += 32) bad = bad || !isfinite(v[(size_t)row * ncols + i]);
-    if (__any_sync(0xffffffffu, bad) && lane == 0) flag[row] = 1;
+    if (__any_sync(0xffffffffu, bad) && lane == 0) { flag[row] = 1; if (count) atomicAdd(count, 1); }
 }
-void launch_flag_nonfinite(const float* v, int nrows, int ncols, int* flag, cudaStream_t st) {
-    if (nrows > 0 && ncols > 0) k_flag_nonfinite<<<(nrows + 7) / 8, 256, 0, st>>>(v, nrows, ncols, flag);
+void launch_flag_nonfinite(const float* v, int nrows, int ncols, int* flag, int* count, cudaStream_t st) {
+    if (nrows > 0 && ncols > 0) k_flag_nonfinite<<<(nrows + 7) / 8, 256, 0, st>>>(v, nrows, ncols, flag, count);
 }
 
 // ---- host-callable launch wrappers ---------------------------------------------------------------

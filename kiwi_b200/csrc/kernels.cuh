@@ -52,6 +52,6 @@ cudaError_t launch_probe_export(const ReceiverDev* rcv, int ir, int ic, const Ca
 void launch_mt_contract(const ReceiverDev* rcv, int nrcv, const MtLoc* locs, int nloc, const float* mts, const int* cand_of, const float* seis,
                         size_t seis_stride, const SeisHdr* shdrs, const float* refdata, const float* taperdata, int method, float dt,
                         float syn_factor, int nmisfits, float* out, cudaStream_t st);
-void launch_flag_nonfinite(const float* v, int nrows, int ncols, int* flag, cudaStream_t st);
+void launch_flag_nonfinite(const float* v, int nrows, int ncols, int* flag, int* count /* may be null */, cudaStream_t st);
 cudaError_t launch_outer_misfits(const float* mis, int nm, const void* rc /* {misfit_base, ncomp}[nr] */, int nr, const double* rweights, int l1,
                                  int anarchy, int nrows, const double* bweights, double* out, int ns, int* best, double* bestv, cudaStream_t st);
