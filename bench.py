@@ -257,18 +257,22 @@ def roofline(wname, w, B, steps, stage, nsynth, synth_ms, b_alg, b_log):
     """roofline object of the dominant kernel of a workload"""
     peak, peak_kind = peaks()
     if w.get("source") == "moment_tensor" and stage[3] > stage[2]:
-        # grid-search path: the tensor-core contraction + misfit epilogue dominates.  Algorithmic flops:
-        # 2 * Ncand * 6 * (samples of all traces) (SURVEY.md 8d with the taps folded into the basis); the
-        # 3xTF32 split executes 4x that (K = 24).  Peak: measured dense bf16 / 2 (TF32 runs at half the bf16 rate).
+        # grid-search path: the fused synthesis + tensor-core contraction + misfit epilogue (k_mt_fused).  Algorithmic flops:
+        # 2 * Ncand * 6 * (samples of all traces) (SURVEY.md 8d: GF components x 6 MT components x N candidates, six non-zero
+        # coefficients per candidate and component); executed: K = 32 per sample (7 rows -- six GF components and the reference --
+        # in four hi/lo split products, padded).  Peak: measured dense bf16 / 2 (TF32 runs at half the bf16 rate).
         sum_t = sum(d.size for (f, d) in REFS.values())
         flops = 2.0 * B * 6.0 * sum_t
         ms_launch = stage[3] / max(steps, 1)
         pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", 1400.0) / 2.0 if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 700.0
         ach = flops / (ms_launch * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "k_mt_contract", "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk,
+        fused = stage[2] == 0
+        roof = {"bound": "tensor", "kernel": "k_mt_fused" if fused else "k_mt_contract", "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk,
                 "peak_kind": "measured bf16 sustained / 2 (tf32)", "traffic": None, "algorithmic_flops_per_step": flops,
-                "executed_flops_per_step": 4.0 * flops, "ms_per_launch_group": ms_launch,
-                "note": "K = 6 contraction: the kernel is bound by its misfit epilogue (TMEM -> registers -> fp64 norm), not by the tensor pipe"}
+                "executed_flops_per_step": (32.0 / 6.0 if fused else 4.0) * flops, "ms_per_launch_group": ms_launch,
+                "note": "K = 6 contraction: a (location, receiver) pair is ~600 samples x 100 candidates x K = 32, so the kernel is bound by what "
+                        "surrounds the MMAs (gather + tap filter of the GF components, operand tiles, TMEM -> registers -> fp64 norm), "
+                        "not by the tensor pipe (ncu: tensor pipe ~10 % active, issue slots ~35 %)"}
     else:
         # one "launch" = the depth-band launches of k_synth that together synthesise a sub-chunk of candidates
         ms_per_step = synth_ms / max(steps, 1)

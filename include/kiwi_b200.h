@@ -164,9 +164,12 @@ int kiwi_set_floating_shiftrange(kiwi_ctx* ctx, int ireceiver, float shift_lo, f
 
 /* Point moment-tensor grid searches (candidates of kiwi_eval_sources that share time, position and rise
  * time and differ only in the tensor; the grids of python/tunguska/gridsearch.py:114-139 over a
- * moment_tensor source): by default such batches are evaluated by synthesising six unit-tensor basis
- * seismograms per location and contracting all tensors against them on the tensor cores (tcgen05).
- * enabled = 0 forces the direct per-candidate path (same results within rounding). */
+ * moment_tensor source): by default such batches are evaluated per (location, receiver) by one kernel that
+ * gathers and time-shifts the Green's function components of the location once and contracts the make_weights
+ * coefficients of all its tensors against them on the tensor cores (tcgen05), the misfit norm as epilogue.
+ * enabled = 0 forces the direct per-candidate path, enabled = 2 the unfused variant (six unit-tensor basis
+ * seismograms per location through the general synthesis, then the contraction), which is also what windows
+ * too long for the fused kernel fall back to (same results within rounding). */
 int kiwi_set_mt_grid(kiwi_ctx* ctx, int enabled);
 
 /* Candidates of one kiwi_eval_sources batch that differ only in the scalar moment (bilateral, eikonal,

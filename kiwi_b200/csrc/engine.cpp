@@ -122,6 +122,7 @@ struct kiwi_ctx {
     float thickness_limit = 0.f;
     std::string prep_error;                  // message of the last failed discretisation
     bool mt_grid_enabled = true;             // point moment-tensor grid searches go through the tcgen05 contraction
+    bool mt_grid_fused = true;               // ... with the synthesis fused into it where the windows fit (k_mt_fused)
     DevBuf d_map, d_status_out;
     DevBuf d_taprec;              // shift table of the current batch (k_tap_table)
     DevBuf d_partial;             // running strip sums of the depth bands of k_synth
@@ -931,7 +932,7 @@ int eval_mt_grid(kiwi_ctx* c, int n, const float* params, float* d_out, int* h_s
             return 0;
         };
         static const bool no_fused = getenv("KIWI_NO_MT_FUSED") != nullptr;
-        int rc = no_fused ? 2 : eval_batch(c, KIWI_SOURCE_MOMENT_TENSOR, nloc, 11, probe.data(), nullptr, pstatus.data(), false, &hook);
+        int rc = (no_fused || !c->mt_grid_fused) ? 2 : eval_batch(c, KIWI_SOURCE_MOMENT_TENSOR, nloc, 11, probe.data(), nullptr, pstatus.data(), false, &hook);
         if (rc == 1) return 1;
         if (rc == 0) {
             int overflow = 0;
@@ -1288,6 +1289,7 @@ int kiwi_set_share_syntheses(kiwi_ctx* c, int enabled) {
 int kiwi_set_mt_grid(kiwi_ctx* c, int enabled) {
     if (!c) return kiwi_set_error("null context");
     c->mt_grid_enabled = enabled != 0;
+    c->mt_grid_fused = enabled != 2;
     return 0;
 }
 

@@ -266,8 +266,8 @@ class Engine:
         _check(lib.kiwi_set_share_syntheses(self._h, int(bool(enabled))))
 
     def set_mt_grid(self, enabled):
-        """tensor-core path for point moment-tensor grid searches on (default) / off"""
-        _check(lib.kiwi_set_mt_grid(self._h, int(bool(enabled))))
+        """tensor-core path for point moment-tensor grid searches on (default) / off; 2 = on, synthesis not fused into the contraction"""
+        _check(lib.kiwi_set_mt_grid(self._h, 2 if (not isinstance(enabled, bool) and enabled == 2) else int(bool(enabled))))
 
     def set_floating_shiftrange(self, lo, hi, ireceiver=0):
         _check(lib.kiwi_set_floating_shiftrange(self._h, ireceiver, lo, hi))

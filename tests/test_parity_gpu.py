@@ -462,10 +462,14 @@ def test_moment_tensor_grid_search_tensor_core_path(norm, taper):
     mo, so = o.eval_sources("moment_tensor", p)
     assert not sg.any() and not so.any()
     assert np.all(np.abs(mg - mo) <= misfit_tol(mo)), np.abs((mg - mo) / misfit_tol(mo)).max()
+    g.set_mt_grid(2)                       # the unfused variant: basis seismograms through k_synth, then k_mt_contract
+    mu, su = g.eval_sources("moment_tensor", p)
+    assert g.last_timing()["launches"][2] >= 1 and g.last_timing()["launches"][3] >= 1 and not su.any()
+    assert np.all(np.abs(mu - mo) <= misfit_tol(mo)), np.abs((mu - mo) / misfit_tol(mo)).max()
     g.set_mt_grid(False)
     md, sd = g.eval_sources("moment_tensor", p)
     assert np.all(np.abs(mg - md) <= misfit_tol(mo)), np.abs((mg - md) / misfit_tol(mo)).max()
-    assert not np.array_equal(mg, md)      # really two different code paths
+    assert not np.array_equal(mg, md) and not np.array_equal(mg, mu) and not np.array_equal(mu, md)     # really three different code paths
 
 
 # eikonal: time north east depth moment strike dip rake bord-x bord-y bord-radius nukl-x nukl-y rel-rupture-velocity rise-time

@@ -198,14 +198,17 @@ def test_random_moment_tensor_grid(seed):
         pytest.skip("all receivers disabled")
     mg, sg = g.eval_sources("moment_tensor", p)
     used_grid = g.last_timing()["launches"][3] >= 1
+    g.set_mt_grid(2)                      # synthesis not fused into the contraction (k_synth + k_mt_contract)
+    mu, su = g.eval_sources("moment_tensor", p)
     g.set_mt_grid(False)
     md, sd = g.eval_sources("moment_tensor", p)
     mo, so = o.eval_sources("moment_tensor", p)
-    assert np.array_equal(sg > 0, so > 0) and np.array_equal(sd > 0, so > 0), (sg, sd, so)
+    assert np.array_equal(sg > 0, so > 0) and np.array_equal(sd > 0, so > 0) and np.array_equal(su > 0, so > 0), (sg, su, sd, so)
     ok = so == 0
     tol = RTOL * np.maximum(np.abs(mo), 0.1 * np.abs(mo[..., 1:2]))
     assert np.all(np.abs(md[ok] - mo[ok]) <= tol[ok]), ("direct", cfg, float(np.abs((md[ok] - mo[ok]) / tol[ok]).max()))
     assert np.all(np.abs(mg[ok] - mo[ok]) <= tol[ok]), ("grid" if used_grid else "direct (no grid found)", cfg, float(np.abs((mg[ok] - mo[ok]) / tol[ok]).max()))
+    assert np.all(np.abs(mu[ok] - mo[ok]) <= tol[ok]), ("unfused grid" if used_grid else "direct (no grid found)", cfg, float(np.abs((mu[ok] - mo[ok]) / tol[ok]).max()))
 
 
 @pytest.mark.parametrize("seed", range(int(os.environ.get("KIWI_RANDOM_SHARE_CASES", "8"))))
