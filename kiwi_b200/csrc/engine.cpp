@@ -202,8 +202,16 @@ int upload_receivers(kiwi_ctx* c) {
                 kh::initial_probe_span(h.ref_ds0[k], h.ref_ds1[k], &r.ref_sp0[k], &r.ref_sp1[k]);   // comparator.f90:222-271
                 r.ref_off[k] = (long long)refdata.size();
                 refdata.insert(refdata.end(), h.ref[k].begin(), h.ref[k].end());
+                {
+                    double ss = 0.;
+                    for (float v : h.ref[k]) ss += (double)v * (double)v;
+                    const double rms = h.ref[k].empty() ? 0. : std::sqrt(ss / (double)h.ref[k].size());
+                    int ex = 0;
+                    if (rms > 0. && std::isfinite(rms)) std::frexp(rms, &ex);
+                    r.ref_rs[k] = std::ldexp(1.f, -std::min(std::max(ex, -100), 100));
+                }
             } else {
-                r.ref_ds0[k] = 0; r.ref_ds1[k] = -1; r.ref_off[k] = 0;
+                r.ref_ds0[k] = 0; r.ref_ds1[k] = -1; r.ref_off[k] = 0; r.ref_rs[k] = 1.f;
             }
         }
         if (!h.taper_x.empty()) {

@@ -1636,9 +1636,13 @@ __global__ void __launch_bounds__(128) k_mt_contract(const ReceiverDev* __restri
                 return v;
             };
             auto tapval = [&](int x) -> float { return tapered ? ((x >= R.tp0 && x <= R.tp1) ? tp[x - R.tp0] : 0.f) : 1.f; };
-            double acc = 0.;
+            // The residuals of a chunk are squared and summed 32 at a time in fp32 before they enter the fp64 sum (comparator.f90:639-659 sums in
+            // double): with moments of 1e18 and Green's functions of order one a square would leave the fp32 range.  Both operand rows are
+            // therefore scaled by a power of two (exact) that brings the reference trace to order one; the sum is scaled back in double.
+            const float rs = R.ref_rs[ic];
+            double acc = 0.;                   // sum of the scaled residuals (or of their squares)
             // (i) left of the synthetic's data span the synthetic is zero: reference only
-            for (int x = p0; x <= min(p1, sds0 - 1); x++) { const float a = refval(x); acc += l1 ? (double)fabsf(fa * a) : (double)(fa * a) * (double)(fa * a); }
+            for (int x = p0; x <= min(p1, sds0 - 1); x++) { const float a = (fa * refval(x)) * rs; acc += l1 ? (double)fabsf(a) : (double)a * (double)a; }
             // (ii) columns x in [xs, xe] come out of the tensor-core contraction, 128 at a time; xe = sds1 is
             // always included when the span reaches past it, its value is the continuation (comparator.f90:264-267)
             const int xs = max(p0, sds0), xe = min(p1, sds1) < xs ? -1 : ((p1 > sds1) ? sds1 : min(p1, sds1));
@@ -1656,10 +1660,10 @@ __global__ void __launch_bounds__(128) k_mt_contract(const ReceiverDev* __restri
             auto fetch_col = [&](int c0) {
                 const int x = c0 + tid;
                 const bool in = x <= xe;
-                const float scale = in ? fb * tapval(x) : 0.f;
+                const float scale = in ? (fb * tapval(x)) * rs : 0.f;
 #pragma unroll
                 for (int k = 0; k < 6; k++) colv[k] = in ? __ldg(seis + (item0 + (size_t)k * item_stride) * seis_stride + (x - sh.base)) * scale : 0.f;
-                colref = in ? fa * refval(x) : 0.f;
+                colref = in ? (fa * refval(x)) * rs : 0.f;
             };
             if (xe >= xs) fetch_col(xs);
             for (int c0 = xs; xe >= xs && c0 <= xe; c0 += MTC_N) {
@@ -1752,9 +1756,10 @@ __global__ void __launch_bounds__(128) k_mt_contract(const ReceiverDev* __restri
             }
             // (iii) right of the data span the synthetic repeats its last sample
             for (int x = max(max(p0, sds0), sds1 + 1); x <= p1; x++) {
-                const float r = fa * refval(x) - fb * (e_last * tapval(x));
+                const float r = (fa * refval(x) - fb * (e_last * tapval(x))) * rs;
                 acc += l1 ? (double)fabsf(r) : (double)r * (double)r;
             }
+            acc = l1 ? acc / (double)rs : acc / ((double)rs * (double)rs);
             // reference-only norm (the same for all candidates): block reduction
             double accn = 0.;
             for (int x = q0 + tid; x <= q1; x += MTC_M) { const float a = refval(x); accn += l1 ? (double)fabsf(a) : (double)a * (double)a; }
@@ -2052,9 +2057,11 @@ __global__ void __launch_bounds__(128, 4) k_mt_fused(GfdbDev db, const ReceiverD
                     return v;
                 };
                 auto tapval = [&](int x) -> float { return tapered ? ((x >= R.tp0 && x <= R.tp1) ? tp[x - R.tp0] : 0.f) : 1.f; };
-                double acc = 0.;
+                // (the residuals are squared in fp32: both operand rows scaled by a power of two that brings the reference to order one, see k_mt_contract)
+                const float rs = R.ref_rs[ic];
+                double acc = 0.;                   // sum of the scaled residuals (or of their squares)
                 // (i) left of the synthetic's data span the synthetic is zero: reference only
-                for (int x = p0; x <= min(p1, sds0 - 1); x++) { const float a = refval(x); acc += l1 ? (double)fabsf(fa * a) : (double)(fa * a) * (double)(fa * a); }
+                for (int x = p0; x <= min(p1, sds0 - 1); x++) { const float a = (fa * refval(x)) * rs; acc += l1 ? (double)fabsf(a) : (double)a * (double)a; }
                 // (ii) columns x in [xs, xe] come out of the tensor-core contraction, 128 at a time
                 const int xs = max(p0, sds0), xe = min(p1, sds1) < xs ? -1 : ((p1 > sds1) ? sds1 : min(p1, sds1));
                 // last sample of this thread's candidate (continued to the right, comparator.f90:264-267)
@@ -2068,10 +2075,10 @@ __global__ void __launch_bounds__(128, 4) k_mt_fused(GfdbDev db, const ReceiverD
                 auto fetch_col = [&](int c0) {
                     const int x = c0 + tid;
                     const bool in = x <= xe;
-                    const float scale = in ? fb * tapval(x) : 0.f;
+                    const float scale = in ? (fb * tapval(x)) * rs : 0.f;
 #pragma unroll
                     for (int k = 0; k < 6; k++) colv[k] = (in && k < nrow) ? strip_at(k, x) * scale : 0.f;
-                    colv[6] = in ? fa * refval(x) : 0.f;
+                    colv[6] = in ? (fa * refval(x)) * rs : 0.f;
                 };
                 if (xe >= xs) fetch_col(xs);
                 for (int c0 = xs; xe >= xs && c0 <= xe; c0 += MTC_N) {
@@ -2159,9 +2166,10 @@ __global__ void __launch_bounds__(128, 4) k_mt_fused(GfdbDev db, const ReceiverD
                 }
                 // (iii) right of the data span the synthetic repeats its last sample
                 for (int x = max(max(p0, sds0), sds1 + 1); x <= p1; x++) {
-                    const float r = fa * refval(x) - fb * (e_last * tapval(x));
+                    const float r = (fa * refval(x) - fb * (e_last * tapval(x))) * rs;
                     acc += l1 ? (double)fabsf(r) : (double)r * (double)r;
                 }
+                acc = l1 ? acc / (double)rs : acc / ((double)rs * (double)rs);
                 // reference-only norm (the same for all candidates): block reduction
                 double accn = 0.;
                 for (int x = q0 + tid; x <= q1; x += MTC_M) { const float a = refval(x); accn += l1 ? (double)fabsf(a) : (double)a * (double)a; }

@@ -131,3 +131,49 @@ def test_synthetic_window_of_4000_samples():
     mo, so = o.eval_sources("bilateral", q)
     assert np.array_equal(sg, so) and not sg.any()
     assert np.all(np.abs(mg - mo) <= misfit_tol(mo))
+
+
+def test_moment_tensor_grid_beyond_the_fused_kernels_limits():
+    """a point moment-tensor grid whose rise time gives more distinct quad shifts than the fused kernel (k_mt_fused) keeps: the engine
+    falls back to the unfused tensor-core path (k_synth + k_mt_contract) and says nothing; results against the oracle as for any other
+    grid (second pass: a short rise time, fused kernel, no synthesis stage of its own)"""
+    from test_parity_gpu import _mt_grid
+    ncomps = [len(c) for c in COMPS6]
+    for risetime in (9.0, 0.7):
+        g, o = engines(sc.small_db(), COMPS6)
+        o.eval_sources("moment_tensor", sc.MT_SMALL)
+        sc.set_refs_from(o, [g, o], ncomps)
+        p = _mt_grid()
+        p[:, 10] = risetime                   # 9 s at effective_dt 0.2: 46 time centroids, 12 distinct quad shifts
+        mg, sg = g.eval_sources("moment_tensor", p)
+        t = g.last_timing()["launches"]
+        assert t[3] >= 1                      # a tensor-core path ran
+        assert (t[2] >= 1) == (risetime > 5)  # ... with a synthesis stage of its own only where the fused kernel does not fit
+        mo, so = o.eval_sources("moment_tensor", p)
+        assert not sg.any() and not so.any()
+        assert np.all(np.abs(mg - mo) <= misfit_tol(mo)), np.abs((mg - mo) / misfit_tol(mo)).max()
+
+
+def test_moment_tensor_grid_on_4000_sample_windows():
+    """the same on the long-trace database: the strips of a (location, receiver) pair do not fit the fused kernel's shared memory"""
+    from kiwi_b200 import Engine
+    from kiwi_b200 import synthetic
+    db = long_trace_db()
+    lat, lon, dep = sc.small_receivers(4, dmin=26e3, dmax=36e3)
+    comps = ["ned", "ar", "d", "neu"]
+    g, o = Engine(0), OracleEngine()
+    for e in (g, o):
+        sc.setup(e, db, lat, lon, dep, comps, effective_dt=1.0)
+    base = np.array([1.0, 500, -800, 2500, 1e18, -0.4e18, -0.6e18, 0.3e18, 0.2e18, -0.5e18, 2.0], dtype=np.float32)
+    o.eval_sources("moment_tensor", base)
+    sc.set_refs_from(o, [g, o], [len(c) for c in comps], dt=0.5)
+    mts = synthetic.fibonacci_moment_tensors(40) * 1e18
+    p = np.tile(base, (2 * 40, 1))
+    p[:, 4:10] = np.concatenate([mts, mts])
+    p[40:, 1] += 700; p[40:, 3] += 500
+    mg, sg = g.eval_sources("moment_tensor", p)
+    t = g.last_timing()["launches"]
+    assert t[3] >= 1 and t[2] >= 1           # tensor-core path, unfused
+    mo, so = o.eval_sources("moment_tensor", p)
+    assert not sg.any() and not so.any()
+    assert np.all(np.abs(mg - mo) <= misfit_tol(mo)), np.abs((mg - mo) / misfit_tol(mo)).max()
