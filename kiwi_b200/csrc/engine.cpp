@@ -858,19 +858,25 @@ typedef MtLoc MtLocHost;
 int eval_mt_grid(kiwi_ctx* c, int n, const float* params, float* d_out, int* h_status, bool* used) {
     *used = false;
     if (n < 64) return 0;
+    static const bool trace = getenv("KIWI_TRACE") != nullptr;
+    const auto tg0 = std::chrono::steady_clock::now();
     struct Key { unsigned v[5]; bool operator==(const Key& o) const { return memcmp(v, o.v, sizeof v) == 0; } };
     struct KeyHash { size_t operator()(const Key& k) const { size_t h = 1469598103934665603ull; for (unsigned x : k.v) { h ^= x; h *= 1099511628211ull; } return h; } };
     std::unordered_map<Key, int, KeyHash> ids;
     std::vector<int> loc_of(n);
     std::vector<int> first_of;
-    Key prev; int prev_loc = -1;   // grids usually list their candidates location by location: the table is asked once per run
-    for (int i = 0; i < n; i++) {
-        const float* p = params + (size_t)i * 11;
+    // grids usually list their candidates location by location: the table is asked once per run, and if no location comes back after
+    // another one has started (`runs`), the candidates are already sorted by location
+    Key prev; int prev_loc = -1;
+    bool runs = true;
+    const unsigned* up = reinterpret_cast<const unsigned*>(params);
+    for (int i = 0; i < n; i++, up += 11) {
+        if (prev_loc >= 0 && up[0] == prev.v[0] && up[1] == prev.v[1] && up[2] == prev.v[2] && up[3] == prev.v[3] && up[10] == prev.v[4]) { loc_of[i] = prev_loc; continue; }
         Key k;
-        memcpy(&k.v[0], &p[0], 16); memcpy(&k.v[4], &p[10], 4);
-        if (prev_loc >= 0 && k == prev) { loc_of[i] = prev_loc; continue; }
+        k.v[0] = up[0]; k.v[1] = up[1]; k.v[2] = up[2]; k.v[3] = up[3]; k.v[4] = up[10];
         auto it = ids.find(k);
         if (it == ids.end()) { it = ids.emplace(k, (int)first_of.size()).first; first_of.push_back(i); }
+        else runs = false;
         loc_of[i] = prev_loc = it->second;
         prev = k;
     }
@@ -883,10 +889,16 @@ int eval_mt_grid(kiwi_ctx* c, int n, const float* params, float* d_out, int* h_s
     MtLocHost* locs = c->h_mt.as<MtLocHost>();
     float* mts = reinterpret_cast<float*>(c->h_mt.as<char>() + off_mts);
     int* cand_of = reinterpret_cast<int*>(c->h_mt.as<char>() + off_cand);
-    for (int l = 0; l < nloc; l++) locs[l] = MtLocHost{0, 0};
-    for (int i = 0; i < n; i++) locs[loc_of[i]].mt_count++;
-    for (int l = 1; l < nloc; l++) locs[l].mt_begin = locs[l - 1].mt_begin + locs[l - 1].mt_count;
-    {
+    if (runs) {   // sorted already: location l is the run [first_of[l], first_of[l+1])
+        for (int l = 0; l < nloc; l++) locs[l] = MtLocHost{first_of[l], (l + 1 < nloc ? first_of[l + 1] : n) - first_of[l]};
+        for (int i = 0; i < n; i++) {
+            cand_of[i] = i;
+            memcpy(&mts[(size_t)i * 6], params + (size_t)i * 11 + 4, sizeof(float) * 6);
+        }
+    } else {
+        for (int l = 0; l < nloc; l++) locs[l] = MtLocHost{0, 0};
+        for (int i = 0; i < n; i++) locs[loc_of[i]].mt_count++;
+        for (int l = 1; l < nloc; l++) locs[l].mt_begin = locs[l - 1].mt_begin + locs[l - 1].mt_count;
         std::vector<int> fill(nloc, 0);
         for (int i = 0; i < n; i++) {
             const int l = loc_of[i], at = locs[l].mt_begin + fill[l]++;
@@ -900,6 +912,7 @@ int eval_mt_grid(kiwi_ctx* c, int n, const float* params, float* d_out, int* h_s
     CU_OK(cudaMemcpyAsync(c->d_mtlocs.p, locs, sizeof(MtLocHost) * nloc, cudaMemcpyHostToDevice, c->stream));
     CU_OK(cudaMemcpyAsync(c->d_mts.p, mts, sizeof(float) * 6 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     CU_OK(cudaMemcpyAsync(c->d_candof.p, cand_of, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    const auto tg1 = std::chrono::steady_clock::now();
     const int nrcv = (int)c->rcv.size();
     SynthHook hook;
     hook.fn = [&](int cand0, int ncand, const float* seis, size_t seis_stride, const SeisHdr* shdrs, const CandDev*) -> int {
@@ -962,6 +975,7 @@ int eval_mt_grid(kiwi_ctx* c, int n, const float* params, float* d_out, int* h_s
             if (eval_batch(c, KIWI_SOURCE_MOMENT_TENSOR, nloc * 6, 11, basis.data(), nullptr, bstatus.data(), false, &hook)) return 1;
         }
     }
+    const auto tg2 = std::chrono::steady_clock::now();
     if (h_status) {   // status of the basis, or 2 where a misfit came out NaN/Inf (as k_misfit_td reports it on the direct path)
         CU_OK(c->d_status_out.ensure(sizeof(int) * ((size_t)n + 1)));
         CU_OK(cudaMemsetAsync(c->d_status_out.p, 0, sizeof(int) * ((size_t)n + 1), c->stream));
@@ -979,6 +993,12 @@ int eval_mt_grid(kiwi_ctx* c, int n, const float* params, float* d_out, int* h_s
             const int bs = bstatus[(size_t)loc_of[i] * 6];
             h_status[i] = bs != KIWI_STATUS_OK ? bs : ((nbad > 0 && nonfinite[i]) ? KIWI_STATUS_NONFINITE : KIWI_STATUS_OK);
         }
+    }
+    if (trace) {
+        const auto tg3 = std::chrono::steady_clock::now();
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "[kiwi trace] moment-tensor grid of %d candidates at %d locations: grouping + staging %.3f ms, evaluation %.3f ms, status %.3f ms\n", n, nloc,
+                ms(tg0, tg1), ms(tg1, tg2), ms(tg2, tg3));
     }
     *used = true;
     return 0;

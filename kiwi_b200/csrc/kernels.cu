@@ -2481,8 +2481,11 @@ cudaError_t launch_mt_fused(GfdbDev db, const ReceiverDev* rcv, int nrcv, const 
     if (nloc * nrcv > 0) {
         // receivers per CTA: enough CTAs for a few waves over the 148 SMs x 3 resident CTAs, as few set-ups as possible
         int rpc = 1;
-        while (rpc < nrcv && 2 * rpc <= MTF_MAXRCV && (long long)nloc * ((nrcv + 2 * rpc - 1) / (2 * rpc)) >= 148LL * 4 * 8) rpc *= 2;
-        const int nrblk = (nrcv + rpc - 1) / rpc;
+        while (rpc < nrcv && 2 * rpc <= 8 && (long long)nloc * ((nrcv + 2 * rpc - 1) / (2 * rpc)) >= 148LL * 4 * 8) rpc *= 2;   // (measured flat from 5 to 13, slower beyond)
+        if (const char* ev = getenv("KIWI_MTF_RPC")) rpc = std::min(std::max(atoi(ev), 1), MTF_MAXRCV);   // tuning experiments
+        int nrblk = (nrcv + rpc - 1) / rpc;
+        rpc = (nrcv + nrblk - 1) / nrblk;          // blocks of equal size
+        nrblk = (nrcv + rpc - 1) / rpc;
         k_mt_fused<<<nloc * nrblk, 128, smem, st>>>(db, rcv, nrcv, locs, mts, cand_of, recs, hdrs, taprec, strip_cap, refdata, taperdata, method, dt,
                                                    syn_factor, nmisfits, out, rpc, overflow);
     }
