@@ -226,10 +226,11 @@ def candidates(w, n):
         base = np.array([0, 0, 0, 15000, 2e20, 91, 87, 164, 0, 0, 9000, 0, 0, 0.8, 0.0], np.float32)
         p = np.tile(base, (n, 1))
         i = np.arange(n)
-        p[:, 10] = np.linspace(5000.0, 12000.0, 4)[i % 4]                 # bord radius
-        p[:, 13] = np.linspace(0.7, 0.9, 3)[(i // 4) % 3]                 # relative rupture velocity
+        nrad = 4 if n <= 300 else -(-n // 75)                             # (more radii where a larger batch is asked for: all candidates distinct)
+        p[:, 10] = np.linspace(5000.0, 12000.0, nrad)[i % nrad]           # bord radius
+        p[:, 13] = np.linspace(0.7, 0.9, 3)[(i // nrad) % 3]              # relative rupture velocity
         g5 = np.linspace(-3000.0, 3000.0, 5)
-        p[:, 11] = g5[(i // 12) % 5]; p[:, 12] = g5[(i // 60) % 5]          # nucleation point on a 5 x 5 grid
+        p[:, 11] = g5[(i // (3 * nrad)) % 5]; p[:, 12] = g5[(i // (15 * nrad)) % 5]   # nucleation point on a 5 x 5 grid
         return "eikonal", p.astype(np.float32), base
     return "bilateral", synthetic.bilateral_sweep(n), synthetic.IZMIT
 

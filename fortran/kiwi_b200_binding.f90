@@ -414,6 +414,13 @@ module kiwi_b200_binding
             integer(c_int) :: rc
         end function
 
+        function kiwi_set_eikonal_device(ctx, min_batch) bind(C, name="kiwi_set_eikonal_device") result(rc)
+            import :: c_ptr, c_int
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: min_batch
+            integer(c_int) :: rc
+        end function
+
         function kiwi_set_share_syntheses(ctx, enabled) bind(C, name="kiwi_set_share_syntheses") result(rc)
             import :: c_ptr, c_int
             type(c_ptr), value :: ctx

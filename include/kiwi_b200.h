@@ -172,6 +172,12 @@ int kiwi_set_floating_shiftrange(kiwi_ctx* ctx, int ireceiver, float shift_lo, f
  * too long for the fused kernel fall back to (same results within rounding). */
 int kiwi_set_mt_grid(kiwi_ctx* ctx, int enabled);
 
+/* Eikonal / mt_eikonal sources: the fast-marching solve of the rupture front (eikonal.f90:29-199), sequential by construction and 70 % of the
+ * discretiser's time, runs per candidate on a host thread.  Batches of min_batch candidates or more can run their solves on the device
+ * instead (one warp per candidate, bit-identical results, up to 1924 solves side by side; a wave takes ~2.5 s whatever its size, so this
+ * is for batches of thousands of candidates on hosts with few cores).  Default 0 = always on the host. */
+int kiwi_set_eikonal_device(kiwi_ctx* ctx, int min_batch);
+
 /* Candidates of one kiwi_eval_sources batch that differ only in the scalar moment (bilateral, eikonal,
  * mt_eikonal: parameter 5) share one synthesis and differ only in the scaling + misfit stage -- the batched
  * form of the reference's `only_moment_changed` shortcut (minimizer_engine.f90:511-521).  On by default;
@@ -292,6 +298,11 @@ int kiwi_trace_span(kiwi_ctx* ctx, int ix, int iz, int ig, int* span2);
 /* the fast-marching solver of the eikonal sources (eikonal.f90:29-199, heap.f90) as the host runs it per candidate: arrival times on a
  * grid (nx, ny), ix fastest, of a front starting at initialpoint.  Host only, no GPU needed. */
 int kiwi_eikonal_fmm(int nx, int ny, const float* speed, const float* origin2, const float* delta2, const float* initialpoint2, float* times);
+/* the same solver on the device, njobs grids at a time (one warp per grid replaying heap.f90 operation by operation: results equal the
+ * host solver's bit for bit; csrc/eikonal.cu).  nx, ny: [njobs]; speed, times: [njobs] host arrays of nx*ny; origin2, delta2,
+ * initialpoint2: [njobs][2].  *kernel_ms (may be NULL) receives the kernel time. */
+int kiwi_eikonal_fmm_device(int njobs, const int* nx, const int* ny, const float* const* speed, const float* origin2, const float* delta2,
+                            const float* initialpoint2, float* const* times, float* kernel_ms);
 
 /* ---- measurement support -------------------------------------------------------------------- */
 /* algorithmic / logical bytes per evaluation of the last kiwi_eval_sources batch (SURVEY.md

@@ -49,6 +49,7 @@ SIGNATURES = {
     "kiwi_set_synthetics_factor": (C.c_int, [C.c_void_p, C.c_float]),
     "kiwi_set_share_syntheses": (C.c_int, [C.c_void_p, C.c_int]),
     "kiwi_set_mt_grid": (C.c_int, [C.c_void_p, C.c_int]),
+    "kiwi_set_eikonal_device": (C.c_int, [C.c_void_p, C.c_int]),
     "kiwi_set_floating_shiftrange": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float]),
     "kiwi_get_nmisfits": (C.c_int, [C.c_void_p]),
     "kiwi_get_n_source_params": (C.c_int, [C.c_int]),
@@ -79,6 +80,7 @@ SIGNATURES = {
     "kiwi_get_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_float_p, C.c_int]),
     "kiwi_get_probe_spectrum": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p, c_int_p, c_float_p, C.c_int]),
     "kiwi_eikonal_fmm": (C.c_int, [C.c_int, C.c_int, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p]),
+    "kiwi_eikonal_fmm_device": (C.c_int, [C.c_int, c_int_p, c_int_p, C.POINTER(c_float_p), c_float_p, c_float_p, c_float_p, C.POINTER(c_float_p), c_float_p]),
     "kiwi_get_seismogram": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_float_p, C.c_int]),
     "kiwi_discretize_source": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, c_float_p, C.c_int, c_int_p, c_int_p]),
     "kiwi_get_indices": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_int_p, c_int_p, c_float_p, c_float_p, c_int_p, C.c_int, c_int_p]),

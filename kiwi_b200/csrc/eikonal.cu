@@ -1,0 +1,264 @@
+// Fast-marching solver of the eikonal sources on the device (eikonal.f90:29-199, heap.f90:48-232).
+//
+// The reference's solver cannot be reordered: a node is updated from the current values of all four neighbours, tentative
+// or final (eikonal.f90:151-155), and the two-sided update is accepted whenever its discriminant is non-negative (:163-166),
+// so the table it leaves depends on the exact order in which the binary heap hands out equal and nearly equal keys.  What
+// runs in parallel here is therefore one *sequential* solve per candidate: one warp per candidate, the heap of (key, index)
+// pairs in shared memory, times / back-pointers / speeds in global memory (the front touches a few rows at a time, which stay
+// in L1/L2).  Lane 0 replays heap.f90 operation by operation; the four neighbour stencils of a popped node do not contain
+// each other, so lanes 0..3 evaluate them side by side (one memory round trip) before lane 0 applies their heap updates in
+// the reference's order (left, right, down, up).  All arithmetic is IEEE fp32 in the reference's operation order
+// (__f*_rn intrinsics: no FMA contraction), so the result equals the host solver's (source_eikonal_host.cpp) bit for bit.
+//
+// A warp walks ~1.5e3 dependent cycles per node where a host core needs ~150 ns, so one solve is slower than on the host;
+// the device wins on batches of a few hundred candidates and more (grid searches), which is when the engine uses it.
+#include "kernels.cuh"
+#include <cfloat>
+#include <cstdio>
+#include <vector>
+
+#define EIK_HCAP 2040          // heap entries kept in shared memory (16 KB per candidate: 13 candidates per SM); the rest spills to global memory
+
+namespace {
+
+struct EikHeap {
+    EikItem* sm;        // [EIK_HCAP + 1], 1-based
+    EikItem* ovf;       // global overflow, entries EIK_HCAP+1 ...
+    int* bp;            // back-pointers, 1-based node index
+    int n;
+    // heap positions of the four neighbours of the node being processed, kept current in registers: their back-pointers were just
+    // written to global memory and reading them back would cost a round trip to L2 per neighbour
+    int w0, w1, w2, w3, p0, p1, p2, p3;
+    __device__ __forceinline__ EikItem get(int i) const { return i <= EIK_HCAP ? sm[i] : ovf[i - EIK_HCAP]; }
+    __device__ __forceinline__ void put(int i, EikItem v) {
+        if (i <= EIK_HCAP) sm[i] = v; else ovf[i - EIK_HCAP] = v;
+        bp[v.idx] = i;
+        if (v.idx == w0) p0 = i;
+        if (v.idx == w1) p1 = i;
+        if (v.idx == w2) p2 = i;
+        if (v.idx == w3) p3 = i;
+    }
+    __device__ __forceinline__ void setkey(int i, float k) { if (i <= EIK_HCAP) sm[i].key = k; else ovf[i - EIK_HCAP].key = k; }
+    // heap.f90:210-232
+    __device__ void upheap(int v) {
+        EikItem x = get(v);
+        bool moved = false;
+        while (v > 1) {
+            const int u = (v - 2) / 2 + 1;
+            const EikItem p = get(u);
+            if (p.key <= x.key) break;
+            put(v, p);
+            v = u; moved = true;
+        }
+        if (moved) put(v, x);
+    }
+    // heap.f90:176-208
+    __device__ void downheap(int v) {
+        EikItem x = get(v);
+        bool moved = false;
+        int w = 2 * (v - 1) + 2;
+        while (w <= n) {
+            EikItem c = get(w);
+            if (w + 1 <= n) { const EikItem c2 = get(w + 1); if (c2.key < c.key) { c = c2; w = w + 1; } }
+            if (x.key <= c.key) break;
+            put(v, c);
+            v = w; moved = true;
+            w = 2 * (v - 1) + 2;
+        }
+        if (moved) put(v, x);
+    }
+};
+
+}  // namespace
+
+__global__ void __launch_bounds__(32) k_eikonal_fmm(const EikJob* __restrict__ jobs, int njobs) {
+    __shared__ EikItem s_heap[EIK_HCAP + 1];
+    const int job = blockIdx.x;
+    if (job >= njobs) return;
+    const EikJob J = jobs[job];
+    const int lane = threadIdx.x;
+    const int nx = J.nx, ny = J.ny, nn = nx * ny;
+    const float infinity = FLT_MAX * 0.1f;
+    const float dx = J.dx, dy = J.dy;
+    const float dx2 = __fmul_rn(dx, dx), dy2 = __fmul_rn(dy, dy), dx2dy2 = __fmul_rn(dx2, dy2), dx2pdy2 = __fadd_rn(dx2, dy2);
+    float* T = J.T - 1;            // 1-based views
+    int* bp = J.bp - 1;
+    const float* S = J.S - 1;
+    const int FARAWAY = -1, ALIVE = 0;
+    for (int i = 1 + lane; i <= nn; i += 32) { T[i] = infinity; bp[i] = FARAWAY; }
+    __syncwarp();
+    EikHeap H;
+    H.sm = s_heap; H.ovf = J.ovf; H.bp = bp; H.n = 0;
+    H.w0 = H.w1 = H.w2 = H.w3 = 0; H.p0 = H.p1 = H.p2 = H.p3 = 0;
+    const int ix0 = J.ix0, iy0 = J.iy0;
+    const int i0 = (iy0 - 1) * nx + ix0;
+    if (lane == 0) {
+        T[i0] = 0.f;
+        if (!(nx == 1 && ny == 1)) {
+            bp[i0] = ALIVE;
+            if (1 < ix0) T[i0 - 1] = __fdiv_rn(dx, S[i0 - 1]);
+            if (ix0 < nx) T[i0 + 1] = __fdiv_rn(dx, S[i0 + 1]);
+            if (1 < iy0) T[i0 - nx] = __fdiv_rn(dy, S[i0 - nx]);
+            if (iy0 < ny) T[i0 + nx] = __fdiv_rn(dy, S[i0 + nx]);
+            auto push = [&](int i) {   // heap.f90:70-93
+                H.n = H.n + 1;
+                EikItem it; it.key = T[i]; it.idx = i;
+                H.put(H.n, it);
+                H.upheap(H.n);
+            };
+            if (1 < ix0) push(i0 - 1);
+            if (ix0 < nx) push(i0 + 1);
+            if (1 < iy0) push(i0 - nx);
+            if (iy0 < ny) push(i0 + nx);
+        }
+    }
+    if (nx == 1 && ny == 1) return;
+    __syncwarp();
+    int nalive = 1;
+    int hn = __shfl_sync(0xffffffffu, H.n, 0);
+    while (nalive <= nn) {
+        if (hn == 0) break;
+        // ---- popheap heap.f90:95-124 (lane 0) ------------------------------------------------------------------
+        int imin = 0;
+        H.w0 = H.w1 = H.w2 = H.w3 = 0;
+        if (lane == 0) {
+            const EikItem top = H.get(1), last = H.get(H.n);
+            imin = top.idx;
+            H.n = H.n - 1;
+            if (H.n >= 1) { H.put(1, last); H.downheap(1); }
+            bp[imin] = ALIVE;
+        }
+        __syncwarp();
+        imin = __shfl_sync(0xffffffffu, imin, 0);
+        nalive = nalive + 1;
+        const int iy = (imin - 1) / nx + 1, ix = imin - (iy - 1) * nx;
+        // ---- the four neighbour stencils, lanes 0..3: left, right, down, up (eikonal.f90:134-190) -----------------------
+        int i = 0, state = ALIVE;      // state: ALIVE (skip), FARAWAY, or > 0 (in the heap)
+        float t = 0.f, told = 0.f;
+        if (lane < 4) {
+            const bool valid = lane == 0 ? 1 < ix : (lane == 1 ? ix < nx : (lane == 2 ? 1 < iy : iy < ny));
+            if (valid) {
+                i = lane == 0 ? imin - 1 : (lane == 1 ? imin + 1 : (lane == 2 ? imin - nx : imin + nx));
+                const int jx = lane == 0 ? ix - 1 : (lane == 1 ? ix + 1 : ix), jy = lane == 2 ? iy - 1 : (lane == 3 ? iy + 1 : iy);
+                // (all loads are issued before the state is looked at: one round trip)
+                float a = infinity, b = infinity, c = infinity, d = infinity;
+                state = bp[i];
+                told = T[i];
+                const float sp = S[i];
+                if (1 < jx) a = T[i - 1];
+                if (jx < nx) b = T[i + 1];
+                if (1 < jy) c = T[i - nx];
+                if (jy < ny) d = T[i + nx];
+                if (state != ALIVE) {
+                    const float aa = fminf(a, b), cc = fminf(c, d);
+                    if (fmaxf(aa, cc) != infinity) {
+                        const float q = __fmul_rn(__fsub_rn(aa, cc), sp);
+                        const float s = __fmul_rn(dx2dy2, __fsub_rn(dx2pdy2, __fmul_rn(q, q)));
+                        if (s >= 0.f)
+                            t = fmaxf(t, __fdiv_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(aa, dy2), __fmul_rn(cc, dx2)), sp), __fsqrt_rn(s)), __fmul_rn(sp, dx2pdy2)));
+                    }
+                    if (cc == infinity) {
+                        if (a < infinity) t = fmaxf(t, __fadd_rn(a, __fdiv_rn(dx, sp)));
+                        if (b < infinity) t = fmaxf(t, __fadd_rn(b, __fdiv_rn(dx, sp)));
+                    }
+                    if (aa == infinity) {
+                        if (c < infinity) t = fmaxf(t, __fadd_rn(c, __fdiv_rn(dy, sp)));
+                        if (d < infinity) t = fmaxf(t, __fadd_rn(d, __fdiv_rn(dy, sp)));
+                    }
+                    if (t == 0.f) {   // fallback condition
+                        t = infinity;
+                        if (a < infinity) t = fminf(t, __fadd_rn(a, __fdiv_rn(dx, sp)));
+                        if (b < infinity) t = fminf(t, __fadd_rn(b, __fdiv_rn(dx, sp)));
+                        if (c < infinity) t = fminf(t, __fadd_rn(c, __fdiv_rn(dy, sp)));
+                        if (d < infinity) t = fminf(t, __fadd_rn(d, __fdiv_rn(dy, sp)));
+                    }
+                }
+            }
+        }
+        // ---- their heap updates in the reference's order (lane 0) ----------------------------------------------------------
+        {   // the neighbours' heap positions as the stencil lanes read them; put() keeps them current from here on
+            const int i_0 = __shfl_sync(0xffffffffu, i, 0), i_1 = __shfl_sync(0xffffffffu, i, 1), i_2 = __shfl_sync(0xffffffffu, i, 2), i_3 = __shfl_sync(0xffffffffu, i, 3);
+            const int s_0 = __shfl_sync(0xffffffffu, state, 0), s_1 = __shfl_sync(0xffffffffu, state, 1), s_2 = __shfl_sync(0xffffffffu, state, 2), s_3 = __shfl_sync(0xffffffffu, state, 3);
+            H.w0 = i_0; H.w1 = i_1; H.w2 = i_2; H.w3 = i_3; H.p0 = s_0; H.p1 = s_1; H.p2 = s_2; H.p3 = s_3;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int ik = __shfl_sync(0xffffffffu, i, k), sk = __shfl_sync(0xffffffffu, state, k);
+            const float tk = __shfl_sync(0xffffffffu, t, k), toldk = __shfl_sync(0xffffffffu, told, k);
+            if (lane == 0 && sk != ALIVE && ik != 0) {
+                if (sk == FARAWAY) {   // pushheap with the node's current (infinite) time
+                    H.n = H.n + 1;
+                    EikItem it; it.key = toldk; it.idx = ik;
+                    H.put(H.n, it);
+                    H.upheap(H.n);
+                }
+                if (tk != 0.f && toldk != tk) {   // updateheap heap.f90:126-150
+                    T[ik] = tk;
+                    const int pos = k == 0 ? H.p0 : (k == 1 ? H.p1 : (k == 2 ? H.p2 : H.p3));
+                    H.setkey(pos, tk);
+                    if (tk < toldk) H.upheap(pos);
+                    if (tk > toldk) H.downheap(k == 0 ? H.p0 : (k == 1 ? H.p1 : (k == 2 ? H.p2 : H.p3)));
+                }
+            }
+        }
+        __syncwarp();
+        hn = __shfl_sync(0xffffffffu, H.n, 0);
+    }
+}
+
+int eikonal_heap_smem_entries() { return EIK_HCAP; }
+cudaError_t launch_eikonal_fmm(const EikJob* d_jobs, int njobs, cudaStream_t st) {
+    if (njobs <= 0) return cudaSuccess;
+    cudaFuncSetAttribute(k_eikonal_fmm, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    k_eikonal_fmm<<<njobs, 32, 0, st>>>(d_jobs, njobs);
+    return cudaGetLastError();
+}
+void eikonal_start_node(const float origin[2], const float delta[2], const float initialpoint[2], int nx, int ny, int* ix0, int* iy0) {   // eikonal.f90:60-67
+    int ix = (int)((initialpoint[0] - origin[0]) / delta[0]) + 1, iy = (int)((initialpoint[1] - origin[1]) / delta[1]) + 1;
+    if (ix < 1) ix = 1;
+    if (nx < ix) ix = nx;
+    if (iy < 1) iy = 1;
+    if (ny < iy) iy = ny;
+    *ix0 = ix; *iy0 = iy;
+}
+
+// Batch entry point for tests and measurements: njobs grids (host arrays), solved concurrently on the device.
+// speed[j] / times[j]: host (nx[j] x ny[j]), ix fastest.  Returns the kernel time in *kernel_ms.
+extern "C" int kiwi_eikonal_fmm_device(int njobs, const int* nx, const int* ny, const float* const* speed, const float* origin2,
+                                       const float* delta2, const float* initialpoint2, float* const* times, float* kernel_ms) {
+    if (njobs <= 0) return 0;
+    std::vector<EikJob> jobs(njobs);
+    std::vector<void*> allocs;
+    auto fail = [&](const char* what) { for (void* p : allocs) cudaFree(p); fprintf(stderr, "kiwi_eikonal_fmm_device: %s\n", what); return 1; };
+    for (int j = 0; j < njobs; j++) {
+        const size_t nn = (size_t)nx[j] * ny[j];
+        if (nx[j] < 1 || ny[j] < 1) return fail("invalid grid");
+        float *dS = nullptr, *dT = nullptr; int* dbp = nullptr; EikItem* dovf = nullptr;
+        if (cudaMalloc(&dS, nn * 4) != cudaSuccess || cudaMalloc(&dT, nn * 4) != cudaSuccess || cudaMalloc(&dbp, nn * 4) != cudaSuccess) return fail("out of device memory");
+        allocs.push_back(dS); allocs.push_back(dT); allocs.push_back(dbp);
+        if (nn > EIK_HCAP) { if (cudaMalloc(&dovf, (nn - EIK_HCAP + 1) * sizeof(EikItem)) != cudaSuccess) return fail("out of device memory"); allocs.push_back(dovf); }
+        cudaMemcpy(dS, speed[j], nn * 4, cudaMemcpyHostToDevice);
+        EikJob& J = jobs[j];
+        J.nx = nx[j]; J.ny = ny[j]; J.dx = delta2[2 * j]; J.dy = delta2[2 * j + 1];
+        eikonal_start_node(origin2 + 2 * j, delta2 + 2 * j, initialpoint2 + 2 * j, J.nx, J.ny, &J.ix0, &J.iy0);
+        J.S = dS; J.T = dT; J.bp = dbp; J.ovf = dovf;
+    }
+    EikJob* djobs = nullptr;
+    if (cudaMalloc(&djobs, sizeof(EikJob) * njobs) != cudaSuccess) return fail("out of device memory");
+    allocs.push_back(djobs);
+    cudaMemcpy(djobs, jobs.data(), sizeof(EikJob) * njobs, cudaMemcpyHostToDevice);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    launch_eikonal_fmm(djobs, njobs, 0);
+    cudaEventRecord(e1);
+    cudaError_t err = cudaDeviceSynchronize();
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (kernel_ms) *kernel_ms = ms;
+    if (err != cudaSuccess) return fail(cudaGetErrorString(err));
+    for (int j = 0; j < njobs; j++) cudaMemcpy(times[j], jobs[j].T, (size_t)nx[j] * ny[j] * 4, cudaMemcpyDeviceToHost);
+    for (void* p : allocs) cudaFree(p);
+    return 0;
+}

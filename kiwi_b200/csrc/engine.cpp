@@ -122,6 +122,11 @@ struct kiwi_ctx {
     float thickness_limit = 0.f;
     std::string prep_error;                  // message of the last failed discretisation
     bool mt_grid_enabled = true;             // point moment-tensor grid searches go through the tcgen05 contraction
+    // batches of eikonal sources from this size on run their fast-marching solves on the device (0 = never, the default: measured at
+    // config C4 with 1024 distinct candidates on a 16-core host, the device path -- speed fields up, one wave of solves, times down,
+    // the two host parts of the discretiser around it -- does 184 evaluations/s against 211 with every solve on a host thread; a
+    // wave takes ~2.4 s whatever its size because its largest grid sets it)
+    int eikonal_device_min = getenv("KIWI_EIKONAL_DEVICE_MIN") ? atoi(getenv("KIWI_EIKONAL_DEVICE_MIN")) : 0;
     bool mt_grid_fused = true;               // ... with the synthesis fused into it where the windows fit (k_mt_fused)
     DevBuf d_map, d_status_out;
     DevBuf d_taprec;              // shift table of the current batch (k_tap_table)
@@ -133,6 +138,7 @@ struct kiwi_ctx {
     DevBuf d_gm;                  // ground-motion values [cand][rcv][3]
     DevBuf d_xcorr;               // cross-correlations [rcv][component][shift] (autoshift_ref_seismogram)
     bool dedup_enabled = true;               // candidates that differ only in the moment share one synthesis
+    DevBuf d_eik_s, d_eik_t, d_eik_bp, d_eik_ovf, d_eik_jobs;   // fast-marching solves of a wave of eikonal candidates
     DevBuf d_mtlocs, d_mts, d_candof, d_orc, d_orw, d_obw, d_oout, d_obest, d_obestv;
     int last_eval_ns = 0;                    // candidates whose misfit block sits in d_out (kiwi_eval_sources)
     // description of the last chunk evaluated (inspection entry points, accounting)
@@ -259,6 +265,22 @@ bool all_refs_set(const kiwi_ctx* c) {
     return true;
 }
 
+void eikonal_to_prep(const kh::EikonalPrep& e, kh::SourcePrep* sp) {
+    kh::SourcePrep& o = *sp;
+    o = kh::SourcePrep();
+    o.explicit_groups = true;
+    o.nx = e.nx; o.ny = e.ny; o.ngroups = (int)e.groups.size();
+    o.moment = e.moment; o.risetime = e.risetime;
+    memcpy(o.mhat, e.mhat, sizeof o.mhat);
+    o.toff = e.tap_time; o.wt = e.tap_wt;
+    o.nt = 0;
+    for (const kh::EikonalGroup& g : e.groups) {
+        o.g_north.push_back(g.north); o.g_east.push_back(g.east); o.g_depth.push_back(g.depth); o.g_gw.push_back(g.gw);
+        o.g_tap_begin.push_back(g.tap_begin); o.g_tap_count.push_back(g.tap_count); o.g_tbase.push_back(0.f);
+        o.nt = std::max(o.nt, g.tap_count);
+    }
+}
+
 int prep_candidate(kiwi_ctx* c, int sourcetype, const float* p, float effective_dt, kh::SourcePrep* sp, std::string* err) {
     if (sourcetype == KIWI_SOURCE_BILATERAL) return kh::prep_bilateral(p, effective_dt, sp) ? 0 : 1;
     if (sourcetype == KIWI_SOURCE_MOMENT_TENSOR) return kh::prep_moment_tensor(p, effective_dt, sp) ? 0 : 1;
@@ -270,22 +292,83 @@ int prep_candidate(kiwi_ctx* c, int sourcetype, const float* p, float effective_
             if (err) *err = e.err;
             return 1;
         }
-        kh::SourcePrep& o = *sp;
-        o = kh::SourcePrep();
-        o.explicit_groups = true;
-        o.nx = e.nx; o.ny = e.ny; o.ngroups = (int)e.groups.size();
-        o.moment = e.moment; o.risetime = e.risetime;
-        memcpy(o.mhat, e.mhat, sizeof o.mhat);
-        o.toff = e.tap_time; o.wt = e.tap_wt;
-        o.nt = 0;
-        for (const kh::EikonalGroup& g : e.groups) {
-            o.g_north.push_back(g.north); o.g_east.push_back(g.east); o.g_depth.push_back(g.depth); o.g_gw.push_back(g.gw);
-            o.g_tap_begin.push_back(g.tap_begin); o.g_tap_count.push_back(g.tap_count); o.g_tbase.push_back(0.f);
-            o.nt = std::max(o.nt, g.tap_count);
-        }
+        eikonal_to_prep(e, sp);
         return 0;
     }
     return 1;
+}
+
+// Eikonal sources of a large batch, optionally (kiwi_set_eikonal_device): the fast-marching solves (70 % of the host discretiser,
+// sequential by construction) run on the device, one warp per candidate (csrc/eikonal.cu: the host solver's results bit for bit),
+// between the two host parts of the discretiser, which are spread over the host cores.  One solve is ~25 x slower on the device than
+// on a host core (2.5 us against 0.1 us per node) but up to 1924 of them run side by side.
+int prep_eikonal_batch_device(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* params, std::vector<kh::SourcePrep>& prep,
+                              std::vector<int>& bad, std::vector<std::string>& errs) {
+    const bool mt = sourcetype == KIWI_SOURCE_MT_EIKONAL;
+    std::vector<kh::EikonalWork> works(n);
+    std::vector<kh::EikonalPrep> eps(n);
+    const int nthreads = (int)std::min<size_t>((size_t)n, std::max(1u, std::thread::hardware_concurrency()));
+    auto parallel_for = [&](const std::function<void(int)>& body) {
+        std::atomic<int> next(0);
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; t++) pool.emplace_back([&]() { for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) body(i); });
+        for (std::thread& t : pool) t.join();
+    };
+    parallel_for([&](int i) {
+        bad[i] = kh::prep_eikonal_begin(params + (size_t)i * nparams, mt, c->effective_dt, c->olat, c->olon, c->crust, c->constraints, &works[i], &eps[i]) ? 0 : 1;
+        if (bad[i]) errs[i] = eps[i].err;
+    });
+    // waves of solves: at most `wave_jobs` at a time (all resident at once) and `wave_nodes` nodes of device arrays (20 bytes per node)
+    std::vector<int> order;
+    for (int i = 0; i < n; i++) if (!bad[i]) order.push_back(i);
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return works[a].speed.size() > works[b].speed.size(); });   // long solves first
+    size_t fr = 0, tot = 0;
+    CU_OK(cudaMemGetInfo(&fr, &tot));
+    const size_t wave_nodes = std::max<size_t>((size_t)1 << 22, std::min<size_t>(fr / 3, (size_t)24 << 30) / 20);
+    const int wave_jobs = 148 * 13;
+    const int hcap = eikonal_heap_smem_entries();
+    size_t at = 0;
+    while (at < order.size()) {
+        size_t nodes = 0, end = at;
+        while (end < order.size() && (int)(end - at) < wave_jobs && (end == at || nodes + works[order[end]].speed.size() <= wave_nodes)) nodes += works[order[end++]].speed.size();
+        const int nj = (int)(end - at);
+        CU_OK(c->d_eik_s.ensure(nodes * 4)); CU_OK(c->d_eik_t.ensure(nodes * 4)); CU_OK(c->d_eik_bp.ensure(nodes * 4));
+        CU_OK(c->d_eik_ovf.ensure(nodes * sizeof(EikItem))); CU_OK(c->d_eik_jobs.ensure(sizeof(EikJob) * nj));
+        std::vector<EikJob> jobs(nj);
+        size_t off = 0;
+        for (int j = 0; j < nj; j++) {
+            kh::EikonalWork& w = works[order[at + j]];
+            const size_t nn = w.speed.size();
+            EikJob& J = jobs[j];
+            J.nx = w.fnx; J.ny = w.fny; J.dx = w.delta[0]; J.dy = w.delta[1];
+            eikonal_start_node(w.first, w.delta, w.initialpoint, w.fnx, w.fny, &J.ix0, &J.iy0);
+            J.S = c->d_eik_s.as<float>() + off; J.T = c->d_eik_t.as<float>() + off; J.bp = c->d_eik_bp.as<int>() + off;
+            J.ovf = nn > (size_t)hcap ? c->d_eik_ovf.as<EikItem>() + off : nullptr;
+            CU_OK(cudaMemcpyAsync(c->d_eik_s.as<float>() + off, w.speed.data(), nn * 4, cudaMemcpyHostToDevice, c->stream));
+            off += nn;
+        }
+        CU_OK(cudaMemcpyAsync(c->d_eik_jobs.p, jobs.data(), sizeof(EikJob) * nj, cudaMemcpyHostToDevice, c->stream));
+        cudaError_t e = launch_eikonal_fmm(c->d_eik_jobs.as<EikJob>(), nj, c->stream);
+        if (e != cudaSuccess) return kiwi_set_error("CUDA error launching the fast-marching solver: %s", cudaGetErrorString(e));
+        c->launches[0] += 1;
+        off = 0;
+        for (int j = 0; j < nj; j++) {
+            kh::EikonalWork& w = works[order[at + j]];
+            w.times.resize(w.speed.size());
+            CU_OK(cudaMemcpyAsync(w.times.data(), c->d_eik_t.as<float>() + off, w.speed.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+            off += w.speed.size();
+        }
+        CU_OK(cudaStreamSynchronize(c->stream));
+        CU_OK(cudaGetLastError());
+        at = end;
+    }
+    parallel_for([&](int i) {
+        if (bad[i]) return;
+        if (!kh::prep_eikonal_finish(&works[i], &eps[i])) { bad[i] = 1; errs[i] = eps[i].err; }
+        else eikonal_to_prep(eps[i], &prep[i]);
+        works[i] = kh::EikonalWork();   // (the fine grids are 20 bytes per node: released as soon as they are done with)
+    });
+    return 0;
 }
 
 // Depth bands of k_synth.  A launch over all groups of its candidates gathers from the whole depth range of the sources: for a
@@ -548,7 +631,11 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         };
         const bool heavy = sourcetype == KIWI_SOURCE_EIKONAL || sourcetype == KIWI_SOURCE_MT_EIKONAL;
         const int nthreads = heavy ? (int)std::min<size_t>((size_t)n, std::max(1u, std::thread::hardware_concurrency())) : 1;
-        if (nthreads > 1) {
+        const int device_min = c->eikonal_device_min;
+        if (heavy && device_min > 0 && n >= device_min) {
+            if (prep_eikonal_batch_device(c, sourcetype, n, nparams, params, prep, bad, errs)) return 1;
+            for (int i = 0; i < n; i++) if (bad[i]) prep[i] = kh::SourcePrep();
+        } else if (nthreads > 1) {
             std::atomic<int> next(0);
             std::vector<std::thread> pool;
             for (int t = 0; t < nthreads; t++)
@@ -1066,7 +1153,7 @@ void kiwi_destroy(kiwi_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->d_slabs, &c->d_nodes, &c->d_tspan, &c->d_nspan, &c->d_rcv, &c->d_refdata, &c->d_taper, &c->d_cands, &c->d_bilat, &c->d_gf, &c->d_gi,
-                      &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift, &c->d_map, &c->d_status_out, &c->d_taprec, &c->d_partial, &c->d_fftz, &c->d_gm, &c->d_xcorr, &c->d_mtlocs, &c->d_mts, &c->d_candof, &c->d_orc, &c->d_orw, &c->d_obw, &c->d_oout, &c->d_obest, &c->d_obestv})
+                      &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift, &c->d_map, &c->d_status_out, &c->d_taprec, &c->d_partial, &c->d_fftz, &c->d_gm, &c->d_xcorr, &c->d_eik_s, &c->d_eik_t, &c->d_eik_bp, &c->d_eik_ovf, &c->d_eik_jobs, &c->d_mtlocs, &c->d_mts, &c->d_candof, &c->d_orc, &c->d_orw, &c->d_obw, &c->d_oout, &c->d_obest, &c->d_obestv})
         b->release();
     c->h_stage.release(); c->h_out.release(); c->h_mt.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -1311,6 +1398,12 @@ int kiwi_set_source_crustal_thickness_limit(kiwi_ctx* c, float limit) {   // par
 int kiwi_set_share_syntheses(kiwi_ctx* c, int enabled) {
     if (!c) return kiwi_set_error("null context");
     c->dedup_enabled = enabled != 0;
+    return 0;
+}
+
+int kiwi_set_eikonal_device(kiwi_ctx* c, int min_batch) {
+    if (!c) return kiwi_set_error("null context");
+    c->eikonal_device_min = min_batch < 0 ? 0 : min_batch;
     return 0;
 }
 

@@ -62,6 +62,20 @@ void eikonal_solver_fmm(const float* speed, int nx, int ny, const float origin[2
                         float* times);
 bool prep_eikonal(const float* params, bool mt_variant, float shortest_doi, double olat_rad, double olon_rad, const Crust2x2& crust,
                   const std::vector<Halfspace>& constraints, EikonalPrep* out);
+// the same in three steps (begin: geometry and speed field of the fine grid; the fast-marching solve, on the host or -- for large batches --
+// on the device between the two; finish: down-sampling and the sub-source table).  `params` must stay valid until finish.
+struct EikonalWork {
+    const float* p = nullptr; float rot_rup[9] = {0}, rot_slip[9] = {0}; int idx[6] = {0};
+    bool mt_variant = false; float shortest_doi = 0.f;
+    float first[2] = {0, 0}, last[2] = {0, 0}, delta[2] = {0, 0}, initialpoint[2] = {0, 0};
+    int fnx = 0, fny = 0;
+    float minspeed = 0.f, invalid_speed = 0.f;
+    std::vector<float> speed, times, points;     // fine grid (fnx, fny), ix fastest; points: north, east, depth per node
+};
+bool prep_eikonal_begin(const float* params, bool mt_variant, float shortest_doi, double olat_rad, double olon_rad, const Crust2x2& crust,
+                        const std::vector<Halfspace>& constraints, EikonalWork* work, EikonalPrep* out);
+void prep_eikonal_solve_host(EikonalWork* work);
+bool prep_eikonal_finish(EikonalWork* work, EikonalPrep* out);
 
 bool prep_bilateral(const float* params14, float shortest_doi, SourcePrep* out);
 bool prep_moment_tensor(const float* params11, float shortest_doi, SourcePrep* out);

@@ -55,3 +55,19 @@ void launch_mt_contract(const ReceiverDev* rcv, int nrcv, const MtLoc* locs, int
 void launch_flag_nonfinite(const float* v, int nrows, int ncols, int* flag, int* count /* may be null */, cudaStream_t st);
 cudaError_t launch_outer_misfits(const float* mis, int nm, const void* rc /* {misfit_base, ncomp}[nr] */, int nr, const double* rweights, int l1,
                                  int anarchy, int nrows, const double* bweights, double* out, int ns, int* best, double* bestv, cudaStream_t st);
+
+// ---- fast-marching solver of the eikonal sources on the device (eikonal.cu) ----------------------------------------------------------
+struct EikItem { float key; int idx; };
+// one solve: T, bp, S are 0-based device arrays of nx*ny (node i of the reference = element i-1)
+struct EikJob {
+    int nx, ny;
+    float dx, dy;
+    int ix0, iy0;           // 1-based start node (eikonal_start_node)
+    const float* S;
+    float* T;
+    int* bp;
+    EikItem* ovf;           // heap entries beyond eikonal_heap_smem_entries(): room for nx*ny - that many, or null if none are needed
+};
+int eikonal_heap_smem_entries();
+void eikonal_start_node(const float origin[2], const float delta[2], const float initialpoint[2], int nx, int ny, int* ix0, int* iy0);
+cudaError_t launch_eikonal_fmm(const EikJob* d_jobs, int njobs, cudaStream_t st);

@@ -358,10 +358,21 @@ void discretize_subfault_time(float duration_subfault, float risetime, float max
 }
 }  // namespace
 
-bool prep_eikonal(const float* p, bool mt_variant, float shortest_doi, double olat_rad, double olon_rad, const Crust2x2& crust,
-                  const std::vector<Halfspace>& constraints, EikonalPrep* out) {
+// The discretiser in three steps, so that the fast-marching solves of a large batch can run on the device (csrc/eikonal.cu) between the
+// two host parts: prep_eikonal_begin (geometry, speed field) -> times of the fine grid -> prep_eikonal_finish (down-sampling, table).
+static Psm psm_of(const EikonalWork& w) {
+    Psm s;
+    s.p = w.p; memcpy(s.rot_rup, w.rot_rup, sizeof s.rot_rup);
+    s.i_bsx = w.idx[0]; s.i_bsy = w.idx[1]; s.i_brad = w.idx[2]; s.i_nsx = w.idx[3]; s.i_nsy = w.idx[4]; s.i_relv = w.idx[5];
+    return s;
+}
+
+bool prep_eikonal_begin(const float* p, bool mt_variant, float shortest_doi, double olat_rad, double olon_rad, const Crust2x2& crust,
+                        const std::vector<Halfspace>& constraints, EikonalWork* work, EikonalPrep* out) {
     EikonalPrep& o = *out;
     o = EikonalPrep();
+    EikonalWork& w = *work;
+    w = EikonalWork();
     if (!crust.loaded) { o.err = "crust2x2 model not loaded"; return false; }
     Psm s;
     s.p = p;
@@ -372,7 +383,7 @@ bool prep_eikonal(const float* p, bool mt_variant, float shortest_doi, double ol
     for (int i = 0; i < (mt_variant ? 20 : 15); i++) if (!std::isfinite(p[i])) { o.err = "non-finite source parameter"; return false; }
     // psm_update_dep_params :233-257
     const float strike = d2r_r(p[5]), dip = d2r_r(p[6]);
-    float rot_slip[9];
+    float* rot_slip = w.rot_slip;
     init_euler(dip, strike, 0.f, s.rot_rup);
     if (!mt_variant) { const float rake = d2r_r(p[7]); init_euler(dip, strike, -rake, rot_slip); }
     const float bord_shift_x = p[s.i_bsx], bord_shift_y = p[s.i_bsy], bord_radius = p[s.i_brad];
@@ -418,7 +429,8 @@ bool prep_eikonal(const float* p, bool mt_variant, float shortest_doi, double ol
     if (nd[0] < 0 || nd[1] < 0 || (long long)nd[0] * nd[1] > 4000000LL) { o.err = "eikonal grid too large"; return false; }
     float delta[2] = {dims[0] / (float)nd[0], dims[1] / (float)nd[1]};
     const int fnx = nd[0], fny = nd[1];
-    std::vector<float> speed((size_t)fnx * fny), times((size_t)fnx * fny), points((size_t)3 * fnx * fny);
+    std::vector<float>&speed = w.speed, &points = w.points;
+    speed.assign((size_t)fnx * fny, 0.f); points.assign((size_t)3 * fnx * fny, 0.f);
     // crust2x2_get_profile(psm%origin): the origin is in RADIANS here (source_eikonal.f90:472), kept as is
     const CrustProfile profile = crust2x2_get_profile(crust, (float)olat_rad, (float)olon_rad);
     // psm_initial_point_intolerant_rc :401-432
@@ -454,7 +466,30 @@ bool prep_eikonal(const float* p, bool mt_variant, float shortest_doi, double ol
     const float invalid_speed = minspeed * 0.5f;
     for (float& v : speed) if (v == 0.f) v = invalid_speed;
     if (!(minspeed > 0.f) || minspeed == std::numeric_limits<float>::max()) { o.err = "no valid point in the rupture area"; return false; }
-    eikonal_solver_fmm(speed.data(), fnx, fny, first, delta, initialpoint, times.data());
+    w.p = p; memcpy(w.rot_rup, s.rot_rup, sizeof w.rot_rup);
+    w.idx[0] = s.i_bsx; w.idx[1] = s.i_bsy; w.idx[2] = s.i_brad; w.idx[3] = s.i_nsx; w.idx[4] = s.i_nsy; w.idx[5] = s.i_relv;
+    w.mt_variant = mt_variant; w.shortest_doi = shortest_doi;
+    for (int k = 0; k < 2; k++) { w.first[k] = first[k]; w.last[k] = last[k]; w.delta[k] = delta[k]; w.initialpoint[k] = initialpoint[k]; }
+    w.fnx = fnx; w.fny = fny; w.minspeed = minspeed; w.invalid_speed = invalid_speed;
+    return true;
+}
+
+void prep_eikonal_solve_host(EikonalWork* work) {
+    EikonalWork& w = *work;
+    w.times.assign(w.speed.size(), 0.f);
+    eikonal_solver_fmm(w.speed.data(), w.fnx, w.fny, w.first, w.delta, w.initialpoint, w.times.data());
+}
+
+bool prep_eikonal_finish(EikonalWork* work, EikonalPrep* out) {
+    EikonalPrep& o = *out;
+    EikonalWork& w = *work;
+    const Psm s = psm_of(w);
+    const float* p = w.p;
+    const bool mt_variant = w.mt_variant;
+    const float shortest_doi = w.shortest_doi, minspeed = w.minspeed, invalid_speed = w.invalid_speed;
+    const float* first = w.first; const float* last = w.last;
+    const float* rot_slip = w.rot_slip;
+    std::vector<float>&speed = w.speed, &times = w.times, &points = w.points;
     for (size_t c = 0; c < speed.size(); c++) if (speed[c] == invalid_speed) times[c] = -1.f;
     // ---- coarse grid size :274-277, 617-638 ------------------------------------------------------------------
     const float maxdt = shortest_doi;
@@ -550,6 +585,14 @@ bool prep_eikonal(const float* p, bool mt_variant, float shortest_doi, double ol
     o.nx = nxc; o.ny = nyc;
     if (o.groups.empty()) { o.err = "Empty rupture area"; return false; }
     return true;
+}
+
+bool prep_eikonal(const float* p, bool mt_variant, float shortest_doi, double olat_rad, double olon_rad, const Crust2x2& crust,
+                  const std::vector<Halfspace>& constraints, EikonalPrep* out) {
+    EikonalWork w;
+    if (!prep_eikonal_begin(p, mt_variant, shortest_doi, olat_rad, olon_rad, crust, constraints, &w, out)) return false;
+    prep_eikonal_solve_host(&w);
+    return prep_eikonal_finish(&w, out);
 }
 
 }  // namespace kh

@@ -269,6 +269,10 @@ class Engine:
         """tensor-core path for point moment-tensor grid searches on (default) / off; 2 = on, synthesis not fused into the contraction"""
         _check(lib.kiwi_set_mt_grid(self._h, 2 if (not isinstance(enabled, bool) and enabled == 2) else int(bool(enabled))))
 
+    def set_eikonal_device(self, min_batch):
+        """batches of at least min_batch eikonal sources run their fast-marching solves on the device (0 = never, the default)"""
+        _check(lib.kiwi_set_eikonal_device(self._h, int(min_batch)))
+
     def set_floating_shiftrange(self, lo, hi, ireceiver=0):
         _check(lib.kiwi_set_floating_shiftrange(self._h, ireceiver, lo, hi))
 
@@ -582,6 +586,19 @@ def eikonal_fmm(speed, origin, delta, initialpoint):
     o, d, p = _f32(origin), _f32(delta), _f32(initialpoint)
     _check(lib.kiwi_eikonal_fmm(nx, ny, _fp(sp), _fp(o), _fp(d), _fp(p), _fp(times)))
     return times
+
+
+def eikonal_fmm_device(speeds, origins, deltas, initialpoints):
+    """the same on the device, a batch of grids at a time (kiwi_eikonal_fmm_device): list of speed[ny][nx] -> (list of times, kernel ms)"""
+    sps = [np.ascontiguousarray(s, dtype=np.float32) for s in speeds]
+    n = len(sps)
+    nx = np.array([s.shape[1] for s in sps], dtype=np.int32); ny = np.array([s.shape[0] for s in sps], dtype=np.int32)
+    times = [np.zeros_like(s) for s in sps]
+    o, d, p = (np.ascontiguousarray(np.asarray(v, dtype=np.float32).reshape(n, 2)) for v in (origins, deltas, initialpoints))
+    sp_ptrs = (c_float_p * n)(*[_fp(s) for s in sps]); t_ptrs = (c_float_p * n)(*[_fp(t) for t in times])
+    ms = C.c_float(0)
+    _check(lib.kiwi_eikonal_fmm_device(n, nx.ctypes.data_as(c_int_p), ny.ctypes.data_as(c_int_p), sp_ptrs, _fp(o), _fp(d), _fp(p), t_ptrs, C.byref(ms)))
+    return times, float(ms.value)
 
 
 def lmdif_batched(fcn, x0, m, ftol=None, xtol=None, gtol=0.0, maxfev=None, epsfcn=0.0, diag=None, mode=1, factor=100.0):

@@ -32,7 +32,7 @@ def test_fortran_binding_covers_the_engine_facing_entry_points():
     src = open(os.path.join(ROOT, "fortran", "kiwi_b200_binding.f90")).read()
     bound = set(re.findall(r'name="(kiwi_[a-z0-9_]+)"', src))
     assert bound <= names, sorted(bound - names)
-    tools = {"kiwi_discretize_source", "kiwi_eikonal_fmm", "kiwi_eval_sources_device", "kiwi_get_indices", "kiwi_get_n_source_params", "kiwi_get_spans",
+    tools = {"kiwi_discretize_source", "kiwi_eikonal_fmm", "kiwi_eikonal_fmm_device", "kiwi_eval_sources_device", "kiwi_get_indices", "kiwi_get_n_source_params", "kiwi_get_spans",
              "kiwi_gfdb_build_ahfull", "kiwi_gfdb_meta", "kiwi_gfdb_view", "kiwi_gfdb_write", "kiwi_global_misfits", "kiwi_gulunay",
              "kiwi_h5_read_root_dataset", "kiwi_host_alloc", "kiwi_host_free", "kiwi_last_batch_bytes", "kiwi_last_timing", "kiwi_lmdif_batched",
              "kiwi_trace_span", "kiwi_version"}
