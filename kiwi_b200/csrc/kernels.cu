@@ -2027,7 +2027,7 @@ __global__ void __launch_bounds__(128, 4) k_mt_fused(GfdbDev db, const ReceiverD
                     row[0] = sF; row[1] = sF + (size_t)SF; row[2] = sF + 2 * (size_t)SF; row[3] = sF + 8 * (size_t)SF;
                     row[4] = sF + 3 * (size_t)SF; row[5] = sF + 4 * (size_t)SF;
                 }
-                if (!ng10) a7[3] = 0.f;                  // (no g9 / g10 in an eight-component database: their strips were not written)
+                if (!ng10) { a7[3] = 0.f; row[3] = row[0]; }   // (no g9 / g10 in an eight-component database: their strips were not written)
                 a7[6] = have ? -1.f : 0.f;
                 {   // A tile: [hi | hi | lo | lo]
                     float hi[7], lo[7];
