@@ -173,9 +173,10 @@ int kiwi_set_floating_shiftrange(kiwi_ctx* ctx, int ireceiver, float shift_lo, f
 int kiwi_set_mt_grid(kiwi_ctx* ctx, int enabled);
 
 /* Eikonal / mt_eikonal sources: the fast-marching solve of the rupture front (eikonal.f90:29-199), sequential by construction and 70 % of the
- * discretiser's time, runs per candidate on a host thread.  Batches of min_batch candidates or more can run their solves on the device
- * instead (one warp per candidate, bit-identical results, up to 1924 solves side by side; a wave takes ~2.5 s whatever its size, so this
- * is for batches of thousands of candidates on hosts with few cores).  Default 0 = always on the host. */
+ * discretiser's time, runs per candidate on a host thread or on the device (one warp per candidate, bit-identical results, up to 1924
+ * solves side by side, each ~25 x slower than on a host core; a wave lasts as long as its largest grid).  min_batch < 0 (default): the
+ * engine shares the solves of a batch between host threads and device where that is faster (the device takes the small grids while the
+ * host threads work through the large ones); 0: host threads only; k > 0: all solves of batches of k candidates or more on the device. */
 int kiwi_set_eikonal_device(kiwi_ctx* ctx, int min_batch);
 
 /* Candidates of one kiwi_eval_sources batch that differ only in the scalar moment (bilateral, eikonal,

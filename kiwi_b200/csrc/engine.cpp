@@ -122,11 +122,12 @@ struct kiwi_ctx {
     float thickness_limit = 0.f;
     std::string prep_error;                  // message of the last failed discretisation
     bool mt_grid_enabled = true;             // point moment-tensor grid searches go through the tcgen05 contraction
-    // batches of eikonal sources from this size on run their fast-marching solves on the device (0 = never, the default: measured at
-    // config C4 with 1024 distinct candidates on a 16-core host, the device path -- speed fields up, one wave of solves, times down,
-    // the two host parts of the discretiser around it -- does 184 evaluations/s against 211 with every solve on a host thread; a
-    // wave takes ~2.4 s whatever its size because its largest grid sets it)
-    int eikonal_device_min = getenv("KIWI_EIKONAL_DEVICE_MIN") ? atoi(getenv("KIWI_EIKONAL_DEVICE_MIN")) : 0;
+    // where the fast-marching solves of a batch of eikonal sources run: -1 (default) = shared between the host threads and the device
+    // (prep_eikonal_batch_device), 0 = host threads only, k > 0 = all on the device for batches of k candidates or more.  All on the
+    // device loses to 16 host threads (C4, 1024 distinct candidates: 184 against 211 evaluations/s: a wave lasts as long as its largest
+    // grid, 2.4 s); sharing gives the device the small grids while the host threads work through the large ones.
+    int eikonal_device_min = getenv("KIWI_EIKONAL_DEVICE_MIN") ? atoi(getenv("KIWI_EIKONAL_DEVICE_MIN")) : -1;
+    int eikonal_last_device_solves = 0;      // solves of the last batch that ran on the device
     bool mt_grid_fused = true;               // ... with the synthesis fused into it where the windows fit (k_mt_fused)
     DevBuf d_map, d_status_out;
     DevBuf d_taprec;              // shift table of the current batch (k_tap_table)
@@ -302,42 +303,80 @@ int prep_candidate(kiwi_ctx* c, int sourcetype, const float* p, float effective_
 // sequential by construction) run on the device, one warp per candidate (csrc/eikonal.cu: the host solver's results bit for bit),
 // between the two host parts of the discretiser, which are spread over the host cores.  One solve is ~25 x slower on the device than
 // on a host core (2.5 us against 0.1 us per node) but up to 1924 of them run side by side.
+// `share`: true = the engine decides which solves go to the device (the small grids, as long as their wave ends before the host threads
+// are through with the large ones -- they run at the same time); false = all of them.
 int prep_eikonal_batch_device(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* params, std::vector<kh::SourcePrep>& prep,
-                              std::vector<int>& bad, std::vector<std::string>& errs) {
+                              std::vector<int>& bad, std::vector<std::string>& errs, bool share) {
     const bool mt = sourcetype == KIWI_SOURCE_MT_EIKONAL;
     std::vector<kh::EikonalWork> works(n);
     std::vector<kh::EikonalPrep> eps(n);
-    const int nthreads = (int)std::min<size_t>((size_t)n, std::max(1u, std::thread::hardware_concurrency()));
-    auto parallel_for = [&](const std::function<void(int)>& body) {
-        std::atomic<int> next(0);
+    const int ncores = (int)std::max(1u, std::thread::hardware_concurrency());
+    const int nthreads = std::min(n, ncores);
+    auto parallel_over = [&](const std::vector<int>& items, const std::function<void(int)>& body) {
+        std::atomic<size_t> next(0);
         std::vector<std::thread> pool;
-        for (int t = 0; t < nthreads; t++) pool.emplace_back([&]() { for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) body(i); });
+        const int nt = (int)std::min<size_t>(items.size(), (size_t)nthreads);
+        for (int t = 0; t < nt; t++) pool.emplace_back([&]() { for (size_t k = next.fetch_add(1); k < items.size(); k = next.fetch_add(1)) body(items[k]); });
         for (std::thread& t : pool) t.join();
     };
-    parallel_for([&](int i) {
+    std::vector<int> all(n);
+    for (int i = 0; i < n; i++) all[i] = i;
+    parallel_over(all, [&](int i) {
         bad[i] = kh::prep_eikonal_begin(params + (size_t)i * nparams, mt, c->effective_dt, c->olat, c->olon, c->crust, c->constraints, &works[i], &eps[i]) ? 0 : 1;
         if (bad[i]) errs[i] = eps[i].err;
     });
-    // waves of solves: at most `wave_jobs` at a time (all resident at once) and `wave_nodes` nodes of device arrays (20 bytes per node)
-    std::vector<int> order;
+    std::vector<int> order;      // valid candidates, small grids first
     for (int i = 0; i < n; i++) if (!bad[i]) order.push_back(i);
-    std::sort(order.begin(), order.end(), [&](int a, int b) { return works[a].speed.size() > works[b].speed.size(); });   // long solves first
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return works[a].speed.size() < works[b].speed.size(); });
     size_t fr = 0, tot = 0;
     CU_OK(cudaMemGetInfo(&fr, &tot));
-    const size_t wave_nodes = std::max<size_t>((size_t)1 << 22, std::min<size_t>(fr / 3, (size_t)24 << 30) / 20);
-    const int wave_jobs = 148 * 13;
+    const size_t wave_nodes = std::max<size_t>((size_t)1 << 22, std::min<size_t>(fr / 3, (size_t)24 << 30) / 20);   // 20 bytes per node on the device
+    const int wave_jobs = 148 * 13;                                                                                  // solves resident at a time
+    // ---- which solves go to the device -----------------------------------------------------------------------------
+    // measured rates (profiles/r02_eikonal_device.txt): a warp 2.6 us per node whatever else runs, a host core 0.1 us per node for the solve
+    // and 0.045 us for the down-sampling that follows; staging ~8 bytes per node at ~8 GB/s.  The device takes a prefix of the
+    // size-ordered list: its wave lasts as long as its largest grid.
+    size_t ndev = order.size();
+    if (share) {
+        const double dev_node = 2.6e-6, host_solve = 1.0e-7, host_finish = 0.45e-7, stage = 1.0e-9;
+        double all_solve = 0., all_finish = 0.;
+        for (int i : order) { all_solve += host_solve * works[i].speed.size(); all_finish += host_finish * works[i].speed.size(); }
+        double best = (all_solve + all_finish) / ncores, dev_solve = 0., dev_finish = 0., nodes = 0.;
+        ndev = 0;
+        for (size_t k = 0; k < order.size() && (int)k < wave_jobs; k++) {
+            const double nn = (double)works[order[k]].speed.size();
+            nodes += nn;
+            if (nodes > (double)wave_nodes) break;
+            dev_solve += host_solve * nn; dev_finish += host_finish * nn;
+            const double t_dev = dev_node * nn + stage * nodes;                                  // (nn = the largest grid so far)
+            const double t_host = (all_solve - dev_solve + all_finish - dev_finish) / ncores;   // the rest, solved and finished on the host meanwhile
+            const double total = std::max(t_dev, t_host) + dev_finish / ncores;
+            if (total < 0.97 * best) { best = total; ndev = k + 1; }
+        }
+    }
     const int hcap = eikonal_heap_smem_entries();
+    std::vector<int> host_items(order.begin() + ndev, order.end());
+    std::reverse(host_items.begin(), host_items.end());      // long solves first
+    auto host_part = [&]() {
+        parallel_over(host_items, [&](int i) {
+            kh::prep_eikonal_solve_host(&works[i]);
+            if (!kh::prep_eikonal_finish(&works[i], &eps[i])) { bad[i] = 1; errs[i] = eps[i].err; }
+            else eikonal_to_prep(eps[i], &prep[i]);
+            works[i] = kh::EikonalWork();   // (the fine grids are 20 bytes per node: released as soon as they are done with)
+        });
+    };
+    bool host_done = false;
     size_t at = 0;
-    while (at < order.size()) {
+    while (at < ndev) {
         size_t nodes = 0, end = at;
-        while (end < order.size() && (int)(end - at) < wave_jobs && (end == at || nodes + works[order[end]].speed.size() <= wave_nodes)) nodes += works[order[end++]].speed.size();
+        while (end < ndev && (int)(end - at) < wave_jobs && (end == at || nodes + works[order[end]].speed.size() <= wave_nodes)) nodes += works[order[end++]].speed.size();
         const int nj = (int)(end - at);
         CU_OK(c->d_eik_s.ensure(nodes * 4)); CU_OK(c->d_eik_t.ensure(nodes * 4)); CU_OK(c->d_eik_bp.ensure(nodes * 4));
         CU_OK(c->d_eik_ovf.ensure(nodes * sizeof(EikItem))); CU_OK(c->d_eik_jobs.ensure(sizeof(EikJob) * nj));
         std::vector<EikJob> jobs(nj);
         size_t off = 0;
-        for (int j = 0; j < nj; j++) {
-            kh::EikonalWork& w = works[order[at + j]];
+        for (int j = 0; j < nj; j++) {    // (largest grid of the wave first: it sets the wave's length)
+            kh::EikonalWork& w = works[order[end - 1 - j]];
             const size_t nn = w.speed.size();
             EikJob& J = jobs[j];
             J.nx = w.fnx; J.ny = w.fny; J.dx = w.delta[0]; J.dy = w.delta[1];
@@ -348,12 +387,14 @@ int prep_eikonal_batch_device(kiwi_ctx* c, int sourcetype, int n, int nparams, c
             off += nn;
         }
         CU_OK(cudaMemcpyAsync(c->d_eik_jobs.p, jobs.data(), sizeof(EikJob) * nj, cudaMemcpyHostToDevice, c->stream));
+        CU_OK(cudaStreamSynchronize(c->stream));   // (jobs is a stack-lifetime staging vector)
         cudaError_t e = launch_eikonal_fmm(c->d_eik_jobs.as<EikJob>(), nj, c->stream);
         if (e != cudaSuccess) return kiwi_set_error("CUDA error launching the fast-marching solver: %s", cudaGetErrorString(e));
         c->launches[0] += 1;
+        if (!host_done) { host_part(); host_done = true; }   // the host threads work through their share while the wave runs
         off = 0;
         for (int j = 0; j < nj; j++) {
-            kh::EikonalWork& w = works[order[at + j]];
+            kh::EikonalWork& w = works[order[end - 1 - j]];
             w.times.resize(w.speed.size());
             CU_OK(cudaMemcpyAsync(w.times.data(), c->d_eik_t.as<float>() + off, w.speed.size() * 4, cudaMemcpyDeviceToHost, c->stream));
             off += w.speed.size();
@@ -362,12 +403,15 @@ int prep_eikonal_batch_device(kiwi_ctx* c, int sourcetype, int n, int nparams, c
         CU_OK(cudaGetLastError());
         at = end;
     }
-    parallel_for([&](int i) {
-        if (bad[i]) return;
+    if (!host_done) host_part();
+    std::vector<int> dev_items(order.begin(), order.begin() + ndev);
+    std::reverse(dev_items.begin(), dev_items.end());
+    parallel_over(dev_items, [&](int i) {
         if (!kh::prep_eikonal_finish(&works[i], &eps[i])) { bad[i] = 1; errs[i] = eps[i].err; }
         else eikonal_to_prep(eps[i], &prep[i]);
-        works[i] = kh::EikonalWork();   // (the fine grids are 20 bytes per node: released as soon as they are done with)
+        works[i] = kh::EikonalWork();
     });
+    c->eikonal_last_device_solves = (int)ndev;
     return 0;
 }
 
@@ -631,9 +675,12 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         };
         const bool heavy = sourcetype == KIWI_SOURCE_EIKONAL || sourcetype == KIWI_SOURCE_MT_EIKONAL;
         const int nthreads = heavy ? (int)std::min<size_t>((size_t)n, std::max(1u, std::thread::hardware_concurrency())) : 1;
+        // eikonal_device_min: k > 0 = batches of k candidates or more solve on the device, all of them; -1 = the engine shares the solves
+        // of a batch between the host threads and the device where that is faster (the default); 0 = host only
         const int device_min = c->eikonal_device_min;
-        if (heavy && device_min > 0 && n >= device_min) {
-            if (prep_eikonal_batch_device(c, sourcetype, n, nparams, params, prep, bad, errs)) return 1;
+        c->eikonal_last_device_solves = 0;
+        if (heavy && ((device_min > 0 && n >= device_min) || (device_min < 0 && n >= 2 * nthreads))) {
+            if (prep_eikonal_batch_device(c, sourcetype, n, nparams, params, prep, bad, errs, device_min < 0)) return 1;
             for (int i = 0; i < n; i++) if (bad[i]) prep[i] = kh::SourcePrep();
         } else if (nthreads > 1) {
             std::atomic<int> next(0);
@@ -928,9 +975,9 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
     cudaEventElapsedTime(&c->ms[4], c->ev[0], c->ev[1]);
     if (trace) {
         const auto tw2 = std::chrono::steady_clock::now();
-        fprintf(stderr, "[kiwi trace] batch of %d: host prep %.3f ms, rest (uploads, launches, device) %.3f ms, device stages %.3f ms\n", n,
-                std::chrono::duration<double, std::milli>(tw1 - tw0).count(), std::chrono::duration<double, std::milli>(tw2 - tw1).count(),
-                c->ms[0] + c->ms[1] + c->ms[2] + c->ms[3]);
+        fprintf(stderr, "[kiwi trace] batch of %d: host prep %.3f ms (%d fast-marching solves on the device), rest (uploads, launches, device) %.3f ms, device stages %.3f ms\n", n,
+                std::chrono::duration<double, std::milli>(tw1 - tw0).count(), c->eikonal_last_device_solves,
+                std::chrono::duration<double, std::milli>(tw2 - tw1).count(), c->ms[0] + c->ms[1] + c->ms[2] + c->ms[3]);
     }
     return 0;
 }
@@ -1403,7 +1450,7 @@ int kiwi_set_share_syntheses(kiwi_ctx* c, int enabled) {
 
 int kiwi_set_eikonal_device(kiwi_ctx* c, int min_batch) {
     if (!c) return kiwi_set_error("null context");
-    c->eikonal_device_min = min_batch < 0 ? 0 : min_batch;
+    c->eikonal_device_min = min_batch < 0 ? -1 : min_batch;
     return 0;
 }
 

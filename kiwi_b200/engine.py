@@ -270,7 +270,7 @@ class Engine:
         _check(lib.kiwi_set_mt_grid(self._h, 2 if (not isinstance(enabled, bool) and enabled == 2) else int(bool(enabled))))
 
     def set_eikonal_device(self, min_batch):
-        """batches of at least min_batch eikonal sources run their fast-marching solves on the device (0 = never, the default)"""
+        """fast-marching solves of eikonal batches: -1 shared between host threads and device (default), 0 host only, k > 0 all on the device from k candidates on"""
         _check(lib.kiwi_set_eikonal_device(self._h, int(min_batch)))
 
     def set_floating_shiftrange(self, lo, hi, ireceiver=0):
