@@ -52,27 +52,36 @@ struct EikHeap {
         }
         if (moved) put(v, x);
     }
-    // heap.f90:176-208
-    __device__ void downheap(int v) {
+    // the same store without the position tracking (during a pop none of the tracked nodes is set)
+    __device__ __forceinline__ void put_plain(int i, EikItem v) { if (i <= EIK_HCAP) sm[i] = v; else ovf[i - EIK_HCAP] = v; bp[v.idx] = i; }
+    // heap.f90:176-208.  The children of entry v are entries 2v and 2v+1: one 16-byte read while both are in shared memory.
+    template <bool TRACK>
+    __device__ void downheap_t(int v) {
         EikItem x = get(v);
         bool moved = false;
         int w = 2 * (v - 1) + 2;
         while (w <= n) {
-            EikItem c = get(w);
-            if (w + 1 <= n) { const EikItem c2 = get(w + 1); if (c2.key < c.key) { c = c2; w = w + 1; } }
+            EikItem c, c2;
+            const bool two = w + 1 <= n;
+            if (w + 1 <= EIK_HCAP) {
+                const int4 q = *reinterpret_cast<const int4*>(sm + w);   // (w is even: 16-byte aligned)
+                c.key = __int_as_float(q.x); c.idx = q.y; c2.key = __int_as_float(q.z); c2.idx = q.w;
+            } else { c = get(w); c2 = two ? get(w + 1) : c; }
+            if (two && c2.key < c.key) { c = c2; w = w + 1; }
             if (x.key <= c.key) break;
-            put(v, c);
+            if (TRACK) put(v, c); else put_plain(v, c);
             v = w; moved = true;
             w = 2 * (v - 1) + 2;
         }
-        if (moved) put(v, x);
+        if (moved) { if (TRACK) put(v, x); else put_plain(v, x); }
     }
+    __device__ void downheap(int v) { downheap_t<true>(v); }
 };
 
 }  // namespace
 
 __global__ void __launch_bounds__(32) k_eikonal_fmm(const EikJob* __restrict__ jobs, int njobs) {
-    __shared__ EikItem s_heap[EIK_HCAP + 1];
+    __shared__ __align__(16) EikItem s_heap[EIK_HCAP + 2];
     const int job = blockIdx.x;
     if (job >= njobs) return;
     const EikJob J = jobs[job];
@@ -125,7 +134,7 @@ __global__ void __launch_bounds__(32) k_eikonal_fmm(const EikJob* __restrict__ j
             const EikItem top = H.get(1), last = H.get(H.n);
             imin = top.idx;
             H.n = H.n - 1;
-            if (H.n >= 1) { H.put(1, last); H.downheap(1); }
+            if (H.n >= 1) { H.put_plain(1, last); H.downheap_t<false>(1); }
             bp[imin] = ALIVE;
         }
         __syncwarp();
