@@ -21,28 +21,61 @@
 
 namespace {
 
+// shared-memory accesses by 32-bit shared address (a generic pointer makes the compiler re-derive the shared window per access)
+__device__ __forceinline__ EikItem lds_item(unsigned addr) {
+    EikItem v;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=f"(v.key), "=r"(v.idx) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void lds_pair(unsigned addr, EikItem& a, EikItem& b) {
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(a.key), "=r"(a.idx), "=f"(b.key), "=r"(b.idx) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void sts_item(unsigned addr, const EikItem& v) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "f"(v.key), "r"(v.idx) : "memory");
+}
+__device__ __forceinline__ void sts_key(unsigned addr, float k) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "f"(k) : "memory"); }
+
 struct EikHeap {
-    EikItem* sm;        // [EIK_HCAP + 1], 1-based
+    unsigned sbase;     // shared address of entry 0 of the shared-memory part (entries 1..EIK_HCAP used, 8 bytes each)
     EikItem* ovf;       // global overflow, entries EIK_HCAP+1 ...
     int* bp;            // back-pointers, 1-based node index
     int n;
     // heap positions of the four neighbours of the node being processed, kept current in registers: their back-pointers were just
     // written to global memory and reading them back would cost a round trip to L2 per neighbour
     int w0, w1, w2, w3, p0, p1, p2, p3;
-    __device__ __forceinline__ EikItem get(int i) const { return i <= EIK_HCAP ? sm[i] : ovf[i - EIK_HCAP]; }
-    __device__ __forceinline__ void put(int i, EikItem v) {
-        if (i <= EIK_HCAP) sm[i] = v; else ovf[i - EIK_HCAP] = v;
-        bp[v.idx] = i;
-        if (v.idx == w0) p0 = i;
-        if (v.idx == w1) p1 = i;
-        if (v.idx == w2) p2 = i;
-        if (v.idx == w3) p3 = i;
+    __device__ __forceinline__ EikItem get(int i) const { return i <= EIK_HCAP ? lds_item(sbase + 8u * (unsigned)i) : ovf[i - EIK_HCAP]; }
+    __device__ __forceinline__ void track(int idx, int i) {
+        if (idx == w0) p0 = i;
+        if (idx == w1) p1 = i;
+        if (idx == w2) p2 = i;
+        if (idx == w3) p3 = i;
     }
-    __device__ __forceinline__ void setkey(int i, float k) { if (i <= EIK_HCAP) sm[i].key = k; else ovf[i - EIK_HCAP].key = k; }
+    __device__ __forceinline__ void put(int i, EikItem v) {
+        if (i <= EIK_HCAP) sts_item(sbase + 8u * (unsigned)i, v); else ovf[i - EIK_HCAP] = v;
+        bp[v.idx] = i;
+        track(v.idx, i);
+    }
+    // the same store without the position tracking (during a pop none of the tracked nodes is set)
+    __device__ __forceinline__ void put_plain(int i, EikItem v) {
+        if (i <= EIK_HCAP) sts_item(sbase + 8u * (unsigned)i, v); else ovf[i - EIK_HCAP] = v;
+        bp[v.idx] = i;
+    }
+    __device__ __forceinline__ void setkey(int i, float k) { if (i <= EIK_HCAP) sts_key(sbase + 8u * (unsigned)i, k); else ovf[i - EIK_HCAP].key = k; }
     // heap.f90:210-232
     __device__ void upheap(int v) {
         EikItem x = get(v);
         bool moved = false;
+        if (v <= EIK_HCAP) {   // the whole path to the root is in shared memory
+            while (v > 1) {
+                const int u = v >> 1;            // (v - 2) / 2 + 1
+                const EikItem p = lds_item(sbase + 8u * (unsigned)u);
+                if (p.key <= x.key) break;
+                sts_item(sbase + 8u * (unsigned)v, p); bp[p.idx] = v; track(p.idx, v);
+                v = u; moved = true;
+            }
+            if (moved) { sts_item(sbase + 8u * (unsigned)v, x); bp[x.idx] = v; track(x.idx, v); }
+            return;
+        }
         while (v > 1) {
             const int u = (v - 2) / 2 + 1;
             const EikItem p = get(u);
@@ -52,26 +85,33 @@ struct EikHeap {
         }
         if (moved) put(v, x);
     }
-    // the same store without the position tracking (during a pop none of the tracked nodes is set)
-    __device__ __forceinline__ void put_plain(int i, EikItem v) { if (i <= EIK_HCAP) sm[i] = v; else ovf[i - EIK_HCAP] = v; bp[v.idx] = i; }
     // heap.f90:176-208.  The children of entry v are entries 2v and 2v+1: one 16-byte read while both are in shared memory.
     template <bool TRACK>
     __device__ void downheap_t(int v) {
         EikItem x = get(v);
         bool moved = false;
-        int w = 2 * (v - 1) + 2;
+        int w = 2 * v;                           // 2 * (v - 1) + 2
+        if (n <= EIK_HCAP) {   // the whole heap is in shared memory (the usual case)
+            while (w <= n) {
+                EikItem c, c2;
+                lds_pair(sbase + 8u * (unsigned)w, c, c2);   // (w is even: 16-byte aligned; entry n+1 may be stale, it is not used then)
+                if (w < n && c2.key < c.key) { c = c2; w = w + 1; }
+                if (x.key <= c.key) break;
+                sts_item(sbase + 8u * (unsigned)v, c); bp[c.idx] = v;
+                if (TRACK) track(c.idx, v);
+                v = w; moved = true;
+                w = 2 * v;
+            }
+            if (moved) { sts_item(sbase + 8u * (unsigned)v, x); bp[x.idx] = v; if (TRACK) track(x.idx, v); }
+            return;
+        }
         while (w <= n) {
-            EikItem c, c2;
-            const bool two = w + 1 <= n;
-            if (w + 1 <= EIK_HCAP) {
-                const int4 q = *reinterpret_cast<const int4*>(sm + w);   // (w is even: 16-byte aligned)
-                c.key = __int_as_float(q.x); c.idx = q.y; c2.key = __int_as_float(q.z); c2.idx = q.w;
-            } else { c = get(w); c2 = two ? get(w + 1) : c; }
-            if (two && c2.key < c.key) { c = c2; w = w + 1; }
+            EikItem c = get(w);
+            if (w + 1 <= n) { const EikItem c2 = get(w + 1); if (c2.key < c.key) { c = c2; w = w + 1; } }
             if (x.key <= c.key) break;
             if (TRACK) put(v, c); else put_plain(v, c);
             v = w; moved = true;
-            w = 2 * (v - 1) + 2;
+            w = 2 * v;
         }
         if (moved) { if (TRACK) put(v, x); else put_plain(v, x); }
     }
@@ -97,7 +137,7 @@ __global__ void __launch_bounds__(32) k_eikonal_fmm(const EikJob* __restrict__ j
     for (int i = 1 + lane; i <= nn; i += 32) { T[i] = infinity; bp[i] = FARAWAY; }
     __syncwarp();
     EikHeap H;
-    H.sm = s_heap; H.ovf = J.ovf; H.bp = bp; H.n = 0;
+    H.sbase = (unsigned)__cvta_generic_to_shared(s_heap); H.ovf = J.ovf; H.bp = bp; H.n = 0;
     H.w0 = H.w1 = H.w2 = H.w3 = 0; H.p0 = H.p1 = H.p2 = H.p3 = 0;
     const int ix0 = J.ix0, iy0 = J.iy0;
     const int i0 = (iy0 - 1) * nx + ix0;

@@ -333,12 +333,12 @@ int prep_eikonal_batch_device(kiwi_ctx* c, int sourcetype, int n, int nparams, c
     const size_t wave_nodes = std::max<size_t>((size_t)1 << 22, std::min<size_t>(fr / 3, (size_t)24 << 30) / 20);   // 20 bytes per node on the device
     const int wave_jobs = 148 * 13;                                                                                  // solves resident at a time
     // ---- which solves go to the device -----------------------------------------------------------------------------
-    // measured rates (profiles/r02_eikonal_device.txt): a warp 2.6 us per node whatever else runs, a host core 0.1 us per node for the solve
+    // measured rates (profiles/r02_eikonal_device.txt): a warp 2.1-2.5 us per node (1 to 1036 solves resident), a host core 0.1 us per node for the solve
     // and 0.045 us for the down-sampling that follows; staging ~8 bytes per node at ~8 GB/s.  The device takes a prefix of the
     // size-ordered list: its wave lasts as long as its largest grid.
     size_t ndev = order.size();
     if (share) {
-        const double dev_node = 2.6e-6, host_solve = 1.0e-7, host_finish = 0.45e-7, stage = 1.0e-9;
+        const double dev_node = 2.4e-6, host_solve = 1.0e-7, host_finish = 0.45e-7, stage = 1.0e-9;
         double all_solve = 0., all_finish = 0.;
         for (int i : order) { all_solve += host_solve * works[i].speed.size(); all_finish += host_finish * works[i].speed.size(); }
         double best = (all_solve + all_finish) / ncores, dev_solve = 0., dev_finish = 0., nodes = 0.;
