@@ -216,9 +216,12 @@ int upload_receivers(kiwi_ctx* c) {
                     int ex = 0;
                     if (rms > 0. && std::isfinite(rms)) std::frexp(rms, &ex);
                     r.ref_rs[k] = std::ldexp(1.f, -std::min(std::max(ex, -100), 100));
+                    double sa = 0.;
+                    for (float v : h.ref[k]) sa += (double)fabsf(v);
+                    r.ref_ss[k] = ss; r.ref_sa[k] = sa;
                 }
             } else {
-                r.ref_ds0[k] = 0; r.ref_ds1[k] = -1; r.ref_off[k] = 0; r.ref_rs[k] = 1.f;
+                r.ref_ds0[k] = 0; r.ref_ds1[k] = -1; r.ref_off[k] = 0; r.ref_rs[k] = 1.f; r.ref_ss[k] = 0.; r.ref_sa[k] = 0.;
             }
         }
         if (!h.taper_x.empty()) {

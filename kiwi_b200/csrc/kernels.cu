@@ -2170,14 +2170,19 @@ __global__ void __launch_bounds__(128, 4) k_mt_fused(GfdbDev db, const ReceiverD
                     acc += l1 ? (double)fabsf(r) : (double)r * (double)r;
                 }
                 acc = l1 ? acc / (double)rs : acc / ((double)rs * (double)rs);
-                // reference-only norm (the same for all candidates): block reduction
-                double accn = 0.;
-                for (int x = q0 + tid; x <= q1; x += MTC_M) { const float a = refval(x); accn += l1 ? (double)fabsf(a) : (double)a * (double)a; }
-                for (int ofs = 16; ofs; ofs >>= 1) accn += __shfl_xor_sync(0xffffffffu, accn, ofs);
-                const unsigned rb = nred++ & 1u;   // alternating buffers: one barrier between the writes and the reads is enough
-                if (lane == 0) s_red[rb][warp] = accn;
-                __syncthreads();
-                accn = s_red[rb][0] + s_red[rb][1] + s_red[rb][2] + s_red[rb][3];
+                // reference-only norm (the same for all candidates).  Untapered it is the sum over the reference's data span, which the host
+                // has formed once per receiver component; with a taper the span depends on the synthetic's: block reduction
+                double accn;
+                if (!tapered && q0 == rds0 && q1 == rds1) accn = l1 ? R.ref_sa[ic] : R.ref_ss[ic];
+                else {
+                    accn = 0.;
+                    for (int x = q0 + tid; x <= q1; x += MTC_M) { const float a = refval(x); accn += l1 ? (double)fabsf(a) : (double)a * (double)a; }
+                    for (int ofs = 16; ofs; ofs >>= 1) accn += __shfl_xor_sync(0xffffffffu, accn, ofs);
+                    const unsigned rb = nred++ & 1u;   // alternating buffers: one barrier between the writes and the reads is enough
+                    if (lane == 0) s_red[rb][warp] = accn;
+                    __syncthreads();
+                    accn = s_red[rb][0] + s_red[rb][1] + s_red[rb][2] + s_red[rb][3];
+                }
                 if (o) {
                     float mis, nf;
                     if (l1) { mis = (float)((double)dt * acc); nf = fa * (float)((double)dt * accn); }

@@ -49,6 +49,8 @@ struct ReceiverDev {
     long long ref_off[KIWI_MAX_COMP];                     // offset of the ref samples in d_refdata
     float ref_rs[KIWI_MAX_COMP];                          // power of two that brings the rms of the reference trace to order one: the
                                                           // tensor-core misfit kernels square fp32 residuals scaled by it (k_mt_fused)
+    double ref_ss[KIWI_MAX_COMP], ref_sa[KIWI_MAX_COMP];  // sum of squares / of magnitudes of the reference's data span in double (the
+                                                          // untapered reference-only norm, comparator.f90:639-659: the same for every candidate)
     // taper (piecewise_linear_function.f90:195-237), tabulated on [tp0, tp1] by the host
     int has_taper, tp0, tp1;     // tp0 = floor(x1/dt)+1, tp1 = floor(xn/dt): support of the taper
     int dps0, dps1;              // discrete_plf_span (comparator.f90:1145-1157)
