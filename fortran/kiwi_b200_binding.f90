@@ -414,6 +414,13 @@ module kiwi_b200_binding
             integer(c_int) :: rc
         end function
 
+        function kiwi_set_accumulation(ctx, reference_order) bind(C, name="kiwi_set_accumulation") result(rc)
+            import :: c_ptr, c_int
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: reference_order
+            integer(c_int) :: rc
+        end function
+
         function kiwi_set_eikonal_device(ctx, min_batch) bind(C, name="kiwi_set_eikonal_device") result(rc)
             import :: c_ptr, c_int
             type(c_ptr), value :: ctx

@@ -50,6 +50,7 @@ SIGNATURES = {
     "kiwi_set_share_syntheses": (C.c_int, [C.c_void_p, C.c_int]),
     "kiwi_set_mt_grid": (C.c_int, [C.c_void_p, C.c_int]),
     "kiwi_set_eikonal_device": (C.c_int, [C.c_void_p, C.c_int]),
+    "kiwi_set_accumulation": (C.c_int, [C.c_void_p, C.c_int]),
     "kiwi_set_floating_shiftrange": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float]),
     "kiwi_get_nmisfits": (C.c_int, [C.c_void_p]),
     "kiwi_get_n_source_params": (C.c_int, [C.c_int]),

@@ -24,9 +24,9 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-pthread",
              "-I" + os.path.join(CUDA_HOME, "include"), "-Wall", "-Wno-unused-function", "-Wno-misleading-indentation"]
 
-CU_SOURCES = ["kernels.cu", "gulunay.cu", "eikonal.cu"]
+CU_SOURCES = ["kernels.cu", "gulunay.cu", "eikonal.cu", "synth_exact.cu"]
 # per-file extra flags: the interpolation kernels are written operation by operation (no FMA contraction)
-EXTRA_NVCC_FLAGS = {"gulunay.cu": ["-fmad=false"], "eikonal.cu": ["-fmad=false"]}
+EXTRA_NVCC_FLAGS = {"gulunay.cu": ["-fmad=false"], "eikonal.cu": ["-fmad=false"], "synth_exact.cu": ["-fmad=false"]}
 CXX_SOURCES = ["engine.cpp", "host_math.cpp", "gfdb_host.cpp", "source_eikonal_host.cpp", "lm_host.cpp", "gfdb_hdf_host.cpp"]
 
 

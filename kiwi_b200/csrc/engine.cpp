@@ -128,6 +128,7 @@ struct kiwi_ctx {
     // grid, 2.4 s); sharing gives the device the small grids while the host threads work through the large ones.
     int eikonal_device_min = getenv("KIWI_EIKONAL_DEVICE_MIN") ? atoi(getenv("KIWI_EIKONAL_DEVICE_MIN")) : -1;
     int eikonal_last_device_solves = 0;      // solves of the last batch that ran on the device
+    bool accum_reference = false;            // kiwi_set_accumulation: synthesis in the reference's order of operations (synth_exact.cu)
     bool mt_grid_fused = true;               // ... with the synthesis fused into it where the windows fit (k_mt_fused)
     DevBuf d_map, d_status_out;
     DevBuf d_taprec;              // shift table of the current batch (k_tap_table)
@@ -601,7 +602,7 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
     }
     if (upload_receivers(c)) return 1;
     if (!hook && want_misfits && !general && sourcetype == KIWI_SOURCE_MOMENT_TENSOR &&
-        (c->misfit_method == KIWI_L2NORM || c->misfit_method == KIWI_L1NORM) && c->mt_grid_enabled) {
+        (c->misfit_method == KIWI_L2NORM || c->misfit_method == KIWI_L1NORM) && c->mt_grid_enabled && !c->accum_reference) {
         bool used = false;
         const int rc = eval_mt_grid(c, n, params, d_out, h_status, &used);
         if (rc || used) return rc;
@@ -827,8 +828,9 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
             static const int init3[4] = {0, INT_MAX, INT_MIN, 0};   // max window length, min first sample, max last sample
             CU_OK(cudaMemcpyAsync(c->d_tmax.p, init3, sizeof init3, cudaMemcpyHostToDevice, st));
         }
+        const bool exact = c->accum_reference && !hook;
         launch_geometry(c->db, c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>(), nc, g, Galloc, c->interpolate ? 1 : 0, c->xunder, c->zunder,
-                        c->d_recs.as<GeoRec>(), rec_stride, c->d_hdrs.as<PairHdr>(), c->d_tmax.as<int>(), st);
+                        c->d_recs.as<GeoRec>(), rec_stride, c->d_hdrs.as<PairHdr>(), c->d_tmax.as<int>(), st, exact ? 1 : 0);
         c->launches[1] += 1;
         int tm3[4] = {0, 0, 0, 0};
         CU_OK(cudaMemcpyAsync(tm3, c->d_tmax.p, sizeof tm3, cudaMemcpyDeviceToHost, st));
@@ -896,7 +898,31 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
                 c->ms[3] += b;
                 continue;
             }
-            if (tmax > 0) {
+            if (tmax > 0 && exact) {
+                // reference-order synthesis: one thread per output sample walks the centroids one after the other
+                const int wcap = 4 * nq + 32;
+                if (4 * nq > synth_exact_max_samples() || synth_exact_smem_bytes(wcap) > (size_t)200 * 1024)
+                    return kiwi_set_error("synthetic window of %d samples is too long for the reference-order synthesis", tmax);
+                CU_OK(c->d_tmax.ensure(sizeof(int) * 8));
+                int* d_overflow = c->d_tmax.as<int>() + 5;
+                CU_OK(cudaMemsetAsync(d_overflow, 0, sizeof(int), st));
+                cudaError_t e = launch_synth_exact(c->db, c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>() + s0, ns_, g, taps, Galloc,
+                                                   c->d_recs.as<GeoRec>() + poff * rec_stride, rec_stride, c->d_hdrs.as<PairHdr>() + poff, nq, margin_q,
+                                                   c->interpolate ? 1 : 0, c->xunder, c->zunder, wcap, c->d_seis.as<float>(), seis_stride,
+                                                   c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, d_overflow, st);
+                if (e != cudaSuccess) return kiwi_set_error("CUDA error launching the reference-order synthesis: %s", cudaGetErrorString(e));
+                c->launches[2] += 1;
+                int overflow = 0;
+                CU_OK(cudaMemcpyAsync(&overflow, d_overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+                CU_OK(cudaStreamSynchronize(st));
+                if (overflow) return kiwi_set_error("a Green's function window is too long for the reference-order synthesis");
+                if (max_rise > 0.f) {
+                    e = launch_fold(c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>() + s0, ns_, c->d_seis.as<float>(), seis_stride,
+                                    c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, c->db.dt, st);
+                    if (e != cudaSuccess) return kiwi_set_error("CUDA error launching the rise-time fold: %s", cudaGetErrorString(e));
+                    c->launches[2] += 1;
+                }
+            } else if (tmax > 0) {
                 if (nbands > 1) CU_OK(c->d_partial.ensure(synth_partial_bytes(nq) * (size_t)ns_ * nrcv));
                 cudaError_t e = launch_synth(c->db, c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>() + s0, ns_, g,
                                              c->d_recs.as<GeoRec>() + poff * rec_stride, rec_stride, c->d_hdrs.as<PairHdr>() + poff, nq, margin_q,
@@ -1448,6 +1474,13 @@ int kiwi_set_source_crustal_thickness_limit(kiwi_ctx* c, float limit) {   // par
 int kiwi_set_share_syntheses(kiwi_ctx* c, int enabled) {
     if (!c) return kiwi_set_error("null context");
     c->dedup_enabled = enabled != 0;
+    return 0;
+}
+
+int kiwi_set_accumulation(kiwi_ctx* c, int reference_order) {
+    if (!c) return kiwi_set_error("null context");
+    c->accum_reference = reference_order != 0;
+    c->src_dirty = true;
     return 0;
 }
 

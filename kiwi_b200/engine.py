@@ -269,6 +269,10 @@ class Engine:
         """tensor-core path for point moment-tensor grid searches on (default) / off; 2 = on, synthesis not fused into the contraction"""
         _check(lib.kiwi_set_mt_grid(self._h, 2 if (not isinstance(enabled, bool) and enabled == 2) else int(bool(enabled))))
 
+    def set_accumulation(self, reference_order):
+        """synthesis in the reference's order of floating-point operations (slow; kiwi_set_accumulation) on / off (default)"""
+        _check(lib.kiwi_set_accumulation(self._h, int(bool(reference_order))))
+
     def set_eikonal_device(self, min_batch):
         """fast-marching solves of eikonal batches: -1 shared between host threads and device (default), 0 host only, k > 0 all on the device from k candidates on"""
         _check(lib.kiwi_set_eikonal_device(self._h, int(min_batch)))
