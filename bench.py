@@ -507,6 +507,34 @@ def cpu_baseline(w, db, rlat, rlon, rdep, dt, stype, cands, gpu_misfits, geng=No
                 ntr += 1
         parity.update(worst)
         parity["seis_traces_compared"] = ntr
+    if geng is not None:
+        # the same sample in the reference's order of operations (kiwi_set_accumulation, csrc/synth_exact.cu): held against the fp32
+        # restatement as it stands, at the north_star bar (1e-5 relative for seismograms and misfits)
+        try:
+            geng.set_accumulation(True)
+            mr, sr = geng.eval_sources(stype, cands[:n])
+            tr_ = geng.last_timing()
+            ro = {"misfit_vs_fp32_path": float(np.max(np.abs(mr - mo) / np.maximum(np.abs(mo), 1e-300))), "unit": UNIT,
+                  "value": n / (tr_["total_ms"] * 1e-3) if tr_["total_ms"] > 0 else None}
+            geng.set_source_params(stype, cands[n - 1])
+            worst_ro = 0.0
+            for ir in np.unique(np.linspace(1, w["nrcv"], min(w["nrcv"], 100)).astype(int)):
+                for ic in range(1, 4):
+                    (fa, da), (fb, dbb) = geng.get_seismogram(int(ir), ic), o.get_seismogram(int(ir), ic)
+                    peak = float(np.abs(dbb).max()) if dbb.size else 0.0
+                    if (fa, da.size) != (fb, dbb.size):
+                        worst_ro = float("inf")
+                    elif peak > 0:
+                        worst_ro = max(worst_ro, float(np.abs(da - dbb).max()) / peak)
+            ro["seis_vs_fp32_path"] = worst_ro
+            ro["ok"] = bool(worst_ro <= 1e-5 and ro["misfit_vs_fp32_path"] <= 1e-5)
+            ro["note"] = ("reference-order synthesis (every operation of make_seismogram per output sample in the reference's order) against "
+                          "the fp32 restatement as it stands: max |a - b| / trace peak, max relative misfit deviation; value = its own rate")
+            parity["reference_order"] = ro
+        except Exception as exc:
+            parity["reference_order"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+        finally:
+            geng.set_accumulation(False)
     sn = parity.get("seis_fp32_path_vs_double_accumulation", 0.0)
     parity["ok"] = bool(parity.get("seis_vs_double_accumulation", 0.0) <= 1e-5 and parity.get("seis_vs_fp32_path", 0.0) <= 1e-5 + 1.5 * sn and
                         dw <= 1e-5 and d32 <= max(1e-5, 2.0 * d32w))
