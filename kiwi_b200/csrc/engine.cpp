@@ -739,7 +739,7 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         if (TT > 0x7fffff00LL) return kiwi_set_error("too many (sub-source, time) pairs in one batch");
         const int Galloc = std::max(G, 1), Talloc = std::max(Tp, 1);
         CU_OK(c->d_cands.ensure(sizeof(CandDev) * nc));
-        CU_OK(c->d_gf.ensure(sizeof(float) * 11 * (size_t)Galloc));
+        CU_OK(c->d_gf.ensure(sizeof(float) * 12 * (size_t)Galloc));
         CU_OK(c->d_gi.ensure(sizeof(int) * 6 * (size_t)Galloc));
         CU_OK(c->d_taprec.ensure(sizeof(float4) * 2 * ((size_t)TT + 1)));
         CU_OK(c->d_tf.ensure(sizeof(float) * 2 * (size_t)Talloc));
@@ -747,6 +747,7 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         float* gf = c->d_gf.as<float>();
         g.north = gf; g.east = gf + Galloc; g.depth = gf + 2 * (size_t)Galloc; g.tbase = gf + 3 * (size_t)Galloc; g.mhat = gf + 4 * (size_t)Galloc;
         g.gw = gf + 10 * (size_t)Galloc;
+        g.lam = nullptr;
         int* gi = c->d_gi.as<int>();
         g.tap_begin = gi; g.tap_count = gi + Galloc; g.its_min = gi + 2 * (size_t)Galloc; g.its_max = gi + 3 * (size_t)Galloc;
         g.tt_begin = gi + 4 * (size_t)Galloc; g.nstep = gi + 5 * (size_t)Galloc;
@@ -829,6 +830,15 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
             CU_OK(cudaMemcpyAsync(c->d_tmax.p, init3, sizeof init3, cudaMemcpyHostToDevice, st));
         }
         const bool exact = c->accum_reference && !hook;
+        if (exact) {   // atan2f of the sub-source positions from the host library (see approx_differential_azidist in kernels.cu)
+            std::vector<float> ne((size_t)2 * Galloc), lam((size_t)Galloc, 0.f);
+            CU_OK(cudaMemcpyAsync(ne.data(), g.north, sizeof(float) * 2 * (size_t)Galloc, cudaMemcpyDeviceToHost, st));   // north, east: adjacent
+            CU_OK(cudaStreamSynchronize(st));
+            for (int k = 0; k < G; k++) lam[k] = atan2f(ne[(size_t)Galloc + k], ne[k]);
+            g.lam = gf + 11 * (size_t)Galloc;
+            CU_OK(cudaMemcpyAsync(g.lam, lam.data(), sizeof(float) * (size_t)Galloc, cudaMemcpyHostToDevice, st));
+            CU_OK(cudaStreamSynchronize(st));
+        }
         launch_geometry(c->db, c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>(), nc, g, Galloc, c->interpolate ? 1 : 0, c->xunder, c->zunder,
                         c->d_recs.as<GeoRec>(), rec_stride, c->d_hdrs.as<PairHdr>(), c->d_tmax.as<int>(), st, exact ? 1 : 0);
         c->launches[1] += 1;

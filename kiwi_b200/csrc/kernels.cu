@@ -186,7 +186,7 @@ __device__ __forceinline__ double wrapd(double x, double mi, double ma) { return
 // orthodrome.f90:77-156 (flat approximation and const-azimuth approximation are switched off by
 // constants, :67,72; r == 0 still takes the const-azimuth branch because dist/0 = +Inf > huge)
 __device__ void approx_differential_azidist(float delta_x, float delta_y, double azimuth, double backazimuth, double dist,
-                                            double& new_azimuth, double& new_backazimuth, double& new_dist) {
+                                            double& new_azimuth, double& new_backazimuth, double& new_dist, const float* host_lambda = nullptr) {
     const double pi_ = (double)3.14159265358979f;       // constants.f90:22: default-real literal
     const double earthradius = (double)(6371.f * 1000.f);
     double r = (double)__fsqrt_rn(A_(M_(delta_x, delta_x), M_(delta_y, delta_y)));
@@ -197,7 +197,9 @@ __device__ void approx_differential_azidist(float delta_x, float delta_y, double
     } else {
         double a = r / earthradius;
         double b = dist / earthradius;
-        double lambda = (double)atan2f(delta_y, delta_x);
+        // (reference-order mode: the host library's atan2f of the sub-source position, handed in -- the device's own may be an ulp off,
+        //  which at 50 km is a few millimetres of epicentral distance: one fp32 ulp)
+        double lambda = host_lambda ? (double)*host_lambda : (double)atan2f(delta_y, delta_x);
         double gamma = azimuth - lambda;
         double sa, ca, sb, cb, sg, cg;
         sincos(a, &sa, &ca); sincos(b, &sb, &cb); sincos(gamma, &sg, &cg);
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(256, 3) k_geometry(GfdbDev db, const ReceiverD
             const int gi = cand.group_begin + ip;
             const float dnorth = g.north[gi], deast = g.east[gi], depth = g.depth[gi];
             double azi, bazi, dist;
-            approx_differential_azidist(dnorth, deast, R.azi0, R.bazi0, R.dist0, azi, bazi, dist);
+            approx_differential_azidist(dnorth, deast, R.azi0, R.bazi0, R.dist0, azi, bazi, dist, (trig_only && g.lam) ? g.lam + gi : nullptr);
             GeoRec rec;
             {   // make_weights seismogram.f90:316-336 on the group's moment-tensor shape; the scalar tap
                 // weight wt multiplies the result later (the reference applies it to m first)

@@ -2,9 +2,10 @@
 make_seismogram / trace_multiply_add / gfdb_get_trace_bilin (seismogram.f90:131-289, sparse_trace.f90:597-707, gfdb.f90:865-950) per output
 sample in the reference's order.  Against the fp32 restatement AS IT STANDS, at the north_star bar of 1e-5 for seismograms and misfits --
 no appeal to the reference's own accumulation noise -- on the small scenario for every source type and at the full size of config C3
-(~1e4 sub-sources x 200 receivers) and of a C5 candidate on 300 of its 2000 receivers.  What is left (measured <= 1e-6 of the trace peak)
-comes from the device's double-precision libm in the geometry pre-pass: the epicentral distance of a few sub-sources per receiver is one
-fp32 ulp off the host's."""
+(~1e4 sub-sources x 200 receivers) and of a C5 candidate on 300 of its 2000 receivers.  Measured: 2e-7 of the trace peak, 98 % of the
+samples bit-identical (the point moment tensor of the small scenario: all of them); the sub-source azimuth atan2f(east, north) comes from
+the host library in this mode, because the device's differs from it by an ulp often enough to move the epicentral distance of ~2 % of
+the sub-sources by one fp32 ulp."""
 import numpy as np
 import pytest
 
@@ -14,7 +15,7 @@ from test_parity_gpu import CIRC, COMPS6, EIK, MTEIK, PLP, engines
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-5          # BASELINE.json north_star
-TIGHT = 2e-6         # what the mode delivers in practice (guards against regressions of the operation order)
+TIGHT = 1e-6         # the mode delivers 2e-7 in practice (guards against regressions of the operation order)
 
 
 def deviation(g, o, nrcv, ncomps):
@@ -42,7 +43,7 @@ def test_small_scenario_every_source_type(stype, params):
     g.set_accumulation(True)
     g.set_source_params(stype, p)
     worst, same = deviation(g, o, 6, ncomps)
-    assert worst <= TIGHT and same > 0.5, (worst, same)
+    assert worst <= TIGHT and same > 0.9, (worst, same)
     sc.set_refs_from(o, [g, o], ncomps)
     q = np.tile(p, (3, 1)); q[1, 3] += 300; q[2, 1] -= 250
     mg, sg = g.eval_sources(stype, q)
@@ -61,7 +62,7 @@ def test_c3_full_size_against_the_fp32_restatement_as_it_stands():
     g.set_source_params("bilateral", synthetic.IZMIT)
     worst, same = deviation(g, o, w["nrcv"], [3] * w["nrcv"])
     print("C3, reference order: %.2e of the trace peak from the fp32 restatement, %.0f %% of the samples bit-identical" % (worst, 100 * same))
-    assert worst <= RTOL and worst <= 5e-6, worst
+    assert worst <= RTOL and worst <= TIGHT, worst
     g.set_accumulation(False)
     g.set_source_params("bilateral", synthetic.IZMIT)
     fast, _ = deviation(g, o, w["nrcv"], [3] * w["nrcv"])
@@ -87,4 +88,4 @@ def test_c5_candidate_on_300_receivers():
     g.set_accumulation(True)
     g.set_source_params("bilateral", cand)
     worst, same = deviation(g, o, w["nrcv"], [3] * w["nrcv"])
-    assert worst <= RTOL and worst <= 5e-6, worst
+    assert worst <= RTOL and worst <= TIGHT, worst
