@@ -830,7 +830,7 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
             CU_OK(cudaMemcpyAsync(c->d_tmax.p, init3, sizeof init3, cudaMemcpyHostToDevice, st));
         }
         const bool exact = c->accum_reference && !hook;
-        if (exact) {   // atan2f of the sub-source positions from the host library (see approx_differential_azidist in kernels.cu)
+        {   // atan2f of the sub-source positions from the host library (see approx_differential_azidist in kernels.cu)
             std::vector<float> ne((size_t)2 * Galloc), lam((size_t)Galloc, 0.f);
             CU_OK(cudaMemcpyAsync(ne.data(), g.north, sizeof(float) * 2 * (size_t)Galloc, cudaMemcpyDeviceToHost, st));   // north, east: adjacent
             CU_OK(cudaStreamSynchronize(st));

@@ -197,8 +197,8 @@ __device__ void approx_differential_azidist(float delta_x, float delta_y, double
     } else {
         double a = r / earthradius;
         double b = dist / earthradius;
-        // (reference-order mode: the host library's atan2f of the sub-source position, handed in -- the device's own may be an ulp off,
-        //  which at 50 km is a few millimetres of epicentral distance: one fp32 ulp)
+        // (the host library's atan2f of the sub-source position, handed in: the device's own is an ulp off it often enough to move
+        //  the epicentral distance of ~2 % of the sub-sources by one fp32 ulp -- at 50 km an ulp of the angle is a few millimetres)
         double lambda = host_lambda ? (double)*host_lambda : (double)atan2f(delta_y, delta_x);
         double gamma = azimuth - lambda;
         double sa, ca, sb, cb, sg, cg;
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(256, 3) k_geometry(GfdbDev db, const ReceiverD
             const int gi = cand.group_begin + ip;
             const float dnorth = g.north[gi], deast = g.east[gi], depth = g.depth[gi];
             double azi, bazi, dist;
-            approx_differential_azidist(dnorth, deast, R.azi0, R.bazi0, R.dist0, azi, bazi, dist, (trig_only && g.lam) ? g.lam + gi : nullptr);
+            approx_differential_azidist(dnorth, deast, R.azi0, R.bazi0, R.dist0, azi, bazi, dist, g.lam ? g.lam + gi : nullptr);
             GeoRec rec;
             {   // make_weights seismogram.f90:316-336 on the group's moment-tensor shape; the scalar tap
                 // weight wt multiplies the result later (the reference applies it to m first)

@@ -85,7 +85,7 @@ struct GroupSoA {
     float *north, *east, *depth, *tbase;
     float* mhat;                // [6][ngroups_total] : mxx myy mzz mxy mxz myz
     float* gw;                  // scalar weight of the group (sub-fault weight of an eikonal source, source_eikonal.f90:697; 1 otherwise)
-    float* lam;                 // reference-order mode: atan2f(east, north) of the group from the host library (orthodrome.f90:121), or null
+    float* lam;                 // atan2f(east, north) of the group from the host library (orthodrome.f90:121), or null = the device's own
     int *tap_begin, *tap_count; // taps of this group
     int *its_min, *its_max;     // min/max of floor((tbase (+) toff)/dt) over the taps
     // receiver-independent shift table of the group (k_tap_table): what trace_multiply_add derives from

@@ -92,9 +92,13 @@ def test_c3_seismograms_and_integers_match_the_fp32_oracle():
         assert np.array_equal(ig["ix"][ok], io["ix"][ok]), "ix of receiver %d" % ir
         assert np.array_equal(ig["iz"], io["iz"]) and np.array_equal(ig["its"], io["its"]), "iz / its of receiver %d" % ir
         assert np.array_equal(ig["diz"], io["diz"])
+        # since the sub-source azimuths atan2f(east, north) come from the host library (round 2) the distance coordinate agrees to the last
+        # bit as well, flagged pairs included: indices and bilinear weights are bit-exact everywhere
+        assert np.array_equal(ig["ix"], io["ix"]) and np.array_equal(ig["dix"].view(np.uint32), io["dix"].view(np.uint32)), "ix / dix of receiver %d" % ir
     # a distance of ~1000 cells is within 4 ulps of an edge with probability ~1e-3
     assert nflag <= 4e-3 * npairs, "%d of %d (sub-source, receiver) pairs flagged as sitting on a cell edge" % (nflag, npairs)
-    assert ndiff <= 1e-4 * npairs, "%d of %d GF distance indices differ" % (ndiff, npairs)
+    print("C3: %d of %d (sub-source, receiver) pairs flagged as sitting on a cell edge, %d distance indices differ" % (nflag, npairs, ndiff))
+    assert ndiff == 0, "%d of %d GF distance indices differ" % (ndiff, npairs)
     assert_seismograms(g, o, ow, w["nrcv"], "C3")
 
 
