@@ -16,6 +16,7 @@
 #include <cfloat>
 #include <cstdio>
 #include <vector>
+#include <algorithm>
 
 #define EIK_HCAP 2040          // heap entries kept in shared memory (16 KB per candidate: 13 candidates per SM); the rest spills to global memory
 
@@ -132,9 +133,10 @@ __global__ void __launch_bounds__(32) k_eikonal_fmm(const EikJob* __restrict__ j
     const float dx2 = __fmul_rn(dx, dx), dy2 = __fmul_rn(dy, dy), dx2dy2 = __fmul_rn(dx2, dy2), dx2pdy2 = __fadd_rn(dx2, dy2);
     float* T = J.T - 1;            // 1-based views
     int* bp = J.bp - 1;
-    const float* S = J.S - 1;
+    float* S = const_cast<float*>(J.S) - 1;
     const int FARAWAY = -1, ALIVE = 0;
     for (int i = 1 + lane; i <= nn; i += 32) { T[i] = infinity; bp[i] = FARAWAY; }
+    if (J.invalid_speed > 0.f) for (int i = 1 + lane; i <= nn; i += 32) if (S[i] == 0.f) S[i] = J.invalid_speed;
     __syncwarp();
     EikHeap H;
     H.sbase = (unsigned)__cvta_generic_to_shared(s_heap); H.ovf = J.ovf; H.bp = bp; H.n = 0;
@@ -255,6 +257,138 @@ __global__ void __launch_bounds__(32) k_eikonal_fmm(const EikJob* __restrict__ j
     }
 }
 
+// ---- the rest of the discretiser's fine-grid work (source_eikonal.f90:435-601), so that a candidate whose solve runs on the device
+// never sends its grid over PCIe: the speed field before the solve, the down-sampling after it.  -fmad=false: every operation is the
+// IEEE operation of the host code (source_eikonal_host.cpp), in its order.
+namespace {
+__device__ __forceinline__ void eik_rc_to_ned(const EikGeom& G, const float rc[3], float out[3]) {   // :612-617
+    for (int i = 0; i < 3; i++) {
+        float a = 0.f;
+        for (int j = 0; j < 3; j++) a = a + G.rot[i * 3 + j] * rc[j];
+        out[i] = a + G.shift[i];
+    }
+}
+__device__ __forceinline__ void eik_ned_to_rc(const EikGeom& G, const float pt[3], float out[3]) {   // :605-610
+    const float d[3] = {pt[0] - G.shift[0], pt[1] - G.shift[1], pt[2] - G.shift[2]};
+    for (int i = 0; i < 3; i++) {
+        float a = 0.f;
+        for (int j = 0; j < 3; j++) a = a + G.rot[j * 3 + i] * d[j];
+        out[i] = a;
+    }
+}
+__device__ __forceinline__ void eik_fine_point(const EikGeom& G, int ix, int iy, float pt[3]) {
+    const float rc[3] = {G.first[0] + ((float)ix - 0.5f) * G.delta[0], G.first[1] + ((float)iy - 0.5f) * G.delta[1], 0.f};
+    eik_rc_to_ned(G, rc, pt);
+}
+}  // namespace
+
+// speed field: one thread per fine node; blockIdx.y = candidate
+__global__ void __launch_bounds__(256) k_eik_speed(EikGeom* __restrict__ geoms, float* __restrict__ S) {
+    __shared__ EikGeom G;
+    __shared__ int s_min;
+    EikGeom* gp = geoms + blockIdx.y;
+    for (int i = threadIdx.x; i < (int)(sizeof(EikGeom) / 4); i += blockDim.x) reinterpret_cast<int*>(&G)[i] = reinterpret_cast<const int*>(gp)[i];
+    if (threadIdx.x == 0) s_min = 0x7f7fffff;
+    __syncthreads();
+    const int nn = G.fnx * G.fny;
+    float* Sc = S + G.node_off;
+    int mymin = 0x7f7fffff;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nn; c += gridDim.x * blockDim.x) {
+        const int iy = c / G.fnx + 1, ix = c - (iy - 1) * G.fnx + 1;
+        float pt[3];
+        eik_fine_point(G, ix, iy, pt);
+        const float d[3] = {pt[0] - G.center[0], pt[1] - G.center[1], pt[2] - G.center[2]};
+        float dd = 0.f;
+        for (int i = 0; i < 3; i++) dd = dd + d[i] * d[i];
+        bool inside = !(sqrtf(dd) > G.radius);
+        for (int k = 0; k < G.ncons && inside; k++) {   // point_in_halfspace geometry.f90:57-71
+            const float v[3] = {G.cpoint[k][0] - pt[0], G.cpoint[k][1] - pt[1], G.cpoint[k][2] - pt[2]};
+            float a = 0.f;
+            for (int i = 0; i < 3; i++) a = a + G.cnormal[k][i] * v[i];
+            inside = a >= 0.f;
+        }
+        float sp = 0.f;
+        if (inside) {   // crust2x2_get_at_depth crust2x2.f90:160-193
+            float vs = G.vs[5];
+            for (int l = 0; l < 5; l++) if (G.thr[l] >= pt[2]) { vs = G.vs[l]; break; }
+            sp = vs * G.relv;
+            mymin = min(mymin, __float_as_int(sp));       // (positive floats order like their bit patterns)
+        }
+        Sc[c] = sp;
+    }
+    atomicMin(&s_min, mymin);
+    __syncthreads();
+    if (threadIdx.x == 0) atomicMin(&gp->minspeed_bits, s_min);
+}
+
+// down-sampling: one thread per sub-fault (coarse cell) walks the fine points that can fall into it, in fine-grid order (iy outer, ix
+// inner: the order in which the reference adds them up), twice: means, then durations.  blockIdx.y = candidate.
+// coarse output per cell: ntimes, mean time (-1 = no point), duration, mean north / east / depth
+__global__ void __launch_bounds__(128) k_eik_down(const EikGeom* __restrict__ geoms, const float* __restrict__ S, const float* __restrict__ T,
+                                                  float* __restrict__ coarse) {
+    __shared__ EikGeom G;
+    for (int i = threadIdx.x; i < (int)(sizeof(EikGeom) / 4); i += blockDim.x) reinterpret_cast<int*>(&G)[i] = reinterpret_cast<const int*>(geoms + blockIdx.y)[i];
+    __syncthreads();
+    const int nc = G.nxc * G.nyc;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nc) return;
+    const int iyc = k / G.nxc + 1, ixc = k - (iyc - 1) * G.nxc + 1;
+    const float* Sc = S + G.node_off;
+    const float* Tc = T + G.node_off;
+    // fine points that can map into this cell: two fine cells of slack on either side (the mapping goes through a rotation and back)
+    const float rx = G.cdelta[0] / G.delta[0], ry = G.cdelta[1] / G.delta[1];
+    const int ix_lo = max(1, (int)floorf((float)(ixc - 1) * rx) - 2), ix_hi = min(G.fnx, (int)ceilf((float)ixc * rx) + 3);
+    const int iy_lo = max(1, (int)floorf((float)(iyc - 1) * ry) - 2), iy_hi = min(G.fny, (int)ceilf((float)iyc * ry) + 3);
+    float ntimes = 0.f, ctimes = -1.f, cspeed = 0.f, cp[3] = {0.f, 0.f, 0.f};
+    auto mine = [&](int ix, int iy, int c, float pt[3]) -> bool {
+        if (Sc[c] == G.invalid_speed) return false;         // time set to -1 by the reference (:513-515)
+        eik_fine_point(G, ix, iy, pt);
+        float rc[3];
+        eik_ned_to_rc(G, pt, rc);
+        const int jx = (int)floorf((rc[0] - G.first[0]) / G.cdelta[0]) + 1, jy = (int)floorf((rc[1] - G.first[1]) / G.cdelta[1]) + 1;
+        return jx == ixc && jy == iyc;
+    };
+    for (int iy = iy_lo; iy <= iy_hi; iy++)
+        for (int ix = ix_lo; ix <= ix_hi; ix++) {
+            const int c = (iy - 1) * G.fnx + (ix - 1);
+            float pt[3];
+            if (!mine(ix, iy, c, pt)) continue;
+            ntimes = ntimes + 1.f;
+            if (ctimes == -1.f) ctimes = 0.f;
+            ctimes = ctimes + Tc[c];
+            cspeed = cspeed + 1.f / Sc[c];
+            for (int q = 0; q < 3; q++) cp[q] = cp[q] + pt[q];
+        }
+    float cdur = 0.f;
+    if (ntimes > 0.f) {
+        ctimes = 1.f / ntimes * ctimes;
+        for (int q = 0; q < 3; q++) cp[q] = 1.f / ntimes * cp[q];
+        for (int iy = iy_lo; iy <= iy_hi; iy++)
+            for (int ix = ix_lo; ix <= ix_hi; ix++) {
+                const int c = (iy - 1) * G.fnx + (ix - 1);
+                float pt[3];
+                if (!mine(ix, iy, c, pt)) continue;
+                cdur = cdur + fabsf(Tc[c] - ctimes);
+            }
+        cdur = 4.f / ntimes * cdur;
+    }
+    (void)cspeed;
+    float* o = coarse + G.coarse_off + (size_t)6 * k;
+    o[0] = ntimes; o[1] = ctimes; o[2] = cdur; o[3] = cp[0]; o[4] = cp[1]; o[5] = cp[2];
+}
+
+cudaError_t launch_eik_speed(EikGeom* d_geoms, int ncand, int max_nodes, float* S, cudaStream_t st) {
+    if (ncand <= 0) return cudaSuccess;
+    const int bx = std::max(1, std::min((max_nodes + 255) / 256, 64));
+    k_eik_speed<<<dim3(bx, ncand), 256, 0, st>>>(d_geoms, S);
+    return cudaGetLastError();
+}
+cudaError_t launch_eik_down(const EikGeom* d_geoms, int ncand, int max_cells, const float* S, const float* T, float* coarse, cudaStream_t st) {
+    if (ncand <= 0) return cudaSuccess;
+    k_eik_down<<<dim3((max_cells + 127) / 128, ncand), 128, 0, st>>>(d_geoms, S, T, coarse);
+    return cudaGetLastError();
+}
+
 int eikonal_heap_smem_entries() { return EIK_HCAP; }
 cudaError_t launch_eikonal_fmm(const EikJob* d_jobs, int njobs, cudaStream_t st) {
     if (njobs <= 0) return cudaSuccess;
@@ -290,7 +424,7 @@ extern "C" int kiwi_eikonal_fmm_device(int njobs, const int* nx, const int* ny, 
         EikJob& J = jobs[j];
         J.nx = nx[j]; J.ny = ny[j]; J.dx = delta2[2 * j]; J.dy = delta2[2 * j + 1];
         eikonal_start_node(origin2 + 2 * j, delta2 + 2 * j, initialpoint2 + 2 * j, J.nx, J.ny, &J.ix0, &J.iy0);
-        J.S = dS; J.T = dT; J.bp = dbp; J.ovf = dovf;
+        J.S = dS; J.T = dT; J.bp = dbp; J.ovf = dovf; J.invalid_speed = 0.f;
     }
     EikJob* djobs = nullptr;
     if (cudaMalloc(&djobs, sizeof(EikJob) * njobs) != cudaSuccess) return fail("out of device memory");

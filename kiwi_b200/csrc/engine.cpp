@@ -140,7 +140,7 @@ struct kiwi_ctx {
     DevBuf d_gm;                  // ground-motion values [cand][rcv][3]
     DevBuf d_xcorr;               // cross-correlations [rcv][component][shift] (autoshift_ref_seismogram)
     bool dedup_enabled = true;               // candidates that differ only in the moment share one synthesis
-    DevBuf d_eik_s, d_eik_t, d_eik_bp, d_eik_ovf, d_eik_jobs;   // fast-marching solves of a wave of eikonal candidates
+    DevBuf d_eik_s, d_eik_t, d_eik_bp, d_eik_ovf, d_eik_jobs, d_eik_geoms, d_eik_coarse;   // fast-marching solves of a wave of eikonal candidates
     DevBuf d_mtlocs, d_mts, d_candof, d_orc, d_orw, d_obw, d_oout, d_obest, d_obestv;
     int last_eval_ns = 0;                    // candidates whose misfit block sits in d_out (kiwi_eval_sources)
     // description of the last chunk evaluated (inspection entry points, accounting)
@@ -307,8 +307,10 @@ int prep_candidate(kiwi_ctx* c, int sourcetype, const float* p, float effective_
 // sequential by construction) run on the device, one warp per candidate (csrc/eikonal.cu: the host solver's results bit for bit),
 // between the two host parts of the discretiser, which are spread over the host cores.  One solve is ~25 x slower on the device than
 // on a host core (2.5 us against 0.1 us per node) but up to 1924 of them run side by side.
-// `share`: true = the engine decides which solves go to the device (the small grids, as long as their wave ends before the host threads
+// `share`: true = the engine decides which candidates go to the device (the small grids, as long as their wave ends before the host threads
 // are through with the large ones -- they run at the same time); false = all of them.
+// A candidate that goes to the device does all of its fine-grid work there (speed field k_eik_speed, solve k_eikonal_fmm, down-sampling
+// k_eik_down): only its geometry goes up and its sub-fault table comes down.  The others take the host path as before.
 int prep_eikonal_batch_device(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* params, std::vector<kh::SourcePrep>& prep,
                               std::vector<int>& bad, std::vector<std::string>& errs, bool share) {
     const bool mt = sourcetype == KIWI_SOURCE_MT_EIKONAL;
@@ -323,98 +325,149 @@ int prep_eikonal_batch_device(kiwi_ctx* c, int sourcetype, int n, int nparams, c
         for (int t = 0; t < nt; t++) pool.emplace_back([&]() { for (size_t k = next.fetch_add(1); k < items.size(); k = next.fetch_add(1)) body(items[k]); });
         for (std::thread& t : pool) t.join();
     };
-    std::vector<int> all(n);
-    for (int i = 0; i < n; i++) all[i] = i;
-    parallel_over(all, [&](int i) {
-        bad[i] = kh::prep_eikonal_begin(params + (size_t)i * nparams, mt, c->effective_dt, c->olat, c->olon, c->crust, c->constraints, &works[i], &eps[i]) ? 0 : 1;
+    for (int i = 0; i < n; i++) {   // geometry of the fine grids (cheap)
+        bad[i] = kh::prep_eikonal_setup(params + (size_t)i * nparams, mt, c->effective_dt, c->olat, c->olon, c->crust, c->constraints, &works[i], &eps[i]) ? 0 : 1;
         if (bad[i]) errs[i] = eps[i].err;
-    });
+        if (!bad[i] && c->constraints.size() > 4) { bad[i] = 1; errs[i] = "more than four constraints"; }
+    }
+    auto nodes_of = [&](int i) { return (size_t)works[i].fnx * works[i].fny; };
     std::vector<int> order;      // valid candidates, small grids first
     for (int i = 0; i < n; i++) if (!bad[i]) order.push_back(i);
-    std::sort(order.begin(), order.end(), [&](int a, int b) { return works[a].speed.size() < works[b].speed.size(); });
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return nodes_of(a) < nodes_of(b); });
     size_t fr = 0, tot = 0;
     CU_OK(cudaMemGetInfo(&fr, &tot));
     const size_t wave_nodes = std::max<size_t>((size_t)1 << 22, std::min<size_t>(fr / 3, (size_t)24 << 30) / 20);   // 20 bytes per node on the device
     const int wave_jobs = 148 * 13;                                                                                  // solves resident at a time
-    // ---- which solves go to the device -----------------------------------------------------------------------------
-    // measured rates (profiles/r02_eikonal_device.txt): a warp 2.1-2.5 us per node (1 to 1036 solves resident), a host core 0.1 us per node for the solve
-    // and 0.045 us for the down-sampling that follows; staging ~8 bytes per node at ~8 GB/s.  The device takes a prefix of the
-    // size-ordered list: its wave lasts as long as its largest grid.
+    // ---- which candidates go to the device -----------------------------------------------------------------------------
+    // measured rates (profiles/r02_eikonal_device.txt): a warp 2.1-2.5 us per node (1 to 1036 solves resident), a host core 0.17 us per
+    // node for speed field + solve + down-sampling.  The device takes a prefix of the size-ordered list: its wave lasts as long as its
+    // largest grid.
     size_t ndev = order.size();
     if (share) {
-        const double dev_node = 2.4e-6, host_solve = 1.0e-7, host_finish = 0.45e-7, stage = 1.0e-9;
-        double all_solve = 0., all_finish = 0.;
-        for (int i : order) { all_solve += host_solve * works[i].speed.size(); all_finish += host_finish * works[i].speed.size(); }
-        double best = (all_solve + all_finish) / ncores, dev_solve = 0., dev_finish = 0., nodes = 0.;
+        const double dev_node = 2.4e-6, host_node = 1.7e-7;
+        double all_host = 0.;
+        for (int i : order) all_host += host_node * nodes_of(i);
+        double best = all_host / ncores, dev_host = 0., nodes = 0.;
         ndev = 0;
         for (size_t k = 0; k < order.size() && (int)k < wave_jobs; k++) {
-            const double nn = (double)works[order[k]].speed.size();
+            const double nn = (double)nodes_of(order[k]);
             nodes += nn;
             if (nodes > (double)wave_nodes) break;
-            dev_solve += host_solve * nn; dev_finish += host_finish * nn;
-            const double t_dev = dev_node * nn + stage * nodes;                                  // (nn = the largest grid so far)
-            const double t_host = (all_solve - dev_solve + all_finish - dev_finish) / ncores;   // the rest, solved and finished on the host meanwhile
-            const double total = std::max(t_dev, t_host) + dev_finish / ncores;
+            dev_host += host_node * nn;
+            const double total = std::max(dev_node * nn, (all_host - dev_host) / ncores);   // (nn = the largest grid so far)
             if (total < 0.97 * best) { best = total; ndev = k + 1; }
         }
     }
-    const int hcap = eikonal_heap_smem_entries();
     std::vector<int> host_items(order.begin() + ndev, order.end());
     std::reverse(host_items.begin(), host_items.end());      // long solves first
     auto host_part = [&]() {
         parallel_over(host_items, [&](int i) {
+            if (!kh::prep_eikonal_speed_host(&works[i], &eps[i])) { bad[i] = 1; errs[i] = eps[i].err; works[i] = kh::EikonalWork(); return; }
             kh::prep_eikonal_solve_host(&works[i]);
             if (!kh::prep_eikonal_finish(&works[i], &eps[i])) { bad[i] = 1; errs[i] = eps[i].err; }
             else eikonal_to_prep(eps[i], &prep[i]);
             works[i] = kh::EikonalWork();   // (the fine grids are 20 bytes per node: released as soon as they are done with)
         });
     };
+    const int hcap = eikonal_heap_smem_entries();
     bool host_done = false;
     size_t at = 0;
     while (at < ndev) {
         size_t nodes = 0, end = at;
-        while (end < ndev && (int)(end - at) < wave_jobs && (end == at || nodes + works[order[end]].speed.size() <= wave_nodes)) nodes += works[order[end++]].speed.size();
+        while (end < ndev && (int)(end - at) < wave_jobs && (end == at || nodes + nodes_of(order[end]) <= wave_nodes)) nodes += nodes_of(order[end++]);
         const int nj = (int)(end - at);
         CU_OK(c->d_eik_s.ensure(nodes * 4)); CU_OK(c->d_eik_t.ensure(nodes * 4)); CU_OK(c->d_eik_bp.ensure(nodes * 4));
         CU_OK(c->d_eik_ovf.ensure(nodes * sizeof(EikItem))); CU_OK(c->d_eik_jobs.ensure(sizeof(EikJob) * nj));
-        std::vector<EikJob> jobs(nj);
+        CU_OK(c->d_eik_geoms.ensure(sizeof(EikGeom) * nj));
+        // ---- geometry up, speed fields, smallest speeds down --------------------------------------------------------------
+        std::vector<EikGeom> geoms(nj);
         size_t off = 0;
+        int max_nodes = 1;
         for (int j = 0; j < nj; j++) {    // (largest grid of the wave first: it sets the wave's length)
-            kh::EikonalWork& w = works[order[end - 1 - j]];
-            const size_t nn = w.speed.size();
+            const kh::EikonalWork& w = works[order[end - 1 - j]];
+            EikGeom& G = geoms[j];
+            memset(&G, 0, sizeof G);
+            G.fnx = w.fnx; G.fny = w.fny;
+            for (int k = 0; k < 2; k++) { G.first[k] = w.first[k]; G.delta[k] = w.delta[k]; }
+            for (int k = 0; k < 3; k++) { G.shift[k] = w.p[1 + k]; G.center[k] = w.center[k]; }
+            memcpy(G.rot, w.rot_rup, sizeof G.rot);
+            G.radius = w.bord_radius; G.relv = w.relv;
+            G.ncons = (int)w.constraints->size();
+            for (int k = 0; k < G.ncons; k++) for (int q = 0; q < 3; q++) { G.cpoint[k][q] = (*w.constraints)[k].point[q]; G.cnormal[k][q] = (*w.constraints)[k].normal[q]; }
+            kh::eikonal_layer_table(w.profile, G.thr, G.vs);
+            G.node_off = off; G.minspeed_bits = 0x7f7fffff;
+            off += (size_t)w.fnx * w.fny;
+            max_nodes = std::max(max_nodes, w.fnx * w.fny);
+        }
+        CU_OK(cudaMemcpyAsync(c->d_eik_geoms.p, geoms.data(), sizeof(EikGeom) * nj, cudaMemcpyHostToDevice, c->stream));
+        cudaError_t e = launch_eik_speed(c->d_eik_geoms.as<EikGeom>(), nj, max_nodes, c->d_eik_s.as<float>(), c->stream);
+        if (e != cudaSuccess) return kiwi_set_error("CUDA error launching the speed-field kernel: %s", cudaGetErrorString(e));
+        std::vector<EikGeom> back(nj);
+        CU_OK(cudaMemcpyAsync(back.data(), c->d_eik_geoms.p, sizeof(EikGeom) * nj, cudaMemcpyDeviceToHost, c->stream));
+        CU_OK(cudaStreamSynchronize(c->stream));
+        // ---- coarse grids, solves, down-sampling ----------------------------------------------------------------------------------
+        std::vector<EikJob> jobs(nj);
+        std::vector<kh::EikonalCoarse> cgs(nj);
+        size_t coff = 0;
+        int max_cells = 1;
+        for (int j = 0; j < nj; j++) {
+            const int i = order[end - 1 - j];
+            kh::EikonalWork& w = works[i];
+            EikGeom& G = geoms[j];
+            float minspeed;
+            memcpy(&minspeed, &back[j].minspeed_bits, 4);
+            G.minspeed_bits = back[j].minspeed_bits;
+            w.minspeed = minspeed; w.invalid_speed = minspeed * 0.5f;
+            bool ok = true;
+            if (!(minspeed > 0.f) || back[j].minspeed_bits == 0x7f7fffff) { ok = false; errs[i] = "no valid point in the rupture area"; }
+            if (ok && !kh::prep_eikonal_coarse_dims(w, &cgs[j], &errs[i])) ok = false;
+            if (!ok) { bad[i] = 1; cgs[j].nxc = cgs[j].nyc = 0; w.invalid_speed = 1.f; }   // (solved all the same, result ignored)
+            G.nxc = cgs[j].nxc; G.nyc = cgs[j].nyc; G.cdelta[0] = cgs[j].cdelta[0]; G.cdelta[1] = cgs[j].cdelta[1];
+            G.invalid_speed = w.invalid_speed; G.coarse_off = coff;
+            coff += (size_t)6 * cgs[j].nxc * cgs[j].nyc;
+            max_cells = std::max(max_cells, cgs[j].nxc * cgs[j].nyc);
             EikJob& J = jobs[j];
+            const size_t nn = (size_t)w.fnx * w.fny;
             J.nx = w.fnx; J.ny = w.fny; J.dx = w.delta[0]; J.dy = w.delta[1];
             eikonal_start_node(w.first, w.delta, w.initialpoint, w.fnx, w.fny, &J.ix0, &J.iy0);
-            J.S = c->d_eik_s.as<float>() + off; J.T = c->d_eik_t.as<float>() + off; J.bp = c->d_eik_bp.as<int>() + off;
-            J.ovf = nn > (size_t)hcap ? c->d_eik_ovf.as<EikItem>() + off : nullptr;
-            CU_OK(cudaMemcpyAsync(c->d_eik_s.as<float>() + off, w.speed.data(), nn * 4, cudaMemcpyHostToDevice, c->stream));
-            off += nn;
+            J.S = c->d_eik_s.as<float>() + G.node_off; J.T = c->d_eik_t.as<float>() + G.node_off; J.bp = c->d_eik_bp.as<int>() + G.node_off;
+            J.ovf = nn > (size_t)hcap ? c->d_eik_ovf.as<EikItem>() + G.node_off : nullptr;
+            J.invalid_speed = w.invalid_speed;
         }
+        CU_OK(c->d_eik_coarse.ensure(sizeof(float) * std::max<size_t>(coff, 6)));
+        CU_OK(cudaMemcpyAsync(c->d_eik_geoms.p, geoms.data(), sizeof(EikGeom) * nj, cudaMemcpyHostToDevice, c->stream));
         CU_OK(cudaMemcpyAsync(c->d_eik_jobs.p, jobs.data(), sizeof(EikJob) * nj, cudaMemcpyHostToDevice, c->stream));
-        CU_OK(cudaStreamSynchronize(c->stream));   // (jobs is a stack-lifetime staging vector)
-        cudaError_t e = launch_eikonal_fmm(c->d_eik_jobs.as<EikJob>(), nj, c->stream);
+        CU_OK(cudaStreamSynchronize(c->stream));   // (geoms and jobs are stack-lifetime staging vectors)
+        e = launch_eikonal_fmm(c->d_eik_jobs.as<EikJob>(), nj, c->stream);
         if (e != cudaSuccess) return kiwi_set_error("CUDA error launching the fast-marching solver: %s", cudaGetErrorString(e));
-        c->launches[0] += 1;
+        e = launch_eik_down(c->d_eik_geoms.as<EikGeom>(), nj, max_cells, c->d_eik_s.as<float>(), c->d_eik_t.as<float>(), c->d_eik_coarse.as<float>(), c->stream);
+        if (e != cudaSuccess) return kiwi_set_error("CUDA error launching the down-sampling kernel: %s", cudaGetErrorString(e));
+        c->launches[0] += 3;
         if (!host_done) { host_part(); host_done = true; }   // the host threads work through their share while the wave runs
-        off = 0;
-        for (int j = 0; j < nj; j++) {
-            kh::EikonalWork& w = works[order[end - 1 - j]];
-            w.times.resize(w.speed.size());
-            CU_OK(cudaMemcpyAsync(w.times.data(), c->d_eik_t.as<float>() + off, w.speed.size() * 4, cudaMemcpyDeviceToHost, c->stream));
-            off += w.speed.size();
-        }
+        std::vector<float> coarse(std::max<size_t>(coff, 6));
+        CU_OK(cudaMemcpyAsync(coarse.data(), c->d_eik_coarse.p, sizeof(float) * coff, cudaMemcpyDeviceToHost, c->stream));
         CU_OK(cudaStreamSynchronize(c->stream));
         CU_OK(cudaGetLastError());
+        // ---- sub-fault tables of the wave ---------------------------------------------------------------------------------------------
+        std::vector<int> js(nj);
+        for (int j = 0; j < nj; j++) js[j] = j;
+        parallel_over(js, [&](int j) {
+            const int i = order[end - 1 - j];
+            if (bad[i]) return;
+            kh::EikonalCoarse& cg = cgs[j];
+            const size_t ncell = (size_t)cg.nxc * cg.nyc;
+            cg.ntimes.resize(ncell); cg.ctimes.resize(ncell); cg.cdur.resize(ncell); cg.cpoints.resize(3 * ncell);
+            const float* o = coarse.data() + geoms[j].coarse_off;
+            for (size_t k = 0; k < ncell; k++) {
+                cg.ntimes[k] = o[6 * k]; cg.ctimes[k] = o[6 * k + 1]; cg.cdur[k] = o[6 * k + 2];
+                cg.cpoints[3 * k] = o[6 * k + 3]; cg.cpoints[3 * k + 1] = o[6 * k + 4]; cg.cpoints[3 * k + 2] = o[6 * k + 5];
+            }
+            if (!kh::prep_eikonal_table(works[i], cg, &eps[i])) { bad[i] = 1; errs[i] = eps[i].err; }
+            else eikonal_to_prep(eps[i], &prep[i]);
+        });
         at = end;
     }
     if (!host_done) host_part();
-    std::vector<int> dev_items(order.begin(), order.begin() + ndev);
-    std::reverse(dev_items.begin(), dev_items.end());
-    parallel_over(dev_items, [&](int i) {
-        if (!kh::prep_eikonal_finish(&works[i], &eps[i])) { bad[i] = 1; errs[i] = eps[i].err; }
-        else eikonal_to_prep(eps[i], &prep[i]);
-        works[i] = kh::EikonalWork();
-    });
     c->eikonal_last_device_solves = (int)ndev;
     return 0;
 }
@@ -1239,7 +1292,7 @@ void kiwi_destroy(kiwi_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->d_slabs, &c->d_nodes, &c->d_tspan, &c->d_nspan, &c->d_rcv, &c->d_refdata, &c->d_taper, &c->d_cands, &c->d_bilat, &c->d_gf, &c->d_gi,
-                      &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift, &c->d_map, &c->d_status_out, &c->d_taprec, &c->d_partial, &c->d_fftz, &c->d_gm, &c->d_xcorr, &c->d_eik_s, &c->d_eik_t, &c->d_eik_bp, &c->d_eik_ovf, &c->d_eik_jobs, &c->d_mtlocs, &c->d_mts, &c->d_candof, &c->d_orc, &c->d_orw, &c->d_obw, &c->d_oout, &c->d_obest, &c->d_obestv})
+                      &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift, &c->d_map, &c->d_status_out, &c->d_taprec, &c->d_partial, &c->d_fftz, &c->d_gm, &c->d_xcorr, &c->d_eik_s, &c->d_eik_t, &c->d_eik_bp, &c->d_eik_ovf, &c->d_eik_jobs, &c->d_eik_geoms, &c->d_eik_coarse, &c->d_mtlocs, &c->d_mts, &c->d_candof, &c->d_orc, &c->d_orw, &c->d_obw, &c->d_oout, &c->d_obest, &c->d_obestv})
         b->release();
     c->h_stage.release(); c->h_out.release(); c->h_mt.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);

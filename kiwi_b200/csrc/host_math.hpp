@@ -71,7 +71,24 @@ struct EikonalWork {
     int fnx = 0, fny = 0;
     float minspeed = 0.f, invalid_speed = 0.f;
     std::vector<float> speed, times, points;     // fine grid (fnx, fny), ix fastest; points: north, east, depth per node
+    // what the speed field of the fine grid is made from (psm_make_eikonal_grid)
+    float center[3] = {0, 0, 0}, bord_radius = 0.f, relv = 0.f;
+    CrustProfile profile;
+    const std::vector<Halfspace>* constraints = nullptr;
 };
+// the down-sampled grid (psm_downsample_grid): per sub-fault the number of fine points, mean rupture time, mean position, duration
+struct EikonalCoarse {
+    int nxc = 0, nyc = 0;
+    float cdelta[2] = {0, 0};
+    std::vector<float> ntimes, ctimes, cpoints, cdur;
+};
+bool prep_eikonal_setup(const float* params, bool mt_variant, float shortest_doi, double olat_rad, double olon_rad, const Crust2x2& crust,
+                        const std::vector<Halfspace>& constraints, EikonalWork* work, EikonalPrep* out);   // geometry only
+bool prep_eikonal_speed_host(EikonalWork* work, EikonalPrep* out);                                        // speed field of the fine grid
+void eikonal_layer_table(const CrustProfile& p, float thr[5], float vs[6]);
+bool prep_eikonal_coarse_dims(const EikonalWork& w, EikonalCoarse* cg, std::string* err);
+void prep_eikonal_downsample_host(EikonalWork* work, EikonalCoarse* cg);
+bool prep_eikonal_table(const EikonalWork& w, const EikonalCoarse& cg, EikonalPrep* out);
 bool prep_eikonal_begin(const float* params, bool mt_variant, float shortest_doi, double olat_rad, double olon_rad, const Crust2x2& crust,
                         const std::vector<Halfspace>& constraints, EikonalWork* work, EikonalPrep* out);
 void prep_eikonal_solve_host(EikonalWork* work);

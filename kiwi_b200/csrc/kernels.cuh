@@ -74,7 +74,27 @@ struct EikJob {
     float* T;
     int* bp;
     EikItem* ovf;           // heap entries beyond eikonal_heap_smem_entries(): room for nx*ny - that many, or null if none are needed
+    float invalid_speed;    // > 0: nodes of speed 0 (outside the rupture area, k_eik_speed) are given this speed first (source_eikonal.f90:497-507)
 };
+// the fine grid of one eikonal candidate as the device sees it (psm_make_eikonal_grid / psm_downsample_grid, source_eikonal.f90:435-601)
+struct EikGeom {
+    int fnx, fny;
+    float first[2], delta[2];
+    float shift[3];         // north, east, depth of the source (params 2..4)
+    float rot[9];           // rotmat_rup, row-major
+    float center[3], radius, relv;
+    int ncons;
+    float cpoint[4][3], cnormal[4][3];   // half-spaces the rupture area is clipped to (parameterized_source.f90:127-181)
+    float thr[5], vs[6];    // crust2x2_get_at_depth as a table (eikonal_layer_table)
+    unsigned long long node_off;         // the candidate's nodes in the S / T arenas
+    int minspeed_bits;      // written by k_eik_speed: bits of the smallest rupture speed inside the area (0x7f7fffff = none)
+    // set by the host once the smallest speed is known
+    int nxc, nyc;
+    float cdelta[2], invalid_speed;
+    unsigned long long coarse_off;       // the candidate's cells in the coarse output arena (6 floats per cell)
+};
+cudaError_t launch_eik_speed(EikGeom* d_geoms, int ncand, int max_nodes, float* S, cudaStream_t st);
+cudaError_t launch_eik_down(const EikGeom* d_geoms, int ncand, int max_cells, const float* S, const float* T, float* coarse, cudaStream_t st);
 int eikonal_heap_smem_entries();
 void eikonal_start_node(const float origin[2], const float delta[2], const float initialpoint[2], int nx, int ny, int* ix0, int* iy0);
 cudaError_t launch_eikonal_fmm(const EikJob* d_jobs, int njobs, cudaStream_t st);

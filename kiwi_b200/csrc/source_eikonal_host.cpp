@@ -367,7 +367,7 @@ static Psm psm_of(const EikonalWork& w) {
     return s;
 }
 
-bool prep_eikonal_begin(const float* p, bool mt_variant, float shortest_doi, double olat_rad, double olon_rad, const Crust2x2& crust,
+bool prep_eikonal_setup(const float* p, bool mt_variant, float shortest_doi, double olat_rad, double olon_rad, const Crust2x2& crust,
                         const std::vector<Halfspace>& constraints, EikonalWork* work, EikonalPrep* out) {
     EikonalPrep& o = *out;
     o = EikonalPrep();
@@ -429,8 +429,6 @@ bool prep_eikonal_begin(const float* p, bool mt_variant, float shortest_doi, dou
     if (nd[0] < 0 || nd[1] < 0 || (long long)nd[0] * nd[1] > 4000000LL) { o.err = "eikonal grid too large"; return false; }
     float delta[2] = {dims[0] / (float)nd[0], dims[1] / (float)nd[1]};
     const int fnx = nd[0], fny = nd[1];
-    std::vector<float>&speed = w.speed, &points = w.points;
-    speed.assign((size_t)fnx * fny, 0.f); points.assign((size_t)3 * fnx * fny, 0.f);
     // crust2x2_get_profile(psm%origin): the origin is in RADIANS here (source_eikonal.f90:472), kept as is
     const CrustProfile profile = crust2x2_get_profile(crust, (float)olat_rad, (float)olon_rad);
     // psm_initial_point_intolerant_rc :401-432
@@ -446,6 +444,28 @@ bool prep_eikonal_begin(const float* p, bool mt_variant, float shortest_doi, dou
         }
     }
     const float initialpoint[2] = {nukl_shift_x, nukl_shift_y};
+    w.p = p; memcpy(w.rot_rup, s.rot_rup, sizeof w.rot_rup);
+    w.idx[0] = s.i_bsx; w.idx[1] = s.i_bsy; w.idx[2] = s.i_brad; w.idx[3] = s.i_nsx; w.idx[4] = s.i_nsy; w.idx[5] = s.i_relv;
+    w.mt_variant = mt_variant; w.shortest_doi = shortest_doi;
+    for (int k = 0; k < 2; k++) { w.first[k] = first[k]; w.last[k] = last[k]; w.delta[k] = delta[k]; w.initialpoint[k] = initialpoint[k]; }
+    w.fnx = fnx; w.fny = fny;
+    memcpy(w.center, center, sizeof w.center); w.bord_radius = bord_radius; w.relv = rel_rupture_velocity;
+    w.profile = profile; w.constraints = &constraints;
+    return true;
+}
+
+// psm_make_eikonal_grid :435-517, the loop over the fine grid: positions, rupture speed, slow rim
+bool prep_eikonal_speed_host(EikonalWork* work, EikonalPrep* out) {
+    EikonalPrep& o = *out;
+    EikonalWork& w = *work;
+    const Psm s = psm_of(w);
+    const int fnx = w.fnx, fny = w.fny;
+    const float* first = w.first; const float* delta = w.delta; const float* center = w.center;
+    const float bord_radius = w.bord_radius, rel_rupture_velocity = w.relv;
+    const std::vector<Halfspace>& constraints = *w.constraints;
+    const CrustProfile& profile = w.profile;
+    std::vector<float>&speed = w.speed, &points = w.points;
+    speed.assign((size_t)fnx * fny, 0.f); points.assign((size_t)3 * fnx * fny, 0.f);
     float minspeed = std::numeric_limits<float>::max();
     for (int iy = 1; iy <= fny; iy++)
         for (int ix = 1; ix <= fnx; ix++) {
@@ -466,12 +486,20 @@ bool prep_eikonal_begin(const float* p, bool mt_variant, float shortest_doi, dou
     const float invalid_speed = minspeed * 0.5f;
     for (float& v : speed) if (v == 0.f) v = invalid_speed;
     if (!(minspeed > 0.f) || minspeed == std::numeric_limits<float>::max()) { o.err = "no valid point in the rupture area"; return false; }
-    w.p = p; memcpy(w.rot_rup, s.rot_rup, sizeof w.rot_rup);
-    w.idx[0] = s.i_bsx; w.idx[1] = s.i_bsy; w.idx[2] = s.i_brad; w.idx[3] = s.i_nsx; w.idx[4] = s.i_nsy; w.idx[5] = s.i_relv;
-    w.mt_variant = mt_variant; w.shortest_doi = shortest_doi;
-    for (int k = 0; k < 2; k++) { w.first[k] = first[k]; w.last[k] = last[k]; w.delta[k] = delta[k]; w.initialpoint[k] = initialpoint[k]; }
-    w.fnx = fnx; w.fny = fny; w.minspeed = minspeed; w.invalid_speed = invalid_speed;
+    w.minspeed = minspeed; w.invalid_speed = invalid_speed;
     return true;
+}
+
+bool prep_eikonal_begin(const float* p, bool mt_variant, float shortest_doi, double olat_rad, double olon_rad, const Crust2x2& crust,
+                        const std::vector<Halfspace>& constraints, EikonalWork* work, EikonalPrep* out) {
+    return prep_eikonal_setup(p, mt_variant, shortest_doi, olat_rad, olon_rad, crust, constraints, work, out) && prep_eikonal_speed_host(work, out);
+}
+
+// crust2x2_get_at_depth as a table for the device (csrc/eikonal.cu): cumulative thickness of the layers it walks and their vs
+void eikonal_layer_table(const CrustProfile& p, float thr[5], float vs[6]) {
+    float d = 0.f;
+    for (int i = 2; i < NLAYERS; i++) { d = d + p.thickness[i]; thr[i - 2] = d; vs[i - 2] = p.vs[i]; }
+    vs[5] = p.vs[LBELOWCRUST];
 }
 
 void prep_eikonal_solve_host(EikonalWork* work) {
@@ -480,36 +508,40 @@ void prep_eikonal_solve_host(EikonalWork* work) {
     eikonal_solver_fmm(w.speed.data(), w.fnx, w.fny, w.first, w.delta, w.initialpoint, w.times.data());
 }
 
-bool prep_eikonal_finish(EikonalWork* work, EikonalPrep* out) {
-    EikonalPrep& o = *out;
-    EikonalWork& w = *work;
-    const Psm s = psm_of(w);
-    const float* p = w.p;
-    const bool mt_variant = w.mt_variant;
-    const float shortest_doi = w.shortest_doi, minspeed = w.minspeed, invalid_speed = w.invalid_speed;
+// coarse grid size source_eikonal.f90:274-277, 617-638
+bool prep_eikonal_coarse_dims(const EikonalWork& w, EikonalCoarse* cg, std::string* err) {
     const float* first = w.first; const float* last = w.last;
-    const float* rot_slip = w.rot_slip;
-    std::vector<float>&speed = w.speed, &times = w.times, &points = w.points;
-    for (size_t c = 0; c < speed.size(); c++) if (speed[c] == invalid_speed) times[c] = -1.f;
-    // ---- coarse grid size :274-277, 617-638 ------------------------------------------------------------------
-    const float maxdt = shortest_doi;
-    const float maxdx = 0.5f * shortest_doi * minspeed, maxdy = 0.5f * shortest_doi * minspeed;
+    const float maxdx = 0.5f * w.shortest_doi * w.minspeed, maxdy = 0.5f * w.shortest_doi * w.minspeed;
     const float sizex = last[0] - first[0], sizey = last[1] - first[1];
     const float fx = sizex / maxdx, fy = sizey / maxdy;
-    if (!(fabsf(fx) < 1e5f) || !(fabsf(fy) < 1e5f)) { o.err = "sub-fault grid too large"; return false; }
+    if (!(fabsf(fx) < 1e5f) || !(fabsf(fy) < 1e5f)) { *err = "sub-fault grid too large"; return false; }
     int nxc = (int)floorf(fx) + 1;
     if (nxc <= 1) nxc = 2;
     if (sizex == 0.f) nxc = 1;
     int nyc = (int)floorf(fy) + 1;
     if (nyc <= 1) nyc = 2;
     if (sizey == 0.f) nyc = 1;
-    // ---- psm_downsample_grid :519-601 ----------------------------------------------------------------------
-    float cdelta[2] = {(last[0] - first[0]) / (float)nxc, (last[1] - first[1]) / (float)nyc};
-    if (cdelta[0] == 0.f || nxc == 0) cdelta[0] = 1.f;
-    if (cdelta[1] == 0.f || nyc == 0) cdelta[1] = 1.f;
+    cg->nxc = nxc; cg->nyc = nyc;
+    cg->cdelta[0] = (last[0] - first[0]) / (float)nxc; cg->cdelta[1] = (last[1] - first[1]) / (float)nyc;
+    if (cg->cdelta[0] == 0.f || nxc == 0) cg->cdelta[0] = 1.f;
+    if (cg->cdelta[1] == 0.f || nyc == 0) cg->cdelta[1] = 1.f;
+    return true;
+}
+
+// psm_downsample_grid :519-601 (sums per coarse cell in fine-grid order); times < 0 = outside the rupture area
+void prep_eikonal_downsample_host(EikonalWork* work, EikonalCoarse* cgp) {
+    EikonalWork& w = *work;
+    EikonalCoarse& cg = *cgp;
+    const Psm s = psm_of(w);
+    const float* first = w.first;
+    const float* cdelta = cg.cdelta;
+    const int nxc = cg.nxc, nyc = cg.nyc;
+    std::vector<float>&speed = w.speed, &times = w.times, &points = w.points;
+    for (size_t c = 0; c < speed.size(); c++) if (speed[c] == w.invalid_speed) times[c] = -1.f;
     const size_t nc = (size_t)nxc * nyc;
-    std::vector<float> ntimes(nc, 0.f), ctimes(nc, -1.f), cspeed(nc, 0.f), cpoints(3 * nc, 0.f), cdur(nc, 0.f), cweights(nc, 0.f);
-    int npf = 0;
+    std::vector<float>&ntimes = cg.ntimes, &ctimes = cg.ctimes, &cpoints = cg.cpoints, &cdur = cg.cdur;
+    ntimes.assign(nc, 0.f); ctimes.assign(nc, -1.f); cpoints.assign(3 * nc, 0.f); cdur.assign(nc, 0.f);
+    std::vector<float> cspeed(nc, 0.f);
     auto coarse_cell = [&](size_t c, int* ixc, int* iyc) {
         float rc[3];
         ned_to_rc(s, &points[3 * c], rc);
@@ -529,7 +561,6 @@ bool prep_eikonal_finish(EikonalWork* work, EikonalPrep* out) {
         ctimes[k] = ctimes[k] + times[c];
         cspeed[k] = cspeed[k] + 1.f / speed[c];
         for (int q = 0; q < 3; q++) cpoints[3 * k + q] = cpoints[3 * k + q] + points[3 * c + q];
-        npf = npf + 1;
     }
     for (size_t k = 0; k < nc; k++)
         if (ntimes[k] > 0.f) {
@@ -537,13 +568,28 @@ bool prep_eikonal_finish(EikonalWork* work, EikonalPrep* out) {
             cspeed[k] = 1.f / (1.f / ntimes[k] * cspeed[k]);
             for (int q = 0; q < 3; q++) cpoints[3 * k + q] = 1.f / ntimes[k] * cpoints[3 * k + q];
         }
-    for (size_t k = 0; k < nc; k++) cweights[k] = ntimes[k] / (float)npf;
     for (size_t c = 0; c < speed.size(); c++) {
         if (cell_of[c] < 0) continue;
         const size_t k = (size_t)cell_of[c];
         cdur[k] = cdur[k] + fabsf(times[c] - ctimes[k]);
     }
     for (size_t k = 0; k < nc; k++) if (ntimes[k] > 0.f) cdur[k] = 4.f / ntimes[k] * cdur[k];
+}
+
+// weights of the sub-faults and psm_to_tdsm_table_eikonal :640-712, from the down-sampled grid
+bool prep_eikonal_table(const EikonalWork& w, const EikonalCoarse& cg, EikonalPrep* out) {
+    EikonalPrep& o = *out;
+    const float* p = w.p;
+    const bool mt_variant = w.mt_variant;
+    const float* rot_slip = w.rot_slip;
+    const float maxdt = w.shortest_doi;
+    const int nxc = cg.nxc, nyc = cg.nyc;
+    const size_t nc = (size_t)nxc * nyc;
+    const std::vector<float>&ntimes = cg.ntimes, &ctimes = cg.ctimes, &cpoints = cg.cpoints, &cdur = cg.cdur;
+    int npf = 0;
+    for (size_t k = 0; k < nc; k++) npf = npf + (int)ntimes[k];   // (the reference counts the fine points as it goes: an exact integer either way)
+    std::vector<float> cweights(nc, 0.f);
+    for (size_t k = 0; k < nc; k++) cweights[k] = ntimes[k] / (float)npf;
     // ---- psm_to_tdsm_table_eikonal :640-712 ----------------------------------------------------------------------
     const float origin_time = p[0];
     float centertime = 0.f;
@@ -585,6 +631,13 @@ bool prep_eikonal_finish(EikonalWork* work, EikonalPrep* out) {
     o.nx = nxc; o.ny = nyc;
     if (o.groups.empty()) { o.err = "Empty rupture area"; return false; }
     return true;
+}
+
+bool prep_eikonal_finish(EikonalWork* work, EikonalPrep* out) {
+    EikonalCoarse cg;
+    if (!prep_eikonal_coarse_dims(*work, &cg, &out->err)) return false;
+    prep_eikonal_downsample_host(work, &cg);
+    return prep_eikonal_table(*work, cg, out);
 }
 
 bool prep_eikonal(const float* p, bool mt_variant, float shortest_doi, double olat_rad, double olon_rad, const Crust2x2& crust,
