@@ -341,7 +341,8 @@ __global__ void __launch_bounds__(128) k_eik_down(const EikGeom* __restrict__ ge
     const int iy_lo = max(1, (int)floorf((float)(iyc - 1) * ry) - 2), iy_hi = min(G.fny, (int)ceilf((float)iyc * ry) + 3);
     float ntimes = 0.f, ctimes = -1.f, cspeed = 0.f, cp[3] = {0.f, 0.f, 0.f};
     auto mine = [&](int ix, int iy, int c, float pt[3]) -> bool {
-        if (Sc[c] == G.invalid_speed) return false;         // time set to -1 by the reference (:513-515)
+        if (Sc[c] == G.invalid_speed || Sc[c] == 0.f) return false;   // outside the rupture area: time set to -1 by the reference (:513-515);
+                                                                       // (0: a candidate solved on the host, whose device copy was never filled)
         eik_fine_point(G, ix, iy, pt);
         float rc[3];
         eik_ned_to_rc(G, pt, rc);

@@ -114,7 +114,7 @@ struct kiwi_ctx {
     DevBuf d_cands, d_bilat, d_gf, d_gi, d_tf, d_recs, d_hdrs, d_seis, d_shdrs, d_out, d_status, d_tmax, d_table, d_tw, d_fshift;
     int tw_n = 0;                            // twiddle table exp(-2 pi i k / tw_n), k < tw_n/2
     std::vector<int> last_fshift;            // floating shifts of the last ns = 1 evaluation
-    PinBuf h_stage, h_out, h_mt;
+    PinBuf h_stage, h_out, h_mt, h_eik;
     size_t work_budget = 0;
     kh::Crust2x2 crust;                      // crust2x2 model (minimizer.f90:1669-1674), needed by the eikonal sources
     std::vector<kh::Halfspace> constraints;  // psm%constraints (parameterized_source.f90:127-166)
@@ -307,22 +307,22 @@ int prep_candidate(kiwi_ctx* c, int sourcetype, const float* p, float effective_
 // sequential by construction) run on the device, one warp per candidate (csrc/eikonal.cu: the host solver's results bit for bit),
 // between the two host parts of the discretiser, which are spread over the host cores.  One solve is ~25 x slower on the device than
 // on a host core (2.5 us against 0.1 us per node) but up to 1924 of them run side by side.
-// `share`: true = the engine decides which candidates go to the device (the small grids, as long as their wave ends before the host threads
+// `share`: true = the engine decides which solves go to the device (the small grids, as long as their wave ends before the host threads
 // are through with the large ones -- they run at the same time); false = all of them.
-// A candidate that goes to the device does all of its fine-grid work there (speed field k_eik_speed, solve k_eikonal_fmm, down-sampling
-// k_eik_down): only its geometry goes up and its sub-fault table comes down.  The others take the host path as before.
+// The rest of the fine-grid work of EVERY candidate runs on the device: the speed field before the solve (k_eik_speed) and the
+// down-sampling after it (k_eik_down).  A candidate solved on the device sends its geometry up and gets its sub-fault table back; one
+// solved on the host gets its speed field through page-locked memory, solves (kh::eikonal_solver_fmm) and sends the times back.
 int prep_eikonal_batch_device(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* params, std::vector<kh::SourcePrep>& prep,
                               std::vector<int>& bad, std::vector<std::string>& errs, bool share) {
     const bool mt = sourcetype == KIWI_SOURCE_MT_EIKONAL;
     std::vector<kh::EikonalWork> works(n);
     std::vector<kh::EikonalPrep> eps(n);
     const int ncores = (int)std::max(1u, std::thread::hardware_concurrency());
-    const int nthreads = std::min(n, ncores);
-    auto parallel_over = [&](const std::vector<int>& items, const std::function<void(int)>& body) {
+    auto parallel_over = [&](size_t count, const std::function<void(size_t)>& body) {
         std::atomic<size_t> next(0);
         std::vector<std::thread> pool;
-        const int nt = (int)std::min<size_t>(items.size(), (size_t)nthreads);
-        for (int t = 0; t < nt; t++) pool.emplace_back([&]() { for (size_t k = next.fetch_add(1); k < items.size(); k = next.fetch_add(1)) body(items[k]); });
+        const int nt = (int)std::min<size_t>(count, (size_t)ncores);
+        for (int t = 0; t < nt; t++) pool.emplace_back([&]() { for (size_t k = next.fetch_add(1); k < count; k = next.fetch_add(1)) body(k); });
         for (std::thread& t : pool) t.join();
     };
     for (int i = 0; i < n; i++) {   // geometry of the fine grids (cheap)
@@ -331,60 +331,57 @@ int prep_eikonal_batch_device(kiwi_ctx* c, int sourcetype, int n, int nparams, c
         if (!bad[i] && c->constraints.size() > 4) { bad[i] = 1; errs[i] = "more than four constraints"; }
     }
     auto nodes_of = [&](int i) { return (size_t)works[i].fnx * works[i].fny; };
-    std::vector<int> order;      // valid candidates, small grids first
-    for (int i = 0; i < n; i++) if (!bad[i]) order.push_back(i);
-    std::sort(order.begin(), order.end(), [&](int a, int b) { return nodes_of(a) < nodes_of(b); });
     size_t fr = 0, tot = 0;
     CU_OK(cudaMemGetInfo(&fr, &tot));
-    const size_t wave_nodes = std::max<size_t>((size_t)1 << 22, std::min<size_t>(fr / 3, (size_t)24 << 30) / 20);   // 20 bytes per node on the device
-    const int wave_jobs = 148 * 13;                                                                                  // solves resident at a time
-    // ---- which candidates go to the device -----------------------------------------------------------------------------
-    // measured rates (profiles/r02_eikonal_device.txt): a warp 2.1-2.5 us per node (1 to 1036 solves resident), a host core 0.17 us per
-    // node for speed field + solve + down-sampling.  The device takes a prefix of the size-ordered list: its wave lasts as long as its
-    // largest grid.
-    size_t ndev = order.size();
-    if (share) {
-        const double dev_node = 2.4e-6, host_node = 1.7e-7;
-        double all_host = 0.;
-        for (int i : order) all_host += host_node * nodes_of(i);
-        double best = all_host / ncores, dev_host = 0., nodes = 0.;
-        ndev = 0;
-        for (size_t k = 0; k < order.size() && (int)k < wave_jobs; k++) {
-            const double nn = (double)nodes_of(order[k]);
-            nodes += nn;
-            if (nodes > (double)wave_nodes) break;
-            dev_host += host_node * nn;
-            const double total = std::max(dev_node * nn, (all_host - dev_host) / ncores);   // (nn = the largest grid so far)
-            if (total < 0.97 * best) { best = total; ndev = k + 1; }
-        }
-    }
-    std::vector<int> host_items(order.begin() + ndev, order.end());
-    std::reverse(host_items.begin(), host_items.end());      // long solves first
-    auto host_part = [&]() {
-        parallel_over(host_items, [&](int i) {
-            if (!kh::prep_eikonal_speed_host(&works[i], &eps[i])) { bad[i] = 1; errs[i] = eps[i].err; works[i] = kh::EikonalWork(); return; }
-            kh::prep_eikonal_solve_host(&works[i]);
-            if (!kh::prep_eikonal_finish(&works[i], &eps[i])) { bad[i] = 1; errs[i] = eps[i].err; }
-            else eikonal_to_prep(eps[i], &prep[i]);
-            works[i] = kh::EikonalWork();   // (the fine grids are 20 bytes per node: released as soon as they are done with)
-        });
-    };
+    const size_t round_nodes = std::max<size_t>((size_t)1 << 22, std::min<size_t>(fr / 3, (size_t)24 << 30) / 20);   // up to 20 bytes per node on the device
+    const int wave_jobs = 148 * 13;                                                                                   // solves resident at a time
     const int hcap = eikonal_heap_smem_entries();
-    bool host_done = false;
-    size_t at = 0;
-    while (at < ndev) {
-        size_t nodes = 0, end = at;
-        while (end < ndev && (int)(end - at) < wave_jobs && (end == at || nodes + nodes_of(order[end]) <= wave_nodes)) nodes += nodes_of(order[end++]);
-        const int nj = (int)(end - at);
-        CU_OK(c->d_eik_s.ensure(nodes * 4)); CU_OK(c->d_eik_t.ensure(nodes * 4)); CU_OK(c->d_eik_bp.ensure(nodes * 4));
-        CU_OK(c->d_eik_ovf.ensure(nodes * sizeof(EikItem))); CU_OK(c->d_eik_jobs.ensure(sizeof(EikJob) * nj));
-        CU_OK(c->d_eik_geoms.ensure(sizeof(EikGeom) * nj));
-        // ---- geometry up, speed fields, smallest speeds down --------------------------------------------------------------
-        std::vector<EikGeom> geoms(nj);
+    c->eikonal_last_device_solves = 0;
+    std::vector<int> valid;
+    for (int i = 0; i < n; i++) if (!bad[i]) valid.push_back(i);
+    size_t vat = 0;
+    while (vat < valid.size()) {
+        // ---- one round: as many candidates as the device arenas hold ------------------------------------------------------
+        size_t vend = vat, rnodes = 0;
+        while (vend < valid.size() && (vend == vat || rnodes + nodes_of(valid[vend]) <= round_nodes)) rnodes += nodes_of(valid[vend++]);
+        std::vector<int> order(valid.begin() + vat, valid.begin() + vend);      // small grids first
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return nodes_of(a) < nodes_of(b); });
+        const int nr = (int)order.size();
+        // which solves go to the device: a prefix of the size-ordered list (its wave lasts as long as its largest grid).  Measured rates
+        // (profiles/r02_eikonal_device.txt): a warp 2.1-2.5 us per node, a host core 0.1 us per node for the solve alone
+        int ndev = std::min(nr, wave_jobs);
+        if (share) {
+            const double dev_node = 2.4e-6, host_node = 1.05e-7;
+            double all_host = 0.;
+            for (int i : order) all_host += host_node * nodes_of(i);
+            double best = all_host / ncores, dev_host = 0.;
+            ndev = 0;
+            for (int k = 0; k < nr && k < wave_jobs; k++) {
+                const double nn = (double)nodes_of(order[k]);
+                dev_host += host_node * nn;
+                const double total = std::max(dev_node * nn, (all_host - dev_host) / ncores);   // (nn = the largest grid so far)
+                if (total < 0.97 * best) { best = total; ndev = k + 1; }
+            }
+        }
+        // device order: the solves of the device, largest grid first (it sets the wave's length), then the candidates solved on the host
+        std::vector<int> cand(nr);
+        for (int j = 0; j < ndev; j++) cand[j] = order[ndev - 1 - j];
+        for (int j = ndev; j < nr; j++) cand[j] = order[nr - 1 - (j - ndev)];     // host solves: long ones first
+        size_t dev_nodes = 0, host_nodes = 0;
+        for (int j = 0; j < nr; j++) (j < ndev ? dev_nodes : host_nodes) += nodes_of(cand[j]);
+        const size_t all_nodes = dev_nodes + host_nodes;
+        CU_OK(c->d_eik_s.ensure(all_nodes * 4)); CU_OK(c->d_eik_t.ensure(all_nodes * 4));
+        CU_OK(c->d_eik_bp.ensure(std::max<size_t>(dev_nodes, 1) * 4)); CU_OK(c->d_eik_ovf.ensure(std::max<size_t>(dev_nodes, 1) * sizeof(EikItem)));
+        CU_OK(c->d_eik_jobs.ensure(sizeof(EikJob) * std::max(ndev, 1))); CU_OK(c->d_eik_geoms.ensure(sizeof(EikGeom) * nr));
+        CU_OK(c->h_eik.ensure(std::max<size_t>(host_nodes, 1) * 8));            // page-locked: speeds, then times of the host solves
+        float* h_speed = c->h_eik.as<float>();
+        float* h_times = h_speed + host_nodes;
+        // ---- geometry up, speed fields, smallest speeds down ------------------------------------------------------------------
+        std::vector<EikGeom> geoms(nr);
         size_t off = 0;
         int max_nodes = 1;
-        for (int j = 0; j < nj; j++) {    // (largest grid of the wave first: it sets the wave's length)
-            const kh::EikonalWork& w = works[order[end - 1 - j]];
+        for (int j = 0; j < nr; j++) {
+            const kh::EikonalWork& w = works[cand[j]];
             EikGeom& G = geoms[j];
             memset(&G, 0, sizeof G);
             G.fnx = w.fnx; G.fny = w.fny;
@@ -399,19 +396,21 @@ int prep_eikonal_batch_device(kiwi_ctx* c, int sourcetype, int n, int nparams, c
             off += (size_t)w.fnx * w.fny;
             max_nodes = std::max(max_nodes, w.fnx * w.fny);
         }
-        CU_OK(cudaMemcpyAsync(c->d_eik_geoms.p, geoms.data(), sizeof(EikGeom) * nj, cudaMemcpyHostToDevice, c->stream));
-        cudaError_t e = launch_eik_speed(c->d_eik_geoms.as<EikGeom>(), nj, max_nodes, c->d_eik_s.as<float>(), c->stream);
+        CU_OK(cudaMemcpyAsync(c->d_eik_geoms.p, geoms.data(), sizeof(EikGeom) * nr, cudaMemcpyHostToDevice, c->stream));
+        cudaError_t e = launch_eik_speed(c->d_eik_geoms.as<EikGeom>(), nr, max_nodes, c->d_eik_s.as<float>(), c->stream);
         if (e != cudaSuccess) return kiwi_set_error("CUDA error launching the speed-field kernel: %s", cudaGetErrorString(e));
-        std::vector<EikGeom> back(nj);
-        CU_OK(cudaMemcpyAsync(back.data(), c->d_eik_geoms.p, sizeof(EikGeom) * nj, cudaMemcpyDeviceToHost, c->stream));
+        std::vector<EikGeom> back(nr);
+        CU_OK(cudaMemcpyAsync(back.data(), c->d_eik_geoms.p, sizeof(EikGeom) * nr, cudaMemcpyDeviceToHost, c->stream));
+        if (host_nodes > 0)   // the speed fields of the host solves (they are the tail of the arena)
+            CU_OK(cudaMemcpyAsync(h_speed, c->d_eik_s.as<float>() + dev_nodes, host_nodes * 4, cudaMemcpyDeviceToHost, c->stream));
         CU_OK(cudaStreamSynchronize(c->stream));
-        // ---- coarse grids, solves, down-sampling ----------------------------------------------------------------------------------
-        std::vector<EikJob> jobs(nj);
-        std::vector<kh::EikonalCoarse> cgs(nj);
+        // ---- coarse grids; solves of the device and their down-sampling ---------------------------------------------------------------
+        std::vector<EikJob> jobs(std::max(ndev, 1));
+        std::vector<kh::EikonalCoarse> cgs(nr);
         size_t coff = 0;
         int max_cells = 1;
-        for (int j = 0; j < nj; j++) {
-            const int i = order[end - 1 - j];
+        for (int j = 0; j < nr; j++) {
+            const int i = cand[j];
             kh::EikonalWork& w = works[i];
             EikGeom& G = geoms[j];
             float minspeed;
@@ -421,38 +420,57 @@ int prep_eikonal_batch_device(kiwi_ctx* c, int sourcetype, int n, int nparams, c
             bool ok = true;
             if (!(minspeed > 0.f) || back[j].minspeed_bits == 0x7f7fffff) { ok = false; errs[i] = "no valid point in the rupture area"; }
             if (ok && !kh::prep_eikonal_coarse_dims(w, &cgs[j], &errs[i])) ok = false;
-            if (!ok) { bad[i] = 1; cgs[j].nxc = cgs[j].nyc = 0; w.invalid_speed = 1.f; }   // (solved all the same, result ignored)
+            if (!ok) { bad[i] = 1; cgs[j].nxc = cgs[j].nyc = 0; w.invalid_speed = 1.f; }   // (a device solve runs all the same, its result is ignored)
             G.nxc = cgs[j].nxc; G.nyc = cgs[j].nyc; G.cdelta[0] = cgs[j].cdelta[0]; G.cdelta[1] = cgs[j].cdelta[1];
             G.invalid_speed = w.invalid_speed; G.coarse_off = coff;
             coff += (size_t)6 * cgs[j].nxc * cgs[j].nyc;
             max_cells = std::max(max_cells, cgs[j].nxc * cgs[j].nyc);
-            EikJob& J = jobs[j];
-            const size_t nn = (size_t)w.fnx * w.fny;
-            J.nx = w.fnx; J.ny = w.fny; J.dx = w.delta[0]; J.dy = w.delta[1];
-            eikonal_start_node(w.first, w.delta, w.initialpoint, w.fnx, w.fny, &J.ix0, &J.iy0);
-            J.S = c->d_eik_s.as<float>() + G.node_off; J.T = c->d_eik_t.as<float>() + G.node_off; J.bp = c->d_eik_bp.as<int>() + G.node_off;
-            J.ovf = nn > (size_t)hcap ? c->d_eik_ovf.as<EikItem>() + G.node_off : nullptr;
-            J.invalid_speed = w.invalid_speed;
+            if (j < ndev) {
+                EikJob& J = jobs[j];
+                const size_t nn = (size_t)w.fnx * w.fny;
+                J.nx = w.fnx; J.ny = w.fny; J.dx = w.delta[0]; J.dy = w.delta[1];
+                eikonal_start_node(w.first, w.delta, w.initialpoint, w.fnx, w.fny, &J.ix0, &J.iy0);
+                J.S = c->d_eik_s.as<float>() + G.node_off; J.T = c->d_eik_t.as<float>() + G.node_off; J.bp = c->d_eik_bp.as<int>() + G.node_off;
+                J.ovf = nn > (size_t)hcap ? c->d_eik_ovf.as<EikItem>() + G.node_off : nullptr;
+                J.invalid_speed = w.invalid_speed;
+            }
         }
         CU_OK(c->d_eik_coarse.ensure(sizeof(float) * std::max<size_t>(coff, 6)));
-        CU_OK(cudaMemcpyAsync(c->d_eik_geoms.p, geoms.data(), sizeof(EikGeom) * nj, cudaMemcpyHostToDevice, c->stream));
-        CU_OK(cudaMemcpyAsync(c->d_eik_jobs.p, jobs.data(), sizeof(EikJob) * nj, cudaMemcpyHostToDevice, c->stream));
+        CU_OK(cudaMemcpyAsync(c->d_eik_geoms.p, geoms.data(), sizeof(EikGeom) * nr, cudaMemcpyHostToDevice, c->stream));
+        if (ndev > 0) CU_OK(cudaMemcpyAsync(c->d_eik_jobs.p, jobs.data(), sizeof(EikJob) * ndev, cudaMemcpyHostToDevice, c->stream));
         CU_OK(cudaStreamSynchronize(c->stream));   // (geoms and jobs are stack-lifetime staging vectors)
-        e = launch_eikonal_fmm(c->d_eik_jobs.as<EikJob>(), nj, c->stream);
-        if (e != cudaSuccess) return kiwi_set_error("CUDA error launching the fast-marching solver: %s", cudaGetErrorString(e));
-        e = launch_eik_down(c->d_eik_geoms.as<EikGeom>(), nj, max_cells, c->d_eik_s.as<float>(), c->d_eik_t.as<float>(), c->d_eik_coarse.as<float>(), c->stream);
-        if (e != cudaSuccess) return kiwi_set_error("CUDA error launching the down-sampling kernel: %s", cudaGetErrorString(e));
-        c->launches[0] += 3;
-        if (!host_done) { host_part(); host_done = true; }   // the host threads work through their share while the wave runs
+        if (ndev > 0) {
+            e = launch_eikonal_fmm(c->d_eik_jobs.as<EikJob>(), ndev, c->stream);
+            if (e != cudaSuccess) return kiwi_set_error("CUDA error launching the fast-marching solver: %s", cudaGetErrorString(e));
+            e = launch_eik_down(c->d_eik_geoms.as<EikGeom>(), ndev, max_cells, c->d_eik_s.as<float>(), c->d_eik_t.as<float>(), c->d_eik_coarse.as<float>(), c->stream);
+            if (e != cudaSuccess) return kiwi_set_error("CUDA error launching the down-sampling kernel: %s", cudaGetErrorString(e));
+            c->launches[0] += 2;
+        }
+        c->launches[0] += 1;
+        // ---- solves of the host, while the wave runs: speeds and times in page-locked memory ----------------------------------------------
+        parallel_over((size_t)(nr - ndev), [&](size_t k) {
+            const int j = ndev + (int)k, i = cand[j];
+            if (bad[i]) return;
+            const kh::EikonalWork& w = works[i];
+            const size_t nn = (size_t)w.fnx * w.fny, o = geoms[j].node_off - dev_nodes;
+            float* sp = h_speed + o;
+            for (size_t q = 0; q < nn; q++) if (sp[q] == 0.f) sp[q] = w.invalid_speed;        // source_eikonal.f90:497-507
+            kh::eikonal_solver_fmm(sp, w.fnx, w.fny, w.first, w.delta, w.initialpoint, h_times + o);
+        });
+        if (nr > ndev) {
+            CU_OK(cudaMemcpyAsync(c->d_eik_t.as<float>() + dev_nodes, h_times, host_nodes * 4, cudaMemcpyHostToDevice, c->stream));
+            e = launch_eik_down(c->d_eik_geoms.as<EikGeom>() + ndev, nr - ndev, max_cells, c->d_eik_s.as<float>(), c->d_eik_t.as<float>(), c->d_eik_coarse.as<float>(),
+                                c->stream);
+            if (e != cudaSuccess) return kiwi_set_error("CUDA error launching the down-sampling kernel: %s", cudaGetErrorString(e));
+            c->launches[0] += 1;
+        }
         std::vector<float> coarse(std::max<size_t>(coff, 6));
         CU_OK(cudaMemcpyAsync(coarse.data(), c->d_eik_coarse.p, sizeof(float) * coff, cudaMemcpyDeviceToHost, c->stream));
         CU_OK(cudaStreamSynchronize(c->stream));
         CU_OK(cudaGetLastError());
-        // ---- sub-fault tables of the wave ---------------------------------------------------------------------------------------------
-        std::vector<int> js(nj);
-        for (int j = 0; j < nj; j++) js[j] = j;
-        parallel_over(js, [&](int j) {
-            const int i = order[end - 1 - j];
+        // ---- sub-fault tables ---------------------------------------------------------------------------------------------------------------
+        parallel_over((size_t)nr, [&](size_t j) {
+            const int i = cand[j];
             if (bad[i]) return;
             kh::EikonalCoarse& cg = cgs[j];
             const size_t ncell = (size_t)cg.nxc * cg.nyc;
@@ -465,10 +483,9 @@ int prep_eikonal_batch_device(kiwi_ctx* c, int sourcetype, int n, int nparams, c
             if (!kh::prep_eikonal_table(works[i], cg, &eps[i])) { bad[i] = 1; errs[i] = eps[i].err; }
             else eikonal_to_prep(eps[i], &prep[i]);
         });
-        at = end;
+        c->eikonal_last_device_solves += ndev;
+        vat = vend;
     }
-    if (!host_done) host_part();
-    c->eikonal_last_device_solves = (int)ndev;
     return 0;
 }
 
@@ -736,7 +753,7 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         // of a batch between the host threads and the device where that is faster (the default); 0 = host only
         const int device_min = c->eikonal_device_min;
         c->eikonal_last_device_solves = 0;
-        if (heavy && ((device_min > 0 && n >= device_min) || (device_min < 0 && n >= 2 * nthreads))) {
+        if (heavy && ((device_min > 0 && n >= device_min) || (device_min < 0 && n >= 2))) {
             if (prep_eikonal_batch_device(c, sourcetype, n, nparams, params, prep, bad, errs, device_min < 0)) return 1;
             for (int i = 0; i < n; i++) if (bad[i]) prep[i] = kh::SourcePrep();
         } else if (nthreads > 1) {
@@ -1294,7 +1311,7 @@ void kiwi_destroy(kiwi_ctx* c) {
     for (DevBuf* b : {&c->d_slabs, &c->d_nodes, &c->d_tspan, &c->d_nspan, &c->d_rcv, &c->d_refdata, &c->d_taper, &c->d_cands, &c->d_bilat, &c->d_gf, &c->d_gi,
                       &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift, &c->d_map, &c->d_status_out, &c->d_taprec, &c->d_partial, &c->d_fftz, &c->d_gm, &c->d_xcorr, &c->d_eik_s, &c->d_eik_t, &c->d_eik_bp, &c->d_eik_ovf, &c->d_eik_jobs, &c->d_eik_geoms, &c->d_eik_coarse, &c->d_mtlocs, &c->d_mts, &c->d_candof, &c->d_orc, &c->d_orw, &c->d_obw, &c->d_oout, &c->d_obest, &c->d_obestv})
         b->release();
-    c->h_stage.release(); c->h_out.release(); c->h_mt.release();
+    c->h_stage.release(); c->h_out.release(); c->h_mt.release(); c->h_eik.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->stream);
     delete c;
