@@ -904,7 +904,15 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
             std::vector<float> ne((size_t)2 * Galloc), lam((size_t)Galloc, 0.f);
             CU_OK(cudaMemcpyAsync(ne.data(), g.north, sizeof(float) * 2 * (size_t)Galloc, cudaMemcpyDeviceToHost, st));   // north, east: adjacent
             CU_OK(cudaStreamSynchronize(st));
-            for (int k = 0; k < G; k++) lam[k] = atan2f(ne[(size_t)Galloc + k], ne[k]);
+            const int nth = G >= 8192 ? (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())) : 1;
+            if (nth > 1) {
+                std::vector<std::thread> pool;
+                for (int t = 0; t < nth; t++)
+                    pool.emplace_back([&, t]() { for (int k = (int)((long long)G * t / nth); k < (int)((long long)G * (t + 1) / nth); k++) lam[k] = atan2f(ne[(size_t)Galloc + k], ne[k]); });
+                for (std::thread& th : pool) th.join();
+            } else {
+                for (int k = 0; k < G; k++) lam[k] = atan2f(ne[(size_t)Galloc + k], ne[k]);
+            }
             g.lam = gf + 11 * (size_t)Galloc;
             CU_OK(cudaMemcpyAsync(g.lam, lam.data(), sizeof(float) * (size_t)Galloc, cudaMemcpyHostToDevice, st));
             CU_OK(cudaStreamSynchronize(st));
