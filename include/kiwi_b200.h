@@ -176,9 +176,10 @@ int kiwi_set_mt_grid(kiwi_ctx* ctx, int enabled);
  * order (taps merged per sample shift, sub-sources spread over warps): within 1e-5 of the trace peak of the exactly accumulated sum at
  * any size, and as far from the reference's result as the reference's own sequential fp32 accumulation is (5e-5 at 1e4 sub-sources).
  * 1: every operation of make_seismogram / trace_multiply_add / gfdb_get_trace_bilin (seismogram.f90:131-289, sparse_trace.f90:597-707,
- * gfdb.f90:865-950) per output sample in the reference's order; differs from the reference only through the device's sincosf / cos / sin of
- * the per-centroid azimuths (last-bit effects), ~100 x slower: for regression against results of the Fortran code and as the checker of
- * the batched kernel's operands.  Point moment-tensor grids take the candidate-by-candidate path in this mode. */
+ * gfdb.f90:865-950) per output sample in the reference's order, with atan2f / sinf / cosf of the azimuths from the host library: the
+ * seismograms equal the restated reference path bit for bit (checked on every sample of config C3 at full size).  ~10 x slower: for
+ * regression against results of the Fortran code and as the checker of the batched kernel's operands.  Point moment-tensor grids take
+ * the candidate-by-candidate path in this mode. */
 int kiwi_set_accumulation(kiwi_ctx* ctx, int reference_order);
 
 /* Eikonal / mt_eikonal sources: the fast-marching solve of the rupture front (eikonal.f90:29-199), sequential by construction and 70 % of the

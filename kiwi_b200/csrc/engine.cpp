@@ -140,6 +140,7 @@ struct kiwi_ctx {
     DevBuf d_gm;                  // ground-motion values [cand][rcv][3]
     DevBuf d_xcorr;               // cross-correlations [rcv][component][shift] (autoshift_ref_seismogram)
     bool dedup_enabled = true;               // candidates that differ only in the moment share one synthesis
+    DevBuf d_azf, d_trig;   // reference-order mode: azimuths of the (pair, group)s and their host-library sinf / cosf
     DevBuf d_eik_s, d_eik_t, d_eik_bp, d_eik_ovf, d_eik_jobs, d_eik_geoms, d_eik_coarse;   // fast-marching solves of a wave of eikonal candidates
     DevBuf d_mtlocs, d_mts, d_candof, d_orc, d_orw, d_obw, d_oout, d_obest, d_obestv;
     int last_eval_ns = 0;                    // candidates whose misfit block sits in d_out (kiwi_eval_sources)
@@ -918,7 +919,30 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
             CU_OK(cudaStreamSynchronize(st));
         }
         launch_geometry(c->db, c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>(), nc, g, Galloc, c->interpolate ? 1 : 0, c->xunder, c->zunder,
-                        c->d_recs.as<GeoRec>(), rec_stride, c->d_hdrs.as<PairHdr>(), c->d_tmax.as<int>(), st, exact ? 1 : 0);
+                        c->d_recs.as<GeoRec>(), rec_stride, c->d_hdrs.as<PairHdr>(), c->d_tmax.as<int>(), st, exact ? 1 : 0,
+                        exact ? (c->d_azf.ensure(sizeof(float) * npairs * rec_stride) == cudaSuccess ? c->d_azf.as<float>() : nullptr) : nullptr);
+        if (exact && c->d_azf.p) {
+            // sinf / cosf of the azimuths from the host library (make_weights seismogram.f90:316-336 calls them per centroid): the device's own
+            // are an ulp off often enough to show in a few samples per trace
+            const size_t na = npairs * rec_stride;
+            std::vector<float> azf(na);
+            std::vector<float4> trig(na);
+            CU_OK(cudaMemcpyAsync(azf.data(), c->d_azf.p, sizeof(float) * na, cudaMemcpyDeviceToHost, st));
+            CU_OK(cudaStreamSynchronize(st));
+            const int nth = (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), std::max<size_t>(1, na / 65536));
+            std::vector<std::thread> pool;
+            for (int t = 0; t < nth; t++)
+                pool.emplace_back([&, t]() {
+                    for (size_t k = na * t / nth; k < na * (t + 1) / nth; k++) {
+                        const float a = azf[k];
+                        trig[k] = make_float4(cosf(a), sinf(a), sinf(2.f * a), cosf(2.f * a));
+                    }
+                });
+            for (std::thread& th : pool) th.join();
+            CU_OK(c->d_trig.ensure(sizeof(float4) * na));
+            CU_OK(cudaMemcpyAsync(c->d_trig.p, trig.data(), sizeof(float4) * na, cudaMemcpyHostToDevice, st));
+            CU_OK(cudaStreamSynchronize(st));
+        }
         c->launches[1] += 1;
         int tm3[4] = {0, 0, 0, 0};
         CU_OK(cudaMemcpyAsync(tm3, c->d_tmax.p, sizeof tm3, cudaMemcpyDeviceToHost, st));
@@ -997,7 +1021,8 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
                 cudaError_t e = launch_synth_exact(c->db, c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>() + s0, ns_, g, taps, Galloc,
                                                    c->d_recs.as<GeoRec>() + poff * rec_stride, rec_stride, c->d_hdrs.as<PairHdr>() + poff, nq, margin_q,
                                                    c->interpolate ? 1 : 0, c->xunder, c->zunder, wcap, c->d_seis.as<float>(), seis_stride,
-                                                   c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, d_overflow, st);
+                                                   c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, d_overflow, st,
+                                                   c->d_trig.p ? c->d_trig.as<float4>() + poff * rec_stride : nullptr);
                 if (e != cudaSuccess) return kiwi_set_error("CUDA error launching the reference-order synthesis: %s", cudaGetErrorString(e));
                 c->launches[2] += 1;
                 int overflow = 0;
@@ -1317,7 +1342,7 @@ void kiwi_destroy(kiwi_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->d_slabs, &c->d_nodes, &c->d_tspan, &c->d_nspan, &c->d_rcv, &c->d_refdata, &c->d_taper, &c->d_cands, &c->d_bilat, &c->d_gf, &c->d_gi,
-                      &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift, &c->d_map, &c->d_status_out, &c->d_taprec, &c->d_partial, &c->d_fftz, &c->d_gm, &c->d_xcorr, &c->d_eik_s, &c->d_eik_t, &c->d_eik_bp, &c->d_eik_ovf, &c->d_eik_jobs, &c->d_eik_geoms, &c->d_eik_coarse, &c->d_mtlocs, &c->d_mts, &c->d_candof, &c->d_orc, &c->d_orw, &c->d_obw, &c->d_oout, &c->d_obest, &c->d_obestv})
+                      &c->d_tf, &c->d_recs, &c->d_hdrs, &c->d_seis, &c->d_shdrs, &c->d_out, &c->d_status, &c->d_tmax, &c->d_table, &c->d_tw, &c->d_fshift, &c->d_map, &c->d_status_out, &c->d_taprec, &c->d_partial, &c->d_fftz, &c->d_gm, &c->d_xcorr, &c->d_azf, &c->d_trig, &c->d_eik_s, &c->d_eik_t, &c->d_eik_bp, &c->d_eik_ovf, &c->d_eik_jobs, &c->d_eik_geoms, &c->d_eik_coarse, &c->d_mtlocs, &c->d_mts, &c->d_candof, &c->d_orc, &c->d_orw, &c->d_obw, &c->d_oout, &c->d_obest, &c->d_obestv})
         b->release();
     c->h_stage.release(); c->h_out.release(); c->h_mt.release(); c->h_eik.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);

@@ -242,7 +242,8 @@ template <bool SINGLE>
 __global__ void __launch_bounds__(256, 3) k_geometry(GfdbDev db, const ReceiverDev* __restrict__ rcv, int nrcv,
                                                    const CandDev* __restrict__ cands, GroupSoA g, int ngroups_total, int interpolate,
                                                    int xunder, int zunder, GeoRec* __restrict__ recs, size_t rec_stride,
-                                                   PairHdr* __restrict__ hdrs, int* __restrict__ tmax, int npairs, int trig_only) {
+                                                   PairHdr* __restrict__ hdrs, int* __restrict__ tmax, int npairs, int trig_only,
+                                                   float* __restrict__ azf_out) {
     const int pair_ = SINGLE ? (int)(blockIdx.x * blockDim.x + threadIdx.x) : (int)blockIdx.x;
     const bool valid = !SINGLE || pair_ < npairs;      // (threads past the end stay for the warp shuffles at the bottom)
     const int pair = valid ? pair_ : 0;
@@ -283,7 +284,9 @@ __global__ void __launch_bounds__(256, 3) k_geometry(GfdbDev db, const ReceiverD
                 rec.f[4] = m[5] * ca - m[4] * sa;
                 rec.f[5] = m[0] * (sa * sa) + m[1] * (ca * ca) - m[3] * s2a;
                 // reference-order synthesis (synth_exact.cu) forms the weights per centroid itself: it gets the azimuth functions
-                // (rounded from double: the device's sincosf may be an ulp off the host library's, which is correctly rounded nearly always)
+                // (rounded from double: the device's sincosf may be an ulp off the host library's, which is correctly rounded nearly always;
+                //  with azf_out the caller replaces them by the host library's own values, computed from the azimuth handed back)
+                if (azf_out) azf_out[(size_t)pair * rec_stride + ip] = azf;
                 if (trig_only) {
                     const double ad = (double)azf, a2 = (double)(2.f * azf);
                     rec.f[0] = (float)cos(ad); rec.f[1] = (float)sin(ad); rec.f[2] = (float)sin(a2); rec.f[3] = (float)cos(a2); rec.f[4] = 0.f; rec.f[5] = 0.f;
@@ -2392,18 +2395,19 @@ void launch_expand_centroids(CandDev cand, GroupSoA g, TapSoA taps, int ngroups_
     k_expand_centroids<<<(cand.ngroups + 127) / 128, 128, 0, st>>>(cand, g, taps, ngroups_total, d_table, cap);
 }
 void launch_geometry(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, int ngroups_total,
-                     int interpolate, int xunder, int zunder, GeoRec* recs, size_t rec_stride, PairHdr* hdrs, int* tmax, cudaStream_t st, int trig_only) {
+                     int interpolate, int xunder, int zunder, GeoRec* recs, size_t rec_stride, PairHdr* hdrs, int* tmax, cudaStream_t st, int trig_only,
+                     float* azf_out) {
     const int npairs = ncand * nrcv;
     if (npairs <= 0) return;
     if (rec_stride == 1) {   // single-group candidates: one thread per pair
         k_geometry<true><<<(npairs + 127) / 128, 128, 0, st>>>(db, rcv, nrcv, cands, g, ngroups_total, interpolate, xunder, zunder, recs, rec_stride, hdrs,
-                                                           tmax, npairs, trig_only);
+                                                           tmax, npairs, trig_only, azf_out);
         return;
     }
     // one thread per group: a CTA no wider than the longest group list
     const int threads = (int)std::min<size_t>(256, std::max<size_t>(32, (rec_stride + 31) / 32 * 32));
     k_geometry<false><<<npairs, threads, 0, st>>>(db, rcv, nrcv, cands, g, ngroups_total, interpolate, xunder, zunder, recs, rec_stride, hdrs, tmax,
-                                                 npairs, trig_only);
+                                                 npairs, trig_only, azf_out);
 }
 size_t synth_smem_bytes(int nwarps, int nq) {
     return (size_t)nwarps * 3 * nq * (sizeof(float4) + sizeof(float)) + 16 + (size_t)nwarps * 3 * sizeof(GeoRec) +

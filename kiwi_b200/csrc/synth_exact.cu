@@ -13,11 +13,14 @@
 // products added in corner order).  The strips of the reference grow as centroids arrive (new samples repeat the last one,
 // strip_extend sparse_trace.f90:316-345); a sample that enters a strip late holds exactly the sum of the tails it would have
 // collected, so the per-sample sequence is the same whatever the growth order.  Compiled with -fmad=false: every operation is
-// the IEEE operation the source shows.  What is not the host's arithmetic are the transcendentals of the geometry pre-pass
-// (sincosf of the azimuth, cos/sin of the back-azimuth difference: device libm), a last-bit effect on some weights.
+// the IEEE operation the source shows.  The transcendentals whose device versions differ from the host library's often enough to
+// show come from the host: atan2f of the sub-source azimuths (engine.cpp, every mode) and sinf / cosf of the per-(receiver,
+// sub-source) azimuths (`trig`, this mode).  With them the seismograms equal the fp32 restatement of the Fortran path bit for bit
+// (tests/test_reference_order_gpu.py: every sample of C3 at full size).
 //
 // One CTA per (candidate, receiver); per group the ten bilinear traces are formed once in shared memory (threads over trace samples),
-// then every thread applies the group's centroids to its output samples.  Cost ~1 s per C3-sized candidate: a verification mode.
+// then every thread applies the group's centroids to its output samples.  19 ms per C3-sized candidate, 130 ms per C5-sized one:
+// a regression / verification mode, 9-12 x the batched kernel's time.
 #include "kiwi_dev.cuh"
 #include "kernels.cuh"
 #include <cfloat>
@@ -46,7 +49,8 @@ __global__ void __launch_bounds__(SX_THREADS) k_synth_exact(GfdbDev db, const Re
                                                             GroupSoA g, TapSoA taps, int ngroups_total, const GeoRec* __restrict__ recs, size_t rec_stride,
                                                             const PairHdr* __restrict__ hdrs, int nq_alloc, int margin_q, int interpolate, int xunder,
                                                             int zunder, int wcap /* floats per trace row in shared memory */, float* __restrict__ seis,
-                                                            size_t seis_stride, SeisHdr* __restrict__ shdrs, int* __restrict__ overflow) {
+                                                            size_t seis_stride, SeisHdr* __restrict__ shdrs, int* __restrict__ overflow,
+                                                            const float4* __restrict__ trig) {
     extern __shared__ __align__(16) unsigned char sx_smem[];
     float* s_tr = reinterpret_cast<float*>(sx_smem);          // [10][wcap]
     __shared__ SxTrace s_meta[KIWI_NG_MAX];
@@ -123,7 +127,8 @@ __global__ void __launch_bounds__(SX_THREADS) k_synth_exact(GfdbDev db, const Re
         float mh[6];
 #pragma unroll
         for (int q = 0; q < 6; q++) mh[q] = g.mhat[(size_t)q * ngroups_total + gi];
-        const float ca = s_rec.f[0], sa = s_rec.f[1], s2a = s_rec.f[2], c2a = s_rec.f[3];   // written by k_geometry in this mode
+        float ca = s_rec.f[0], sa = s_rec.f[1], s2a = s_rec.f[2], c2a = s_rec.f[3];   // written by k_geometry in this mode ...
+        if (trig) { const float4 t4 = __ldg(trig + (size_t)pair * rec_stride + ip); ca = t4.x; sa = t4.y; s2a = t4.z; c2a = t4.w; }   // ... or by the host library
         const float cl = s_rec.cl, sl = s_rec.sl;
         const bool rot = flags & GEO_ROT;
         for (int it = 0; it < tn; it++) {
@@ -210,12 +215,12 @@ int synth_exact_max_samples() { return SX_THREADS * SX_NS; }
 size_t synth_exact_smem_bytes(int wcap) { return (size_t)KIWI_NG_MAX * wcap * sizeof(float); }
 cudaError_t launch_synth_exact(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, TapSoA taps, int ngroups_total,
                                const GeoRec* recs, size_t rec_stride, const PairHdr* hdrs, int nq_alloc, int margin_q, int interpolate, int xunder,
-                               int zunder, int wcap, float* seis, size_t seis_stride, SeisHdr* shdrs, int* overflow, cudaStream_t st) {
+                               int zunder, int wcap, float* seis, size_t seis_stride, SeisHdr* shdrs, int* overflow, cudaStream_t st, const float4* trig) {
     const size_t smem = synth_exact_smem_bytes(wcap);
     cudaError_t e = cudaFuncSetAttribute(k_synth_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (ncand * nrcv > 0)
         k_synth_exact<<<ncand * nrcv, SX_THREADS, smem, st>>>(db, rcv, nrcv, cands, g, taps, ngroups_total, recs, rec_stride, hdrs, nq_alloc, margin_q,
-                                                             interpolate, xunder, zunder, wcap, seis, seis_stride, shdrs, overflow);
+                                                             interpolate, xunder, zunder, wcap, seis, seis_stride, shdrs, overflow, trig);
     return cudaGetLastError();
 }

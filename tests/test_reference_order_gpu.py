@@ -1,11 +1,10 @@
 """The reference-order synthesis (kiwi_set_accumulation(ctx, 1), kiwi_b200/csrc/synth_exact.cu): every floating-point operation of
 make_seismogram / trace_multiply_add / gfdb_get_trace_bilin (seismogram.f90:131-289, sparse_trace.f90:597-707, gfdb.f90:865-950) per output
-sample in the reference's order.  Against the fp32 restatement AS IT STANDS, at the north_star bar of 1e-5 for seismograms and misfits --
-no appeal to the reference's own accumulation noise -- on the small scenario for every source type and at the full size of config C3
-(~1e4 sub-sources x 200 receivers) and of a C5 candidate on 300 of its 2000 receivers.  Measured: 2e-7 of the trace peak, 98 % of the
-samples bit-identical (the point moment tensor of the small scenario: all of them); the sub-source azimuth atan2f(east, north) comes from
-the host library in this mode, because the device's differs from it by an ulp often enough to move the epicentral distance of ~2 % of
-the sub-sources by one fp32 ulp."""
+sample in the reference's order.  Against the fp32 restatement AS IT STANDS: the seismograms are BIT-IDENTICAL -- on the small scenario for
+every source type, at the full size of config C3 (~1e4 sub-sources x 200 receivers x 3 components: 180 765 samples) and for a C5 candidate on
+300 of its 2000 receivers -- and the misfits agree to 1e-6 (north_star bar: 1e-5), with no appeal to the reference's own accumulation noise.
+Three transcendentals come from the host library for that, because the device's differ from glibc's by an ulp often enough to show: atan2f
+of the sub-source azimuth (once per sub-source, in every mode) and sinf / cosf of the per-(receiver, sub-source) azimuths (this mode)."""
 import numpy as np
 import pytest
 
@@ -15,7 +14,7 @@ from test_parity_gpu import CIRC, COMPS6, EIK, MTEIK, PLP, engines
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-5          # BASELINE.json north_star
-TIGHT = 1e-6         # the mode delivers 2e-7 in practice (guards against regressions of the operation order)
+MTOL = 1e-6          # misfits: the norms are summed in double in another order than the reference's loop (last-bit effects after the cast)
 
 
 def deviation(g, o, nrcv, ncomps):
@@ -43,13 +42,13 @@ def test_small_scenario_every_source_type(stype, params):
     g.set_accumulation(True)
     g.set_source_params(stype, p)
     worst, same = deviation(g, o, 6, ncomps)
-    assert worst <= TIGHT and same > 0.9, (worst, same)
+    assert worst == 0.0 and same == 1.0, (worst, same)
     sc.set_refs_from(o, [g, o], ncomps)
     q = np.tile(p, (3, 1)); q[1, 3] += 300; q[2, 1] -= 250
     mg, sg = g.eval_sources(stype, q)
     mo, so = o.eval_sources(stype, q)
     assert np.array_equal(sg, so) and not sg.any()
-    assert np.all(np.abs(mg - mo) <= RTOL * np.abs(mo) + 1e-30), float(np.max(np.abs(mg - mo) / np.abs(mo)))
+    assert np.all(np.abs(mg - mo) <= MTOL * np.abs(mo) + 1e-30), float(np.max(np.abs(mg - mo) / np.abs(mo)))
 
 
 def test_c3_full_size_against_the_fp32_restatement_as_it_stands():
@@ -62,7 +61,7 @@ def test_c3_full_size_against_the_fp32_restatement_as_it_stands():
     g.set_source_params("bilateral", synthetic.IZMIT)
     worst, same = deviation(g, o, w["nrcv"], [3] * w["nrcv"])
     print("C3, reference order: %.2e of the trace peak from the fp32 restatement, %.0f %% of the samples bit-identical" % (worst, 100 * same))
-    assert worst <= RTOL and worst <= TIGHT, worst
+    assert worst == 0.0 and same == 1.0, (worst, same)
     g.set_accumulation(False)
     g.set_source_params("bilateral", synthetic.IZMIT)
     fast, _ = deviation(g, o, w["nrcv"], [3] * w["nrcv"])
@@ -76,7 +75,7 @@ def test_c3_full_size_against_the_fp32_restatement_as_it_stands():
     assert not sg.any() and not so.any()
     rel = float(np.max(np.abs(mg - mo) / np.abs(mo)))
     print("C3, reference order: misfits %.2e relative from the fp32 restatement" % rel)
-    assert rel <= RTOL
+    assert rel <= MTOL
 
 
 def test_c5_candidate_on_300_receivers():
@@ -88,4 +87,4 @@ def test_c5_candidate_on_300_receivers():
     g.set_accumulation(True)
     g.set_source_params("bilateral", cand)
     worst, same = deviation(g, o, w["nrcv"], [3] * w["nrcv"])
-    assert worst <= RTOL and worst <= TIGHT, worst
+    assert worst == 0.0 and same == 1.0, (worst, same)
