@@ -137,6 +137,7 @@ struct kiwi_ctx {
     size_t l2_bytes = 0;          // cudaDevAttrL2CacheSize (choose_bands)
     double rcv_dmin = 0., rcv_dmax = 0., rcv_depmin = 0., rcv_depmax = 0.;   // distance / depth range of the enabled receivers (upload_receivers)
     size_t slab_floats = 0;       // floats of the database slabs in HBM
+    int db_blk_floats = 0;        // floats of the largest node block (ng rows x window), computed on first use
     DevBuf d_gm;                  // ground-motion values [cand][rcv][3]
     DevBuf d_xcorr;               // cross-correlations [rcv][component][shift] (autoshift_ref_seismogram)
     bool dedup_enabled = true;               // candidates that differ only in the moment share one synthesis
@@ -1013,14 +1014,16 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
             if (tmax > 0 && exact) {
                 // reference-order synthesis: one thread per output sample walks the centroids one after the other
                 const int wcap = 4 * nq + 32;
-                if (4 * nq > synth_exact_max_samples() || synth_exact_smem_bytes(wcap) > (size_t)200 * 1024)
+                if (c->db_blk_floats == 0) for (const NodeInfo& ni : c->h_nodes) if (ni.off != ~0ull) c->db_blk_floats = std::max(c->db_blk_floats, ni.wn * c->db.ng);
+                const int blk_cap = (c->db_blk_floats + 3) & ~3;     // the largest node block of the database
+                if (4 * nq > synth_exact_max_samples() || synth_exact_smem_bytes(wcap, blk_cap) > (size_t)220 * 1024)
                     return kiwi_set_error("synthetic window of %d samples is too long for the reference-order synthesis", tmax);
                 CU_OK(c->d_tmax.ensure(sizeof(int) * 8));
                 int* d_overflow = c->d_tmax.as<int>() + 5;
                 CU_OK(cudaMemsetAsync(d_overflow, 0, sizeof(int), st));
                 cudaError_t e = launch_synth_exact(c->db, c->d_rcv.as<ReceiverDev>(), nrcv, c->d_cands.as<CandDev>() + s0, ns_, g, taps, Galloc,
                                                    c->d_recs.as<GeoRec>() + poff * rec_stride, rec_stride, c->d_hdrs.as<PairHdr>() + poff, nq, margin_q,
-                                                   c->interpolate ? 1 : 0, c->xunder, c->zunder, wcap, c->d_seis.as<float>(), seis_stride,
+                                                   c->interpolate ? 1 : 0, c->xunder, c->zunder, wcap, blk_cap, c->d_seis.as<float>(), seis_stride,
                                                    c->d_shdrs.as<SeisHdr>() + poff * KIWI_MAX_COMP, d_overflow, st,
                                                    c->d_trig.p ? c->d_trig.as<float4>() + poff * rec_stride : nullptr);
                 if (e != cudaSuccess) return kiwi_set_error("CUDA error launching the reference-order synthesis: %s", cudaGetErrorString(e));
@@ -1378,7 +1381,7 @@ int kiwi_set_database(kiwi_ctx* c, kiwi_gfdb* db) {
         total += (unsigned long long)ni.wn * ng;
         tmin = std::min(tmin, lo); tmax = std::max(tmax, hi);
     }
-    c->db_tmin = tmin; c->db_tmax = tmax; c->slab_floats = (size_t)total;
+    c->db_tmin = tmin; c->db_tmax = tmax; c->slab_floats = (size_t)total; c->db_blk_floats = 0;
     // fill the slabs through a bounded pinned staging buffer
     CU_OK(c->d_slabs.ensure(sizeof(float) * std::max<unsigned long long>(total, 4)));
     CU_OK(c->d_nodes.ensure(sizeof(NodeInfo) * nnodes));

@@ -25,10 +25,11 @@ void launch_geometry(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev
                      float* azf_out = nullptr /* [pair][rec_stride]: the fp32 azimuth of every (pair, group), for the host library's sinf / cosf */);
 // reference-order synthesis (synth_exact.cu): every operation of make_seismogram per output sample in the reference's order
 int synth_exact_max_samples();
-size_t synth_exact_smem_bytes(int wcap);
+size_t synth_exact_smem_bytes(int wcap, int blk_cap);
 cudaError_t launch_synth_exact(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, TapSoA taps, int ngroups_total,
                                const GeoRec* recs, size_t rec_stride, const PairHdr* hdrs, int nq_alloc, int margin_q, int interpolate, int xunder,
-                               int zunder, int wcap, float* seis, size_t seis_stride, SeisHdr* shdrs, int* overflow, cudaStream_t st,
+                               int zunder, int wcap, int blk_cap /* floats of the largest node block, multiple of 4 */, float* seis, size_t seis_stride,
+                               SeisHdr* shdrs, int* overflow, cudaStream_t st,
                                const float4* trig = nullptr /* [pair][rec_stride] cos, sin, sin 2a, cos 2a from the host library, or null */);
 size_t synth_smem_bytes(int nwarps, int nq);
 // point moment-tensor grid search with the basis synthesis fused in (one group per location): recs / hdrs of the probe sources

@@ -19,7 +19,11 @@
 // (tests/test_reference_order_gpu.py: every sample of C3 at full size).
 //
 // One CTA per (candidate, receiver); per group the ten bilinear traces are formed once in shared memory (threads over trace samples),
-// then every thread applies the group's centroids to its output samples.  19 ms per C3-sized candidate, 130 ms per C5-sized one:
+// then every thread applies the group's centroids to its output samples.  The Green's function rows come in as whole node blocks:
+// a node's ng rows are one contiguous, 16-byte aligned block (kiwi_dev.cuh), so one elected thread fetches the four corner blocks of
+// the NEXT group with four bulk asynchronous copies (cp.async.bulk, completion counted in bytes on an mbarrier) into the second of two
+// shared-memory stages while all threads work on the current one: the gather latency is off the critical path and each block is
+// read from HBM / L2 once per (candidate, receiver, group) and then used by all 256 threads and all of the group's centroids.  19 ms per C3-sized candidate, 130 ms per C5-sized one:
 // a regression / verification mode, 9-12 x the batched kernel's time.
 #include "kiwi_dev.cuh"
 #include "kernels.cuh"
@@ -37,10 +41,27 @@ struct SxTrace {           // one bilinear (or single) trace of the current grou
     int ok;
 };
 
-__device__ __forceinline__ float slab_at(const float* __restrict__ slabs, const NodeInfo& n, int comp, int y) {
-    // dense row: zeros left of the trace and in its gaps, the last sample repeated to the right
+__device__ __forceinline__ float slab_at(const float* __restrict__ blk, const NodeInfo& n, int comp, int y) {
+    // dense row of the staged node block: zeros left of the trace and in its gaps, the last sample repeated to the right
     const int i = min(max(y - n.w0, 0), n.wn - 1);
-    return __ldg(slabs + n.off + (size_t)comp * n.wn + i);
+    return blk[comp * n.wn + i];
+}
+__device__ __forceinline__ unsigned sx_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// the corner blocks of the group whose record is *rec -> stage buffer; returns false (nothing issued) for a skipped group
+__device__ __forceinline__ bool sx_issue(const GfdbDev& db, const GeoRec* rec, float* stage, int blk_cap /* floats per corner */, unsigned bar) {
+    const int flags = rec->flags;
+    if (flags & GEO_SKIP) return false;
+    const int ncorner = (flags & GEO_SINGLE) ? 1 : 4;
+    unsigned bytes = 0;
+    for (int c = 0; c < ncorner; c++) bytes += (unsigned)(rec->node[c].wn * db.ng) * 4u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    for (int c = 0; c < ncorner; c++) {
+        const NodeInfo n = rec->node[c];
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sx_smem_u32(stage + (size_t)c * blk_cap)),
+                     "l"(db.slabs + n.off), "r"((unsigned)(n.wn * db.ng) * 4u), "r"(bar)
+                     : "memory");
+    }
+    return true;
 }
 
 }  // namespace
@@ -48,13 +69,17 @@ __device__ __forceinline__ float slab_at(const float* __restrict__ slabs, const 
 __global__ void __launch_bounds__(SX_THREADS) k_synth_exact(GfdbDev db, const ReceiverDev* __restrict__ rcv, int nrcv, const CandDev* __restrict__ cands,
                                                             GroupSoA g, TapSoA taps, int ngroups_total, const GeoRec* __restrict__ recs, size_t rec_stride,
                                                             const PairHdr* __restrict__ hdrs, int nq_alloc, int margin_q, int interpolate, int xunder,
-                                                            int zunder, int wcap /* floats per trace row in shared memory */, float* __restrict__ seis,
+                                                            int zunder, int wcap /* floats per trace row in shared memory */,
+                                                            int blk_cap /* floats per staged node block */, float* __restrict__ seis,
                                                             size_t seis_stride, SeisHdr* __restrict__ shdrs, int* __restrict__ overflow,
                                                             const float4* __restrict__ trig) {
     extern __shared__ __align__(16) unsigned char sx_smem[];
     float* s_tr = reinterpret_cast<float*>(sx_smem);          // [10][wcap]
+    float* s_stage = s_tr + (size_t)KIWI_NG_MAX * wcap;       // [2 stages][4 corners][blk_cap]: node blocks, 16-byte aligned
     __shared__ SxTrace s_meta[KIWI_NG_MAX];
-    __shared__ GeoRec s_rec;
+    __shared__ __align__(16) GeoRec s_rec2[2];                // records of the current and the next group (with the stage they belong to)
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    __shared__ int s_issued[2];
     const int pair = blockIdx.x;
     const int b = pair / nrcv, ir = pair % nrcv;
     const ReceiverDev& R = rcv[ir];
@@ -74,13 +99,34 @@ __global__ void __launch_bounds__(SX_THREADS) k_synth_exact(GfdbDev db, const Re
 #pragma unroll
     for (int j = 0; j < SX_NS; j++) { ar0[j] = 0.f; ar1[j] = 0.f; dz[j] = 0.f; }
     const GeoRec* myrecs = recs + (size_t)pair * rec_stride;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sx_smem_u32(&s_bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sx_smem_u32(&s_bar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 8 && cand.ngroups > 0) reinterpret_cast<uint4*>(&s_rec2[0])[tid] = __ldg(reinterpret_cast<const uint4*>(myrecs) + tid);
+    __syncthreads();
+    if (tid == 0 && cand.ngroups > 0) s_issued[0] = sx_issue(db, &s_rec2[0], s_stage, blk_cap, sx_smem_u32(&s_bar[0])) ? 1 : 0;
+    unsigned par0 = 0, par1 = 0;     // phase parities of the two stage barriers
 
     for (int ip = 0; ip < cand.ngroups; ip++) {
+        const int st = ip & 1;
+        __syncthreads();             // everybody is done with group ip - 1: its stage and record slot (the other ones) are free
+        if (tid < 8 && ip + 1 < cand.ngroups) reinterpret_cast<uint4*>(&s_rec2[st ^ 1])[tid] = __ldg(reinterpret_cast<const uint4*>(myrecs + ip + 1) + tid);
         __syncthreads();
-        if (tid < 8) reinterpret_cast<uint4*>(&s_rec)[tid] = __ldg(reinterpret_cast<const uint4*>(myrecs + ip) + tid);
-        __syncthreads();
+        if (tid == 0 && ip + 1 < cand.ngroups)   // the next group's blocks start travelling now
+            s_issued[st ^ 1] = sx_issue(db, &s_rec2[st ^ 1], s_stage + (size_t)(st ^ 1) * 4 * blk_cap, blk_cap, sx_smem_u32(&s_bar[st ^ 1])) ? 1 : 0;
+        const GeoRec& s_rec = s_rec2[st];
         const int flags = s_rec.flags;
         if (flags & GEO_SKIP) continue;          // a node is missing: the reference leaves the centroid (seismogram.f90:172)
+        {   // this group's blocks have landed
+            const unsigned bar = sx_smem_u32(&s_bar[st]), par = st ? par1 : par0;
+            unsigned done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(bar), "r"(par) : "memory");
+            if (st) par1 ^= 1; else par0 ^= 1;
+        }
+        const float* blk0 = s_stage + (size_t)st * 4 * blk_cap;
         const bool single = flags & GEO_SINGLE;
         const NodeInfo n0 = s_rec.node[0], n1 = s_rec.node[1], n2 = s_rec.node[2], n3 = s_rec.node[3];
         const float dix = s_rec.dix, diz = s_rec.diz;
@@ -89,7 +135,10 @@ __global__ void __launch_bounds__(SX_THREADS) k_synth_exact(GfdbDev db, const Re
         const int wlo = single ? n0.w0 : min(min(n0.w0, n1.w0), min(n2.w0, n3.w0));
         const int whi = single ? n0.w0 + n0.wn : max(max(n0.w0 + n0.wn, n1.w0 + n1.wn), max(n2.w0 + n2.wn, n3.w0 + n3.wn));
         const int wl_ = whi - wlo;
-        if (wl_ > wcap) { if (tid == 0) atomicExch(overflow, 1); continue; }
+        if (wl_ > wcap || n0.wn * db.ng > blk_cap || (!single && (n1.wn * db.ng > blk_cap || n2.wn * db.ng > blk_cap || n3.wn * db.ng > blk_cap))) {
+            if (tid == 0) atomicExch(overflow, 1);
+            continue;
+        }
         // node indices for the trace spans
         const int ix2 = s_rec.ix1 + (interpolate ? xunder : 1), iz2 = s_rec.iz1 + (interpolate ? zunder : 1);
         const int in0 = (s_rec.ix1 - 1) * db.nz + (s_rec.iz1 - 1), in1 = (s_rec.ix1 - 1) * db.nz + (iz2 - 1), in2 = (ix2 - 1) * db.nz + (s_rec.iz1 - 1),
@@ -108,12 +157,12 @@ __global__ void __launch_bounds__(SX_THREADS) k_synth_exact(GfdbDev db, const Re
         for (int idx = tid; idx < db.ng * wl_; idx += SX_THREADS) {
             const int k = idx / wl_, i = idx - k * wl_, y = wlo + i;
             float v;
-            if (single) v = slab_at(db.slabs, n0, k, y);
+            if (single) v = slab_at(blk0, n0, k, y);
             else {
-                v = w00 * slab_at(db.slabs, n0, k, y);
-                v = v + w01 * slab_at(db.slabs, n1, k, y);
-                v = v + w10 * slab_at(db.slabs, n2, k, y);
-                v = v + w11 * slab_at(db.slabs, n3, k, y);
+                v = w00 * slab_at(blk0, n0, k, y);
+                v = v + w01 * slab_at(blk0 + blk_cap, n1, k, y);
+                v = v + w10 * slab_at(blk0 + 2 * (size_t)blk_cap, n2, k, y);
+                v = v + w11 * slab_at(blk0 + 3 * (size_t)blk_cap, n3, k, y);
             }
             s_tr[(size_t)k * wcap + i] = v;
         }
@@ -212,15 +261,16 @@ __global__ void __launch_bounds__(SX_THREADS) k_synth_exact(GfdbDev db, const Re
 }
 
 int synth_exact_max_samples() { return SX_THREADS * SX_NS; }
-size_t synth_exact_smem_bytes(int wcap) { return (size_t)KIWI_NG_MAX * wcap * sizeof(float); }
+size_t synth_exact_smem_bytes(int wcap, int blk_cap) { return ((size_t)KIWI_NG_MAX * wcap + (size_t)2 * 4 * blk_cap) * sizeof(float); }
 cudaError_t launch_synth_exact(GfdbDev db, const ReceiverDev* rcv, int nrcv, const CandDev* cands, int ncand, GroupSoA g, TapSoA taps, int ngroups_total,
                                const GeoRec* recs, size_t rec_stride, const PairHdr* hdrs, int nq_alloc, int margin_q, int interpolate, int xunder,
-                               int zunder, int wcap, float* seis, size_t seis_stride, SeisHdr* shdrs, int* overflow, cudaStream_t st, const float4* trig) {
-    const size_t smem = synth_exact_smem_bytes(wcap);
+                               int zunder, int wcap, int blk_cap, float* seis, size_t seis_stride, SeisHdr* shdrs, int* overflow, cudaStream_t st,
+                               const float4* trig) {
+    const size_t smem = synth_exact_smem_bytes(wcap, blk_cap);
     cudaError_t e = cudaFuncSetAttribute(k_synth_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (ncand * nrcv > 0)
         k_synth_exact<<<ncand * nrcv, SX_THREADS, smem, st>>>(db, rcv, nrcv, cands, g, taps, ngroups_total, recs, rec_stride, hdrs, nq_alloc, margin_q,
-                                                             interpolate, xunder, zunder, wcap, seis, seis_stride, shdrs, overflow, trig);
+                                                             interpolate, xunder, zunder, wcap, blk_cap, seis, seis_stride, shdrs, overflow, trig);
     return cudaGetLastError();
 }
