@@ -906,7 +906,9 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
             std::vector<float> ne((size_t)2 * Galloc), lam((size_t)Galloc, 0.f);
             CU_OK(cudaMemcpyAsync(ne.data(), g.north, sizeof(float) * 2 * (size_t)Galloc, cudaMemcpyDeviceToHost, st));   // north, east: adjacent
             CU_OK(cudaStreamSynchronize(st));
-            const int nth = G >= 8192 ? (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())) : 1;
+            // (a fifth of a millisecond per 1e4 sub-sources on one core; starting threads inside a process that holds a CUDA context was
+            //  measured at 2-3 ms, so only very large batches are spread)
+            const int nth = G >= 400000 ? (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())) : 1;
             if (nth > 1) {
                 std::vector<std::thread> pool;
                 for (int t = 0; t < nth; t++)
