@@ -14,6 +14,8 @@
 #include <algorithm>
 #include <atomic>
 #include <thread>
+#include <mutex>
+#include <condition_variable>
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -30,6 +32,62 @@
     } while (0)
 
 namespace {
+
+// Host worker threads that live as long as the context: starting a thread inside a process that holds a CUDA context was measured at
+// 2-3 ms, which is the whole host preparation of a small batch.  run(count, body) executes body(0..count-1), dealing the items out in
+// order (long items first is the caller's business), and returns when all are done; the calling thread works too.
+class WorkerPool {
+public:
+    explicit WorkerPool(int nthreads) {
+        for (int t = 0; t < nthreads; t++) threads_.emplace_back([this]() { loop(); });
+    }
+    ~WorkerPool() {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
+        cv_.notify_all();
+        for (std::thread& t : threads_) t.join();
+    }
+    int size() const { return (int)threads_.size() + 1; }
+    void run(size_t count, const std::function<void(size_t)>& body) {
+        if (count == 0) return;
+        if (count == 1 || threads_.empty()) { for (size_t k = 0; k < count; k++) body(k); return; }
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            body_ = &body; count_ = count; next_.store(0); pending_ = (int)threads_.size(); generation_++;
+        }
+        cv_.notify_all();
+        for (size_t k = next_.fetch_add(1); k < count; k = next_.fetch_add(1)) body(k);
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this]() { return pending_ == 0; });
+        body_ = nullptr;
+    }
+private:
+    void loop() {
+        unsigned long long seen = 0;
+        for (;;) {
+            const std::function<void(size_t)>* body; size_t count;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&]() { return stop_ || generation_ != seen; });
+                if (stop_) return;
+                seen = generation_; body = body_; count = count_;
+            }
+            for (size_t k = next_.fetch_add(1); k < count; k = next_.fetch_add(1)) (*body)(k);
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if (--pending_ == 0) done_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(size_t)>* body_ = nullptr;
+    size_t count_ = 0;
+    std::atomic<size_t> next_{0};
+    int pending_ = 0;
+    unsigned long long generation_ = 0;
+    bool stop_ = false;
+};
 
 struct DevBuf {
     void* p = nullptr;
@@ -115,6 +173,7 @@ struct kiwi_ctx {
     int tw_n = 0;                            // twiddle table exp(-2 pi i k / tw_n), k < tw_n/2
     std::vector<int> last_fshift;            // floating shifts of the last ns = 1 evaluation
     PinBuf h_stage, h_out, h_mt, h_eik;
+    std::unique_ptr<WorkerPool> pool;       // host worker threads (created on first use)
     size_t work_budget = 0;
     kh::Crust2x2 crust;                      // crust2x2 model (minimizer.f90:1669-1674), needed by the eikonal sources
     std::vector<kh::Halfspace> constraints;  // psm%constraints (parameterized_source.f90:127-166)
@@ -272,6 +331,11 @@ bool all_refs_set(const kiwi_ctx* c) {
     return true;
 }
 
+WorkerPool& workers(kiwi_ctx* c) {
+    if (!c->pool) c->pool.reset(new WorkerPool((int)std::max(1u, std::thread::hardware_concurrency()) - 1));
+    return *c->pool;
+}
+
 void eikonal_to_prep(const kh::EikonalPrep& e, kh::SourcePrep* sp) {
     kh::SourcePrep& o = *sp;
     o = kh::SourcePrep();
@@ -320,13 +384,7 @@ int prep_eikonal_batch_device(kiwi_ctx* c, int sourcetype, int n, int nparams, c
     std::vector<kh::EikonalWork> works(n);
     std::vector<kh::EikonalPrep> eps(n);
     const int ncores = (int)std::max(1u, std::thread::hardware_concurrency());
-    auto parallel_over = [&](size_t count, const std::function<void(size_t)>& body) {
-        std::atomic<size_t> next(0);
-        std::vector<std::thread> pool;
-        const int nt = (int)std::min<size_t>(count, (size_t)ncores);
-        for (int t = 0; t < nt; t++) pool.emplace_back([&]() { for (size_t k = next.fetch_add(1); k < count; k = next.fetch_add(1)) body(k); });
-        for (std::thread& t : pool) t.join();
-    };
+    auto parallel_over = [&](size_t count, const std::function<void(size_t)>& body) { workers(c).run(count, body); };
     for (int i = 0; i < n; i++) {   // geometry of the fine grids (cheap)
         bad[i] = kh::prep_eikonal_setup(params + (size_t)i * nparams, mt, c->effective_dt, c->olat, c->olon, c->crust, c->constraints, &works[i], &eps[i]) ? 0 : 1;
         if (bad[i]) errs[i] = eps[i].err;
@@ -759,11 +817,7 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
             if (prep_eikonal_batch_device(c, sourcetype, n, nparams, params, prep, bad, errs, device_min < 0)) return 1;
             for (int i = 0; i < n; i++) if (bad[i]) prep[i] = kh::SourcePrep();
         } else if (nthreads > 1) {
-            std::atomic<int> next(0);
-            std::vector<std::thread> pool;
-            for (int t = 0; t < nthreads; t++)
-                pool.emplace_back([&]() { for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) work(i); });
-            for (std::thread& t : pool) t.join();
+            workers(c).run((size_t)n, [&](size_t i) { work((int)i); });
         } else {
             for (int i = 0; i < n; i++) work(i);
         }
@@ -906,14 +960,10 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
             std::vector<float> ne((size_t)2 * Galloc), lam((size_t)Galloc, 0.f);
             CU_OK(cudaMemcpyAsync(ne.data(), g.north, sizeof(float) * 2 * (size_t)Galloc, cudaMemcpyDeviceToHost, st));   // north, east: adjacent
             CU_OK(cudaStreamSynchronize(st));
-            // (a fifth of a millisecond per 1e4 sub-sources on one core; starting threads inside a process that holds a CUDA context was
-            //  measured at 2-3 ms, so only very large batches are spread)
-            const int nth = G >= 400000 ? (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())) : 1;
-            if (nth > 1) {
-                std::vector<std::thread> pool;
-                for (int t = 0; t < nth; t++)
-                    pool.emplace_back([&, t]() { for (int k = (int)((long long)G * t / nth); k < (int)((long long)G * (t + 1) / nth); k++) lam[k] = atan2f(ne[(size_t)Galloc + k], ne[k]); });
-                for (std::thread& th : pool) th.join();
+            // (a fifth of a millisecond per 1e4 sub-sources on one core: spread over the context's worker threads from a few thousand on)
+            if (G >= 4096) {
+                const size_t nblk = ((size_t)G + 2047) / 2048;
+                workers(c).run(nblk, [&](size_t b) { for (int k = (int)(b * 2048); k < std::min(G, (int)((b + 1) * 2048)); k++) lam[k] = atan2f(ne[(size_t)Galloc + k], ne[k]); });
             } else {
                 for (int k = 0; k < G; k++) lam[k] = atan2f(ne[(size_t)Galloc + k], ne[k]);
             }
@@ -932,16 +982,13 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
             std::vector<float4> trig(na);
             CU_OK(cudaMemcpyAsync(azf.data(), c->d_azf.p, sizeof(float) * na, cudaMemcpyDeviceToHost, st));
             CU_OK(cudaStreamSynchronize(st));
-            const int nth = (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), std::max<size_t>(1, na / 65536));
-            std::vector<std::thread> pool;
-            for (int t = 0; t < nth; t++)
-                pool.emplace_back([&, t]() {
-                    for (size_t k = na * t / nth; k < na * (t + 1) / nth; k++) {
-                        const float a = azf[k];
-                        trig[k] = make_float4(cosf(a), sinf(a), sinf(2.f * a), cosf(2.f * a));
-                    }
-                });
-            for (std::thread& th : pool) th.join();
+            const size_t nblk = (na + 16383) / 16384;
+            workers(c).run(nblk, [&](size_t b) {
+                for (size_t k = b * 16384; k < std::min(na, (b + 1) * 16384); k++) {
+                    const float a = azf[k];
+                    trig[k] = make_float4(cosf(a), sinf(a), sinf(2.f * a), cosf(2.f * a));
+                }
+            });
             CU_OK(c->d_trig.ensure(sizeof(float4) * na));
             CU_OK(cudaMemcpyAsync(c->d_trig.p, trig.data(), sizeof(float4) * na, cudaMemcpyHostToDevice, st));
             CU_OK(cudaStreamSynchronize(st));
