@@ -187,7 +187,9 @@ struct kiwi_ctx {
     // grid, 2.4 s); sharing gives the device the small grids while the host threads work through the large ones.
     int eikonal_device_min = getenv("KIWI_EIKONAL_DEVICE_MIN") ? atoi(getenv("KIWI_EIKONAL_DEVICE_MIN")) : -1;
     int eikonal_last_device_solves = 0;      // solves of the last batch that ran on the device
-    bool accum_reference = false;            // kiwi_set_accumulation: synthesis in the reference's order of operations (synth_exact.cu)
+    // kiwi_set_accumulation: synthesis in the reference's order of operations (synth_exact.cu); KIWI_ACCUMULATION=reference makes it the default,
+    // for drivers that talk to the command front-end and are not to be touched
+    bool accum_reference = getenv("KIWI_ACCUMULATION") && std::string(getenv("KIWI_ACCUMULATION")) == "reference";
     bool mt_grid_fused = true;               // ... with the synthesis fused into it where the windows fit (k_mt_fused)
     DevBuf d_map, d_status_out;
     DevBuf d_taprec;              // shift table of the current batch (k_tap_table)

@@ -104,7 +104,7 @@ bool do_command(State& S, const std::string& cmd, const std::vector<std::string>
                                   "shift_ref_seismogram", "autoshift_ref_seismogram", "set_misfit_filter_1", "output_cross_correlations",
                                   "get_cached_traces_memory", "set_cached_traces_memory_limit", "set_verbose", "set_ignore_sigint",
                                   "get_principal_axes", "get_source_crustal_thickness", "output_distances", "output_seismogram_spectra",
-                                  "output_source_model"};
+                                  "output_source_model", "set_accumulation"};
     bool is_known = false;
     for (const char* k : known) if (cmd == k) is_known = true;
     if (!is_known) return fail("unknown command: " + cmd);   // minimizer.f90:1809-1811
@@ -311,6 +311,10 @@ bool do_command(State& S, const std::string& cmd, const std::vector<std::string>
         return true;
     }
     if (cmd == "set_cached_traces_memory_limit" || cmd == "set_verbose" || cmd == "set_ignore_sigint") return true;   // nothing to steer here
+    if (cmd == "set_accumulation") {   // extension: order of the floating-point operations of the synthesis (kiwi_set_accumulation)
+        if (w.size() != 2 || (w[1] != "reference" && w[1] != "batched")) return fail("usage: set_accumulation reference|batched");
+        return kiwi_set_accumulation(S.ctx, w[1] == "reference" ? 1 : 0) ? cfail() : true;
+    }
     if (cmd == "set_synthetics_factor") {
         if (!to_floats(w, 1, &v) || v.size() != 1) return fail("usage: set_synthetics_factor factor");
         return kiwi_set_synthetics_factor(S.ctx, v[0]) ? cfail() : true;

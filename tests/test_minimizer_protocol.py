@@ -158,3 +158,31 @@ def test_session_with_interpolated_database_and_autoshift(tmp_path):
     e.set_database(db, 2, 1)
     m = e._db.meta()
     assert m["nx"] == 2 * db.meta()["nx"] and abs(m["dx"] - db.meta()["dx"] / 2) < 1e-3
+
+
+@pytest.mark.gpu
+def test_set_accumulation_command(tmp_path):
+    """the front-end's extension `set_accumulation reference|batched` (kiwi_set_accumulation): with `reference` the seismogram files hold
+    the oracle's samples bit for bit"""
+    from oracle_lib import OracleEngine
+    db = sc.small_db()
+    dbfile = tmp_path / "db.kgf1"
+    db.write(dbfile)
+    lat, lon, dep = sc.small_receivers(2)
+    comps = ["ned", "ar"]
+    rfile = tmp_path / "receivers.table"
+    with open(rfile, "w") as f:
+        for a, b, c, d in zip(lat, lon, dep, comps):
+            f.write("%.10f %.10f %g %s\n" % (a, b, c, d))
+    p = " ".join("%.9g" % v for v in sc.BILAT_SMALL)
+    base = str(tmp_path / "syn")
+    out = talk(["set_database %s" % dbfile, "set_local_interpolation bilinear", "set_receivers %s has_depth" % rfile,
+                "set_source_location %g %g 0" % sc.ORIGIN, "set_effective_dt 0.2", "set_accumulation nonsense", "set_accumulation reference",
+                "set_source_params bilateral " + p, "output_seismograms %s table synthetics plain" % base, "set_accumulation batched"])
+    assert "set_accumulation: nok >" in out and out.count("set_accumulation: ok") == 2 and "output_seismograms: ok" in out, out
+    o = OracleEngine()
+    sc.setup(o, db, lat, lon, dep, comps)
+    o.eval_sources("bilateral", sc.BILAT_SMALL)
+    first, data = o.get_seismogram(1, 1, 1)
+    tab = np.loadtxt(base + "-1-n.table")
+    assert tab.shape[0] == data.size and np.array_equal(tab[:, 1].astype(np.float32), data)      # (%.9g: every fp32 value survives the file)
