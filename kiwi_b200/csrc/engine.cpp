@@ -390,7 +390,6 @@ int prep_eikonal_batch_device(kiwi_ctx* c, int sourcetype, int n, int nparams, c
     for (int i = 0; i < n; i++) {   // geometry of the fine grids (cheap)
         bad[i] = kh::prep_eikonal_setup(params + (size_t)i * nparams, mt, c->effective_dt, c->olat, c->olon, c->crust, c->constraints, &works[i], &eps[i]) ? 0 : 1;
         if (bad[i]) errs[i] = eps[i].err;
-        if (!bad[i] && c->constraints.size() > 4) { bad[i] = 1; errs[i] = "more than four constraints"; }
     }
     auto nodes_of = [&](int i) { return (size_t)works[i].fnx * works[i].fny; };
     size_t fr = 0, tot = 0;
@@ -815,7 +814,7 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
         // of a batch between the host threads and the device where that is faster (the default); 0 = host only
         const int device_min = c->eikonal_device_min;
         c->eikonal_last_device_solves = 0;
-        if (heavy && ((device_min > 0 && n >= device_min) || (device_min < 0 && n >= 2))) {
+        if (heavy && c->constraints.size() <= 4 && ((device_min > 0 && n >= device_min) || (device_min < 0 && n >= 2))) {   // (EikGeom holds four half-spaces)
             if (prep_eikonal_batch_device(c, sourcetype, n, nparams, params, prep, bad, errs, device_min < 0)) return 1;
             for (int i = 0; i < n; i++) if (bad[i]) prep[i] = kh::SourcePrep();
         } else if (nthreads > 1) {
