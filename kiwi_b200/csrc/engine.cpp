@@ -1196,18 +1196,31 @@ int eval_mt_grid(kiwi_ctx* c, int n, const float* params, float* d_out, int* h_s
     std::vector<int> first_of;
     // grids usually list their candidates location by location: the table is asked once per run, and if no location comes back after
     // another one has started (`runs`), the candidates are already sorted by location
-    Key prev; int prev_loc = -1;
     bool runs = true;
-    const unsigned* up = reinterpret_cast<const unsigned*>(params);
-    for (int i = 0; i < n; i++, up += 11) {
-        if (prev_loc >= 0 && up[0] == prev.v[0] && up[1] == prev.v[1] && up[2] == prev.v[2] && up[3] == prev.v[3] && up[10] == prev.v[4]) { loc_of[i] = prev_loc; continue; }
-        Key k;
-        k.v[0] = up[0]; k.v[1] = up[1]; k.v[2] = up[2]; k.v[3] = up[3]; k.v[4] = up[10];
-        auto it = ids.find(k);
-        if (it == ids.end()) { it = ids.emplace(k, (int)first_of.size()).first; first_of.push_back(i); }
-        else runs = false;
-        loc_of[i] = prev_loc = it->second;
-        prev = k;
+    const unsigned* up0 = reinterpret_cast<const unsigned*>(params);
+    {
+        // where a run of equal locations starts (worker threads), the table only at the starts, the runs' members again on the workers
+        std::vector<char> starts(n);
+        const size_t blk = 8192, nblk = ((size_t)n + blk - 1) / blk;
+        workers(c).run(nblk, [&](size_t b) {
+            for (size_t i = b * blk; i < std::min((size_t)n, (b + 1) * blk); i++) {
+                const unsigned* u = up0 + i * 11;
+                starts[i] = i == 0 || u[0] != u[-11] || u[1] != u[-10] || u[2] != u[-9] || u[3] != u[-8] || u[10] != u[-1];
+            }
+        });
+        std::vector<int> run_begin, run_loc;
+        for (int i = 0; i < n; i++) {
+            if (!starts[i]) continue;
+            const unsigned* u = up0 + (size_t)i * 11;
+            Key k;
+            k.v[0] = u[0]; k.v[1] = u[1]; k.v[2] = u[2]; k.v[3] = u[3]; k.v[4] = u[10];
+            auto it = ids.find(k);
+            if (it == ids.end()) { it = ids.emplace(k, (int)first_of.size()).first; first_of.push_back(i); }
+            else runs = false;
+            run_begin.push_back(i); run_loc.push_back(it->second);
+        }
+        run_begin.push_back(n);
+        workers(c).run(run_loc.size(), [&](size_t r) { for (int i = run_begin[r]; i < run_begin[r + 1]; i++) loc_of[i] = run_loc[r]; });
     }
     const int nloc = (int)first_of.size();
     if ((long long)nloc * 8 > n) return 0;   // fewer than 8 tensors per location on average: the direct path is as good
@@ -1220,10 +1233,13 @@ int eval_mt_grid(kiwi_ctx* c, int n, const float* params, float* d_out, int* h_s
     int* cand_of = reinterpret_cast<int*>(c->h_mt.as<char>() + off_cand);
     if (runs) {   // sorted already: location l is the run [first_of[l], first_of[l+1])
         for (int l = 0; l < nloc; l++) locs[l] = MtLocHost{first_of[l], (l + 1 < nloc ? first_of[l + 1] : n) - first_of[l]};
-        for (int i = 0; i < n; i++) {
-            cand_of[i] = i;
-            memcpy(&mts[(size_t)i * 6], params + (size_t)i * 11 + 4, sizeof(float) * 6);
-        }
+        const size_t blk = 8192, nblk = ((size_t)n + blk - 1) / blk;
+        workers(c).run(nblk, [&](size_t b) {
+            for (size_t i = b * blk; i < std::min((size_t)n, (b + 1) * blk); i++) {
+                cand_of[i] = (int)i;
+                memcpy(&mts[i * 6], params + i * 11 + 4, sizeof(float) * 6);
+            }
+        });
     } else {
         for (int l = 0; l < nloc; l++) locs[l] = MtLocHost{0, 0};
         for (int i = 0; i < n; i++) locs[loc_of[i]].mt_count++;
@@ -1318,10 +1334,13 @@ int eval_mt_grid(kiwi_ctx* c, int n, const float* params, float* d_out, int* h_s
             CU_OK(cudaMemcpyAsync(nonfinite.data(), c->d_status_out.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
             CU_OK(cudaStreamSynchronize(c->stream));
         }
-        for (int i = 0; i < n; i++) {
-            const int bs = bstatus[(size_t)loc_of[i] * 6];
-            h_status[i] = bs != KIWI_STATUS_OK ? bs : ((nbad > 0 && nonfinite[i]) ? KIWI_STATUS_NONFINITE : KIWI_STATUS_OK);
-        }
+        const size_t blk = 16384, nblk = ((size_t)n + blk - 1) / blk;
+        workers(c).run(nblk, [&](size_t b) {
+            for (size_t i = b * blk; i < std::min((size_t)n, (b + 1) * blk); i++) {
+                const int bs = bstatus[(size_t)loc_of[i] * 6];
+                h_status[i] = bs != KIWI_STATUS_OK ? bs : ((nbad > 0 && nonfinite[i]) ? KIWI_STATUS_NONFINITE : KIWI_STATUS_OK);
+            }
+        });
     }
     if (trace) {
         const auto tg3 = std::chrono::steady_clock::now();
