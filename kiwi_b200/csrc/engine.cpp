@@ -913,7 +913,7 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
             c->launches[0] += 1;
         } else {   // groups defined on the host: the single group of a point moment tensor
                    // (source_moment_tensor.f90:256-263), the sub-faults of an eikonal source (source_eikonal.f90:684-707)
-            std::vector<float> hf((size_t)11 * Galloc, 0.f);
+            std::vector<float> hf((size_t)12 * Galloc, 0.f);
             std::vector<int> hi((size_t)6 * Galloc, 0);
             for (int i = 0; i < nc; i++) {
                 const kh::SourcePrep& sp = prep[b0 + i];
@@ -936,8 +936,10 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
                         hi[gi] = cands[i].tap_begin; hi[(size_t)Galloc + gi] = sp.nt;
                     }
                     for (int q = 0; q < 6; q++) hf[(4 + q) * (size_t)Galloc + gi] = sp.mhat[q];
+                    hf[11 * (size_t)Galloc + gi] = atan2f(hf[(size_t)Galloc + gi], hf[gi]);   // the host library's atan2f(east, north), see below
                 }
             }
+            g.lam = gf + 11 * (size_t)Galloc;
             CU_OK(cudaMemcpyAsync(c->d_gf.p, hf.data(), sizeof(float) * hf.size(), cudaMemcpyHostToDevice, st));
             CU_OK(cudaMemcpyAsync(c->d_gi.p, hi.data(), sizeof(int) * hi.size(), cudaMemcpyHostToDevice, st));
             CU_OK(cudaStreamSynchronize(st));
@@ -957,7 +959,8 @@ int eval_batch(kiwi_ctx* c, int sourcetype, int n, int nparams, const float* par
             CU_OK(cudaMemcpyAsync(c->d_tmax.p, init3, sizeof init3, cudaMemcpyHostToDevice, st));
         }
         const bool exact = c->accum_reference && !hook;
-        {   // atan2f of the sub-source positions from the host library (see approx_differential_azidist in kernels.cu)
+        if (!g.lam) {   // atan2f of the sub-source positions from the host library (see approx_differential_azidist in kernels.cu); sources whose
+                        // sub-sources were laid out on the host have it already
             std::vector<float> ne((size_t)2 * Galloc), lam((size_t)Galloc, 0.f);
             CU_OK(cudaMemcpyAsync(ne.data(), g.north, sizeof(float) * 2 * (size_t)Galloc, cudaMemcpyDeviceToHost, st));   // north, east: adjacent
             CU_OK(cudaStreamSynchronize(st));
