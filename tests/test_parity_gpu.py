@@ -69,14 +69,14 @@ def test_indices_shifts_spans_bit_exact(interp, under):
     for ir in range(1, 7):
         ig, io = g.get_indices(ir), o.get_indices(ir)
         assert ig["ix"].size == io["ix"].size == 204
-        ok = ig["near"] == 0   # device libm vs glibc may differ only where the coordinate sits on a cell edge
+        ok = ig["near"] == 0   # the device still reports the pairs whose coordinate sits on a cell edge
         nflag += int((~ok).sum())
+        # all of them equal, flagged or not, to the last bit: since round 2 the one transcendental of the distance chain whose device
+        # version differs from glibc's often enough to matter (atan2f of the sub-source azimuth) comes from the host library
         for k in ("ix", "iz", "its"):
-            assert np.array_equal(ig[k][ok], io[k][ok]), k
-        assert np.array_equal(ig["its"], io["its"])
-        # dix/diz derive from real(dist): equal unless fp64 libm differs in the last bits (SURVEY.md 7 hard part 1)
-        assert np.allclose(ig["dix"][ok], io["dix"][ok], rtol=0, atol=2e-4)
-        assert np.allclose(ig["diz"][ok], io["diz"][ok], rtol=0, atol=0)
+            assert np.array_equal(ig[k], io[k]), k
+        assert np.array_equal(ig["dix"].view(np.uint32), io["dix"].view(np.uint32))
+        assert np.array_equal(ig["diz"].view(np.uint32), io["diz"].view(np.uint32))
         for ic in range(1, len(COMPS6[ir - 1]) + 1):
             fg, dg = g.get_seismogram(ir, ic)
             fo, do = o.get_seismogram(ir, ic)
