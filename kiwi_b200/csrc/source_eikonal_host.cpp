@@ -174,29 +174,34 @@ struct IndexHeap {
     int n = 0, cap = 0;
     void init(int maxsize) { item.assign((size_t)maxsize + 1, HeapItem{0.f, 0}); n = 0; cap = maxsize; }
 };
+// (the sift loops move a hole instead of swapping: the same comparisons and the same final arrangement as heap.f90's swaps, half the writes)
 static inline void upheap(IndexHeap& h, int element, int* bp) {   // :210-232
     HeapItem* a = h.item.data();
     int v = element;
+    const HeapItem x = a[v];
+    bool moved = false;
     while (v > 1) {
         const int u = (v - 2) / 2 + 1;
-        if (a[u].key <= a[v].key) return;
-        std::swap(a[u], a[v]);
-        bp[a[u].idx] = u; bp[a[v].idx] = v;
-        v = u;
+        if (a[u].key <= x.key) break;
+        a[v] = a[u]; bp[a[v].idx] = v;
+        v = u; moved = true;
     }
+    if (moved) { a[v] = x; bp[x.idx] = v; }
 }
 static inline void downheap(IndexHeap& h, int element, int* bp) {   // :176-208
     HeapItem* a = h.item.data();
     int v = element;
+    const HeapItem x = a[v];
+    bool moved = false;
     int w = 2 * (v - 1) + 2;
     while (w <= h.n) {
         if (w + 1 <= h.n && a[w + 1].key < a[w].key) w = w + 1;
-        if (a[v].key <= a[w].key) return;
-        std::swap(a[v], a[w]);
-        bp[a[v].idx] = v; bp[a[w].idx] = w;
-        v = w;
+        if (x.key <= a[w].key) break;
+        a[v] = a[w]; bp[a[v].idx] = v;
+        v = w; moved = true;
         w = 2 * (v - 1) + 2;
     }
+    if (moved) { a[v] = x; bp[x.idx] = v; }
 }
 static inline void pushheap(IndexHeap& h, int keyindex, const float* keys, int* bp) {   // :70-93
     if (h.n + 1 > h.cap) return;
