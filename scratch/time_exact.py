@@ -13,8 +13,9 @@ for name in ("c3", "c5"):
     for mode in (0, 1):
         g.set_accumulation(mode)
         mg, sg = g.eval_sources("bilateral", p)
+        mg, sg = g.eval_sources("bilateral", p)      # (second call: buffers and worker threads exist)
         t = g.last_timing()
-        print(name, "mode", mode, "synthesis ms per candidate", t["synthesis_ms"] / 2, flush=True)
+        print(name, "mode", mode, "per candidate: synthesis ms", t["synthesis_ms"] / 2, "geometry ms", t["geometry_ms"] / 2, "total ms", t["total_ms"] / 2, flush=True)
         if name == "c3":
             mo, so = o.eval_sources("bilateral", p)
             print("   misfits vs fp32 oracle: max rel dev", float(np.max(np.abs(mg - mo) / np.maximum(np.abs(mo), 1e-30))), " rel to norm factor", float(np.max(np.abs(mg - mo) / np.abs(mo[..., 1:2]))), flush=True)
