@@ -15,10 +15,16 @@
 #include "kernels.cuh"
 #include <cfloat>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 #include <algorithm>
 
-#define EIK_HCAP 2040          // heap entries kept in shared memory (16 KB per candidate: 13 candidates per SM); the rest spills to global memory
+// Heap entries kept in shared memory; the rest spills to global memory.  Two builds of the solver: 2040 entries (16 KB per candidate,
+// 13 candidates per SM) for batches that fit one such wave, 980 entries (8 KB, 26 per SM) for larger batches -- a warp spends its time
+// in dependent fixed-latency instructions (profiles/r02_k_eikonal_fmm_full.md: issue slots 13.5 % at 13 warps per SM), so twice the
+// resident solves is close to twice the throughput, at the price of the deepest heap level of the larger fronts living in L2.
+#define EIK_HCAP_LARGE 2040
+#define EIK_HCAP_SMALL 980
 
 namespace {
 
@@ -36,6 +42,7 @@ __device__ __forceinline__ void sts_item(unsigned addr, const EikItem& v) {
 }
 __device__ __forceinline__ void sts_key(unsigned addr, float k) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "f"(k) : "memory"); }
 
+template <int EIK_HCAP>
 struct EikHeap {
     unsigned sbase;     // shared address of entry 0 of the shared-memory part (entries 1..EIK_HCAP used, 8 bytes each)
     EikItem* ovf;       // global overflow, entries EIK_HCAP+1 ...
@@ -62,67 +69,65 @@ struct EikHeap {
         bp[v.idx] = i;
     }
     __device__ __forceinline__ void setkey(int i, float k) { if (i <= EIK_HCAP) sts_key(sbase + 8u * (unsigned)i, k); else ovf[i - EIK_HCAP].key = k; }
-    // heap.f90:210-232
+    // heap.f90:210-232.  The part of the path that lies in the global overflow first, then the shared-memory part to the root.
     __device__ void upheap(int v) {
-        EikItem x = get(v);
-        bool moved = false;
-        if (v <= EIK_HCAP) {   // the whole path to the root is in shared memory
-            while (v > 1) {
-                const int u = v >> 1;            // (v - 2) / 2 + 1
-                const EikItem p = lds_item(sbase + 8u * (unsigned)u);
-                if (p.key <= x.key) break;
-                sts_item(sbase + 8u * (unsigned)v, p); bp[p.idx] = v; track(p.idx, v);
-                v = u; moved = true;
-            }
-            if (moved) { sts_item(sbase + 8u * (unsigned)v, x); bp[x.idx] = v; track(x.idx, v); }
-            return;
-        }
-        while (v > 1) {
+        const EikItem x = get(v);
+        const int v0 = v;
+        while (v > EIK_HCAP) {                   // (not entered while the whole heap is in shared memory, the usual case)
             const int u = (v - 2) / 2 + 1;
             const EikItem p = get(u);
-            if (p.key <= x.key) break;
+            if (p.key <= x.key) { if (v != v0) put(v, x); return; }
             put(v, p);
-            v = u; moved = true;
+            v = u;
         }
-        if (moved) put(v, x);
+        while (v > 1) {
+            const int u = v >> 1;                // (v - 2) / 2 + 1
+            const EikItem p = lds_item(sbase + 8u * (unsigned)u);
+            if (p.key <= x.key) break;
+            sts_item(sbase + 8u * (unsigned)v, p); bp[p.idx] = v; track(p.idx, v);
+            v = u;
+        }
+        if (v != v0) { sts_item(sbase + 8u * (unsigned)v, x); bp[x.idx] = v; track(x.idx, v); }
     }
-    // heap.f90:176-208.  The children of entry v are entries 2v and 2v+1: one 16-byte read while both are in shared memory.
+    // heap.f90:176-208: item x sinks from entry v (x_in_place: it is stored there already).  The children of entry v are entries 2v
+    // and 2v+1: one 16-byte read while both are in shared memory.
     template <bool TRACK>
-    __device__ void downheap_t(int v) {
-        EikItem x = get(v);
-        bool moved = false;
+    __device__ void sink(int v, const EikItem x, const bool x_in_place) {
+        const int v0 = v;
         int w = 2 * v;                           // 2 * (v - 1) + 2
-        if (n <= EIK_HCAP) {   // the whole heap is in shared memory (the usual case)
-            while (w <= n) {
-                EikItem c, c2;
-                lds_pair(sbase + 8u * (unsigned)w, c, c2);   // (w is even: 16-byte aligned; entry n+1 may be stale, it is not used then)
-                if (w < n && c2.key < c.key) { c = c2; w = w + 1; }
-                if (x.key <= c.key) break;
-                sts_item(sbase + 8u * (unsigned)v, c); bp[c.idx] = v;
-                if (TRACK) track(c.idx, v);
-                v = w; moved = true;
-                w = 2 * v;
-            }
-            if (moved) { sts_item(sbase + 8u * (unsigned)v, x); bp[x.idx] = v; if (TRACK) track(x.idx, v); }
-            return;
-        }
-        while (w <= n) {
-            EikItem c = get(w);
-            if (w + 1 <= n) { const EikItem c2 = get(w + 1); if (c2.key < c.key) { c = c2; w = w + 1; } }
-            if (x.key <= c.key) break;
-            if (TRACK) put(v, c); else put_plain(v, c);
-            v = w; moved = true;
+        const int nboth = min(n - 1, EIK_HCAP - 1);   // w <= nboth: both children exist and are in shared memory
+        bool open = true;
+        while (w <= nboth) {
+            EikItem c, c2;
+            lds_pair(sbase + 8u * (unsigned)w, c, c2);   // (w is even: 16-byte aligned)
+            if (c2.key < c.key) { c = c2; w = w + 1; }
+            if (x.key <= c.key) { open = false; break; }
+            sts_item(sbase + 8u * (unsigned)v, c); bp[c.idx] = v;
+            if (TRACK) track(c.idx, v);
+            v = w;
             w = 2 * v;
         }
-        if (moved) { if (TRACK) put(v, x); else put_plain(v, x); }
+        if (open) {
+            while (w <= n) {                     // an only child, or the deepest levels of a heap that reaches into the global overflow
+                EikItem c = get(w);
+                if (w + 1 <= n) { const EikItem c2 = get(w + 1); if (c2.key < c.key) { c = c2; w = w + 1; } }
+                if (x.key <= c.key) break;
+                if (TRACK) put(v, c); else put_plain(v, c);
+                v = w;
+                w = 2 * v;
+            }
+        }
+        if (!x_in_place || v != v0) { if (TRACK) put(v, x); else put_plain(v, x); }
     }
-    __device__ void downheap(int v) { downheap_t<true>(v); }
+    __device__ void downheap(int v) { sink<true>(v, get(v), true); }
 };
 
 }  // namespace
 
+template <int EIK_HCAP>
 __global__ void __launch_bounds__(32) k_eikonal_fmm(const EikJob* __restrict__ jobs, int njobs) {
     __shared__ __align__(16) EikItem s_heap[EIK_HCAP + 2];
+    __shared__ float4 s_x[4];
     const int job = blockIdx.x;
     if (job >= njobs) return;
     const EikJob J = jobs[job];
@@ -130,6 +135,7 @@ __global__ void __launch_bounds__(32) k_eikonal_fmm(const EikJob* __restrict__ j
     const int nx = J.nx, ny = J.ny, nn = nx * ny;
     const float infinity = FLT_MAX * 0.1f;
     const float dx = J.dx, dy = J.dy;
+    const float rnx = 1.f / (float)nx;   // (only to guess a quotient that is then corrected in integers)
     const float dx2 = __fmul_rn(dx, dx), dy2 = __fmul_rn(dy, dy), dx2dy2 = __fmul_rn(dx2, dy2), dx2pdy2 = __fadd_rn(dx2, dy2);
     float* T = J.T - 1;            // 1-based views
     int* bp = J.bp - 1;
@@ -138,7 +144,7 @@ __global__ void __launch_bounds__(32) k_eikonal_fmm(const EikJob* __restrict__ j
     for (int i = 1 + lane; i <= nn; i += 32) { T[i] = infinity; bp[i] = FARAWAY; }
     if (J.invalid_speed > 0.f) for (int i = 1 + lane; i <= nn; i += 32) if (S[i] == 0.f) S[i] = J.invalid_speed;
     __syncwarp();
-    EikHeap H;
+    EikHeap<EIK_HCAP> H;
     H.sbase = (unsigned)__cvta_generic_to_shared(s_heap); H.ovf = J.ovf; H.bp = bp; H.n = 0;
     H.w0 = H.w1 = H.w2 = H.w3 = 0; H.p0 = H.p1 = H.p2 = H.p3 = 0;
     const int ix0 = J.ix0, iy0 = J.iy0;
@@ -176,13 +182,16 @@ __global__ void __launch_bounds__(32) k_eikonal_fmm(const EikJob* __restrict__ j
             const EikItem top = H.get(1), last = H.get(H.n);
             imin = top.idx;
             H.n = H.n - 1;
-            if (H.n >= 1) { H.put_plain(1, last); H.downheap_t<false>(1); }
+            if (H.n >= 1) H.template sink<false>(1, last, false);   // (the last entry moves to the root and sinks)
             bp[imin] = ALIVE;
         }
         __syncwarp();
         imin = __shfl_sync(0xffffffffu, imin, 0);
         nalive = nalive + 1;
-        const int iy = (imin - 1) / nx + 1, ix = imin - (iy - 1) * nx;
+        int iy = __float2int_rz(__fmul_rn(__int2float_rn(imin - 1), rnx)), ix = imin - 1 - iy * nx;   // (imin - 1) / nx and the remainder
+        while (ix < 0) { iy = iy - 1; ix = ix + nx; }
+        while (ix >= nx) { iy = iy + 1; ix = ix - nx; }
+        iy = iy + 1; ix = ix + 1;
         // ---- the four neighbour stencils, lanes 0..3: left, right, down, up (eikonal.f90:134-190) -----------------------
         int i = 0, state = ALIVE;      // state: ALIVE (skip), FARAWAY, or > 0 (in the heap)
         float t = 0.f, told = 0.f;
@@ -227,15 +236,19 @@ __global__ void __launch_bounds__(32) k_eikonal_fmm(const EikJob* __restrict__ j
             }
         }
         // ---- their heap updates in the reference's order (lane 0) ----------------------------------------------------------
-        {   // the neighbours' heap positions as the stencil lanes read them; put() keeps them current from here on
-            const int i_0 = __shfl_sync(0xffffffffu, i, 0), i_1 = __shfl_sync(0xffffffffu, i, 1), i_2 = __shfl_sync(0xffffffffu, i, 2), i_3 = __shfl_sync(0xffffffffu, i, 3);
-            const int s_0 = __shfl_sync(0xffffffffu, state, 0), s_1 = __shfl_sync(0xffffffffu, state, 1), s_2 = __shfl_sync(0xffffffffu, state, 2), s_3 = __shfl_sync(0xffffffffu, state, 3);
-            H.w0 = i_0; H.w1 = i_1; H.w2 = i_2; H.w3 = i_3; H.p0 = s_0; H.p1 = s_1; H.p2 = s_2; H.p3 = s_3;
-        }
+        // (the four results travel to lane 0 through shared memory: one store and four loads instead of two dozen shuffles)
+        if (lane < 4) s_x[lane] = make_float4(__int_as_float(i), __int_as_float(state), t, told);
+        __syncwarp();
+        float4 xs[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) xs[k] = s_x[k];
+        // the neighbours' heap positions as the stencil lanes read them; put() keeps them current from here on
+        H.w0 = __float_as_int(xs[0].x); H.w1 = __float_as_int(xs[1].x); H.w2 = __float_as_int(xs[2].x); H.w3 = __float_as_int(xs[3].x);
+        H.p0 = __float_as_int(xs[0].y); H.p1 = __float_as_int(xs[1].y); H.p2 = __float_as_int(xs[2].y); H.p3 = __float_as_int(xs[3].y);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const int ik = __shfl_sync(0xffffffffu, i, k), sk = __shfl_sync(0xffffffffu, state, k);
-            const float tk = __shfl_sync(0xffffffffu, t, k), toldk = __shfl_sync(0xffffffffu, told, k);
+            const int ik = __float_as_int(xs[k].x), sk = __float_as_int(xs[k].y);
+            const float tk = xs[k].z, toldk = xs[k].w;
             if (lane == 0 && sk != ALIVE && ik != 0) {
                 if (sk == FARAWAY) {   // pushheap with the node's current (infinite) time
                     H.n = H.n + 1;
@@ -390,11 +403,23 @@ cudaError_t launch_eik_down(const EikGeom* d_geoms, int ncand, int max_cells, co
     return cudaGetLastError();
 }
 
-int eikonal_heap_smem_entries() { return EIK_HCAP; }
+int eikonal_heap_smem_entries() { return EIK_HCAP_SMALL; }   // (a job carries overflow room whenever its grid has more nodes than this)
+int eikonal_wave_jobs(int small_heap) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms * (small_heap ? 26 : 13);
+}
 cudaError_t launch_eikonal_fmm(const EikJob* d_jobs, int njobs, cudaStream_t st) {
     if (njobs <= 0) return cudaSuccess;
-    cudaFuncSetAttribute(k_eikonal_fmm, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    k_eikonal_fmm<<<njobs, 32, 0, st>>>(d_jobs, njobs);
+    static const int forced = [] { const char* e = getenv("KIWI_EIKONAL_HEAP"); return e ? atoi(e) : 0; }();   // measurements: 980 or 2040
+    const bool small = forced ? forced < EIK_HCAP_LARGE : njobs > eikonal_wave_jobs(0);
+    if (small) {
+        cudaFuncSetAttribute(k_eikonal_fmm<EIK_HCAP_SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        k_eikonal_fmm<EIK_HCAP_SMALL><<<njobs, 32, 0, st>>>(d_jobs, njobs);
+    } else {
+        cudaFuncSetAttribute(k_eikonal_fmm<EIK_HCAP_LARGE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        k_eikonal_fmm<EIK_HCAP_LARGE><<<njobs, 32, 0, st>>>(d_jobs, njobs);
+    }
     return cudaGetLastError();
 }
 void eikonal_start_node(const float origin[2], const float delta[2], const float initialpoint[2], int nx, int ny, int* ix0, int* iy0) {   // eikonal.f90:60-67
@@ -420,7 +445,7 @@ extern "C" int kiwi_eikonal_fmm_device(int njobs, const int* nx, const int* ny, 
         float *dS = nullptr, *dT = nullptr; int* dbp = nullptr; EikItem* dovf = nullptr;
         if (cudaMalloc(&dS, nn * 4) != cudaSuccess || cudaMalloc(&dT, nn * 4) != cudaSuccess || cudaMalloc(&dbp, nn * 4) != cudaSuccess) return fail("out of device memory");
         allocs.push_back(dS); allocs.push_back(dT); allocs.push_back(dbp);
-        if (nn > EIK_HCAP) { if (cudaMalloc(&dovf, (nn - EIK_HCAP + 1) * sizeof(EikItem)) != cudaSuccess) return fail("out of device memory"); allocs.push_back(dovf); }
+        if (nn > EIK_HCAP_SMALL) { if (cudaMalloc(&dovf, (nn - EIK_HCAP_SMALL + 1) * sizeof(EikItem)) != cudaSuccess) return fail("out of device memory"); allocs.push_back(dovf); }
         cudaMemcpy(dS, speed[j], nn * 4, cudaMemcpyHostToDevice);
         EikJob& J = jobs[j];
         J.nx = nx[j]; J.ny = ny[j]; J.dx = delta2[2 * j]; J.dy = delta2[2 * j + 1];

@@ -187,6 +187,7 @@ struct kiwi_ctx {
     // grid, 2.4 s); sharing gives the device the small grids while the host threads work through the large ones.
     int eikonal_device_min = getenv("KIWI_EIKONAL_DEVICE_MIN") ? atoi(getenv("KIWI_EIKONAL_DEVICE_MIN")) : -1;
     int eikonal_last_device_solves = 0;      // solves of the last batch that ran on the device
+    double eikonal_dev_node_small = [] { const char* e = getenv("KIWI_EIKONAL_DEV_NODE_SMALL"); return e ? atof(e) : 3.2e-6; }();   // s per node and solve at 26 solves per SM
     // kiwi_set_accumulation: synthesis in the reference's order of operations (synth_exact.cu); KIWI_ACCUMULATION=reference makes it the default,
     // for drivers that talk to the command front-end and are not to be touched
     bool accum_reference = getenv("KIWI_ACCUMULATION") && std::string(getenv("KIWI_ACCUMULATION")) == "reference";
@@ -394,8 +395,8 @@ int prep_eikonal_batch_device(kiwi_ctx* c, int sourcetype, int n, int nparams, c
     auto nodes_of = [&](int i) { return (size_t)works[i].fnx * works[i].fny; };
     size_t fr = 0, tot = 0;
     CU_OK(cudaMemGetInfo(&fr, &tot));
-    const size_t round_nodes = std::max<size_t>((size_t)1 << 22, std::min<size_t>(fr / 3, (size_t)24 << 30) / 20);   // up to 20 bytes per node on the device
-    const int wave_jobs = 148 * 13;                                                                                   // solves resident at a time
+    const size_t round_nodes = std::max<size_t>((size_t)1 << 22, std::min<size_t>(fr / 2, (size_t)80 << 30) / 20);   // up to 20 bytes per node on the device
+    const int wave_large = eikonal_wave_jobs(0), wave_jobs = eikonal_wave_jobs(1);   // solves resident at a time (16 KB / 8 KB heaps, see eikonal.cu)
     const int hcap = eikonal_heap_smem_entries();
     c->eikonal_last_device_solves = 0;
     std::vector<int> valid;
@@ -412,7 +413,7 @@ int prep_eikonal_batch_device(kiwi_ctx* c, int sourcetype, int n, int nparams, c
         // (profiles/r02_eikonal_device.txt): a warp 2.1-2.5 us per node, a host core 0.1 us per node for the solve alone
         int ndev = std::min(nr, wave_jobs);
         if (share) {
-            const double dev_node = 2.4e-6, host_node = 1.05e-7;
+            const double dev_node_large = 2.4e-6, dev_node_small = c->eikonal_dev_node_small, host_node = 1.05e-7;
             double all_host = 0.;
             for (int i : order) all_host += host_node * nodes_of(i);
             double best = all_host / ncores, dev_host = 0.;
@@ -420,7 +421,7 @@ int prep_eikonal_batch_device(kiwi_ctx* c, int sourcetype, int n, int nparams, c
             for (int k = 0; k < nr && k < wave_jobs; k++) {
                 const double nn = (double)nodes_of(order[k]);
                 dev_host += host_node * nn;
-                const double total = std::max(dev_node * nn, (all_host - dev_host) / ncores);   // (nn = the largest grid so far)
+                const double total = std::max((k < wave_large ? dev_node_large : dev_node_small) * nn, (all_host - dev_host) / ncores);   // (nn = the largest grid so far)
                 if (total < 0.97 * best) { best = total; ndev = k + 1; }
             }
         }

@@ -99,5 +99,6 @@ struct EikGeom {
 cudaError_t launch_eik_speed(EikGeom* d_geoms, int ncand, int max_nodes, float* S, cudaStream_t st);
 cudaError_t launch_eik_down(const EikGeom* d_geoms, int ncand, int max_cells, const float* S, const float* T, float* coarse, cudaStream_t st);
 int eikonal_heap_smem_entries();
+int eikonal_wave_jobs(int small_heap);   // solves resident at a time with the 16 KB (0) or the 8 KB (1) heap
 void eikonal_start_node(const float origin[2], const float delta[2], const float initialpoint[2], int nx, int ny, int* ix0, int* iy0);
 cudaError_t launch_eikonal_fmm(const EikJob* d_jobs, int njobs, cudaStream_t st);
