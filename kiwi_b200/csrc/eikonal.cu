@@ -411,7 +411,8 @@ int eikonal_wave_jobs(int small_heap) {
 }
 cudaError_t launch_eikonal_fmm(const EikJob* d_jobs, int njobs, cudaStream_t st) {
     if (njobs <= 0) return cudaSuccess;
-    static const int forced = [] { const char* e = getenv("KIWI_EIKONAL_HEAP"); return e ? atoi(e) : 0; }();   // measurements: 980 or 2040
+    const char* env = getenv("KIWI_EIKONAL_HEAP");   // tests and measurements: 980 or 2040
+    const int forced = env ? atoi(env) : 0;
     const bool small = forced ? forced < EIK_HCAP_LARGE : njobs > eikonal_wave_jobs(0);
     if (small) {
         cudaFuncSetAttribute(k_eikonal_fmm<EIK_HCAP_SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

@@ -36,7 +36,37 @@ def test_bit_exact_against_the_host_solver():
         assert np.array_equal(host.view(np.uint32), t.view(np.uint32)), (sp.shape, d, ip, float(np.abs(host - t).max()))
 
 
-def test_heap_larger_than_its_shared_memory_part():
+@pytest.fixture(params=["2040", "980"])
+def heap_build(request, monkeypatch):
+    """both builds of the solver: 2040 heap entries in shared memory (13 solves per SM, batches of one wave) and 980 (26 per SM, larger
+    batches); KIWI_EIKONAL_HEAP forces one whatever the batch size"""
+    monkeypatch.setenv("KIWI_EIKONAL_HEAP", request.param)
+    return request.param
+
+
+def test_both_heap_builds_bit_exact(heap_build):
+    cases = fields()
+    dev, ms = engine.eikonal_fmm_device([c[0] for c in cases], [c[1] for c in cases], [c[2] for c in cases], [c[3] for c in cases])
+    for (sp, o, d, ip), t in zip(cases, dev):
+        host = engine.eikonal_fmm(sp, o, d, ip)
+        assert np.array_equal(host.view(np.uint32), t.view(np.uint32)), (heap_build, sp.shape)
+
+
+def test_front_around_the_shared_memory_boundary(heap_build):
+    """layered 500 x 500 disc field (what the eikonal sources solve): the front grows through 980 entries and shrinks back, so entries
+    move between the shared-memory part and the global overflow in both directions"""
+    n = 500
+    sp = np.repeat(np.array([2400.0, 3100.0, 3600.0], np.float32)[np.minimum(np.arange(n) * 3 // n, 2)][:, None], n, 1).copy()
+    yy, xx = np.mgrid[0:n, 0:n]
+    sp[(xx - n / 2.0) ** 2 + (yy - n / 2.0) ** 2 > (0.5 * n) ** 2] = 1200.0
+    ip = (n * 12.5 - 3000.0, n * 12.5 + 1500.0)
+    dev, ms = engine.eikonal_fmm_device([sp, sp[:, ::-1].copy()], [(0.0, 0.0)] * 2, [(25.0, 25.0)] * 2, [ip] * 2)
+    for field, t in zip((sp, sp[:, ::-1].copy()), dev):
+        host = engine.eikonal_fmm(field, (0.0, 0.0), (25.0, 25.0), ip)
+        assert np.array_equal(host.view(np.uint32), t.view(np.uint32))
+
+
+def test_heap_larger_than_its_shared_memory_part(heap_build):
     """a thin, long, fast channel in a slow field makes the front (the heap) longer than 4096 entries"""
     ny, nx = 900, 1200
     sp = np.full((ny, nx), 400.0, np.float32)
@@ -47,7 +77,7 @@ def test_heap_larger_than_its_shared_memory_part():
     assert np.array_equal(host.view(np.uint32), dev[0].view(np.uint32))
 
 
-def test_batch_of_eikonal_sources_solved_on_the_device_equals_the_host_path():
+def test_batch_of_eikonal_sources_solved_on_the_device_equals_the_host_path(heap_build):
     """the engine's device path for large batches (kiwi_set_eikonal_device): sub-source tables and misfits identical to the host path's"""
     import scenario as sc
     from test_parity_gpu import COMPS6, EIK, engines
