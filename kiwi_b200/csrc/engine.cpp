@@ -1772,14 +1772,23 @@ int kiwi_outer_misfits(kiwi_ctx* c, int ns, const float* d_misfits, const double
         CU_OK(c->d_obw.ensure(sizeof(double) * (size_t)nboot * nr));
         CU_OK(cudaMemcpyAsync(c->d_obw.p, bweights, sizeof(double) * (size_t)nboot * nr, cudaMemcpyHostToDevice, c->stream));
     }
-    CU_OK(c->d_oout.ensure(sizeof(double) * (size_t)nrows * std::max(ns, 1)));
+    // the [1 + nboot][ns] matrix lives on the device as a whole only if the caller wants it; otherwise blocks of rows are reduced to
+    // their minima one after the other (1000 bootstrap rows of a 10^6-candidate grid would be 8 GB)
+    const size_t row_bytes = sizeof(double) * (size_t)std::max(ns, 1);
+    const char* pass_env = getenv("KIWI_OUTER_PASS_BYTES");   // (tests: a small pass)
+    const size_t pass_bytes = pass_env ? (size_t)atoll(pass_env) : (size_t)256 << 20;
+    const int rows_per_pass = misfits_by_s ? nrows : (int)std::min<size_t>((size_t)nrows, std::max<size_t>(1, pass_bytes / row_bytes));
+    CU_OK(c->d_oout.ensure(row_bytes * rows_per_pass));
     CU_OK(c->d_obest.ensure(sizeof(int) * nrows));
     CU_OK(c->d_obestv.ensure(sizeof(double) * nrows));
     if ((size_t)2 * nr * sizeof(double) > (size_t)200 * 1024) return kiwi_set_error("too many receivers for the outer-misfit kernel");
-    cudaError_t e = launch_outer_misfits(d_misfits, c->nmisfits, c->d_orc.p, nr, receiver_weights ? c->d_orw.as<double>() : nullptr,
-                                         outer_norm == KIWI_L1NORM, anarchy != 0, nrows, nboot > 0 ? c->d_obw.as<double>() : nullptr,
-                                         c->d_oout.as<double>(), ns, c->d_obest.as<int>(), c->d_obestv.as<double>(), c->stream);
-    if (e != cudaSuccess) return kiwi_set_error("CUDA error in the outer-misfit kernel: %s", cudaGetErrorString(e));
+    for (int row0 = 0; row0 < nrows; row0 += rows_per_pass) {
+        cudaError_t e = launch_outer_misfits(d_misfits, c->nmisfits, c->d_orc.p, nr, receiver_weights ? c->d_orw.as<double>() : nullptr,
+                                             outer_norm == KIWI_L1NORM, anarchy != 0, std::min(rows_per_pass, nrows - row0),
+                                             nboot > 0 ? c->d_obw.as<double>() : nullptr, c->d_oout.as<double>(), ns, c->d_obest.as<int>(),
+                                             c->d_obestv.as<double>(), c->stream, row0);
+        if (e != cudaSuccess) return kiwi_set_error("CUDA error in the outer-misfit kernel: %s", cudaGetErrorString(e));
+    }
     if (misfits_by_s && ns > 0) CU_OK(cudaMemcpyAsync(misfits_by_s, c->d_oout.p, sizeof(double) * (size_t)nrows * ns, cudaMemcpyDeviceToHost, c->stream));
     if (best && ns > 0) CU_OK(cudaMemcpyAsync(best, c->d_obest.p, sizeof(int) * nrows, cudaMemcpyDeviceToHost, c->stream));
     if (best_value && ns > 0) CU_OK(cudaMemcpyAsync(best_value, c->d_obestv.p, sizeof(double) * nrows, cudaMemcpyDeviceToHost, c->stream));

@@ -2308,7 +2308,8 @@ struct OuterRcv { int misfit_base, ncomp; };   // enabled receivers only: ncomp 
 __global__ void __launch_bounds__(128) k_outer_misfits(const float* __restrict__ mis /* [ns][nm][2] */, int nm, const OuterRcv* __restrict__ rc,
                                                         int nr, const double* __restrict__ rweights /* [nr] or null */, int l1, int anarchy,
                                                         int nrows, const double* __restrict__ bweights /* [nrows-1][nr] or null */,
-                                                        double* __restrict__ out /* [nrows][ns] */, int ns) {
+                                                        double* __restrict__ out /* [nrows][ns] */, int ns, int row0) {
+    // rows row0 .. row0 + nrows - 1 of the [1 + nboot][ns] matrix (row 0: no bootstrap weights), written to out[0 .. nrows)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* a = reinterpret_cast<double*>(smem_raw);
     double* b = a + nr;
@@ -2332,7 +2333,7 @@ __global__ void __launch_bounds__(128) k_outer_misfits(const float* __restrict__
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int row = 0; row < nrows; row++) {
-        const double* bw = (row == 0 || !bweights) ? nullptr : bweights + (size_t)(row - 1) * nr;
+        const double* bw = (row0 + row == 0 || !bweights) ? nullptr : bweights + (size_t)(row0 + row - 1) * nr;
         double sa = 0., sb = 0.;
         for (int r = threadIdx.x; r < nr; r += blockDim.x) {
             const double k = bw ? bw[r] : 1.0;
@@ -2520,13 +2521,13 @@ cudaError_t launch_fold(const ReceiverDev* rcv, int nrcv, const CandDev* cands, 
 }
 
 cudaError_t launch_outer_misfits(const float* mis, int nm, const void* rc, int nr, const double* rweights, int l1, int anarchy, int nrows,
-                                 const double* bweights, double* out, int ns, int* best, double* bestv, cudaStream_t st) {
+                                 const double* bweights, double* out, int ns, int* best, double* bestv, cudaStream_t st, int row0) {
     const size_t smem = (size_t)2 * nr * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(k_outer_misfits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (ns > 0) {
-        k_outer_misfits<<<ns, 128, smem, st>>>(mis, nm, (const OuterRcv*)rc, nr, rweights, l1, anarchy, nrows, bweights, out, ns);
-        k_row_argmin<<<nrows, 256, 0, st>>>(out, ns, best, bestv);
+        k_outer_misfits<<<ns, 128, smem, st>>>(mis, nm, (const OuterRcv*)rc, nr, rweights, l1, anarchy, nrows, bweights, out, ns, row0);
+        k_row_argmin<<<nrows, 256, 0, st>>>(out, ns, best + row0, bestv + row0);
     }
     return cudaGetLastError();
 }

@@ -64,7 +64,8 @@ void launch_mt_contract(const ReceiverDev* rcv, int nrcv, const MtLoc* locs, int
                         float syn_factor, int nmisfits, float* out, cudaStream_t st);
 void launch_flag_nonfinite(const float* v, int nrows, int ncols, int* flag, int* count /* may be null */, cudaStream_t st);
 cudaError_t launch_outer_misfits(const float* mis, int nm, const void* rc /* {misfit_base, ncomp}[nr] */, int nr, const double* rweights, int l1,
-                                 int anarchy, int nrows, const double* bweights, double* out, int ns, int* best, double* bestv, cudaStream_t st);
+                                 int anarchy, int nrows, const double* bweights, double* out, int ns, int* best, double* bestv, cudaStream_t st,
+                                 int row0 = 0 /* rows row0 .. row0 + nrows - 1 of the [1 + nboot][ns] matrix, written to out[0 .. nrows) */);
 
 // ---- fast-marching solver of the eikonal sources on the device (eikonal.cu) ----------------------------------------------------------
 struct EikItem { float key; int idx; };

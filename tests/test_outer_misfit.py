@@ -26,7 +26,7 @@ def test_restatement_matches_the_engine_formula_for_plain_l2():
 @pytest.mark.gpu
 @pytest.mark.parametrize("outer_norm", ["l2norm", "l1norm"])
 @pytest.mark.parametrize("anarchy", [False, True])
-def test_outer_misfits_on_device(outer_norm, anarchy):
+def test_outer_misfits_on_device(outer_norm, anarchy, monkeypatch):
     from kiwi_b200 import Engine
     from oracle_lib import OracleEngine
     lat, lon, dep = sc.small_receivers(6)
@@ -68,6 +68,10 @@ def test_outer_misfits_on_device(outer_norm, anarchy):
     st2 = g.eval_sources_on_device("bilateral", p)
     out2, best2, _ = g.outer_misfits(receiver_weights=weights, outer_norm=outer_norm, anarchy=anarchy, bweights=bw, want_matrix=True)
     assert np.array_equal(st2, status) and np.array_equal(best2, best) and np.allclose(out2[:, ok], out[:, ok], rtol=0, atol=0)
+    # only the minima wanted: the bootstrap rows are reduced in passes (here three rows at a time), the matrix never exists as a whole
+    monkeypatch.setenv("KIWI_OUTER_PASS_BYTES", str(3 * 9 * 8))
+    out3, best3, bestv3 = g.outer_misfits(receiver_weights=weights, outer_norm=outer_norm, anarchy=anarchy, bweights=bw, want_matrix=False)
+    assert out3 is None and np.array_equal(best3, best) and np.array_equal(bestv3, bestv)
 
 
 @pytest.mark.gpu
