@@ -125,7 +125,7 @@ struct EikHeap {
 }  // namespace
 
 template <int EIK_HCAP>
-__global__ void __launch_bounds__(32) k_eikonal_fmm(const EikJob* __restrict__ jobs, int njobs) {
+__global__ void __launch_bounds__(32) k_eikonal_fmm(const EikJob* __restrict__ jobs, int njobs, int prefetch_entries) {
     __shared__ __align__(16) EikItem s_heap[EIK_HCAP + 2];
     __shared__ float4 s_x[4];
     const int job = blockIdx.x;
@@ -186,6 +186,20 @@ __global__ void __launch_bounds__(32) k_eikonal_fmm(const EikJob* __restrict__ j
             bp[imin] = ALIVE;
         }
         __syncwarp();
+        // What the next pops will read, asked for now (to L2): with thousands of solves in flight the rows around a front do not stay
+        // in L2 between two visits (profiles/r02_k_eikonal_fmm_wave_full.md: hit rate 19 %, the warps wait for DRAM 40 % of the time).
+        // The root after this pop is the next node unless one of the four updates below undercuts it; entries 2 and 3 are its likely
+        // successors.  Lanes 0..10 / 11..21 / 22..31 take one heap entry each: T rows -2..2, S rows -1..1, back-pointer rows -1..1.
+        {
+            const int g = lane / 11, q = lane - g * 11;
+            if (g < prefetch_entries && 1 + g <= hn - 1) {
+                const int m = lds_item(H.sbase + 8u * (unsigned)(1 + g)).idx;
+                const int r = q < 5 ? q - 2 : (q < 8 ? q - 6 : q - 9);
+                const int k = max(1, min(nn, m + r * nx));
+                const void* ptr = q < 5 ? (const void*)(T + k) : (q < 8 ? (const void*)(S + k) : (const void*)(bp + k));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+            }
+        }
         imin = __shfl_sync(0xffffffffu, imin, 0);
         nalive = nalive + 1;
         int iy = __float2int_rz(__fmul_rn(__int2float_rn(imin - 1), rnx)), ix = imin - 1 - iy * nx;   // (imin - 1) / nx and the remainder
@@ -414,12 +428,14 @@ cudaError_t launch_eikonal_fmm(const EikJob* d_jobs, int njobs, cudaStream_t st)
     const char* env = getenv("KIWI_EIKONAL_HEAP");   // tests and measurements: 980 or 2040
     const int forced = env ? atoi(env) : 0;
     const bool small = forced ? forced < EIK_HCAP_LARGE : njobs > eikonal_wave_jobs(0);
+    const char* penv = getenv("KIWI_EIKONAL_PREFETCH");   // heap entries whose stencils are prefetched after a pop (0..3)
+    const int prefetch = penv ? atoi(penv) : (njobs > 2 * 148 ? 3 : 0);
     if (small) {
         cudaFuncSetAttribute(k_eikonal_fmm<EIK_HCAP_SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        k_eikonal_fmm<EIK_HCAP_SMALL><<<njobs, 32, 0, st>>>(d_jobs, njobs);
+        k_eikonal_fmm<EIK_HCAP_SMALL><<<njobs, 32, 0, st>>>(d_jobs, njobs, prefetch);
     } else {
         cudaFuncSetAttribute(k_eikonal_fmm<EIK_HCAP_LARGE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        k_eikonal_fmm<EIK_HCAP_LARGE><<<njobs, 32, 0, st>>>(d_jobs, njobs);
+        k_eikonal_fmm<EIK_HCAP_LARGE><<<njobs, 32, 0, st>>>(d_jobs, njobs, prefetch);
     }
     return cudaGetLastError();
 }
