@@ -42,7 +42,7 @@ WORKLOADS = {
     # amplitude-spectrum L1 misfit (shared-memory FFT kernel); bord radius 5-12 km so that every centroid stays inside bench-L.
     # 4096 candidates per step (round 1: 32): the fast-marching solves are sequential per candidate and differ 6-fold in size; the
     # device solves them one warp each, 26 to an SM (3848 at a time), while the host threads solve the largest grids: the wave lasts
-    # as long as its largest grid, so the rate grows with the batch (137 evals/s at 32, 490 at 1024, 980 at 4096)
+    # as long as its largest grid, so the rate grows with the batch (137 evals/s at 32, 490 at 1024, 1040 at 4096)
     "c4": dict(db="bench-L", nx=2000, nz=150, dx=100.0, dz=200.0, nrcv=200, effective_dt=0.5, dmin=45e3, dmax=150e3,
                norm="ampspec_l1norm", batch=4096, cpu_sample=1, source="eikonal",
                taper=([2.0, 6.0, 70.0, 80.0], [0, 1, 1, 0]), filter=([0.01, 0.02, 0.1, 0.2], [0, 1, 1, 0])),

@@ -145,7 +145,7 @@ struct HostReceiver {   // t_receiver, receiver.f90:58-99 (host mirror)
 struct kiwi_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [6], [7]: around the fast-marching wave
     // database (set_database)
     bool db_set = false;
     GfdbDev db{};
@@ -187,7 +187,12 @@ struct kiwi_ctx {
     // grid, 2.4 s); sharing gives the device the small grids while the host threads work through the large ones.
     int eikonal_device_min = getenv("KIWI_EIKONAL_DEVICE_MIN") ? atoi(getenv("KIWI_EIKONAL_DEVICE_MIN")) : -1;
     int eikonal_last_device_solves = 0;      // solves of the last batch that ran on the device
-    double eikonal_dev_node_small = [] { const char* e = getenv("KIWI_EIKONAL_DEV_NODE_SMALL"); return e ? atof(e) : 3.2e-6; }();   // s per node and solve at 26 solves per SM
+    // cost model of the shared fast-marching solves, seconds per fine node: a device solve at up to 13 / at 26 solves per SM (the wave
+    // lasts as long as its largest grid), a host core.  Start values measured on a B200 with 16 host cores
+    // (profiles/r02_eikonal_device.txt); every shared batch corrects them with what it took (prep_eikonal_batch_device)
+    double eik_dev_node[2] = {2.4e-6, [] { const char* e = getenv("KIWI_EIKONAL_DEV_NODE_SMALL"); return e ? atof(e) : 3.2e-6; }()};
+    double eik_host_node = 1.05e-7;
+    bool eik_adapt = [] { const char* e = getenv("KIWI_EIKONAL_ADAPT"); return !e || atoi(e) != 0; }();
     // kiwi_set_accumulation: synthesis in the reference's order of operations (synth_exact.cu); KIWI_ACCUMULATION=reference makes it the default,
     // for drivers that talk to the command front-end and are not to be touched
     bool accum_reference = getenv("KIWI_ACCUMULATION") && std::string(getenv("KIWI_ACCUMULATION")) == "reference";
@@ -413,7 +418,7 @@ int prep_eikonal_batch_device(kiwi_ctx* c, int sourcetype, int n, int nparams, c
         // (profiles/r02_eikonal_device.txt): a warp 2.1-2.5 us per node, a host core 0.1 us per node for the solve alone
         int ndev = std::min(nr, wave_jobs);
         if (share) {
-            const double dev_node_large = 2.4e-6, dev_node_small = c->eikonal_dev_node_small, host_node = 1.05e-7;
+            const double dev_node_large = c->eik_dev_node[0], dev_node_small = c->eik_dev_node[1], host_node = c->eik_host_node;
             double all_host = 0.;
             for (int i : order) all_host += host_node * nodes_of(i);
             double best = all_host / ncores, dev_host = 0.;
@@ -502,7 +507,9 @@ int prep_eikonal_batch_device(kiwi_ctx* c, int sourcetype, int n, int nparams, c
         if (ndev > 0) CU_OK(cudaMemcpyAsync(c->d_eik_jobs.p, jobs.data(), sizeof(EikJob) * ndev, cudaMemcpyHostToDevice, c->stream));
         CU_OK(cudaStreamSynchronize(c->stream));   // (geoms and jobs are stack-lifetime staging vectors)
         if (ndev > 0) {
+            cudaEventRecord(c->ev[6], c->stream);
             e = launch_eikonal_fmm(c->d_eik_jobs.as<EikJob>(), ndev, c->stream);
+            cudaEventRecord(c->ev[7], c->stream);
             if (e != cudaSuccess) return kiwi_set_error("CUDA error launching the fast-marching solver: %s", cudaGetErrorString(e));
             e = launch_eik_down(c->d_eik_geoms.as<EikGeom>(), ndev, max_cells, c->d_eik_s.as<float>(), c->d_eik_t.as<float>(), c->d_eik_coarse.as<float>(), c->stream);
             if (e != cudaSuccess) return kiwi_set_error("CUDA error launching the down-sampling kernel: %s", cudaGetErrorString(e));
@@ -510,6 +517,7 @@ int prep_eikonal_batch_device(kiwi_ctx* c, int sourcetype, int n, int nparams, c
         }
         c->launches[0] += 1;
         // ---- solves of the host, while the wave runs: speeds and times in page-locked memory ----------------------------------------------
+        const auto th0 = std::chrono::steady_clock::now();
         parallel_over((size_t)(nr - ndev), [&](size_t k) {
             const int j = ndev + (int)k, i = cand[j];
             if (bad[i]) return;
@@ -519,6 +527,7 @@ int prep_eikonal_batch_device(kiwi_ctx* c, int sourcetype, int n, int nparams, c
             for (size_t q = 0; q < nn; q++) if (sp[q] == 0.f) sp[q] = w.invalid_speed;        // source_eikonal.f90:497-507
             kh::eikonal_solver_fmm(sp, w.fnx, w.fny, w.first, w.delta, w.initialpoint, h_times + o);
         });
+        const double host_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - th0).count();
         if (nr > ndev) {
             CU_OK(cudaMemcpyAsync(c->d_eik_t.as<float>() + dev_nodes, h_times, host_nodes * 4, cudaMemcpyHostToDevice, c->stream));
             e = launch_eik_down(c->d_eik_geoms.as<EikGeom>() + ndev, nr - ndev, max_cells, c->d_eik_s.as<float>(), c->d_eik_t.as<float>(), c->d_eik_coarse.as<float>(),
@@ -530,6 +539,23 @@ int prep_eikonal_batch_device(kiwi_ctx* c, int sourcetype, int n, int nparams, c
         CU_OK(cudaMemcpyAsync(coarse.data(), c->d_eik_coarse.p, sizeof(float) * coff, cudaMemcpyDeviceToHost, c->stream));
         CU_OK(cudaStreamSynchronize(c->stream));
         CU_OK(cudaGetLastError());
+        if (share && c->eik_adapt && ndev > 0) {
+            // what this round took corrects the cost model of the next one (a grid search sends batch after batch of the same kind):
+            // the wave's length over its largest grid, the host threads' time over their nodes
+            float wave_ms = 0.f;
+            if (cudaEventElapsedTime(&wave_ms, c->ev[6], c->ev[7]) == cudaSuccess && wave_ms > 1.f) {
+                const double dn = wave_ms * 1e-3 / (double)nodes_of(cand[0]);
+                double& m = c->eik_dev_node[ndev > wave_large ? 1 : 0];
+                m = std::min(1e-5, std::max(1e-6, 0.5 * (m + dn)));
+            }
+            if (nr - ndev >= ncores && host_s > 1e-3) {
+                const double hn = host_s * ncores / (double)host_nodes;
+                c->eik_host_node = std::min(1e-6, std::max(5e-8, 0.5 * (c->eik_host_node + hn)));
+            }
+            if (getenv("KIWI_TRACE")) fprintf(stderr, "[kiwi trace] fast-marching round: %d solves on the device (wave %.1f ms, largest grid %zu nodes), %d on %d host threads (%.1f ms); "
+                                              "model now %.2f / %.2f us per node on the device, %.0f ns on a host core\n", ndev, wave_ms, nodes_of(cand[0]), nr - ndev, ncores,
+                                              host_s * 1e3, c->eik_dev_node[0] * 1e6, c->eik_dev_node[1] * 1e6, c->eik_host_node * 1e9);
+        }
         // ---- sub-fault tables ---------------------------------------------------------------------------------------------------------------
         parallel_over((size_t)nr, [&](size_t j) {
             const int i = cand[j];
