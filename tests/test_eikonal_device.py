@@ -100,3 +100,9 @@ def test_batch_of_eikonal_sources_solved_on_the_device_equals_the_host_path(heap
     assert np.array_equal(sh, sd) and sh[7] != 0 and (sh != 0).sum() == 1
     ok = sh == 0
     assert np.array_equal(mh[ok].view(np.uint32), md[ok].view(np.uint32))
+    # the default: solves shared between the device and the host threads by a cost model that every batch corrects; whatever the
+    # split, the results are the host path's
+    g.set_eikonal_device(-1)
+    for _ in range(3):
+        ms_, ss_ = g.eval_sources("eikonal", p)
+        assert np.array_equal(ss_, sh) and np.array_equal(mh[ok].view(np.uint32), ms_[ok].view(np.uint32))
