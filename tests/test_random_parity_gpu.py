@@ -147,7 +147,19 @@ def test_random_case(seed):
     tolw = tolerance(mw, 1.0)
     assert np.all(np.abs(mg[ok] - mw[ok]) <= tolw[ok]), (cfg, stype, float(np.abs((mg[ok] - mw[ok]) / tolw[ok]).max()))
     lim = np.maximum(tol, 2.0 * np.abs(mo - mw))
-    assert np.all(np.abs(mg[ok] - mo[ok]) <= lim[ok]), (cfg, stype, float(np.abs((mg[ok] - mo[ok]) / lim[ok]).max()))
+    if np.all(np.abs(mg[ok] - mo[ok]) <= lim[ok]):
+        return
+    # Still beyond (8 of 1500 seeds, by up to 3.7 x, profiles/r02_random_sweep.md): components that are small sums of large terms --
+    # a transverse or near-nodal trace 20-50 x smaller than the tensor terms it is made of -- carry the rounding noise of those terms,
+    # ~3e-6 of their own peak in either implementation, and one draw of that noise (the fp32 restatement's) is no bound for another
+    # (the batched order of operations).  There the bar is the one seismogram parity implies, 1e-5 of the norm factor, for the batched
+    # path, and the tight bar for the reference's order of operations (kiwi_set_accumulation), whose seismograms are the restatement's.
+    tol1 = tolerance(mo, 1.0)
+    assert np.all(np.abs(mg[ok] - mo[ok]) <= tol1[ok]), (cfg, stype, float(np.abs((mg[ok] - mo[ok]) / tol1[ok]).max()))
+    g.set_accumulation(True)
+    mr, sr = g.eval_sources(stype, cands)
+    assert np.array_equal(sr > 0, so > 0)
+    assert np.all(np.abs(mr[ok] - mo[ok]) <= tol[ok]), ("reference order", cfg, stype, float(np.abs((mr[ok] - mo[ok]) / tol[ok]).max()))
 
 
 def random_grid_case(seed):
