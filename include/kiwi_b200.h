@@ -183,10 +183,11 @@ int kiwi_set_mt_grid(kiwi_ctx* ctx, int enabled);
 int kiwi_set_accumulation(kiwi_ctx* ctx, int reference_order);
 
 /* Eikonal / mt_eikonal sources: the fast-marching solve of the rupture front (eikonal.f90:29-199), sequential by construction and 70 % of the
- * discretiser's time, runs per candidate on a host thread or on the device (one warp per candidate, bit-identical results, up to 1924
+ * discretiser's time, runs per candidate on a host thread or on the device (one warp per candidate, bit-identical results, up to 3848
  * solves side by side, each ~25 x slower than on a host core; a wave lasts as long as its largest grid).  min_batch < 0 (default): the
  * engine shares the solves of a batch between host threads and device where that is faster (the device takes the small grids while the
- * host threads work through the large ones); 0: host threads only; k > 0: all solves of batches of k candidates or more on the device. */
+ * host threads work through the large ones; the split follows a cost model that every batch corrects with what it took, the results do
+ * not depend on it); 0: host threads only; k > 0: all solves of batches of k candidates or more on the device. */
 int kiwi_set_eikonal_device(kiwi_ctx* ctx, int min_batch);
 
 /* Candidates of one kiwi_eval_sources batch that differ only in the scalar moment (bilateral, eikonal,
