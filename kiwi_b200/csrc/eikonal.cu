@@ -10,8 +10,9 @@
 // the reference's order (left, right, down, up).  All arithmetic is IEEE fp32 in the reference's operation order
 // (__f*_rn intrinsics: no FMA contraction), so the result equals the host solver's (source_eikonal_host.cpp) bit for bit.
 //
-// A warp walks ~1.5e3 dependent cycles per node where a host core needs ~150 ns, so one solve is slower than on the host;
-// the device wins on batches of a few hundred candidates and more (grid searches), which is when the engine uses it.
+// A warp walks ~4e3 dependent cycles (2.1 us, ~470 instructions) per node where a host core needs ~100 ns, so one solve is ~20 x
+// slower than on the host; the device wins by running thousands of them side by side (0.73-0.85 ns per node over 3848 solves,
+// profiles/r02_eikonal_device.txt), i.e. on the batches of a grid search, which is when the engine uses it.
 #include "kernels.cuh"
 #include <cfloat>
 #include <cstdio>
